@@ -1,0 +1,881 @@
+/* TEST INFRASTRUCTURE (oracle/) -- see emc_oracle.h for the rules.
+ *
+ * Plain-C restatement of the reference algorithm for the per-time-step
+ * particle loop.  Operation ORDER follows the reference expression by
+ * expression (left-to-right as g++ evaluates them, no FMA contraction:
+ * compile with -ffp-contract=off) so that results are bit-identical to the
+ * reference built with the same compiler flags.
+ */
+#include "emc_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* reference: include/emcConstants.hpp:9-27 (literal, non-CODATA values) */
+static const double C_PI = 3.14159265358979323846;
+static const double C_Q = 1.60219e-19;
+static const double C_KB = 1.38066e-23;
+static const double C_HBAR = 1.05459e-34;
+static const double C_EPS0 = 8.85419e-12;
+
+/* ------------------------------------------------------------------ RNG */
+/* std::mt19937_64 (reference: include/emcUtil.hpp:15).  Published MT19937-64
+ * recurrence (Matsumoto & Nishimura); pinned by the 10000th output of the
+ * default seed 5489 == 9981545732273789042 (C++ standard [rand.predef]). */
+#define MT_N 312
+#define MT_M 156
+void orc_mt_seed(uint64_t *st, uint64_t seed) {
+  st[0] = seed;
+  for (int i = 1; i < MT_N; i++)
+    st[i] = 6364136223846793005ULL * (st[i - 1] ^ (st[i - 1] >> 62)) + (uint64_t)i;
+  st[MT_N] = MT_N;
+}
+uint64_t orc_mt_next(uint64_t *st) {
+  if (st[MT_N] >= MT_N) {
+    const uint64_t UM = 0xFFFFFFFF80000000ULL, LM = 0x7FFFFFFFULL;
+    for (int i = 0; i < MT_N; i++) {
+      uint64_t x = (st[i] & UM) | (st[(i + 1) % MT_N] & LM);
+      uint64_t xa = x >> 1;
+      if (x & 1ULL)
+        xa ^= 0xB5026F5AA96619E9ULL;
+      st[i] = st[(i + MT_M) % MT_N] ^ xa;
+    }
+    st[MT_N] = 0;
+  }
+  uint64_t y = st[st[MT_N]++];
+  y ^= (y >> 29) & 0x5555555555555555ULL;
+  y ^= (y << 17) & 0x71D67FFFEDA60000ULL;
+  y ^= (y << 37) & 0xFFF7EEE000000000ULL;
+  y ^= (y >> 43);
+  return y;
+}
+void orc_mt_fill(uint64_t seed, uint64_t *out, int64_t n) {
+  uint64_t st[MT_N + 1];
+  orc_mt_seed(st, seed);
+  for (int64_t i = 0; i < n; i++)
+    out[i] = orc_mt_next(st);
+}
+
+/* Philox4x32-10 (Salmon et al., SC'11), the counter-based generator of the
+ * B200 path.  Not part of the reference; restated here so that CPU and GPU
+ * consume identical streams in PHILOX mode. */
+void orc_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+  uint32_t k0 = key[0], k1 = key[1];
+  for (int r = 0; r < 10; r++) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    uint32_t n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+/* draw `idx` of (particle, step): counter = (particle lo, particle hi, step,
+ * idx/2); word pair idx%2 of the 128-bit block, low word first. */
+uint64_t orc_philox_draw(uint64_t seed, uint64_t particle, uint64_t step, uint64_t idx) {
+  uint32_t ctr[4] = {(uint32_t)particle, (uint32_t)(particle >> 32),
+                     (uint32_t)step, (uint32_t)(idx >> 1)};
+  uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  uint32_t o[4];
+  orc_philox4x32(ctr, key, o);
+  return (idx & 1) ? ((uint64_t)o[3] << 32 | o[2]) : ((uint64_t)o[1] << 32 | o[0]);
+}
+
+/* libstdc++ std::uniform_real_distribution<double>(a,b) on a 64-bit engine:
+ * one raw draw, generate_canonical = double(x) / 2^64, clamped below 1
+ * (SURVEY App. A.2 [probe]); then u*(b-a)+a. */
+double orc_uniform(uint64_t raw, double a, double b) {
+  double u = (double)raw / 18446744073709551616.0;
+  if (u >= 1.0)
+    u = nextafter(1.0, 0.0);
+  return u * (b - a) + a;
+}
+
+typedef struct {
+  const orc_rng_cfg_t *cfg;
+  int64_t particle; /* local index */
+  uint64_t step;
+  uint64_t k; /* draws consumed by this particle in this step (PHILOX) */
+  int32_t *recPid;
+  int64_t recCap, recCount;
+} rng_t;
+
+static uint64_t rng_raw(rng_t *r) {
+  uint64_t x;
+  switch (r->cfg->mode) {
+  case ORC_RNG_MT_GLOBAL:
+    x = orc_mt_next(r->cfg->mtState);
+    break;
+  case ORC_RNG_STREAMS: {
+    int64_t p = r->particle;
+    x = r->cfg->draws[r->cfg->offsets[p] + r->cfg->cursor[p]++];
+    break;
+  }
+  default:
+    x = orc_philox_draw(r->cfg->philoxSeed,
+                        (uint64_t)(r->cfg->particleIdBase + r->particle), r->step, r->k++);
+  }
+  if (r->recPid && r->recCount < r->recCap)
+    r->recPid[r->recCount] = (int32_t)r->particle;
+  r->recCount++;
+  return x;
+}
+static double rng_u01(rng_t *r) { return orc_uniform(rng_raw(r), 0., 1.); }
+static double rng_ulog(rng_t *r) { return orc_uniform(rng_raw(r), 1e-6, 1.); }
+
+/* ---------------------------------------------------------- valley math */
+static double sq3(const double k[3]) {
+  /* emcUtil.hpp:26-31: res = 0; res += e*e in order */
+  double res = 0;
+  res += k[0] * k[0];
+  res += k[1] * k[1];
+  res += k[2] * k[2];
+  return res;
+}
+static int is_aniso(const orc_valley_t *v) { return v->kind >= 2; }
+static int is_nonparabolic(const orc_valley_t *v) { return v->kind & 1; }
+
+/* emcNonParabolicAnistropValley.hpp:122, emcNonParabolicIsotropValley.hpp:99,
+ * emcParabolic*Valley.hpp (gamma = E) */
+double orc_gamma(const orc_valley_t *v, double e) {
+  return is_nonparabolic(v) ? e * (1 + v->alpha * e) : e;
+}
+/* :90-92 / :60-62 ; parabolic: constant */
+double orc_eff_mass_cond(const orc_valley_t *v, double e) {
+  return is_nonparabolic(v) ? v->mCond * (1 + 2 * e * v->alpha) : v->mCond;
+}
+/* emcNonParabolicAnistropValley.hpp:109-113, emcNonParabolicIsotropValley.hpp:78-82,
+ * emcParabolicIsotropValley.hpp:62-65, emcParabolicAnisotropValley.hpp:100-103 */
+double orc_energy(const orc_valley_t *v, const double k[3]) {
+  if (is_nonparabolic(v)) {
+    double gamma = C_HBAR * C_HBAR * sq3(k) / (v->mCond * C_Q);
+    return gamma / (1 + sqrt(1 + 2 * v->alpha * gamma));
+  }
+  return C_HBAR * C_HBAR * sq3(k) / (2 * v->mCond * C_Q);
+}
+/* aniso non-parabolic :103-106 multiplies (2 m gamma q); the three others
+ * multiply (2 m q gamma|E) */
+double orc_norm_wave_vec(const orc_valley_t *v, double e) {
+  if (v->kind == ORC_VALLEY_NONPARABOLIC_ANISO)
+    return sqrt(2 * v->mCond * orc_gamma(v, e) * C_Q) / C_HBAR;
+  return sqrt(2 * v->mCond * C_Q * orc_gamma(v, e)) / C_HBAR;
+}
+/* :140-153 */
+void orc_to_ellipse(const orc_valley_t *v, int s, const double in[3], double out[3]) {
+  if (!is_aniso(v)) {
+    out[0] = in[0]; out[1] = in[1]; out[2] = in[2];
+    return;
+  }
+  const double *r = v->rot[s];
+  double a = in[0], b = in[1], c = in[2];
+  out[0] = a * r[0] + b * r[1] + c * r[2];
+  out[1] = a * r[3] + b * r[4] + c * r[5];
+  out[2] = a * r[6] + b * r[7] + c * r[8];
+}
+/* :157-170 */
+void orc_to_device(const orc_valley_t *v, int s, const double in[3], double out[3]) {
+  if (!is_aniso(v)) {
+    out[0] = in[0]; out[1] = in[1]; out[2] = in[2];
+    return;
+  }
+  const double *r = v->rot[s];
+  double a = in[0], b = in[1], c = in[2];
+  out[0] = a * r[0] + b * r[3] + c * r[6];
+  out[1] = a * r[1] + b * r[4] + c * r[7];
+  out[2] = a * r[2] + b * r[5] + c * r[8];
+}
+/* getVelocity: aniso NP :126-136, iso NP :85-90, iso P :74-77, aniso P :106-114 */
+void orc_velocity(const orc_valley_t *v, const double k[3], double e, int s, double out[3]) {
+  switch (v->kind) {
+  case ORC_VALLEY_NONPARABOLIC_ANISO: {
+    double ke[3], ve[3];
+    orc_to_ellipse(v, s, k, ke);
+    double npf = sqrt(1 + 4 * v->alpha * orc_gamma(v, e));
+    for (int i = 0; i < 3; i++)
+      ve[i] = C_HBAR * v->vogt[i] * ke[i] / (v->mCond * npf);
+    orc_to_device(v, s, ve, out);
+    break;
+  }
+  case ORC_VALLEY_PARABOLIC_ANISO: {
+    double ke[3], ve[3];
+    orc_to_ellipse(v, s, k, ke);
+    for (int i = 0; i < 3; i++)
+      ve[i] = C_HBAR * v->vogt[i] * ke[i] / v->mCond;
+    orc_to_device(v, s, ve, out);
+    break;
+  }
+  case ORC_VALLEY_NONPARABOLIC_ISO: {
+    double f = C_HBAR / (v->mCond * sqrt(1 + 4 * v->alpha * orc_gamma(v, e)));
+    for (int i = 0; i < 3; i++)
+      out[i] = k[i] * f;
+    break;
+  }
+  default: {
+    double f = C_HBAR / v->mCond;
+    for (int i = 0; i < 3; i++)
+      out[i] = k[i] * f;
+  }
+  }
+}
+
+/* include/emcParticleDrift.hpp:12-36 */
+void orc_drift(const orc_valley_t *v, double dt, double k[3], double *energy, int s,
+               double pos[3], int dim, const double force[3]) {
+  double kOld[3], kNew[3], fE[3], dP[3], dPd[3];
+  orc_to_ellipse(v, s, k, kOld);
+  memcpy(kNew, kOld, sizeof kNew);
+  orc_to_ellipse(v, s, force, fE);
+  for (int i = 0; i < 3; i++)
+    kNew[i] += fE[i] * dt * v->vogt[i] / C_HBAR;
+  orc_to_device(v, s, kNew, k);
+  *energy = orc_energy(v, k);
+  for (int i = 0; i < 3; i++) {
+    double avgK = (kNew[i] + kOld[i]) / 2;
+    dP[i] = C_HBAR * v->vogt[i] * avgK * dt / orc_eff_mass_cond(v, *energy);
+  }
+  orc_to_device(v, s, dP, dPd);
+  for (int i = 0; i < dim; i++)
+    pos[i] = pos[i] + dPd[i];
+}
+
+/* include/emcUtil.hpp:131-139 */
+void orc_random_direction(double norm, double rand1, double rand2, double out[3]) {
+  double phi = 2 * C_PI * rand1;
+  double cosTheta = 1 - 2 * rand2;
+  out[0] = norm * sqrt(1 - cosTheta * cosTheta) * cos(phi);
+  out[1] = norm * sqrt(1 - cosTheta * cosTheta) * sin(phi);
+  out[2] = norm * cosTheta;
+}
+/* include/emcUtil.hpp:143-175 */
+void orc_random_direction_wrt_k(const double k[3], double cosTheta, double rnd, double out[3]) {
+  double kxy = sqrt(k[0] * k[0] + k[1] * k[1]);
+  double normK = sqrt(kxy * kxy + k[2] * k[2]);
+  if (normK == 0.) {
+    out[0] = out[1] = out[2] = 0.;
+    return;
+  }
+  double ct0 = k[2] / normK;
+  double st0 = kxy / normK;
+  double cfi0 = (kxy > 0.) ? k[0] / kxy : 1.;
+  double sfi0 = (kxy > 0.) ? k[1] / kxy : 0.;
+  double st = sqrt(1.0 - cosTheta * cosTheta);
+  double phi = 2.0 * C_PI * rnd;
+  double kxp = normK * st * cos(phi);
+  double kyp = normK * st * sin(phi);
+  double kzp = normK * cosTheta;
+  out[0] = kxp * cfi0 * ct0 - kyp * sfi0 + kzp * cfi0 * st0;
+  out[1] = kxp * sfi0 * ct0 + kyp * cfi0 + kzp * sfi0 * st0;
+  out[2] = -kxp * st0 + kzp * ct0;
+}
+
+/* ------------------------------------------------------------------ model */
+enum { MK_ACOUSTIC = 1, MK_ZERO = 2, MK_FIRST = 3, MK_COULOMB = 4 };
+
+typedef struct {
+  int kind, valley, finalValley, region, emission, nFinal, nInitSub;
+  double scatterConst, scatterConst2, phononEnergy, regionDoping;
+  int32_t finalSub[ORC_MAX_SUB][ORC_MAX_FINAL];
+} mech_t;
+
+typedef struct {
+  int valley, region, nMech;
+  int mechIdx[64];
+  double *cum; /* [nMech][nLevels] */
+  double tau;
+} tableset_t;
+
+struct orc_model {
+  int nLevels;
+  double maxEnergy, dE, temperature, rho, vSound;
+  int nValleys;
+  orc_valley_t valleys[16];
+  int nMech;
+  mech_t mech[256];
+  int nSets;
+  tableset_t sets[64];
+};
+
+orc_model_t *orc_model_create(int nLevels, double maxEnergy, double temperature,
+                              double rho, double vSound) {
+  orc_model_t *m = (orc_model_t *)calloc(1, sizeof *m);
+  m->nLevels = nLevels;
+  m->maxEnergy = maxEnergy;
+  m->dE = maxEnergy / nLevels; /* emcScatterHandler.hpp:76 */
+  m->temperature = temperature;
+  m->rho = rho;
+  m->vSound = vSound;
+  return m;
+}
+void orc_model_destroy(orc_model_t *m) {
+  if (!m)
+    return;
+  for (int i = 0; i < m->nSets; i++)
+    free(m->sets[i].cum);
+  free(m);
+}
+
+/* valley constructors: emcNonParabolicAnistropValley.hpp:54-80,185-204 etc. */
+int orc_add_valley(orc_model_t *m, int kind, const double relMass[3], double particleMass,
+                   int deg, double alpha, double eBottom, const double *dirs) {
+  if (m->nValleys >= 16 || deg > ORC_MAX_SUB)
+    return -1;
+  orc_valley_t *v = &m->valleys[m->nValleys];
+  memset(v, 0, sizeof *v);
+  v->kind = kind;
+  v->deg = deg;
+  v->alpha = (kind & 1) ? alpha : 0.;
+  v->eBottom = eBottom;
+  for (int s = 0; s < ORC_MAX_SUB; s++)
+    v->rot[s][0] = v->rot[s][4] = v->rot[s][8] = 1.;
+  if (kind >= 2) {
+    double prod = 1.;
+    for (int i = 0; i < 3; i++)
+      prod = prod * relMass[i];
+    v->mDos = pow(prod, 1. / 3.) * particleMass;
+    double acc = 0.;
+    for (int i = 0; i < 3; i++)
+      acc += 1. / relMass[i];
+    v->mCond = 3. * particleMass / acc;
+    for (int i = 0; i < 3; i++)
+      v->vogt[i] = sqrt(orc_eff_mass_cond(v, 0.) / (relMass[i] * particleMass));
+    if (dirs) {
+      for (int s = 0; s < deg; s++)
+        for (int r = 0; r < 3; r++) {
+          const double *d = dirs + (s * 3 + r) * 3;
+          double nrm = sqrt(sq3(d)); /* emcUtil.hpp:34-47 */
+          for (int c = 0; c < 3; c++)
+            v->rot[s][r * 3 + c] = (nrm == 0.) ? d[c] : d[c] / nrm;
+        }
+    }
+  } else {
+    v->mCond = v->mDos = relMass[0] * particleMass;
+    v->vogt[0] = v->vogt[1] = v->vogt[2] = 1.;
+  }
+  return m->nValleys++;
+}
+
+static double dos_mass_at_zero(const orc_valley_t *v) {
+  /* getEffMassDOS(0): non-parabolic = m*pow(1+2*alpha*0, 3.) */
+  return is_nonparabolic(v) ? v->mDos * pow(1 + 2 * v->alpha * 0., 3.) : v->mDos;
+}
+
+/* emcAcousticScatterMechanism.hpp:47-56 */
+int orc_add_acoustic(orc_model_t *m, int valley, int region, double sigma) {
+  mech_t *x = &m->mech[m->nMech];
+  memset(x, 0, sizeof *x);
+  x->kind = MK_ACOUSTIC;
+  x->valley = x->finalValley = valley;
+  x->region = region;
+  double cL = m->rho * pow(m->vSound, 2);
+  x->scatterConst = sqrt(2.0 * C_Q) * pow(sigma * C_Q, 2) * C_KB * m->temperature /
+                    (C_PI * cL * pow(C_HBAR, 4));
+  return m->nMech++;
+}
+
+/* emcZeroOrderInterValleyScatterMechanism.hpp:12-21, emcFirstOrder...:12-20 */
+int orc_add_intervalley(orc_model_t *m, int order, int emission, int valley, int finalValley,
+                        int region, double defPot, double phE, int nInitSub, int nFinal,
+                        const int32_t *finalSub) {
+  if (nFinal > ORC_MAX_FINAL || nInitSub > ORC_MAX_SUB)
+    return -1;
+  mech_t *x = &m->mech[m->nMech];
+  memset(x, 0, sizeof *x);
+  x->kind = order == 0 ? MK_ZERO : MK_FIRST;
+  x->valley = valley;
+  x->finalValley = finalValley;
+  x->region = region;
+  x->emission = emission;
+  x->nFinal = nFinal;
+  x->nInitSub = nInitSub;
+  x->phononEnergy = phE;
+  for (int i = 0; i < nInitSub; i++)
+    for (int j = 0; j < nFinal; j++)
+      x->finalSub[i][j] = finalSub[i * nFinal + j];
+  double result;
+  if (order == 0)
+    result = nFinal * sqrt(C_Q) * pow(defPot / C_HBAR, 2) * C_Q /
+             (C_PI * m->rho * phE * sqrt(2));
+  else
+    result = nFinal * sqrt(2) * pow(C_Q, 5. / 2.) * pow(defPot, 2) /
+             (C_PI * m->rho * pow(C_HBAR, 4) * phE);
+  double nrPh = 1. / (exp(C_Q * phE / (C_KB * m->temperature)) - 1.);
+  x->scatterConst = emission ? result * (nrPh + 1) : result * nrPh;
+  return m->nMech++;
+}
+
+/* emcCoulombScatterMechanism.hpp:23-32 */
+int orc_add_coulomb(orc_model_t *m, int valley, int region, double epsR, double regionDoping) {
+  mech_t *x = &m->mech[m->nMech];
+  memset(x, 0, sizeof *x);
+  x->kind = MK_COULOMB;
+  x->valley = x->finalValley = valley;
+  x->region = region;
+  double epsMat = C_EPS0 * epsR;
+  double Vt = C_KB / C_Q * m->temperature; /* emcDevice.hpp:87 */
+  x->scatterConst = sqrt(2 * C_Q) * pow(C_KB * m->temperature, 2) / (C_PI * pow(C_HBAR, 4));
+  x->scatterConst2 = 8 * epsMat * Vt / (C_HBAR * C_HBAR);
+  x->regionDoping = fabs(regionDoping);
+  return m->nMech++;
+}
+
+static double delta_valley(const orc_model_t *m, const mech_t *x) {
+  return m->valleys[x->finalValley].eBottom - m->valleys[x->valley].eBottom;
+}
+
+/* getScatterRate of each built-in mechanism */
+double orc_raw_rate(const orc_model_t *m, int g, double energy) {
+  const mech_t *x = &m->mech[g];
+  const orc_valley_t *vi = &m->valleys[x->valley];
+  const orc_valley_t *vf = &m->valleys[x->finalValley];
+  switch (x->kind) {
+  case MK_ACOUSTIC: { /* emcAcousticScatterMechanism.hpp:60-67 */
+    double md = dos_mass_at_zero(vi);
+    double alpha = vi->alpha;
+    double gamma = orc_gamma(vi, energy);
+    return x->scatterConst * pow(md, 3. / 2.) * sqrt(gamma) * (2 * alpha * energy + 1.0);
+  }
+  case MK_ZERO: { /* emcZeroOrder...:103-117, :246-260 */
+    double dV = delta_valley(m, x);
+    double ef = x->emission ? energy - x->phononEnergy - dV : energy + x->phononEnergy - dV;
+    if (ef > 0) {
+      double md = dos_mass_at_zero(vf);
+      double alpha = vf->alpha;
+      double gamma = orc_gamma(vf, ef);
+      return x->scatterConst * pow(md, 3. / 2.) * sqrt(gamma) * (2 * alpha * ef + 1.0);
+    }
+    return 0;
+  }
+  case MK_FIRST: { /* emcFirstOrder...:102-119, :250-267 */
+    double dV = delta_valley(m, x);
+    double ef = x->emission ? energy - x->phononEnergy - dV : energy + x->phononEnergy - dV;
+    if (ef > 0) {
+      double md = dos_mass_at_zero(vf);
+      double alpha = vf->alpha;
+      double gamma = orc_gamma(vi, energy);
+      double gammaF = orc_gamma(vf, ef);
+      return x->scatterConst * pow(md, 5. / 2.) * sqrt(gammaF) * (2 * alpha * ef + 1.0) *
+             (gamma + gammaF);
+    }
+    return 0;
+  }
+  case MK_COULOMB: { /* emcCoulombScatterMechanism.hpp:36-46 */
+    double md = dos_mass_at_zero(vi);
+    double mc = orc_eff_mass_cond(vi, 0.);
+    double alpha = vi->alpha;
+    double gamma = orc_gamma(vi, energy);
+    return x->scatterConst * pow(md, 3. / 2.) / x->regionDoping * sqrt(gamma) *
+           (2 * alpha * energy + 1.0) / (1 + (x->scatterConst2 * mc * gamma / x->regionDoping));
+  }
+  }
+  return 0;
+}
+
+/* emcScatterHandler.hpp:220-273: std::map keyed (valley, region) => sets sorted
+ * lexicographically; mechanisms in insertion order inside a set. */
+int orc_build_tables(orc_model_t *m) {
+  for (int i = 0; i < m->nSets; i++)
+    free(m->sets[i].cum);
+  m->nSets = 0;
+  for (int g = 0; g < m->nMech; g++) {
+    int found = -1;
+    for (int i = 0; i < m->nSets; i++)
+      if (m->sets[i].valley == m->mech[g].valley && m->sets[i].region == m->mech[g].region)
+        found = i;
+    if (found < 0) {
+      if (m->nSets >= 64)
+        return -1;
+      found = m->nSets++;
+      m->sets[found].valley = m->mech[g].valley;
+      m->sets[found].region = m->mech[g].region;
+      m->sets[found].nMech = 0;
+      m->sets[found].cum = NULL;
+    }
+    if (m->sets[found].nMech >= 64)
+      return -1;
+    m->sets[found].mechIdx[m->sets[found].nMech++] = g;
+  }
+  /* sort sets by (valley, region) like std::map<tuple> */
+  for (int i = 0; i < m->nSets; i++)
+    for (int j = i + 1; j < m->nSets; j++) {
+      tableset_t *a = &m->sets[i], *b = &m->sets[j];
+      if (b->valley < a->valley || (b->valley == a->valley && b->region < a->region)) {
+        tableset_t t = *a;
+        *a = *b;
+        *b = t;
+      }
+    }
+  const int L = m->nLevels;
+  for (int i = 0; i < m->nSets; i++) {
+    tableset_t *s = &m->sets[i];
+    s->cum = (double *)malloc(sizeof(double) * s->nMech * L);
+    for (int t = 0; t < s->nMech; t++)
+      for (int l = 0; l < L; l++)
+        s->cum[t * L + l] = orc_raw_rate(m, s->mechIdx[t], (l + 1) * m->dE);
+    for (int t = 1; t < s->nMech; t++)
+      for (int l = 0; l < L; l++)
+        s->cum[t * L + l] = s->cum[t * L + l] + s->cum[(t - 1) * L + l];
+    double maxRate = s->cum[(s->nMech - 1) * L];
+    for (int l = 1; l < L; l++)
+      if (s->cum[(s->nMech - 1) * L + l] > maxRate)
+        maxRate = s->cum[(s->nMech - 1) * L + l];
+    for (int t = 0; t < s->nMech; t++)
+      for (int l = 0; l < L; l++)
+        s->cum[t * L + l] /= maxRate;
+    s->tau = 1. / maxRate;
+  }
+  return 0;
+}
+
+int orc_n_valleys(const orc_model_t *m) { return m->nValleys; }
+int orc_get_valley(const orc_model_t *m, int v, orc_valley_t *out) {
+  if (v < 0 || v >= m->nValleys)
+    return -1;
+  *out = m->valleys[v];
+  return 0;
+}
+int orc_n_mechanisms(const orc_model_t *m) { return m->nMech; }
+int orc_n_tablesets(const orc_model_t *m) { return m->nSets; }
+int orc_tableset_info(const orc_model_t *m, int i, int32_t *valley, int32_t *region,
+                      int32_t *nMech, double *tau) {
+  if (i < 0 || i >= m->nSets)
+    return -1;
+  *valley = m->sets[i].valley;
+  *region = m->sets[i].region;
+  *nMech = m->sets[i].nMech;
+  *tau = m->sets[i].tau;
+  return 0;
+}
+static void fill_mech_desc(const orc_model_t *m, int g, orc_mech_t *d) {
+  const mech_t *x = &m->mech[g];
+  memset(d, 0, sizeof *d);
+  d->globalId = g;
+  d->finalValley = x->finalValley;
+  d->nFinal = x->nFinal;
+  memcpy(d->finalSub, x->finalSub, sizeof d->finalSub);
+  switch (x->kind) {
+  case MK_ACOUSTIC:
+    d->sampler = ORC_SAMPLER_ISOTROPIC_ELASTIC;
+    break;
+  case MK_ZERO:
+  case MK_FIRST: {
+    d->sampler = ORC_SAMPLER_INTERVALLEY;
+    /* abs: E += (hw - dV); em: E -= (hw + dV)  (emcZeroOrder...:125, :268).
+     * a - b == a + (-b) exactly, so a signed shift reproduces both. */
+    double dV = delta_valley(m, x);
+    d->p[0] = x->emission ? -(x->phononEnergy + dV) : (x->phononEnergy - dV);
+    break;
+  }
+  case MK_COULOMB: {
+    d->sampler = ORC_SAMPLER_COULOMB;
+    double mc = orc_eff_mass_cond(&m->valleys[x->valley], 0.);
+    d->p[0] = x->regionDoping / (x->scatterConst2 * mc); /* debyeEnergy :55 */
+    break;
+  }
+  }
+}
+int orc_tableset_copy(const orc_model_t *m, int i, double *cum, orc_mech_t *mech) {
+  if (i < 0 || i >= m->nSets)
+    return -1;
+  const tableset_t *s = &m->sets[i];
+  if (cum)
+    memcpy(cum, s->cum, sizeof(double) * s->nMech * m->nLevels);
+  if (mech)
+    for (int t = 0; t < s->nMech; t++)
+      fill_mech_desc(m, s->mechIdx[t], &mech[t]);
+  return 0;
+}
+static int find_set(const orc_model_t *m, int valley, int region) {
+  for (int i = 0; i < m->nSets; i++)
+    if (m->sets[i].valley == valley && m->sets[i].region == region)
+      return i;
+  return -1;
+}
+/* emcScatterHandler.hpp:79-84 */
+double orc_tau(const orc_model_t *m, int valley, int region) {
+  int i = find_set(m, valley, region);
+  return i >= 0 ? m->sets[i].tau : 2e-15;
+}
+double orc_dE(const orc_model_t *m) { return m->dE; }
+
+/* emcScatterHandler.hpp:237-244 (x86-64 g++ behaviour of the size_t cast,
+ * SURVEY App. B.4): -1 -> 0, above range -> n-1 */
+int orc_energy_level(const orc_model_t *m, double energy) {
+  double f = floor(energy / m->dE) - 1;
+  int64_t lvl = (int64_t)f;
+  if (lvl == -1)
+    return 0;
+  if (lvl < 0 || lvl > m->nLevels - 1)
+    return m->nLevels - 1;
+  return (int)lvl;
+}
+/* emcScatterHandler.hpp:148-170; returns table index or -1 (self-scatter) */
+int orc_select(const orc_model_t *m, int si, double energy, double r) {
+  const tableset_t *s = &m->sets[si];
+  const int L = m->nLevels;
+  int lvl = orc_energy_level(m, energy);
+  if (r > s->cum[(s->nMech - 1) * L + lvl])
+    return -1;
+  double lower = 0;
+  for (int t = 0; t < s->nMech; t++) {
+    double upper = s->cum[t * L + lvl];
+    if (r >= lower && r < upper)
+      return t;
+    lower = upper;
+  }
+  return -1;
+}
+
+/* ------------------------------------------------------- final states */
+static void scatter_with(const orc_model_t *m, const orc_mech_t *d, orc_ensemble_t *e,
+                         int64_t p, rng_t *rng) {
+  double k[3] = {e->kx[p], e->ky[p], e->kz[p]}, out[3];
+  switch (d->sampler) {
+  case ORC_SAMPLER_ISOTROPIC_ELASTIC: {
+    /* emcAcousticScatterMechanism.hpp:70-72; g++ evaluates the two dist(rng)
+     * arguments right-to-left: first draw -> rand2 (cos theta) */
+    double nrm = sqrt(sq3(k));
+    double r2 = rng_u01(rng);
+    double r1 = rng_u01(rng);
+    orc_random_direction(nrm, r1, r2, out);
+    break;
+  }
+  case ORC_SAMPLER_INTERVALLEY: {
+    /* emcZeroOrder...:119-129 / :262-272, emcFirstOrder...:121-131 / :269-279 */
+    int subOld = e->sub[p];
+    e->valley[p] = d->finalValley;
+    uint64_t raw = rng_raw(rng);
+    e->sub[p] = d->finalSub[subOld][raw % (uint64_t)d->nFinal];
+    e->energy[p] += d->p[0];
+    double knew = orc_norm_wave_vec(&m->valleys[d->finalValley], e->energy[p]);
+    double r2 = rng_u01(rng);
+    double r1 = rng_u01(rng);
+    orc_random_direction(knew, r1, r2, out);
+    break;
+  }
+  case ORC_SAMPLER_COULOMB: {
+    /* emcCoulombScatterMechanism.hpp:48-59 */
+    const orc_valley_t *v = &m->valleys[e->valley[p]];
+    double gamma = orc_gamma(v, e->energy[p]);
+    double rnd = rng_u01(rng);
+    double debyeEnergy = d->p[0];
+    double cosTheta = 1.0 - rnd * 2.0 / ((1 - rnd) * gamma / debyeEnergy + 1.0);
+    double r = rng_u01(rng);
+    orc_random_direction_wrt_k(k, cosTheta, r, out);
+    break;
+  }
+  default:
+    return;
+  }
+  e->kx[p] = out[0];
+  e->ky[p] = out[1];
+  e->kz[p] = out[2];
+}
+
+static void drift_wrap(const orc_model_t *m, orc_ensemble_t *e, int64_t p, double dt,
+                       const double force[3], const double box[3]) {
+  /* basicBulkParticleHandler.hpp:600-613 */
+  double k[3] = {e->kx[p], e->ky[p], e->kz[p]};
+  double pos[3] = {e->x[p], e->y[p], e->z[p]};
+  orc_drift(&m->valleys[e->valley[p]], dt, k, &e->energy[p], e->sub[p], pos, 3, force);
+  for (int d = 0; d < 3; d++) {
+    if (pos[d] < 0)
+      pos[d] = pos[d] + box[d];
+    else if (pos[d] > box[d])
+      pos[d] = pos[d] - box[d];
+  }
+  e->kx[p] = k[0]; e->ky[p] = k[1]; e->kz[p] = k[2];
+  e->x[p] = pos[0]; e->y[p] = pos[1]; e->z[p] = pos[2];
+}
+
+void orc_bulk_observables(const orc_model_t *m, const orc_ensemble_t *e,
+                          const double fieldDir[3], double *obs) {
+  /* :289-347; fieldDir already normalised (ctor :101) */
+  for (int v = 0; v < m->nValleys * 3; v++)
+    obs[v] = 0.;
+  for (int64_t p = 0; p < e->n; p++) {
+    int v = e->valley[p];
+    double k[3] = {e->kx[p], e->ky[p], e->kz[p]}, vel[3];
+    orc_velocity(&m->valleys[v], k, e->energy[p], e->sub[p], vel);
+    obs[v * 3 + 0] += e->energy[p];
+    obs[v * 3 + 1] += vel[0] * fieldDir[0] + vel[1] * fieldDir[1] + vel[2] * fieldDir[2];
+    obs[v * 3 + 2] += 1.;
+  }
+}
+
+int orc_bulk_steps(const orc_model_t *m, orc_ensemble_t *e, const double box[3],
+                   const double fieldDirIn[3], double fieldStrength, double charge,
+                   double dt, int nSteps,
+                   int64_t firstStep, const orc_rng_cfg_t *cfg, double *obs,
+                   int32_t *recPid, int64_t recCap, int64_t *recCount, int64_t *events,
+                   int64_t evCap, int64_t *evCount) {
+  rng_t rng;
+  memset(&rng, 0, sizeof rng);
+  rng.cfg = cfg;
+  rng.recPid = recPid;
+  rng.recCap = recCap;
+  int64_t nEv = 0;
+  /* ctor :100-102: normalize(dir); appliedField = scale(dir, strength) */
+  double dir[3] = {fieldDirIn[0], fieldDirIn[1], fieldDirIn[2]};
+  {
+    double nrm = sqrt(sq3(dir));
+    if (nrm != 0.)
+      for (int d = 0; d < 3; d++)
+        dir[d] /= nrm;
+  }
+  double field[3] = {dir[0] * fieldStrength, dir[1] * fieldStrength, dir[2] * fieldStrength};
+  /* :186 force = scale(appliedField, charge) */
+  double force[3] = {field[0] * charge, field[1] * charge, field[2] * charge};
+  orc_mech_t desc;
+  for (int s = 0; s < nSteps; s++) {
+    for (int64_t p = 0; p < e->n; p++) {
+      rng.particle = p;
+      rng.step = (uint64_t)(firstStep + s);
+      rng.k = 0;
+      /* :195-213 */
+      double tau = e->tau[p];
+      drift_wrap(m, e, p, tau < dt ? tau : dt, force, box);
+      double tRem = dt - tau;
+      while (tRem > 0) {
+        int si = find_set(m, e->valley[p], e->region[p]);
+        int t = -2;
+        if (si >= 0 && m->sets[si].nMech > 0) {
+          double r = rng_u01(&rng);
+          t = orc_select(m, si, e->energy[p], r);
+          if (t >= 0) {
+            fill_mech_desc(m, m->sets[si].mechIdx[t], &desc);
+            scatter_with(m, &desc, e, p, &rng);
+          }
+          if (events && nEv < evCap) {
+            events[nEv * 4 + 0] = firstStep + s;
+            events[nEv * 4 + 1] = p;
+            events[nEv * 4 + 2] = t;
+            events[nEv * 4 + 3] = t >= 0 ? m->sets[si].mechIdx[t] : -1;
+          }
+          nEv++;
+        }
+        /* emcParticleType.hpp:187-189: uses the NEW valley, unchanged region */
+        double newTau = -log(rng_ulog(&rng)) * orc_tau(m, e->valley[p], e->region[p]);
+        tau += newTau;
+        drift_wrap(m, e, p, tRem < newTau ? tRem : newTau, force, box);
+        tRem -= newTau;
+      }
+      tau -= dt;
+      e->tau[p] = tau;
+      /* :216-220 grain clock (no grain mechanism: only the clock runs) */
+      if (e->grainTau) {
+        e->grainTau[p] -= dt;
+        if (e->grainTau[p] <= 0)
+          e->grainTau[p] = -log(rng_ulog(&rng)) * 1.;
+      }
+    }
+    if (obs)
+      orc_bulk_observables(m, e, dir, obs + (size_t)s * m->nValleys * 3);
+  }
+  if (recCount)
+    *recCount = rng.recCount;
+  if (evCount)
+    *evCount = nEv;
+  return 0;
+}
+
+/* ---------------------------------------------------------- initialisation */
+int64_t orc_generate_initial(const orc_model_t *m, const double box[3], const int32_t cells[3],
+                             double doping, uint64_t *mtState, orc_ensemble_t *out,
+                             int64_t capacity, int64_t *drawsConsumed) {
+  orc_rng_cfg_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.mode = ORC_RNG_MT_GLOBAL;
+  cfg.mtState = mtState;
+  rng_t rng;
+  memset(&rng, 0, sizeof rng);
+  rng.cfg = &cfg;
+  double h[3];
+  int64_t ext[3];
+  for (int d = 0; d < 3; d++) {
+    h[d] = box[d] / cells[d];
+    ext[d] = (int64_t)round(box[d] / h[d]) + 1; /* emcUtil.hpp:109-119 */
+  }
+  /* emcDevice.hpp:333-343 */
+  double cellVolume = 1.;
+  for (int d = 0; d < 3; d++)
+    cellVolume = cellVolume * h[d];
+  const double Vt = C_KB / C_Q * m->temperature;
+  int64_t n = 0;
+  for (int64_t cz = 0; cz < ext[2]; cz++)
+    for (int64_t cy = 0; cy < ext[1]; cy++)
+      for (int64_t cx = 0; cx < ext[0]; cx++) {
+        int64_t c[3] = {cx, cy, cz};
+        /* emcElectron.hpp:48-61 */
+        double dens = doping;
+        for (int d = 0; d < 3; d++)
+          if (c[d] == 0 || c[d] == ext[d] - 1)
+            dens *= 0.5;
+        double nr = dens * cellVolume;
+        /* basicBulkParticleHandler.hpp:150-156 */
+        for (;;) {
+          int create = 0;
+          if (nr >= 1) {
+            create = 1;
+          } else {
+            if (rng_u01(&rng) < nr)
+              create = 2;
+            else
+              break;
+          }
+          if (n < capacity) {
+            /* emcParticleInitialization.hpp:14-29 */
+            double pos[3];
+            for (int d = 0; d < 3; d++) {
+              if (c[d] == ext[d] - 1)
+                pos[d] = ((double)c[d] - rng_u01(&rng) * 0.5) * h[d];
+              else if (c[d] == 0)
+                pos[d] = rng_u01(&rng) * 0.5 * h[d];
+              else
+                pos[d] = ((double)c[d] + rng_u01(&rng) - 0.5) * h[d];
+            }
+            /* emcElectron.hpp:75-90 */
+            int valley = (int)floor(m->nValleys * rng_ulog(&rng));
+            const orc_valley_t *v = &m->valleys[valley];
+            int sub = (int)floor(v->deg * rng_ulog(&rng));
+            /* emcParticleInitialization.hpp:36-51 */
+            double energy = -1.5 * Vt * log(rng_ulog(&rng));
+            double r2 = rng_u01(&rng); /* right-to-left: first draw is rand2 */
+            double r1 = rng_u01(&rng);
+            double k[3];
+            orc_random_direction(orc_norm_wave_vec(v, energy), r1, r2, k);
+            for (int d = 0; d < 3; d++)
+              if ((c[d] == 0 && k[d] < 0) || (c[d] == ext[d] - 1 && k[d] > 0))
+                k[d] *= -1;
+            double tau = -log(rng_ulog(&rng)) * orc_tau(m, valley, 0);
+            double gtau = -log(rng_ulog(&rng)) * 1.;
+            out->kx[n] = k[0]; out->ky[n] = k[1]; out->kz[n] = k[2];
+            out->energy[n] = energy;
+            out->tau[n] = tau;
+            if (out->grainTau)
+              out->grainTau[n] = gtau;
+            out->x[n] = pos[0]; out->y[n] = pos[1]; out->z[n] = pos[2];
+            out->valley[n] = valley;
+            out->sub[n] = sub;
+            out->region[n] = 0;
+          } else {
+            /* still consume the draws so the count stays meaningful */
+            for (int i = 0; i < 10; i++)
+              rng_raw(&rng);
+          }
+          n++;
+          if (create == 2)
+            break;
+          nr--;
+        }
+      }
+  out->n = n <= capacity ? n : capacity;
+  if (drawsConsumed)
+    *drawsConsumed = rng.recCount;
+  return n <= capacity ? n : -n;
+}

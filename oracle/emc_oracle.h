@@ -1,0 +1,152 @@
+/* TEST INFRASTRUCTURE (oracle/).  CPU restatement of ViennaEMC's per-time-step
+ * particle loop, used ONLY as the checker by tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline leg.  Never linked into, imported by or executed
+ * from the product path (viennaemc_b200/, include/).
+ *
+ * Parity status: PINNED.  Every function below is checked bit-for-bit against
+ * outputs of the unmodified reference (oracle/_ref/ref_bulk_driver, built from
+ * /root/reference by oracle/Makefile; vectors committed under tests/golden/ by
+ * oracle/make_golden.py) and against the reference's own known-answer tests
+ * (tests/testParticleMovement, tests/testValleyCoordinateTransformation).
+ *
+ * All file:line citations are relative to the reference tree.
+ */
+#ifndef EMC_ORACLE_H
+#define EMC_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_MAX_SUB 8
+#define ORC_MAX_FINAL 8
+
+enum { ORC_VALLEY_PARABOLIC_ISO = 0, ORC_VALLEY_NONPARABOLIC_ISO = 1,
+       ORC_VALLEY_PARABOLIC_ANISO = 2, ORC_VALLEY_NONPARABOLIC_ANISO = 3 };
+
+enum { ORC_SAMPLER_NONE = 0, ORC_SAMPLER_ISOTROPIC_ELASTIC = 1,
+       ORC_SAMPLER_INTERVALLEY = 2, ORC_SAMPLER_COULOMB = 3 };
+
+enum { ORC_RNG_MT_GLOBAL = 0, ORC_RNG_STREAMS = 1, ORC_RNG_PHILOX = 2 };
+
+typedef struct {
+  int32_t kind, deg;
+  double mCond, mDos, alpha, eBottom;
+  double vogt[3];
+  double rot[ORC_MAX_SUB][9];
+} orc_valley_t;
+
+typedef struct {
+  int32_t sampler, finalValley, nFinal, globalId;
+  double p[4]; /* INTERVALLEY: p[0] = signed energy shift; COULOMB: p[0] = Debye energy */
+  int32_t finalSub[ORC_MAX_SUB][ORC_MAX_FINAL];
+} orc_mech_t;
+
+typedef struct {
+  int64_t n;
+  double *kx, *ky, *kz, *energy, *tau, *grainTau, *x, *y, *z;
+  int32_t *valley, *sub, *region;
+} orc_ensemble_t;
+
+typedef struct {
+  int32_t mode;
+  /* MT_GLOBAL: one std::mt19937_64-equivalent stream shared by all particles,
+   * consumed in particle order like the reference's single-thread rngs[0] */
+  uint64_t *mtState; /* [313], see orc_mt_seed */
+  /* STREAMS (replay): particle p consumes draws[offsets[p] + cursor[p]++] */
+  const uint64_t *draws;
+  const int64_t *offsets; /* [n+1] */
+  int64_t *cursor;        /* [n], in/out */
+  /* PHILOX: key = seed, counter = (particle id, step, draw index / 2) */
+  uint64_t philoxSeed;
+  int64_t particleIdBase; /* global id of local particle 0 (multi-GPU shards) */
+} orc_rng_cfg_t;
+
+typedef struct orc_model orc_model_t;
+
+/* ---- model construction (host-side math of the reference) ---- */
+orc_model_t *orc_model_create(int nLevels, double maxEnergy, double temperature,
+                              double rho, double vSound);
+void orc_model_destroy(orc_model_t *m);
+int orc_add_valley(orc_model_t *m, int kind, const double relMass[3],
+                   double particleMass, int deg, double alpha, double eBottom,
+                   const double *dirs /* [deg][3][3] un-normalised or NULL */);
+int orc_add_acoustic(orc_model_t *m, int valley, int region, double sigma);
+int orc_add_intervalley(orc_model_t *m, int order, int emission, int valley,
+                        int finalValley, int region, double defPot,
+                        double phononEnergy, int nInitSub, int nFinal,
+                        const int32_t *finalSub /* [nInitSub][nFinal] */);
+int orc_add_coulomb(orc_model_t *m, int valley, int region, double epsR,
+                    double regionDoping);
+int orc_build_tables(orc_model_t *m);
+
+int orc_n_valleys(const orc_model_t *m);
+int orc_get_valley(const orc_model_t *m, int v, orc_valley_t *out);
+int orc_n_mechanisms(const orc_model_t *m);
+double orc_raw_rate(const orc_model_t *m, int globalMech, double energy);
+int orc_n_tablesets(const orc_model_t *m);
+int orc_tableset_info(const orc_model_t *m, int i, int32_t *valley,
+                      int32_t *region, int32_t *nMech, double *tau);
+int orc_tableset_copy(const orc_model_t *m, int i, double *cum /*[nMech][nLevels]*/,
+                      orc_mech_t *mech /*[nMech]*/);
+double orc_tau(const orc_model_t *m, int valley, int region);
+double orc_dE(const orc_model_t *m);
+
+/* ---- valley math / kernels of the path ---- */
+double orc_energy(const orc_valley_t *v, const double k[3]);
+double orc_norm_wave_vec(const orc_valley_t *v, double energy);
+double orc_gamma(const orc_valley_t *v, double energy);
+double orc_eff_mass_cond(const orc_valley_t *v, double energy);
+void orc_velocity(const orc_valley_t *v, const double k[3], double energy,
+                  int sub, double out[3]);
+void orc_to_ellipse(const orc_valley_t *v, int sub, const double in[3], double out[3]);
+void orc_to_device(const orc_valley_t *v, int sub, const double in[3], double out[3]);
+void orc_drift(const orc_valley_t *v, double dt, double k[3], double *energy,
+               int sub, double pos[3], int dim, const double force[3]);
+void orc_random_direction(double norm, double rand1, double rand2, double out[3]);
+void orc_random_direction_wrt_k(const double k[3], double cosTheta, double rand,
+                                double out[3]);
+double orc_uniform(uint64_t raw, double a, double b);
+int orc_energy_level(const orc_model_t *m, double energy);
+int orc_select(const orc_model_t *m, int tableset, double energy, double r);
+
+/* ---- RNG primitives ---- */
+void orc_mt_seed(uint64_t *state /*[313]*/, uint64_t seed);
+uint64_t orc_mt_next(uint64_t *state);
+void orc_mt_fill(uint64_t seed, uint64_t *out, int64_t n);
+void orc_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+uint64_t orc_philox_draw(uint64_t seed, uint64_t particle, uint64_t step, uint64_t idx);
+
+/* ---- ensemble ---- */
+/* reference: basicBulkParticleHandler::generateInitialParticles (:143-159) with a
+ * single constant doping region; draws come from the given mt19937_64 state.
+ * Returns number of particles created, or -needed if capacity is too small.
+ * drawsConsumed (optional) receives the number of raw draws used. */
+int64_t orc_generate_initial(const orc_model_t *m, const double box[3],
+                             const int32_t cells[3], double doping,
+                             uint64_t *mtState, orc_ensemble_t *out,
+                             int64_t capacity, int64_t *drawsConsumed);
+
+/* One or more time steps of basicBulkParticleHandler::moveParticles (:181-225)
+ * followed by the three observable passes (:289-347).
+ *  obs: [nSteps][nValleys][3] = {sum E, sum v.Edir, count} (may be NULL)
+ *  recPid/recCap/recCount: optional log of which particle consumed each draw
+ *  events/evCap/evCount: optional log (step, particle, mechIndexInTableset or -1, globalMech or -1)
+ */
+int orc_bulk_steps(const orc_model_t *m, orc_ensemble_t *ens, const double box[3],
+                   const double fieldDir[3] /* un-normalised ok */, double fieldStrength,
+                   double charge, double dt, int nSteps,
+                   int64_t firstStepIndex, const orc_rng_cfg_t *rng,
+                   double *obs, int32_t *recPid,
+                   int64_t recCap, int64_t *recCount, int64_t *events,
+                   int64_t evCap, int64_t *evCount);
+
+/* observables only (reference :289-347), sums not yet divided */
+void orc_bulk_observables(const orc_model_t *m, const orc_ensemble_t *ens,
+                          const double fieldDir[3], double *obs /*[nValleys][3]*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,62 @@
+"""TEST INFRASTRUCTURE: generate tests/golden/*.npz from the UNMODIFIED reference.
+
+Runs oracle/_ref/ref_bulk_driver (built by oracle/Makefile from /root/reference,
+development container only) for every case in tests/scenarios.py::GOLDEN_CASES and
+stores its dumps as compressed numpy archives.  The fixtures travel to the GPU
+box; the reference tree does not.
+
+    python oracle/make_golden.py
+"""
+import os
+import struct
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from scenarios import GOLDEN_CASES  # noqa: E402
+
+DT = {"d": np.float64, "q": np.int64, "Q": np.uint64}
+
+
+def read_blob(path):
+    out = {}
+    with open(path, "rb") as f:
+        data = f.read()
+    o = 0
+    while o < len(data):
+        (nl,) = struct.unpack_from("<I", data, o); o += 4
+        name = data[o:o + nl].decode(); o += nl
+        dt = chr(data[o]); o += 1
+        (nd,) = struct.unpack_from("<I", data, o); o += 4
+        dims = struct.unpack_from("<%dQ" % nd, data, o); o += 8 * nd
+        n = int(np.prod(dims)) if nd else 1
+        arr = np.frombuffer(data, dtype=DT[dt], count=n, offset=o).reshape(dims).copy(); o += 8 * n
+        out[name] = arr
+    return out
+
+
+def main():
+    subprocess.check_call(["make", "-C", HERE, "_ref/ref_bulk_driver"])
+    drv = os.path.join(HERE, "_ref", "ref_bulk_driver")
+    os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    for name, case in GOLDEN_CASES.items():
+        with tempfile.TemporaryDirectory() as tmp:  # the reference writes rate files into the CWD
+            out = os.path.join(tmp, "ref.bin")
+            cmd = [drv, "--out", out]
+            for k, v in case["args"].items():
+                cmd += ["--" + k, str(v)]
+            subprocess.check_call(cmd, cwd=tmp, stdout=subprocess.DEVNULL)
+            blob = read_blob(out)
+        dst = os.path.join(ROOT, "tests", "golden", name + ".npz")
+        np.savez_compressed(dst, **blob)
+        print(name, "->", dst, os.path.getsize(dst) // 1024, "KiB; particles", int(blob["params"][-1]),
+              "draws", len(blob["draws"]), "events", len(blob["events"]))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,99 @@
+"""Scenario definitions shared by the parity tests (TEST INFRASTRUCTURE).
+
+`si`    : Si X valleys + the shipped bulkSimulation mechanism set
+          (reference: examples/SiliconFunctions.hpp:21-145, examples/bulkSimulation/bulkSimulation.cpp:100-103)
+`mixed` : synthetic four-valley material, one valley of every 3-D valley class, built identically in
+          oracle/ref_bulk_driver.cpp::buildMixed against the reference headers.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+
+from oracle import pyoracle as po  # noqa: E402
+
+SI_G = [[0], [1], [2]]
+SI_F = [[1, 1, 2, 2], [0, 0, 2, 2], [0, 0, 1, 1]]
+SI_DIRS = [[[1, 0, 0], [0, 1, 0], [0, 0, 1]],
+           [[0, 1, 0], [1, 0, 0], [0, 0, 1]],
+           [[0, 0, 1], [0, 1, 0], [1, 0, 0]]]
+
+
+def build_si(mechs=("acoustic", "zero", "first"), n_levels=1000, max_energy=1.0, temperature=300.0,
+             doping=1e23, regions=(0,)):
+    m = po.Model(n_levels, max_energy, temperature, 2329.0, 9040.0)
+    m.add_valley(po.VALLEY_NONPARABOLIC_ANISO, [0.916, 0.196, 0.196], 3, 0.5, 0.0, SI_DIRS)
+    for reg in regions:
+        if "acoustic" in mechs:
+            m.add_acoustic(0, reg, 9.0)
+        if "coulomb" in mechs:
+            m.add_coulomb(0, reg, 11.8, doping)
+        if "zero" in mechs:
+            m.add_intervalley(0, False, 0, 0, reg, 5.23e10, 0.06, SI_F)
+            m.add_intervalley(0, True, 0, 0, reg, 5.23e10, 0.06, SI_F)
+            m.add_intervalley(0, False, 0, 0, reg, 5.23e10, 0.06, SI_G)
+            m.add_intervalley(0, True, 0, 0, reg, 5.23e10, 0.06, SI_G)
+        if "first" in mechs:
+            m.add_intervalley(1, False, 0, 0, reg, 2.5, 0.023, SI_F)
+            m.add_intervalley(1, True, 0, 0, reg, 2.5, 0.023, SI_F)
+            m.add_intervalley(1, False, 0, 0, reg, 4.0, 0.018, SI_G)
+            m.add_intervalley(1, True, 0, 0, reg, 4.0, 0.018, SI_G)
+    m.build_tables()
+    return m
+
+
+MIXED_DEG = [1, 4, 2, 3]
+MIXED_L_DIRS = [[[1, 1, 1], [-1, 1, 0], [-1, -1, 2]],
+                [[-1, 1, 1], [1, 1, 0], [1, -1, 2]],
+                [[1, -1, 1], [1, 1, 0], [-1, 1, 2]],
+                [[1, 1, -1], [1, 0, 1], [-1, 2, 1]]]
+
+
+def build_mixed(mechs=("acoustic", "zero", "first", "coulomb"), n_levels=250, max_energy=2.0,
+                temperature=300.0, doping=1e23):
+    m = po.Model(n_levels, max_energy, temperature, 2329.0, 9040.0)
+    m.add_valley(po.VALLEY_NONPARABOLIC_ISO, 0.067, 1, 0.61, 0.0)
+    m.add_valley(po.VALLEY_NONPARABOLIC_ANISO, [1.9, 0.075, 0.11], 4, 0.46, 0.05, MIXED_L_DIRS)
+    m.add_valley(po.VALLEY_PARABOLIC_ISO, 0.3, 2, 0.0, 0.03)
+    m.add_valley(po.VALLEY_PARABOLIC_ANISO, [0.9, 0.2, 0.3], 3, 0.0, 0.08, SI_DIRS)
+    for vi in range(4):
+        if "acoustic" in mechs:
+            m.add_acoustic(vi, 0, 7.0 + vi)
+        if "coulomb" in mechs:
+            m.add_coulomb(vi, 0, 11.8, doping)
+        for vf in range(4):
+            if vf == vi:
+                continue
+            sm = [[sf for sf in range(MIXED_DEG[vf])] for _ in range(MIXED_DEG[vi])]
+            if "zero" in mechs:
+                m.add_intervalley(0, False, vi, vf, 0, 6e10, 0.03, sm)
+                m.add_intervalley(0, True, vi, vf, 0, 6e10, 0.03, sm)
+            if "first" in mechs and (vi + vf) % 2 == 1:
+                m.add_intervalley(1, False, vi, vf, 0, 3.0, 0.02, sm)
+                m.add_intervalley(1, True, vi, vf, 0, 3.0, 0.02, sm)
+    m.build_tables()
+    return m
+
+
+# golden cases: name -> (ref driver args, model builder kwargs)
+GOLDEN_CASES = {
+    "si_bulk": dict(
+        args=dict(material="si", mechs="acoustic,zero,first", cells=2, box=1e-7, doping=1e23, field=1e6,
+                  fdir="-1,0,0", dt=1e-16, steps=1200, seed=7, levels=1000, emax=1.0),
+        builder="si", kwargs=dict(mechs=("acoustic", "zero", "first"), n_levels=1000, max_energy=1.0)),
+    "si_coulomb_bigdt": dict(
+        args=dict(material="si", mechs="acoustic,zero,first,coulomb", cells=3, box=1.2e-7, doping=1e23,
+                  field=3e6, fdir="1,2,-0.5", dt=1e-15, steps=25, seed=12345, levels=500, emax=4.0),
+        builder="si", kwargs=dict(mechs=("acoustic", "zero", "first", "coulomb"), n_levels=500, max_energy=4.0)),
+    "mixed": dict(
+        args=dict(material="mixed", mechs="acoustic,zero,first,coulomb", cells=2, box=1e-7, doping=1e23,
+                  field=2e6, fdir="0.3,-1,0.2", dt=2e-15, steps=80, seed=11, levels=250, emax=2.0),
+        builder="mixed", kwargs=dict(mechs=("acoustic", "zero", "first", "coulomb"), n_levels=250, max_energy=2.0)),
+}
+
+
+def build_model(case: str):
+    c = GOLDEN_CASES[case]
+    return (build_si if c["builder"] == "si" else build_mixed)(**c["kwargs"])
