@@ -1,0 +1,228 @@
+/*
+ * emcgpu.h -- C ABI of the B200-native ensemble Monte Carlo particle loop.
+ *
+ * This is the drop-in boundary for ONE path of ViennaEMC: the per-time-step
+ * particle loop (free flight, null-scatter selection, final-state sampling,
+ * per-step observables; for device runs additionally charge assignment and the
+ * Poisson update).  The reference is a header-only C++17 library with no FFI of
+ * its own; the entry points below are what its particle handlers bind to once
+ * their bodies are replaced.  Each entry point cites the
+ * reference interface it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - plain C, plain pointers and sizes, no C++/torch types;
+ *   - every call returns an emcgpu_status (0 = ok); a human readable message
+ *     for the last failure is available from emcgpu_last_error();
+ *   - host buffers are caller-owned and copied during the call; device memory is
+ *     owned by the context.  Pointers documented as DEVICE pointers must point
+ *     to memory of the context's CUDA device;
+ *   - all calls on one context must come from one host thread at a time (the
+ *     reference drives its handlers from a single thread as well);
+ *   - there is NO CPU fallback: without a CUDA device every call fails with
+ *     EMCGPU_E_CUDA, and a scatter mechanism without a device sampler is
+ *     rejected with EMCGPU_E_UNSUPPORTED_MECHANISM (message carries getName()).
+ */
+#ifndef EMCGPU_H
+#define EMCGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMCGPU_ABI_VERSION 1
+#define EMCGPU_MAX_VALLEYS 8
+#define EMCGPU_MAX_SUBVALLEYS 8
+#define EMCGPU_MAX_FINAL 8
+#define EMCGPU_MAX_MECH_PER_SET 16
+#define EMCGPU_MAX_TABLESETS 32
+#define EMCGPU_NAME_LEN 48
+
+typedef enum {
+  EMCGPU_OK = 0,
+  EMCGPU_E_INVALID = 1,               /* bad argument / call order            */
+  EMCGPU_E_CUDA = 2,                  /* CUDA runtime failure, no device      */
+  EMCGPU_E_UNSUPPORTED_MECHANISM = 3, /* mechanism has no device sampler      */
+  EMCGPU_E_UNSUPPORTED_VALLEY = 4,
+  EMCGPU_E_CAPACITY = 5,              /* fixed-size limit above exceeded      */
+  EMCGPU_E_REPLAY_EXHAUSTED = 6       /* replay stream ran out of draws       */
+} emcgpu_status;
+
+/* Valley classes of include/ValleyTypes/ (3-D):
+ *   emcParabolicIsotropValley.hpp, emcNonParabolicIsotropValley.hpp,
+ *   emcParabolicAnisotropValley.hpp, emcNonParabolicAnistropValley.hpp */
+typedef enum {
+  EMCGPU_VALLEY_PARABOLIC_ISOTROP = 0,
+  EMCGPU_VALLEY_NONPARABOLIC_ISOTROP = 1,
+  EMCGPU_VALLEY_PARABOLIC_ANISOTROP = 2,
+  EMCGPU_VALLEY_NONPARABOLIC_ANISOTROP = 3
+} emcgpu_valley_kind;
+
+/* One emcAbstractValley (include/ValleyTypes/emcAbstractValley.hpp:20-91) as the
+ * numbers its virtuals return: getEffMassCond(0), getEffMassDOS(0),
+ * getNonParabolicity(), getBottomEnergy(), getDegeneracyFactor(),
+ * getVogtTransformationFactor() and, per sub-valley, the row-major rotation
+ * used by transformToEllipseCoord (emcNonParabolicAnistropValley.hpp:140-153). */
+typedef struct {
+  int32_t kind; /* emcgpu_valley_kind */
+  int32_t degeneracy;
+  double effMassCond; /* [kg], band edge */
+  double effMassDOS;  /* [kg], band edge */
+  double alpha;       /* [1/eV], 0 for parabolic */
+  double bottomEnergy; /* [eV] */
+  double vogt[3];
+  double rot[EMCGPU_MAX_SUBVALLEYS][9];
+} emcgpu_valley_t;
+
+/* Device final-state samplers, selected by mechanism ID.  Each replaces the
+ * scatterParticle() of the named reference classes. */
+typedef enum {
+  EMCGPU_SAMPLER_NONE = 0, /* rejected: "no device sampler" */
+  /* emcAcousticScatterMechanism.hpp:70-72 (elastic, isotropic) */
+  EMCGPU_SAMPLER_ISOTROPIC_ELASTIC = 1,
+  /* emcZeroOrderInterValleyScatterMechanism.hpp:119-129, :262-272 and
+   * emcFirstOrderInterValleyScatterMechanism.hpp:121-131, :269-279:
+   * valley <- finalValley, subValley <- finalSub[sub][raw % nFinal],
+   * E += param[0] (signed: +(hw - dE_valley) absorption, -(hw + dE_valley)
+   * emission), |k| <- k_norm(E) in the final valley, isotropic direction */
+  EMCGPU_SAMPLER_INTERVALLEY = 2,
+  /* emcCoulombScatterMechanism.hpp:48-59 (Brooks-Herring); param[0] = Debye
+   * energy N_D/(c2 m_c) of the table set's region */
+  EMCGPU_SAMPLER_COULOMB = 3
+} emcgpu_sampler_id;
+
+/* One emcScatterMechanism (include/ScatterMechanisms/emcScatterMechanism.hpp:17-53)
+ * as seen by the device: which sampler, its parameters, its name for errors. */
+typedef struct {
+  int32_t sampler; /* emcgpu_sampler_id */
+  int32_t finalValley;
+  int32_t nFinal;
+  int32_t mechId; /* caller's global mechanism index, echoed in event logs */
+  double param[4];
+  uint8_t finalSub[EMCGPU_MAX_SUBVALLEYS][EMCGPU_MAX_FINAL];
+  char name[EMCGPU_NAME_LEN];
+} emcgpu_mech_t;
+
+/* The normalised cumulative scatter tables of one (valley, region) key exactly
+ * as emcScatterHandler::renormalizeTables leaves them
+ * (include/emcScatterHandler.hpp:248-273): cum[m][l], m in insertion order,
+ * l = energy level ((l+1)*dE), all divided by the maximal cumulative rate;
+ * tau = 1/that maximum. */
+typedef struct {
+  int32_t valley;
+  int32_t region;
+  int32_t nMech;
+  int32_t reserved;
+  double tau;
+  const double *cum;         /* HOST, [nMech][nLevels] */
+  const emcgpu_mech_t *mech; /* HOST, [nMech] */
+} emcgpu_tableset_t;
+
+/* SoA ensemble streams (replaces the AoS emcParticle<T> of include/emcParticle.hpp:10-18
+ * plus the separate position vector, basicBulkParticleHandler.hpp:58-59). */
+enum { EMCGPU_KX = 0, EMCGPU_KY, EMCGPU_KZ, EMCGPU_ENERGY, EMCGPU_TAU,
+       EMCGPU_X, EMCGPU_Y, EMCGPU_Z, EMCGPU_N_STREAMS };
+/* packed index word: valley | subValley << 8 | region << 16 */
+#define EMCGPU_PACK(valley, sub, region) \
+  ((uint32_t)(valley) | ((uint32_t)(sub) << 8) | ((uint32_t)(region) << 16))
+
+/* math mode of the step kernels */
+typedef enum {
+  /* reference operation order, every op individually rounded (no FMA
+   * contraction): the mode used for replay parity */
+  EMCGPU_MATH_EXACT = 0,
+  /* hoisted constants + FMA; agrees with EXACT to ~1e-15 per step */
+  EMCGPU_MATH_FAST = 1
+} emcgpu_math_mode;
+
+typedef struct emcgpu_ctx emcgpu_ctx;
+
+/* ---- life cycle ------------------------------------------------------- */
+int emcgpu_abi_version(void);
+/* cudaDevice: ordinal of the GPU this context lives on. */
+int emcgpu_create(int cudaDevice, emcgpu_ctx **out);
+void emcgpu_destroy(emcgpu_ctx *ctx);
+/* message of the last failed call on ctx (ctx == NULL: last emcgpu_create failure) */
+const char *emcgpu_last_error(const emcgpu_ctx *ctx);
+/* number of kernels launched by this context so far (bench bookkeeping) */
+int64_t emcgpu_launch_count(const emcgpu_ctx *ctx);
+/* run all later work of ctx on this cudaStream_t (NULL = default stream) */
+int emcgpu_set_stream(emcgpu_ctx *ctx, void *cudaStream);
+int emcgpu_synchronize(emcgpu_ctx *ctx);
+
+/* ---- physics model (built on the host by the reference-compatible API) - */
+/* replaces the per-particle virtual calls into emcParticleType::valleys
+ * (include/ParticleType/emcParticleType.hpp:34, :121-124) */
+int emcgpu_set_valleys(emcgpu_ctx *ctx, const emcgpu_valley_t *valleys, int nValleys);
+/* replaces the std::map look-ups of emcScatterHandler::scatterParticle
+ * (include/emcScatterHandler.hpp:148-170) and getTau (:79-84).  Can be called
+ * again at any time (emcScatterHandler::reinitScatterTables, :100-108). */
+int emcgpu_set_tables(emcgpu_ctx *ctx, const emcgpu_tableset_t *sets, int nSets,
+                      int nLevels, double maxEnergy);
+
+/* ---- ensemble --------------------------------------------------------- */
+/* upload n particles; soa[EMCGPU_N_STREAMS] are HOST arrays of length n.
+ * particleIdBase: global id of particle 0 (keys the Philox streams so that
+ * trajectories do not depend on how the ensemble is sharded across GPUs). */
+int emcgpu_set_ensemble(emcgpu_ctx *ctx, int64_t n, const double *const *soa,
+                        const uint32_t *packed, int64_t particleIdBase);
+int emcgpu_get_ensemble(emcgpu_ctx *ctx, double *const *soa, uint32_t *packed);
+int64_t emcgpu_ensemble_size(const emcgpu_ctx *ctx);
+/* Device-side creation of a thermal bulk ensemble (same distributions as
+ * emcElectron::generateInitialParticle, include/ParticleType/emcElectron.hpp:75-90,
+ * emcParticleInitialization.hpp:14-51, positions uniform in the box), keyed by
+ * Philox(seed, particleIdBase + i).  For ensembles too large to build on the host. */
+int emcgpu_generate_bulk_ensemble(emcgpu_ctx *ctx, int64_t n, const double box[3],
+                                  double temperature, int32_t region, uint64_t seed,
+                                  int64_t particleIdBase);
+/* DEVICE pointers to the SoA streams (for zero-copy consumers, e.g. dlpack) */
+int emcgpu_ensemble_device_ptrs(emcgpu_ctx *ctx, double **soaOut /*[8]*/, uint32_t **packedOut);
+
+/* ---- random numbers --------------------------------------------------- */
+/* counter-based Philox4x32-10: draw i of particle p in step s is word pair
+ * (i & 1) of Philox(key = seed, counter = (p_lo, p_hi, s, i >> 1)).  Replaces
+ * the per-thread std::mt19937_64 of basicBulkParticleHandler.hpp:110-119. */
+int emcgpu_rng_philox(emcgpu_ctx *ctx, uint64_t seed);
+/* replay: particle p consumes draws[offsets[p]], draws[offsets[p]+1], ... (raw
+ * 64-bit engine outputs recorded from the reference run).  HOST arrays;
+ * offsets has n+1 entries. */
+int emcgpu_rng_replay(emcgpu_ctx *ctx, const uint64_t *draws, const int64_t *offsets, int64_t n);
+
+/* ---- bulk run: basicBulkParticleHandler (examples/bulkSimulation/
+ *      basicBulkParticleHandler.hpp) -------------------------------------- */
+/* ctor / resetAppliedFieldStrength (:93-137): periodic box, field = strength *
+ * normalised(direction), force = charge * field (:186). */
+int emcgpu_bulk_configure(emcgpu_ctx *ctx, const double box[3], const double fieldDirection[3],
+                          double fieldStrength, double charge, int mathMode);
+/* nSteps x { moveParticles(dt) (:181-225) ; getAvgEnergy, getAvgDriftVelocity,
+ * getValleyOccupationProbability (:289-347) }.  obs (HOST, may be NULL) receives
+ * [nSteps][nValleys][3] = { sum of energies, sum of v.E_dir, particle count }
+ * per valley after each step (sums over THIS context's particles; divide after
+ * the cross-GPU reduction). stepsPerLaunch > 1 keeps the state in registers for
+ * that many consecutive steps. */
+int emcgpu_bulk_step(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPerLaunch, double *obs);
+/* same, observables left on the device: obsDevice is a DEVICE buffer of
+ * nSteps*nValleys*3 doubles that is zeroed and accumulated into; asynchronous
+ * on the context's stream. */
+int emcgpu_bulk_step_device(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPerLaunch,
+                            double *obsDevice);
+/* observables of the current state without moving (:289-347), HOST out [nValleys][3] */
+int emcgpu_bulk_observables(emcgpu_ctx *ctx, double *obs);
+/* index of the next time step (Philox counter word); starts at 1 like
+ * bulkSimulation.cpp:150 and advances by nSteps per emcgpu_bulk_step call */
+int emcgpu_set_step_index(emcgpu_ctx *ctx, int64_t nextStep);
+int64_t emcgpu_get_step_index(const emcgpu_ctx *ctx);
+
+/* ---- diagnostics used by the parity tests ------------------------------ */
+/* log up to capacity scatter selections as (step, particleId, tableIndex or -1
+ * for self-scattering, mechId or -1); 0 disables. */
+int emcgpu_event_log_enable(emcgpu_ctx *ctx, int64_t capacity);
+/* copies the log (HOST, [count][4] int64) and returns the number of events
+ * seen (may exceed capacity); resets the log. */
+int64_t emcgpu_event_log_read(emcgpu_ctx *ctx, int64_t *out, int64_t capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMCGPU_H */

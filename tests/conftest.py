@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx_factory():
+    from viennaemc_b200 import capi
+
+    made = []
+
+    def make(device=0):
+        c = capi.Context(device)
+        made.append(c)
+        return c
+
+    yield make
+    for c in made:
+        c.close()

@@ -1,0 +1,91 @@
+"""Glue between the oracle model (test infrastructure) and the GPU C ABI (product)."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from oracle import pyoracle as po
+from viennaemc_b200 import capi
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# tolerance of BASELINE.json north_star: fp64 particle state within 1e-12 relative
+STATE_RTOL = 1e-12
+
+
+def load_golden(case):
+    return np.load(os.path.join(GOLDEN_DIR, case + ".npz"))
+
+
+def golden_ensemble(g, prefix):
+    return po.Ensemble.from_arrays(g[prefix + "k"], g[prefix + "pos"], g[prefix + "energy"], g[prefix + "tau"],
+                                   g[prefix + "grainTau"], g[prefix + "idx"])
+
+
+def upload_model(ctx: capi.Context, model: po.Model):
+    """oracle model -> emcgpu_set_valleys / emcgpu_set_tables"""
+    valleys = []
+    for v in model.valleys():
+        rot = np.array([list(v.rot[s]) for s in range(po.MAX_SUB)])
+        valleys.append(capi.make_valley(v.kind, v.deg, v.mCond, v.mDos, v.alpha, v.eBottom, list(v.vogt), rot))
+    ctx.set_valleys(valleys)
+    sets = []
+    for ts in model.tablesets():
+        mechs = []
+        for m in ts["mech"]:
+            fs = np.array([[m.finalSub[s][f] for f in range(max(1, m.nFinal))] for s in range(po.MAX_SUB)])
+            mechs.append(capi.make_mech(m.sampler, name=f"mech{m.globalId}", mech_id=m.globalId,
+                                        final_valley=m.finalValley, final_sub=fs if m.nFinal > 0 else None,
+                                        params=[m.p[0], m.p[1]]))
+        sets.append(dict(valley=ts["valley"], region=ts["region"], tau=ts["tau"], cum=ts["cum"], mech=mechs))
+    ctx.set_tables(sets, model.n_levels, model.max_energy)
+
+
+def upload_ensemble(ctx: capi.Context, ens: po.Ensemble, particle_id_base=0):
+    ctx.set_ensemble([ens.kx, ens.ky, ens.kz, ens.energy, ens.tau, ens.x, ens.y, ens.z], ens.packed(),
+                     particle_id_base)
+
+
+def download_ensemble(ctx: capi.Context) -> po.Ensemble:
+    streams, packed = ctx.get_ensemble()
+    e = po.Ensemble(len(packed))
+    e.n = len(packed)
+    e.kx, e.ky, e.kz, e.energy, e.tau, e.x, e.y, e.z = streams
+    e.valley = (packed & 0xFF).astype(np.int32)
+    e.sub = ((packed >> 8) & 0xFF).astype(np.int32)
+    e.region = (packed >> 16).astype(np.int32)
+    return e
+
+
+def rel_err(a, b, scale=None):
+    """max |a-b| / max(|b|, scale); scale defaults to the RMS magnitude of b."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if scale is None:
+        scale = float(np.sqrt(np.mean(b * b))) if b.size else 1.0
+    den = np.maximum(np.abs(b), scale if scale > 0 else 1.0)
+    return float(np.max(np.abs(a - b) / den)) if b.size else 0.0
+
+
+def assert_state_close(got: po.Ensemble, want: po.Ensemble, box, rtol=STATE_RTOL, what=""):
+    assert got.n == want.n
+    n = want.n
+    # indices: bit-exact
+    for f in ("valley", "sub", "region"):
+        assert np.array_equal(getattr(got, f)[:n], getattr(want, f)[:n]), f"{what}: {f} differs"
+    kmag = float(np.sqrt(np.mean(want.kx[:n] ** 2 + want.ky[:n] ** 2 + want.kz[:n] ** 2)))
+    errs = {}
+    for f in ("kx", "ky", "kz"):
+        errs[f] = rel_err(getattr(got, f)[:n], getattr(want, f)[:n], kmag)
+    errs["energy"] = rel_err(got.energy[:n], want.energy[:n])
+    errs["tau"] = rel_err(got.tau[:n], want.tau[:n])
+    for f, b in zip(("x", "y", "z"), box):
+        errs[f] = rel_err(getattr(got, f)[:n], getattr(want, f)[:n], b)
+    bad = {k: v for k, v in errs.items() if not v <= rtol}
+    assert not bad, f"{what}: state differs beyond {rtol}: {bad}"
+    return errs
+
+
+def field_dir_of(args):
+    return [float(x) for x in args["fdir"].split(",")]

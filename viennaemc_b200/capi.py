@@ -1,0 +1,266 @@
+"""ctypes binding of libemcgpu.so (the C ABI declared in include/emcgpu.h).
+
+This is the thin Python view of the drop-in boundary used by tests/, bench.py and
+__graft_entry__.py.  It loads the in-tree CUDA library and fails loudly if it is
+missing: there is no CPU fallback anywhere in the product path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libemcgpu.so")
+
+MAX_VALLEYS, MAX_SUB, MAX_FINAL, MAX_MECH_PER_SET, MAX_TABLESETS, NAME_LEN = 8, 8, 8, 16, 32, 48
+N_STREAMS = 8
+KX, KY, KZ, ENERGY, TAU, X, Y, Z = range(8)
+STREAM_NAMES = ("kx", "ky", "kz", "energy", "tau", "x", "y", "z")
+
+OK, E_INVALID, E_CUDA, E_UNSUPPORTED_MECHANISM, E_UNSUPPORTED_VALLEY, E_CAPACITY, E_REPLAY_EXHAUSTED = range(7)
+SAMPLER_NONE, SAMPLER_ISOTROPIC_ELASTIC, SAMPLER_INTERVALLEY, SAMPLER_COULOMB = range(4)
+MATH_EXACT, MATH_FAST = 0, 1
+
+_DP = C.POINTER(C.c_double)
+
+
+class ValleyC(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("degeneracy", C.c_int32), ("effMassCond", C.c_double),
+                ("effMassDOS", C.c_double), ("alpha", C.c_double), ("bottomEnergy", C.c_double),
+                ("vogt", C.c_double * 3), ("rot", (C.c_double * 9) * MAX_SUB)]
+
+
+class MechC(C.Structure):
+    _fields_ = [("sampler", C.c_int32), ("finalValley", C.c_int32), ("nFinal", C.c_int32), ("mechId", C.c_int32),
+                ("param", C.c_double * 4), ("finalSub", (C.c_uint8 * MAX_FINAL) * MAX_SUB),
+                ("name", C.c_char * NAME_LEN)]
+
+
+class TableSetC(C.Structure):
+    _fields_ = [("valley", C.c_int32), ("region", C.c_int32), ("nMech", C.c_int32), ("reserved", C.c_int32),
+                ("tau", C.c_double), ("cum", _DP), ("mech", C.POINTER(MechC))]
+
+
+class EmcGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"emcgpu error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load libemcgpu.so; raises if the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -m viennaemc_b200.build` "
+                          "(the product path has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.emcgpu_abi_version.restype = C.c_int
+    L.emcgpu_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.emcgpu_destroy.argtypes = [vp]
+    L.emcgpu_destroy.restype = None
+    L.emcgpu_last_error.argtypes = [vp]
+    L.emcgpu_last_error.restype = C.c_char_p
+    L.emcgpu_launch_count.argtypes = [vp]
+    L.emcgpu_launch_count.restype = C.c_int64
+    L.emcgpu_set_stream.argtypes = [vp, vp]
+    L.emcgpu_synchronize.argtypes = [vp]
+    L.emcgpu_set_valleys.argtypes = [vp, C.POINTER(ValleyC), C.c_int]
+    L.emcgpu_set_tables.argtypes = [vp, C.POINTER(TableSetC), C.c_int, C.c_int, C.c_double]
+    L.emcgpu_set_ensemble.argtypes = [vp, C.c_int64, C.POINTER(_DP), C.POINTER(C.c_uint32), C.c_int64]
+    L.emcgpu_get_ensemble.argtypes = [vp, C.POINTER(_DP), C.POINTER(C.c_uint32)]
+    L.emcgpu_ensemble_size.argtypes = [vp]
+    L.emcgpu_ensemble_size.restype = C.c_int64
+    L.emcgpu_generate_bulk_ensemble.argtypes = [vp, C.c_int64, _DP, C.c_double, C.c_int32, C.c_uint64, C.c_int64]
+    L.emcgpu_ensemble_device_ptrs.argtypes = [vp, C.POINTER(_DP), C.POINTER(C.POINTER(C.c_uint32))]
+    L.emcgpu_rng_philox.argtypes = [vp, C.c_uint64]
+    L.emcgpu_rng_replay.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_int64), C.c_int64]
+    L.emcgpu_bulk_configure.argtypes = [vp, _DP, _DP, C.c_double, C.c_double, C.c_int]
+    L.emcgpu_bulk_step.argtypes = [vp, C.c_double, C.c_int, C.c_int, _DP]
+    L.emcgpu_bulk_step_device.argtypes = [vp, C.c_double, C.c_int, C.c_int, vp]
+    L.emcgpu_bulk_observables.argtypes = [vp, _DP]
+    L.emcgpu_set_step_index.argtypes = [vp, C.c_int64]
+    L.emcgpu_get_step_index.argtypes = [vp]
+    L.emcgpu_get_step_index.restype = C.c_int64
+    L.emcgpu_event_log_enable.argtypes = [vp, C.c_int64]
+    L.emcgpu_event_log_read.argtypes = [vp, C.POINTER(C.c_int64), C.c_int64]
+    L.emcgpu_event_log_read.restype = C.c_int64
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "emcgpu_abi_version", "emcgpu_create", "emcgpu_destroy", "emcgpu_last_error", "emcgpu_launch_count",
+    "emcgpu_set_stream", "emcgpu_synchronize", "emcgpu_set_valleys", "emcgpu_set_tables", "emcgpu_set_ensemble",
+    "emcgpu_get_ensemble", "emcgpu_ensemble_size", "emcgpu_generate_bulk_ensemble",
+    "emcgpu_ensemble_device_ptrs", "emcgpu_rng_philox", "emcgpu_rng_replay", "emcgpu_bulk_configure",
+    "emcgpu_bulk_step", "emcgpu_bulk_step_device", "emcgpu_bulk_observables", "emcgpu_set_step_index",
+    "emcgpu_get_step_index", "emcgpu_event_log_enable", "emcgpu_event_log_read",
+]
+
+
+def make_valley(kind, degeneracy, eff_mass_cond, eff_mass_dos, alpha, bottom_energy, vogt, rot) -> ValleyC:
+    v = ValleyC()
+    v.kind, v.degeneracy = int(kind), int(degeneracy)
+    v.effMassCond, v.effMassDOS, v.alpha, v.bottomEnergy = eff_mass_cond, eff_mass_dos, alpha, bottom_energy
+    for i in range(3):
+        v.vogt[i] = vogt[i]
+    rot = np.asarray(rot, dtype=np.float64).reshape(-1, 9)
+    for s in range(MAX_SUB):
+        for j in range(9):
+            v.rot[s][j] = rot[s][j] if s < len(rot) else (1.0 if j in (0, 4, 8) else 0.0)
+    return v
+
+
+def make_mech(sampler, name="", mech_id=0, final_valley=0, final_sub=None, params=()) -> MechC:
+    m = MechC()
+    m.sampler, m.finalValley, m.mechId = int(sampler), int(final_valley), int(mech_id)
+    m.name = name.encode()[: NAME_LEN - 1]
+    for i, p in enumerate(params):
+        m.param[i] = p
+    if final_sub is not None:
+        fs = np.asarray(final_sub)
+        m.nFinal = fs.shape[1]
+        for s in range(fs.shape[0]):
+            for f in range(fs.shape[1]):
+                m.finalSub[s][f] = int(fs[s, f])
+    return m
+
+
+class Context:
+    """One GPU context (one per process / per GPU)."""
+
+    def __init__(self, device: int = 0):
+        self.L = load()
+        h = C.c_void_p()
+        rc = self.L.emcgpu_create(device, C.byref(h))
+        if rc != OK:
+            raise EmcGpuError(rc, self.L.emcgpu_last_error(None).decode())
+        self.h = h
+        self.n_valleys = 0
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.emcgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != OK:
+            raise EmcGpuError(rc, self.L.emcgpu_last_error(self.h).decode())
+
+    # -- model
+    def set_valleys(self, valleys):
+        arr = (ValleyC * len(valleys))(*valleys)
+        self._chk(self.L.emcgpu_set_valleys(self.h, arr, len(valleys)))
+        self.n_valleys = len(valleys)
+
+    def set_tables(self, sets, n_levels, max_energy):
+        """sets: list of dicts(valley, region, tau, cum ndarray [nMech][nLevels], mech list[MechC])"""
+        arr = (TableSetC * max(1, len(sets)))()
+        keep = []
+        for i, s in enumerate(sets):
+            cum = np.ascontiguousarray(s["cum"], dtype=np.float64)
+            mech = (MechC * len(s["mech"]))(*s["mech"])
+            keep += [cum, mech]
+            arr[i].valley, arr[i].region, arr[i].nMech, arr[i].tau = s["valley"], s["region"], cum.shape[0], s["tau"]
+            arr[i].cum = cum.ctypes.data_as(_DP)
+            arr[i].mech = mech
+        self._chk(self.L.emcgpu_set_tables(self.h, arr, len(sets), int(n_levels), float(max_energy)))
+
+    # -- ensemble
+    def set_ensemble(self, streams, packed, particle_id_base=0):
+        streams = [np.ascontiguousarray(a, dtype=np.float64) for a in streams]
+        packed = np.ascontiguousarray(packed, dtype=np.uint32)
+        n = len(packed)
+        ptrs = (_DP * N_STREAMS)(*[a.ctypes.data_as(_DP) for a in streams])
+        self._chk(self.L.emcgpu_set_ensemble(self.h, n, ptrs, packed.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                             particle_id_base))
+
+    def get_ensemble(self):
+        n = self.size
+        streams = [np.empty(n, dtype=np.float64) for _ in range(N_STREAMS)]
+        packed = np.empty(n, dtype=np.uint32)
+        ptrs = (_DP * N_STREAMS)(*[a.ctypes.data_as(_DP) for a in streams])
+        self._chk(self.L.emcgpu_get_ensemble(self.h, ptrs, packed.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return streams, packed
+
+    @property
+    def size(self):
+        return int(self.L.emcgpu_ensemble_size(self.h))
+
+    def generate_bulk_ensemble(self, n, box, temperature=300.0, region=0, seed=12345, particle_id_base=0):
+        b = (C.c_double * 3)(*box)
+        self._chk(self.L.emcgpu_generate_bulk_ensemble(self.h, n, b, temperature, region, seed, particle_id_base))
+
+    def device_ptrs(self):
+        ptrs = (_DP * N_STREAMS)()
+        packed = C.POINTER(C.c_uint32)()
+        self._chk(self.L.emcgpu_ensemble_device_ptrs(self.h, ptrs, C.byref(packed)))
+        return [C.cast(p, C.c_void_p).value for p in ptrs], C.cast(packed, C.c_void_p).value
+
+    # -- rng
+    def rng_philox(self, seed):
+        self._chk(self.L.emcgpu_rng_philox(self.h, seed))
+
+    def rng_replay(self, draws, offsets):
+        draws = np.ascontiguousarray(draws, dtype=np.uint64)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self._chk(self.L.emcgpu_rng_replay(self.h, draws.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                           offsets.ctypes.data_as(C.POINTER(C.c_int64)), len(offsets) - 1))
+
+    # -- bulk
+    def bulk_configure(self, box, field_dir, field_strength, charge=-1.60219e-19, math_mode=MATH_EXACT):
+        b = (C.c_double * 3)(*box)
+        d = (C.c_double * 3)(*field_dir)
+        self._chk(self.L.emcgpu_bulk_configure(self.h, b, d, field_strength, charge, math_mode))
+
+    def bulk_step(self, dt, n_steps=1, steps_per_launch=1, want_obs=True):
+        obs = np.zeros((n_steps, self.n_valleys, 3)) if want_obs else None
+        self._chk(self.L.emcgpu_bulk_step(self.h, dt, n_steps, steps_per_launch,
+                                          obs.ctypes.data_as(_DP) if want_obs else None))
+        return obs
+
+    def bulk_step_device(self, dt, n_steps, steps_per_launch, obs_device_ptr):
+        self._chk(self.L.emcgpu_bulk_step_device(self.h, dt, n_steps, steps_per_launch, obs_device_ptr))
+
+    def bulk_observables(self):
+        obs = np.zeros((self.n_valleys, 3))
+        self._chk(self.L.emcgpu_bulk_observables(self.h, obs.ctypes.data_as(_DP)))
+        return obs
+
+    def set_step_index(self, s):
+        self._chk(self.L.emcgpu_set_step_index(self.h, s))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._chk(self.L.emcgpu_set_stream(self.h, cuda_stream_ptr))
+
+    def synchronize(self):
+        self._chk(self.L.emcgpu_synchronize(self.h))
+
+    @property
+    def launch_count(self):
+        return int(self.L.emcgpu_launch_count(self.h))
+
+    def event_log_enable(self, capacity):
+        self._chk(self.L.emcgpu_event_log_enable(self.h, capacity))
+
+    def event_log_read(self, capacity):
+        out = np.zeros((capacity, 4), dtype=np.int64)
+        n = self.L.emcgpu_event_log_read(self.h, out.ctypes.data_as(C.POINTER(C.c_int64)), capacity)
+        if n < 0:
+            raise EmcGpuError(E_CUDA, self.L.emcgpu_last_error(self.h).decode())
+        return out[: min(n, capacity)], int(n)

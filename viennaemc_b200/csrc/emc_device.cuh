@@ -1,0 +1,390 @@
+// Device functions of the particle loop: arithmetic policy (EXACT / FAST),
+// counter-based and replay RNG, valley math, free flight, selection and the
+// final-state samplers.  Every function cites the reference code it replaces
+// (paths relative to the reference tree).
+#pragma once
+#include <cstdint>
+
+#include "emc_model.cuh"
+
+namespace emc {
+
+// ---------------------------------------------------------------------------
+// Arithmetic policy.  EXACT: every operation individually rounded in the
+// reference's order (the __d*_rn intrinsics are never contracted into FMAs),
+// so that replay runs track the reference to the last bits of libm.  FAST:
+// plain operators, nvcc contracts a*b+c into DFMA.
+template <bool EXACT> struct Arith {
+  static __device__ __forceinline__ double mul(double a, double b) {
+    if constexpr (EXACT) return __dmul_rn(a, b); else return a * b;
+  }
+  static __device__ __forceinline__ double add(double a, double b) {
+    if constexpr (EXACT) return __dadd_rn(a, b); else return a + b;
+  }
+  static __device__ __forceinline__ double sub(double a, double b) {
+    if constexpr (EXACT) return __dsub_rn(a, b); else return a - b;
+  }
+  static __device__ __forceinline__ double div(double a, double b) {
+    if constexpr (EXACT) return __ddiv_rn(a, b); else return a / b;
+  }
+  static __device__ __forceinline__ double sqrt(double a) {
+    if constexpr (EXACT) return __dsqrt_rn(a); else return ::sqrt(a);
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Random numbers.
+enum RngMode : int { RNG_PHILOX = 0, RNG_REPLAY = 1 };
+
+// Philox4x32-10 (Salmon et al. 2011).  One call yields two 64-bit draws.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Per (particle, step) stream of raw 64-bit draws.  Draw i is word pair (i&1)
+// of Philox(key = seed, counter = (id_lo, id_hi, step, i>>1)), or the next
+// entry of the particle's recorded replay stream.
+struct Rng {
+  // philox
+  uint32_t k0, k1, idLo, idHi, step, n;
+  uint64_t cached;
+  // replay
+  const uint64_t *stream; // first unread draw of this particle
+  const uint64_t *streamEnd;
+  int *status;
+
+  template <int MODE> __device__ __forceinline__ uint64_t raw() {
+    if constexpr (MODE == RNG_PHILOX) {
+      uint64_t r;
+      if ((n & 1u) == 0u) {
+        uint32_t o[4];
+        philox4x32_10(idLo, idHi, step, n >> 1, k0, k1, o);
+        r = (uint64_t)o[1] << 32 | o[0];
+        cached = (uint64_t)o[3] << 32 | o[2];
+      } else {
+        r = cached;
+      }
+      n++;
+      return r;
+    } else {
+      if (stream >= streamEnd) {
+        atomicExch(status, (int)EMCGPU_E_REPLAY_EXHAUSTED);
+        return 0x8000000000000000ull;
+      }
+      return *stream++;
+    }
+  }
+};
+
+// libstdc++ generate_canonical<double,53> on a 64-bit engine followed by
+// uniform_real_distribution's u*(b-a)+a: always individually
+// rounded, in both math modes, so that indices never depend on the mode.
+__device__ __forceinline__ double canonical(uint64_t raw) {
+  double u = __dmul_rn(__ull2double_rn(raw), 5.42101086242752217e-20 /* 2^-64 */);
+  return u >= 1.0 ? 0.99999999999999988898 /* nextafter(1,0) */ : u;
+}
+__device__ __forceinline__ double uniform01(uint64_t raw) {
+  // (u * (1 - 0)) + 0
+  return canonical(raw);
+}
+__device__ __forceinline__ double uniformLog(uint64_t raw) {
+  // U[1e-6, 1): u * (1. - 1e-6) + 1e-6   (emcParticleType.hpp:37)
+  return __dadd_rn(__dmul_rn(canonical(raw), 1.0 - 1e-6), 1e-6);
+}
+
+// ---------------------------------------------------------------------------
+// Valley math (include/ValleyTypes/*.hpp)
+struct Vec3 {
+  double x, y, z;
+};
+
+__device__ __forceinline__ double pick(const Vec3 &v, unsigned code) {
+  const unsigned i = code & 3u;
+  const double a = i == 0 ? v.x : (i == 1 ? v.y : v.z);
+  return (code & 4u) ? -a : a;
+}
+__device__ __forceinline__ Vec3 permute(const Vec3 &v, unsigned p) {
+  return Vec3{pick(v, p), pick(v, p >> 4), pick(v, p >> 8)};
+}
+
+// transformToEllipseCoord (emcNonParabolicAnistropValley.hpp:140-153): R_s * v
+template <bool EXACT>
+__device__ __forceinline__ Vec3 toEllipse(const DevValley &v, int s, const Vec3 &a) {
+  using A = Arith<EXACT>;
+  if (v.rotKind == ROT_IDENTITY) return a;
+  if (v.rotKind == ROT_SIGNED_PERMUTATION) return permute(a, v.permToE[s]);
+  const double *r = v.rot[s];
+  Vec3 o;
+  o.x = A::add(A::add(A::mul(a.x, r[0]), A::mul(a.y, r[1])), A::mul(a.z, r[2]));
+  o.y = A::add(A::add(A::mul(a.x, r[3]), A::mul(a.y, r[4])), A::mul(a.z, r[5]));
+  o.z = A::add(A::add(A::mul(a.x, r[6]), A::mul(a.y, r[7])), A::mul(a.z, r[8]));
+  return o;
+}
+// transformToDeviceCoord (:157-170): R_s^T * v
+template <bool EXACT>
+__device__ __forceinline__ Vec3 toDevice(const DevValley &v, int s, const Vec3 &a) {
+  using A = Arith<EXACT>;
+  if (v.rotKind == ROT_IDENTITY) return a;
+  if (v.rotKind == ROT_SIGNED_PERMUTATION) return permute(a, v.permToD[s]);
+  const double *r = v.rot[s];
+  Vec3 o;
+  o.x = A::add(A::add(A::mul(a.x, r[0]), A::mul(a.y, r[3])), A::mul(a.z, r[6]));
+  o.y = A::add(A::add(A::mul(a.x, r[1]), A::mul(a.y, r[4])), A::mul(a.z, r[7]));
+  o.z = A::add(A::add(A::mul(a.x, r[2]), A::mul(a.y, r[5])), A::mul(a.z, r[8]));
+  return o;
+}
+
+// getGamma (emcNonParabolicAnistropValley.hpp:122; parabolic: E)
+template <bool EXACT> __device__ __forceinline__ double gammaOf(const DevValley &v, double e) {
+  using A = Arith<EXACT>;
+  if (!v.nonParabolic) return e;
+  return A::mul(e, A::add(1.0, A::mul(v.alpha, e)));
+}
+
+// getEnergy(k): non-parabolic g = hbar*hbar*|k|^2/(m q), E = g/(1+sqrt(1+2 a g))
+// (emcNonParabolicAnistropValley.hpp:109-113, emcNonParabolicIsotropValley.hpp:78-82);
+// parabolic hbar*hbar*|k|^2/(2 m q) (emcParabolicIsotropValley.hpp:62-65)
+template <bool EXACT> __device__ __forceinline__ double energyOfSq(const DevValley &v, double sq) {
+  using A = Arith<EXACT>;
+  if constexpr (EXACT) {
+    const double h2 = kHbar * kHbar; // folded exactly like the reference's constexpr product
+    if (v.nonParabolic) {
+      const double g = A::div(A::mul(h2, sq), v.xMq);
+      return A::div(g, A::add(1.0, A::sqrt(A::add(1.0, A::mul(A::mul(2.0, v.alpha), g)))));
+    }
+    return A::div(A::mul(h2, sq), v.xTwoMq);
+  } else {
+    const double g = v.fE * sq;
+    if (v.nonParabolic) return g / (1.0 + ::sqrt(fma(2.0 * v.alpha, g, 1.0)));
+    return g;
+  }
+}
+template <bool EXACT> __device__ __forceinline__ double sqNorm(const Vec3 &k) {
+  using A = Arith<EXACT>;
+  // emcUtil.hpp:26-31: res = 0; res += e*e, in order
+  return A::add(A::add(A::mul(k.x, k.x), A::mul(k.y, k.y)), A::mul(k.z, k.z));
+}
+
+// getEffMassCond(E) (:90-92): m (1 + 2 E alpha); parabolic: m
+template <bool EXACT> __device__ __forceinline__ double massFactor(const DevValley &v, double e) {
+  using A = Arith<EXACT>;
+  if (!v.nonParabolic) return 1.0;
+  return A::add(1.0, A::mul(A::mul(2.0, e), v.alpha));
+}
+
+// getNormWaveVec(E): sqrt(2 m gamma q)/hbar (aniso non-parabolic, :103-106) or
+// sqrt(2 m q gamma)/hbar (the three other classes)
+template <bool EXACT> __device__ __forceinline__ double normWaveVec(const DevValley &v, double e) {
+  using A = Arith<EXACT>;
+  const double g = gammaOf<EXACT>(v, e);
+  const double twoM = A::mul(2.0, v.mCond);
+  double arg;
+  if (v.kind == EMCGPU_VALLEY_NONPARABOLIC_ANISOTROP)
+    arg = A::mul(A::mul(twoM, g), kQ);
+  else
+    arg = A::mul(A::mul(twoM, kQ), g);
+  return A::div(A::sqrt(arg), kHbar);
+}
+
+// getVelocity(k, E, s) . dirE, where dirE is the field direction already in
+// the sub-valley's ellipse frame (emcNonParabolicAnistropValley.hpp:126-136 and
+// the three sibling classes; basicBulkParticleHandler.hpp:326-347).
+template <bool EXACT>
+__device__ __forceinline__ double driftVelocity(const DevValley &v, int s, const Vec3 &k, double e,
+                                                const Vec3 &dir) {
+  using A = Arith<EXACT>;
+  if constexpr (EXACT) {
+    double npf = 1.0;
+    if (v.nonParabolic)
+      npf = A::sqrt(A::add(1.0, A::mul(A::mul(4.0, v.alpha), gammaOf<EXACT>(v, e))));
+    Vec3 vel;
+    if (v.kind >= EMCGPU_VALLEY_PARABOLIC_ANISOTROP) {
+      const Vec3 ke = toEllipse<EXACT>(v, s, k);
+      const double den = v.nonParabolic ? A::mul(v.mCond, npf) : v.mCond;
+      Vec3 ve;
+      ve.x = A::div(A::mul(A::mul(kHbar, v.vogt[0]), ke.x), den);
+      ve.y = A::div(A::mul(A::mul(kHbar, v.vogt[1]), ke.y), den);
+      ve.z = A::div(A::mul(A::mul(kHbar, v.vogt[2]), ke.z), den);
+      vel = toDevice<EXACT>(v, s, ve);
+    } else {
+      const double f = v.nonParabolic ? A::div(kHbar, A::mul(v.mCond, npf)) : A::div(kHbar, v.mCond);
+      vel.x = A::mul(k.x, f);
+      vel.y = A::mul(k.y, f);
+      vel.z = A::mul(k.z, f);
+    }
+    // innerProduct (emcUtil.hpp:51-54)
+    return A::add(A::add(A::mul(vel.x, dir.x), A::mul(vel.y, dir.y)), A::mul(vel.z, dir.z));
+  } else {
+    // sqrt(1 + 4 a gamma(E)) == 1 + 2 a E for the Kane dispersion
+    const Vec3 ke = toEllipse<false>(v, s, k);
+    const Vec3 de = toEllipse<false>(v, s, dir);
+    const double num = v.fVel[0] * ke.x * de.x + v.fVel[1] * ke.y * de.y + v.fVel[2] * ke.z * de.z;
+    return v.nonParabolic ? num / fma(2.0 * v.alpha, e, 1.0) : num;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Particle state held in registers during a step.
+struct Particle {
+  Vec3 k;
+  double energy, tau;
+  Vec3 pos;
+  int valley, sub, region;
+};
+
+// drift() (include/emcParticleDrift.hpp:12-36): Herring-Vogt free flight of
+// duration dt under `force` (device frame), leapfrog position update with the
+// conduction mass at the NEW energy.  DIM = number of position components that
+// are advanced (2-D devices drop z, :33-35).
+template <bool EXACT, int DIM>
+__device__ __forceinline__ void drift(const DevValley &v, Particle &p, double dt, const Vec3 &force) {
+  using A = Arith<EXACT>;
+  const Vec3 kOld = toEllipse<EXACT>(v, p.sub, p.k);
+  const Vec3 fE = toEllipse<EXACT>(v, p.sub, force);
+  Vec3 kNew, dP;
+  if constexpr (EXACT) {
+    kNew.x = A::add(kOld.x, A::div(A::mul(A::mul(fE.x, dt), v.vogt[0]), kHbar));
+    kNew.y = A::add(kOld.y, A::div(A::mul(A::mul(fE.y, dt), v.vogt[1]), kHbar));
+    kNew.z = A::add(kOld.z, A::div(A::mul(A::mul(fE.z, dt), v.vogt[2]), kHbar));
+    p.k = toDevice<EXACT>(v, p.sub, kNew);
+    p.energy = energyOfSq<EXACT>(v, sqNorm<EXACT>(p.k));
+    const double mass = v.nonParabolic ? A::mul(v.mCond, massFactor<EXACT>(v, p.energy)) : v.mCond;
+    dP.x = A::div(A::mul(A::mul(A::mul(kHbar, v.vogt[0]), A::div(A::add(kNew.x, kOld.x), 2.0)), dt), mass);
+    dP.y = A::div(A::mul(A::mul(A::mul(kHbar, v.vogt[1]), A::div(A::add(kNew.y, kOld.y), 2.0)), dt), mass);
+    dP.z = A::div(A::mul(A::mul(A::mul(kHbar, v.vogt[2]), A::div(A::add(kNew.z, kOld.z), 2.0)), dt), mass);
+  } else {
+    kNew.x = fma(fE.x * v.fDk[0], dt, kOld.x);
+    kNew.y = fma(fE.y * v.fDk[1], dt, kOld.y);
+    kNew.z = fma(fE.z * v.fDk[2], dt, kOld.z);
+    p.k = toDevice<EXACT>(v, p.sub, kNew);
+    p.energy = energyOfSq<EXACT>(v, kNew.x * kNew.x + kNew.y * kNew.y + kNew.z * kNew.z);
+    const double w = v.nonParabolic ? dt / fma(2.0 * v.alpha, p.energy, 1.0) : dt;
+    dP.x = v.fPos[0] * (kNew.x + kOld.x) * w;
+    dP.y = v.fPos[1] * (kNew.y + kOld.y) * w;
+    dP.z = v.fPos[2] * (kNew.z + kOld.z) * w;
+  }
+  const Vec3 d = toDevice<EXACT>(v, p.sub, dP);
+  p.pos.x = A::add(p.pos.x, d.x);
+  if constexpr (DIM > 1) p.pos.y = A::add(p.pos.y, d.y);
+  if constexpr (DIM > 2) p.pos.z = A::add(p.pos.z, d.z);
+}
+
+// periodic wrap of the bulk handler (basicBulkParticleHandler.hpp:600-613)
+template <bool EXACT> __device__ __forceinline__ double wrap1(double x, double maxPos) {
+  using A = Arith<EXACT>;
+  if (x < 0.0) return A::add(x, maxPos);
+  if (x > maxPos) return A::sub(x, maxPos);
+  return x;
+}
+
+// initRandomDirection (include/emcUtil.hpp:131-139)
+template <bool EXACT> __device__ __forceinline__ Vec3 randomDirection(double norm, double rand1, double rand2) {
+  using A = Arith<EXACT>;
+  const double phi = A::mul(2.0 * kPi, rand1);
+  const double c = A::sub(1.0, A::mul(2.0, rand2));
+  double sp, cp;
+  sincos(phi, &sp, &cp);
+  const double ns = A::mul(norm, A::sqrt(A::sub(1.0, A::mul(c, c))));
+  return Vec3{A::mul(ns, cp), A::mul(ns, sp), A::mul(norm, c)};
+}
+
+// initRandomDirectionWithRespectToCurrentK (include/emcUtil.hpp:143-175)
+template <bool EXACT>
+__device__ __forceinline__ Vec3 randomDirectionWrtK(const Vec3 &k, double cosTheta, double rnd) {
+  using A = Arith<EXACT>;
+  const double kxy = A::sqrt(A::add(A::mul(k.x, k.x), A::mul(k.y, k.y)));
+  const double normK = A::sqrt(A::add(A::mul(kxy, kxy), A::mul(k.z, k.z)));
+  if (normK == 0.0) return Vec3{0.0, 0.0, 0.0};
+  const double ct0 = A::div(k.z, normK), st0 = A::div(kxy, normK);
+  const double cfi0 = kxy > 0.0 ? A::div(k.x, kxy) : 1.0;
+  const double sfi0 = kxy > 0.0 ? A::div(k.y, kxy) : 0.0;
+  const double st = A::sqrt(A::sub(1.0, A::mul(cosTheta, cosTheta)));
+  const double phi = A::mul(2.0 * kPi, rnd);
+  double sp, cp;
+  sincos(phi, &sp, &cp);
+  const double kxp = A::mul(A::mul(normK, st), cp);
+  const double kyp = A::mul(A::mul(normK, st), sp);
+  const double kzp = A::mul(normK, cosTheta);
+  Vec3 o;
+  o.x = A::add(A::sub(A::mul(A::mul(kxp, cfi0), ct0), A::mul(kyp, sfi0)), A::mul(A::mul(kzp, cfi0), st0));
+  o.y = A::add(A::add(A::mul(A::mul(kxp, sfi0), ct0), A::mul(kyp, cfi0)), A::mul(A::mul(kzp, sfi0), st0));
+  o.z = A::add(A::mul(-kxp, st0), A::mul(kzp, ct0));
+  return o;
+}
+
+// getEnergyLevel (include/emcScatterHandler.hpp:237-244), with the x86-64 g++
+// behaviour of the size_t conversion
+__device__ __forceinline__ int energyLevel(double energy, double dE, int nLevels) {
+  const double f = floor(__ddiv_rn(energy, dE)) - 1.0;
+  if (f == -1.0) return 0;
+  if (!(f >= 0.0) || f > (double)(nLevels - 1)) return nLevels - 1;
+  return (int)f;
+}
+
+// Null-scatter selection (include/emcScatterHandler.hpp:148-170) as a binary
+// search: first m with r < cum[m]; -1 = self-scattering.  row points to the
+// nMech cumulative entries of the particle's energy level.
+__device__ __forceinline__ int selectMechanism(const double *row, int nMech, double r) {
+  if (r > row[nMech - 1]) return -1;
+  int lo = 0, hi = nMech; // answer in [lo, hi]; hi == nMech means none
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (r < row[mid]) hi = mid; else lo = mid + 1;
+  }
+  return lo < nMech ? lo : -1;
+}
+
+// Final-state samplers, selected by mechanism ID.
+template <bool EXACT, int RNG_MODE>
+__device__ __forceinline__ void sampleFinalState(const DevModel &model, const DevMech &mech, Particle &p,
+                                                 Rng &rng) {
+  using A = Arith<EXACT>;
+  switch (mech.sampler) {
+  case EMCGPU_SAMPLER_ISOTROPIC_ELASTIC: {
+    // emcAcousticScatterMechanism.hpp:70-72; g++ evaluates the two dist(rng)
+    // arguments right to left: first draw = cos(theta) variate
+    const double nrm = A::sqrt(sqNorm<EXACT>(p.k));
+    const double r2 = uniform01(rng.raw<RNG_MODE>());
+    const double r1 = uniform01(rng.raw<RNG_MODE>());
+    p.k = randomDirection<EXACT>(nrm, r1, r2);
+    break;
+  }
+  case EMCGPU_SAMPLER_INTERVALLEY: {
+    // emcZeroOrderInterValleyScatterMechanism.hpp:119-129 / :262-272,
+    // emcFirstOrderInterValleyScatterMechanism.hpp:121-131 / :269-279
+    const uint64_t raw = rng.raw<RNG_MODE>();
+    p.sub = mech.finalSub[p.sub][raw % (uint64_t)mech.nFinal];
+    p.valley = mech.finalValley;
+    p.energy = A::add(p.energy, mech.param[0]);
+    const double kn = normWaveVec<EXACT>(model.valleys[p.valley], p.energy);
+    const double r2 = uniform01(rng.raw<RNG_MODE>());
+    const double r1 = uniform01(rng.raw<RNG_MODE>());
+    p.k = randomDirection<EXACT>(kn, r1, r2);
+    break;
+  }
+  case EMCGPU_SAMPLER_COULOMB: {
+    // emcCoulombScatterMechanism.hpp:48-59
+    const double g = gammaOf<EXACT>(model.valleys[p.valley], p.energy);
+    const double rnd = uniform01(rng.raw<RNG_MODE>());
+    const double den = A::add(A::div(A::mul(A::sub(1.0, rnd), g), mech.param[0]), 1.0);
+    const double c = A::sub(1.0, A::div(A::mul(rnd, 2.0), den));
+    const double r = uniform01(rng.raw<RNG_MODE>());
+    p.k = randomDirectionWrtK<EXACT>(p.k, c, r);
+    break;
+  }
+  default:
+    break;
+  }
+}
+
+} // namespace emc

@@ -1,0 +1,674 @@
+// C-ABI implementation (include/emcgpu.h): context, model upload, ensemble
+// management and kernel launches.  No CPU fallback: every compute entry point
+// needs a CUDA device and fails with EMCGPU_E_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "emc_bulk_kernel.cuh"
+
+using namespace emc;
+
+namespace {
+
+thread_local std::string g_createError;
+
+struct DeviceBuffer {
+  void *ptr = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&ptr, need);
+    if (e == cudaSuccess) bytes = need;
+    return e;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+  }
+};
+
+} // namespace
+
+struct emcgpu_ctx {
+  int device = 0;
+  int smCount = 0;
+  int maxSmemOptin = 0;
+  cudaStream_t stream = nullptr;
+  std::string error;
+  int64_t launches = 0;
+
+  // model
+  bool haveValleys = false, haveTables = false;
+  DevModel hModel{};
+  std::vector<DevMech> hMechs;
+  DeviceBuffer dModel, dMechs, dTables;
+
+  // ensemble
+  int64_t n = 0, capacity = 0, idBase = 0;
+  DeviceBuffer dEnsemble;
+  double *dStream[EMCGPU_N_STREAMS] = {};
+  uint32_t *dPacked = nullptr;
+
+  // rng
+  int rngMode = RNG_PHILOX;
+  uint64_t seed = 0;
+  DeviceBuffer dDraws, dOffsets, dCursor;
+
+  // bulk configuration
+  bool bulkConfigured = false;
+  Vec3 box{}, force{}, dir{};
+  int mathMode = EMCGPU_MATH_EXACT;
+  int64_t nextStep = 1;
+
+  // outputs
+  DeviceBuffer dObs, dStatus, dEvents, dEvCount;
+  int64_t evCap = 0;
+};
+
+namespace {
+
+int fail(emcgpu_ctx *ctx, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->error = buf; else g_createError = buf;
+  return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      return fail(ctx, EMCGPU_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));        \
+  } while (0)
+
+int bind(emcgpu_ctx *ctx) {
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  return EMCGPU_OK;
+}
+
+// classify R (row-major, rows = ellipse axes): identity, signed permutation, general
+int classifyRotation(const double *r, uint16_t *toE, uint16_t *toD) {
+  bool identity = true, perm = true;
+  int src[3] = {-1, -1, -1}, sign[3] = {0, 0, 0};
+  for (int i = 0; i < 3; i++) {
+    int nz = 0;
+    for (int j = 0; j < 3; j++) {
+      const double x = r[i * 3 + j];
+      if (x != (i == j ? 1.0 : 0.0)) identity = false;
+      if (x != 0.0) {
+        nz++;
+        if (x == 1.0 || x == -1.0) {
+          src[i] = j;
+          sign[i] = x < 0 ? 1 : 0;
+        } else {
+          perm = false;
+        }
+      }
+    }
+    if (nz != 1) perm = false;
+  }
+  if (perm && (src[0] == src[1] || src[0] == src[2] || src[1] == src[2])) perm = false;
+  *toE = *toD = 0;
+  if (!perm) return ROT_GENERAL;
+  for (int i = 0; i < 3; i++) {
+    // toEllipse: out[i] = sign_i * in[src_i]; toDevice: out[src_i] = sign_i * in[i]
+    *toE |= (uint16_t)((src[i] | (sign[i] << 2)) << (4 * i));
+    *toD |= (uint16_t)((i | (sign[i] << 2)) << (4 * src[i]));
+  }
+  return identity ? ROT_IDENTITY : ROT_SIGNED_PERMUTATION;
+}
+
+cudaError_t uploadModel(emcgpu_ctx *ctx) {
+  cudaError_t e = ctx->dModel.ensure(sizeof(DevModel));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpyAsync(ctx->dModel.ptr, &ctx->hModel, sizeof(DevModel), cudaMemcpyHostToDevice, ctx->stream);
+}
+
+size_t bulkSmemBytes(const emcgpu_ctx *ctx, int nSteps, bool tablesInSmem) {
+  size_t off = (sizeof(DevModel) + 15) & ~size_t(15);
+  off += (size_t)nSteps * ctx->hModel.nValleys * 3 * sizeof(double);
+  off = (off + 15) & ~size_t(15);
+  off += ctx->hMechs.size() * sizeof(DevMech);
+  off = (off + 15) & ~size_t(15);
+  if (tablesInSmem) off += (size_t)ctx->hModel.tableDoubles * sizeof(double);
+  return off;
+}
+
+void fillBulkParams(emcgpu_ctx *ctx, BulkParams &P) {
+  memset(&P, 0, sizeof P);
+  for (int s = 0; s < EMCGPU_N_STREAMS; s++) P.stream[s] = ctx->dStream[s];
+  P.packed = ctx->dPacked;
+  P.n = ctx->n;
+  P.idBase = ctx->idBase;
+  P.model = static_cast<const DevModel *>(ctx->dModel.ptr);
+  P.tables = static_cast<const double *>(ctx->dTables.ptr);
+  P.mechs = static_cast<const DevMech *>(ctx->dMechs.ptr);
+  P.nMechTotal = (int32_t)ctx->hMechs.size();
+  P.box = ctx->box;
+  P.force = ctx->force;
+  P.dir = ctx->dir;
+  P.seed = ctx->seed;
+  P.draws = static_cast<const uint64_t *>(ctx->dDraws.ptr);
+  P.offsets = static_cast<const int64_t *>(ctx->dOffsets.ptr);
+  P.cursor = static_cast<uint32_t *>(ctx->dCursor.ptr);
+  P.events = static_cast<long long *>(ctx->dEvents.ptr);
+  P.evCap = ctx->evCap;
+  P.evCount = static_cast<unsigned long long *>(ctx->dEvCount.ptr);
+  P.status = static_cast<int *>(ctx->dStatus.ptr);
+}
+
+template <bool EXACT, int MODE>
+cudaError_t launchBulk(emcgpu_ctx *ctx, const BulkParams &P, size_t smem, int grid) {
+  auto kernel = bulkStepKernel<EXACT, MODE>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kernel<<<grid, kBulkThreads, smem, ctx->stream>>>(P);
+  ctx->launches++;
+  return cudaGetLastError();
+}
+
+int checkReady(emcgpu_ctx *ctx, bool needEnsemble) {
+  if (!ctx) return EMCGPU_E_INVALID;
+  if (!ctx->haveValleys) return fail(ctx, EMCGPU_E_INVALID, "emcgpu_set_valleys has not been called");
+  if (!ctx->haveTables) return fail(ctx, EMCGPU_E_INVALID, "emcgpu_set_tables has not been called");
+  if (!ctx->bulkConfigured) return fail(ctx, EMCGPU_E_INVALID, "emcgpu_bulk_configure has not been called");
+  if (needEnsemble && ctx->n <= 0) return fail(ctx, EMCGPU_E_INVALID, "the ensemble is empty");
+  return EMCGPU_OK;
+}
+
+int allocEnsemble(emcgpu_ctx *ctx, int64_t n) {
+  // every stream starts on a 256-byte boundary
+  const size_t strideD = ((size_t)n * sizeof(double) + 255) & ~size_t(255);
+  const size_t strideP = ((size_t)n * sizeof(uint32_t) + 255) & ~size_t(255);
+  CUDA_TRY(ctx, ctx->dEnsemble.ensure(strideD * EMCGPU_N_STREAMS + strideP));
+  unsigned char *base = static_cast<unsigned char *>(ctx->dEnsemble.ptr);
+  for (int s = 0; s < EMCGPU_N_STREAMS; s++) ctx->dStream[s] = reinterpret_cast<double *>(base + strideD * s);
+  ctx->dPacked = reinterpret_cast<uint32_t *>(base + strideD * EMCGPU_N_STREAMS);
+  ctx->n = n;
+  ctx->capacity = n;
+  return EMCGPU_OK;
+}
+
+int checkStatusWord(emcgpu_ctx *ctx) {
+  int status = 0;
+  CUDA_TRY(ctx, cudaMemcpyAsync(&status, ctx->dStatus.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (status != 0) {
+    cudaMemsetAsync(ctx->dStatus.ptr, 0, sizeof(int), ctx->stream);
+    if (status == EMCGPU_E_REPLAY_EXHAUSTED)
+      return fail(ctx, status, "replay stream exhausted: a particle needed more draws than were recorded");
+    return fail(ctx, status, "device reported status %d", status);
+  }
+  return EMCGPU_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int emcgpu_abi_version(void) { return EMCGPU_ABI_VERSION; }
+
+int emcgpu_create(int cudaDevice, emcgpu_ctx **out) {
+  if (!out) return fail(nullptr, EMCGPU_E_INVALID, "out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(nullptr, EMCGPU_E_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  if (cudaDevice < 0 || cudaDevice >= count)
+    return fail(nullptr, EMCGPU_E_INVALID, "cudaDevice %d out of range [0,%d)", cudaDevice, count);
+  emcgpu_ctx *ctx = new emcgpu_ctx();
+  ctx->device = cudaDevice;
+  cudaDeviceProp prop;
+  if ((e = cudaSetDevice(cudaDevice)) != cudaSuccess ||
+      (e = cudaGetDeviceProperties(&prop, cudaDevice)) != cudaSuccess) {
+    delete ctx;
+    return fail(nullptr, EMCGPU_E_CUDA, "cannot open device %d: %s", cudaDevice, cudaGetErrorString(e));
+  }
+  if (prop.major != 10) {
+    delete ctx;
+    return fail(nullptr, EMCGPU_E_CUDA, "device %d is sm_%d%d; this library contains sm_100a code only",
+                cudaDevice, prop.major, prop.minor);
+  }
+  ctx->smCount = prop.multiProcessorCount;
+  ctx->maxSmemOptin = (int)prop.sharedMemPerBlockOptin;
+  if ((e = ctx->dStatus.ensure(sizeof(int))) != cudaSuccess ||
+      (e = ctx->dEvCount.ensure(sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMemset(ctx->dStatus.ptr, 0, sizeof(int))) != cudaSuccess ||
+      (e = cudaMemset(ctx->dEvCount.ptr, 0, sizeof(unsigned long long))) != cudaSuccess) {
+    delete ctx;
+    return fail(nullptr, EMCGPU_E_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
+  }
+  *out = ctx;
+  return EMCGPU_OK;
+}
+
+void emcgpu_destroy(emcgpu_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (DeviceBuffer *b : {&ctx->dModel, &ctx->dMechs, &ctx->dTables, &ctx->dEnsemble, &ctx->dDraws,
+                          &ctx->dOffsets, &ctx->dCursor, &ctx->dObs, &ctx->dStatus, &ctx->dEvents,
+                          &ctx->dEvCount})
+    b->release();
+  delete ctx;
+}
+
+const char *emcgpu_last_error(const emcgpu_ctx *ctx) {
+  return ctx ? ctx->error.c_str() : g_createError.c_str();
+}
+
+int64_t emcgpu_launch_count(const emcgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int emcgpu_set_stream(emcgpu_ctx *ctx, void *cudaStream) {
+  if (!ctx) return EMCGPU_E_INVALID;
+  ctx->stream = static_cast<cudaStream_t>(cudaStream);
+  return EMCGPU_OK;
+}
+
+int emcgpu_synchronize(emcgpu_ctx *ctx) {
+  if (!ctx) return EMCGPU_E_INVALID;
+  if (int r = bind(ctx)) return r;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return EMCGPU_OK;
+}
+
+int emcgpu_set_valleys(emcgpu_ctx *ctx, const emcgpu_valley_t *valleys, int nValleys) {
+  if (!ctx) return EMCGPU_E_INVALID;
+  if (!valleys || nValleys < 1) return fail(ctx, EMCGPU_E_INVALID, "need at least one valley");
+  if (nValleys > EMCGPU_MAX_VALLEYS)
+    return fail(ctx, EMCGPU_E_CAPACITY, "%d valleys exceed EMCGPU_MAX_VALLEYS=%d", nValleys, EMCGPU_MAX_VALLEYS);
+  if (int r = bind(ctx)) return r;
+  DevModel &M = ctx->hModel;
+  M.nValleys = nValleys;
+  for (int i = 0; i < nValleys; i++) {
+    const emcgpu_valley_t &in = valleys[i];
+    if (in.kind < 0 || in.kind > EMCGPU_VALLEY_NONPARABOLIC_ANISOTROP)
+      return fail(ctx, EMCGPU_E_UNSUPPORTED_VALLEY, "valley %d: unknown valley class %d", i, in.kind);
+    if (in.degeneracy < 1 || in.degeneracy > EMCGPU_MAX_SUBVALLEYS)
+      return fail(ctx, EMCGPU_E_CAPACITY, "valley %d: degeneracy %d outside [1,%d]", i, in.degeneracy,
+                  EMCGPU_MAX_SUBVALLEYS);
+    if (!(in.effMassCond > 0) || in.alpha < 0)
+      return fail(ctx, EMCGPU_E_INVALID, "valley %d: effective mass must be > 0 and alpha >= 0", i);
+    DevValley &v = M.valleys[i];
+    memset(&v, 0, sizeof v);
+    v.kind = in.kind;
+    v.deg = in.degeneracy;
+    v.nonParabolic = in.kind & 1;
+    v.mCond = in.effMassCond;
+    v.alpha = v.nonParabolic ? in.alpha : 0.0;
+    v.eBottom = in.bottomEnergy;
+    const bool aniso = in.kind >= EMCGPU_VALLEY_PARABOLIC_ANISOTROP;
+    for (int d = 0; d < 3; d++) v.vogt[d] = aniso ? in.vogt[d] : 1.0;
+    v.xMq = v.mCond * kQ;
+    v.xTwoMq = 2 * v.mCond * kQ;
+    v.fE = v.nonParabolic ? kHbar * kHbar / (v.mCond * kQ) : kHbar * kHbar / (2 * v.mCond * kQ);
+    for (int d = 0; d < 3; d++) {
+      v.fPos[d] = kHbar * v.vogt[d] / (2 * v.mCond);
+      v.fVel[d] = kHbar * v.vogt[d] / v.mCond;
+      v.fDk[d] = v.vogt[d] / kHbar;
+    }
+    int worst = ROT_IDENTITY;
+    for (int s = 0; s < EMCGPU_MAX_SUBVALLEYS; s++) {
+      double ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+      const double *r = (aniso && s < in.degeneracy) ? in.rot[s] : ident;
+      memcpy(v.rot[s], r, sizeof ident);
+      const int kind = classifyRotation(r, &v.permToE[s], &v.permToD[s]);
+      if (kind > worst) worst = kind;
+    }
+    v.rotKind = worst;
+  }
+  ctx->haveValleys = true;
+  if (ctx->haveTables) CUDA_TRY(ctx, uploadModel(ctx));
+  return EMCGPU_OK;
+}
+
+int emcgpu_set_tables(emcgpu_ctx *ctx, const emcgpu_tableset_t *sets, int nSets, int nLevels,
+                      double maxEnergy) {
+  if (!ctx) return EMCGPU_E_INVALID;
+  if (!ctx->haveValleys) return fail(ctx, EMCGPU_E_INVALID, "call emcgpu_set_valleys before emcgpu_set_tables");
+  if (nSets < 0 || (nSets > 0 && !sets) || nLevels < 1 || !(maxEnergy > 0))
+    return fail(ctx, EMCGPU_E_INVALID, "bad table arguments");
+  if (nSets > EMCGPU_MAX_TABLESETS)
+    return fail(ctx, EMCGPU_E_CAPACITY, "%d table sets exceed EMCGPU_MAX_TABLESETS=%d", nSets,
+                EMCGPU_MAX_TABLESETS);
+  if (int r = bind(ctx)) return r;
+  DevModel &M = ctx->hModel;
+  M.nSets = nSets;
+  M.nLevels = nLevels;
+  M.dE = maxEnergy / nLevels;
+  M.defaultTau = 2e-15;
+  M.nRegions = 0;
+  memset(M.setOf, -1, sizeof M.setOf);
+  std::vector<DevMech> mechs;
+  std::vector<double> tables;
+  for (int i = 0; i < nSets; i++) {
+    const emcgpu_tableset_t &in = sets[i];
+    if (in.valley < 0 || in.valley >= M.nValleys)
+      return fail(ctx, EMCGPU_E_INVALID, "table set %d: valley %d does not exist", i, in.valley);
+    if (in.region < 0 || in.region >= kMaxRegions)
+      return fail(ctx, EMCGPU_E_CAPACITY, "table set %d: region %d outside [0,%d)", i, in.region, kMaxRegions);
+    if (in.nMech < 1 || in.nMech > EMCGPU_MAX_MECH_PER_SET)
+      return fail(ctx, EMCGPU_E_CAPACITY, "table set %d: %d mechanisms outside [1,%d]", i, in.nMech,
+                  EMCGPU_MAX_MECH_PER_SET);
+    if (!in.cum || !in.mech) return fail(ctx, EMCGPU_E_INVALID, "table set %d: NULL tables", i);
+    if (M.setOf[in.valley][in.region] >= 0)
+      return fail(ctx, EMCGPU_E_INVALID, "duplicate table set for valley %d region %d", in.valley, in.region);
+    M.setOf[in.valley][in.region] = (int8_t)i;
+    if (in.region + 1 > M.nRegions) M.nRegions = in.region + 1;
+    DevTableSet &ts = M.sets[i];
+    ts.nMech = in.nMech;
+    ts.stride = (in.nMech + 1) & ~1;
+    ts.tabOffset = (int32_t)tables.size();
+    ts.mechOffset = (int32_t)mechs.size();
+    ts.tau = in.tau;
+    // transpose to level-major rows so that one selection touches one short row
+    tables.resize(tables.size() + (size_t)nLevels * ts.stride, 2.0 /* padding: never selected */);
+    for (int m = 0; m < in.nMech; m++)
+      for (int l = 0; l < nLevels; l++)
+        tables[ts.tabOffset + (size_t)l * ts.stride + m] = in.cum[(size_t)m * nLevels + l];
+    for (int m = 0; m < in.nMech; m++) {
+      const emcgpu_mech_t &mi = in.mech[m];
+      char name[EMCGPU_NAME_LEN + 1];
+      memcpy(name, mi.name, EMCGPU_NAME_LEN);
+      name[EMCGPU_NAME_LEN] = 0;
+      if (mi.sampler <= EMCGPU_SAMPLER_NONE || mi.sampler > EMCGPU_SAMPLER_COULOMB)
+        return fail(ctx, EMCGPU_E_UNSUPPORTED_MECHANISM,
+                    "scatter mechanism '%s' (valley %d, region %d) has no device sampler; it cannot run on "
+                    "the GPU path and there is no CPU fallback",
+                    name, in.valley, in.region);
+      DevMech d;
+      memset(&d, 0, sizeof d);
+      d.sampler = mi.sampler;
+      d.finalValley = mi.finalValley;
+      d.nFinal = mi.nFinal;
+      d.mechId = mi.mechId;
+      d.param[0] = mi.param[0];
+      d.param[1] = mi.param[1];
+      if (mi.sampler == EMCGPU_SAMPLER_INTERVALLEY) {
+        if (mi.finalValley < 0 || mi.finalValley >= M.nValleys)
+          return fail(ctx, EMCGPU_E_INVALID, "mechanism '%s': final valley %d does not exist", name, mi.finalValley);
+        if (mi.nFinal < 1 || mi.nFinal > EMCGPU_MAX_FINAL)
+          return fail(ctx, EMCGPU_E_CAPACITY, "mechanism '%s': %d final sub-valleys outside [1,%d]", name,
+                      mi.nFinal, EMCGPU_MAX_FINAL);
+        const int degF = M.valleys[mi.finalValley].deg;
+        for (int s = 0; s < M.valleys[in.valley].deg; s++)
+          for (int f = 0; f < mi.nFinal; f++)
+            if (mi.finalSub[s][f] >= degF)
+              return fail(ctx, EMCGPU_E_INVALID, "mechanism '%s': final sub-valley %d >= degeneracy %d", name,
+                          mi.finalSub[s][f], degF);
+        memcpy(d.finalSub, mi.finalSub, sizeof d.finalSub);
+      }
+      mechs.push_back(d);
+    }
+  }
+  if (tables.empty()) tables.resize(2, 2.0);
+  M.tableDoubles = (int64_t)tables.size();
+  ctx->hMechs = mechs;
+  CUDA_TRY(ctx, ctx->dTables.ensure(tables.size() * sizeof(double)));
+  CUDA_TRY(ctx, ctx->dMechs.ensure(std::max<size_t>(1, mechs.size()) * sizeof(DevMech)));
+  // synchronous copies: the staging vectors die at the end of this call
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpy(ctx->dTables.ptr, tables.data(), tables.size() * sizeof(double), cudaMemcpyHostToDevice));
+  if (!mechs.empty())
+    CUDA_TRY(ctx, cudaMemcpy(ctx->dMechs.ptr, mechs.data(), mechs.size() * sizeof(DevMech), cudaMemcpyHostToDevice));
+  ctx->haveTables = true;
+  CUDA_TRY(ctx, uploadModel(ctx));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return EMCGPU_OK;
+}
+
+int emcgpu_set_ensemble(emcgpu_ctx *ctx, int64_t n, const double *const *soa, const uint32_t *packed,
+                        int64_t particleIdBase) {
+  if (!ctx) return EMCGPU_E_INVALID;
+  if (n < 0 || (n > 0 && (!soa || !packed))) return fail(ctx, EMCGPU_E_INVALID, "bad ensemble arguments");
+  if (int r = bind(ctx)) return r;
+  ctx->idBase = particleIdBase;
+  if (n == 0) {
+    ctx->n = 0;
+    return EMCGPU_OK;
+  }
+  if (int r = allocEnsemble(ctx, n)) return r;
+  for (int s = 0; s < EMCGPU_N_STREAMS; s++) {
+    if (!soa[s]) return fail(ctx, EMCGPU_E_INVALID, "stream %d is NULL", s);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dStream[s], soa[s], n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dPacked, packed, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (ctx->rngMode == RNG_REPLAY) ctx->rngMode = RNG_PHILOX; // replay streams belong to the old ensemble
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return EMCGPU_OK;
+}
+
+int emcgpu_get_ensemble(emcgpu_ctx *ctx, double *const *soa, uint32_t *packed) {
+  if (!ctx) return EMCGPU_E_INVALID;
+  if (int r = bind(ctx)) return r;
+  if (ctx->n == 0) return EMCGPU_OK;
+  if (!soa) return fail(ctx, EMCGPU_E_INVALID, "soa is NULL");
+  for (int s = 0; s < EMCGPU_N_STREAMS; s++)
+    if (soa[s])
+      CUDA_TRY(ctx, cudaMemcpyAsync(soa[s], ctx->dStream[s], ctx->n * sizeof(double), cudaMemcpyDeviceToHost,
+                                    ctx->stream));
+  if (packed)
+    CUDA_TRY(ctx, cudaMemcpyAsync(packed, ctx->dPacked, ctx->n * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return EMCGPU_OK;
+}
+
+int64_t emcgpu_ensemble_size(const emcgpu_ctx *ctx) { return ctx ? ctx->n : 0; }
+
+int emcgpu_ensemble_device_ptrs(emcgpu_ctx *ctx, double **soaOut, uint32_t **packedOut) {
+  if (!ctx || !soaOut) return EMCGPU_E_INVALID;
+  for (int s = 0; s < EMCGPU_N_STREAMS; s++) soaOut[s] = ctx->dStream[s];
+  if (packedOut) *packedOut = ctx->dPacked;
+  return EMCGPU_OK;
+}
+
+int emcgpu_generate_bulk_ensemble(emcgpu_ctx *ctx, int64_t n, const double box[3], double temperature,
+                                  int32_t region, uint64_t seed, int64_t particleIdBase) {
+  if (!ctx) return EMCGPU_E_INVALID;
+  if (!ctx->haveValleys || !ctx->haveTables)
+    return fail(ctx, EMCGPU_E_INVALID, "set valleys and tables before generating an ensemble");
+  if (n < 1 || !box || !(temperature > 0)) return fail(ctx, EMCGPU_E_INVALID, "bad arguments");
+  if (int r = bind(ctx)) return r;
+  if (int r = allocEnsemble(ctx, n)) return r;
+  ctx->idBase = particleIdBase;
+  GenParams G;
+  memset(&G, 0, sizeof G);
+  for (int s = 0; s < EMCGPU_N_STREAMS; s++) G.stream[s] = ctx->dStream[s];
+  G.packed = ctx->dPacked;
+  G.n = n;
+  G.idBase = particleIdBase;
+  G.model = static_cast<const DevModel *>(ctx->dModel.ptr);
+  G.box = Vec3{box[0], box[1], box[2]};
+  G.thermalVoltage = kKB / kQ * temperature; // emcDevice.hpp:87
+  G.region = region;
+  G.seed = seed;
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->smCount * 16);
+  bulkGenerateKernel<<<grid, 256, 0, ctx->stream>>>(G);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  if (ctx->rngMode == RNG_REPLAY) ctx->rngMode = RNG_PHILOX;
+  return EMCGPU_OK;
+}
+
+int emcgpu_rng_philox(emcgpu_ctx *ctx, uint64_t seed) {
+  if (!ctx) return EMCGPU_E_INVALID;
+  ctx->rngMode = RNG_PHILOX;
+  ctx->seed = seed;
+  return EMCGPU_OK;
+}
+
+int emcgpu_rng_replay(emcgpu_ctx *ctx, const uint64_t *draws, const int64_t *offsets, int64_t n) {
+  if (!ctx) return EMCGPU_E_INVALID;
+  if (!draws || !offsets || n != ctx->n)
+    return fail(ctx, EMCGPU_E_INVALID, "replay streams must cover exactly the %lld uploaded particles",
+                (long long)ctx->n);
+  if (int r = bind(ctx)) return r;
+  const int64_t total = offsets[n];
+  CUDA_TRY(ctx, ctx->dDraws.ensure(std::max<int64_t>(1, total) * sizeof(uint64_t)));
+  CUDA_TRY(ctx, ctx->dOffsets.ensure((n + 1) * sizeof(int64_t)));
+  CUDA_TRY(ctx, ctx->dCursor.ensure(n * sizeof(uint32_t)));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (total > 0) CUDA_TRY(ctx, cudaMemcpy(ctx->dDraws.ptr, draws, total * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  CUDA_TRY(ctx, cudaMemcpy(ctx->dOffsets.ptr, offsets, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+  CUDA_TRY(ctx, cudaMemset(ctx->dCursor.ptr, 0, n * sizeof(uint32_t)));
+  ctx->rngMode = RNG_REPLAY;
+  return EMCGPU_OK;
+}
+
+int emcgpu_bulk_configure(emcgpu_ctx *ctx, const double box[3], const double fieldDirection[3],
+                          double fieldStrength, double charge, int mathMode) {
+  if (!ctx) return EMCGPU_E_INVALID;
+  if (!box || !fieldDirection) return fail(ctx, EMCGPU_E_INVALID, "NULL argument");
+  if (mathMode != EMCGPU_MATH_EXACT && mathMode != EMCGPU_MATH_FAST)
+    return fail(ctx, EMCGPU_E_INVALID, "unknown math mode %d", mathMode);
+  for (int d = 0; d < 3; d++)
+    if (!(box[d] > 0)) return fail(ctx, EMCGPU_E_INVALID, "box extent must be positive");
+  // basicBulkParticleHandler ctor (:100-102): normalize(dir); field = dir*strength
+  double dir[3] = {fieldDirection[0], fieldDirection[1], fieldDirection[2]};
+  double sq = 0;
+  for (int d = 0; d < 3; d++) sq += dir[d] * dir[d];
+  const double nrm = std::sqrt(sq);
+  if (nrm != 0)
+    for (int d = 0; d < 3; d++) dir[d] /= nrm;
+  ctx->box = Vec3{box[0], box[1], box[2]};
+  ctx->dir = Vec3{dir[0], dir[1], dir[2]};
+  // moveParticles (:186): force = scale(appliedField, charge)
+  ctx->force = Vec3{dir[0] * fieldStrength * charge, dir[1] * fieldStrength * charge,
+                    dir[2] * fieldStrength * charge};
+  ctx->mathMode = mathMode;
+  ctx->bulkConfigured = true;
+  return EMCGPU_OK;
+}
+
+int emcgpu_set_step_index(emcgpu_ctx *ctx, int64_t nextStep) {
+  if (!ctx) return EMCGPU_E_INVALID;
+  ctx->nextStep = nextStep;
+  return EMCGPU_OK;
+}
+int64_t emcgpu_get_step_index(const emcgpu_ctx *ctx) { return ctx ? ctx->nextStep : 0; }
+
+int emcgpu_bulk_step_device(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPerLaunch, double *obsDevice) {
+  if (int r = checkReady(ctx, true)) return r;
+  if (!(dt > 0) || nSteps < 1 || !obsDevice) return fail(ctx, EMCGPU_E_INVALID, "bad step arguments");
+  if (int r = bind(ctx)) return r;
+  if (stepsPerLaunch < 1) stepsPerLaunch = 1;
+  if (stepsPerLaunch > kMaxStepsPerLaunch) stepsPerLaunch = kMaxStepsPerLaunch;
+  const int nV = ctx->hModel.nValleys;
+  CUDA_TRY(ctx, cudaMemsetAsync(obsDevice, 0, (size_t)nSteps * nV * 3 * sizeof(double), ctx->stream));
+  BulkParams P;
+  fillBulkParams(ctx, P);
+  P.dt = dt;
+  const int blocksNeeded = (int)std::min<int64_t>((ctx->n + kBulkThreads - 1) / kBulkThreads, 1 << 30);
+  for (int done = 0; done < nSteps;) {
+    const int chunk = std::min(stepsPerLaunch, nSteps - done);
+    P.nSteps = chunk;
+    P.step0 = ctx->nextStep + done;
+    P.obs = obsDevice + (size_t)done * nV * 3;
+    bool inSmem = true;
+    size_t smem = bulkSmemBytes(ctx, chunk, true);
+    if (smem > (size_t)ctx->maxSmemOptin) {
+      inSmem = false;
+      smem = bulkSmemBytes(ctx, chunk, false);
+      if (smem > (size_t)ctx->maxSmemOptin)
+        return fail(ctx, EMCGPU_E_CAPACITY, "model does not fit in shared memory (%zu bytes)", smem);
+    }
+    P.tablesInSmem = inSmem ? 1 : 0;
+    // persistent grid: as many CTAs as can be resident (2 per SM by launch
+    // bounds, fewer if the tables are large), never more than the work needs
+    int perSm = (int)std::min<size_t>(2, (size_t)(ctx->maxSmemOptin + 1024) / (smem + 1024));
+    if (perSm < 1) perSm = 1;
+    const int grid = std::max(1, std::min(blocksNeeded, ctx->smCount * perSm));
+    cudaError_t e;
+    const bool exact = ctx->mathMode == EMCGPU_MATH_EXACT;
+    if (ctx->rngMode == RNG_PHILOX)
+      e = exact ? launchBulk<true, RNG_PHILOX>(ctx, P, smem, grid) : launchBulk<false, RNG_PHILOX>(ctx, P, smem, grid);
+    else
+      e = exact ? launchBulk<true, RNG_REPLAY>(ctx, P, smem, grid) : launchBulk<false, RNG_REPLAY>(ctx, P, smem, grid);
+    if (e != cudaSuccess) return fail(ctx, EMCGPU_E_CUDA, "bulk step launch failed: %s", cudaGetErrorString(e));
+    done += chunk;
+  }
+  ctx->nextStep += nSteps;
+  return EMCGPU_OK;
+}
+
+int emcgpu_bulk_step(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPerLaunch, double *obs) {
+  if (int r = checkReady(ctx, true)) return r;
+  if (nSteps < 1) return fail(ctx, EMCGPU_E_INVALID, "nSteps must be >= 1");
+  if (int r = bind(ctx)) return r;
+  const size_t bytes = (size_t)nSteps * ctx->hModel.nValleys * 3 * sizeof(double);
+  CUDA_TRY(ctx, ctx->dObs.ensure(bytes));
+  if (int r = emcgpu_bulk_step_device(ctx, dt, nSteps, stepsPerLaunch, static_cast<double *>(ctx->dObs.ptr)))
+    return r;
+  if (obs) CUDA_TRY(ctx, cudaMemcpyAsync(obs, ctx->dObs.ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return checkStatusWord(ctx); // synchronises
+}
+
+int emcgpu_bulk_observables(emcgpu_ctx *ctx, double *obs) {
+  if (int r = checkReady(ctx, true)) return r;
+  if (!obs) return fail(ctx, EMCGPU_E_INVALID, "obs is NULL");
+  if (int r = bind(ctx)) return r;
+  const size_t bytes = (size_t)ctx->hModel.nValleys * 3 * sizeof(double);
+  CUDA_TRY(ctx, ctx->dObs.ensure(bytes));
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->dObs.ptr, 0, bytes, ctx->stream));
+  BulkParams P;
+  fillBulkParams(ctx, P);
+  P.obs = static_cast<double *>(ctx->dObs.ptr);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ctx->n + kBulkThreads - 1) / kBulkThreads,
+                                                                (int64_t)ctx->smCount * 8));
+  if (ctx->mathMode == EMCGPU_MATH_EXACT)
+    bulkObservablesKernel<true><<<grid, kBulkThreads, 0, ctx->stream>>>(P);
+  else
+    bulkObservablesKernel<false><<<grid, kBulkThreads, 0, ctx->stream>>>(P);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaMemcpyAsync(obs, ctx->dObs.ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return EMCGPU_OK;
+}
+
+int emcgpu_event_log_enable(emcgpu_ctx *ctx, int64_t capacity) {
+  if (!ctx || capacity < 0) return EMCGPU_E_INVALID;
+  if (int r = bind(ctx)) return r;
+  if (capacity > 0) CUDA_TRY(ctx, ctx->dEvents.ensure((size_t)capacity * 4 * sizeof(long long)));
+  ctx->evCap = capacity;
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->dEvCount.ptr, 0, sizeof(unsigned long long), ctx->stream));
+  return EMCGPU_OK;
+}
+
+int64_t emcgpu_event_log_read(emcgpu_ctx *ctx, int64_t *out, int64_t capacity) {
+  if (!ctx) return -1;
+  if (bind(ctx)) return -1;
+  unsigned long long count = 0;
+  if (cudaMemcpyAsync(&count, ctx->dEvCount.ptr, sizeof count, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+      cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    fail(ctx, EMCGPU_E_CUDA, "cannot read the event counter");
+    return -1;
+  }
+  const int64_t have = std::min<int64_t>((int64_t)count, std::min(capacity, ctx->evCap));
+  if (have > 0 && out) {
+    if (cudaMemcpy(out, ctx->dEvents.ptr, (size_t)have * 4 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) {
+      fail(ctx, EMCGPU_E_CUDA, "cannot read the event log");
+      return -1;
+    }
+  }
+  cudaMemsetAsync(ctx->dEvCount.ptr, 0, sizeof(unsigned long long), ctx->stream);
+  return (int64_t)count;
+}
+
+} // extern "C"
