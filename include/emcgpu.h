@@ -150,6 +150,9 @@ int64_t emcgpu_launch_count(const emcgpu_ctx *ctx);
 /* run all later work of ctx on this cudaStream_t (NULL = default stream) */
 int emcgpu_set_stream(emcgpu_ctx *ctx, void *cudaStream);
 int emcgpu_synchronize(emcgpu_ctx *ctx);
+/* tuning knobs (no effect on results): "vec" = particles per lane and loop
+ * iteration of the one-step kernel (1, 2 or 4; default 2) */
+int emcgpu_set_option(emcgpu_ctx *ctx, const char *name, int64_t value);
 
 /* ---- physics model (built on the host by the reference-compatible API) - */
 /* replaces the per-particle virtual calls into emcParticleType::valleys

@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--math", type=int, default=1)
     ap.add_argument("--dt", type=float, default=1e-16)
+    ap.add_argument("--vec", type=int, nargs="+", default=[2])
+    ap.add_argument("--settle", type=int, default=0, help="untimed steps (fused) to leave the initial transient")
     args = ap.parse_args()
     import torch
     m = build_si()
@@ -33,7 +35,12 @@ def main():
         ctx.rng_philox(5)
         ctx.bulk_configure(box, [-1, 0, 0], 1e6, math_mode=args.math)
         obs = torch.zeros(args.steps * 3, dtype=torch.float64, device="cuda")
-        for spl in args.spl:
+        if args.settle:
+            obs0 = torch.zeros(args.settle * 3, dtype=torch.float64, device="cuda")
+            ctx.bulk_step_device(args.dt, args.settle, 16, obs0.data_ptr())
+        for spl, vec in [(s, v) for s in args.spl for v in (args.vec if s == 1 else [0])]:
+            if vec:
+                ctx.set_option("vec", vec)
             ctx.bulk_step_device(args.dt, args.steps, spl, obs.data_ptr())  # warm-up
             ctx.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -45,7 +52,7 @@ def main():
             rate = n * args.steps / (ms * 1e-3)
             launches = (args.steps + spl - 1) // spl
             gbs = 136.0 * n * launches / (ms * 1e-3) / 1e9
-            print(f"n={n:>10} spl={spl:>3} steps={args.steps} {ms:9.3f} ms  {rate:.3e} p-steps/s  "
+            print(f"n={n:>10} spl={spl:>3} vec={vec} steps={args.steps} {ms:9.3f} ms  {rate:.3e} p-steps/s  "
                   f"state traffic {gbs:8.1f} GB/s ({gbs/6555.8*100:5.1f}% of measured HBM peak)", flush=True)
         ctx.close()
 

@@ -72,6 +72,7 @@ def load():
     L.emcgpu_launch_count.restype = C.c_int64
     L.emcgpu_set_stream.argtypes = [vp, vp]
     L.emcgpu_synchronize.argtypes = [vp]
+    L.emcgpu_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.emcgpu_set_valleys.argtypes = [vp, C.POINTER(ValleyC), C.c_int]
     L.emcgpu_set_tables.argtypes = [vp, C.POINTER(TableSetC), C.c_int, C.c_int, C.c_double]
     L.emcgpu_set_ensemble.argtypes = [vp, C.c_int64, C.POINTER(_DP), C.POINTER(C.c_uint32), C.c_int64]
@@ -98,7 +99,7 @@ def load():
 
 EXPORTED_SYMBOLS = [
     "emcgpu_abi_version", "emcgpu_create", "emcgpu_destroy", "emcgpu_last_error", "emcgpu_launch_count",
-    "emcgpu_set_stream", "emcgpu_synchronize", "emcgpu_set_valleys", "emcgpu_set_tables", "emcgpu_set_ensemble",
+    "emcgpu_set_stream", "emcgpu_synchronize", "emcgpu_set_option", "emcgpu_set_valleys", "emcgpu_set_tables", "emcgpu_set_ensemble",
     "emcgpu_get_ensemble", "emcgpu_ensemble_size", "emcgpu_generate_bulk_ensemble",
     "emcgpu_ensemble_device_ptrs", "emcgpu_rng_philox", "emcgpu_rng_replay", "emcgpu_bulk_configure",
     "emcgpu_bulk_step", "emcgpu_bulk_step_device", "emcgpu_bulk_observables", "emcgpu_set_step_index",
@@ -247,6 +248,9 @@ class Context:
 
     def set_stream(self, cuda_stream_ptr):
         self._chk(self.L.emcgpu_set_stream(self.h, cuda_stream_ptr))
+
+    def set_option(self, name, value):
+        self._chk(self.L.emcgpu_set_option(self.h, name.encode(), int(value)))
 
     def synchronize(self):
         self._chk(self.L.emcgpu_synchronize(self.h))

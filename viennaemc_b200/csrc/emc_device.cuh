@@ -279,6 +279,104 @@ __device__ __forceinline__ void drift(const DevValley &v, Particle &p, double dt
   if constexpr (DIM > 2) p.pos.z = A::add(p.pos.z, d.z);
 }
 
+// ---------------------------------------------------------------------------
+// FAST-mode full-dt free flight (the >= 98 % case: tau >= dt, no scattering).
+// Because the field is uniform and the rotations are linear, the Herring-Vogt
+// update of emcParticleDrift.hpp:12-36 collapses, per (valley, sub-valley), to
+//   k'   = k + dk                       dk = R^T diag(vogt/hbar) R F dt
+//   E'   = g / (1 + S)                  g = hbar^2 |k'|^2/(m q), S = sqrt(1 + 2 a g)
+//   pos' = pos + M (k' + k) dt / S      M = R^T diag(hbar vogt/(2 m)) R ; 1 + 2 a E' == S
+//   v.Ê  = (c . k') / S                 c = R^T diag(hbar vogt/m) R Ê
+// (parabolic valleys: a = 0, S = 1).  The constants are rebuilt by every CTA at
+// kernel start from the valley description; one reciprocal square root and one
+// reciprocal replace the reference's sqrt + 5 divisions.
+struct FastSub {
+  double dk[3];
+  double m[9];
+  double c[3];
+};
+struct FastValley {
+  double fE;  // hbar^2/(m q)
+  double c2a; // 2 alpha fE
+  int32_t diag, pad;
+};
+
+__device__ __forceinline__ void buildFastSub(const DevValley &v, int s, const Vec3 &force, const Vec3 &dir,
+                                             double dt, FastSub &o) {
+  const double *r = v.rot[s];
+  const double f[3] = {force.x, force.y, force.z}, d[3] = {dir.x, dir.y, dir.z};
+  double fe[3], de[3];
+  for (int i = 0; i < 3; i++) {
+    fe[i] = (r[3 * i] * f[0] + r[3 * i + 1] * f[1] + r[3 * i + 2] * f[2]) * v.fDk[i] * dt;
+    de[i] = (r[3 * i] * d[0] + r[3 * i + 1] * d[1] + r[3 * i + 2] * d[2]) * v.fVel[i];
+  }
+  for (int a = 0; a < 3; a++) {
+    o.dk[a] = r[a] * fe[0] + r[3 + a] * fe[1] + r[6 + a] * fe[2];
+    o.c[a] = r[a] * de[0] + r[3 + a] * de[1] + r[6 + a] * de[2];
+    for (int b = 0; b < 3; b++)
+      o.m[3 * a + b] = r[a] * v.fPos[0] * r[b] + r[3 + a] * v.fPos[1] * r[3 + b] + r[6 + a] * v.fPos[2] * r[6 + b];
+  }
+}
+
+// 1/sqrt(x) and 1/x for x in the normal range, without the special-case
+// branches of the library versions: MUFU seed (reads the high word only,
+// ~2^-20) + one cubic Newton step (-> ~2^-60 before rounding).
+__device__ __forceinline__ double rsqrtNormal(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-(x * y), y, 1.0); // 1 - x y^2
+  const double t = fma(0.375, e, 0.5) * e;
+  return fma(y, t, y);
+}
+__device__ __forceinline__ double rcpNormal(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x, y, 1.0);
+  const double t = fma(e, e, e);
+  return fma(y, t, y);
+}
+
+// One whole time step of a particle that does not scatter (tau >= dt):
+// drift(dt), periodic wrap, tau -= dt; returns v.Ê for the drift-velocity
+// observable (basicBulkParticleHandler.hpp:195-213, :326-347).
+__device__ __forceinline__ double fastStep(const FastSub &fs, const FastValley &fv, double dt, const Vec3 &box,
+                                           double &kx, double &ky, double &kz, double &energy, double &tau,
+                                           double &px, double &py, double &pz) {
+  const double nx = kx + fs.dk[0], ny = ky + fs.dk[1], nz = kz + fs.dk[2];
+  const double sq = fma(nz, nz, fma(ny, ny, nx * nx));
+  const double g = fv.fE * sq;
+  const double x = fma(fv.c2a, sq, 1.0);
+  const double r = rsqrtNormal(x); // 1/S
+  const double d = fma(x, r, 1.0); // 1 + S
+  const double y = rcpNormal(d);
+  double e = g * y;
+  e = fma(fma(-d, e, g), y, e);
+  const double w = dt * r;
+  const double sx = (nx + kx) * w, sy = (ny + ky) * w, sz = (nz + kz) * w;
+  double dx, dy, dz;
+  if (fv.diag) {
+    dx = fs.m[0] * sx;
+    dy = fs.m[4] * sy;
+    dz = fs.m[8] * sz;
+  } else {
+    dx = fma(fs.m[2], sz, fma(fs.m[1], sy, fs.m[0] * sx));
+    dy = fma(fs.m[5], sz, fma(fs.m[4], sy, fs.m[3] * sx));
+    dz = fma(fs.m[8], sz, fma(fs.m[7], sy, fs.m[6] * sx));
+  }
+  px += dx;
+  py += dy;
+  pz += dz;
+  px += px < 0.0 ? box.x : (px > box.x ? -box.x : 0.0);
+  py += py < 0.0 ? box.y : (py > box.y ? -box.y : 0.0);
+  pz += pz < 0.0 ? box.z : (pz > box.z ? -box.z : 0.0);
+  kx = nx;
+  ky = ny;
+  kz = nz;
+  energy = e;
+  tau -= dt;
+  return fma(fs.c[2], nz, fma(fs.c[1], ny, fs.c[0] * nx)) * r;
+}
+
 // periodic wrap of the bulk handler (basicBulkParticleHandler.hpp:600-613)
 template <bool EXACT> __device__ __forceinline__ double wrap1(double x, double maxPos) {
   using A = Arith<EXACT>;

@@ -43,6 +43,8 @@ struct emcgpu_ctx {
   int device = 0;
   int smCount = 0;
   int maxSmemOptin = 0;
+  int maxSmemPerSm = 0;
+  int optVec = 2; // particles per lane and iteration of the streaming step kernel (1, 2, 4)
   cudaStream_t stream = nullptr;
   std::string error;
   int64_t launches = 0;
@@ -137,14 +139,10 @@ cudaError_t uploadModel(emcgpu_ctx *ctx) {
   return cudaMemcpyAsync(ctx->dModel.ptr, &ctx->hModel, sizeof(DevModel), cudaMemcpyHostToDevice, ctx->stream);
 }
 
-size_t bulkSmemBytes(const emcgpu_ctx *ctx, int nSteps, bool tablesInSmem) {
-  size_t off = (sizeof(DevModel) + 15) & ~size_t(15);
-  off += (size_t)nSteps * ctx->hModel.nValleys * 3 * sizeof(double);
-  off = (off + 15) & ~size_t(15);
-  off += ctx->hMechs.size() * sizeof(DevMech);
-  off = (off + 15) & ~size_t(15);
-  if (tablesInSmem) off += (size_t)ctx->hModel.tableDoubles * sizeof(double);
-  return off;
+size_t bulkSmemBytes(const emcgpu_ctx *ctx, int nObsDoubles, bool tablesInSmem, int queueWords) {
+  return BulkSmem(nObsDoubles, ctx->hModel.nValleys, (int)ctx->hMechs.size(), ctx->hModel.tableDoubles, tablesInSmem,
+                  queueWords)
+      .total;
 }
 
 void fillBulkParams(emcgpu_ctx *ctx, BulkParams &P) {
@@ -170,15 +168,34 @@ void fillBulkParams(emcgpu_ctx *ctx, BulkParams &P) {
   P.status = static_cast<int *>(ctx->dStatus.ptr);
 }
 
-template <bool EXACT, int MODE>
-cudaError_t launchBulk(emcgpu_ctx *ctx, const BulkParams &P, size_t smem, int grid) {
-  auto kernel = bulkStepKernel<EXACT, MODE>;
+template <typename K> cudaError_t launchKernel(emcgpu_ctx *ctx, K kernel, const BulkParams &P, size_t smem, int grid) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kernel<<<grid, kBulkThreads, smem, ctx->stream>>>(P);
   ctx->launches++;
   return cudaGetLastError();
 }
+
+// K1b, several steps per launch
+cudaError_t launchFused(emcgpu_ctx *ctx, const BulkParams &P, size_t smem, int grid) {
+  const bool exact = ctx->mathMode == EMCGPU_MATH_EXACT;
+  if (ctx->rngMode == RNG_PHILOX)
+    return exact ? launchKernel(ctx, bulkStepKernel<true, RNG_PHILOX>, P, smem, grid)
+                 : launchKernel(ctx, bulkStepKernel<false, RNG_PHILOX>, P, smem, grid);
+  return exact ? launchKernel(ctx, bulkStepKernel<true, RNG_REPLAY>, P, smem, grid)
+               : launchKernel(ctx, bulkStepKernel<false, RNG_REPLAY>, P, smem, grid);
+}
+
+// K1a, one step per launch
+template <int VEC> cudaError_t launchStreamVec(emcgpu_ctx *ctx, const BulkParams &P, size_t smem, int grid) {
+  const bool exact = ctx->mathMode == EMCGPU_MATH_EXACT;
+  if (ctx->rngMode == RNG_PHILOX)
+    return exact ? launchKernel(ctx, bulkStreamKernel<true, RNG_PHILOX, VEC>, P, smem, grid)
+                 : launchKernel(ctx, bulkStreamKernel<false, RNG_PHILOX, VEC>, P, smem, grid);
+  return exact ? launchKernel(ctx, bulkStreamKernel<true, RNG_REPLAY, VEC>, P, smem, grid)
+               : launchKernel(ctx, bulkStreamKernel<false, RNG_REPLAY, VEC>, P, smem, grid);
+}
+int streamQueueWords(int vec) { return (kBulkThreads / 32) * (32 + 32 * vec); }
 
 int checkReady(emcgpu_ctx *ctx, bool needEnsemble) {
   if (!ctx) return EMCGPU_E_INVALID;
@@ -246,6 +263,7 @@ int emcgpu_create(int cudaDevice, emcgpu_ctx **out) {
   }
   ctx->smCount = prop.multiProcessorCount;
   ctx->maxSmemOptin = (int)prop.sharedMemPerBlockOptin;
+  ctx->maxSmemPerSm = (int)prop.sharedMemPerMultiprocessor;
   if ((e = ctx->dStatus.ensure(sizeof(int))) != cudaSuccess ||
       (e = ctx->dEvCount.ensure(sizeof(unsigned long long))) != cudaSuccess ||
       (e = cudaMemset(ctx->dStatus.ptr, 0, sizeof(int))) != cudaSuccess ||
@@ -278,6 +296,16 @@ int emcgpu_set_stream(emcgpu_ctx *ctx, void *cudaStream) {
   if (!ctx) return EMCGPU_E_INVALID;
   ctx->stream = static_cast<cudaStream_t>(cudaStream);
   return EMCGPU_OK;
+}
+
+int emcgpu_set_option(emcgpu_ctx *ctx, const char *name, int64_t value) {
+  if (!ctx || !name) return EMCGPU_E_INVALID;
+  if (!strcmp(name, "vec")) {
+    if (value != 1 && value != 2 && value != 4) return fail(ctx, EMCGPU_E_INVALID, "vec must be 1, 2 or 4");
+    ctx->optVec = (int)value;
+    return EMCGPU_OK;
+  }
+  return fail(ctx, EMCGPU_E_INVALID, "unknown option '%s'", name);
 }
 
 int emcgpu_synchronize(emcgpu_ctx *ctx) {
@@ -574,32 +602,40 @@ int emcgpu_bulk_step_device(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPer
   BulkParams P;
   fillBulkParams(ctx, P);
   P.dt = dt;
-  const int blocksNeeded = (int)std::min<int64_t>((ctx->n + kBulkThreads - 1) / kBulkThreads, 1 << 30);
+  if (ctx->n >= (int64_t)1 << 32) return fail(ctx, EMCGPU_E_CAPACITY, "at most 2^32-1 particles per context");
   for (int done = 0; done < nSteps;) {
     const int chunk = std::min(stepsPerLaunch, nSteps - done);
     P.nSteps = chunk;
     P.step0 = ctx->nextStep + done;
     P.obs = obsDevice + (size_t)done * nV * 3;
+    const bool stream = chunk == 1;
+    const int vec = ctx->optVec;
+    const int queueWords = stream ? streamQueueWords(vec) : 0;
     bool inSmem = true;
-    size_t smem = bulkSmemBytes(ctx, chunk, true);
+    size_t smem = bulkSmemBytes(ctx, chunk * nV * 3, true, queueWords);
     if (smem > (size_t)ctx->maxSmemOptin) {
       inSmem = false;
-      smem = bulkSmemBytes(ctx, chunk, false);
+      smem = bulkSmemBytes(ctx, chunk * nV * 3, false, queueWords);
       if (smem > (size_t)ctx->maxSmemOptin)
         return fail(ctx, EMCGPU_E_CAPACITY, "model does not fit in shared memory (%zu bytes)", smem);
     }
     P.tablesInSmem = inSmem ? 1 : 0;
     // persistent grid: as many CTAs as can be resident (2 per SM by launch
     // bounds, fewer if the tables are large), never more than the work needs
-    int perSm = (int)std::min<size_t>(2, (size_t)(ctx->maxSmemOptin + 1024) / (smem + 1024));
+    int perSm = (int)std::min<size_t>(2, (size_t)(ctx->maxSmemPerSm) / (smem + 1024));
     if (perSm < 1) perSm = 1;
+    const int64_t perCta = (int64_t)kBulkThreads * (stream ? vec : 1);
+    const int blocksNeeded = (int)std::min<int64_t>((ctx->n + perCta - 1) / perCta, 1 << 30);
     const int grid = std::max(1, std::min(blocksNeeded, ctx->smCount * perSm));
     cudaError_t e;
-    const bool exact = ctx->mathMode == EMCGPU_MATH_EXACT;
-    if (ctx->rngMode == RNG_PHILOX)
-      e = exact ? launchBulk<true, RNG_PHILOX>(ctx, P, smem, grid) : launchBulk<false, RNG_PHILOX>(ctx, P, smem, grid);
+    if (!stream)
+      e = launchFused(ctx, P, smem, grid);
+    else if (vec == 1)
+      e = launchStreamVec<1>(ctx, P, smem, grid);
+    else if (vec == 2)
+      e = launchStreamVec<2>(ctx, P, smem, grid);
     else
-      e = exact ? launchBulk<true, RNG_REPLAY>(ctx, P, smem, grid) : launchBulk<false, RNG_REPLAY>(ctx, P, smem, grid);
+      e = launchStreamVec<4>(ctx, P, smem, grid);
     if (e != cudaSuccess) return fail(ctx, EMCGPU_E_CUDA, "bulk step launch failed: %s", cudaGetErrorString(e));
     done += chunk;
   }
