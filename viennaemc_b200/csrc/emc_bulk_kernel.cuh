@@ -47,6 +47,10 @@ struct BulkParams {
 };
 
 constexpr int kBulkThreads = 256;
+#ifndef EMC_STREAM_THREADS
+#define EMC_STREAM_THREADS 256
+#endif
+constexpr int kStreamThreads = EMC_STREAM_THREADS;
 constexpr int kMaxStepsPerLaunch = 64;
 
 // ---- TMA bulk copy global -> shared, completion on an mbarrier ------------
@@ -60,17 +64,24 @@ __device__ __forceinline__ void mbarExpectTx(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ void mbarWait(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ bool mbarTryWait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile("{\n"
                ".reg .pred p;\n"
-               "WAIT_LOOP:\n"
-               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-               "@p bra DONE;\n"
-               "bra WAIT_LOOP;\n"
-               "DONE:\n"
-               "}" ::"r"(smemAddr(bar)),
-               "r"(parity)
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+               "selp.u32 %0, 1, 0, p;\n"
+               "}"
+               : "=r"(ok)
+               : "r"(smemAddr(bar)), "r"(parity)
                : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbarWait(uint64_t *bar, uint32_t parity) {
+  while (!mbarTryWait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void mbarArrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(bar)) : "memory");
 }
 __device__ __forceinline__ void tmaBulkLoad(void *dstSmem, const void *srcGlobal, uint32_t bytes,
                                             uint64_t *bar) {
@@ -78,6 +89,36 @@ __device__ __forceinline__ void tmaBulkLoad(void *dstSmem, const void *srcGlobal
                    smemAddr(dstSmem)),
                "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar))
                : "memory");
+}
+// same with an L2 cache policy (streaming data: evict first)
+__device__ __forceinline__ uint64_t l2EvictFirstPolicy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tmaBulkLoadHint(void *dstSmem, const void *srcGlobal, uint32_t bytes, uint64_t *bar,
+                                                uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smemAddr(dstSmem)),
+      "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar)), "l"(policy)
+      : "memory");
+}
+// TMA bulk copy shared -> global, completion tracked by the issuing thread's bulk groups
+__device__ __forceinline__ void tmaBulkStore(void *dstGlobal, const void *srcSmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dstGlobal), "r"(smemAddr(srcSmem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tmaCommitGroup() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tmaWaitGroupRead() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N> __device__ __forceinline__ void tmaWaitGroup() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fenceProxyAsyncShared() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
 __device__ __forceinline__ double warpSum(double v) {
@@ -254,6 +295,29 @@ __device__ __forceinline__ double bulkParticleStep(const CtaState &C, const Bulk
   return driftVelocity<EXACT>(C.model->valleys[p.valley], p.sub, p.k, p.energy, P.dir);
 }
 
+// Out-of-line copy of the complete step for the rare paths of the pipelined
+// kernel (keeps their register needs away from the streaming loop).
+template <bool EXACT, int RNG_MODE>
+__device__ __noinline__ double bulkParticleStepNI(const CtaState &C, const BulkParams &P, Particle &p, Rng &rng,
+                                                  int64_t particleIndex) {
+  const uint64_t id = (uint64_t)(P.idBase + particleIndex);
+  rng.k0 = (uint32_t)P.seed;
+  rng.k1 = (uint32_t)(P.seed >> 32);
+  rng.idLo = (uint32_t)id;
+  rng.idHi = (uint32_t)(id >> 32);
+  rng.status = P.status;
+  rng.n = 0;
+  rng.step = (uint32_t)P.step0;
+  if constexpr (RNG_MODE == RNG_REPLAY) {
+    rng.stream = P.draws + P.offsets[particleIndex] + P.cursor[particleIndex];
+    rng.streamEnd = P.draws + P.offsets[particleIndex + 1];
+  }
+  const double vd = bulkParticleStep<EXACT, RNG_MODE>(C, P, p, rng, P.idBase + particleIndex, P.step0);
+  if constexpr (RNG_MODE == RNG_REPLAY)
+    P.cursor[particleIndex] = (uint32_t)(rng.stream - (P.draws + P.offsets[particleIndex]));
+  return vd;
+}
+
 // Per-valley partial sums of one warp into the CTA's shared accumulators
 // (basicBulkParticleHandler.hpp:289-347).  Whole warp must call.
 __device__ __forceinline__ void accumulateObsWarp(double *o, int nV, bool live, int valley, double e, double vd) {
@@ -297,6 +361,17 @@ template <int RNG_MODE> __device__ __forceinline__ void attachReplay(const BulkP
     rng.stream = P.draws + P.offsets[i] + P.cursor[i];
     rng.streamEnd = P.draws + P.offsets[i + 1];
   }
+}
+__device__ __forceinline__ void storeParticleState(const BulkParams &P, int64_t i, const Particle &p) {
+  P.stream[EMCGPU_KX][i] = p.k.x;
+  P.stream[EMCGPU_KY][i] = p.k.y;
+  P.stream[EMCGPU_KZ][i] = p.k.z;
+  P.stream[EMCGPU_ENERGY][i] = p.energy;
+  P.stream[EMCGPU_TAU][i] = p.tau;
+  P.stream[EMCGPU_X][i] = p.pos.x;
+  P.stream[EMCGPU_Y][i] = p.pos.y;
+  P.stream[EMCGPU_Z][i] = p.pos.z;
+  P.packed[i] = (uint32_t)p.valley | ((uint32_t)p.sub << 8) | ((uint32_t)p.region << 16);
 }
 template <int RNG_MODE>
 __device__ __forceinline__ void storeParticle(const BulkParams &P, int64_t i, const Particle &p, const Rng &rng) {
@@ -382,12 +457,12 @@ __device__ __noinline__ void processQueued(const CtaState &C, const BulkParams &
 }
 
 template <bool EXACT, int RNG_MODE, int VEC>
-__global__ void __launch_bounds__(kBulkThreads, 2) bulkStreamKernel(const __grid_constant__ BulkParams P) {
+__global__ void __launch_bounds__(kStreamThreads, 2) bulkStreamKernel(const __grid_constant__ BulkParams P) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   __shared__ uint64_t tableBar;
   constexpr int QW = 32 + 32 * VEC;
   const int nV = P.model->nValleys;
-  const CtaState C = stageCta(P, smemRaw, &tableBar, nV * 3, (kBulkThreads / 32) * QW);
+  const CtaState C = stageCta(P, smemRaw, &tableBar, nV * 3, (kStreamThreads / 32) * QW);
   const DevModel &model = *C.model;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t *q = C.queue + warp * QW;
@@ -500,6 +575,407 @@ __global__ void __launch_bounds__(kBulkThreads, 2) bulkStreamKernel(const __grid
       atomicAdd(C.obs + 0, se);
       atomicAdd(C.obs + 1, sv);
       atomicAdd(C.obs + 2, (double)cnt);
+    }
+  }
+  __syncthreads();
+  for (int j = tid; j < nV * 3; j += blockDim.x) {
+    const double v = C.obs[j];
+    if (v != 0.0) atomicAdd(P.obs + j, v);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K1a/TMA: ONE time step per launch as a warp-specialised TMA pipeline, one
+// persistent CTA per SM.
+//
+//   loader warp (1 lane)       tile t -> ring stage t % S:  9 cp.async.bulk loads
+//                              (one per SoA stream, L2 evict-first) completing on
+//                              full[stage], as soon as the stage's previous
+//                              tenant has been stored (freed[stage]).
+//   storer warp (1 lane)       when the consumers are done with a stage
+//                              (done[stage]): 9 cp.async.bulk stores back to the
+//                              same global addresses; publishes how many tiles
+//                              are complete in global memory (storesDone).
+//   10 consumer warps          claim 64-particle sub-tiles dynamically, update
+//                              them in place in shared memory (fastStep), arrive
+//                              on done[stage].
+//   scattering particles       (tau < dt) are copied -- state and all -- into a
+//                              CTA-wide shared-memory event queue and left
+//                              untouched in the tile.  Whenever 32 are queued a
+//                              consumer warp claims the batch, runs the complete
+//                              scattering step with all lanes busy and writes the
+//                              result straight to global memory once the store of
+//                              the tile they came from has completed (so the two
+//                              writes cannot be reordered; the lines are still in
+//                              L2, so no extra DRAM traffic).  Sub-tiles in which
+//                              >= 25 % of the particles scatter (dt >~ tau
+//                              regimes) are processed in place instead.
+//
+// Loads run S-1 tiles ahead of the arithmetic independent of occupancy and
+// register pressure; dynamic sub-tile claiming keeps the pipeline moving while
+// some warp is busy with an event batch.
+constexpr int kTmaConsumerWarps = 10;
+constexpr int kTmaThreads = (kTmaConsumerWarps + 2) * 32; // + loader warp + storer warp
+constexpr int kTile = 256; // particles per tile
+constexpr int kSubTile = 64;
+constexpr int kSubsPerTile = kTile / kSubTile;
+constexpr int kTileBytes = kTile * (EMCGPU_N_STREAMS * 8 + 4);
+constexpr int kQueueCap = 256;
+constexpr int kMaxStages = 8;
+// a claimed sub-tile is at most ceil(warps/subs) tiles ahead of the oldest
+// unfinished one; the ring must be deeper than that for the parity waits to be
+// unambiguous
+constexpr int kMinStages = (kTmaConsumerWarps + kSubsPerTile - 1) / kSubsPerTile + 2;
+constexpr int kDenseEvents = kSubTile / 4;
+
+constexpr int kStoreLag = 6; // bulk stores allowed in flight before their completion is awaited
+
+struct TmaControl {
+  uint64_t full[kMaxStages];
+  uint64_t done[kMaxStages];
+  uint64_t freed[kMaxStages];
+  uint64_t tableBar;
+  unsigned nextSub;
+  unsigned qTail, qHead;
+  unsigned storesDone; // number of this CTA's tiles whose store is complete
+};
+struct EventQueue {
+  double f[EMCGPU_N_STREAMS][kQueueCap];
+  uint32_t w[kQueueCap];
+  uint32_t idx[kQueueCap];
+  uint32_t tile[kQueueCap];
+  uint32_t flag[kQueueCap];
+};
+constexpr int kTmaQueueWords = (int)((sizeof(TmaControl) + sizeof(EventQueue) + 3) / 4);
+
+__host__ __device__ inline size_t tmaRingOffset(const BulkSmem &L) { return (L.total + 127) & ~size_t(127); }
+
+__device__ __forceinline__ void storeCursor(const BulkParams &P, int64_t i, const Rng &rng) {
+  P.cursor[i] = (uint32_t)(rng.stream - (P.draws + P.offsets[i]));
+}
+
+// Scattering step of up to 32 queued particles, all lanes busy.
+template <bool EXACT, int RNG_MODE>
+__device__ __noinline__ void processEventBatch(const CtaState &C, const BulkParams &P, TmaControl *ctl,
+                                               EventQueue *Q, unsigned head, int count) {
+  const int lane = threadIdx.x & 31;
+  const bool active = lane < count;
+  Particle p;
+  Rng rng;
+  double e = 0.0, vd = 0.0;
+  uint32_t idx = 0, tile = 0;
+  p.valley = 0;
+  if (active) {
+    const unsigned pos = head + lane, slot = pos % kQueueCap;
+    const uint32_t epoch = pos / kQueueCap + 1;
+    while (*reinterpret_cast<const volatile uint32_t *>(&Q->flag[slot]) != 2 * epoch - 1) { // full, this epoch
+    }
+    __threadfence_block();
+    p.k = Vec3{Q->f[EMCGPU_KX][slot], Q->f[EMCGPU_KY][slot], Q->f[EMCGPU_KZ][slot]};
+    p.energy = Q->f[EMCGPU_ENERGY][slot];
+    p.tau = Q->f[EMCGPU_TAU][slot];
+    p.pos = Vec3{Q->f[EMCGPU_X][slot], Q->f[EMCGPU_Y][slot], Q->f[EMCGPU_Z][slot]};
+    const uint32_t w = Q->w[slot];
+    idx = Q->idx[slot];
+    tile = Q->tile[slot];
+    __threadfence_block();
+    *const_cast<volatile uint32_t *>(&Q->flag[slot]) = 2 * epoch; // consumed: the slot may be refilled
+    p.valley = w & 0xffu;
+    p.sub = (w >> 8) & 0xffu;
+    p.region = w >> 16;
+    vd = bulkParticleStepNI<EXACT, RNG_MODE>(C, P, p, rng, idx);
+    e = p.energy;
+  }
+  __syncwarp();
+  // the tile this particle sits in is written back unchanged by the storer warp;
+  // our write must come after that store has completed
+  const unsigned newest = __reduce_max_sync(0xffffffffu, tile);
+  while (*reinterpret_cast<volatile unsigned *>(&ctl->storesDone) <= newest) {
+  }
+  __threadfence_block();
+  if (active) storeParticleState(P, idx, p);
+  accumulateObsWarp(C.obs, C.model->nValleys, active, p.valley, e, vd);
+}
+
+template <bool EXACT, int RNG_MODE>
+__global__ void __launch_bounds__(kTmaThreads, 1) bulkTmaKernel(const __grid_constant__ BulkParams P, const int stages) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  const int nV = P.model->nValleys;
+  const BulkSmem L(nV * 3, nV, P.nMechTotal, P.model->tableDoubles, P.tablesInSmem != 0, kTmaQueueWords);
+  TmaControl *ctl = reinterpret_cast<TmaControl *>(smemRaw + L.queue);
+  EventQueue *Q = reinterpret_cast<EventQueue *>(smemRaw + L.queue + sizeof(TmaControl));
+  unsigned char *ring = smemRaw + tmaRingOffset(L);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; s++) {
+      mbarInit(&ctl->full[s], 1);
+      mbarInit(&ctl->done[s], kSubsPerTile);
+      mbarInit(&ctl->freed[s], 1);
+    }
+    ctl->nextSub = 0;
+    ctl->qTail = 0;
+    ctl->qHead = 0;
+    ctl->storesDone = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fenceProxyAsyncShared();
+  }
+  for (int i = tid; i < kQueueCap; i += blockDim.x) Q->flag[i] = 0;
+  const CtaState C = stageCta(P, smemRaw, &ctl->tableBar, nV * 3, kTmaQueueWords); // fences + __syncthreads inside
+  const DevModel &model = *C.model;
+
+  const int64_t nTiles = P.n / kTile;
+  const int myTiles = blockIdx.x < nTiles ? (int)((nTiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  const double dt = P.dt;
+  const bool single = nV == 1;
+  double accE = 0.0, accV = 0.0;
+  unsigned accN = 0;
+
+  if (warp == kTmaConsumerWarps) {
+    // ----------------------------- loader warp -----------------------------
+    if (lane == 0) {
+      const uint64_t pol = l2EvictFirstPolicy();
+      for (int t = 0; t < myTiles; t++) {
+        const int st = t % stages;
+        if (t >= stages) mbarWait(&ctl->freed[st], (t / stages - 1) & 1); // the previous tenant has been stored
+        const int64_t i0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * kTile;
+        unsigned char *dst = ring + (size_t)st * kTileBytes;
+        mbarExpectTx(&ctl->full[st], kTileBytes);
+#pragma unroll
+        for (int c = 0; c < EMCGPU_N_STREAMS; c++)
+          tmaBulkLoadHint(dst + c * kTile * 8, P.stream[c] + i0, kTile * 8, &ctl->full[st], pol);
+        tmaBulkLoadHint(dst + EMCGPU_N_STREAMS * kTile * 8, P.packed + i0, kTile * 4, &ctl->full[st], pol);
+      }
+    }
+  } else if (warp == kTmaConsumerWarps + 1) {
+    // ----------------------------- storer warp -----------------------------
+    if (lane == 0) {
+      for (int t = 0; t < myTiles; t++) {
+        const int st = t % stages;
+        mbarWait(&ctl->done[st], (t / stages) & 1);
+        const int64_t i0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * kTile;
+        const unsigned char *src = ring + (size_t)st * kTileBytes;
+#pragma unroll
+        for (int c = 0; c < EMCGPU_N_STREAMS; c++) tmaBulkStore(P.stream[c] + i0, src + c * kTile * 8, kTile * 8);
+        tmaBulkStore(P.packed + i0, src + EMCGPU_N_STREAMS * kTile * 8, kTile * 4);
+        tmaCommitGroup();
+        tmaWaitGroupRead<0>(); // shared memory has been read: the stage may be reloaded
+        mbarArrive(&ctl->freed[st]);
+        tmaWaitGroup<kStoreLag>(); // all but the kStoreLag newest stores are complete in global memory
+        if (t + 1 > kStoreLag) {
+          asm volatile("fence.proxy.async;" ::: "memory");
+          __threadfence_block();
+          *reinterpret_cast<volatile unsigned *>(&ctl->storesDone) = (unsigned)(t + 1 - kStoreLag);
+        }
+      }
+      tmaWaitGroup<0>();
+      asm volatile("fence.proxy.async;" ::: "memory");
+      __threadfence_block();
+      *reinterpret_cast<volatile unsigned *>(&ctl->storesDone) = (unsigned)myTiles + 1u;
+    }
+  } else {
+    // --------------------------- consumer warps ---------------------------
+    const unsigned ltMask = (1u << lane) - 1u;
+    for (;;) {
+      unsigned q = 0;
+      if (lane == 0) q = atomicAdd(&ctl->nextSub, 1u);
+      q = __shfl_sync(0xffffffffu, q, 0);
+      const int t = (int)(q / kSubsPerTile), sub = (int)(q % kSubsPerTile);
+      if (t >= myTiles) break;
+      const int st = t % stages;
+      mbarWait(&ctl->full[st], (t / stages) & 1);
+      unsigned char *tileBase = ring + (size_t)st * kTileBytes;
+      const int j = sub * kSubTile + 2 * lane;
+      const int64_t i0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * kTile + j;
+      double s[EMCGPU_N_STREAMS][2];
+      uint32_t w[2];
+#pragma unroll
+      for (int c = 0; c < EMCGPU_N_STREAMS; c++) {
+        const double2 v = *reinterpret_cast<const double2 *>(tileBase + c * kTile * 8 + j * 8);
+        s[c][0] = v.x;
+        s[c][1] = v.y;
+      }
+      {
+        const uint2 v = *reinterpret_cast<const uint2 *>(tileBase + EMCGPU_N_STREAMS * kTile * 8 + j * 4);
+        w[0] = v.x;
+        w[1] = v.y;
+      }
+      bool ev[2];
+      double eOut[2], vOut[2];
+#pragma unroll
+      for (int jj = 0; jj < 2; jj++) {
+        ev[jj] = false;
+        eOut[jj] = 0.0;
+        vOut[jj] = 0.0;
+        if (s[EMCGPU_TAU][jj] >= dt) {
+          const int valley = w[jj] & 0xffu, sv = (w[jj] >> 8) & 0xffu;
+          if constexpr (EXACT) {
+            Particle p;
+            p.k = Vec3{s[EMCGPU_KX][jj], s[EMCGPU_KY][jj], s[EMCGPU_KZ][jj]};
+            p.energy = s[EMCGPU_ENERGY][jj];
+            p.tau = s[EMCGPU_TAU][jj];
+            p.pos = Vec3{s[EMCGPU_X][jj], s[EMCGPU_Y][jj], s[EMCGPU_Z][jj]};
+            p.valley = valley;
+            p.sub = sv;
+            const DevValley &v = model.valleys[valley];
+            drift<true, 3>(v, p, dt, P.force);
+            s[EMCGPU_KX][jj] = p.k.x;
+            s[EMCGPU_KY][jj] = p.k.y;
+            s[EMCGPU_KZ][jj] = p.k.z;
+            s[EMCGPU_ENERGY][jj] = p.energy;
+            s[EMCGPU_TAU][jj] = __dsub_rn(p.tau, dt);
+            s[EMCGPU_X][jj] = wrap1<true>(p.pos.x, P.box.x);
+            s[EMCGPU_Y][jj] = wrap1<true>(p.pos.y, P.box.y);
+            s[EMCGPU_Z][jj] = wrap1<true>(p.pos.z, P.box.z);
+            vOut[jj] = driftVelocity<true>(v, sv, p.k, p.energy, P.dir);
+          } else {
+            vOut[jj] = fastStep(C.fast[valley * EMCGPU_MAX_SUBVALLEYS + sv], C.fastV[valley], dt, P.box,
+                                s[EMCGPU_KX][jj], s[EMCGPU_KY][jj], s[EMCGPU_KZ][jj], s[EMCGPU_ENERGY][jj],
+                                s[EMCGPU_TAU][jj], s[EMCGPU_X][jj], s[EMCGPU_Y][jj], s[EMCGPU_Z][jj]);
+          }
+          eOut[jj] = s[EMCGPU_ENERGY][jj];
+          if (single) {
+            accE += eOut[jj];
+            accV += vOut[jj];
+            accN++;
+          }
+        } else {
+          ev[jj] = true;
+        }
+      }
+      const unsigned m0 = __ballot_sync(0xffffffffu, ev[0]), m1 = __ballot_sync(0xffffffffu, ev[1]);
+      const int nEv = __popc(m0) + __popc(m1);
+      const bool dense = nEv >= kDenseEvents;
+      if (dense) {
+        // dt >~ tau regime: most lanes scatter, process them right here
+#pragma unroll
+        for (int jj = 0; jj < 2; jj++) {
+          bool did = false;
+          int valley = 0;
+          if (ev[jj]) {
+            Particle p;
+            Rng rng;
+            p.k = Vec3{s[EMCGPU_KX][jj], s[EMCGPU_KY][jj], s[EMCGPU_KZ][jj]};
+            p.energy = s[EMCGPU_ENERGY][jj];
+            p.tau = s[EMCGPU_TAU][jj];
+            p.pos = Vec3{s[EMCGPU_X][jj], s[EMCGPU_Y][jj], s[EMCGPU_Z][jj]};
+            p.valley = w[jj] & 0xffu;
+            p.sub = (w[jj] >> 8) & 0xffu;
+            p.region = w[jj] >> 16;
+            vOut[jj] = bulkParticleStepNI<EXACT, RNG_MODE>(C, P, p, rng, i0 + jj);
+            s[EMCGPU_KX][jj] = p.k.x;
+            s[EMCGPU_KY][jj] = p.k.y;
+            s[EMCGPU_KZ][jj] = p.k.z;
+            s[EMCGPU_ENERGY][jj] = p.energy;
+            s[EMCGPU_TAU][jj] = p.tau;
+            s[EMCGPU_X][jj] = p.pos.x;
+            s[EMCGPU_Y][jj] = p.pos.y;
+            s[EMCGPU_Z][jj] = p.pos.z;
+            w[jj] = (uint32_t)p.valley | ((uint32_t)p.sub << 8) | ((uint32_t)p.region << 16);
+            eOut[jj] = p.energy;
+            valley = p.valley;
+            did = true;
+          }
+          __syncwarp();
+          accumulateObsWarp(C.obs, nV, did, valley, eOut[jj], vOut[jj]);
+          ev[jj] = false;
+        }
+      }
+      if (!single) {
+#pragma unroll
+        for (int jj = 0; jj < 2; jj++) {
+          const bool fastDone = !dense ? !ev[jj] : !((jj ? m1 : m0) >> lane & 1u);
+          accumulateObsWarp(C.obs, nV, fastDone, (int)(w[jj] & 0xffu), eOut[jj], vOut[jj]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < EMCGPU_N_STREAMS; c++)
+        *reinterpret_cast<double2 *>(tileBase + c * kTile * 8 + j * 8) = make_double2(s[c][0], s[c][1]);
+      if (dense)
+        *reinterpret_cast<uint2 *>(tileBase + EMCGPU_N_STREAMS * kTile * 8 + j * 4) = make_uint2(w[0], w[1]);
+      fenceProxyAsyncShared();
+      __syncwarp();
+      if (lane == 0) mbarArrive(&ctl->done[st]);
+      if (!dense && nEv > 0) {
+        // copy the scattering particles into the CTA-wide event queue
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&ctl->qTail, (unsigned)nEv);
+        base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+        for (int jj = 0; jj < 2; jj++) {
+          if (ev[jj]) {
+            const unsigned pos = base + (jj ? __popc(m0) : 0) + __popc((jj ? m1 : m0) & ltMask);
+            const unsigned slot = pos % kQueueCap;
+            const uint32_t epoch = pos / kQueueCap + 1;
+            while (*reinterpret_cast<volatile uint32_t *>(&Q->flag[slot]) != 2 * (epoch - 1)) { // previous tenant read
+            }
+#pragma unroll
+            for (int c = 0; c < EMCGPU_N_STREAMS; c++) Q->f[c][slot] = s[c][jj];
+            Q->w[slot] = w[jj];
+            Q->idx[slot] = (uint32_t)(i0 + jj);
+            Q->tile[slot] = (uint32_t)t;
+            __threadfence_block();
+            *reinterpret_cast<volatile uint32_t *>(&Q->flag[slot]) = 2 * epoch - 1;
+          }
+        }
+        __syncwarp();
+      }
+      // drain full batches
+      for (;;) {
+        unsigned h = 0;
+        int got = 0;
+        if (lane == 0) {
+          h = *reinterpret_cast<volatile unsigned *>(&ctl->qHead);
+          const unsigned tl = *reinterpret_cast<volatile unsigned *>(&ctl->qTail);
+          if (tl - h >= 32u) got = atomicCAS(&ctl->qHead, h, h + 32u) == h ? 1 : 2;
+        }
+        got = __shfl_sync(0xffffffffu, got, 0);
+        if (got == 0) break;
+        if (got == 2) continue; // lost the race, look again
+        h = __shfl_sync(0xffffffffu, h, 0);
+        processEventBatch<EXACT, RNG_MODE>(C, P, ctl, Q, h, 32);
+      }
+    }
+    // all pushes are complete once every consumer warp is here
+    asm volatile("bar.sync 1, %0;" ::"n"(kTmaConsumerWarps * 32) : "memory");
+    if (warp == 0) {
+      unsigned h = *reinterpret_cast<volatile unsigned *>(&ctl->qHead);
+      const unsigned tl = *reinterpret_cast<volatile unsigned *>(&ctl->qTail);
+      while (h != tl) {
+        const int take = min(32u, tl - h);
+        processEventBatch<EXACT, RNG_MODE>(C, P, ctl, Q, h, take);
+        h += take;
+      }
+    }
+    // the n % kTile particles behind the last whole tile: plain global path
+    if (blockIdx.x == 0) {
+      const int64_t first = nTiles * kTile;
+      const int rounds = (int)((P.n - first + kTmaConsumerWarps * 32 - 1) / (kTmaConsumerWarps * 32));
+      for (int r = 0; r < rounds; r++) {
+        const int64_t i = first + (int64_t)r * kTmaConsumerWarps * 32 + tid;
+        const bool live = i < P.n;
+        Particle p;
+        Rng rng;
+        double e = 0.0, vd = 0.0;
+        p.valley = 0;
+        if (live) {
+          loadParticle(P, i, p, rng);
+          vd = bulkParticleStepNI<EXACT, RNG_MODE>(C, P, p, rng, i);
+          e = p.energy;
+          storeParticleState(P, i, p);
+        }
+        __syncwarp();
+        accumulateObsWarp(C.obs, nV, live, p.valley, e, vd);
+      }
+    }
+    if (single) {
+      const double se = warpSum(accE), sv = warpSum(accV);
+      const unsigned cnt = __reduce_add_sync(0xffffffffu, accN);
+      if (lane == 0 && cnt) {
+        atomicAdd(C.obs + 0, se);
+        atomicAdd(C.obs + 1, sv);
+        atomicAdd(C.obs + 2, (double)cnt);
+      }
     }
   }
   __syncthreads();

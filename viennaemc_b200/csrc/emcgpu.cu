@@ -45,6 +45,8 @@ struct emcgpu_ctx {
   int maxSmemOptin = 0;
   int maxSmemPerSm = 0;
   int optVec = 2; // particles per lane and iteration of the streaming step kernel (1, 2, 4)
+  int optKernel = 0; // one-step kernel: 0 = TMA pipeline when it fits, 1 = plain streaming kernel
+  int optStages = 0; // cap on the TMA ring depth (0 = as many as fit)
   cudaStream_t stream = nullptr;
   std::string error;
   int64_t launches = 0;
@@ -168,10 +170,12 @@ void fillBulkParams(emcgpu_ctx *ctx, BulkParams &P) {
   P.status = static_cast<int *>(ctx->dStatus.ptr);
 }
 
-template <typename K> cudaError_t launchKernel(emcgpu_ctx *ctx, K kernel, const BulkParams &P, size_t smem, int grid) {
+template <typename K>
+cudaError_t launchKernel(emcgpu_ctx *ctx, K kernel, const BulkParams &P, size_t smem, int grid,
+                         int threads = kBulkThreads) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kernel<<<grid, kBulkThreads, smem, ctx->stream>>>(P);
+  kernel<<<grid, threads, smem, ctx->stream>>>(P);
   ctx->launches++;
   return cudaGetLastError();
 }
@@ -190,12 +194,37 @@ cudaError_t launchFused(emcgpu_ctx *ctx, const BulkParams &P, size_t smem, int g
 template <int VEC> cudaError_t launchStreamVec(emcgpu_ctx *ctx, const BulkParams &P, size_t smem, int grid) {
   const bool exact = ctx->mathMode == EMCGPU_MATH_EXACT;
   if (ctx->rngMode == RNG_PHILOX)
-    return exact ? launchKernel(ctx, bulkStreamKernel<true, RNG_PHILOX, VEC>, P, smem, grid)
-                 : launchKernel(ctx, bulkStreamKernel<false, RNG_PHILOX, VEC>, P, smem, grid);
-  return exact ? launchKernel(ctx, bulkStreamKernel<true, RNG_REPLAY, VEC>, P, smem, grid)
-               : launchKernel(ctx, bulkStreamKernel<false, RNG_REPLAY, VEC>, P, smem, grid);
+    return exact ? launchKernel(ctx, bulkStreamKernel<true, RNG_PHILOX, VEC>, P, smem, grid, kStreamThreads)
+                 : launchKernel(ctx, bulkStreamKernel<false, RNG_PHILOX, VEC>, P, smem, grid, kStreamThreads);
+  return exact ? launchKernel(ctx, bulkStreamKernel<true, RNG_REPLAY, VEC>, P, smem, grid, kStreamThreads)
+               : launchKernel(ctx, bulkStreamKernel<false, RNG_REPLAY, VEC>, P, smem, grid, kStreamThreads);
 }
-int streamQueueWords(int vec) { return (kBulkThreads / 32) * (32 + 32 * vec); }
+// K1a/TMA, one step per launch, warp-specialised TMA pipeline
+cudaError_t launchTma(emcgpu_ctx *ctx, const BulkParams &P, size_t smem, int grid, int stages) {
+  const bool exact = ctx->mathMode == EMCGPU_MATH_EXACT;
+  auto go = [&](auto kernel) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, kTmaThreads, smem, ctx->stream>>>(P, stages);
+    ctx->launches++;
+    return cudaGetLastError();
+  };
+  if (ctx->rngMode == RNG_PHILOX)
+    return exact ? go(bulkTmaKernel<true, RNG_PHILOX>) : go(bulkTmaKernel<false, RNG_PHILOX>);
+  return exact ? go(bulkTmaKernel<true, RNG_REPLAY>) : go(bulkTmaKernel<false, RNG_REPLAY>);
+}
+// ring stages that fit beside the model (and the tables) in shared memory; 0 = does not fit
+int tmaStages(const emcgpu_ctx *ctx, bool tablesInSmem, size_t *smemOut) {
+  const BulkSmem L(ctx->hModel.nValleys * 3, ctx->hModel.nValleys, (int)ctx->hMechs.size(), ctx->hModel.tableDoubles,
+                   tablesInSmem, kTmaQueueWords);
+  const size_t ring = tmaRingOffset(L);
+  if (ring + (size_t)kMinStages * kTileBytes > (size_t)ctx->maxSmemOptin) return 0;
+  const int stages = (int)std::min<size_t>(kMaxStages, ((size_t)ctx->maxSmemOptin - ring) / kTileBytes);
+  *smemOut = ring + (size_t)stages * kTileBytes;
+  return stages;
+}
+
+int streamQueueWords(int vec) { return (kStreamThreads / 32) * (32 + 32 * vec); }
 
 int checkReady(emcgpu_ctx *ctx, bool needEnsemble) {
   if (!ctx) return EMCGPU_E_INVALID;
@@ -303,6 +332,15 @@ int emcgpu_set_option(emcgpu_ctx *ctx, const char *name, int64_t value) {
   if (!strcmp(name, "vec")) {
     if (value != 1 && value != 2 && value != 4) return fail(ctx, EMCGPU_E_INVALID, "vec must be 1, 2 or 4");
     ctx->optVec = (int)value;
+    return EMCGPU_OK;
+  }
+  if (!strcmp(name, "kernel")) {
+    if (value != 0 && value != 1) return fail(ctx, EMCGPU_E_INVALID, "kernel must be 0 (TMA pipeline) or 1 (streaming)");
+    ctx->optKernel = (int)value;
+    return EMCGPU_OK;
+  }
+  if (!strcmp(name, "stages")) {
+    ctx->optStages = (int)value;
     return EMCGPU_OK;
   }
   return fail(ctx, EMCGPU_E_INVALID, "unknown option '%s'", name);
@@ -609,6 +647,29 @@ int emcgpu_bulk_step_device(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPer
     P.step0 = ctx->nextStep + done;
     P.obs = obsDevice + (size_t)done * nV * 3;
     const bool stream = chunk == 1;
+    if (stream && ctx->optKernel != 1) {
+      // preferred: the TMA pipeline (tables in shared memory if they fit beside >= kMinStages ring stages)
+      size_t smem = 0;
+      bool inSmem = true;
+      int stages = tmaStages(ctx, true, &smem);
+      if (!stages) {
+        inSmem = false;
+        stages = tmaStages(ctx, false, &smem);
+      }
+      if (stages) {
+        if (ctx->optStages >= kMinStages && ctx->optStages < stages) {
+          smem -= (size_t)(stages - ctx->optStages) * kTileBytes;
+          stages = ctx->optStages;
+        }
+        P.tablesInSmem = inSmem ? 1 : 0;
+        const int64_t nTiles = ctx->n / kTile;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nTiles, ctx->smCount));
+        cudaError_t e = launchTma(ctx, P, smem, grid, stages);
+        if (e != cudaSuccess) return fail(ctx, EMCGPU_E_CUDA, "bulk step launch failed: %s", cudaGetErrorString(e));
+        done += chunk;
+        continue;
+      }
+    }
     const int vec = ctx->optVec;
     const int queueWords = stream ? streamQueueWords(vec) : 0;
     bool inSmem = true;
@@ -624,7 +685,7 @@ int emcgpu_bulk_step_device(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPer
     // bounds, fewer if the tables are large), never more than the work needs
     int perSm = (int)std::min<size_t>(2, (size_t)(ctx->maxSmemPerSm) / (smem + 1024));
     if (perSm < 1) perSm = 1;
-    const int64_t perCta = (int64_t)kBulkThreads * (stream ? vec : 1);
+    const int64_t perCta = stream ? (int64_t)kStreamThreads * vec : (int64_t)kBulkThreads;
     const int blocksNeeded = (int)std::min<int64_t>((ctx->n + perCta - 1) / perCta, 1 << 30);
     const int grid = std::max(1, std::min(blocksNeeded, ctx->smCount * perSm));
     cudaError_t e;
