@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--math", type=int, default=1)
     ap.add_argument("--dt", type=float, default=1e-16)
     ap.add_argument("--vec", type=int, nargs="+", default=[2])
+    ap.add_argument("--opt", nargs="*", default=[], help="name=value context options")
     ap.add_argument("--settle", type=int, default=0, help="untimed steps (fused) to leave the initial transient")
     args = ap.parse_args()
     import torch
@@ -30,6 +31,9 @@ def main():
     for n in args.n:
         ctx = capi.Context(0)
         upload_model(ctx, m)
+        for o in args.opt:
+            k, v = o.split("=")
+            ctx.set_option(k, int(v))
         box = [(n / 1e23) ** (1 / 3)] * 3
         ctx.generate_bulk_ensemble(n, box, 300.0, 0, seed=1)
         ctx.rng_philox(5)

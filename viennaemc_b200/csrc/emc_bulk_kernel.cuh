@@ -339,7 +339,7 @@ __device__ __forceinline__ void loadParticle(const BulkParams &P, int64_t i, Par
   p.k.x = P.stream[EMCGPU_KX][i];
   p.k.y = P.stream[EMCGPU_KY][i];
   p.k.z = P.stream[EMCGPU_KZ][i];
-  p.energy = P.stream[EMCGPU_ENERGY][i];
+  p.energy = 0.0; // never read: every step starts with a drift, which recomputes E from k (emcParticleDrift.hpp:25)
   p.tau = P.stream[EMCGPU_TAU][i];
   p.pos.x = P.stream[EMCGPU_X][i];
   p.pos.y = P.stream[EMCGPU_Y][i];
@@ -486,7 +486,14 @@ __global__ void __launch_bounds__(kStreamThreads, 2) bulkStreamKernel(const __gr
     for (int j = 0; j < VEC; j++) ev[j] = false;
     if (live) {
 #pragma unroll
-      for (int c = 0; c < EMCGPU_N_STREAMS; c++) VecIO<VEC>::ld(P.stream[c] + i0, s[c]);
+      for (int c = 0; c < EMCGPU_N_STREAMS; c++) {
+        if (c == EMCGPU_ENERGY) { // write-only stream, see loadParticle
+#pragma unroll
+          for (int j = 0; j < VEC; j++) s[c][j] = 0.0;
+        } else {
+          VecIO<VEC>::ld(P.stream[c] + i0, s[c]);
+        }
+      }
       VecIO<VEC>::ldw(P.packed + i0, w);
 #pragma unroll
       for (int j = 0; j < VEC; j++) {
@@ -621,13 +628,14 @@ constexpr int kSubTile = 64;
 constexpr int kSubsPerTile = kTile / kSubTile;
 constexpr int kTileBytes = kTile * (EMCGPU_N_STREAMS * 8 + 4);
 constexpr int kQueueCap = 256;
-constexpr int kMaxStages = 8;
-// a claimed sub-tile is at most ceil(warps/subs) tiles ahead of the oldest
-// unfinished one; the ring must be deeper than that for the parity waits to be
-// unambiguous
-constexpr int kMinStages = (kTmaConsumerWarps + kSubsPerTile - 1) / kSubsPerTile + 2;
+constexpr int kMaxStages = 16;
+constexpr int kMinStages = 3;
+// bytes the loader brings in per tile: every stream except the energy, which
+// the step never reads (each step starts with a drift that recomputes E from k)
+constexpr int kTileLoadBytes = kTile * ((EMCGPU_N_STREAMS - 1) * 8 + 4);
 constexpr int kDenseEvents = kSubTile / 4;
 
+constexpr int kFreeLag = 0;  // bulk stores whose shared-memory reads may still be pending
 constexpr int kStoreLag = 6; // bulk stores allowed in flight before their completion is awaited
 
 struct TmaControl {
@@ -637,7 +645,9 @@ struct TmaControl {
   uint64_t tableBar;
   unsigned nextSub;
   unsigned qTail, qHead;
-  unsigned storesDone; // number of this CTA's tiles whose store is complete
+  unsigned storesDone;  // number of this CTA's tiles whose store is complete
+  unsigned loadsIssued; // number of this CTA's tiles whose loads have been issued
+  unsigned dirty[kMaxStages]; // the packed index words of the stage were modified (dense sub-tiles)
 };
 struct EventQueue {
   double f[EMCGPU_N_STREAMS][kQueueCap];
@@ -717,6 +727,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1) bulkTmaKernel(const __grid_con
     ctl->qTail = 0;
     ctl->qHead = 0;
     ctl->storesDone = 0;
+    ctl->loadsIssued = 0;
+    for (int s = 0; s < stages; s++) ctl->dirty[s] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fenceProxyAsyncShared();
   }
@@ -740,11 +752,14 @@ __global__ void __launch_bounds__(kTmaThreads, 1) bulkTmaKernel(const __grid_con
         if (t >= stages) mbarWait(&ctl->freed[st], (t / stages - 1) & 1); // the previous tenant has been stored
         const int64_t i0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * kTile;
         unsigned char *dst = ring + (size_t)st * kTileBytes;
-        mbarExpectTx(&ctl->full[st], kTileBytes);
+        mbarExpectTx(&ctl->full[st], kTileLoadBytes);
 #pragma unroll
         for (int c = 0; c < EMCGPU_N_STREAMS; c++)
-          tmaBulkLoadHint(dst + c * kTile * 8, P.stream[c] + i0, kTile * 8, &ctl->full[st], pol);
+          if (c != EMCGPU_ENERGY)
+            tmaBulkLoadHint(dst + c * kTile * 8, P.stream[c] + i0, kTile * 8, &ctl->full[st], pol);
         tmaBulkLoadHint(dst + EMCGPU_N_STREAMS * kTile * 8, P.packed + i0, kTile * 4, &ctl->full[st], pol);
+        // full[st] is now in the phase of tile t: consumers may wait on its parity
+        *reinterpret_cast<volatile unsigned *>(&ctl->loadsIssued) = (unsigned)(t + 1);
       }
     }
   } else if (warp == kTmaConsumerWarps + 1) {
@@ -757,19 +772,24 @@ __global__ void __launch_bounds__(kTmaThreads, 1) bulkTmaKernel(const __grid_con
         const unsigned char *src = ring + (size_t)st * kTileBytes;
 #pragma unroll
         for (int c = 0; c < EMCGPU_N_STREAMS; c++) tmaBulkStore(P.stream[c] + i0, src + c * kTile * 8, kTile * 8);
-        tmaBulkStore(P.packed + i0, src + EMCGPU_N_STREAMS * kTile * 8, kTile * 4);
+        // valley / sub-valley / region only change in scattering events: the event
+        // path writes them itself, except for sub-tiles processed in place
+        if (*reinterpret_cast<volatile unsigned *>(&ctl->dirty[st])) {
+          tmaBulkStore(P.packed + i0, src + EMCGPU_N_STREAMS * kTile * 8, kTile * 4);
+          *reinterpret_cast<volatile unsigned *>(&ctl->dirty[st]) = 0;
+        }
         tmaCommitGroup();
-        tmaWaitGroupRead<0>(); // shared memory has been read: the stage may be reloaded
-        mbarArrive(&ctl->freed[st]);
+        // stores stay in flight: a stage is handed back to the loader once the
+        // store issued kFreeLag tiles ago has finished reading shared memory
+        tmaWaitGroupRead<kFreeLag>();
+        if (t >= kFreeLag) mbarArrive(&ctl->freed[(t - kFreeLag) % stages]);
         tmaWaitGroup<kStoreLag>(); // all but the kStoreLag newest stores are complete in global memory
         if (t + 1 > kStoreLag) {
-          asm volatile("fence.proxy.async;" ::: "memory");
           __threadfence_block();
           *reinterpret_cast<volatile unsigned *>(&ctl->storesDone) = (unsigned)(t + 1 - kStoreLag);
         }
       }
       tmaWaitGroup<0>();
-      asm volatile("fence.proxy.async;" ::: "memory");
       __threadfence_block();
       *reinterpret_cast<volatile unsigned *>(&ctl->storesDone) = (unsigned)myTiles + 1u;
     }
@@ -783,23 +803,27 @@ __global__ void __launch_bounds__(kTmaThreads, 1) bulkTmaKernel(const __grid_con
       const int t = (int)(q / kSubsPerTile), sub = (int)(q % kSubsPerTile);
       if (t >= myTiles) break;
       const int st = t % stages;
+      while (*reinterpret_cast<volatile unsigned *>(&ctl->loadsIssued) <= (unsigned)t) {
+      }
       mbarWait(&ctl->full[st], (t / stages) & 1);
-      unsigned char *tileBase = ring + (size_t)st * kTileBytes;
+      const uint32_t tileBase = smemAddr(ring + (size_t)st * kTileBytes);
       const int j = sub * kSubTile + 2 * lane;
       const int64_t i0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * kTile + j;
       double s[EMCGPU_N_STREAMS][2];
       uint32_t w[2];
 #pragma unroll
       for (int c = 0; c < EMCGPU_N_STREAMS; c++) {
-        const double2 v = *reinterpret_cast<const double2 *>(tileBase + c * kTile * 8 + j * 8);
-        s[c][0] = v.x;
-        s[c][1] = v.y;
+        if (c == EMCGPU_ENERGY) {
+          s[c][0] = s[c][1] = 0.0;
+        } else {
+          asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];"
+                       : "=d"(s[c][0]), "=d"(s[c][1])
+                       : "r"(tileBase + c * kTile * 8 + j * 8));
+        }
       }
-      {
-        const uint2 v = *reinterpret_cast<const uint2 *>(tileBase + EMCGPU_N_STREAMS * kTile * 8 + j * 4);
-        w[0] = v.x;
-        w[1] = v.y;
-      }
+      asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];"
+                   : "=r"(w[0]), "=r"(w[1])
+                   : "r"(tileBase + EMCGPU_N_STREAMS * kTile * 8 + j * 4));
       bool ev[2];
       double eOut[2], vOut[2];
 #pragma unroll
@@ -890,9 +914,15 @@ __global__ void __launch_bounds__(kTmaThreads, 1) bulkTmaKernel(const __grid_con
       }
 #pragma unroll
       for (int c = 0; c < EMCGPU_N_STREAMS; c++)
-        *reinterpret_cast<double2 *>(tileBase + c * kTile * 8 + j * 8) = make_double2(s[c][0], s[c][1]);
-      if (dense)
-        *reinterpret_cast<uint2 *>(tileBase + EMCGPU_N_STREAMS * kTile * 8 + j * 4) = make_uint2(w[0], w[1]);
+        asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(tileBase + c * kTile * 8 + j * 8), "d"(s[c][0]),
+                     "d"(s[c][1])
+                     : "memory");
+      if (dense) {
+        asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(tileBase + EMCGPU_N_STREAMS * kTile * 8 + j * 4),
+                     "r"(w[0]), "r"(w[1])
+                     : "memory");
+        *reinterpret_cast<volatile unsigned *>(&ctl->dirty[st]) = 1u;
+      }
       fenceProxyAsyncShared();
       __syncwarp();
       if (lane == 0) mbarArrive(&ctl->done[st]);

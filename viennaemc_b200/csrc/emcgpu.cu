@@ -47,6 +47,7 @@ struct emcgpu_ctx {
   int optVec = 2; // particles per lane and iteration of the streaming step kernel (1, 2, 4)
   int optKernel = 0; // one-step kernel: 0 = TMA pipeline when it fits, 1 = plain streaming kernel
   int optStages = 0; // cap on the TMA ring depth (0 = as many as fit)
+  int optTablesGlobal = 0; // 1 = leave the rate tables in global memory / L2 (more ring stages)
   cudaStream_t stream = nullptr;
   std::string error;
   int64_t launches = 0;
@@ -337,6 +338,10 @@ int emcgpu_set_option(emcgpu_ctx *ctx, const char *name, int64_t value) {
   if (!strcmp(name, "kernel")) {
     if (value != 0 && value != 1) return fail(ctx, EMCGPU_E_INVALID, "kernel must be 0 (TMA pipeline) or 1 (streaming)");
     ctx->optKernel = (int)value;
+    return EMCGPU_OK;
+  }
+  if (!strcmp(name, "tables_global")) {
+    ctx->optTablesGlobal = value != 0;
     return EMCGPU_OK;
   }
   if (!strcmp(name, "stages")) {
@@ -651,7 +656,7 @@ int emcgpu_bulk_step_device(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPer
       // preferred: the TMA pipeline (tables in shared memory if they fit beside >= kMinStages ring stages)
       size_t smem = 0;
       bool inSmem = true;
-      int stages = tmaStages(ctx, true, &smem);
+      int stages = ctx->optTablesGlobal ? 0 : tmaStages(ctx, true, &smem);
       if (!stages) {
         inSmem = false;
         stages = tmaStages(ctx, false, &smem);
