@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""Benchmark of the bulk particle loop (BASELINE.json: particle-steps/s, Si bulk EMC; HBM GB/s vs peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (configs[1] of BASELINE.json): Si electrons, the shipped bulkSimulation mechanism set
+(acoustic + zero- and first-order intervalley, 1000 energy levels of 1 meV), 300 K, 10 kV/cm along
+-x, dt = 1e-16 s; 1e8 particles PER GPU (weak scaling), generated on the device from the
+reference's initial distributions and advanced out of the initial transient before timing.
+One "step" = one time step of every particle of the shard = ONE launch of the step kernel, which
+also reduces the per-valley observables of that step (the reference's moveParticles(dt) + the three
+getAvg* passes, bulkSimulation.cpp:150-157).  The rate tables are built on the host by the drop-in
+C++ API (libemchost) -- not by the oracle.
+
+N > 1: one process per GPU (torchrun), the ensemble is block-partitioned, no per-step communication;
+the [K x valleys x 3] observable series is all-reduced (NCCL) once, inside the timed region.
+
+--impl reference: the reference's OWN OpenMP implementation of the same path
+(oracle/_ref/ref_bulk_bench: unmodified basicBulkParticleHandler::moveParticles + observable passes)
+on the host cores, on a bounded sample of the workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle_steps_per_s"
+UNIT = "particle-steps/s"
+BYTES_PER_PARTICLE_STEP = 136.0  # 8 fp64 + 1 u32 read and written per particle-step
+DT = 1e-16
+FIELD = 1e6
+DOPING = 1e23
+SEED = 12345
+
+
+def workload_config(particles_per_gpu, n_gpus, extra=None):
+    cfg = {
+        "workload": "Si bulk EMC (BASELINE configs[1]): 6 X valleys non-parabolic, acoustic + zero/first-order "
+                    "intervalley phonons (shipped bulkSimulation set), 300 K, 10 kV/cm, dt=1e-16 s",
+        "particles_per_gpu": int(particles_per_gpu),
+        "particles_total": int(particles_per_gpu) * n_gpus,
+        "steps_per_launch": 1,
+        "observables": "per-step per-valley <E>, <v.E>, occupation fused into the step kernel",
+        "l2": "no flush needed: state per GPU (%.1f GB) is far larger than L2" % (particles_per_gpu * 68 / 1e9),
+        "parallelism": f"particles block-partitioned over {n_gpus} GPU(s), one all-reduce of the observable series",
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md recipe)
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            time.sleep(0.3)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# the reference's CPU implementation (oracle/_ref, built from the unmodified reference headers)
+REF_BENCH = os.path.join(ROOT, "oracle", "_ref", "ref_bulk_bench")
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_ref_bench(particles, steps, warmup, threads):
+    out = subprocess.run([REF_BENCH, "--particles", str(int(particles)), "--steps", str(int(steps)), "--warmup",
+                          str(int(warmup)), "--threads", str(threads), "--field", str(FIELD), "--dt", str(DT), "--seed",
+                          str(SEED)], capture_output=True, text=True, check=True,
+                         env=dict(os.environ, OMP_NUM_THREADS=str(threads)))
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def run_port_bench(particles, steps):
+    """fallback when the reference binary is not there: the single-threaded oracle port"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import pyoracle as po
+    from scenarios import build_si
+    m = build_si()
+    box = [(particles / DOPING) ** (1 / 3)] * 3
+    ens, _ = m.generate_initial(box, [5, 5, 5], DOPING, po.mt_state(SEED))
+    t0 = time.perf_counter()
+    m.bulk_steps(ens, box, [-1, 0, 0], FIELD, DT, steps, po.rng_philox(SEED), first_step=1)
+    dt = time.perf_counter() - t0
+    return {"particles": ens.n, "steps": steps, "threads": 1, "psteps_per_s": ens.n * steps / dt,
+            "move_s": dt, "obs_s": 0.0}
+
+
+def cpu_reference(steps, warmup, budget_s):
+    """Time the reference on a bounded sample: calibrate briefly, then size the ensemble so that
+    steps+warmup time steps take about budget_s."""
+    cores = host_cores()
+    if os.path.exists(REF_BENCH):
+        cal = run_ref_bench(100000, 20, 5, cores)
+        rate = cal["psteps_per_s"]
+        particles = max(20000, min(5_000_000, int(rate * budget_s / max(1, steps + warmup))))
+        res = run_ref_bench(particles, steps, warmup, cores)
+        kind = "reference"
+    else:
+        particles = 2000
+        res = run_port_bench(particles, min(steps, 20))
+        kind, cores = "port", 1
+        steps = res["steps"]
+    sample = (f"{res['particles']} particles x {steps} time steps of the same workload "
+              f"(moveParticles + 3 observable passes per step), {res['threads']} OpenMP thread(s)")
+    return {"value": res["psteps_per_s"], "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+            "move_only_value": res.get("psteps_per_s_move_only"),
+            "seconds": res["move_s"] + res["obs_s"]}, res
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    base, res = cpu_reference(args.steps, args.warmup, budget_s=90.0)
+    ms = 1e3 * base["seconds"] / max(1, res["steps"])
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.particles, args.gpus,
+                                      {"reference_sample": base["sample"],
+                                       "note": "reference CPU path: throughput does not depend on the GPU count"}),
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+def main_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from viennaemc_b200 import capi, hostapi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:  # convenience: spawn the ranks ourselves
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), *sys.argv]
+            return subprocess.call(cmd)
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback "
+                         "(use --impl reference for the CPU reference)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n_local = int(args.particles)
+    n_total = n_local * world
+    box = [(n_total / DOPING) ** (1.0 / 3.0)] * 3
+    ctx = capi.Context(local_rank)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    hostapi.si_upload(ctx, hostapi.si_spec(box=box, spacing=[b / 5 for b in box], doping=DOPING))
+    ctx.generate_bulk_ensemble(n_local, box, 300.0, 0, seed=SEED, particle_id_base=rank * n_local)
+    ctx.rng_philox(SEED)
+    ctx.bulk_configure(box, [-1, 0, 0], FIELD, math_mode=capi.MATH_FAST)
+    ctx.set_step_index(1)
+    n_v = 1
+    K, W = args.steps, args.warmup
+
+    # leave the initial transient (untimed set-up; fused launches)
+    if args.settle > 0:
+        scratch = torch.zeros(args.settle * n_v * 3, dtype=torch.float64, device="cuda")
+        ctx.bulk_step_device(DT, args.settle, 16, scratch.data_ptr())
+        del scratch
+    obs = torch.zeros(K * n_v * 3, dtype=torch.float64, device="cuda")
+    warm = torch.zeros(max(1, W) * n_v * 3, dtype=torch.float64, device="cuda")
+
+    def timed(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- headline: K steps, one launch per step, inputs resident in HBM -------------------------
+    if W > 0:
+        ctx.bulk_step_device(DT, W, 1, warm.data_ptr())
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    def run_steps():
+        ctx.bulk_step_device(DT, K, 1, obs.data_ptr())
+        if world > 1:
+            dist.all_reduce(obs)  # the only communication of a bulk run
+
+    ms = timed(run_steps)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launch_count - launches0
+    value = n_total * K / (ms * 1e-3)
+    series = obs.view(K, n_v, 3).cpu().numpy()
+    assert np.all(series[:, :, 2].sum(axis=1) == n_total), "particle count not conserved"
+    mean_e = float((series[:, 0, 0] / series[:, 0, 2]).mean())
+    mean_v = float((series[:, 0, 1] / series[:, 0, 2]).mean())
+
+    # ---- informational: the same K steps with 16 time steps fused per launch -------------------
+    fused_ms = timed(lambda: ctx.bulk_step_device(DT, K, 16, obs.data_ptr()))
+    fused = {"steps_per_launch": 16, "value": n_total * K / (fused_ms * 1e-3), "unit": UNIT,
+             "ms_per_step": fused_ms / K,
+             "note": "state stays in registers for 16 steps: 136 B of HBM traffic per particle per 16 steps"}
+
+    # ---- end to end through the C ABI with HOST buffers ----------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = [torch.empty(n_local, dtype=torch.float64, pin_memory=True) for _ in range(capi.N_STREAMS)]
+        host_packed = torch.empty(n_local, dtype=torch.int32, pin_memory=True)
+        streams = [h.numpy() for h in host]
+        packed = host_packed.numpy().view(np.uint32)
+        ctx.get_ensemble_into(streams, packed)  # the job's input now lives in (pinned) host memory
+        obs_host = np.zeros((K, n_v, 3))
+        base_id = rank * n_local
+
+        def run_e2e():
+            ctx.set_ensemble_from(streams, packed, base_id)  # H2D, 68 B per particle
+            for s in range(K):  # per step: kernel + D2H of that step's observables (24 B per valley)
+                ctx.L.emcgpu_bulk_step(ctx.h, DT, 1, 1, obs_host[s].ctypes.data_as(capi._DP))
+            ctx.get_ensemble_into(streams, packed)  # D2H, 68 B per particle
+
+        e2e_ms = timed(run_e2e)
+        assert np.all(obs_host[:, :, 2].sum(axis=1) == n_local)
+        e2e = {"value": n_total * K / (e2e_ms * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": 68.0 * n_local / K, "d2h_bytes_per_step": 68.0 * n_local / K + 24.0 * n_v,
+               "ms_total": e2e_ms,
+               "what": "emcgpu_set_ensemble from pinned host arrays + K x emcgpu_bulk_step(1 step, host observables) "
+                       "+ emcgpu_get_ensemble to pinned host arrays, all inside the timed region (per rank)"}
+        del host, host_packed
+
+    # ---- roofline of the step kernel -------------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = BYTES_PER_PARTICLE_STEP * n_local * K / (ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        t = json.load(open(tpath))
+        if int(t.get("particles", 0)) == n_local:
+            traffic = t["dram_bytes_per_launch"]
+    roofline = {"bound": "hbm", "kernel": "bulkTmaKernel<FAST, PHILOX> (one time step per launch)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": BYTES_PER_PARTICLE_STEP * n_local,
+                "avg_launch_ms": ms / K,
+                "note": "per GPU; launch duration = CUDA-event time of the K-step region / K"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": workload_config(n_local, world, {"settle_steps": args.settle, "math": "FAST (FMA, hoisted constants)",
+                                                       "rng": "Philox4x32-10 keyed by global particle id and step"}),
+            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "fused": fused,
+            "observables": {"mean_energy_eV": mean_e, "mean_drift_velocity_m_s": mean_v}}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                base, _ = cpu_reference(steps=50, warmup=5, budget_s=15.0)
+                line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            except Exception as exc:  # the baseline is reported, never required
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": host_cores(), "kind": "reference",
+                                        "sample": f"failed: {exc}"}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--particles", type=float, default=1e8, help="particles per GPU")
+    ap.add_argument("--settle", type=int, default=2000, help="untimed time steps before the measurement")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    sys.exit(main_reference(args) if args.impl == "reference" else main_ours(args))
+
+
+if __name__ == "__main__":
+    main()

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--math", type=int, default=1)
     ap.add_argument("--dt", type=float, default=1e-16)
     ap.add_argument("--vec", type=int, nargs="+", default=[2])
+    ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--opt", nargs="*", default=[], help="name=value context options")
     ap.add_argument("--settle", type=int, default=0, help="untimed steps (fused) to leave the initial transient")
     args = ap.parse_args()
@@ -47,12 +48,14 @@ def main():
                 ctx.set_option("vec", vec)
             ctx.bulk_step_device(args.dt, args.steps, spl, obs.data_ptr())  # warm-up
             ctx.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            ctx.bulk_step_device(args.dt, args.steps, spl, obs.data_ptr())
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1)
+            ms = 1e30
+            for _ in range(args.reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ctx.bulk_step_device(args.dt, args.steps, spl, obs.data_ptr())
+                e1.record()
+                torch.cuda.synchronize()
+                ms = min(ms, e0.elapsed_time(e1))
             rate = n * args.steps / (ms * 1e-3)
             launches = (args.steps + spl - 1) // spl
             gbs = 136.0 * n * launches / (ms * 1e-3) / 1e9

@@ -47,8 +47,56 @@ def build_emcgpu(force: bool = False, verbose: bool = False) -> str:
     return target
 
 
+HOST_INC = os.path.join(PKG, "host", "include")
+# host code builds the rate tables: plain IEEE arithmetic, no FMA contraction, no -march=native,
+# so that the tables do not depend on the build machine
+HOST_FLAGS = ["-std=c++17", "-O2", "-ffp-contract=off", "-fPIC"]
+REFERENCE = "/root/reference"
+
+
+def build_emchost(force: bool = False) -> str:
+    """libemchost.so: the drop-in C++ host API instantiated for the silicon model (include/emchost.h)."""
+    target = os.path.join(LIBDIR, "libemchost.so")
+    src = os.path.join(PKG, "host", "src", "emchost.cpp")
+    deps = _sources(os.path.join(PKG, "host"), os.path.join(ROOT, "include")) + [os.path.join(LIBDIR, "libemcgpu.so")]
+    if force or _newer(target, deps):
+        subprocess.check_call(["g++", *HOST_FLAGS, "-shared", "-I", os.path.join(ROOT, "include"), "-I", HOST_INC,
+                               "-o", target, src, "-L", LIBDIR, "-lemcgpu", "-Wl,-rpath,$ORIGIN"])
+    return target
+
+
+def build_examples(force: bool = False) -> dict:
+    """Example drivers on top of the drop-in headers.  `reference_bulkSimulation_gpu` is the UNMODIFIED
+    main() of the reference's examples/bulkSimulation/bulkSimulation.cpp compiled against OUR headers
+    (pre-including our basicBulkParticleHandler.hpp, whose include guard makes the example's own
+    quote-include a no-op); it can only be (re)built where the reference tree is mounted, the binary
+    travels to the GPU box."""
+    bindir = os.path.join(PKG, "bin")
+    os.makedirs(bindir, exist_ok=True)
+    out = {}
+    common = ["g++", *HOST_FLAGS, "-I", HOST_INC, "-I", os.path.join(ROOT, "include")]
+    link = ["-L", LIBDIR, "-lemcgpu", "-Wl,-rpath,$ORIGIN/../lib"]
+    deps = _sources(os.path.join(PKG, "host"), os.path.join(ROOT, "include")) + [os.path.join(LIBDIR, "libemcgpu.so")]
+    own = os.path.join(PKG, "host", "examples", "bulkSimulation.cpp")
+    if os.path.exists(own):
+        target = os.path.join(bindir, "bulkSimulation")
+        if force or _newer(target, deps):
+            subprocess.check_call([*common, "-o", target, own, *link])
+        out["bulkSimulation"] = target
+    ref_main = os.path.join(REFERENCE, "examples", "bulkSimulation", "bulkSimulation.cpp")
+    target = os.path.join(bindir, "reference_bulkSimulation_gpu")
+    if os.path.exists(ref_main) and (force or _newer(target, deps)):
+        subprocess.check_call([*common, "-include", os.path.join(HOST_INC, "basicBulkParticleHandler.hpp"), "-o", target,
+                               ref_main, *link])
+    if os.path.exists(target):
+        out["reference_bulkSimulation_gpu"] = target
+    return out
+
+
 def build_all(force: bool = False) -> dict:
-    return {"emcgpu": build_emcgpu(force)}
+    out = {"emcgpu": build_emcgpu(force), "emchost": build_emchost(force)}
+    out.update(build_examples(force))
+    return out
 
 
 if __name__ == "__main__":

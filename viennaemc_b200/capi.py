@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libemcgpu.so")
+# EMCGPU_LIB: developer override to A/B-test another build of the same library (never a CPU path)
+LIB_PATH = os.environ.get("EMCGPU_LIB") or os.path.join(_PKG, "lib", "libemcgpu.so")
 
 MAX_VALLEYS, MAX_SUB, MAX_FINAL, MAX_MECH_PER_SET, MAX_TABLESETS, NAME_LEN = 8, 8, 8, 16, 32, 48
 N_STREAMS = 8
@@ -198,6 +199,23 @@ class Context:
         ptrs = (_DP * N_STREAMS)(*[a.ctypes.data_as(_DP) for a in streams])
         self._chk(self.L.emcgpu_get_ensemble(self.h, ptrs, packed.ctypes.data_as(C.POINTER(C.c_uint32))))
         return streams, packed
+
+    def set_ensemble_from(self, streams, packed, particle_id_base=0):
+        """upload from caller-owned host arrays WITHOUT copying them first (e.g. views of pinned memory)"""
+        n = len(packed)
+        assert all(a.dtype == np.float64 and a.flags.c_contiguous and len(a) == n for a in streams)
+        assert packed.dtype == np.uint32 and packed.flags.c_contiguous
+        ptrs = (_DP * N_STREAMS)(*[a.ctypes.data_as(_DP) for a in streams])
+        self._chk(self.L.emcgpu_set_ensemble(self.h, n, ptrs, packed.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                             particle_id_base))
+
+    def get_ensemble_into(self, streams, packed):
+        """download into caller-owned host arrays (e.g. views of pinned memory)"""
+        n = self.size
+        assert all(a.dtype == np.float64 and a.flags.c_contiguous and len(a) == n for a in streams)
+        assert packed.dtype == np.uint32 and packed.flags.c_contiguous and len(packed) == n
+        ptrs = (_DP * N_STREAMS)(*[a.ctypes.data_as(_DP) for a in streams])
+        self._chk(self.L.emcgpu_get_ensemble(self.h, ptrs, packed.ctypes.data_as(C.POINTER(C.c_uint32))))
 
     @property
     def size(self):

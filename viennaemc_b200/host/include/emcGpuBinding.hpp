@@ -1,0 +1,129 @@
+// Glue between the drop-in host API and the C ABI of the CUDA library
+// (include/emcgpu.h): flattens a particle type -- valleys, cumulative rate tables,
+// device sampler descriptors -- into the plain structs the ABI takes, and turns
+// ABI failures into the API's error convention (emcMessage: print + abort,
+// reference include/emcMessage.hpp:43-65).
+//
+// There is no CPU path behind this header: a valley class without a device
+// dispersion or a scatter mechanism without a device sampler is an error that
+// names the offender.
+#ifndef EMC_GPU_BINDING_HPP
+#define EMC_GPU_BINDING_HPP
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <emcgpu.h>
+
+#include <ParticleType/emcParticleType.hpp>
+#include <emcMessage.hpp>
+
+namespace emcgpu {
+
+inline void require(emcgpu_ctx *ctx, int status, const std::string &what) {
+  if (status == EMCGPU_OK)
+    return;
+  emcMessage::getInstance()
+      .addError(what + " failed (emcgpu status " + std::to_string(status) + "): " + emcgpu_last_error(ctx))
+      .print();
+}
+
+// emcgpu_set_valleys + emcgpu_set_tables for one particle type.  To be called after
+// init/reinitScatterTables(); may be repeated whenever the tables were rebuilt.
+template <class T, class DeviceType> void uploadParticleType(emcgpu_ctx *ctx, const emcParticleType<T, DeviceType> &type) {
+  const SizeType nValleys = type.getNrValleys();
+  std::vector<emcgpu_valley_t> valleys(nValleys);
+  for (SizeType v = 0; v < nValleys; v++) {
+    const auto *valley = type.getValley(v);
+    emcgpu_valley_t &out = valleys[v];
+    std::memset(&out, 0, sizeof out);
+    out.kind = valley->deviceValleyKind();
+    if (out.kind < 0)
+      emcMessage::getInstance()
+          .addError("Valley " + std::to_string(v) + " of " + type.getName() +
+                    " has no device dispersion (deviceValleyKind() < 0); it cannot run on the GPU path and "
+                    "there is no CPU fallback.")
+          .print();
+    out.degeneracy = static_cast<int32_t>(valley->getDegeneracyFactor());
+    if (out.degeneracy > EMCGPU_MAX_SUBVALLEYS)
+      emcMessage::getInstance().addError("Valley degeneracy exceeds EMCGPU_MAX_SUBVALLEYS.").print();
+    out.effMassCond = valley->getEffMassCond();
+    out.effMassDOS = valley->getEffMassDOS();
+    out.alpha = valley->getNonParabolicity();
+    out.bottomEnergy = valley->getBottomEnergy();
+    const auto &vogt = valley->getVogtTransformationFactor();
+    for (int i = 0; i < 3; i++)
+      out.vogt[i] = vogt[i];
+    // column j of R_s = image of the unit vector e_j under the public transform
+    for (int s = 0; s < EMCGPU_MAX_SUBVALLEYS; s++) {
+      for (int j = 0; j < 3; j++) {
+        std::array<T, 3> e = {0, 0, 0};
+        e[j] = 1;
+        const auto col = s < out.degeneracy ? valley->transformToEllipseCoord(s, e) : e;
+        for (int i = 0; i < 3; i++)
+          out.rot[s][3 * i + j] = col[i];
+      }
+    }
+  }
+  require(ctx, emcgpu_set_valleys(ctx, valleys.data(), static_cast<int>(nValleys)), "emcgpu_set_valleys");
+
+  const auto &handler = type.scatterHandler;
+  const SizeType nLevels = handler.getNrEnergyLevels();
+  std::vector<emcgpu_tableset_t> sets;
+  std::vector<std::vector<double>> cumStore;
+  std::vector<std::vector<emcgpu_mech_t>> mechStore;
+  for (const auto &[key, set] : handler.getTableSets()) {
+    if (set.cum.empty())
+      continue; // no mechanisms: the device uses the default tau as well
+    cumStore.emplace_back();
+    mechStore.emplace_back();
+    auto &cum = cumStore.back();
+    auto &mechs = mechStore.back();
+    for (SizeType m = 0; m < set.cum.size(); m++) {
+      cum.insert(cum.end(), set.cum[m].begin(), set.cum[m].end());
+      const auto &mech = handler.getMechanism(set.mechanisms[m]);
+      const emcDeviceSamplerDesc desc = mech.deviceSampler(key.second);
+      emcgpu_mech_t out;
+      std::memset(&out, 0, sizeof out);
+      out.sampler = desc.samplerId;
+      out.finalValley = static_cast<int32_t>(desc.finalValley);
+      out.mechId = static_cast<int32_t>(set.mechanisms[m]);
+      for (int i = 0; i < 4; i++)
+        out.param[i] = desc.param[i];
+      std::strncpy(out.name, mech.getName().c_str(), EMCGPU_NAME_LEN - 1);
+      if (!desc.finalSubValleys.empty()) {
+        out.nFinal = static_cast<int32_t>(desc.finalSubValleys.begin()->second.size());
+        if (out.nFinal > EMCGPU_MAX_FINAL)
+          emcMessage::getInstance().addError(mech.getName() + ": too many final subvalleys for the device.").print();
+        for (const auto &[from, to] : desc.finalSubValleys) {
+          if (from >= EMCGPU_MAX_SUBVALLEYS || static_cast<int32_t>(to.size()) != out.nFinal)
+            emcMessage::getInstance()
+                .addError(mech.getName() + ": final subvalley lists must have equal length on the device.")
+                .print();
+          for (SizeType f = 0; f < to.size(); f++)
+            out.finalSub[from][f] = static_cast<uint8_t>(to[f]);
+        }
+      }
+      mechs.push_back(out);
+    }
+    emcgpu_tableset_t ts;
+    std::memset(&ts, 0, sizeof ts);
+    ts.valley = static_cast<int32_t>(key.first);
+    ts.region = static_cast<int32_t>(key.second);
+    ts.nMech = static_cast<int32_t>(set.cum.size());
+    ts.tau = set.tau;
+    sets.push_back(ts);
+  }
+  for (SizeType i = 0; i < sets.size(); i++) {
+    sets[i].cum = cumStore[i].data();
+    sets[i].mech = mechStore[i].data();
+  }
+  require(ctx, emcgpu_set_tables(ctx, sets.data(), static_cast<int>(sets.size()), static_cast<int>(nLevels),
+                                 handler.getMaxEnergy()),
+          "emcgpu_set_tables");
+}
+
+} // namespace emcgpu
+
+#endif
