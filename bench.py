@@ -195,7 +195,7 @@ def main_ours(args):
     import torch
     import torch.distributed as dist
 
-    from viennaemc_b200 import capi, hostapi
+    from viennaemc_b200 import capi, hostapi, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -231,7 +231,9 @@ def main_ours(args):
     ctx = capi.Context(local_rank)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     hostapi.si_upload(ctx, hostapi.si_spec(box=box, spacing=[b / 5 for b in box], doping=DOPING))
-    ctx.generate_bulk_ensemble(n_local, box, 300.0, 0, seed=SEED, particle_id_base=rank * n_local)
+    first_id, last_id = sharding.shard_range(n_total, rank, world)
+    assert last_id - first_id == n_local
+    ctx.generate_bulk_ensemble(n_local, box, 300.0, 0, seed=SEED, particle_id_base=first_id)
     ctx.rng_philox(SEED)
     ctx.bulk_configure(box, [-1, 0, 0], FIELD, math_mode=capi.MATH_FAST)
     ctx.set_step_index(1)
@@ -265,8 +267,7 @@ def main_ours(args):
 
     def run_steps():
         ctx.bulk_step_device(DT, K, 1, obs.data_ptr())
-        if world > 1:
-            dist.all_reduce(obs)  # the only communication of a bulk run
+        sharding.allreduce_observables(obs)  # the only communication of a bulk run (no-op for one rank)
 
     ms = timed(run_steps)
     clocks = sampler.stop() if rank == 0 else None
@@ -292,7 +293,7 @@ def main_ours(args):
         packed = host_packed.numpy().view(np.uint32)
         ctx.get_ensemble_into(streams, packed)  # the job's input now lives in (pinned) host memory
         obs_host = np.zeros((K, n_v, 3))
-        base_id = rank * n_local
+        base_id = first_id
 
         def run_e2e():
             ctx.set_ensemble_from(streams, packed, base_id)  # H2D, 68 B per particle
