@@ -879,3 +879,480 @@ int64_t orc_generate_initial(const orc_model_t *m, const double box[3], const in
     *drawsConsumed = rng.recCount;
   return n <= capacity ? n : -n;
 }
+
+/* ======================================================================================
+ * Device-run path.  All file:line citations relative to the reference tree.
+ * ====================================================================================== */
+int64_t orc_dev_cells(const orc_device_t *d) {
+  int64_t n = 1;
+  for (int i = 0; i < d->dim; i++)
+    n *= d->extent[i];
+  return n;
+}
+static void dev_coord(const orc_device_t *d, int64_t cell, int64_t c[3]) {
+  c[0] = cell % d->extent[0];
+  c[1] = (cell / d->extent[0]) % d->extent[1];
+  c[2] = d->dim > 2 ? cell / ((int64_t)d->extent[0] * d->extent[1]) : 0;
+}
+static int64_t dev_cell(const orc_device_t *d, const int64_t c[3]) {
+  int64_t idx = c[0] + (int64_t)d->extent[0] * c[1];
+  if (d->dim > 2)
+    idx += (int64_t)d->extent[0] * d->extent[1] * c[2];
+  return idx;
+}
+/* first face (XMIN, XMAX, YMIN, YMAX, ZMIN, ZMAX) the cell lies on, or -1 (emcSurface.hpp:340-349) */
+static int dev_first_face(const orc_device_t *d, int64_t cell) {
+  const int8_t *fc = d->faceContact + cell * 2 * d->dim;
+  for (int f = 0; f < 2 * d->dim; f++)
+    if (fc[f] != -2)
+      return f;
+  return -1;
+}
+int orc_dev_contact_idx(const orc_device_t *d, int64_t cell) {
+  int f = dev_first_face(d, cell);
+  return f < 0 ? -1 : d->faceContact[cell * 2 * d->dim + f];
+}
+int orc_dev_is_ohmic(const orc_device_t *d, int64_t cell) {
+  int c = orc_dev_contact_idx(d, cell);
+  return c >= 0 && d->contactType[c] == ORC_CONTACT_OHMIC;
+}
+int orc_dev_is_reservoir(const orc_device_t *d, int64_t cell) {
+  int c = orc_dev_contact_idx(d, cell);
+  return c >= 0 && (d->contactType[c] == ORC_CONTACT_OHMIC || d->contactType[c] == ORC_CONTACT_SCHOTTKY);
+}
+/* emcDevice.hpp:274-281 posToCoord: round(pos / spacing) per dimension */
+static int64_t dev_pos_to_cell(const orc_device_t *d, const double pos[3]) {
+  int64_t c[3] = {0, 0, 0};
+  for (int i = 0; i < d->dim; i++)
+    c[i] = (int64_t)round(pos[i] / d->spacing[i]);
+  return dev_cell(d, c);
+}
+
+void orc_initial_potential(const orc_device_t *d, double *pot) {
+  const int64_t n = orc_dev_cells(d);
+  for (int64_t i = 0; i < n; i++)
+    pot[i] = asinh(0.5 * (d->doping[i] / d->ni));
+}
+
+int orc_sor(const orc_device_t *d, double *pot, const double *conc, double accuracyVolt, double omega, int resetBC,
+            int maxSweeps) {
+  const int dim = d->dim;
+  const int64_t n = orc_dev_cells(d);
+  /* emcSORSolver.hpp:27, :330-368 */
+  const double accuracy = accuracyVolt / d->thermalVoltage;
+  double h[3], hF[3];
+  for (int i = 0; i < dim; i++)
+    h[i] = d->spacing[i] / d->debyeLength;
+  if (dim == 2) {
+    hF[0] = h[1] / h[0];
+    hF[1] = h[0] / h[1];
+  } else {
+    hF[0] = h[1] * h[2] / h[0];
+    hF[1] = h[0] * h[2] / h[1];
+    hF[2] = h[0] * h[1] / h[2];
+  }
+  double hFSum = 0., hProd = 1.;
+  for (int i = 0; i < dim; i++) {
+    hFSum += hF[i];
+    hProd = hProd * h[i];
+  }
+  int64_t stride[3] = {1, d->extent[0], (int64_t)d->extent[0] * d->extent[1]};
+  if (resetBC) {
+    /* :57-73 / :139-155: faces in the order XMIN, XMAX, YMIN, ... ; ohmic cells become Dirichlet values */
+    for (int f = 0; f < 2 * dim; f++)
+      for (int64_t cell = 0; cell < n; cell++) {
+        int c = d->faceContact[cell * 2 * dim + f];
+        if (c >= 0 && d->contactType[c] == ORC_CONTACT_OHMIC) {
+          double builtIn = asinh(0.5 * (d->doping[cell] / d->ni));
+          pot[cell] = conc ? d->contactVoltage[c] / d->thermalVoltage + builtIn : builtIn;
+        }
+      }
+  }
+  int sweeps = 0;
+  double error;
+  do {
+    error = 0;
+    for (int64_t cell = 0; cell < n; cell++) {
+      if (orc_dev_is_reservoir(d, cell))
+        continue;
+      int64_t c[3];
+      dev_coord(d, cell, c);
+      const double cur = pot[cell];
+      double p, nn;
+      if (conc) {
+        p = exp(-cur);
+        nn = conc[cell];
+      } else {
+        nn = exp(cur);
+        p = 1. / nn;
+      }
+      const double dop = d->doping[cell] / d->ni;
+      double num = hProd * (p - nn + dop + cur * (p + nn));
+      double den = 2 * hFSum + hProd * (nn + p);
+      for (int i = 0; i < dim; i++) {
+        for (int side = 0; side < 2; side++) {
+          const int atFace = side == 0 ? c[i] == 0 : c[i] == d->extent[i] - 1;
+          if (!atFace) {
+            num += pot[cell + (side == 0 ? -stride[i] : stride[i])] * hF[i];
+          } else {
+            num += pot[cell + (side == 0 ? stride[i] : -stride[i])] * hF[i]; /* mirror */
+            /* checkForGateContact :399-412 */
+            int ct = d->faceContact[cell * 2 * dim + 2 * i + side];
+            if (ct >= 0 && d->contactType[ct] == ORC_CONTACT_GATE) {
+              double gammaOx = d->gateEpsOx[ct] / d->epsR;
+              double tOx = d->gateThickness[ct] / d->debyeLength;
+              double gF = 2 * gammaOx / tOx;
+              double Vg = d->gateBarrier[ct] / d->thermalVoltage;
+              if (conc)
+                Vg += d->contactVoltage[ct] / d->thermalVoltage;
+              num += gF * Vg * hF[i] * h[i];
+              den += gF * hF[i] * h[i];
+            }
+          }
+        }
+      }
+      const double delta = omega * (num / den - cur);
+      pot[cell] = cur + delta;
+      if (fabs(delta) > error)
+        error = fabs(delta);
+    }
+    sweeps++;
+  } while (error > accuracy && (maxSweeps <= 0 || sweeps < maxSweeps));
+  return sweeps;
+}
+
+void orc_efield(const orc_device_t *d, const double *pot, double *e) {
+  const int dim = d->dim;
+  const int64_t n = orc_dev_cells(d);
+  int64_t stride[3] = {1, d->extent[0], (int64_t)d->extent[0] * d->extent[1]};
+  for (int i = 0; i < dim; i++) {
+    double *ed = e + (int64_t)i * n;
+    for (int64_t cell = 0; cell < n; cell++) {
+      int64_t c[3];
+      dev_coord(d, cell, c);
+      if (c[i] != 0 && c[i] != d->extent[i] - 1)
+        ed[cell] = ((pot[cell - stride[i]] - pot[cell + stride[i]]) * d->thermalVoltage) / (2 * d->spacing[i]);
+    }
+    /* setEFieldBoundaryValues :58-82: normal component 0 on artificial boundaries, copied from the
+     * inner neighbour at contacts */
+    for (int64_t cell = 0; cell < n; cell++) {
+      int64_t c[3];
+      dev_coord(d, cell, c);
+      if (c[i] == 0) {
+        int ct = d->faceContact[cell * 2 * dim + 2 * i];
+        ed[cell] = ct == -1 ? 0. : ed[cell + stride[i]];
+      } else if (c[i] == d->extent[i] - 1) {
+        int ct = d->faceContact[cell * 2 * dim + 2 * i + 1];
+        ed[cell] = ct == -1 ? 0. : ed[cell - stride[i]];
+      }
+    }
+  }
+}
+
+int orc_ngp_assign(const orc_device_t *d, int64_t n, const double *x, const double *y, const double *z,
+                   double nrCarriers, double *count) {
+  for (int64_t p = 0; p < n; p++) {
+    const double pos[3] = {x[p], y[p], d->dim > 2 ? z[p] : 0.};
+    count[dev_pos_to_cell(d, pos)] += nrCarriers;
+  }
+  return 0;
+}
+
+void orc_concentration(const orc_device_t *d, const double *count, double *conc) {
+  const int64_t n = orc_dev_cells(d);
+  const double factor = 1. / d->cellVolume;
+  for (int64_t cell = 0; cell < n; cell++) {
+    int64_t c[3];
+    dev_coord(d, cell, c);
+    double v = (count[cell] / d->ni) * factor;
+    for (int i = 0; i < d->dim; i++)
+      if (c[i] == 0 || c[i] == d->extent[i] - 1)
+        v *= 2;
+    conc[cell] = v;
+  }
+}
+
+void orc_expected_at_contact(const orc_device_t *d, double *expected) {
+  const int64_t n = orc_dev_cells(d);
+  for (int64_t cell = 0; cell < n; cell++) {
+    expected[cell] = 0;
+    if (!orc_dev_is_reservoir(d, cell))
+      continue;
+    int64_t c[3];
+    dev_coord(d, cell, c);
+    double v = d->cellVolume * d->doping[cell];
+    for (int i = 0; i < d->dim; i++)
+      if (c[i] == 0 || c[i] == d->extent[i] - 1)
+        v *= 0.5;
+    expected[cell] = v;
+  }
+}
+
+/* emcBasicParticleHandler.hpp:239-253 addParticle: position (emcParticleInitialization.hpp:14-29), then
+ * emcElectron::generate{Initial,Injected}Particle (emcElectron.hpp:75-104) */
+static void dev_create_particle(const orc_model_t *m, const orc_device_t *d, const int64_t c[3], rng_t *rng,
+                                orc_ensemble_t *out, int64_t slot) {
+  double pos[3] = {0, 0, 0};
+  for (int i = 0; i < d->dim; i++) {
+    if (c[i] == d->extent[i] - 1)
+      pos[i] = ((double)c[i] - rng_u01(rng) * 0.5) * d->spacing[i];
+    else if (c[i] == 0)
+      pos[i] = rng_u01(rng) * 0.5 * d->spacing[i];
+    else
+      pos[i] = ((double)c[i] + rng_u01(rng) - 0.5) * d->spacing[i];
+  }
+  const int region = d->region[dev_cell(d, c)];
+  const int valley = (int)floor(m->nValleys * rng_ulog(rng));
+  const orc_valley_t *v = &m->valleys[valley];
+  const int sub = (int)floor(v->deg * rng_ulog(rng));
+  const double energy = -1.5 * d->thermalVoltage * log(rng_ulog(rng));
+  const double r2 = rng_u01(rng);
+  const double r1 = rng_u01(rng);
+  double k[3];
+  orc_random_direction(orc_norm_wave_vec(v, energy), r1, r2, k);
+  for (int i = 0; i < d->dim; i++)
+    if ((c[i] == 0 && k[i] < 0) || (c[i] == d->extent[i] - 1 && k[i] > 0))
+      k[i] *= -1;
+  const double tau = -log(rng_ulog(rng)) * orc_tau(m, valley, region);
+  const double gtau = -log(rng_ulog(rng)) * 1.;
+  if (slot >= 0) {
+    out->kx[slot] = k[0]; out->ky[slot] = k[1]; out->kz[slot] = k[2];
+    out->energy[slot] = energy;
+    out->tau[slot] = tau;
+    if (out->grainTau)
+      out->grainTau[slot] = gtau;
+    out->x[slot] = pos[0]; out->y[slot] = pos[1]; out->z[slot] = pos[2];
+    out->valley[slot] = valley;
+    out->sub[slot] = sub;
+    out->region[slot] = region;
+  }
+}
+
+int64_t orc_device_generate_initial(const orc_model_t *m, const orc_device_t *d, double nrCarriers, uint64_t *mtState,
+                                    orc_ensemble_t *out, int64_t capacity) {
+  orc_rng_cfg_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.mode = ORC_RNG_MT_GLOBAL;
+  cfg.mtState = mtState;
+  rng_t rng;
+  memset(&rng, 0, sizeof rng);
+  rng.cfg = &cfg;
+  const int64_t cells = orc_dev_cells(d);
+  int64_t n = 0;
+  for (int64_t cell = 0; cell < cells; cell++) {
+    int64_t c[3];
+    dev_coord(d, cell, c);
+    double dens = d->doping[cell]; /* emcElectron.hpp:48-61, usePotentialForInit == false */
+    for (int i = 0; i < d->dim; i++)
+      if (c[i] == 0 || c[i] == d->extent[i] - 1)
+        dens *= 0.5;
+    double nr = dens * d->cellVolume;
+    while (nr >= 1) { /* emcAbstractParticleHandler.hpp:139-146 */
+      dev_create_particle(m, d, c, &rng, out, n < capacity ? n : -1);
+      n++;
+      nr -= nrCarriers;
+    }
+    if (rng_u01(&rng) < nr) {
+      dev_create_particle(m, d, c, &rng, out, n < capacity ? n : -1);
+      n++;
+    }
+  }
+  out->n = n <= capacity ? n : capacity;
+  return n <= capacity ? n : -n;
+}
+
+/* emcAbstractParticleHandler.hpp:238-249 driftParticle = drift + handleParticleAtBoundary
+ * (emcParticleDrift.hpp:42-66, default specular reflection emcScatterHandler.hpp:172-191) + region update */
+static int dev_drift_particle(const orc_model_t *m, const orc_device_t *d, orc_ensemble_t *e, int64_t p, double dt,
+                              const double force[3]) {
+  double k[3] = {e->kx[p], e->ky[p], e->kz[p]};
+  double pos[3] = {e->x[p], e->y[p], d->dim > 2 ? e->z[p] : 0.};
+  orc_drift(&m->valleys[e->valley[p]], dt, k, &e->energy[p], e->sub[p], pos, d->dim, force);
+  int removed = 0, out = 0;
+  for (int i = 0; i < d->dim; i++)
+    if (pos[i] < 0 || pos[i] > d->maxPos[i])
+      out = 1;
+  if (out) {
+    double clamped[3] = {0, 0, 0};
+    for (int i = 0; i < d->dim; i++) {
+      double lo = pos[i] < d->maxPos[i] ? pos[i] : d->maxPos[i]; /* std::max(0., std::min(pos, max)) */
+      clamped[i] = 0. > lo ? 0. : lo;
+    }
+    if (orc_dev_is_ohmic(d, dev_pos_to_cell(d, clamped))) {
+      removed = 1;
+      for (int i = 0; i < d->dim; i++)
+        pos[i] = clamped[i];
+    } else {
+      for (int i = 0; i < d->dim; i++) {
+        if (pos[i] < 0) {
+          pos[i] = -pos[i];
+          k[i] = -k[i];
+        } else if (pos[i] > d->maxPos[i]) {
+          pos[i] = 2 * d->maxPos[i] - pos[i];
+          k[i] = -k[i];
+        }
+      }
+    }
+  }
+  e->kx[p] = k[0]; e->ky[p] = k[1]; e->kz[p] = k[2];
+  e->x[p] = pos[0]; e->y[p] = pos[1];
+  if (d->dim > 2)
+    e->z[p] = pos[2];
+  if (!removed)
+    e->region[p] = d->region[dev_pos_to_cell(d, pos)];
+  return removed;
+}
+
+/* emcNGPScheme.hpp:51-66 */
+static void dev_force(const orc_device_t *d, const orc_ensemble_t *e, int64_t p, const double *ef, double charge,
+                      double force[3]) {
+  const double pos[3] = {e->x[p], e->y[p], d->dim > 2 ? e->z[p] : 0.};
+  const int64_t cell = dev_pos_to_cell(d, pos), n = orc_dev_cells(d);
+  force[2] = 0;
+  for (int i = 0; i < d->dim; i++)
+    force[i] = charge * ef[(int64_t)i * n + cell];
+}
+
+int orc_device_step(const orc_model_t *m, const orc_device_t *d, orc_ensemble_t *e, const double *ef, double charge,
+                    double dt, int64_t stepIndex, const orc_rng_cfg_t *cfg, int8_t *removedOut,
+                    int32_t *removedPerContact, int32_t *recPid, int64_t recCap, int64_t *recCount, int64_t *events,
+                    int64_t evCap, int64_t *evCount) {
+  rng_t rng;
+  memset(&rng, 0, sizeof rng);
+  rng.cfg = cfg;
+  rng.recPid = recPid;
+  rng.recCap = recCap;
+  int64_t nEv = 0;
+  orc_mech_t desc;
+  for (int c = 0; c < d->nContacts; c++)
+    removedPerContact[c] = 0;
+  for (int64_t p = 0; p < e->n; p++) {
+    rng.particle = p;
+    rng.step = (uint64_t)stepIndex;
+    rng.k = 0;
+    double force[3];
+    dev_force(d, e, p, ef, charge, force);
+    int removed = 0;
+    double tau = e->tau[p];
+    if (tau >= dt) {
+      removed = dev_drift_particle(m, d, e, p, dt, force);
+    } else {
+      removed = dev_drift_particle(m, d, e, p, tau, force);
+      double tRem = dt - tau;
+      while (tRem > 0 && !removed) {
+        int si = find_set(m, e->valley[p], e->region[p]);
+        int t = -2;
+        if (si >= 0 && m->sets[si].nMech > 0) {
+          double r = rng_u01(&rng);
+          t = orc_select(m, si, e->energy[p], r);
+          if (t >= 0) {
+            fill_mech_desc(m, m->sets[si].mechIdx[t], &desc);
+            scatter_with(m, &desc, e, p, &rng);
+          }
+          if (events && nEv < evCap) {
+            events[nEv * 4 + 0] = stepIndex;
+            events[nEv * 4 + 1] = p;
+            events[nEv * 4 + 2] = t;
+            events[nEv * 4 + 3] = t >= 0 ? m->sets[si].mechIdx[t] : -1;
+          }
+          nEv++;
+        }
+        double newTau = -log(rng_ulog(&rng)) * orc_tau(m, e->valley[p], e->region[p]);
+        tau += newTau;
+        dev_force(d, e, p, ef, charge, force);
+        removed = dev_drift_particle(m, d, e, p, tRem < newTau ? tRem : newTau, force);
+        tRem -= newTau;
+      }
+    }
+    tau -= dt;
+    e->tau[p] = tau;
+    removedOut[p] = (int8_t)removed;
+    if (removed) {
+      const double pos[3] = {e->x[p], e->y[p], d->dim > 2 ? e->z[p] : 0.};
+      removedPerContact[orc_dev_contact_idx(d, dev_pos_to_cell(d, pos))]++;
+    }
+    if (e->grainTau)
+      e->grainTau[p] -= dt; /* no grain mechanism in the device configs: the clock never fires (1 s) */
+  }
+  if (recCount)
+    *recCount = rng.recCount;
+  if (evCount)
+    *evCount = nEv;
+  return 0;
+}
+
+static void ens_move(orc_ensemble_t *e, int64_t dst, int64_t src) {
+  e->kx[dst] = e->kx[src]; e->ky[dst] = e->ky[src]; e->kz[dst] = e->kz[src];
+  e->energy[dst] = e->energy[src];
+  e->tau[dst] = e->tau[src];
+  if (e->grainTau)
+    e->grainTau[dst] = e->grainTau[src];
+  e->x[dst] = e->x[src]; e->y[dst] = e->y[src]; e->z[dst] = e->z[src];
+  e->valley[dst] = e->valley[src]; e->sub[dst] = e->sub[src]; e->region[dst] = e->region[src];
+}
+
+int64_t orc_compact(orc_ensemble_t *e, const int8_t *removed) {
+  int64_t w = 0;
+  for (int64_t p = 0; p < e->n; p++)
+    if (!removed[p]) {
+      if (w != p)
+        ens_move(e, w, p);
+      w++;
+    }
+  e->n = w;
+  return w;
+}
+
+int64_t orc_contacts(const orc_model_t *m, const orc_device_t *d, orc_ensemble_t *e, int64_t capacity,
+                     const double *expected, double nrCarriers, uint64_t *mtState, int32_t *net) {
+  const int64_t cells = orc_dev_cells(d);
+  double *have = (double *)calloc((size_t)cells, sizeof(double));
+  for (int c = 0; c < d->nContacts; c++)
+    net[c] = 0;
+  /* :165-181: scan in index order, keep a particle while the cell is below its expected population */
+  int64_t w = 0;
+  for (int64_t p = 0; p < e->n; p++) {
+    const double pos[3] = {e->x[p], e->y[p], d->dim > 2 ? e->z[p] : 0.};
+    const int64_t cell = dev_pos_to_cell(d, pos);
+    int keep = 1;
+    if (orc_dev_is_reservoir(d, cell)) {
+      if (have[cell] < expected[cell])
+        have[cell] += nrCarriers;
+      else {
+        keep = 0;
+        net[orc_dev_contact_idx(d, cell)]--;
+      }
+    }
+    if (keep) {
+      if (w != p)
+        ens_move(e, w, p);
+      w++;
+    }
+  }
+  e->n = w;
+  /* emcAbstractParticleHandler.hpp:200-216 generateInjectedParticles */
+  orc_rng_cfg_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.mode = ORC_RNG_MT_GLOBAL;
+  cfg.mtState = mtState;
+  rng_t rng;
+  memset(&rng, 0, sizeof rng);
+  rng.cfg = &cfg;
+  int64_t total = w;
+  for (int64_t cell = 0; cell < cells; cell++) {
+    if (!orc_dev_is_reservoir(d, cell))
+      continue;
+    int64_t c[3];
+    dev_coord(d, cell, c);
+    double diff = expected[cell] - have[cell];
+    while (diff > 0) {
+      dev_create_particle(m, d, c, &rng, e, total < capacity ? total : -1);
+      total++;
+      net[orc_dev_contact_idx(d, cell)]++;
+      diff -= nrCarriers;
+    }
+  }
+  free(have);
+  e->n = total <= capacity ? total : capacity;
+  return total <= capacity ? total : -total;
+}

@@ -149,4 +149,64 @@ void orc_bulk_observables(const orc_model_t *m, const orc_ensemble_t *ens,
 #ifdef __cplusplus
 }
 #endif
+
+/* ======================================================================================
+ * Device-run path.  Parity status: PINNED against
+ * oracle/_ref/ref_device_driver (unmodified reference headers; fixtures tests/golden/device_*.npz).
+ * ====================================================================================== */
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { ORC_CONTACT_OHMIC = 0, ORC_CONTACT_SCHOTTKY = 1, ORC_CONTACT_GATE = 2 }; /* emcContact.hpp */
+
+typedef struct {
+  int32_t dim; /* 2 or 3 */
+  int32_t extent[3];
+  double spacing[3], maxPos[3];
+  double thermalVoltage, debyeLength, ni, cellVolume, epsR;
+  int32_t nContacts;
+  const int32_t *contactType;
+  const double *contactVoltage, *gateEpsOx, *gateThickness, *gateBarrier; /* [nContacts] */
+  const int32_t *region;     /* [cells], x fastest */
+  const int8_t *faceContact; /* [cells][2*dim]: -2 cell not on that face, -1 artificial boundary, >= 0 contact */
+  const double *doping;      /* [cells], 1/m^3 */
+} orc_device_t;
+
+int64_t orc_dev_cells(const orc_device_t *d);
+int orc_dev_is_ohmic(const orc_device_t *d, int64_t cell);     /* emcSurface.hpp isOhmicContact */
+int orc_dev_is_reservoir(const orc_device_t *d, int64_t cell); /* isReservoirContact */
+int orc_dev_contact_idx(const orc_device_t *d, int64_t cell);  /* getOhmicContactIdx */
+
+/* emcSimulationResults.hpp:208-213 */
+void orc_initial_potential(const orc_device_t *d, double *pot);
+/* emcSORSolver.hpp:49-128 (conc == NULL) / :131-197; returns the number of sweeps */
+int orc_sor(const orc_device_t *d, double *pot, const double *conc, double accuracyVolt, double omega, int resetBC,
+            int maxSweeps);
+/* emcEFieldCalculation.hpp:13-30, :58-82; e[dim][cells] */
+void orc_efield(const orc_device_t *d, const double *pot, double *e);
+/* emcNGPScheme.hpp:36-47 (adds to count) */
+int orc_ngp_assign(const orc_device_t *d, int64_t n, const double *x, const double *y, const double *z,
+                   double nrCarriers, double *count);
+/* emcSimulationResults.hpp:98-116 */
+void orc_concentration(const orc_device_t *d, const double *count, double *conc);
+/* emcAbstractParticleHandler.hpp:263-277 + emcElectron.hpp:63-73 */
+void orc_expected_at_contact(const orc_device_t *d, double *expected);
+/* emcAbstractParticleHandler.hpp:133-148 with density from the doping (usePotentialForInit = false) */
+int64_t orc_device_generate_initial(const orc_model_t *m, const orc_device_t *d, double nrCarriers, uint64_t *mtState,
+                                    orc_ensemble_t *out, int64_t capacity);
+/* emcBasicParticleHandler.hpp:76-145 for one step: per-particle removed flags and per-contact counts; the
+ * ensemble is NOT compacted (orc_compact does that, keeping the order like removeParticles :267-277). */
+int orc_device_step(const orc_model_t *m, const orc_device_t *d, orc_ensemble_t *ens, const double *e, double charge,
+                    double dt, int64_t stepIndex, const orc_rng_cfg_t *rng, int8_t *removed, int32_t *removedPerContact,
+                    int32_t *recPid, int64_t recCap, int64_t *recCount, int64_t *events, int64_t evCap, int64_t *evCount);
+int64_t orc_compact(orc_ensemble_t *ens, const int8_t *removed);
+/* emcBasicParticleHandler.hpp:158-192: delete excess reservoir particles in index order, inject the missing
+ * ones (cells in storage order, draws from the global mt19937_64); net[contact] = injected - deleted */
+int64_t orc_contacts(const orc_model_t *m, const orc_device_t *d, orc_ensemble_t *ens, int64_t capacity,
+                     const double *expected, double nrCarriers, uint64_t *mtState, int32_t *net);
+
+#ifdef __cplusplus
+}
+#endif
 #endif

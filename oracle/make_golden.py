@@ -18,7 +18,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from scenarios import GOLDEN_CASES  # noqa: E402
+from scenarios import DEVICE_CASES, GOLDEN_CASES  # noqa: E402
 
 DT = {"d": np.float64, "q": np.int64, "Q": np.uint64}
 
@@ -58,5 +58,25 @@ def main():
               "draws", len(blob["draws"]), "events", len(blob["events"]))
 
 
+def main_device():
+    subprocess.check_call(["make", "-C", HERE, "_ref/ref_device_driver"], stdout=subprocess.DEVNULL,
+                          stderr=subprocess.DEVNULL)
+    drv = os.path.join(HERE, "_ref", "ref_device_driver")
+    for name, args in DEVICE_CASES.items():
+        with tempfile.TemporaryDirectory() as tmp:
+            out = os.path.join(tmp, "ref.bin")
+            cmd = [drv, "--out", out]
+            for k, v in args.items():
+                cmd += ["--" + k, str(v)]
+            subprocess.check_call(cmd, cwd=tmp, stdout=subprocess.DEVNULL)
+            blob = read_blob(out)
+        dst = os.path.join(ROOT, "tests", "golden", name + ".npz")
+        np.savez_compressed(dst, **blob)
+        print(name, "->", dst, os.path.getsize(dst) // 1024, "KiB; draws", len(blob["draws"]))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) < 2 or sys.argv[1] != "device":
+        main()
+    if len(sys.argv) < 2 or sys.argv[1] == "device":
+        main_device()

@@ -351,3 +351,227 @@ def streams_from_record(draws: np.ndarray, rec_pid: np.ndarray, n: int):
     offsets = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(counts, out=offsets[1:])
     return np.ascontiguousarray(draws[order]), offsets
+
+
+# ======================================================================================
+# Device-run path (orc_device_t and friends)
+CONTACT_OHMIC, CONTACT_SCHOTTKY, CONTACT_GATE = range(3)
+_I8P = C.POINTER(C.c_int8)
+
+
+class DeviceC(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("extent", C.c_int32 * 3), ("spacing", C.c_double * 3),
+                ("maxPos", C.c_double * 3), ("thermalVoltage", C.c_double), ("debyeLength", C.c_double),
+                ("ni", C.c_double), ("cellVolume", C.c_double), ("epsR", C.c_double), ("nContacts", C.c_int32),
+                ("contactType", _IP), ("contactVoltage", _DP), ("gateEpsOx", _DP), ("gateThickness", _DP),
+                ("gateBarrier", _DP), ("region", _IP), ("faceContact", _I8P), ("doping", _DP)]
+
+
+_DEV_BOUND = False
+
+
+def _bind_device(L):
+    global _DEV_BOUND
+    if _DEV_BOUND:
+        return
+    dp = C.POINTER(DeviceC)
+    L.orc_dev_cells.restype = C.c_int64
+    L.orc_dev_cells.argtypes = [dp]
+    L.orc_initial_potential.argtypes = [dp, _DP]
+    L.orc_sor.argtypes = [dp, _DP, _DP, C.c_double, C.c_double, C.c_int, C.c_int]
+    L.orc_efield.argtypes = [dp, _DP, _DP]
+    L.orc_ngp_assign.argtypes = [dp, C.c_int64, _DP, _DP, _DP, C.c_double, _DP]
+    L.orc_concentration.argtypes = [dp, _DP, _DP]
+    L.orc_expected_at_contact.argtypes = [dp, _DP]
+    L.orc_device_generate_initial.restype = C.c_int64
+    L.orc_device_generate_initial.argtypes = [C.c_void_p, dp, C.c_double, C.POINTER(C.c_uint64),
+                                              C.POINTER(EnsembleC), C.c_int64]
+    L.orc_device_step.argtypes = [C.c_void_p, dp, C.POINTER(EnsembleC), _DP, C.c_double, C.c_double, C.c_int64,
+                                  C.POINTER(RngCfg), _I8P, _IP, _IP, C.c_int64, C.POINTER(C.c_int64),
+                                  C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64)]
+    L.orc_compact.restype = C.c_int64
+    L.orc_compact.argtypes = [C.POINTER(EnsembleC), _I8P]
+    L.orc_contacts.restype = C.c_int64
+    L.orc_contacts.argtypes = [C.c_void_p, dp, C.POINTER(EnsembleC), C.c_int64, _DP, C.c_double,
+                               C.POINTER(C.c_uint64), _IP]
+    _DEV_BOUND = True
+
+
+KB, EPS0 = 1.38066e-23, 8.85419e-12
+
+
+class Device:
+    """Box device with doping regions and contacts, flattened the way the C ABI takes it
+    (reference: emcDevice.hpp, emcDopingProfile.hpp, emcSurface.hpp)."""
+
+    def __init__(self, max_pos, spacing, temperature=300.0, eps_r=11.8, ni=1.45e16, device_width=1e-6):
+        self.L = lib()
+        _bind_device(self.L)
+        self.dim = len(max_pos)
+        self.max_pos = [float(x) for x in max_pos]
+        self.spacing = [float(x) for x in spacing]
+        self.extent = [int(round(m / h)) + 1 for m, h in zip(max_pos, spacing)]  # emcUtil.hpp:109-119
+        self.cells = int(np.prod(self.extent))
+        self.vt = KB / Q * temperature  # emcDevice.hpp:87
+        self.ni, self.eps_r = ni, eps_r
+        self.debye = float(np.sqrt(EPS0 * eps_r * self.vt / Q / ni))  # emcDevice.hpp:88-90
+        vol = 1.0
+        for h in self.spacing:
+            vol = vol * h
+        if self.dim == 2:
+            vol *= device_width
+        self.cell_volume = vol
+        self.doping = np.full(self.cells, ni, dtype=np.float64)
+        self.region = np.full(self.cells, -1, dtype=np.int32)
+        self.n_regions = 0
+        self.face_contact = np.full((self.cells, 2 * self.dim), -2, dtype=np.int8)
+        coords = self.coords()
+        for d in range(self.dim):
+            self.face_contact[coords[:, d] == 0, 2 * d] = -1
+            self.face_contact[coords[:, d] == self.extent[d] - 1, 2 * d + 1] = -1
+        self.contact_type, self.contact_voltage = [], []
+        self.gate_eps, self.gate_thick, self.gate_barrier = [], [], []
+
+    def coords(self):
+        idx = np.arange(self.cells)
+        out = np.zeros((self.cells, self.dim), dtype=np.int64)
+        for d in range(self.dim):
+            out[:, d] = idx % self.extent[d]
+            idx = idx // self.extent[d]
+        return out
+
+    def _to_coord(self, pos, spacing):
+        return int(np.floor(abs(pos / spacing) + 0.5) * (1 if pos >= 0 else -1))  # std::round
+
+    def add_doping_region(self, lo, hi, doping):
+        c = self.coords()
+        inside = np.ones(self.cells, dtype=bool)
+        for d in range(self.dim):
+            a, b = self._to_coord(lo[d], self.spacing[d]), self._to_coord(hi[d], self.spacing[d])
+            inside &= (c[:, d] >= min(a, b)) & (c[:, d] <= max(a, b))
+        self.doping[inside] = doping
+        self.region[inside] = self.n_regions
+        self.n_regions += 1
+
+    def add_contact(self, face, kind, voltage, lo, hi, eps_ox=0.0, thickness=0.0, barrier=0.0):
+        """face: 0 XMIN, 1 XMAX, 2 YMIN, ...; lo/hi: positions along the face's own axes (emcDevice.hpp:178-215)"""
+        idx = len(self.contact_type)
+        fixed = face // 2
+        axes = [d for d in range(self.dim) if d != fixed]
+        c = self.coords()
+        on_face = c[:, fixed] == (0 if face % 2 == 0 else self.extent[fixed] - 1)
+        sel = on_face.copy()
+        for a, l, h in zip(axes, lo, hi):
+            ca, cb = self._to_coord(l, self.spacing[a]), self._to_coord(h, self.spacing[a])
+            sel &= (c[:, a] >= ca) & (c[:, a] <= cb)
+        self.face_contact[sel, face] = idx
+        if kind in (CONTACT_OHMIC, CONTACT_SCHOTTKY):
+            # emcSurface.hpp:351-381 updateAllOccurences: the contact also owns those cells on the other faces
+            for f in range(2 * self.dim):
+                on_f = self.face_contact[:, f] != -2
+                self.face_contact[sel & on_f, f] = idx
+        self.contact_type.append(kind)
+        self.contact_voltage.append(float(voltage))
+        self.gate_eps.append(float(eps_ox))
+        self.gate_thick.append(float(thickness))
+        self.gate_barrier.append(float(barrier))
+        return idx
+
+    def c(self) -> DeviceC:
+        d = DeviceC()
+        d.dim = self.dim
+        for i in range(3):
+            d.extent[i] = self.extent[i] if i < self.dim else 1
+            d.spacing[i] = self.spacing[i] if i < self.dim else 1.0
+            d.maxPos[i] = self.max_pos[i] if i < self.dim else 0.0
+        d.thermalVoltage, d.debyeLength, d.ni, d.cellVolume, d.epsR = self.vt, self.debye, self.ni, self.cell_volume, self.eps_r
+        d.nContacts = len(self.contact_type)
+        self._keep = [np.asarray(self.contact_type, dtype=np.int32), np.asarray(self.contact_voltage, dtype=np.float64),
+                      np.asarray(self.gate_eps, dtype=np.float64), np.asarray(self.gate_thick, dtype=np.float64),
+                      np.asarray(self.gate_barrier, dtype=np.float64), np.ascontiguousarray(self.region),
+                      np.ascontiguousarray(self.face_contact), np.ascontiguousarray(self.doping)]
+        k = self._keep
+        d.contactType, d.contactVoltage, d.gateEpsOx, d.gateThickness, d.gateBarrier = _ip(k[0]), _dp(k[1]), _dp(k[2]), _dp(k[3]), _dp(k[4])
+        d.region, d.faceContact, d.doping = _ip(k[5]), k[6].ctypes.data_as(_I8P), _dp(k[7])
+        return d
+
+    # ---- grid operations
+    def initial_potential(self):
+        pot = np.zeros(self.cells)
+        self.L.orc_initial_potential(C.byref(self.c()), _dp(pot))
+        return pot
+
+    def sor(self, pot, conc=None, accuracy=1e-4, omega=1.8, reset_bc=True, max_sweeps=0):
+        sweeps = self.L.orc_sor(C.byref(self.c()), _dp(pot), _dp(conc) if conc is not None else None, accuracy, omega,
+                                int(reset_bc), max_sweeps)
+        return sweeps
+
+    def efield(self, pot):
+        e = np.zeros((self.dim, self.cells))
+        self.L.orc_efield(C.byref(self.c()), _dp(pot), _dp(e))
+        return e
+
+    def ngp_assign(self, ens, nr_carriers=1.0):
+        count = np.zeros(self.cells)
+        self.L.orc_ngp_assign(C.byref(self.c()), ens.n, _dp(ens.x), _dp(ens.y), _dp(ens.z), nr_carriers, _dp(count))
+        return count
+
+    def concentration(self, count):
+        conc = np.zeros(self.cells)
+        self.L.orc_concentration(C.byref(self.c()), _dp(count), _dp(conc))
+        return conc
+
+    def expected_at_contact(self):
+        e = np.zeros(self.cells)
+        self.L.orc_expected_at_contact(C.byref(self.c()), _dp(e))
+        return e
+
+    def generate_initial(self, model, mt, nr_carriers=1.0, capacity=None):
+        cap = capacity or int(self.doping.sum() * self.cell_volume * 1.2) + 1000
+        ens = Ensemble(cap)
+        c = ens.c()
+        n = self.L.orc_device_generate_initial(model.h, C.byref(self.c()), nr_carriers, C.cast(mt, C.POINTER(C.c_uint64)),
+                                               C.byref(c), cap)
+        assert n >= 0, "capacity too small"
+        ens.n = int(n)
+        return ens
+
+    def step(self, model, ens, efield, dt, rng, step_index=1, charge=-Q, record=False, log_events=False):
+        n = ens.n
+        removed = np.zeros(max(1, n), dtype=np.int8)
+        per_contact = np.zeros(max(1, len(self.contact_type)), dtype=np.int32)
+        rec_cap = 64 * n + 1024 if record else 0
+        rec = np.zeros(max(1, rec_cap), dtype=np.int32)
+        rec_count = C.c_int64(0)
+        ev_cap = 16 * n + 1024 if log_events else 0
+        ev = np.zeros((max(1, ev_cap), 4), dtype=np.int64)
+        ev_count = C.c_int64(0)
+        cfg = rng
+        c = ens.c()
+        ef = np.ascontiguousarray(efield, dtype=np.float64)
+        self.L.orc_device_step(model.h, C.byref(self.c()), C.byref(c), _dp(ef), charge, dt, step_index, C.byref(cfg),
+                               removed.ctypes.data_as(_I8P), _ip(per_contact), _ip(rec) if record else None, rec_cap,
+                               C.byref(rec_count), ev.ctypes.data_as(C.POINTER(C.c_int64)) if log_events else None, ev_cap,
+                               C.byref(ev_count))
+        out = dict(removed=removed[:n], removed_per_contact=per_contact[: len(self.contact_type)])
+        if record:
+            assert rec_count.value <= rec_cap
+            out["rec_pid"] = rec[: rec_count.value]
+        if log_events:
+            out["events"] = ev[: ev_count.value]
+        return out
+
+    def compact(self, ens, removed):
+        c = ens.c()
+        ens.n = int(self.L.orc_compact(C.byref(c), np.ascontiguousarray(removed, dtype=np.int8).ctypes.data_as(_I8P)))
+        return ens
+
+    def contacts(self, model, ens, expected, mt, nr_carriers=1.0):
+        net = np.zeros(max(1, len(self.contact_type)), dtype=np.int32)
+        cap = len(ens.kx)
+        c = ens.c()
+        n = self.L.orc_contacts(model.h, C.byref(self.c()), C.byref(c), cap, _dp(expected), nr_carriers,
+                                C.cast(mt, C.POINTER(C.c_uint64)), _ip(net))
+        assert n >= 0, "ensemble capacity too small for the injected particles"
+        ens.n = int(n)
+        return net[: len(self.contact_type)]

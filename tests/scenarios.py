@@ -97,3 +97,45 @@ GOLDEN_CASES = {
 def build_model(case: str):
     c = GOLDEN_CASES[case]
     return (build_si if c["builder"] == "si" else build_mixed)(**c["kwargs"])
+
+
+# device-run golden cases (oracle/_ref/ref_device_driver): name -> driver args.  2-D silicon bars with ohmic
+# contacts on the XMIN / XMAX faces (resistor2D.cpp scaled down); "device_gate" adds a gate contact on the
+# middle third of YMIN and a second doping region (Robin boundary term, region look-ups, per-region tables).
+DEVICE_CASES = {
+    "device_bar": dict(lx=2e-7, ly=1e-7, hx=1e-8, hy=2.5e-8, doping=1e22, doping2=0, voltage=0.05, dt=1e-15,
+                       steps=10, levels=1000, emax=4.0, gate=0, seed=5),
+    "device_gate": dict(lx=3e-7, ly=1e-7, hx=1e-8, hy=2e-8, doping=2e22, doping2=5e21, voltage=0.3, dt=5e-16,
+                        steps=6, levels=500, emax=4.0, gate=1, seed=9),
+}
+
+
+def build_device(case: str):
+    """oracle-side model + device of a DEVICE_CASES entry (mirrors oracle/ref_device_driver.cpp)"""
+    a = DEVICE_CASES[case]
+    regions = (0, 1) if a["doping2"] else (0,)
+    dev = po.Device([a["lx"], a["ly"]], [a["hx"], a["hy"]], device_width=1e-6)
+    dev.add_doping_region([0, 0], [a["lx"], a["ly"]], a["doping"])
+    if a["doping2"]:
+        dev.add_doping_region([a["lx"] / 2, 0], [a["lx"], a["ly"]], a["doping2"])
+    dev.add_contact(1, po.CONTACT_OHMIC, 0.0, [0.0], [a["ly"]])
+    dev.add_contact(0, po.CONTACT_OHMIC, a["voltage"], [0.0], [a["ly"]])
+    if a["gate"]:
+        dev.add_contact(2, po.CONTACT_GATE, 0.5, [a["lx"] / 3], [2 * a["lx"] / 3], 3.9, 1.2e-9, 1.15 / 2)
+    m = po.Model(a["levels"], a["emax"], 300.0, 2329.0, 9040.0)
+    m.add_valley(po.VALLEY_NONPARABOLIC_ANISO, [0.916, 0.196, 0.196], 3, 0.5, 0.0, SI_DIRS)
+    dop = [a["doping"], a["doping2"]]
+    # mechanism order of the driver: Acoustic, Zero x4, First x4, Coulomb -- each added for all regions at once
+    for reg in regions:
+        m.add_acoustic(0, reg, 9.0)
+    for emission, sub in ((False, SI_F), (True, SI_F), (False, SI_G), (True, SI_G)):
+        for reg in regions:
+            m.add_intervalley(0, emission, 0, 0, reg, 5.23e10, 0.06, sub)
+    for (dp, hw), sub in (((2.5, 0.023), SI_F), ((4.0, 0.018), SI_G)):
+        for emission in (False, True):
+            for reg in regions:
+                m.add_intervalley(1, emission, 0, 0, reg, dp, hw, sub)
+    for reg in regions:
+        m.add_coulomb(0, reg, 11.8, dop[reg])
+    m.build_tables()
+    return m, dev

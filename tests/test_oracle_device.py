@@ -1,0 +1,119 @@
+"""CPU: the device-run part of the oracle (oracle/emc_oracle.c, orc_device_* / orc_sor / orc_efield / ...)
+against the UNMODIFIED reference (tests/golden/device_*.npz, recorded by oracle/_ref/ref_device_driver from
+emcSORSolver, calcEFieldAtGridPts, emcNGPScheme, emcSimulationResults, emcBasicParticleHandler).
+Everything is compared bit for bit, step by step."""
+import numpy as np
+import pytest
+
+from helpers import load_golden
+from oracle import pyoracle as po
+from scenarios import DEVICE_CASES, build_device
+
+CASES = list(DEVICE_CASES)
+
+
+def ens_from(g, p):
+    pos = np.concatenate([g[p + "pos"], np.zeros((len(g[p + "energy"]), 1))], axis=1)
+    return po.Ensemble.from_arrays(g[p + "k"], pos, g[p + "energy"], g[p + "tau"], g[p + "label"], g[p + "idx"])
+
+
+def assert_same_ensemble(a, b, what):
+    assert a.n == b.n, what
+    for f in ("kx", "ky", "kz", "energy", "tau", "x", "y", "valley", "sub", "region"):
+        assert np.array_equal(getattr(a, f)[: a.n], getattr(b, f)[: b.n]), f"{what}: {f}"
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_flattened_device_description_equals_the_reference(case):
+    g = load_golden(case)
+    m, dev = build_device(case)
+    ny, nx = g["region"].shape
+    assert dev.extent == [nx, ny]
+    assert np.array_equal(dev.region, g["region"].ravel())
+    assert np.array_equal(dev.doping / dev.ni, g["doping_norm"].ravel())
+    assert np.array_equal(dev.face_contact, g["face_contact"].reshape(-1, 4))
+    vt, debye, vol, ni = g["device_consts"][:4]
+    assert (dev.vt, dev.debye, dev.cell_volume, dev.ni) == (vt, debye, vol, ni)
+    d = dev.c()
+    is_ohmic = np.array([dev.L.orc_dev_is_ohmic(po.C.byref(d), i) for i in range(dev.cells)])
+    is_res = np.array([dev.L.orc_dev_is_reservoir(po.C.byref(d), i) for i in range(dev.cells)])
+    cidx = np.array([dev.L.orc_dev_contact_idx(po.C.byref(d), i) for i in range(dev.cells)])
+    assert np.array_equal(is_ohmic, g["is_ohmic"].ravel())
+    assert np.array_equal(is_res, g["is_reservoir"].ravel())
+    assert np.array_equal(cidx, g["contact_idx"].ravel())
+    assert np.array_equal(dev.expected_at_contact(), g["expected_at_contact"].ravel())
+    for ts in m.tablesets():
+        key = f"_v{ts['valley']}_r{ts['region']}"
+        assert np.array_equal(ts["cum"], g["cum" + key]) and ts["tau"] == g["tau" + key][0]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_equilibrium_chain_bit_for_bit(case):
+    """calcEquilibriumCharacteristics (emcSimulation.hpp:139-146): potential guess, SOR, E field, initial
+    particles, NGP assignment, concentration."""
+    g = load_golden(case)
+    a = DEVICE_CASES[case]
+    m, dev = build_device(case)
+    pot = dev.initial_potential()
+    assert np.array_equal(pot, g["pot_guess"].ravel())
+    dev.sor(pot, None, 1e-4, 1.8, True)
+    assert np.array_equal(pot, g["pot_eq"].ravel())
+    e = dev.efield(pot)
+    assert np.array_equal(e[0], g["ex_eq"].ravel()) and np.array_equal(e[1], g["ey_eq"].ravel())
+    mt = po.mt_state(a["seed"])
+    ens = dev.generate_initial(m, mt)
+    ref = ens_from(g, "init_")
+    assert_same_ensemble(ens, ref, "initial ensemble")
+    count = dev.ngp_assign(ens)
+    assert np.array_equal(count, g["count_eq"].ravel()) and count.sum() == ens.n
+    assert np.array_equal(dev.concentration(count), g["conc_eq"].ravel())
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_emc_steps_bit_for_bit(case):
+    """performEMCStep (emcSimulation.hpp:177-192) step by step, consuming the reference's own draw sequence."""
+    g = load_golden(case)
+    a = DEVICE_CASES[case]
+    m, dev = build_device(case)
+    draws = g["draws"]
+    marks = g["draw_marks"].reshape(-1, 3)
+    expected = dev.expected_at_contact()
+    pot = g["pot_eq"].ravel().copy()
+    conc = g["conc_eq"].ravel().copy()
+    # one global mt19937_64 stream like the reference's single-thread rngs[0]: fast-forward past the creation draws
+    mt = po.mt_state(a["seed"])
+    for _ in range(int(g["draws_init_count"][0])):
+        po.lib().orc_mt_next(mt)
+    ens = ens_from(g, "init_")
+    cap = ens.n + 200
+    big = po.Ensemble(cap)
+    for f in po.Ensemble.F64 + po.Ensemble.I32:
+        getattr(big, f)[: ens.n] = getattr(ens, f)
+    big.n = ens.n
+    ens = big
+    for s in range(a["steps"]):
+        p = f"s{s}_"
+        dev.sor(pot, conc, 1e-4, 1.8, s == 0)
+        assert np.array_equal(pot, g[p + "pot"].ravel()), f"step {s}: potential"
+        e = dev.efield(pot)
+        assert np.array_equal(e[0], g[p + "ex"].ravel()) and np.array_equal(e[1], g[p + "ey"].ravel())
+        assert_same_ensemble(ens, ens_from(g, p + "pre_"), f"step {s}: pre")
+        assert int(marks[s, 0]) == int(g["draws_init_count"][0]) + sum(
+            int(marks[j, 2] - marks[j, 0]) for j in range(s))
+        res = dev.step(m, ens, e, a["dt"], po.rng_mt(mt), step_index=s + 1)
+        assert np.array_equal(res["removed_per_contact"], g[p + "removed_per_contact"]), f"step {s}: removed"
+        dev.compact(ens, res["removed"])
+        assert_same_ensemble(ens, ens_from(g, p + "drift_"), f"step {s}: after drift")
+        net = dev.contacts(m, ens, expected, mt)
+        assert np.array_equal(net, g[p + "net_injected_per_contact"]), f"step {s}: contacts"
+        assert_same_ensemble(ens, ens_from(g, p + "post_"), f"step {s}: after contacts")
+        count = dev.ngp_assign(ens)
+        assert np.array_equal(count, g[p + "count"].ravel())
+        conc = dev.concentration(count)
+        assert np.array_equal(conc, g[p + "conc"].ravel())
+    # the oracle consumed exactly as many draws as the reference
+    nxt = po.lib().orc_mt_next(mt)
+    ref_mt = po.mt_state(a["seed"])
+    for _ in range(len(draws)):
+        po.lib().orc_mt_next(ref_mt)
+    assert nxt == po.lib().orc_mt_next(ref_mt)
