@@ -217,6 +217,79 @@ int emcgpu_bulk_observables(emcgpu_ctx *ctx, double *obs);
 int emcgpu_set_step_index(emcgpu_ctx *ctx, int64_t nextStep);
 int64_t emcgpu_get_step_index(const emcgpu_ctx *ctx);
 
+/* ---- device run: emcSimulation + emcBasicParticleHandler + emcNGPScheme + emcSORSolver --------------
+ * (include/emcSimulation.hpp:139-193, include/ParticleHandler/emcBasicParticleHandler.hpp,
+ *  include/PMSchemes/emcNGPScheme.hpp, include/PMSchemes/emcEFieldCalculation.hpp,
+ *  include/PoissonSolver/emcSORSolver.hpp, include/emcSimulationResults.hpp:98-116)
+ * The box device with its doping regions and contacts crosses the boundary as flat arrays: */
+#define EMCGPU_MAX_CONTACTS 16
+typedef enum { EMCGPU_CONTACT_OHMIC = 0, EMCGPU_CONTACT_SCHOTTKY = 1, EMCGPU_CONTACT_GATE = 2 } emcgpu_contact_type;
+typedef struct {
+  int32_t dim; /* 2 or 3 */
+  int32_t nContacts;
+  int32_t extent[3];   /* grid points per dimension (emcDevice::getGridExtent) */
+  int32_t reserved;
+  double spacing[3];   /* [m] */
+  double maxPos[3];    /* [m] */
+  double thermalVoltage, debyeLength, ni, cellVolume, epsR; /* emcDevice.hpp:87-90, :333-343 */
+  const int32_t *contactType;                               /* HOST [nContacts], emcgpu_contact_type */
+  const double *contactVoltage;                             /* HOST [nContacts], volts */
+  const double *gateEpsOx, *gateThickness, *gateBarrier;    /* HOST [nContacts] (gate contacts) */
+  const int32_t *region;     /* HOST [cells], x fastest: emcDopingProfile::getDopingRegionIdx */
+  const int8_t *faceContact; /* HOST [cells][2*dim] in face order XMIN XMAX YMIN YMAX ZMIN ZMAX:
+                                -2 cell not on that face, -1 artificial boundary, >= 0 contact index
+                                (emcSurface::idxContactGrid incl. the corner sharing of updateAllOccurences) */
+  const double *doping;      /* HOST [cells], 1/m^3 */
+} emcgpu_device_t;
+
+typedef enum {
+  EMCGPU_GRID_POTENTIAL = 0, /* normalised by Vt */
+  EMCGPU_GRID_CONCENTRATION, /* normalised by Ni (particle type of this context) */
+  EMCGPU_GRID_COUNT,         /* carriers per grid point (emcSimulationResults::nrPart) */
+  EMCGPU_GRID_EFIELD_X,
+  EMCGPU_GRID_EFIELD_Y,
+  EMCGPU_GRID_EFIELD_Z,
+  EMCGPU_GRID_EXPECTED,      /* expected reservoir population per contact cell (expNrPart) */
+  EMCGPU_N_GRIDS
+} emcgpu_grid_id;
+
+/* Device + particle charge + carriers per simulated particle.  Allocates the device-resident grids;
+ * the potential starts as asinh(doping / 2 Ni) (emcSimulationResults.hpp:208-213).  `expected` (HOST,
+ * [cells], may be NULL = cellVolume * doping * 1/2 per boundary dimension at reservoir cells,
+ * emcElectron.hpp:63-73) is the population the contact cells are kept at. */
+int emcgpu_device_configure(emcgpu_ctx *ctx, const emcgpu_device_t *device, double charge, double nrCarriersPerParticle,
+                            const double *expected, int mathMode);
+int emcgpu_device_set_grid(emcgpu_ctx *ctx, int grid, const double *host);
+int emcgpu_device_get_grid(emcgpu_ctx *ctx, int grid, double *host);
+/* room for particles injected at contacts: the ensemble is re-allocated for at least this many */
+int emcgpu_device_reserve(emcgpu_ctx *ctx, int64_t capacity);
+/* emcSORSolver::calcEquilibriumPotential (:49-128, equilibrium != 0) / calcNonEquilibriumPotential (:131-197)
+ * on the POTENTIAL grid, with the CONCENTRATION grid as electron density; accuracy in volts.  Same update
+ * order as the reference (hyperplane sweep).  sweeps (HOST, may be NULL) receives the sweep count. */
+int emcgpu_device_poisson(emcgpu_ctx *ctx, int equilibrium, double accuracyVolt, double omega, int resetBC,
+                          int32_t *sweeps);
+/* pmScheme.calcEField (emcNGPScheme.hpp:69-73): POTENTIAL -> EFIELD_* */
+int emcgpu_device_efield(emcgpu_ctx *ctx);
+/* handler.assignParticlesToMesh (emcNGPScheme.hpp:36-47): ensemble -> COUNT (zeroed first) */
+int emcgpu_device_assign(emcgpu_ctx *ctx);
+/* results.updateCurrentParticleConcentrations (:98-116): COUNT -> CONCENTRATION */
+int emcgpu_device_concentration(emcgpu_ctx *ctx);
+/* handler.driftScatterParticles(dt, eField) (:76-145): one time step of every particle in EFIELD_*, particles
+ * that leave through an ohmic contact are removed (order of the others kept).  removedPerContact: HOST
+ * [nContacts] out.  Uses the context's rng (Philox: step index advances by one per call). */
+int emcgpu_device_step(emcgpu_ctx *ctx, double dt, int32_t *removedPerContact);
+/* handler.handleOhmicContacts() (:158-192): delete the excess particles of every reservoir cell (first come,
+ * first kept, in index order), inject the missing ones (appended, cells in storage order).
+ * netPerContact: HOST [nContacts] out = injected - deleted.  replayDraws (HOST, may be NULL): the raw draws the
+ * reference consumed in this call, (dim + 7) per injected particle. */
+int emcgpu_device_contacts(emcgpu_ctx *ctx, int32_t *netPerContact, const uint64_t *replayDraws, int64_t nReplayDraws);
+/* nSteps x performEMCStep (emcSimulation.hpp:177-192): poisson(resetBC only in the first step when asked) ->
+ * efield -> step -> contacts -> assign -> concentration, everything device resident.  counters (HOST, may be
+ * NULL): [nSteps][2][nContacts] = {left through contact, injected - deleted} per step; sweeps (HOST, may be
+ * NULL): [nSteps] SOR sweeps per step. */
+int emcgpu_device_run(emcgpu_ctx *ctx, double dt, int nSteps, double accuracyVolt, double omega, int resetBCFirst,
+                      int32_t *counters, int32_t *sweeps);
+
 /* ---- diagnostics used by the parity tests ------------------------------ */
 /* log up to capacity scatter selections as (step, particleId, tableIndex or -1
  * for self-scattering, mechId or -1); 0 disables. */

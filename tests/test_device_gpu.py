@@ -1,0 +1,209 @@
+"""GPU parity tests of the device-run path through the C ABI (emcgpu_device_*),
+against the golden fixtures recorded from the UNMODIFIED reference (tests/golden/device_*.npz) and against the
+oracle on seeded inputs.
+
+Bars (BASELINE.json north_star): integer / index results bit-exact (NGP counts, contact bookkeeping, removed and
+injected particles, scatter events, valley / region indices); fp64 within 1e-12 relative (particle state,
+potential, field, concentration) -- the device libm (exp, log, sincos, asinh) differs from glibc in the last bit.
+"""
+import numpy as np
+import pytest
+
+from helpers import STATE_RTOL, download_ensemble, load_golden, rel_err, upload_ensemble, upload_model
+from oracle import pyoracle as po
+from scenarios import DEVICE_CASES, build_device
+from test_oracle_device import ens_from
+from viennaemc_b200 import capi
+
+pytestmark = pytest.mark.gpu
+CASES = list(DEVICE_CASES)
+
+
+def configure(ctx, dev: po.Device, expected=None, math_mode=capi.MATH_EXACT):
+    ctx.device_configure(dev.dim, dev.extent, dev.spacing, dev.max_pos, dev.vt, dev.debye, dev.ni, dev.cell_volume,
+                         dev.eps_r, dev.contact_type, dev.contact_voltage, dev.gate_eps, dev.gate_thick,
+                         dev.gate_barrier, dev.region, dev.face_contact, dev.doping, expected=expected,
+                         math_mode=math_mode)
+
+
+def assert_grid_close(got, want, what, rtol=STATE_RTOL):
+    want = np.asarray(want).ravel()
+    scale = float(np.abs(want).max()) or 1.0
+    err = float(np.max(np.abs(got - want))) / scale
+    assert err <= rtol, f"{what}: {err:.3e}"
+
+
+def assert_ensemble_close(got: po.Ensemble, want: po.Ensemble, dev, what):
+    assert got.n == want.n, what
+    n = want.n
+    for f in ("valley", "sub", "region"):
+        assert np.array_equal(getattr(got, f)[:n], getattr(want, f)[:n]), f"{what}: {f}"
+    kmag = float(np.sqrt(np.mean(want.kx[:n] ** 2 + want.ky[:n] ** 2 + want.kz[:n] ** 2)))
+    errs = {f: rel_err(getattr(got, f)[:n], getattr(want, f)[:n], kmag) for f in ("kx", "ky", "kz")}
+    errs["energy"] = rel_err(got.energy[:n], want.energy[:n])
+    errs["tau"] = rel_err(got.tau[:n], want.tau[:n])
+    errs["x"] = rel_err(got.x[:n], want.x[:n], dev.max_pos[0])
+    errs["y"] = rel_err(got.y[:n], want.y[:n], dev.max_pos[1])
+    bad = {k: v for k, v in errs.items() if not v <= STATE_RTOL}
+    assert not bad, f"{what}: {bad}"
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_grid_chain_against_the_reference(gpu_ctx_factory, case):
+    """initial guess -> equilibrium SOR -> E field; NGP assignment -> concentration; non-equilibrium SOR of step 0."""
+    g = load_golden(case)
+    m, dev = build_device(case)
+    ctx = gpu_ctx_factory()
+    upload_model(ctx, m)
+    configure(ctx, dev)
+    assert np.array_equal(ctx.device_get_grid(capi.GRID_EXPECTED), g["expected_at_contact"].ravel())
+    assert_grid_close(ctx.device_get_grid(capi.GRID_POTENTIAL), g["pot_guess"], "initial guess")
+    # the oracle's sweep count is the reference's (bit-identical iterates, tests/test_oracle_device.py)
+    pot = dev.initial_potential()
+    ref_sweeps = dev.sor(pot, None, 1e-4, 1.8, True)
+    sweeps = ctx.device_poisson(True, 1e-4, 1.8, True)
+    assert sweeps == ref_sweeps
+    assert_grid_close(ctx.device_get_grid(capi.GRID_POTENTIAL), g["pot_eq"], "equilibrium potential")
+    ctx.device_efield()
+    assert_grid_close(ctx.device_get_grid(capi.GRID_EFIELD_X), g["ex_eq"], "Ex")
+    assert_grid_close(ctx.device_get_grid(capi.GRID_EFIELD_Y), g["ey_eq"], "Ey")
+    # particles of the reference -> counts (exact) -> concentration
+    upload_ensemble(ctx, ens_from(g, "init_"))
+    ctx.device_assign()
+    assert np.array_equal(ctx.device_get_grid(capi.GRID_COUNT), g["count_eq"].ravel())
+    ctx.device_concentration()
+    assert_grid_close(ctx.device_get_grid(capi.GRID_CONCENTRATION), g["conc_eq"], "concentration", 1e-15)
+    # non-equilibrium solve of step 0 (Dirichlet values reset), from the reference's own inputs
+    ctx.device_set_grid(capi.GRID_POTENTIAL, g["pot_eq"])
+    ctx.device_set_grid(capi.GRID_CONCENTRATION, g["conc_eq"])
+    pot = g["pot_eq"].ravel().copy()
+    ref_sweeps = dev.sor(pot, g["conc_eq"].ravel().copy(), 1e-4, 1.8, True)
+    assert ctx.device_poisson(False, 1e-4, 1.8, True) == ref_sweeps
+    assert_grid_close(ctx.device_get_grid(capi.GRID_POTENTIAL), g["s0_pot"], "non-equilibrium potential")
+
+
+def _step_streams(g, a, m, dev, s):
+    """Per-particle replay streams of the reference's drift/scatter phase of step s.  The attribution of each raw draw
+    comes from the oracle run that reproduces the reference bit for bit (tests/test_oracle_device.py)."""
+    p = f"s{s}_"
+    marks = g["draw_marks"].reshape(-1, 3)
+    ens = ens_from(g, p + "pre_")
+    e = np.stack([g[p + "ex"].ravel(), g[p + "ey"].ravel()])
+    draws = g["draws"][int(marks[s, 0]):int(marks[s, 1])]
+    mt = np.zeros(0)
+    # replay through the oracle with a flat stream to learn who consumed what
+    flat = po.rng_streams(np.ascontiguousarray(draws), np.zeros(ens.n + 1, dtype=np.int64), np.zeros(ens.n, dtype=np.int64))
+    # (a flat stream shared by all particles = offsets all zero is not what STREAMS means; use the recorder instead)
+    st = po.mt_state(a["seed"])
+    for _ in range(int(marks[s, 0])):
+        po.lib().orc_mt_next(st)
+    work = ens.copy()
+    res = dev.step(m, work, e, a["dt"], po.rng_mt(st), step_index=s + 1, record=True, log_events=True)
+    assert len(res["rec_pid"]) == len(draws)
+    sd, offsets = po.streams_from_record(draws, res["rec_pid"], ens.n)
+    return ens, e, sd, offsets, work, res
+
+
+@pytest.mark.parametrize("math_mode", [capi.MATH_EXACT, capi.MATH_FAST], ids=["exact", "fast"])
+@pytest.mark.parametrize("case", CASES)
+def test_particle_step_replays_the_reference(gpu_ctx_factory, case, math_mode):
+    """driftScatterParticles of every recorded step, fed the reference's own draws: removed particles, per-contact
+    counts, scatter events and indices exact; state within 1e-12 of the REFERENCE's ensemble."""
+    g = load_golden(case)
+    a = DEVICE_CASES[case]
+    m, dev = build_device(case)
+    ctx = gpu_ctx_factory()
+    upload_model(ctx, m)
+    configure(ctx, dev, math_mode=math_mode)
+    n_events = 0
+    for s in range(a["steps"]):
+        p = f"s{s}_"
+        ens, e, sd, offsets, oracle_after, res = _step_streams(g, a, m, dev, s)
+        upload_ensemble(ctx, ens)
+        ctx.rng_replay(sd, offsets)
+        ctx.device_set_grid(capi.GRID_EFIELD_X, e[0])
+        ctx.device_set_grid(capi.GRID_EFIELD_Y, e[1])
+        ctx.set_step_index(s + 1)
+        ctx.event_log_enable(1 << 16)
+        removed = ctx.device_step(a["dt"])
+        assert np.array_equal(removed, g[p + "removed_per_contact"]), f"step {s}"
+        got = download_ensemble(ctx)
+        assert_ensemble_close(got, ens_from(g, p + "drift_"), dev, f"{case} step {s}")
+        ev, n_ev = ctx.event_log_read(1 << 16)
+        dev_ev = ev[np.lexsort((ev[:, 3], ev[:, 2], ev[:, 1], ev[:, 0]))]
+        cpu_ev = res["events"][np.lexsort((res["events"][:, 3], res["events"][:, 2], res["events"][:, 1], res["events"][:, 0]))]
+        assert np.array_equal(dev_ev, cpu_ev), f"step {s}: scatter events"
+        n_events += n_ev
+    assert n_events > 100
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_contacts_replay_the_reference(gpu_ctx_factory, case):
+    """handleOhmicContacts of every recorded step: which particles are deleted, how many are injected per contact
+    (exact), and the injected particles themselves from the reference's draws."""
+    g = load_golden(case)
+    a = DEVICE_CASES[case]
+    m, dev = build_device(case)
+    marks = g["draw_marks"].reshape(-1, 3)
+    ctx = gpu_ctx_factory()
+    upload_model(ctx, m)
+    configure(ctx, dev, expected=g["expected_at_contact"].ravel())
+    ctx.rng_philox(1)
+    injected_total = 0
+    for s in range(a["steps"]):
+        p = f"s{s}_"
+        before = ens_from(g, p + "drift_")
+        upload_ensemble(ctx, before)
+        ctx.set_step_index(s + 2)
+        draws = g["draws"][int(marks[s, 1]):int(marks[s, 2])]
+        net = ctx.device_contacts(replay_draws=draws)
+        assert np.array_equal(net, g[p + "net_injected_per_contact"]), f"step {s}"
+        assert_ensemble_close(download_ensemble(ctx), ens_from(g, p + "post_"), dev, f"{case} contacts {s}")
+        injected_total += len(draws) // 9
+        ctx.device_assign()
+        assert np.array_equal(ctx.device_get_grid(capi.GRID_COUNT), g[p + "count"].ravel())
+        ctx.device_concentration()
+        assert_grid_close(ctx.device_get_grid(capi.GRID_CONCENTRATION), g[p + "conc"], "concentration", 1e-15)
+    assert injected_total > 0
+
+
+def test_self_consistent_run_conserves_bookkeeping_and_stays_physical(gpu_ctx_factory):
+    """emcgpu_device_run (Philox): particle count changes exactly by the per-contact counters, counts grid sums to
+    the ensemble size, the potential keeps its Dirichlet values, reservoir cells stay at their expected population,
+    and the run is deterministic."""
+    case = "device_bar"
+    g = load_golden(case)
+    a = DEVICE_CASES[case]
+    m, dev = build_device(case)
+    finals = []
+    for _ in range(2):
+        ctx = gpu_ctx_factory()
+        upload_model(ctx, m)
+        configure(ctx, dev, math_mode=capi.MATH_FAST)
+        ctx.device_set_grid(capi.GRID_POTENTIAL, g["pot_eq"])
+        ctx.device_set_grid(capi.GRID_CONCENTRATION, g["conc_eq"])
+        upload_ensemble(ctx, ens_from(g, "init_"))
+        ctx.device_reserve(4096)
+        ctx.rng_philox(2026)
+        ctx.set_step_index(1)
+        n0 = ctx.size
+        counters, sweeps = ctx.device_run(a["dt"], 200, 1e-4, 1.8, True)
+        assert np.all(sweeps >= 1)
+        left, net = counters[:, 0, :].sum(), counters[:, 1, :].sum()
+        assert ctx.size == n0 - left + net
+        count = ctx.device_get_grid(capi.GRID_COUNT)
+        assert count.sum() == ctx.size
+        pot = ctx.device_get_grid(capi.GRID_POTENTIAL)
+        ohmic = g["is_ohmic"].ravel().astype(bool)
+        assert np.allclose(pot[ohmic], g["s0_pot"].ravel()[ohmic], rtol=1e-13)
+        expected = g["expected_at_contact"].ravel()
+        res_cells = g["is_reservoir"].ravel().astype(bool)
+        assert np.all(count[res_cells] >= np.floor(expected[res_cells])) and np.all(count[res_cells] <= np.ceil(expected[res_cells]))
+        e = download_ensemble(ctx)
+        assert e.x.min() >= 0 and e.x.max() <= dev.max_pos[0] and e.y.min() >= 0 and e.y.max() <= dev.max_pos[1]
+        assert np.isfinite(e.energy).all() and e.energy.min() > 0
+        # electrons flow from the grounded XMAX contact (index 0) towards the positive XMIN contact (index 1)
+        assert counters[:, 0, 1].sum() > counters[:, 0, 0].sum()
+        finals.append(e)
+    for f in ("kx", "energy", "x", "y", "tau"):
+        assert np.array_equal(getattr(finals[0], f), getattr(finals[1], f)), f

@@ -37,10 +37,10 @@ def build_emcgpu(force: bool = False, verbose: bool = False) -> str:
     """libemcgpu.so: the CUDA kernels + the C ABI of include/emcgpu.h."""
     os.makedirs(LIBDIR, exist_ok=True)
     target = os.path.join(LIBDIR, "libemcgpu.so")
-    src = os.path.join(PKG, "csrc", "emcgpu.cu")
+    src = [os.path.join(PKG, "csrc", "emcgpu.cu"), os.path.join(PKG, "csrc", "emcgpu_device.cu")]
     deps = _sources(os.path.join(PKG, "csrc"), os.path.join(ROOT, "include"))
     if force or _newer(target, deps):
-        cmd = ["nvcc", *NVCC_FLAGS, "-o", target, src]
+        cmd = ["nvcc", *NVCC_FLAGS, "-o", target, *src]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.check_call(cmd)

@@ -94,9 +94,34 @@ def load():
     L.emcgpu_event_log_enable.argtypes = [vp, C.c_int64]
     L.emcgpu_event_log_read.argtypes = [vp, C.POINTER(C.c_int64), C.c_int64]
     L.emcgpu_event_log_read.restype = C.c_int64
+    IP32 = C.POINTER(C.c_int32)
+    L.emcgpu_device_configure.argtypes = [vp, C.POINTER(DeviceC), C.c_double, C.c_double, _DP, C.c_int]
+    L.emcgpu_device_set_grid.argtypes = [vp, C.c_int, _DP]
+    L.emcgpu_device_get_grid.argtypes = [vp, C.c_int, _DP]
+    L.emcgpu_device_reserve.argtypes = [vp, C.c_int64]
+    L.emcgpu_device_poisson.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_int, IP32]
+    L.emcgpu_device_efield.argtypes = [vp]
+    L.emcgpu_device_assign.argtypes = [vp]
+    L.emcgpu_device_concentration.argtypes = [vp]
+    L.emcgpu_device_step.argtypes = [vp, C.c_double, IP32]
+    L.emcgpu_device_contacts.argtypes = [vp, IP32, C.POINTER(C.c_uint64), C.c_int64]
+    L.emcgpu_device_run.argtypes = [vp, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, IP32, IP32]
     _lib = L
     return L
 
+
+class DeviceC(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("nContacts", C.c_int32), ("extent", C.c_int32 * 3), ("reserved", C.c_int32),
+                ("spacing", C.c_double * 3), ("maxPos", C.c_double * 3), ("thermalVoltage", C.c_double),
+                ("debyeLength", C.c_double), ("ni", C.c_double), ("cellVolume", C.c_double), ("epsR", C.c_double),
+                ("contactType", C.POINTER(C.c_int32)), ("contactVoltage", _DP), ("gateEpsOx", _DP),
+                ("gateThickness", _DP), ("gateBarrier", _DP), ("region", C.POINTER(C.c_int32)),
+                ("faceContact", C.POINTER(C.c_int8)), ("doping", _DP)]
+
+
+(GRID_POTENTIAL, GRID_CONCENTRATION, GRID_COUNT, GRID_EFIELD_X, GRID_EFIELD_Y, GRID_EFIELD_Z,
+ GRID_EXPECTED) = range(7)
+CONTACT_OHMIC, CONTACT_SCHOTTKY, CONTACT_GATE = range(3)
 
 EXPORTED_SYMBOLS = [
     "emcgpu_abi_version", "emcgpu_create", "emcgpu_destroy", "emcgpu_last_error", "emcgpu_launch_count",
@@ -105,6 +130,9 @@ EXPORTED_SYMBOLS = [
     "emcgpu_ensemble_device_ptrs", "emcgpu_rng_philox", "emcgpu_rng_replay", "emcgpu_bulk_configure",
     "emcgpu_bulk_step", "emcgpu_bulk_step_device", "emcgpu_bulk_observables", "emcgpu_set_step_index",
     "emcgpu_get_step_index", "emcgpu_event_log_enable", "emcgpu_event_log_read",
+    "emcgpu_device_configure", "emcgpu_device_set_grid", "emcgpu_device_get_grid", "emcgpu_device_reserve",
+    "emcgpu_device_poisson", "emcgpu_device_efield", "emcgpu_device_assign", "emcgpu_device_concentration",
+    "emcgpu_device_step", "emcgpu_device_contacts", "emcgpu_device_run",
 ]
 
 
@@ -260,6 +288,82 @@ class Context:
         obs = np.zeros((self.n_valleys, 3))
         self._chk(self.L.emcgpu_bulk_observables(self.h, obs.ctypes.data_as(_DP)))
         return obs
+
+    # -- device run
+    def device_configure(self, dim, extent, spacing, max_pos, thermal_voltage, debye_length, ni, cell_volume, eps_r,
+                         contact_type, contact_voltage, gate_eps, gate_thickness, gate_barrier, region, face_contact,
+                         doping, charge=-1.60219e-19, nr_carriers=1.0, expected=None, math_mode=MATH_EXACT):
+        d = DeviceC()
+        d.dim, d.nContacts = dim, len(contact_type)
+        for i in range(3):
+            d.extent[i] = extent[i] if i < dim else 1
+            d.spacing[i] = spacing[i] if i < dim else 1.0
+            d.maxPos[i] = max_pos[i] if i < dim else 0.0
+        d.thermalVoltage, d.debyeLength, d.ni, d.cellVolume, d.epsR = thermal_voltage, debye_length, ni, cell_volume, eps_r
+        keep = [np.ascontiguousarray(contact_type, dtype=np.int32), np.ascontiguousarray(contact_voltage, dtype=np.float64),
+                np.ascontiguousarray(gate_eps, dtype=np.float64), np.ascontiguousarray(gate_thickness, dtype=np.float64),
+                np.ascontiguousarray(gate_barrier, dtype=np.float64), np.ascontiguousarray(region, dtype=np.int32),
+                np.ascontiguousarray(face_contact, dtype=np.int8), np.ascontiguousarray(doping, dtype=np.float64)]
+        d.contactType = keep[0].ctypes.data_as(C.POINTER(C.c_int32))
+        d.contactVoltage, d.gateEpsOx, d.gateThickness, d.gateBarrier = [k.ctypes.data_as(_DP) for k in keep[1:5]]
+        d.region = keep[5].ctypes.data_as(C.POINTER(C.c_int32))
+        d.faceContact = keep[6].ctypes.data_as(C.POINTER(C.c_int8))
+        d.doping = keep[7].ctypes.data_as(_DP)
+        exp = np.ascontiguousarray(expected, dtype=np.float64) if expected is not None else None
+        self._chk(self.L.emcgpu_device_configure(self.h, C.byref(d), charge, nr_carriers,
+                                                 exp.ctypes.data_as(_DP) if exp is not None else None, math_mode))
+        self.n_cells = int(np.prod(extent[:dim]))
+        self.n_contacts = len(contact_type)
+
+    def device_set_grid(self, grid, values):
+        v = np.ascontiguousarray(values, dtype=np.float64).ravel()
+        assert v.size == self.n_cells
+        self._chk(self.L.emcgpu_device_set_grid(self.h, grid, v.ctypes.data_as(_DP)))
+
+    def device_get_grid(self, grid):
+        v = np.zeros(self.n_cells)
+        self._chk(self.L.emcgpu_device_get_grid(self.h, grid, v.ctypes.data_as(_DP)))
+        return v
+
+    def device_reserve(self, capacity):
+        self._chk(self.L.emcgpu_device_reserve(self.h, capacity))
+
+    def device_poisson(self, equilibrium, accuracy=1e-4, omega=1.8, reset_bc=True):
+        sweeps = C.c_int32(0)
+        self._chk(self.L.emcgpu_device_poisson(self.h, int(equilibrium), accuracy, omega, int(reset_bc), C.byref(sweeps)))
+        return sweeps.value
+
+    def device_efield(self):
+        self._chk(self.L.emcgpu_device_efield(self.h))
+
+    def device_assign(self):
+        self._chk(self.L.emcgpu_device_assign(self.h))
+
+    def device_concentration(self):
+        self._chk(self.L.emcgpu_device_concentration(self.h))
+
+    def device_step(self, dt):
+        rem = np.zeros(max(1, self.n_contacts), dtype=np.int32)
+        self._chk(self.L.emcgpu_device_step(self.h, dt, rem.ctypes.data_as(C.POINTER(C.c_int32))))
+        return rem[: self.n_contacts]
+
+    def device_contacts(self, replay_draws=None):
+        net = np.zeros(max(1, self.n_contacts), dtype=np.int32)
+        if replay_draws is not None:
+            rd = np.ascontiguousarray(replay_draws, dtype=np.uint64)
+            self._chk(self.L.emcgpu_device_contacts(self.h, net.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                    rd.ctypes.data_as(C.POINTER(C.c_uint64)), len(rd)))
+        else:
+            self._chk(self.L.emcgpu_device_contacts(self.h, net.ctypes.data_as(C.POINTER(C.c_int32)), None, 0))
+        return net[: self.n_contacts]
+
+    def device_run(self, dt, n_steps, accuracy=1e-4, omega=1.8, reset_bc_first=True):
+        counters = np.zeros((n_steps, 2, max(1, self.n_contacts)), dtype=np.int32)
+        sweeps = np.zeros(n_steps, dtype=np.int32)
+        self._chk(self.L.emcgpu_device_run(self.h, dt, n_steps, accuracy, omega, int(reset_bc_first),
+                                           counters.ctypes.data_as(C.POINTER(C.c_int32)),
+                                           sweeps.ctypes.data_as(C.POINTER(C.c_int32))))
+        return counters[:, :, : self.n_contacts], sweeps
 
     def set_step_index(self, s):
         self._chk(self.L.emcgpu_set_step_index(self.h, s))

@@ -1130,7 +1130,7 @@ struct GenParams {
   uint64_t seed;
 };
 
-__global__ void __launch_bounds__(256) bulkGenerateKernel(const GenParams G) {
+static __global__ void __launch_bounds__(256) bulkGenerateKernel(const GenParams G) {
   const DevModel &model = *G.model;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < G.n; i += stride) {

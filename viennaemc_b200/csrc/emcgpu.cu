@@ -10,7 +10,7 @@
 #include <string>
 #include <vector>
 
-#include "emc_bulk_kernel.cuh"
+#include "emcgpu_internal.cuh"
 
 using namespace emc;
 
@@ -18,71 +18,10 @@ namespace {
 
 thread_local std::string g_createError;
 
-struct DeviceBuffer {
-  void *ptr = nullptr;
-  size_t bytes = 0;
-  cudaError_t ensure(size_t need) {
-    if (need <= bytes) return cudaSuccess;
-    if (ptr) cudaFree(ptr);
-    ptr = nullptr;
-    bytes = 0;
-    cudaError_t e = cudaMalloc(&ptr, need);
-    if (e == cudaSuccess) bytes = need;
-    return e;
-  }
-  void release() {
-    if (ptr) cudaFree(ptr);
-    ptr = nullptr;
-    bytes = 0;
-  }
-};
-
 } // namespace
 
-struct emcgpu_ctx {
-  int device = 0;
-  int smCount = 0;
-  int maxSmemOptin = 0;
-  int maxSmemPerSm = 0;
-  int optVec = 2; // particles per lane and iteration of the streaming step kernel (1, 2, 4)
-  int optKernel = 0; // one-step kernel: 0 = TMA pipeline when it fits, 1 = plain streaming kernel
-  int optStages = 0; // cap on the TMA ring depth (0 = as many as fit)
-  int optTablesGlobal = 0; // 1 = leave the rate tables in global memory / L2 (more ring stages)
-  cudaStream_t stream = nullptr;
-  std::string error;
-  int64_t launches = 0;
-
-  // model
-  bool haveValleys = false, haveTables = false;
-  DevModel hModel{};
-  std::vector<DevMech> hMechs;
-  DeviceBuffer dModel, dMechs, dTables;
-
-  // ensemble
-  int64_t n = 0, capacity = 0, idBase = 0;
-  DeviceBuffer dEnsemble;
-  double *dStream[EMCGPU_N_STREAMS] = {};
-  uint32_t *dPacked = nullptr;
-
-  // rng
-  int rngMode = RNG_PHILOX;
-  uint64_t seed = 0;
-  DeviceBuffer dDraws, dOffsets, dCursor;
-
-  // bulk configuration
-  bool bulkConfigured = false;
-  Vec3 box{}, force{}, dir{};
-  int mathMode = EMCGPU_MATH_EXACT;
-  int64_t nextStep = 1;
-
-  // outputs
-  DeviceBuffer dObs, dStatus, dEvents, dEvCount;
-  int64_t evCap = 0;
-};
-
-namespace {
-
-int fail(emcgpu_ctx *ctx, int code, const char *fmt, ...) {
+namespace emc {
+int failWith(emcgpu_ctx *ctx, int code, const char *fmt, ...) {
   char buf[512];
   va_list ap;
   va_start(ap, fmt);
@@ -91,18 +30,13 @@ int fail(emcgpu_ctx *ctx, int code, const char *fmt, ...) {
   if (ctx) ctx->error = buf; else g_createError = buf;
   return code;
 }
+} // namespace emc
 
-#define CUDA_TRY(ctx, expr)                                                                   \
-  do {                                                                                        \
-    cudaError_t _e = (expr);                                                                  \
-    if (_e != cudaSuccess)                                                                    \
-      return fail(ctx, EMCGPU_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));        \
-  } while (0)
+namespace {
 
-int bind(emcgpu_ctx *ctx) {
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  return EMCGPU_OK;
-}
+#define fail emc::failWith
+
+int bind(emcgpu_ctx *ctx) { return emc::bindDevice(ctx); }
 
 // classify R (row-major, rows = ellipse axes): identity, signed permutation, general
 int classifyRotation(const double *r, uint16_t *toE, uint16_t *toD) {
@@ -236,7 +170,9 @@ int checkReady(emcgpu_ctx *ctx, bool needEnsemble) {
   return EMCGPU_OK;
 }
 
-int allocEnsemble(emcgpu_ctx *ctx, int64_t n) {
+int allocEnsemble(emcgpu_ctx *ctx, int64_t n) { return emc::allocEnsembleStreams(ctx, n); }
+} // namespace
+int emc::allocEnsembleStreams(emcgpu_ctx *ctx, int64_t n) {
   // every stream starts on a 256-byte boundary
   const size_t strideD = ((size_t)n * sizeof(double) + 255) & ~size_t(255);
   const size_t strideP = ((size_t)n * sizeof(uint32_t) + 255) & ~size_t(255);
@@ -248,6 +184,7 @@ int allocEnsemble(emcgpu_ctx *ctx, int64_t n) {
   ctx->capacity = n;
   return EMCGPU_OK;
 }
+namespace {
 
 int checkStatusWord(emcgpu_ctx *ctx) {
   int status = 0;
@@ -313,6 +250,7 @@ void emcgpu_destroy(emcgpu_ctx *ctx) {
                           &ctx->dOffsets, &ctx->dCursor, &ctx->dObs, &ctx->dStatus, &ctx->dEvents,
                           &ctx->dEvCount})
     b->release();
+  emc::releaseDeviceRun(ctx);
   delete ctx;
 }
 

@@ -1,0 +1,103 @@
+// Internals shared by the translation units of libemcgpu.so: the context behind the
+// opaque emcgpu_ctx handle of include/emcgpu.h, device buffers and error helpers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "emc_bulk_kernel.cuh"
+
+namespace emc {
+
+struct DeviceBuffer {
+  void *ptr = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&ptr, need);
+    if (e == cudaSuccess) bytes = need;
+    return e;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+  }
+  template <class T> T *as() const { return static_cast<T *>(ptr); }
+};
+
+struct DeviceRunState; // emcgpu_device.cu
+
+} // namespace emc
+
+struct emcgpu_ctx {
+  int device = 0;
+  int smCount = 0;
+  int maxSmemOptin = 0;
+  int maxSmemPerSm = 0;
+  int optVec = 2;          // particles per lane and iteration of the streaming step kernel (1, 2, 4)
+  int optKernel = 0;       // one-step kernel: 0 = TMA pipeline when it fits, 1 = plain streaming kernel
+  int optStages = 0;       // cap on the TMA ring depth (0 = as many as fit)
+  int optTablesGlobal = 0; // 1 = leave the rate tables in global memory / L2 (more ring stages)
+  cudaStream_t stream = nullptr;
+  std::string error;
+  int64_t launches = 0;
+
+  // model
+  bool haveValleys = false, haveTables = false;
+  emc::DevModel hModel{};
+  std::vector<emc::DevMech> hMechs;
+  emc::DeviceBuffer dModel, dMechs, dTables;
+
+  // ensemble
+  int64_t n = 0, capacity = 0, idBase = 0;
+  emc::DeviceBuffer dEnsemble;
+  double *dStream[EMCGPU_N_STREAMS] = {};
+  uint32_t *dPacked = nullptr;
+
+  // rng
+  int rngMode = emc::RNG_PHILOX;
+  uint64_t seed = 0;
+  emc::DeviceBuffer dDraws, dOffsets, dCursor;
+
+  // bulk configuration
+  bool bulkConfigured = false;
+  emc::Vec3 box{}, force{}, dir{};
+  int mathMode = EMCGPU_MATH_EXACT;
+  int64_t nextStep = 1;
+
+  // outputs
+  emc::DeviceBuffer dObs, dStatus, dEvents, dEvCount;
+  int64_t evCap = 0;
+
+  // device-run path (emcgpu_device.cu), created by emcgpu_device_configure
+  emc::DeviceRunState *run = nullptr;
+};
+
+namespace emc {
+
+int failWith(emcgpu_ctx *ctx, int code, const char *fmt, ...);
+
+#define CUDA_TRY(ctx, expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      return emc::failWith(ctx, EMCGPU_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+inline int bindDevice(emcgpu_ctx *ctx) {
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  return EMCGPU_OK;
+}
+// compacted-ensemble bookkeeping shared with the device-run code
+int allocEnsembleStreams(emcgpu_ctx *ctx, int64_t n);
+void releaseDeviceRun(emcgpu_ctx *ctx);
+
+} // namespace emc
