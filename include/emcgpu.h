@@ -250,6 +250,8 @@ typedef enum {
   EMCGPU_GRID_EFIELD_Y,
   EMCGPU_GRID_EFIELD_Z,
   EMCGPU_GRID_EXPECTED,      /* expected reservoir population per contact cell (expNrPart) */
+  EMCGPU_GRID_SUM_POTENTIAL,     /* running sums of emcSimulationResults::updateAverageCharacteristics (:87-93) */
+  EMCGPU_GRID_SUM_CONCENTRATION,
   EMCGPU_N_GRIDS
 } emcgpu_grid_id;
 
@@ -289,6 +291,10 @@ int emcgpu_device_contacts(emcgpu_ctx *ctx, int32_t *netPerContact, const uint64
  * NULL): [nSteps] SOR sweeps per step. */
 int emcgpu_device_run(emcgpu_ctx *ctx, double dt, int nSteps, double accuracyVolt, double omega, int resetBCFirst,
                       int32_t *counters, int32_t *sweeps);
+/* the same; the last nAverage steps also add POTENTIAL / CONCENTRATION to the SUM_* grids
+ * (results.updateAverageCharacteristics, emcSimulation.hpp:122-123) */
+int emcgpu_device_run_averaging(emcgpu_ctx *ctx, double dt, int nSteps, int nAverage, double accuracyVolt, double omega,
+                                int resetBCFirst, int32_t *counters, int32_t *sweeps);
 
 /* ---- diagnostics used by the parity tests ------------------------------ */
 /* log up to capacity scatter selections as (step, particleId, tableIndex or -1

@@ -106,6 +106,8 @@ def load():
     L.emcgpu_device_step.argtypes = [vp, C.c_double, IP32]
     L.emcgpu_device_contacts.argtypes = [vp, IP32, C.POINTER(C.c_uint64), C.c_int64]
     L.emcgpu_device_run.argtypes = [vp, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, IP32, IP32]
+    L.emcgpu_device_run_averaging.argtypes = [vp, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, IP32,
+                                              IP32]
     _lib = L
     return L
 
@@ -120,7 +122,7 @@ class DeviceC(C.Structure):
 
 
 (GRID_POTENTIAL, GRID_CONCENTRATION, GRID_COUNT, GRID_EFIELD_X, GRID_EFIELD_Y, GRID_EFIELD_Z,
- GRID_EXPECTED) = range(7)
+ GRID_EXPECTED, GRID_SUM_POTENTIAL, GRID_SUM_CONCENTRATION) = range(9)
 CONTACT_OHMIC, CONTACT_SCHOTTKY, CONTACT_GATE = range(3)
 
 EXPORTED_SYMBOLS = [
@@ -132,7 +134,7 @@ EXPORTED_SYMBOLS = [
     "emcgpu_get_step_index", "emcgpu_event_log_enable", "emcgpu_event_log_read",
     "emcgpu_device_configure", "emcgpu_device_set_grid", "emcgpu_device_get_grid", "emcgpu_device_reserve",
     "emcgpu_device_poisson", "emcgpu_device_efield", "emcgpu_device_assign", "emcgpu_device_concentration",
-    "emcgpu_device_step", "emcgpu_device_contacts", "emcgpu_device_run",
+    "emcgpu_device_step", "emcgpu_device_contacts", "emcgpu_device_run", "emcgpu_device_run_averaging",
 ]
 
 
@@ -357,10 +359,10 @@ class Context:
             self._chk(self.L.emcgpu_device_contacts(self.h, net.ctypes.data_as(C.POINTER(C.c_int32)), None, 0))
         return net[: self.n_contacts]
 
-    def device_run(self, dt, n_steps, accuracy=1e-4, omega=1.8, reset_bc_first=True):
+    def device_run(self, dt, n_steps, accuracy=1e-4, omega=1.8, reset_bc_first=True, n_average=0):
         counters = np.zeros((n_steps, 2, max(1, self.n_contacts)), dtype=np.int32)
         sweeps = np.zeros(n_steps, dtype=np.int32)
-        self._chk(self.L.emcgpu_device_run(self.h, dt, n_steps, accuracy, omega, int(reset_bc_first),
+        self._chk(self.L.emcgpu_device_run_averaging(self.h, dt, n_steps, n_average, accuracy, omega, int(reset_bc_first),
                                            counters.ctypes.data_as(C.POINTER(C.c_int32)),
                                            sweeps.ctypes.data_as(C.POINTER(C.c_int32))))
         return counters[:, :, : self.n_contacts], sweeps

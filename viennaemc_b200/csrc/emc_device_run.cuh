@@ -119,6 +119,14 @@ __global__ void concentrationKernel(const __grid_constant__ DevGeometry G, const
   conc[cell] = v;
 }
 
+// emcSimulationResults::updateAverageCharacteristics (:87-93): running sums of potential and concentration
+__global__ void accumulateKernel(int cells, const double *pot, const double *conc, double *sumPot, double *sumConc) {
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= cells) return;
+  sumPot[cell] = __dadd_rn(sumPot[cell], pot[cell]);
+  sumConc[cell] = __dadd_rn(sumConc[cell], conc[cell]);
+}
+
 // interior: Vt (phi[prev] - phi[next]) / (2 h); on a face: 0 (artificial boundary) or the inner neighbour's value (contact)
 __global__ void efieldKernel(const __grid_constant__ DevGeometry G, const double *pot, double *e) {
   const int cell = blockIdx.x * blockDim.x + threadIdx.x;

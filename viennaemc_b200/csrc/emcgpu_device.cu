@@ -513,9 +513,15 @@ int emcgpu_device_contacts(emcgpu_ctx *ctx, int32_t *netPerContact, const uint64
 
 int emcgpu_device_run(emcgpu_ctx *ctx, double dt, int nSteps, double accuracyVolt, double omega, int resetBCFirst,
                       int32_t *counters, int32_t *sweeps) {
+  return emcgpu_device_run_averaging(ctx, dt, nSteps, 0, accuracyVolt, omega, resetBCFirst, counters, sweeps);
+}
+
+int emcgpu_device_run_averaging(emcgpu_ctx *ctx, double dt, int nSteps, int nAverage, double accuracyVolt, double omega,
+                                int resetBCFirst, int32_t *counters, int32_t *sweeps) {
   if (int r = needRun(ctx)) return r;
   if (int r = needModel(ctx)) return r;
-  if (!(dt > 0) || nSteps < 1 || !(accuracyVolt > 0)) return fail(ctx, EMCGPU_E_INVALID, "bad run arguments");
+  if (!(dt > 0) || nSteps < 1 || !(accuracyVolt > 0) || nAverage < 0 || nAverage > nSteps)
+    return fail(ctx, EMCGPU_E_INVALID, "bad run arguments");
   const int nC = ctx->run->geo.nContacts;
   for (int s = 0; s < nSteps; s++) {
     if (int r = doPoisson(ctx, false, accuracyVolt, omega, resetBCFirst && s == 0, sweeps ? sweeps + s : nullptr)) return r;
@@ -524,6 +530,14 @@ int emcgpu_device_run(emcgpu_ctx *ctx, double dt, int nSteps, double accuracyVol
     if (int r = doContacts(ctx, counters ? counters + (size_t)s * 2 * nC + nC : nullptr, nullptr, 0)) return r;
     if (int r = doAssign(ctx)) return r;
     if (int r = doConcentration(ctx)) return r;
+    if (s >= nSteps - nAverage) {
+      DeviceRunState *r = ctx->run;
+      accumulateKernel<<<gridBlocks(r->geo.cells), 256, 0, ctx->stream>>>(
+          r->geo.cells, r->grid[EMCGPU_GRID_POTENTIAL].as<const double>(), r->grid[EMCGPU_GRID_CONCENTRATION].as<const double>(),
+          r->grid[EMCGPU_GRID_SUM_POTENTIAL].as<double>(), r->grid[EMCGPU_GRID_SUM_CONCENTRATION].as<double>());
+      ctx->launches++;
+      CUDA_TRY(ctx, cudaGetLastError());
+    }
   }
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return EMCGPU_OK;

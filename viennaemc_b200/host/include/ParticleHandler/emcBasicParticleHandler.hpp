@@ -1,0 +1,226 @@
+// Particle handler of a device run -- GPU resident.
+// Interface mirrored: reference include/ParticleHandler/emcBasicParticleHandler.hpp (ctor :52-60,
+// getNrParticles, printNrParticles, driftScatterParticles :76-145, assignParticlesToMesh :148-153,
+// handleOhmicContacts :158-192, print :194-216, getChannelDriftCurrent :224-237) and the initial
+// ensemble of emcAbstractParticleHandler::generateInitialParticles (:133-148).
+//
+// The ensemble of the (one) moved particle type lives in GPU memory behind a C-ABI context; every
+// public member maps to one emcgpu_device_* call.  emcSimulation does not go through these per-call
+// members in its step loop: it drives the whole step (Poisson, field, particles, contacts, charge
+// assignment) device resident through gpuContext().  Initial particles are created on the host with
+// the reference's draw order (same seed -> same ensemble); contact injection and the step itself draw
+// from counter-based Philox streams.
+#ifndef EMC_BASIC_PARTICLE_HANDLER_HPP
+#define EMC_BASIC_PARTICLE_HANDLER_HPP
+
+#include <cstdlib>
+#include <fstream>
+
+#include <ParticleHandler/emcAbstractParticleHandler.hpp>
+#include <detail/emcBulkEnsembleBuilder.hpp>
+#include <detail/emcDeviceFlatten.hpp>
+#include <emcGpuBinding.hpp>
+
+template <class T, class DeviceType, class PMScheme, SizeType Dim = DeviceType::Dimension>
+class emcBasicParticleHandler : public emcAbstractParticleHandler<T, DeviceType, PMScheme, Dim> {
+  typedef emcAbstractParticleHandler<T, DeviceType, PMScheme, Dim> Base;
+
+public:
+  typedef typename Base::SizeVec SizeVec;
+  typedef typename Base::ValueVec ValueVec;
+  typedef typename Base::MapIdxToParticleTypes MapIdxToParticleTypes;
+  typedef typename Base::NettoParticleCounter NettoParticleCounter;
+
+private:
+  emcgpu_ctx *ctx = nullptr;
+  SizeType gpuType = 0; // index of the particle type that lives on the GPU
+  emcRNG hostRng;       // particle creation only (the reference's rngs[0])
+  SizeType seed;
+  emcdetail::HostEnsemble staging;
+  bool uploaded = false;
+
+  SizeType nrOnGpu() const { return uploaded ? static_cast<SizeType>(emcgpu_ensemble_size(ctx)) : staging.size(); }
+
+  void upload() {
+    if (uploaded)
+      return;
+    const double *ptrs[EMCGPU_N_STREAMS];
+    for (int s = 0; s < EMCGPU_N_STREAMS; s++)
+      ptrs[s] = staging.stream[s].data();
+    emcgpu::require(ctx, emcgpu_set_ensemble(ctx, static_cast<int64_t>(staging.size()), ptrs, staging.packed.data(), 0),
+                    "emcgpu_set_ensemble");
+    emcgpu::require(ctx, emcgpu_rng_philox(ctx, seed), "emcgpu_rng_philox");
+    emcgpu::require(ctx, emcgpu_set_step_index(ctx, 1), "emcgpu_set_step_index");
+    // head room for injected particles: avoids re-allocations during the run
+    emcgpu::require(ctx, emcgpu_device_reserve(ctx, static_cast<int64_t>(staging.size() * 1.25) + 1024),
+                    "emcgpu_device_reserve");
+    uploaded = true;
+  }
+  void download(emcdetail::HostEnsemble &h) const {
+    const SizeType n = nrOnGpu();
+    double *ptrs[EMCGPU_N_STREAMS];
+    for (int s = 0; s < EMCGPU_N_STREAMS; s++) {
+      h.stream[s].resize(n);
+      ptrs[s] = h.stream[s].data();
+    }
+    h.packed.resize(n);
+    if (n)
+      emcgpu::require(ctx, emcgpu_get_ensemble(ctx, ptrs, h.packed.data()), "emcgpu_get_ensemble");
+  }
+
+public:
+  emcBasicParticleHandler() = delete;
+  emcBasicParticleHandler(const emcBasicParticleHandler &) = delete;
+  emcBasicParticleHandler(const DeviceType &inDevice, PMScheme &inPMScheme, MapIdxToParticleTypes &inTypes,
+                          SizeType inNrCarriersPerParticle, SizeType inSeed)
+      : Base(inDevice, inPMScheme, inNrCarriersPerParticle, inTypes), hostRng(inSeed), seed(inSeed) {
+    if (inPMScheme.deviceSchemeId() != 1)
+      emcMessage::getInstance()
+          .addError("The particle-mesh scheme has no device implementation (deviceSchemeId() == 0); it cannot run on "
+                    "the GPU path and there is no CPU fallback.")
+          .print();
+    SizeType moved = 0;
+    for (const auto &[idxType, type] : this->idxTypeToPartType) {
+      if (!type->isMoved())
+        continue;
+      gpuType = idxType;
+      moved++;
+      type->initScatterTables(); // host, exactly as the reference (emcAbstractParticleHandler.hpp:99-101)
+      if (type->scatterHandler.hasGrainScatterMechanism())
+        emcMessage::getInstance()
+            .addError("Grain scattering has no device implementation yet; it cannot run on the GPU path and there is "
+                      "no CPU fallback.")
+            .print();
+    }
+    if (moved != 1)
+      emcMessage::getInstance()
+          .addError("The GPU particle handler moves exactly one particle type (found " + std::to_string(moved) + ").")
+          .print();
+    const char *e = std::getenv("EMCGPU_DEVICE");
+    if (emcgpu_create(e ? std::atoi(e) : 0, &ctx) != EMCGPU_OK)
+      emcMessage::getInstance()
+          .addError(std::string("cannot create the GPU context: ") + emcgpu_last_error(nullptr))
+          .print();
+    auto &type = *this->idxTypeToPartType.at(gpuType);
+    emcgpu::uploadParticleType(ctx, type);
+    emcdetail::FlatDevice<T, Dim> flat(this->device);
+    emcgpu::require(ctx,
+                    emcgpu_device_configure(ctx, &flat.desc, type.getCharge(), static_cast<double>(this->nrCarriersPerPart),
+                                            this->expNrPart[gpuType].raw(), EMCGPU_MATH_FAST),
+                    "emcgpu_device_configure");
+  }
+  ~emcBasicParticleHandler() override {
+    if (ctx)
+      emcgpu_destroy(ctx);
+  }
+
+  // the context that holds the ensemble and the grids of the run (emcSimulation, emcSORSolver::attach, tests)
+  emcgpu_ctx *gpuContext() { return ctx; }
+  SizeType gpuParticleType() const { return gpuType; }
+
+  bool calcsPartPartInteraction() const override { return false; }
+  SizeType getNrParticles(SizeType idxType) const { return idxType == gpuType ? nrOnGpu() : 0; }
+  void printNrParticles() const override {
+    for (const auto &[idxType, type] : this->idxTypeToPartType)
+      std::cout << "\t" << getNrParticles(idxType) << " " << type->getName() << "\n";
+  }
+
+  // cells in storage order; while (n >= 1) { add; n -= carriers per particle }; one more with probability n
+  void generateInitialParticles(const emcGrid<T, Dim> &potential) override {
+    auto &type = *this->idxTypeToPartType.at(gpuType);
+    std::uniform_real_distribution<T> uniform(0., 1.);
+    SizeVec coord;
+    for (coord.fill(0); !this->device.isEndCoord(coord); this->device.advanceCoord(coord)) {
+      auto toCreate = type.getInitialNrParticles(coord, this->device, potential);
+      while (toCreate >= 1) {
+        emcdetail::appendParticle(staging, type, this->device, coord, hostRng);
+        toCreate -= this->nrCarriersPerPart;
+      }
+      if (uniform(hostRng) < toCreate)
+        emcdetail::appendParticle(staging, type, this->device, coord, hostRng);
+    }
+    uploaded = false;
+    upload();
+  }
+
+  NettoParticleCounter driftScatterParticles(T tStep, std::vector<emcGrid<T, Dim>> &eField) override {
+    upload();
+    for (SizeType d = 0; d < Dim; d++)
+      emcgpu::require(ctx, emcgpu_device_set_grid(ctx, EMCGPU_GRID_EFIELD_X + static_cast<int>(d), eField[d].raw()),
+                      "emcgpu_device_set_grid");
+    auto netto = this->initNettoParticleCounter();
+    std::vector<int32_t> removed(std::max<SizeType>(1, netto[gpuType].size()), 0);
+    emcgpu::require(ctx, emcgpu_device_step(ctx, tStep, removed.data()), "emcgpu_device_step");
+    for (SizeType c = 0; c < netto[gpuType].size(); c++)
+      netto[gpuType][c] = removed[c];
+    return netto;
+  }
+
+  void assignParticlesToMesh(SizeType idxType, emcGrid<T, Dim> &gridNrParticles) override {
+    if (idxType != gpuType)
+      return;
+    upload();
+    emcgpu::require(ctx, emcgpu_device_assign(ctx), "emcgpu_device_assign");
+    std::vector<double> count(gridNrParticles.getSize());
+    emcgpu::require(ctx, emcgpu_device_get_grid(ctx, EMCGPU_GRID_COUNT, count.data()), "emcgpu_device_get_grid");
+    SizeType i = 0;
+    for (auto &v : gridNrParticles)
+      v += count[i++];
+  }
+
+  NettoParticleCounter handleOhmicContacts() override {
+    upload();
+    auto netto = this->initNettoParticleCounter();
+    std::vector<int32_t> net(std::max<SizeType>(1, netto[gpuType].size()), 0);
+    emcgpu::require(ctx, emcgpu_device_contacts(ctx, net.data(), nullptr, 0), "emcgpu_device_contacts");
+    for (SizeType c = 0; c < netto[gpuType].size(); c++)
+      netto[gpuType][c] = net[c];
+    return netto;
+  }
+
+  // "<prefix><TypeName><suffix>.txt": box extent, then per particle: index, position, k, energy, sub-valley, valley, tau
+  void print(std::string namePrefix, std::string nameSuffix) override {
+    for (const auto &[idxType, type] : this->idxTypeToPartType) {
+      std::ofstream os(namePrefix + type->getName() + nameSuffix + ".txt");
+      os << this->device.getMaxPos() << "\n";
+      if (idxType != gpuType)
+        continue;
+      emcdetail::HostEnsemble h;
+      const emcdetail::HostEnsemble *src = &staging;
+      if (uploaded) {
+        download(h);
+        src = &h;
+      }
+      const SizeType n = src->size();
+      for (SizeType i = 0; i < n; i++) {
+        os << i << " " << src->stream[EMCGPU_X][i] << " " << src->stream[EMCGPU_Y][i];
+        if (Dim > 2)
+          os << " " << src->stream[EMCGPU_Z][i];
+        os << " " << src->stream[EMCGPU_KX][i] << " " << src->stream[EMCGPU_KY][i] << " " << src->stream[EMCGPU_KZ][i] << " "
+           << src->stream[EMCGPU_ENERGY][i] << " " << ((src->packed[i] >> 8) & 0xffu) << " " << (src->packed[i] & 0xffu)
+           << " " << src->stream[EMCGPU_TAU][i];
+        if (i + 1 < n)
+          os << "\n";
+      }
+    }
+  }
+
+  // Ramo-Shockley estimate q * carriers * sum(v_x) / L over the particles with x0 <= x <= x1
+  T getChannelDriftCurrent(SizeType idxType, T x0, T x1, T channelLength) const {
+    if (idxType != gpuType)
+      return 0;
+    emcdetail::HostEnsemble h;
+    download(h);
+    const auto &type = *this->idxTypeToPartType.at(idxType);
+    T sumVx = 0;
+    for (SizeType i = 0; i < h.size(); i++) {
+      if (h.stream[EMCGPU_X][i] < x0 || h.stream[EMCGPU_X][i] > x1)
+        continue;
+      const std::array<T, 3> k = {h.stream[EMCGPU_KX][i], h.stream[EMCGPU_KY][i], h.stream[EMCGPU_KZ][i]};
+      sumVx += type.getValley(h.packed[i] & 0xffu)->getVelocity(k, h.stream[EMCGPU_ENERGY][i], (h.packed[i] >> 8) & 0xffu)[0];
+    }
+    return constants::q * this->nrCarriersPerPart * sumVx / channelLength;
+  }
+};
+
+#endif

@@ -81,6 +81,10 @@ template <class T, class DeviceType> struct emcParticleType {
     scatterHandler.addScatterMechanism(std::move(newMechanism), regions);
   }
 
+  void setGrainScatterMechanism(std::unique_ptr<emcGrainScatterMechanism<T>> &&newMechanism) {
+    scatterHandler.setGrainScatterMechanism(std::move(newMechanism));
+  }
+
   void initScatterTables() { scatterHandler.initScatterTables(); }
   void reinitScatterTables() { scatterHandler.reinitScatterTables(); }
 

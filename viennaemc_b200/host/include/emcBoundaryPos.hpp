@@ -2,6 +2,9 @@
 #ifndef EMC_BOUNDARY_POS_HPP
 #define EMC_BOUNDARY_POS_HPP
 
-enum class emcBoundaryPos : unsigned { XMIN = 0, XMAX = 1, YMIN = 2, YMAX = 3, ZMIN = 4, ZMAX = 5 };
+#include <emcUtil.hpp>
+
+// value / 2 = dimension normal to the face, value % 2 = 0 at the origin side
+enum struct emcBoundaryPos : SizeType { XMIN = 0, XMAX, YMIN, YMAX, ZMIN, ZMAX, INVALID };
 
 #endif

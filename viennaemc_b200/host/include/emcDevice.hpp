@@ -3,8 +3,8 @@
 // Interface mirrored: reference include/emcDevice.hpp (ctor :78-100, getters :113-160,
 // addConstantDopingRegion :166-171, normalisation helpers :236-262, coordinate
 // helpers :265-291, cell volume :333-343).
-// Contacts (addOhmicContact / addGateContact / addSchottkyContact, reference
-// :178-215) belong to the device-run path and are not part of this bulk-path header yet.
+// Contacts: addOhmicContact / addGateContact / addSchottkyContact (:178-215), positions along a
+// face given in the face's own axes (posToCoord(boundPos, position) :293-330).
 #ifndef EMC_DEVICE_HPP
 #define EMC_DEVICE_HPP
 
@@ -17,6 +17,7 @@
 #include <emcGrid.hpp>
 #include <emcMaterial.hpp>
 #include <emcMessage.hpp>
+#include <emcSurface.hpp>
 #include <emcUtil.hpp>
 
 template <class T, SizeType Dim> class emcDevice {
@@ -29,6 +30,7 @@ public:
   typedef emcDopingProfile<T, Dim> DopingProfileType;
   typedef std::array<T, Dim> ValueVec;
   typedef std::array<SizeType, Dim> SizeVec;
+  typedef emcSurface<T, Dim - 1> SurfaceType;
   typedef std::array<SizeType, Dim - 1> SizeVecSurface;
   typedef std::array<T, Dim - 1> ValueVecSurface;
 
@@ -40,6 +42,7 @@ private:
   T cellVolume, normedCellVolume;
   T thermalVoltage, debyeLength;
   DopingProfileType dopingProfile;
+  SurfaceType surface;
 
   void updateCellVolume() {
     cellVolume = 1.;
@@ -60,7 +63,8 @@ public:
       : material(inMaterial), maxPos(inMaxPos), spacing(inSpacing), temperature(inTemperature),
         thermalVoltage(constants::kB / constants::q * temperature),
         debyeLength(std::sqrt(constants::eps0 * material.getEpsR() * thermalVoltage / constants::q / material.getNi())),
-        dopingProfile(maxPosToExtent(inMaxPos, inSpacing), material.getNi(), material.getNi()) {
+        dopingProfile(maxPosToExtent(inMaxPos, inSpacing), material.getNi(), material.getNi()),
+        surface(maxPosToExtent(inMaxPos, inSpacing), thermalVoltage) {
     if (!(debyeLength > 0) || !std::isfinite(debyeLength))
       throw std::domain_error("emcDevice: computed Debye length is non-positive or non-finite. Check the material's "
                               "intrinsic carrier concentration (Ni) and permittivity.");
@@ -74,6 +78,7 @@ public:
 
   const MaterialType &getMaterial() const { return material; }
   const DopingProfileType &getDopingProfile() const { return dopingProfile; }
+  const SurfaceType &getSurface() const { return surface; }
   T getTemperature() const { return temperature; }
   T getThermalVoltage() const { return thermalVoltage; }
   T getDebyeLength() const { return debyeLength; }
@@ -84,6 +89,22 @@ public:
 
   void addConstantDopingRegion(ValueVec inMinPos, ValueVec inMaxPos, T inDoping) {
     dopingProfile.addConstantDopingRegion(posToCoord(inMinPos), posToCoord(inMaxPos), inDoping);
+  }
+
+  // minPos / maxPos: extent of the contact along the face, in the face's own coordinates [m]
+  void addOhmicContact(emcBoundaryPos boundaryPos, T voltage, ValueVecSurface minPos, ValueVecSurface maxPos) {
+    surface.addContact(boundaryPos, emcContactType::OHMIC, voltage, posToCoord(boundaryPos, minPos),
+                       posToCoord(boundaryPos, maxPos));
+  }
+  void addGateContact(emcBoundaryPos boundaryPos, T voltage, ValueVecSurface minPos, ValueVecSurface maxPos, T epsRoxide,
+                      T thickness, T barrierHeight) {
+    surface.addContact(boundaryPos, emcContactType::GATE, voltage, posToCoord(boundaryPos, minPos),
+                       posToCoord(boundaryPos, maxPos), epsRoxide, thickness, barrierHeight);
+  }
+  void addSchottkyContact(emcBoundaryPos boundaryPos, T voltage, ValueVecSurface minPos, ValueVecSurface maxPos,
+                          T barrierHeight) {
+    surface.addContact(boundaryPos, emcContactType::SCHOTTKY, voltage, posToCoord(boundaryPos, minPos),
+                       posToCoord(boundaryPos, maxPos), 0, 0, barrierHeight);
   }
 
   bool isOutOfBounds(ValueVec &position) const {
@@ -118,6 +139,17 @@ public:
     SizeVec coord;
     for (SizeType d = 0; d < Dim; d++)
       coord[d] = static_cast<SizeType>(std::round(position[d] / spacing[d]));
+    return coord;
+  }
+  // position along a face -> face coordinates (the axes of the face keep their device order)
+  SizeVecSurface posToCoord(emcBoundaryPos boundPos, const ValueVecSurface &position) const {
+    const SizeType fixed = toUnderlying(boundPos) / 2;
+    SizeVecSurface coord;
+    for (SizeType d = 0, o = 0; d < Dim; d++)
+      if (d != fixed) {
+        coord[o] = static_cast<SizeType>(std::round(position[o] / spacing[d]));
+        o++;
+      }
     return coord;
   }
 };

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include <ScatterMechanisms/emcScatterMechanism.hpp>
+#include <emcGrainScatterMechanism.hpp>
 #include <emcUtil.hpp>
 
 template <class T, class DeviceType> class emcScatterHandler {
@@ -43,6 +44,7 @@ private:
   std::vector<std::unique_ptr<ScatterMechanism>> mechanismList;
   std::map<ValleyRegion, TableSet> sets;
   T grainTau = 1.;
+  std::unique_ptr<emcGrainScatterMechanism<T>> grainMechanism;
 
   void tabulate() {
     for (auto &[key, set] : sets) {
@@ -54,6 +56,8 @@ private:
           row.push_back(mechanismList[set.mechanisms[m]]->getScatterRate((level + 1) * dE, key.second));
       }
     }
+    if (grainMechanism)
+      grainTau = 1. / grainMechanism->getScatterRate();
   }
 
   void accumulateAndNormalise() {
@@ -105,6 +109,11 @@ public:
     for (const int region : regions)
       sets[ValleyRegion(valley, static_cast<SizeType>(region))].mechanisms.push_back(idx);
   }
+
+  void setGrainScatterMechanism(std::unique_ptr<emcGrainScatterMechanism<T>> &&newMechanism) {
+    grainMechanism = std::move(newMechanism);
+  }
+  bool hasGrainScatterMechanism() const { return static_cast<bool>(grainMechanism); }
 
   void initScatterTables() {
     tabulate();
