@@ -150,8 +150,13 @@ int64_t emcgpu_launch_count(const emcgpu_ctx *ctx);
 /* run all later work of ctx on this cudaStream_t (NULL = default stream) */
 int emcgpu_set_stream(emcgpu_ctx *ctx, void *cudaStream);
 int emcgpu_synchronize(emcgpu_ctx *ctx);
-/* tuning knobs (no effect on results): "vec" = particles per lane and loop
- * iteration of the one-step kernel (1, 2 or 4; default 2) */
+/* options: "vec" = particles per lane and loop iteration of the one-step kernel
+ * (1, 2 or 4; default 2; no effect on results); "poisson_interval" = n: emcgpu_device_run*
+ * solves Poisson only every n-th step (emcSimulation::setPoissonInterval, emcSimulation.hpp:80);
+ * "sor_order" = 0: the reference's lexicographic Gauss-Seidel order (default; iterates and sweep counts
+ * are the reference's), 1: red-black ordering (same equation and stopping rule, parallel, converges to
+ * the same potential within the solver's accuracy); "sor_kernel" = 1 forces the general hyperplane
+ * form of the lexicographic solver (no effect on results) */
 int emcgpu_set_option(emcgpu_ctx *ctx, const char *name, int64_t value);
 
 /* ---- physics model (built on the host by the reference-compatible API) - */

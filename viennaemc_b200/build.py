@@ -77,12 +77,13 @@ def build_examples(force: bool = False) -> dict:
     common = ["g++", *HOST_FLAGS, "-I", HOST_INC, "-I", os.path.join(ROOT, "include")]
     link = ["-L", LIBDIR, "-lemcgpu", "-Wl,-rpath,$ORIGIN/../lib"]
     deps = _sources(os.path.join(PKG, "host"), os.path.join(ROOT, "include")) + [os.path.join(LIBDIR, "libemcgpu.so")]
-    own = os.path.join(PKG, "host", "examples", "bulkSimulation.cpp")
-    if os.path.exists(own):
-        target = os.path.join(bindir, "bulkSimulation")
-        if force or _newer(target, deps):
-            subprocess.check_call([*common, "-o", target, own, *link])
-        out["bulkSimulation"] = target
+    for name in ("bulkSimulation", "resistor2D"):
+        own = os.path.join(PKG, "host", "examples", name + ".cpp")
+        if os.path.exists(own):
+            target = os.path.join(bindir, name)
+            if force or _newer(target, deps):
+                subprocess.check_call([*common, "-o", target, own, *link])
+            out[name] = target
     ref_main = os.path.join(REFERENCE, "examples", "bulkSimulation", "bulkSimulation.cpp")
     target = os.path.join(bindir, "reference_bulkSimulation_gpu")
     if os.path.exists(ref_main) and (force or _newer(target, deps)):
@@ -90,6 +91,15 @@ def build_examples(force: bool = False) -> dict:
                                ref_main, *link])
     if os.path.exists(target):
         out["reference_bulkSimulation_gpu"] = target
+    # the UNMODIFIED device-run examples of the reference (emcSimulation + emcBasicParticleHandler + emcSORSolver +
+    # PM scheme) compiled against OUR headers: every object they create is the GPU-backed drop-in
+    for name, rel in (("reference_resistor2D_gpu", ("examples", "resistor2D", "resistor2D.cpp")),):
+        ref_main = os.path.join(REFERENCE, *rel)
+        target = os.path.join(bindir, name)
+        if os.path.exists(ref_main) and (force or _newer(target, deps)):
+            subprocess.check_call([*common, "-o", target, ref_main, *link])
+        if os.path.exists(target):
+            out[name] = target
     return out
 
 

@@ -36,6 +36,8 @@ struct DevGeometry {
   const int32_t *region;     // [cells]
   const int8_t *faceContact; // [cells][2*dim]
   const double *doping;      // [cells], 1/m^3
+  const double *dopingNorm;  // [cells], doping / Ni (emcDevice::normalizeDoping)
+  const uint8_t *cellKind;   // [cells]: bit 0 reservoir contact cell (ohmic / Schottky), bit 1 has a gate face
 };
 
 __device__ __forceinline__ void cellCoord(const DevGeometry &g, int cell, int c[3]) {
@@ -66,71 +68,95 @@ __device__ __forceinline__ int posToCell(const DevGeometry &g, double x, double 
 }
 
 // ---------------------------------------------------------------------------
-// K3: nearest-grid-point charge assignment.  Every add is the same integer-valued
-// nrCarriers, so the fp64 sums are exact and independent of the order of the atomics.
-// Warp-aggregated (__match_any_sync on the cell index) into a shared-memory copy of
-// the grid when it fits, flushed with one global atomic per touched cell and CTA.
-struct AssignParams {
-  const double *x, *y, *z;
-  int64_t n;
-  double nrCarriers;
-  double *count; // [cells], zeroed by the caller
-  int32_t useSmem;
+// Control block of the step loop, resident in device memory.  Everything the kernels of one EMC step hand to
+// each other (ensemble size, list sizes, step index, counters) lives here, so that the host never has to
+// wait for a kernel between the steps of a chunk and the per-step launch sequence is the same for every step
+// (it is captured once as a CUDA graph).
+struct RunCtl {
+  int32_t n;          // live particles
+  int32_t nKept;      // survivors of this step's compaction
+  int32_t nReservoir; // entries of this step's reservoir list
+  int32_t toInject;   // particles the contacts inject in this step
+  int32_t slot;       // index of the step inside the running chunk (row of the counter tables)
+  int32_t avgFromSlot; // slots >= this one add potential / concentration to the running sums
+  int32_t poissonInterval;
+  int32_t capacity;   // particles the ensemble allocation can hold
+  long long step;     // Philox step index of the next particle step
+  long long runSteps; // steps done since configure (frozen-field sub-cycling)
+  unsigned int ticket[4]; // "last block done" counters of the multi-block kernels
+  int32_t removedPerContact[kMaxContacts];
+  int32_t net[kMaxContacts];
 };
 
-__global__ void __launch_bounds__(256) ngpAssignKernel(const __grid_constant__ DevGeometry G, const AssignParams A) {
-  extern __shared__ double sCount[];
-  if (A.useSmem) {
-    for (int i = threadIdx.x; i < G.cells; i += blockDim.x) sCount[i] = 0.0;
-    __syncthreads();
-  }
-  const int lane = threadIdx.x & 31;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t nRounded = (A.n + 31) & ~int64_t(31);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nRounded; i += stride) {
-    const bool live = i < A.n;
-    const int cell = live ? posToCell(G, A.x[i], A.y[i], G.dim > 2 ? A.z[i] : 0.0) : -1;
-    const unsigned peers = __match_any_sync(0xffffffffu, cell);
-    if (live && lane == __ffs(peers) - 1) {
-      const double add = A.nrCarriers * __popc(peers);
-      if (A.useSmem)
-        atomicAdd(&sCount[cell], add);
-      else
-        atomicAdd(&A.count[cell], add);
+// true in exactly one block of the grid: the one that finishes last.  Its threads see everything the other
+// blocks wrote before calling this.  The ticket resets itself for the next launch.
+__device__ __forceinline__ bool lastBlockDone(unsigned int *ticket) {
+  __shared__ bool sLast;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) sLast = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;
+  __syncthreads();
+  if (sLast) __threadfence();
+  return sLast;
+}
+
+// in-place exclusive scan of a[0..n) by one block (any size that is a multiple of 32, <= 1024); returns the total
+__device__ int blockExclusiveScan(int32_t *a, int n) {
+  __shared__ int sCarry;
+  __shared__ int sWarp[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
+  if (threadIdx.x == 0) sCarry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = i < n ? __ldcg(a + i) : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
     }
-  }
-  if (A.useSmem) {
+    if (lane == 31) sWarp[warp] = incl;
     __syncthreads();
-    for (int i = threadIdx.x; i < G.cells; i += blockDim.x)
-      if (sCount[i] != 0.0) atomicAdd(&A.count[i], sCount[i]);
+    if (warp == 0) {
+      int w = lane < nWarps ? sWarp[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      sWarp[lane] = w;
+    }
+    __syncthreads();
+    const int warpOff = warp ? sWarp[warp - 1] : 0;
+    const int carry = sCarry;
+    if (i < n) a[i] = carry + warpOff + incl - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) sCarry = carry + warpOff + incl;
+    __syncthreads();
   }
+  return sCarry;
 }
 
 // ---------------------------------------------------------------------------
-// K4: concentration from counts; E = -grad(phi) with the reference's boundary rules
-__global__ void concentrationKernel(const __grid_constant__ DevGeometry G, const double *count, double *conc) {
-  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
-  if (cell >= G.cells) return;
+// K4: concentration from counts (emcSimulationResults::updateCurrentParticleConcentrations :98-116)
+__device__ __forceinline__ double cellConcentration(const DevGeometry &G, int cell, double count) {
   int c[3];
   cellCoord(G, cell, c);
-  double v = __dmul_rn(__ddiv_rn(count[cell], G.ni), __ddiv_rn(1.0, G.cellVolume));
+  double v = __dmul_rn(__ddiv_rn(count, G.ni), __ddiv_rn(1.0, G.cellVolume));
   for (int i = 0; i < G.dim; i++)
     if (c[i] == 0 || c[i] == G.extent[i] - 1) v = __dmul_rn(v, 2.0);
-  conc[cell] = v;
+  return v;
+}
+__global__ void concentrationKernel(const __grid_constant__ DevGeometry G, const double *count, double *conc) {
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell < G.cells) conc[cell] = cellConcentration(G, cell, count[cell]);
 }
 
-// emcSimulationResults::updateAverageCharacteristics (:87-93): running sums of potential and concentration
-__global__ void accumulateKernel(int cells, const double *pot, const double *conc, double *sumPot, double *sumConc) {
-  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
-  if (cell >= cells) return;
-  sumPot[cell] = __dadd_rn(sumPot[cell], pot[cell]);
-  sumConc[cell] = __dadd_rn(sumConc[cell], conc[cell]);
-}
-
-// interior: Vt (phi[prev] - phi[next]) / (2 h); on a face: 0 (artificial boundary) or the inner neighbour's value (contact)
-__global__ void efieldKernel(const __grid_constant__ DevGeometry G, const double *pot, double *e) {
-  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
-  if (cell >= G.cells) return;
+// E = -grad(phi) with the reference's boundary rules (calcEFieldAtGridPts + setEFieldBoundaryValues,
+// emcEFieldCalculation.hpp:13-30, :58-82).  Interior: Vt (phi[prev] - phi[next]) / (2 h); on a face: 0
+// (artificial boundary) or the inner neighbour's value (contact).
+__device__ __forceinline__ void cellEField(const DevGeometry &G, int cell, const double *pot, double *e) {
   int c[3];
   cellCoord(G, cell, c);
   const int stride[3] = {1, G.extent[0], G.extent[0] * G.extent[1]};
@@ -151,35 +177,132 @@ __global__ void efieldKernel(const __grid_constant__ DevGeometry G, const double
     e[(size_t)i * G.cells + cell] = v;
   }
 }
+__global__ void efieldKernel(const __grid_constant__ DevGeometry G, const double *pot, double *e) {
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell < G.cells) cellEField(G, cell, pot, e);
+}
 
 // ---------------------------------------------------------------------------
-// K5: nonlinear SOR in the reference's own (lexicographic Gauss-Seidel) update order.
-// The update of a cell needs the NEW values of its lower neighbours and the OLD values of
-// its upper neighbours; all cells on a hyperplane x+y(+z) = const are therefore independent,
-// and sweeping the hyperplanes in order reproduces the sequential sweep of
-// emcSORSolver.hpp:157-196 exactly (same iterates, same sweep count up to the last bits of exp).
-// One CTA, potential resident in shared memory, convergence loop inside the kernel.
+// K3: nearest-grid-point charge assignment (emcNGPScheme::assignToMesh :36-47).  Every add is the same
+// integer-valued nrCarriers, so the fp64 sums are exact and independent of the order of the atomics.
+// Warp-aggregated (__match_any_sync on the cell index) into a shared-memory copy of the grid when it fits,
+// flushed with one global atomic per touched cell and CTA.  The block that finishes last turns the counts
+// into concentrations, adds to the running sums when asked (updateAverageCharacteristics :87-93) and, inside
+// the step loop, closes the step in the control block.
+struct AssignParams {
+  const double *x, *y, *z;
+  double nrCarriers;
+  double *count; // [cells], zeroed by the caller
+  double *conc;  // [cells] or nullptr: counts only
+  const double *pot;
+  double *sumPot, *sumConc;
+  RunCtl *ctl;
+  int32_t *counters; // [slots][2][nContacts] or nullptr
+  int32_t closeStep; // 1: the ensemble is ctl->nKept + ctl->toInject particles and the step ends here
+  int32_t useSmem;
+};
+
+__global__ void __launch_bounds__(256) ngpAssignKernel(const __grid_constant__ DevGeometry G, const AssignParams A) {
+  extern __shared__ double sCount[];
+  const int64_t n = A.closeStep ? A.ctl->nKept + A.ctl->toInject : A.ctl->n;
+  if (A.useSmem) {
+    for (int i = threadIdx.x; i < G.cells; i += blockDim.x) sCount[i] = 0.0;
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nRounded = (n + 31) & ~int64_t(31);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nRounded; i += stride) {
+    const bool live = i < n;
+    const int cell = live ? posToCell(G, A.x[i], A.y[i], G.dim > 2 ? A.z[i] : 0.0) : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, cell);
+    if (live && lane == __ffs(peers) - 1) {
+      const double add = A.nrCarriers * __popc(peers);
+      if (A.useSmem)
+        atomicAdd(&sCount[cell], add);
+      else
+        atomicAdd(&A.count[cell], add);
+    }
+  }
+  if (A.useSmem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < G.cells; i += blockDim.x)
+      if (sCount[i] != 0.0) atomicAdd(&A.count[i], sCount[i]);
+  }
+  if (!A.conc && !A.closeStep) return;
+  if (!lastBlockDone(&A.ctl->ticket[3])) return;
+  const bool average = A.closeStep && A.ctl->slot >= A.ctl->avgFromSlot;
+  if (A.conc)
+    for (int cell = threadIdx.x; cell < G.cells; cell += blockDim.x) {
+      const double v = cellConcentration(G, cell, __ldcg(A.count + cell));
+      A.conc[cell] = v;
+      if (average) {
+        A.sumPot[cell] = __dadd_rn(A.sumPot[cell], A.pot[cell]);
+        A.sumConc[cell] = __dadd_rn(A.sumConc[cell], v);
+      }
+    }
+  if (A.closeStep && threadIdx.x == 0) {
+    RunCtl &c = *A.ctl;
+    if (A.counters)
+      for (int k = 0; k < G.nContacts; k++) {
+        A.counters[(c.slot * 2 + 0) * G.nContacts + k] = c.removedPerContact[k];
+        A.counters[(c.slot * 2 + 1) * G.nContacts + k] = c.net[k];
+      }
+    for (int k = 0; k < kMaxContacts; k++) c.removedPerContact[k] = c.net[k] = 0;
+    c.n = c.nKept + c.toInject;
+    c.slot++;
+    c.step++;
+    c.runSteps++;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K5: nonlinear SOR in the reference's own (lexicographic Gauss-Seidel) update order, as a PIPELINED
+// WAVEFRONT.  The update of a cell needs the NEW values of its lower neighbours and the OLD values of its
+// upper neighbours, so all cells on a hyperplane x+y(+z) = const are independent, and sweeping the
+// hyperplanes in order reproduces the sequential sweep of emcSORSolver.hpp:157-196 exactly.  A sweep alone
+// is a chain of nPlanes dependent stages with a handful of cells each (121 stages of <= 21 cells on the
+// resistor grid) -- latency, not work.  But sweep s+1 may update plane p as soon as sweep s has finished
+// plane p+1: consecutive sweeps run TWO planes apart, in place, on the one copy of the potential (in a
+// stage the planes written all have one parity and the planes read the other).  S sweeps then take
+// nPlanes + 2(S-1) stages instead of S * nPlanes.
+//
+// How many sweeps are needed is only known when a sweep ends (max |delta| <= accuracy), by which time later
+// sweeps have already touched the potential.  Every update is therefore also logged into a ring of per-sweep
+// snapshots in global memory (write-only, off the dependency chain); when sweep S turns out to be the
+// converged one the result is read from snapshot S.  Sweeps are started in waves of W = (sweeps of the
+// previous solve) + 2, so next to nothing is computed speculatively; a wave that ends unconverged is
+// followed by another.  Iterates, result and sweep count are those of the sequential sweep.
+// One CTA, potential resident in shared memory.
+constexpr int kSorThreads = 1024;
+constexpr int kSorRing = 64; // snapshots / sweeps in flight per wave
+
 struct SorParams {
   double *pot;        // [cells] in/out
   const double *conc; // [cells] or nullptr: equilibrium solve (n = exp(phi), p = 1/n)
+  double *history;    // [kSorRing][cells] snapshots
   double accuracy;    // normalised (volts / Vt)
   double omega;
   int32_t maxSweeps;
   int32_t potInSmem;
-  int32_t *sweepsOut;
+  int32_t *sweepsOut; // in: sweep count of the previous solve (wave width hint); out: of this one
+  double *efield;     // [dim][cells] or nullptr: E = -grad(phi) of the result (pmScheme.calcEField), fused
+  RunCtl *ctl;        // inside the step loop (or nullptr): frozen-field sub-cycling, per-step sweep counts
+  int32_t *sweepsPerStep; // [slots] or nullptr
 };
 
-constexpr int kSorThreads = 512;
-
-__global__ void __launch_bounds__(kSorThreads) sorKernel(const __grid_constant__ DevGeometry G, const SorParams S) {
+__global__ void __launch_bounds__(kSorThreads) sorPlanesKernel(const __grid_constant__ DevGeometry G, const SorParams S) {
   extern __shared__ double sPot[];
-  __shared__ double sErr[kSorThreads / 32];
-  __shared__ double sMax;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double *pot = S.potInSmem ? sPot : S.pot;
-  if (S.potInSmem) {
-    for (int i = tid; i < G.cells; i += blockDim.x) sPot[i] = S.pot[i];
+  __shared__ unsigned long long sErr[kSorRing]; // max |delta| per sweep in flight, as the bits of a non-negative double
+  const int tid = threadIdx.x;
+  if (S.ctl && S.ctl->runSteps % S.ctl->poissonInterval != 0) { // emcSimulation.hpp:116, :180-184: reuse the field
+    if (tid == 0 && S.sweepsPerStep) S.sweepsPerStep[S.ctl->slot] = 0;
+    return;
   }
+  double *pot = S.potInSmem ? sPot : S.pot;
+  if (S.potInSmem)
+    for (int i = tid; i < G.cells; i += blockDim.x) sPot[i] = S.pot[i];
+  if (tid < kSorRing) sErr[tid] = 0ull;
   // emcSORSolver.hpp:330-350
   double h[3] = {1, 1, 1}, hF[3] = {0, 0, 0};
   for (int i = 0; i < G.dim; i++) h[i] = __ddiv_rn(G.spacing[i], G.debyeLength);
@@ -196,35 +319,48 @@ __global__ void __launch_bounds__(kSorThreads) sorKernel(const __grid_constant__
     hFSum = __dadd_rn(hFSum, hF[i]);
     hProd = __dmul_rn(hProd, h[i]);
   }
+  const double twoHFSum = __dmul_rn(2.0, hFSum);
   const int stride[3] = {1, G.extent[0], G.extent[0] * G.extent[1]};
   const int ex = G.extent[0], ey = G.extent[1], ez = G.dim > 2 ? G.extent[2] : 1;
   const int nPlanes = ex + ey + ez - 2;
+  const int nYZ = ey * ez;
+  const int hint = *S.sweepsOut;
+  int width = hint > 0 ? hint + 2 : 24;
+  width = min(width, kSorRing - 1);
   __syncthreads();
-  int sweeps = 0;
-  for (;;) {
-    double myErr = 0.0;
-    for (int plane = 0; plane < nPlanes; plane++) {
-      // cells with x + y + z == plane: enumerate (y, z) pairs, x follows
-      const int nYZ = ey * ez;
-      for (int yz = tid; yz < nYZ; yz += blockDim.x) {
+
+  int firstSweep = 0; // of the current wave
+  int converged = -1;
+  while (converged < 0) {
+    if (S.maxSweeps > 0) width = min(width, S.maxSweeps - firstSweep);
+    const int nStages = nPlanes + 2 * (width - 1);
+    for (int t = 0; t < nStages && converged < 0; t++) {
+      // sweeps of the wave that are inside the grid at this stage: local index j, plane t - 2j
+      const int jLo = t >= nPlanes ? (t - nPlanes + 2) / 2 : 0;
+      const int jHi = min(width - 1, t / 2);
+      const int items = (jHi - jLo + 1) * nYZ;
+      for (int idx = tid; idx < items; idx += blockDim.x) {
+        const int j = jLo + idx / nYZ, yz = idx % nYZ;
         const int y = yz % ey, z = yz / ey;
-        const int x = plane - y - z;
+        const int x = t - 2 * j - y - z;
         if (x < 0 || x >= ex) continue;
         const int cell = x + ex * (y + ey * z);
-        if (cellIsReservoir(G, cell)) continue;
+        const unsigned kind = __ldg(G.cellKind + cell);
+        if (kind & 1u) continue;
+        const int sweep = firstSweep + j;
         const int c[3] = {x, y, z};
         const double cur = pot[cell];
         double p, n;
         if (S.conc) {
           p = exp(-cur);
-          n = S.conc[cell];
+          n = __ldg(S.conc + cell);
         } else {
           n = exp(cur);
           p = __ddiv_rn(1.0, n);
         }
-        const double dop = __ddiv_rn(G.doping[cell], G.ni);
+        const double dop = __ldg(G.dopingNorm + cell);
         double num = __dmul_rn(hProd, __dadd_rn(__dadd_rn(__dsub_rn(p, n), dop), __dmul_rn(cur, __dadd_rn(p, n))));
-        double den = __dadd_rn(__dmul_rn(2.0, hFSum), __dmul_rn(hProd, __dadd_rn(n, p)));
+        double den = __dadd_rn(twoHFSum, __dmul_rn(hProd, __dadd_rn(n, p)));
         for (int i = 0; i < G.dim; i++) {
 #pragma unroll
           for (int side = 0; side < 2; side++) {
@@ -233,7 +369,7 @@ __global__ void __launch_bounds__(kSorThreads) sorKernel(const __grid_constant__
               num = __dadd_rn(num, __dmul_rn(pot[cell + (side == 0 ? -stride[i] : stride[i])], hF[i]));
             } else {
               num = __dadd_rn(num, __dmul_rn(pot[cell + (side == 0 ? stride[i] : -stride[i])], hF[i]));
-              const int ct = G.faceContact[cell * 2 * G.dim + 2 * i + side];
+              const int ct = (kind & 2u) ? G.faceContact[cell * 2 * G.dim + 2 * i + side] : -1;
               if (ct >= 0 && G.contactType[ct] == 2) { // gate: Robin term (:399-412)
                 const double gammaOx = __ddiv_rn(G.gateEpsOx[ct], G.epsR);
                 const double tOx = __ddiv_rn(G.gateThickness[ct], G.debyeLength);
@@ -247,20 +383,362 @@ __global__ void __launch_bounds__(kSorThreads) sorKernel(const __grid_constant__
           }
         }
         const double delta = __dmul_rn(S.omega, __dsub_rn(__ddiv_rn(num, den), cur));
+        const double next = __dadd_rn(cur, delta);
+        pot[cell] = next;
+        S.history[(size_t)(sweep % kSorRing) * G.cells + cell] = next;
+        atomicMax(&sErr[sweep % kSorRing], (unsigned long long)__double_as_longlong(fabs(delta)));
+      }
+      __syncthreads();
+      // the sweep whose last plane was this stage's
+      const int jFin = t - (nPlanes - 1);
+      if (jFin >= 0 && (jFin & 1) == 0 && (jFin >> 1) < width) {
+        const int sweep = firstSweep + (jFin >> 1);
+        const double err = __longlong_as_double((long long)sErr[sweep % kSorRing]);
+        if (!(err > S.accuracy) || (S.maxSweeps > 0 && sweep + 1 >= S.maxSweeps)) converged = sweep;
+      }
+    }
+    if (converged < 0) {
+      __syncthreads();
+      if (tid < kSorRing) sErr[tid] = 0ull;
+      __syncthreads();
+      firstSweep += width;
+      width = min(2 * width, kSorRing - 1);
+    }
+  }
+  // result = snapshot of the converged sweep (cells that are never updated keep their value)
+  for (int i = tid; i < G.cells; i += blockDim.x) {
+    const bool fixed = G.cellKind[i] & 1u;
+    if (!fixed)
+      S.pot[i] = S.history[(size_t)(converged % kSorRing) * G.cells + i];
+    else if (S.potInSmem)
+      S.pot[i] = sPot[i];
+  }
+  if (tid == 0) {
+    *S.sweepsOut = converged + 1;
+    if (S.ctl && S.sweepsPerStep) S.sweepsPerStep[S.ctl->slot] = converged + 1;
+  }
+  if (S.efield) {
+    __syncthreads();
+    for (int i = tid; i < G.cells; i += blockDim.x) cellEField(G, i, S.pot, S.efield);
+  }
+}
+
+// The same pipelined wavefront with a FIXED assignment of work to threads and the update of a cell split
+// over two threads of different warps.  One grid row (y, z) of one sweep of the wave is walked along x, one
+// cell per stage, by a PREPARER and a FINISHER:
+//   preparer, one stage ahead: old value of the cell (final by then), exp(phi), charge term, denominator;
+//   finisher: neighbour sums in the reference's order, division, relaxation, store, error maximum (kept in
+//             a register until the row ends).
+// Warps issue in order, so within one thread the two halves would simply add up; on different warps they
+// overlap and a stage costs the longer of the two.  Hand-over through a double-buffered shared-memory
+// record per row.  Used when a wave of rows fits the CTA (IPT rows per thread pair); sorPlanesKernel is the
+// general form.
+struct SorGate { // Robin term of a gate face (emcSORSolver.hpp:399-412)
+  double numTerm, denTerm;
+};
+__device__ __forceinline__ SorGate sorGateTerm(const DevGeometry &G, int ct, bool nonEquilibrium, double hFi, double hi) {
+  const double gammaOx = __ddiv_rn(G.gateEpsOx[ct], G.epsR);
+  const double tOx = __ddiv_rn(G.gateThickness[ct], G.debyeLength);
+  const double gF = __ddiv_rn(__dmul_rn(2.0, gammaOx), tOx);
+  double Vg = __ddiv_rn(G.gateBarrier[ct], G.thermalVoltage);
+  if (nonEquilibrium) Vg = __dadd_rn(Vg, __ddiv_rn(G.contactVoltage[ct], G.thermalVoltage));
+  SorGate g;
+  g.numTerm = __dmul_rn(__dmul_rn(__dmul_rn(gF, Vg), hFi), hi);
+  g.denTerm = __dmul_rn(__dmul_rn(gF, hFi), hi);
+  return g;
+}
+
+constexpr int kSorPairs = kSorThreads / 2; // finisher threads [0, kSorPairs), preparers behind them
+
+// shared memory: potential (cells doubles, when it fits) followed by the hand-over records
+template <int IPT> constexpr size_t sorRowsHandoverBytes() { return (size_t)2 * IPT * kSorPairs * (3 * sizeof(double) + sizeof(uint32_t)); }
+
+template <int IPT, int DIM>
+__global__ void __launch_bounds__(kSorThreads) sorRowsKernel(const __grid_constant__ DevGeometry G, const SorParams S) {
+  extern __shared__ double sPot[];
+  __shared__ unsigned long long sErr[kSorRing];
+  const int tid = threadIdx.x;
+  if (S.ctl && S.ctl->runSteps % S.ctl->poissonInterval != 0) {
+    if (tid == 0 && S.sweepsPerStep) S.sweepsPerStep[S.ctl->slot] = 0;
+    return;
+  }
+  constexpr int kItems = IPT * kSorPairs;
+  double *pot = S.potInSmem ? sPot : S.pot;
+  double *hand = sPot + (S.potInSmem ? G.cells : 0); // [2][3][kItems] cur, a, den; then [2][kItems] kind
+  uint32_t *handKind = reinterpret_cast<uint32_t *>(hand + 2 * 3 * kItems);
+  if (S.potInSmem)
+    for (int i = tid; i < G.cells; i += blockDim.x) sPot[i] = S.pot[i];
+  if (tid < kSorRing) sErr[tid] = 0ull;
+  double h[3] = {1, 1, 1}, hF[3] = {0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < DIM; i++) h[i] = __ddiv_rn(G.spacing[i], G.debyeLength);
+  if (DIM == 2) {
+    hF[0] = __ddiv_rn(h[1], h[0]);
+    hF[1] = __ddiv_rn(h[0], h[1]);
+  } else {
+    hF[0] = __ddiv_rn(__dmul_rn(h[1], h[2]), h[0]);
+    hF[1] = __ddiv_rn(__dmul_rn(h[0], h[2]), h[1]);
+    hF[2] = __ddiv_rn(__dmul_rn(h[0], h[1]), h[2]);
+  }
+  double hFSum = 0.0, hProd = 1.0;
+#pragma unroll
+  for (int i = 0; i < DIM; i++) {
+    hFSum = __dadd_rn(hFSum, hF[i]);
+    hProd = __dmul_rn(hProd, h[i]);
+  }
+  const double twoHFSum = __dmul_rn(2.0, hFSum);
+  const int ex = G.extent[0], ey = G.extent[1], ez = DIM > 2 ? G.extent[2] : 1;
+  const int strideY = ex, strideZ = ex * ey;
+  const int nPlanes = ex + ey + ez - 2;
+  const int nYZ = ey * ez;
+  const bool nonEq = S.conc != nullptr;
+  const bool preparer = tid >= kSorPairs;
+  const int lane0 = preparer ? tid - kSorPairs : tid;
+  const int hint = *S.sweepsOut;
+  int width = hint > 0 ? hint + 2 : 24;
+  const int widthCap = min(kSorRing - 1, max(1, kItems / nYZ));
+  width = min(width, widthCap);
+  __syncthreads();
+
+  int firstSweep = 0, converged = -1;
+  while (converged < 0) {
+    if (S.maxSweeps > 0) width = min(width, S.maxSweeps - firstSweep);
+    int planeOff[IPT], rowBase[IPT], rowY[IPT], rowZ[IPT], slot[IPT];
+    double err[IPT];
+    bool live[IPT];
+#pragma unroll
+    for (int q = 0; q < IPT; q++) {
+      const int it = lane0 + q * kSorPairs;
+      live[q] = it < width * nYZ;
+      const int j = it / nYZ, yz = it % nYZ;
+      rowY[q] = yz % ey;
+      rowZ[q] = yz / ey;
+      planeOff[q] = 2 * j + rowY[q] + rowZ[q];
+      rowBase[q] = strideY * rowY[q] + strideZ * rowZ[q];
+      slot[q] = (firstSweep + j) % kSorRing;
+      err[q] = 0.0;
+    }
+    const int nStages = nPlanes + 2 * (width - 1);
+    for (int t = -1; t < nStages && converged < 0; t++) {
+      if (preparer) {
+        // cell x of stage t + 1: its old value is final now
+        double *out = hand + (size_t)((t + 1) & 1) * 3 * kItems;
+        uint32_t *outKind = handKind + (size_t)((t + 1) & 1) * kItems;
+#pragma unroll
+        for (int q = 0; q < IPT; q++) {
+          const int x = t + 1 - planeOff[q];
+          if (!live[q] || x < 0 || x >= ex) continue;
+          const int it = lane0 + q * kSorPairs;
+          const int cell = rowBase[q] + x;
+          const unsigned kind = __ldg(G.cellKind + cell);
+          outKind[it] = kind;
+          if (kind & 1u) continue;
+          const double cur = pot[cell];
+          double p, n;
+          if (nonEq) {
+            p = exp(-cur);
+            n = __ldg(S.conc + cell);
+          } else {
+            n = exp(cur);
+            p = __ddiv_rn(1.0, n);
+          }
+          const double dop = __ldg(G.dopingNorm + cell);
+          const double a = __dmul_rn(hProd, __dadd_rn(__dadd_rn(__dsub_rn(p, n), dop), __dmul_rn(cur, __dadd_rn(p, n))));
+          double den = __dadd_rn(twoHFSum, __dmul_rn(hProd, __dadd_rn(n, p)));
+          if (kind & 2u) { // gate faces add to the denominator in face order
+            const int c[3] = {x, rowY[q], rowZ[q]};
+            const int last[3] = {ex - 1, ey - 1, ez - 1};
+#pragma unroll
+            for (int i = 0; i < DIM; i++)
+#pragma unroll
+              for (int side = 0; side < 2; side++) {
+                if (!(side == 0 ? c[i] == 0 : c[i] == last[i])) continue;
+                const int ct = G.faceContact[cell * 2 * DIM + 2 * i + side];
+                if (ct >= 0 && G.contactType[ct] == 2) den = __dadd_rn(den, sorGateTerm(G, ct, nonEq, hF[i], h[i]).denTerm);
+              }
+          }
+          out[it] = cur;
+          out[kItems + it] = a;
+          out[2 * kItems + it] = den;
+        }
+      } else if (t >= 0) {
+        const double *in = hand + (size_t)(t & 1) * 3 * kItems;
+        const uint32_t *inKind = handKind + (size_t)(t & 1) * kItems;
+#pragma unroll
+        for (int q = 0; q < IPT; q++) {
+          const int x = t - planeOff[q];
+          if (!live[q] || x < 0 || x >= ex) continue;
+          const int it = lane0 + q * kSorPairs;
+          const int cell = rowBase[q] + x;
+          const unsigned kind = inKind[it];
+          if (!(kind & 1u)) {
+            const double cur = in[it], den = in[2 * kItems + it];
+            double num = in[kItems + it];
+            const int c[3] = {x, rowY[q], rowZ[q]};
+            const int last[3] = {ex - 1, ey - 1, ez - 1};
+            const int stride[3] = {1, strideY, strideZ};
+#pragma unroll
+            for (int i = 0; i < DIM; i++) {
+#pragma unroll
+              for (int side = 0; side < 2; side++) {
+                const bool atFace = side == 0 ? c[i] == 0 : c[i] == last[i];
+                if (!atFace) {
+                  num = __dadd_rn(num, __dmul_rn(pot[cell + (side == 0 ? -stride[i] : stride[i])], hF[i]));
+                } else {
+                  num = __dadd_rn(num, __dmul_rn(pot[cell + (side == 0 ? stride[i] : -stride[i])], hF[i]));
+                  if (kind & 2u) {
+                    const int ct = G.faceContact[cell * 2 * DIM + 2 * i + side];
+                    if (ct >= 0 && G.contactType[ct] == 2) num = __dadd_rn(num, sorGateTerm(G, ct, nonEq, hF[i], h[i]).numTerm);
+                  }
+                }
+              }
+            }
+            const double delta = __dmul_rn(S.omega, __dsub_rn(__ddiv_rn(num, den), cur));
+            const double next = __dadd_rn(cur, delta);
+            err[q] = fmax(err[q], fabs(delta));
+            pot[cell] = next;
+            S.history[(size_t)slot[q] * G.cells + cell] = next;
+          }
+          if (x == ex - 1) atomicMax(&sErr[slot[q]], (unsigned long long)__double_as_longlong(err[q]));
+        }
+      }
+      __syncthreads();
+      const int jFin = t - (nPlanes - 1);
+      if (jFin >= 0 && (jFin & 1) == 0 && (jFin >> 1) < width) {
+        const int sweep = firstSweep + (jFin >> 1);
+        const double e = __longlong_as_double((long long)sErr[sweep % kSorRing]);
+        if (!(e > S.accuracy) || (S.maxSweeps > 0 && sweep + 1 >= S.maxSweeps)) converged = sweep;
+      }
+    }
+    if (converged < 0) {
+      __syncthreads();
+      if (tid < kSorRing) sErr[tid] = 0ull;
+      __syncthreads();
+      firstSweep += width;
+      width = min(2 * width, widthCap);
+    }
+  }
+  for (int i = tid; i < G.cells; i += blockDim.x) {
+    const bool fixed = G.cellKind[i] & 1u;
+    if (!fixed)
+      S.pot[i] = S.history[(size_t)(converged % kSorRing) * G.cells + i];
+    else if (S.potInSmem)
+      S.pot[i] = sPot[i];
+  }
+  if (tid == 0) {
+    *S.sweepsOut = converged + 1;
+    if (S.ctl && S.sweepsPerStep) S.sweepsPerStep[S.ctl->slot] = converged + 1;
+  }
+  if (S.efield) {
+    __syncthreads();
+    for (int i = tid; i < G.cells; i += blockDim.x) cellEField(G, i, S.pot, S.efield);
+  }
+}
+
+// Red-black ordering of the same relaxation (BASELINE.json north_star: "device-resident red-black SOR"): the cells
+// with even x+y+z are updated from the old values of their (odd) neighbours, then the odd ones from the new even
+// values.  Same equation, same relaxation factor, same stopping rule (max |delta| of a full sweep <= accuracy),
+// but a different -- order-independent, fully parallel -- sequence of iterates than the reference's lexicographic
+// sweep: the converged potential agrees with it to about the accuracy of the solver (tests), not bit for bit.
+// Opt-in (emcgpu_set_option "sor_order" = 1); two barriers per sweep instead of a chain of nPlanes stages.
+template <int DIM>
+__global__ void __launch_bounds__(kSorThreads) sorRedBlackKernel(const __grid_constant__ DevGeometry G, const SorParams S) {
+  extern __shared__ double sPot[];
+  __shared__ double sWarpErr[kSorThreads / 32];
+  __shared__ double sMax;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (S.ctl && S.ctl->runSteps % S.ctl->poissonInterval != 0) {
+    if (tid == 0 && S.sweepsPerStep) S.sweepsPerStep[S.ctl->slot] = 0;
+    return;
+  }
+  double *pot = S.potInSmem ? sPot : S.pot;
+  if (S.potInSmem)
+    for (int i = tid; i < G.cells; i += blockDim.x) sPot[i] = S.pot[i];
+  double h[3] = {1, 1, 1}, hF[3] = {0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < DIM; i++) h[i] = __ddiv_rn(G.spacing[i], G.debyeLength);
+  if (DIM == 2) {
+    hF[0] = __ddiv_rn(h[1], h[0]);
+    hF[1] = __ddiv_rn(h[0], h[1]);
+  } else {
+    hF[0] = __ddiv_rn(__dmul_rn(h[1], h[2]), h[0]);
+    hF[1] = __ddiv_rn(__dmul_rn(h[0], h[2]), h[1]);
+    hF[2] = __ddiv_rn(__dmul_rn(h[0], h[1]), h[2]);
+  }
+  double hFSum = 0.0, hProd = 1.0;
+#pragma unroll
+  for (int i = 0; i < DIM; i++) {
+    hFSum = __dadd_rn(hFSum, hF[i]);
+    hProd = __dmul_rn(hProd, h[i]);
+  }
+  const double twoHFSum = __dmul_rn(2.0, hFSum);
+  const int ex = G.extent[0], ey = G.extent[1], ez = DIM > 2 ? G.extent[2] : 1;
+  const int halfX = (ex + 1) / 2; // cells of one colour per row, at most
+  const int nHalf = halfX * ey * ez;
+  const bool nonEq = S.conc != nullptr;
+  __syncthreads();
+  int sweeps = 0;
+  for (;;) {
+    double myErr = 0.0;
+#pragma unroll 1
+    for (int colour = 0; colour < 2; colour++) {
+      for (int idx = tid; idx < nHalf; idx += blockDim.x) {
+        const int row = idx / halfX, y = row % ey, z = row / ey;
+        const int x = 2 * (idx - row * halfX) + ((y + z + colour) & 1);
+        if (x >= ex) continue;
+        const int cell = x + ex * row;
+        const unsigned kind = __ldg(G.cellKind + cell);
+        if (kind & 1u) continue;
+        const double cur = pot[cell];
+        double p, n;
+        if (nonEq) {
+          p = exp(-cur);
+          n = __ldg(S.conc + cell);
+        } else {
+          n = exp(cur);
+          p = __ddiv_rn(1.0, n);
+        }
+        const double dop = __ldg(G.dopingNorm + cell);
+        double num = __dmul_rn(hProd, __dadd_rn(__dadd_rn(__dsub_rn(p, n), dop), __dmul_rn(cur, __dadd_rn(p, n))));
+        double den = __dadd_rn(twoHFSum, __dmul_rn(hProd, __dadd_rn(n, p)));
+        const int c[3] = {x, y, z};
+        const int last[3] = {ex - 1, ey - 1, ez - 1};
+        const int stride[3] = {1, ex, ex * ey};
+#pragma unroll
+        for (int i = 0; i < DIM; i++) {
+#pragma unroll
+          for (int side = 0; side < 2; side++) {
+            const bool atFace = side == 0 ? c[i] == 0 : c[i] == last[i];
+            if (!atFace) {
+              num = __dadd_rn(num, __dmul_rn(pot[cell + (side == 0 ? -stride[i] : stride[i])], hF[i]));
+            } else {
+              num = __dadd_rn(num, __dmul_rn(pot[cell + (side == 0 ? stride[i] : -stride[i])], hF[i]));
+              if (kind & 2u) {
+                const int ct = G.faceContact[cell * 2 * DIM + 2 * i + side];
+                if (ct >= 0 && G.contactType[ct] == 2) {
+                  const SorGate g = sorGateTerm(G, ct, nonEq, hF[i], h[i]);
+                  num = __dadd_rn(num, g.numTerm);
+                  den = __dadd_rn(den, g.denTerm);
+                }
+              }
+            }
+          }
+        }
+        const double delta = __dmul_rn(S.omega, __dsub_rn(__ddiv_rn(num, den), cur));
         pot[cell] = __dadd_rn(cur, delta);
         myErr = fmax(myErr, fabs(delta));
       }
       __syncthreads();
     }
-    // max |delta| of the sweep
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) myErr = fmax(myErr, __shfl_xor_sync(0xffffffffu, myErr, o));
-    if (lane == 0) sErr[warp] = myErr;
+    if (lane == 0) sWarpErr[warp] = myErr;
     __syncthreads();
-    if (tid == 0) {
-      double m = 0.0;
-      for (int w = 0; w < (int)blockDim.x / 32; w++) m = fmax(m, sErr[w]);
-      sMax = m;
+    if (warp == 0) {
+      double m = lane < (int)(blockDim.x >> 5) ? sWarpErr[lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0) sMax = m;
     }
     __syncthreads();
     sweeps++;
@@ -268,7 +746,14 @@ __global__ void __launch_bounds__(kSorThreads) sorKernel(const __grid_constant__
   }
   if (S.potInSmem)
     for (int i = tid; i < G.cells; i += blockDim.x) S.pot[i] = sPot[i];
-  if (tid == 0 && S.sweepsOut) *S.sweepsOut = sweeps;
+  if (tid == 0) {
+    *S.sweepsOut = sweeps;
+    if (S.ctl && S.sweepsPerStep) S.sweepsPerStep[S.ctl->slot] = sweeps;
+  }
+  if (S.efield) {
+    __syncthreads();
+    for (int i = tid; i < G.cells; i += blockDim.x) cellEField(G, i, S.pot, S.efield);
+  }
 }
 
 // Dirichlet values at ohmic contacts (emcSORSolver.hpp:57-73, :139-155); faces in the reference's order
@@ -286,12 +771,16 @@ __global__ void sorResetBcKernel(const __grid_constant__ DevGeometry G, double *
 
 // ---------------------------------------------------------------------------
 // K2: one time step of every particle of a device run.
+// Per particle it leaves a flag for the contact handling and the compaction that follow:
+//   kGone (-2)  left through an ohmic contact (removed),  kFree (-1) alive,  >= 0 alive in that reservoir cell.
+constexpr int32_t kGone = -2, kFree = -1;
+
 struct DeviceStepParams {
-  BulkParams P;      // ensemble, model, tables, rng (box / force / dir unused)
+  BulkParams P;      // ensemble, model, tables, rng (box / force / dir / n / step0 unused)
   const double *e;   // [dim][cells]
   double charge;
-  int8_t *removed;   // [n] out
-  int32_t *removedPerContact; // [nContacts], zeroed by the caller
+  int32_t *flag;     // [capacity] out
+  RunCtl *ctl;       // n, step index, removedPerContact
 };
 
 template <bool EXACT, int DIM>
@@ -350,15 +839,17 @@ __global__ void __launch_bounds__(kBulkThreads, 2)
   const CtaState C = stageCta(P, smemRaw, &tableBar, 0, 0);
   const DevModel &model = *C.model;
   using A = Arith<EXACT>;
+  const int64_t n = D.ctl->n;
+  const long long step = D.ctl->step;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     Particle p;
     Rng rng;
     loadParticle(P, i, p, rng);
     p.energy = P.stream[EMCGPU_ENERGY][i]; // Coulomb and the table look-up read it before the next drift
     if (DIM < 3) p.pos.z = 0.0;
     attachReplay<RNG_MODE>(P, i, rng);
-    rng.step = (uint32_t)P.step0;
+    rng.step = (uint32_t)step;
     const double dt = P.dt;
     Vec3 force = ngpForce<DIM>(G, D.e, p, D.charge);
     bool removed;
@@ -386,7 +877,7 @@ __global__ void __launch_bounds__(kBulkThreads, 2)
             const unsigned long long ev = atomicAdd(P.evCount, 1ull);
             if ((long long)ev < P.evCap) {
               long long *dst = P.events + 4 * ev;
-              dst[0] = P.step0;
+              dst[0] = step;
               dst[1] = P.idBase + i;
               dst[2] = m;
               dst[3] = mechId;
@@ -406,65 +897,90 @@ __global__ void __launch_bounds__(kBulkThreads, 2)
     }
     p.tau = A::sub(p.tau, dt);
     storeParticle<RNG_MODE>(P, i, p, rng);
-    D.removed[i] = removed ? 1 : 0;
-    if (removed) atomicAdd(&D.removedPerContact[cellContact(G, posToCell(G, p.pos.x, p.pos.y, p.pos.z))], 1);
+    const int cell = posToCell(G, p.pos.x, p.pos.y, p.pos.z);
+    if (removed) {
+      D.flag[i] = kGone;
+      atomicAdd(&D.ctl->removedPerContact[cellContact(G, cell)], 1);
+    } else {
+      D.flag[i] = (G.cellKind[cell] & 1u) ? cell : kFree;
+    }
+  }
+}
+
+// flags of a resting ensemble (emcgpu_device_contacts on its own): kFree or the reservoir cell
+__global__ void __launch_bounds__(256)
+    reservoirFlagKernel(const __grid_constant__ DevGeometry G, const double *x, const double *y, const double *z,
+                        const RunCtl *ctl, int32_t *flag) {
+  const int64_t n = ctl->n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cell = posToCell(G, x[i], y[i], G.dim > 2 ? z[i] : 0.0);
+    flag[i] = (G.cellKind[cell] & 1u) ? cell : kFree;
   }
 }
 
 // ---------------------------------------------------------------------------
-// Order-preserving compaction (removeParticles, emcBasicParticleHandler.hpp:267-277): keep[i] != 0
-// survives.  Three small kernels: per-block counts, exclusive scan of the counts (one CTA), scatter.
-constexpr int kCompactThreads = 256;
+// Ordered selection over the ensemble: particles are handled in chunks of kChunk consecutive indices; a
+// "count" kernel leaves the number of selected particles per chunk and its last block turns them into
+// offsets, a second kernel then writes the selected particles in index order.  Used twice per step:
+//   SELECT_RESERVOIR  flag >= 0     -> the list of (particle, cell) the contact handling ranks
+//   SELECT_KEPT       flag != kGone -> order-preserving compaction (removeParticles, emcBasicParticleHandler.hpp:267-277)
+constexpr int kChunk = 256;
+enum { SELECT_RESERVOIR = 0, SELECT_KEPT = 1 };
 
-__global__ void __launch_bounds__(kCompactThreads) compactCountKernel(const int8_t *drop, int64_t n, int32_t *blockCount) {
-  __shared__ int sWarp[kCompactThreads / 32];
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool keep = i < n && !drop[i];
-  const unsigned b = __ballot_sync(0xffffffffu, keep);
-  if ((threadIdx.x & 31) == 0) sWarp[threadIdx.x >> 5] = __popc(b);
-  __syncthreads();
+template <int WHAT> __device__ __forceinline__ bool selected(int32_t flag) {
+  return WHAT == SELECT_RESERVOIR ? flag >= 0 : flag != kGone;
+}
+
+template <int WHAT>
+__global__ void __launch_bounds__(kChunk) selectCountKernel(const int32_t *flag, RunCtl *ctl, int32_t *chunkCount) {
+  __shared__ int sWarp[kChunk / 32];
+  const int64_t n = ctl->n;
+  const int nChunks = (int)((n + kChunk - 1) / kChunk);
+  for (int chunk = blockIdx.x; chunk < nChunks; chunk += gridDim.x) {
+    const int64_t i = (int64_t)chunk * kChunk + threadIdx.x;
+    const bool sel = i < n && selected<WHAT>(flag[i]);
+    const unsigned b = __ballot_sync(0xffffffffu, sel);
+    if ((threadIdx.x & 31) == 0) sWarp[threadIdx.x >> 5] = __popc(b);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int sum = 0;
+      for (int w = 0; w < kChunk / 32; w++) sum += sWarp[w];
+      chunkCount[chunk] = sum;
+    }
+    __syncthreads();
+  }
+  if (!lastBlockDone(&ctl->ticket[WHAT])) return;
+  const int total = blockExclusiveScan(chunkCount, nChunks);
   if (threadIdx.x == 0) {
-    int s = 0;
-    for (int w = 0; w < kCompactThreads / 32; w++) s += sWarp[w];
-    blockCount[blockIdx.x] = s;
+    if (WHAT == SELECT_RESERVOIR)
+      ctl->nReservoir = total;
+    else
+      ctl->nKept = total;
   }
 }
 
-// exclusive scan of up to a few thousand block counts by one CTA; total -> out[nBlocks]
-__global__ void __launch_bounds__(1024) compactScanKernel(int32_t *blockCount, int nBlocks) {
-  __shared__ int sCarry;
-  __shared__ int sWarp[32];
-  if (threadIdx.x == 0) sCarry = 0;
-  __syncthreads();
-  for (int base = 0; base < nBlocks; base += blockDim.x) {
-    const int i = base + threadIdx.x;
-    const int v = i < nBlocks ? blockCount[i] : 0;
-    int incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if ((threadIdx.x & 31) >= o) incl += t;
+__global__ void __launch_bounds__(kChunk)
+    reservoirListKernel(const int32_t *flag, const RunCtl *ctl, const int32_t *chunkOffset, int32_t *listParticle,
+                        int32_t *listCell) {
+  __shared__ int sWarp[kChunk / 32];
+  const int64_t n = ctl->n;
+  const int nChunks = (int)((n + kChunk - 1) / kChunk);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int chunk = blockIdx.x; chunk < nChunks; chunk += gridDim.x) {
+    const int64_t i = (int64_t)chunk * kChunk + threadIdx.x;
+    const int32_t f = i < n ? flag[i] : kFree;
+    const unsigned b = __ballot_sync(0xffffffffu, f >= 0);
+    if (lane == 0) sWarp[warp] = __popc(b);
+    __syncthreads();
+    if (f >= 0) {
+      int off = chunkOffset[chunk];
+      for (int w = 0; w < warp; w++) off += sWarp[w];
+      off += __popc(b & ((1u << lane) - 1u));
+      listParticle[off] = (int32_t)i;
+      listCell[off] = f;
     }
-    if ((threadIdx.x & 31) == 31) sWarp[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      int w = sWarp[threadIdx.x];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, w, o);
-        if (threadIdx.x >= o) w += t;
-      }
-      sWarp[threadIdx.x] = w;
-    }
-    __syncthreads();
-    const int warpOff = (threadIdx.x >> 5) ? sWarp[(threadIdx.x >> 5) - 1] : 0;
-    const int carry = sCarry;
-    if (i < nBlocks) blockCount[i] = carry + warpOff + incl - v;
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) sCarry = carry + warpOff + incl;
     __syncthreads();
   }
-  if (threadIdx.x == 0) blockCount[nBlocks] = sCarry;
 }
 
 struct EnsemblePtrs {
@@ -473,109 +989,96 @@ struct EnsemblePtrs {
   uint32_t *cursor; // replay cursors travel with their particle (may be null)
 };
 
-__global__ void __launch_bounds__(kCompactThreads)
-    compactScatterKernel(const int8_t *drop, int64_t n, const int32_t *blockOffset, EnsemblePtrs src, EnsemblePtrs dst) {
-  __shared__ int sWarp[kCompactThreads / 32];
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool keep = i < n && !drop[i];
-  const unsigned b = __ballot_sync(0xffffffffu, keep);
+__global__ void __launch_bounds__(kChunk)
+    compactScatterKernel(const int32_t *flag, const RunCtl *ctl, const int32_t *chunkOffset, EnsemblePtrs src, EnsemblePtrs dst) {
+  __shared__ int sWarp[kChunk / 32];
+  const int64_t n = ctl->n;
+  const int nChunks = (int)((n + kChunk - 1) / kChunk);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) sWarp[warp] = __popc(b);
-  __syncthreads();
-  int off = blockOffset[blockIdx.x];
-  for (int w = 0; w < warp; w++) off += sWarp[w];
-  if (keep) {
-    const int64_t j = off + __popc(b & ((1u << lane) - 1u));
+  for (int chunk = blockIdx.x; chunk < nChunks; chunk += gridDim.x) {
+    const int64_t i = (int64_t)chunk * kChunk + threadIdx.x;
+    const bool keep = i < n && flag[i] != kGone;
+    const unsigned b = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) sWarp[warp] = __popc(b);
+    __syncthreads();
+    if (keep) {
+      int off = chunkOffset[chunk];
+      for (int w = 0; w < warp; w++) off += sWarp[w];
+      const int64_t j = off + __popc(b & ((1u << lane) - 1u));
 #pragma unroll
-    for (int c = 0; c < EMCGPU_N_STREAMS; c++) dst.stream[c][j] = src.stream[c][i];
-    dst.packed[j] = src.packed[i];
-    if (src.cursor) dst.cursor[j] = src.cursor[i];
+      for (int c = 0; c < EMCGPU_N_STREAMS; c++) dst.stream[c][j] = src.stream[c][i];
+      dst.packed[j] = src.packed[i];
+      if (src.cursor) dst.cursor[j] = src.cursor[i];
+    }
+    __syncthreads();
   }
 }
 
 // ---------------------------------------------------------------------------
-// K6: ohmic contacts.  (1) mark the excess particles of every reservoir cell -- the reference scans the
-// ensemble in index order and keeps a particle while the cell is below its expected population, so the
-// FIRST particles of a cell (by index) survive; (2) inject the missing ones, cell by cell in storage order.
-// Step (1) is done by one warp walking the ensemble in index order (the reservoir population is a few
-// hundred particles; ranks within a cell come from __match_any_sync); step (2) is embarrassingly parallel.
+// K6: ohmic contacts (emcBasicParticleHandler::handleOhmicContacts :158-192).  The reference scans the ensemble in
+// index order and keeps a particle of a reservoir cell while the cell is below its expected population, so the FIRST
+// particles of a cell (by index) survive: a particle is deleted iff its rank among the particles of its cell is
+// >= slots = ceil(expected / carriers per particle).  The ranks are counted over the (short) ordered reservoir list
+// by all blocks; the block that finishes last derives, cell by cell in storage order, how many particles each
+// reservoir cell is missing (while (diff > 0) { inject; diff -= carriers }) and the per-contact bookkeeping.
 struct ContactParams {
-  const double *x, *y, *z;
-  int64_t n;
   double nrCarriers;
-  const double *expected; // [cells]
-  double *have;           // [cells] out: population kept per reservoir cell
-  int8_t *drop;           // [n] out
-  int32_t *net;           // [nContacts] out: injected - deleted
-  int32_t *injectCount;   // [cells + 1] out: particles to inject per cell, exclusive scan, total at [cells]
+  const double *expected;  // [cells]
+  const int32_t *listParticle, *listCell;
+  int32_t *flag;           // [capacity]: excess particles become kGone
+  int32_t *cellCount;      // [cells] scratch, all zero between launches
+  int32_t *injectCount;    // [cells + 1] out: particles to inject per cell as an exclusive scan, total at [cells]
+  RunCtl *ctl;
 };
 
-__global__ void __launch_bounds__(32) contactMarkKernel(const __grid_constant__ DevGeometry G, const ContactParams K) {
-  const int lane = threadIdx.x;
-  for (int c = lane; c < G.cells; c += 32) K.have[c] = 0.0;
-  for (int c = lane; c < G.nContacts; c += 32) K.net[c] = 0;
-  __syncwarp();
-  for (int64_t base = 0; base < K.n; base += 32) {
-    const int64_t i = base + lane;
-    int cell = -1;
-    if (i < K.n) {
-      const int c = posToCell(G, K.x[i], K.y[i], G.dim > 2 ? K.z[i] : 0.0);
-      if (cellIsReservoir(G, c)) cell = c;
+__device__ __forceinline__ int reservoirSlots(double expected, double nrCarriers) {
+  return expected > 0.0 ? (int)ceil(expected / nrCarriers) : 0;
+}
+
+__global__ void __launch_bounds__(256) contactRankKernel(const __grid_constant__ DevGeometry G, const ContactParams K) {
+  const int m = K.ctl->nReservoir;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+    const int cell = K.listCell[j];
+    int rank = 0;
+    for (int i = 0; i < j; i++) rank += K.listCell[i] == cell;
+    atomicAdd(&K.cellCount[cell], 1);
+    if (rank >= reservoirSlots(K.expected[cell], K.nrCarriers)) {
+      K.flag[K.listParticle[j]] = kGone;
+      atomicAdd(&K.ctl->net[cellContact(G, cell)], -1);
     }
-    const unsigned peers = __match_any_sync(0xffffffffu, cell);
-    bool dropIt = false;
-    if (cell >= 0) {
-      // population of the cell seen by this particle = what earlier chunks left + earlier lanes of this chunk that were kept.
-      // Within a cell every kept particle adds nrCarriers and, once the cell is full, all later ones are dropped, so the
-      // number kept before lane l is min(rank, slots) with slots = ceil((expected - have) / nrCarriers) clipped at 0.
-      const int rank = __popc(peers & ((1u << lane) - 1u));
-      const double have = K.have[cell];
-      const double room = K.expected[cell] - have;
-      const int slots = room > 0.0 ? (int)ceil(room / K.nrCarriers) : 0;
-      dropIt = rank >= slots;
-      const int group = __popc(peers);
-      if (rank == 0) { // the first lane of the group updates the cell and the contact counter
-        const int kept = min(group, slots);
-        K.have[cell] = have + kept * K.nrCarriers;
-        if (group > kept) atomicAdd(&K.net[cellContact(G, cell)], -(group - kept));
-      }
-    }
-    if (i < K.n) K.drop[i] = dropIt ? 1 : 0;
-    __syncwarp();
   }
-  // particles to inject per reservoir cell: while (diff > 0) { inject; diff -= nrCarriers }
-  int carry = 0;
-  for (int base = 0; base < G.cells; base += 32) {
-    const int c = base + lane;
+  if (!lastBlockDone(&K.ctl->ticket[2])) return;
+  for (int c = threadIdx.x; c < G.cells; c += blockDim.x) {
     int cnt = 0;
-    if (c < G.cells && cellIsReservoir(G, c)) {
-      const double diff = K.expected[c] - K.have[c];
+    if (G.cellKind[c] & 1u) {
+      const int group = __ldcg(K.cellCount + c);
+      const int kept = min(group, reservoirSlots(K.expected[c], K.nrCarriers));
+      const double diff = K.expected[c] - kept * K.nrCarriers;
       cnt = diff > 0.0 ? (int)ceil(diff / K.nrCarriers) : 0;
-      if (cnt) atomicAdd(&K.net[cellContact(G, c)], cnt);
+      if (cnt) atomicAdd(&K.ctl->net[cellContact(G, c)], cnt);
+      K.cellCount[c] = 0;
     }
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (c < G.cells) K.injectCount[c] = carry + incl - cnt;
-    carry += __shfl_sync(0xffffffffu, incl, 31);
+    K.injectCount[c] = cnt;
   }
-  if (lane == 0) K.injectCount[G.cells] = carry;
+  __syncthreads();
+  const int total = blockExclusiveScan(K.injectCount, G.cells);
+  if (threadIdx.x == 0) {
+    K.injectCount[G.cells] = total;
+    K.ctl->toInject = total;
+  }
 }
 
 // emcBasicParticleHandler::addParticle(isInitial = false): initParticlePos (emcParticleInitialization.hpp:14-29) +
 // emcElectron::generateInjectedParticle (emcElectron.hpp:92-104).  Draw order: position (dim draws), valley,
 // sub-valley, energy, cos(theta), phi, tau, grainTau = dim + 7 draws per particle; injected particle j of this
 // step uses Philox(seed, counter = (j, 0xC0117AC7, step, .)) or, in replay mode, draws[j * (dim + 7) ...].
+// The particles are appended behind the ctl->nKept survivors of the compaction.
 struct InjectParams {
   EnsemblePtrs ens;
-  int64_t first;              // index of the first injected particle in the (already compacted) ensemble
   const int32_t *injectCount; // exclusive scan per cell, total at [cells]
   const DevModel *model;
   uint64_t seed;
-  int64_t step;
+  RunCtl *ctl;
   const uint64_t *replay; // flat draw stream of the contact phase or nullptr
   int64_t replayCount;
   int *status;
@@ -585,15 +1088,22 @@ template <int DIM>
 __global__ void __launch_bounds__(128) contactInjectKernel(const __grid_constant__ DevGeometry G, const InjectParams J) {
   const DevModel &model = *J.model;
   const int total = J.injectCount[G.cells];
+  const int64_t first = J.ctl->nKept;
+  const long long step = J.ctl->step;
+  if (first + total > J.ctl->capacity) { // the host reserves head room between chunks; running out of it is an error
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      atomicExch(J.status, (int)EMCGPU_E_CAPACITY);
+      J.ctl->toInject = 0; // keeps the later kernels of the chunk inside the allocation
+    }
+    return;
+  }
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x) {
-    // cell of injected particle j: last cell with injectCount[cell] <= j (binary search over the scan)
+    // cell of injected particle j: the last cell whose offset is <= j (empty cells share the offset of their successor)
     int lo = 0, hi = G.cells - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
       if (J.injectCount[mid] <= j) lo = mid; else hi = mid - 1;
     }
-    // skip empty cells that share the same offset: move to the last cell whose range contains j
-    while (lo + 1 < G.cells && J.injectCount[lo + 1] <= j) lo++;
     const int cell = lo;
     int c[3];
     cellCoord(G, cell, c);
@@ -612,7 +1122,7 @@ __global__ void __launch_bounds__(128) contactInjectKernel(const __grid_constant
     } else {
       for (int d = 0; d < kDraws; d += 2) {
         uint32_t o[4];
-        philox4x32_10((uint32_t)j, 0xC0117AC7u, (uint32_t)J.step, (uint32_t)(d >> 1), (uint32_t)J.seed,
+        philox4x32_10((uint32_t)j, 0xC0117AC7u, (uint32_t)step, (uint32_t)(d >> 1), (uint32_t)J.seed,
                       (uint32_t)(J.seed >> 32), o);
         raw[d] = (uint64_t)o[1] << 32 | o[0];
         if (d + 1 < kDraws) raw[d + 1] = (uint64_t)o[3] << 32 | o[2];
@@ -643,7 +1153,7 @@ __global__ void __launch_bounds__(128) contactInjectKernel(const __grid_constant
     const int set = (region >= 0 && region < kMaxRegions) ? model.setOf[valley][region] : -1;
     const double tau0 = set >= 0 ? model.sets[set].tau : model.defaultTau;
     const double tau = __dmul_rn(-log(uniformLog(raw[d++])), tau0);
-    const int64_t at = J.first + j;
+    const int64_t at = first + j;
     J.ens.stream[EMCGPU_KX][at] = kk[0];
     J.ens.stream[EMCGPU_KY][at] = kk[1];
     J.ens.stream[EMCGPU_KZ][at] = kk[2];

@@ -282,6 +282,21 @@ int emcgpu_set_option(emcgpu_ctx *ctx, const char *name, int64_t value) {
     ctx->optTablesGlobal = value != 0;
     return EMCGPU_OK;
   }
+  if (!strcmp(name, "sor_kernel")) {
+    if (value != 0 && value != 1) return fail(ctx, EMCGPU_E_INVALID, "sor_kernel must be 0 (rows) or 1 (hyperplanes)");
+    ctx->optSorKernel = (int)value;
+    return EMCGPU_OK;
+  }
+  if (!strcmp(name, "sor_order")) {
+    if (value != 0 && value != 1) return fail(ctx, EMCGPU_E_INVALID, "sor_order must be 0 (lexicographic) or 1 (red-black)");
+    ctx->optSorOrder = (int)value;
+    return EMCGPU_OK;
+  }
+  if (!strcmp(name, "poisson_interval")) {
+    if (value < 1) return fail(ctx, EMCGPU_E_INVALID, "poisson_interval must be at least 1");
+    ctx->optPoissonInterval = (int)value;
+    return EMCGPU_OK;
+  }
   if (!strcmp(name, "stages")) {
     ctx->optStages = (int)value;
     return EMCGPU_OK;

@@ -10,23 +10,28 @@ using namespace emc;
 
 namespace emc {
 
+constexpr int kRunChunk = 128; // steps of the device-run loop between two host synchronisations
+
 struct DeviceRunState {
   DevGeometry geo{};
   int dim = 2;
   double charge = 0, nrCarriers = 1;
-  DeviceBuffer dRegion, dFace, dDoping;
+  DeviceBuffer dRegion, dFace, dDoping, dDopingNorm, dCellKind, dSorHistory;
   DeviceBuffer grid[EMCGPU_N_GRIDS];
-  DeviceBuffer dRemoved, dRemovedPerContact, dBlockCount, dHave, dNet, dInjectCount, dSweeps, dReplay;
+  DeviceBuffer dCtl, dFlag, dChunkCount, dListParticle, dListCell, dCellCount, dInjectCount, dSweeps, dReplay;
+  DeviceBuffer dCounters, dSweepsPerStep; // per-step outputs of a chunk of the step loop
   DeviceBuffer altEnsemble, altCursor; // second ensemble buffer for the order-preserving compaction
   int64_t reserve = 0;
+  int64_t maxInject = -1; // upper bound of the particles the contacts inject in one step
+  int64_t runSteps = 0; // steps done by emcgpu_device_run* since configure (frozen-field sub-cycling)
 };
 
 void releaseDeviceRun(emcgpu_ctx *ctx) {
   if (!ctx->run) return;
   DeviceRunState *r = ctx->run;
-  for (DeviceBuffer *b : {&r->dRegion, &r->dFace, &r->dDoping, &r->dRemoved, &r->dRemovedPerContact, &r->dBlockCount,
-                          &r->dHave, &r->dNet, &r->dInjectCount, &r->dSweeps, &r->dReplay, &r->altEnsemble,
-                          &r->altCursor})
+  for (DeviceBuffer *b : {&r->dRegion, &r->dFace, &r->dDoping, &r->dDopingNorm, &r->dCellKind, &r->dSorHistory, &r->dCtl, &r->dFlag, &r->dChunkCount, &r->dListParticle,
+                          &r->dListCell, &r->dCellCount, &r->dInjectCount, &r->dSweeps, &r->dReplay, &r->dCounters,
+                          &r->dSweepsPerStep, &r->altEnsemble, &r->altCursor})
     b->release();
   for (auto &g : r->grid) g.release();
   delete r;
@@ -91,35 +96,6 @@ int growEnsemble(emcgpu_ctx *ctx, int64_t cap) {
   return EMCGPU_OK;
 }
 
-// drop the particles flagged in `drop`, keeping the order of the others; returns the new count through ctx->n
-int compactEnsemble(emcgpu_ctx *ctx, const int8_t *drop) {
-  DeviceRunState *r = ctx->run;
-  const int64_t n = ctx->n;
-  if (n == 0) return EMCGPU_OK;
-  if (int rc = growEnsemble(ctx, ctx->capacity)) return rc;
-  const int nBlocks = (int)((n + kCompactThreads - 1) / kCompactThreads);
-  CUDA_TRY(ctx, r->dBlockCount.ensure((size_t)(nBlocks + 1) * sizeof(int32_t)));
-  int32_t *blockCount = r->dBlockCount.as<int32_t>();
-  compactCountKernel<<<nBlocks, kCompactThreads, 0, ctx->stream>>>(drop, n, blockCount);
-  compactScanKernel<<<1, 1024, 0, ctx->stream>>>(blockCount, nBlocks);
-  const bool replay = ctx->rngMode == RNG_REPLAY;
-  if (replay) CUDA_TRY(ctx, r->altCursor.ensure((size_t)ctx->capacity * sizeof(uint32_t)));
-  EnsemblePtrs src = ptrsOf(ctx->dEnsemble.ptr, ctx->capacity, replay ? ctx->dCursor.as<uint32_t>() : nullptr);
-  EnsemblePtrs dst = ptrsOf(r->altEnsemble.ptr, ctx->capacity, replay ? r->altCursor.as<uint32_t>() : nullptr);
-  compactScatterKernel<<<nBlocks, kCompactThreads, 0, ctx->stream>>>(drop, n, blockCount, src, dst);
-  ctx->launches += 3;
-  CUDA_TRY(ctx, cudaGetLastError());
-  int32_t kept = 0;
-  CUDA_TRY(ctx, cudaMemcpyAsync(&kept, blockCount + nBlocks, sizeof kept, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  std::swap(ctx->dEnsemble, r->altEnsemble);
-  if (replay) std::swap(ctx->dCursor, r->altCursor);
-  for (int s = 0; s < EMCGPU_N_STREAMS; s++) ctx->dStream[s] = dst.stream[s];
-  ctx->dPacked = dst.packed;
-  ctx->n = kept;
-  return EMCGPU_OK;
-}
-
 void fillParams(emcgpu_ctx *ctx, BulkParams &P) {
   memset(&P, 0, sizeof P);
   for (int s = 0; s < EMCGPU_N_STREAMS; s++) P.stream[s] = ctx->dStream[s];
@@ -140,18 +116,6 @@ void fillParams(emcgpu_ctx *ctx, BulkParams &P) {
   P.status = ctx->dStatus.as<int>();
 }
 
-template <bool EXACT, int MODE> cudaError_t launchStepDim(emcgpu_ctx *ctx, const DeviceStepParams &D, size_t smem, int grid) {
-  const DevGeometry &G = ctx->run->geo;
-  auto go = [&](auto kernel) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kernel<<<grid, kBulkThreads, smem, ctx->stream>>>(G, D);
-    ctx->launches++;
-    return cudaGetLastError();
-  };
-  return ctx->run->dim == 2 ? go(deviceStepKernel<EXACT, MODE, 2>) : go(deviceStepKernel<EXACT, MODE, 3>);
-}
-
 int readStatus(emcgpu_ctx *ctx) {
   int status = 0;
   CUDA_TRY(ctx, cudaMemcpyAsync(&status, ctx->dStatus.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -160,6 +124,9 @@ int readStatus(emcgpu_ctx *ctx) {
     cudaMemsetAsync(ctx->dStatus.ptr, 0, sizeof(int), ctx->stream);
     if (status == EMCGPU_E_REPLAY_EXHAUSTED)
       return fail(ctx, status, "replay stream exhausted: more draws were needed than were recorded");
+    if (status == EMCGPU_E_CAPACITY)
+      return fail(ctx, status, "the contacts injected more particles than the ensemble allocation holds: "
+                               "call emcgpu_device_reserve with a larger capacity");
     return fail(ctx, status, "device reported status %d", status);
   }
   return EMCGPU_OK;
@@ -167,8 +134,47 @@ int readStatus(emcgpu_ctx *ctx) {
 
 int gridBlocks(int cells) { return (cells + 255) / 256; }
 
-// ---- the pieces of one EMC step, asynchronous on the context's stream unless they return counters -------
-int doPoisson(emcgpu_ctx *ctx, bool equilibrium, double accuracyVolt, double omega, bool resetBC, int32_t *sweepsHost) {
+// ---- control block: uploaded at the start of every API call, read back at its end ------------------------
+int pushCtl(emcgpu_ctx *ctx, int avgFromSlot) {
+  DeviceRunState *r = ctx->run;
+  if (int rc = growEnsemble(ctx, std::max<int64_t>(ctx->capacity, 1))) return rc;
+  const size_t cap = (size_t)ctx->capacity;
+  CUDA_TRY(ctx, r->dFlag.ensure(cap * sizeof(int32_t)));
+  CUDA_TRY(ctx, r->dListParticle.ensure(cap * sizeof(int32_t)));
+  CUDA_TRY(ctx, r->dListCell.ensure(cap * sizeof(int32_t)));
+  CUDA_TRY(ctx, r->dChunkCount.ensure((cap / kChunk + 2) * sizeof(int32_t)));
+  RunCtl h;
+  memset(&h, 0, sizeof h);
+  h.n = (int32_t)ctx->n;
+  h.nKept = (int32_t)ctx->n;
+  h.capacity = (int32_t)ctx->capacity;
+  h.avgFromSlot = avgFromSlot;
+  h.poissonInterval = ctx->optPoissonInterval;
+  h.step = ctx->nextStep;
+  h.runSteps = r->runSteps;
+  CUDA_TRY(ctx, cudaMemcpyAsync(r->dCtl.ptr, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
+  return EMCGPU_OK;
+}
+
+// waits for the stream; ensemble size, step index and the per-contact counters of a single step come back
+int pullCtl(emcgpu_ctx *ctx, RunCtl *out = nullptr) {
+  DeviceRunState *r = ctx->run;
+  RunCtl h;
+  CUDA_TRY(ctx, cudaMemcpyAsync(&h, r->dCtl.ptr, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->n = h.n;
+  ctx->nextStep = h.step;
+  r->runSteps = h.runSteps;
+  if (out) *out = h;
+  return EMCGPU_OK;
+}
+
+int particleGrid(emcgpu_ctx *ctx, int threads, int perSm) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>((ctx->capacity + threads - 1) / threads, (int64_t)perSm * ctx->smCount));
+}
+
+// ---- the pieces of one EMC step: all asynchronous on the context's stream, sizes read from the control block ----
+int doPoisson(emcgpu_ctx *ctx, bool equilibrium, double accuracyVolt, double omega, bool resetBC, bool inLoop, bool withField) {
   DeviceRunState *r = ctx->run;
   const DevGeometry &G = r->geo;
   double *pot = r->grid[EMCGPU_GRID_POTENTIAL].as<double>();
@@ -183,17 +189,40 @@ int doPoisson(emcgpu_ctx *ctx, bool equilibrium, double accuracyVolt, double ome
   S.omega = omega;
   S.maxSweeps = 1000000;
   const size_t smem = (size_t)G.cells * sizeof(double);
-  S.potInSmem = smem <= (size_t)ctx->maxSmemOptin - 1024 ? 1 : 0;
+  S.potInSmem = smem <= (size_t)ctx->maxSmemOptin - 2048 ? 1 : 0;
   S.sweepsOut = r->dSweeps.as<int32_t>();
-  if (S.potInSmem)
-    CUDA_TRY(ctx, cudaFuncSetAttribute(sorKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sorKernel<<<1, kSorThreads, S.potInSmem ? smem : 0, ctx->stream>>>(G, S);
+  CUDA_TRY(ctx, r->dSorHistory.ensure((size_t)kSorRing * G.cells * sizeof(double)));
+  S.history = r->dSorHistory.as<double>();
+  S.efield = withField ? r->grid[EMCGPU_GRID_EFIELD_X].as<double>() : nullptr;
+  S.ctl = inLoop ? r->dCtl.as<RunCtl>() : nullptr;
+  S.sweepsPerStep = inLoop ? r->dSweepsPerStep.as<int32_t>() : nullptr;
+  // one thread pair per grid row when a wave of >= 12 sweeps fits the CTA that way (and the hand-over records fit
+  // next to the potential), hyperplane loop otherwise
+  const int nYZ = G.extent[1] * (G.dim > 2 ? G.extent[2] : 1);
+  auto launch = [&](auto kernel, size_t handover) {
+    size_t bytes = (S.potInSmem ? smem : 0) + handover;
+    if (bytes > (size_t)ctx->maxSmemOptin - 2048) { // potential stays in global memory / L1
+      S.potInSmem = 0;
+      bytes = handover;
+    }
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    kernel<<<1, kSorThreads, bytes, ctx->stream>>>(G, S);
+    return cudaGetLastError();
+  };
+  const int ipt = 16 * nYZ <= kSorPairs ? 1 : 16 * nYZ <= 2 * kSorPairs ? 2 : 4;
+  if (ctx->optSorOrder == 1)
+    CUDA_TRY(ctx, G.dim == 2 ? launch(sorRedBlackKernel<2>, 0) : launch(sorRedBlackKernel<3>, 0));
+  else if (ctx->optSorKernel == 1 || 12 * nYZ > 4 * kSorPairs)
+    CUDA_TRY(ctx, launch(sorPlanesKernel, 0));
+  else if (ipt == 1)
+    CUDA_TRY(ctx, G.dim == 2 ? launch(sorRowsKernel<1, 2>, sorRowsHandoverBytes<1>()) : launch(sorRowsKernel<1, 3>, sorRowsHandoverBytes<1>()));
+  else if (ipt == 2)
+    CUDA_TRY(ctx, G.dim == 2 ? launch(sorRowsKernel<2, 2>, sorRowsHandoverBytes<2>()) : launch(sorRowsKernel<2, 3>, sorRowsHandoverBytes<2>()));
+  else
+    CUDA_TRY(ctx, G.dim == 2 ? launch(sorRowsKernel<4, 2>, sorRowsHandoverBytes<4>()) : launch(sorRowsKernel<4, 3>, sorRowsHandoverBytes<4>()));
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
-  if (sweepsHost) {
-    CUDA_TRY(ctx, cudaMemcpyAsync(sweepsHost, r->dSweeps.ptr, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  }
   return EMCGPU_OK;
 }
 
@@ -206,24 +235,29 @@ int doEfield(emcgpu_ctx *ctx) {
   return EMCGPU_OK;
 }
 
-int doAssign(emcgpu_ctx *ctx) {
+// charge assignment; withConc: the last block also forms the concentration; closeStep: ... and ends the step
+int doAssign(emcgpu_ctx *ctx, bool withConc, bool closeStep) {
   DeviceRunState *r = ctx->run;
   const DevGeometry &G = r->geo;
   double *count = r->grid[EMCGPU_GRID_COUNT].as<double>();
   CUDA_TRY(ctx, cudaMemsetAsync(count, 0, (size_t)G.cells * sizeof(double), ctx->stream));
-  if (ctx->n == 0) return EMCGPU_OK;
   AssignParams A;
   A.x = ctx->dStream[EMCGPU_X];
   A.y = ctx->dStream[EMCGPU_Y];
   A.z = ctx->dStream[EMCGPU_Z];
-  A.n = ctx->n;
   A.nrCarriers = r->nrCarriers;
   A.count = count;
+  A.conc = withConc ? r->grid[EMCGPU_GRID_CONCENTRATION].as<double>() : nullptr;
+  A.pot = r->grid[EMCGPU_GRID_POTENTIAL].as<const double>();
+  A.sumPot = r->grid[EMCGPU_GRID_SUM_POTENTIAL].as<double>();
+  A.sumConc = r->grid[EMCGPU_GRID_SUM_CONCENTRATION].as<double>();
+  A.ctl = r->dCtl.as<RunCtl>();
+  A.counters = r->dCounters.as<int32_t>();
+  A.closeStep = closeStep ? 1 : 0;
   const size_t smem = (size_t)G.cells * sizeof(double);
   A.useSmem = smem <= 96 * 1024 ? 1 : 0;
   if (A.useSmem) CUDA_TRY(ctx, cudaFuncSetAttribute(ngpAssignKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ctx->n + 255) / 256, ctx->smCount));
-  ngpAssignKernel<<<grid, 256, A.useSmem ? smem : 0, ctx->stream>>>(G, A);
+  ngpAssignKernel<<<particleGrid(ctx, 256, 1), 256, A.useSmem ? smem : 0, ctx->stream>>>(G, A);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return EMCGPU_OK;
@@ -238,25 +272,29 @@ int doConcentration(emcgpu_ctx *ctx) {
   return EMCGPU_OK;
 }
 
-int doStep(emcgpu_ctx *ctx, double dt, int32_t *removedHost) {
+template <bool EXACT, int MODE> cudaError_t launchStepDim(emcgpu_ctx *ctx, const DeviceStepParams &D, size_t smem, int grid) {
+  const DevGeometry &G = ctx->run->geo;
+  auto go = [&](auto kernel) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, kBulkThreads, smem, ctx->stream>>>(G, D);
+    ctx->launches++;
+    return cudaGetLastError();
+  };
+  return ctx->run->dim == 2 ? go(deviceStepKernel<EXACT, MODE, 2>) : go(deviceStepKernel<EXACT, MODE, 3>);
+}
+
+// particle step: ensemble in place, flags for the contact handling / compaction, removedPerContact in the control block
+int doStep(emcgpu_ctx *ctx, double dt) {
   DeviceRunState *r = ctx->run;
-  const DevGeometry &G = r->geo;
-  for (int c = 0; c < G.nContacts && removedHost; c++) removedHost[c] = 0;
-  if (ctx->n == 0) {
-    ctx->nextStep++;
-    return EMCGPU_OK;
-  }
-  CUDA_TRY(ctx, r->dRemoved.ensure((size_t)ctx->capacity));
-  CUDA_TRY(ctx, cudaMemsetAsync(r->dRemovedPerContact.ptr, 0, kMaxContacts * sizeof(int32_t), ctx->stream));
   DeviceStepParams D;
   fillParams(ctx, D.P);
   D.P.dt = dt;
   D.P.nSteps = 1;
-  D.P.step0 = ctx->nextStep;
   D.e = r->grid[EMCGPU_GRID_EFIELD_X].as<const double>();
   D.charge = r->charge;
-  D.removed = r->dRemoved.as<int8_t>();
-  D.removedPerContact = r->dRemovedPerContact.as<int32_t>();
+  D.flag = r->dFlag.as<int32_t>();
+  D.ctl = r->dCtl.as<RunCtl>();
   bool inSmem = true;
   size_t smem = BulkSmem(0, ctx->hModel.nValleys, (int)ctx->hMechs.size(), ctx->hModel.tableDoubles, true, 0).total;
   if (smem > (size_t)ctx->maxSmemOptin / 2) { // two CTAs per SM
@@ -264,7 +302,7 @@ int doStep(emcgpu_ctx *ctx, double dt, int32_t *removedHost) {
     smem = BulkSmem(0, ctx->hModel.nValleys, (int)ctx->hMechs.size(), ctx->hModel.tableDoubles, false, 0).total;
   }
   D.P.tablesInSmem = inSmem ? 1 : 0;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ctx->n + kBulkThreads - 1) / kBulkThreads, 2 * ctx->smCount));
+  const int grid = particleGrid(ctx, kBulkThreads, 2);
   const bool exact = ctx->mathMode == EMCGPU_MATH_EXACT;
   cudaError_t e;
   if (ctx->rngMode == RNG_PHILOX)
@@ -272,68 +310,83 @@ int doStep(emcgpu_ctx *ctx, double dt, int32_t *removedHost) {
   else
     e = exact ? launchStepDim<true, RNG_REPLAY>(ctx, D, smem, grid) : launchStepDim<false, RNG_REPLAY>(ctx, D, smem, grid);
   if (e != cudaSuccess) return fail(ctx, EMCGPU_E_CUDA, "device step launch failed: %s", cudaGetErrorString(e));
-  ctx->nextStep++;
-  if (removedHost)
-    CUDA_TRY(ctx, cudaMemcpyAsync(removedHost, r->dRemovedPerContact.ptr, G.nContacts * sizeof(int32_t),
-                                  cudaMemcpyDeviceToHost, ctx->stream));
-  if (int rc = compactEnsemble(ctx, r->dRemoved.as<const int8_t>())) return rc; // synchronises
-  return readStatus(ctx);
+  return EMCGPU_OK;
 }
 
-int doContacts(emcgpu_ctx *ctx, int32_t *netHost, const uint64_t *replayDraws, int64_t nReplay) {
+// drop the particles flagged kGone, keeping the order of the others (into the twin buffer, which becomes the ensemble)
+int doCompaction(emcgpu_ctx *ctx) {
+  DeviceRunState *r = ctx->run;
+  RunCtl *ctl = r->dCtl.as<RunCtl>();
+  const int32_t *flag = r->dFlag.as<const int32_t>();
+  int32_t *chunkCount = r->dChunkCount.as<int32_t>();
+  const int grid = particleGrid(ctx, kChunk, 8);
+  selectCountKernel<SELECT_KEPT><<<grid, kChunk, 0, ctx->stream>>>(flag, ctl, chunkCount);
+  const bool replay = ctx->rngMode == RNG_REPLAY;
+  if (replay) CUDA_TRY(ctx, r->altCursor.ensure((size_t)ctx->capacity * sizeof(uint32_t)));
+  EnsemblePtrs src = ptrsOf(ctx->dEnsemble.ptr, ctx->capacity, replay ? ctx->dCursor.as<uint32_t>() : nullptr);
+  EnsemblePtrs dst = ptrsOf(r->altEnsemble.ptr, ctx->capacity, replay ? r->altCursor.as<uint32_t>() : nullptr);
+  compactScatterKernel<<<grid, kChunk, 0, ctx->stream>>>(flag, ctl, chunkCount, src, dst);
+  ctx->launches += 2;
+  CUDA_TRY(ctx, cudaGetLastError());
+  std::swap(ctx->dEnsemble, r->altEnsemble);
+  if (replay) std::swap(ctx->dCursor, r->altCursor);
+  for (int s = 0; s < EMCGPU_N_STREAMS; s++) ctx->dStream[s] = dst.stream[s];
+  ctx->dPacked = dst.packed;
+  return EMCGPU_OK;
+}
+
+// ohmic contacts on the flags of the step (fromStep) or of the resting ensemble: excess particles -> kGone,
+// compaction, injection behind the survivors
+int doContacts(emcgpu_ctx *ctx, bool fromStep, const uint64_t *replayDraws, int64_t nReplay) {
   DeviceRunState *r = ctx->run;
   const DevGeometry &G = r->geo;
-  CUDA_TRY(ctx, r->dRemoved.ensure((size_t)std::max<int64_t>(1, ctx->capacity)));
+  RunCtl *ctl = r->dCtl.as<RunCtl>();
+  int32_t *flag = r->dFlag.as<int32_t>();
+  int32_t *chunkCount = r->dChunkCount.as<int32_t>();
+  const int grid = particleGrid(ctx, kChunk, 8);
+  if (!fromStep) {
+    reservoirFlagKernel<<<particleGrid(ctx, 256, 4), 256, 0, ctx->stream>>>(G, ctx->dStream[EMCGPU_X], ctx->dStream[EMCGPU_Y],
+                                                                            ctx->dStream[EMCGPU_Z], ctl, flag);
+    ctx->launches++;
+  }
+  selectCountKernel<SELECT_RESERVOIR><<<grid, kChunk, 0, ctx->stream>>>(flag, ctl, chunkCount);
+  reservoirListKernel<<<grid, kChunk, 0, ctx->stream>>>(flag, ctl, chunkCount, r->dListParticle.as<int32_t>(),
+                                                        r->dListCell.as<int32_t>());
   ContactParams K;
-  K.x = ctx->dStream[EMCGPU_X];
-  K.y = ctx->dStream[EMCGPU_Y];
-  K.z = ctx->dStream[EMCGPU_Z];
-  K.n = ctx->n;
   K.nrCarriers = r->nrCarriers;
   K.expected = r->grid[EMCGPU_GRID_EXPECTED].as<const double>();
-  K.have = r->dHave.as<double>();
-  K.drop = r->dRemoved.as<int8_t>();
-  K.net = r->dNet.as<int32_t>();
+  K.listParticle = r->dListParticle.as<const int32_t>();
+  K.listCell = r->dListCell.as<const int32_t>();
+  K.flag = flag;
+  K.cellCount = r->dCellCount.as<int32_t>();
   K.injectCount = r->dInjectCount.as<int32_t>();
-  contactMarkKernel<<<1, 32, 0, ctx->stream>>>(G, K);
+  K.ctl = ctl;
+  contactRankKernel<<<std::min(grid, 2 * ctx->smCount), 256, 0, ctx->stream>>>(G, K);
+  ctx->launches += 3;
+  CUDA_TRY(ctx, cudaGetLastError());
+  if (int rc = doCompaction(ctx)) return rc;
+  InjectParams J;
+  J.ens = ptrsOf(ctx->dEnsemble.ptr, ctx->capacity, ctx->rngMode == RNG_REPLAY ? ctx->dCursor.as<uint32_t>() : nullptr);
+  J.injectCount = K.injectCount;
+  J.model = ctx->dModel.as<const DevModel>();
+  J.seed = ctx->seed;
+  J.ctl = ctl;
+  J.replay = nullptr;
+  J.replayCount = 0;
+  J.status = ctx->dStatus.as<int>();
+  if (replayDraws) {
+    CUDA_TRY(ctx, r->dReplay.ensure((size_t)std::max<int64_t>(1, nReplay) * sizeof(uint64_t)));
+    CUDA_TRY(ctx, cudaMemcpyAsync(r->dReplay.ptr, replayDraws, nReplay * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    J.replay = r->dReplay.as<const uint64_t>();
+    J.replayCount = nReplay;
+  }
+  const int injectGrid = 8; // a few hundred particles per step at most; grid-stride
+  if (r->dim == 2)
+    contactInjectKernel<2><<<injectGrid, 128, 0, ctx->stream>>>(G, J);
+  else
+    contactInjectKernel<3><<<injectGrid, 128, 0, ctx->stream>>>(G, J);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
-  int32_t toInject = 0;
-  CUDA_TRY(ctx, cudaMemcpyAsync(&toInject, K.injectCount + G.cells, sizeof toInject, cudaMemcpyDeviceToHost, ctx->stream));
-  if (netHost)
-    CUDA_TRY(ctx, cudaMemcpyAsync(netHost, r->dNet.ptr, G.nContacts * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  if (int rc = compactEnsemble(ctx, K.drop)) return rc; // synchronises: toInject / netHost are valid now
-  if (ctx->n == 0) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  if (toInject > 0) {
-    if (int rc = growEnsemble(ctx, std::max<int64_t>(ctx->n + toInject, r->reserve))) return rc;
-    InjectParams J;
-    J.ens = ptrsOf(ctx->dEnsemble.ptr, ctx->capacity, ctx->rngMode == RNG_REPLAY ? ctx->dCursor.as<uint32_t>() : nullptr);
-    J.first = ctx->n;
-    J.injectCount = K.injectCount;
-    J.model = ctx->dModel.as<const DevModel>();
-    J.seed = ctx->seed;
-    J.step = ctx->nextStep - 1; // the step whose contacts are handled
-    J.replay = nullptr;
-    J.replayCount = 0;
-    J.status = ctx->dStatus.as<int>();
-    if (replayDraws) {
-      CUDA_TRY(ctx, r->dReplay.ensure((size_t)std::max<int64_t>(1, nReplay) * sizeof(uint64_t)));
-      CUDA_TRY(ctx, cudaMemcpyAsync(r->dReplay.ptr, replayDraws, nReplay * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-      J.replay = r->dReplay.as<const uint64_t>();
-      J.replayCount = nReplay;
-    }
-    const int grid = (toInject + 127) / 128;
-    if (r->dim == 2)
-      contactInjectKernel<2><<<grid, 128, 0, ctx->stream>>>(G, J);
-    else
-      contactInjectKernel<3><<<grid, 128, 0, ctx->stream>>>(G, J);
-    ctx->launches++;
-    CUDA_TRY(ctx, cudaGetLastError());
-    if (ctx->rngMode == RNG_REPLAY && ctx->dCursor.bytes < (size_t)ctx->capacity * sizeof(uint32_t))
-      return fail(ctx, EMCGPU_E_INVALID, "replay streams do not cover injected particles: upload the ensemble again");
-    ctx->n += toInject;
-    return readStatus(ctx);
-  }
   return EMCGPU_OK;
 }
 
@@ -400,6 +453,29 @@ int emcgpu_device_configure(emcgpu_ctx *ctx, const emcgpu_device_t *dev, double 
   G.region = r->dRegion.as<const int32_t>();
   G.faceContact = r->dFace.as<const int8_t>();
   G.doping = r->dDoping.as<const double>();
+  {
+    // per-cell constants of the Poisson sweeps
+    std::vector<double> norm(cells);
+    std::vector<uint8_t> kind(cells, 0);
+    for (int64_t i = 0; i < cells; i++) {
+      norm[i] = dev->doping[i] / dev->ni;
+      const int8_t *fc = dev->faceContact + i * 2 * dev->dim;
+      int first = -1;
+      bool seen = false;
+      for (int f = 0; f < 2 * dev->dim; f++) {
+        if (fc[f] == -2) continue;
+        if (!seen) first = fc[f], seen = true;
+        if (fc[f] >= 0 && dev->contactType[fc[f]] == EMCGPU_CONTACT_GATE) kind[i] |= 2;
+      }
+      if (first >= 0 && dev->contactType[first] != EMCGPU_CONTACT_GATE) kind[i] |= 1;
+    }
+    CUDA_TRY(ctx, r->dDopingNorm.ensure(cells * sizeof(double)));
+    CUDA_TRY(ctx, r->dCellKind.ensure(cells));
+    CUDA_TRY(ctx, cudaMemcpy(r->dDopingNorm.ptr, norm.data(), cells * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(r->dCellKind.ptr, kind.data(), cells, cudaMemcpyHostToDevice));
+    G.dopingNorm = r->dDopingNorm.as<const double>();
+    G.cellKind = r->dCellKind.as<const uint8_t>();
+  }
   // E field components are one allocation [dim][cells] starting at EFIELD_X
   for (int g = 0; g < EMCGPU_N_GRIDS; g++) {
     if (g == EMCGPU_GRID_EFIELD_Y || g == EMCGPU_GRID_EFIELD_Z) continue;
@@ -407,11 +483,15 @@ int emcgpu_device_configure(emcgpu_ctx *ctx, const emcgpu_device_t *dev, double 
     CUDA_TRY(ctx, r->grid[g].ensure(bytes));
     CUDA_TRY(ctx, cudaMemset(r->grid[g].ptr, 0, bytes));
   }
-  CUDA_TRY(ctx, r->dRemovedPerContact.ensure(kMaxContacts * sizeof(int32_t)));
-  CUDA_TRY(ctx, r->dNet.ensure(kMaxContacts * sizeof(int32_t)));
-  CUDA_TRY(ctx, r->dHave.ensure(cells * sizeof(double)));
+  CUDA_TRY(ctx, r->dCtl.ensure(sizeof(RunCtl)));
+  CUDA_TRY(ctx, cudaMemset(r->dCtl.ptr, 0, sizeof(RunCtl)));
+  CUDA_TRY(ctx, r->dCellCount.ensure(cells * sizeof(int32_t)));
+  CUDA_TRY(ctx, cudaMemset(r->dCellCount.ptr, 0, cells * sizeof(int32_t)));
+  CUDA_TRY(ctx, r->dCounters.ensure((size_t)kRunChunk * 2 * kMaxContacts * sizeof(int32_t)));
+  CUDA_TRY(ctx, r->dSweepsPerStep.ensure((size_t)kRunChunk * sizeof(int32_t)));
   CUDA_TRY(ctx, r->dInjectCount.ensure((cells + 1) * sizeof(int32_t)));
   CUDA_TRY(ctx, r->dSweeps.ensure(sizeof(int32_t)));
+  CUDA_TRY(ctx, cudaMemset(r->dSweeps.ptr, 0, sizeof(int32_t)));
   // initial guess of the potential and the contact populations
   std::vector<double> pot(cells), exp(cells, 0.0);
   for (int64_t i = 0; i < cells; i++) pot[i] = std::asinh(0.5 * (dev->doping[i] / dev->ni));
@@ -453,6 +533,7 @@ int emcgpu_device_set_grid(emcgpu_ctx *ctx, int grid, const double *host) {
   if (int r = needRun(ctx)) return r;
   if (grid < 0 || grid >= EMCGPU_N_GRIDS || !host) return fail(ctx, EMCGPU_E_INVALID, "bad grid argument");
   if (grid == EMCGPU_GRID_EFIELD_Z && ctx->run->dim < 3) return fail(ctx, EMCGPU_E_INVALID, "no z field in a 2-D device");
+  if (grid == EMCGPU_GRID_EXPECTED) ctx->run->maxInject = -1;
   CUDA_TRY(ctx, cudaMemcpyAsync(gridPtr(ctx, grid), host, (size_t)ctx->run->geo.cells * sizeof(double), cudaMemcpyHostToDevice,
                                 ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -478,7 +559,9 @@ int emcgpu_device_reserve(emcgpu_ctx *ctx, int64_t capacity) {
 int emcgpu_device_poisson(emcgpu_ctx *ctx, int equilibrium, double accuracyVolt, double omega, int resetBC, int32_t *sweeps) {
   if (int r = needRun(ctx)) return r;
   if (!(accuracyVolt > 0) || !(omega > 0 && omega < 2)) return fail(ctx, EMCGPU_E_INVALID, "bad SOR parameters");
-  if (int r = doPoisson(ctx, equilibrium != 0, accuracyVolt, omega, resetBC != 0, sweeps)) return r;
+  if (int r = doPoisson(ctx, equilibrium != 0, accuracyVolt, omega, resetBC != 0, false, false)) return r;
+  if (sweeps)
+    CUDA_TRY(ctx, cudaMemcpyAsync(sweeps, ctx->run->dSweeps.ptr, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return EMCGPU_OK;
 }
@@ -490,7 +573,8 @@ int emcgpu_device_efield(emcgpu_ctx *ctx) {
 
 int emcgpu_device_assign(emcgpu_ctx *ctx) {
   if (int r = needRun(ctx)) return r;
-  return doAssign(ctx);
+  if (int r = pushCtl(ctx, 0)) return r;
+  return doAssign(ctx, false, false);
 }
 
 int emcgpu_device_concentration(emcgpu_ctx *ctx) {
@@ -502,13 +586,44 @@ int emcgpu_device_step(emcgpu_ctx *ctx, double dt, int32_t *removedPerContact) {
   if (int r = needRun(ctx)) return r;
   if (int r = needModel(ctx)) return r;
   if (!(dt > 0)) return fail(ctx, EMCGPU_E_INVALID, "dt must be positive");
-  return doStep(ctx, dt, removedPerContact);
+  if (int r = pushCtl(ctx, 0)) return r;
+  if (int r = doStep(ctx, dt)) return r;
+  if (int r = doCompaction(ctx)) return r;
+  RunCtl h;
+  if (int r = pullCtl(ctx, &h)) return r;
+  ctx->n = h.nKept;
+  ctx->nextStep = h.step + 1;
+  for (int c = 0; c < ctx->run->geo.nContacts && removedPerContact; c++) removedPerContact[c] = h.removedPerContact[c];
+  return readStatus(ctx);
 }
 
 int emcgpu_device_contacts(emcgpu_ctx *ctx, int32_t *netPerContact, const uint64_t *replayDraws, int64_t nReplayDraws) {
   if (int r = needRun(ctx)) return r;
   if (int r = needModel(ctx)) return r;
-  return doContacts(ctx, netPerContact, replayDraws, nReplayDraws);
+  // one reservoir cell never misses more than its expected population: room for the worst case
+  {
+    DeviceRunState *r = ctx->run;
+    if (r->maxInject < 0) {
+      std::vector<double> exp(r->geo.cells);
+      CUDA_TRY(ctx, cudaMemcpy(exp.data(), r->grid[EMCGPU_GRID_EXPECTED].ptr, exp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+      double total = 0;
+      for (double v : exp) total += std::ceil(std::max(0.0, v) / r->nrCarriers);
+      r->maxInject = (int64_t)total;
+    }
+    if (int rc = growEnsemble(ctx, std::max<int64_t>(ctx->n + r->maxInject, r->reserve))) return rc;
+  }
+  ctx->nextStep--; // the contacts belong to the step that was just done (Philox counter of the injected particles)
+  if (int r = pushCtl(ctx, 0)) return r;
+  ctx->nextStep++;
+  if (int r = doContacts(ctx, false, replayDraws, nReplayDraws)) return r;
+  RunCtl h;
+  if (int r = pullCtl(ctx, &h)) return r;
+  ctx->n = h.nKept + h.toInject;
+  ctx->nextStep = h.step + 1;
+  for (int c = 0; c < ctx->run->geo.nContacts && netPerContact; c++) netPerContact[c] = h.net[c];
+  if (ctx->rngMode == RNG_REPLAY && h.toInject > 0 && ctx->dCursor.bytes < (size_t)ctx->capacity * sizeof(uint32_t))
+    return fail(ctx, EMCGPU_E_INVALID, "replay streams do not cover injected particles: upload the ensemble again");
+  return readStatus(ctx);
 }
 
 int emcgpu_device_run(emcgpu_ctx *ctx, double dt, int nSteps, double accuracyVolt, double omega, int resetBCFirst,
@@ -522,24 +637,34 @@ int emcgpu_device_run_averaging(emcgpu_ctx *ctx, double dt, int nSteps, int nAve
   if (int r = needModel(ctx)) return r;
   if (!(dt > 0) || nSteps < 1 || !(accuracyVolt > 0) || nAverage < 0 || nAverage > nSteps)
     return fail(ctx, EMCGPU_E_INVALID, "bad run arguments");
-  const int nC = ctx->run->geo.nContacts;
-  for (int s = 0; s < nSteps; s++) {
-    if (int r = doPoisson(ctx, false, accuracyVolt, omega, resetBCFirst && s == 0, sweeps ? sweeps + s : nullptr)) return r;
-    if (int r = doEfield(ctx)) return r;
-    if (int r = doStep(ctx, dt, counters ? counters + (size_t)s * 2 * nC : nullptr)) return r;
-    if (int r = doContacts(ctx, counters ? counters + (size_t)s * 2 * nC + nC : nullptr, nullptr, 0)) return r;
-    if (int r = doAssign(ctx)) return r;
-    if (int r = doConcentration(ctx)) return r;
-    if (s >= nSteps - nAverage) {
-      DeviceRunState *r = ctx->run;
-      accumulateKernel<<<gridBlocks(r->geo.cells), 256, 0, ctx->stream>>>(
-          r->geo.cells, r->grid[EMCGPU_GRID_POTENTIAL].as<const double>(), r->grid[EMCGPU_GRID_CONCENTRATION].as<const double>(),
-          r->grid[EMCGPU_GRID_SUM_POTENTIAL].as<double>(), r->grid[EMCGPU_GRID_SUM_CONCENTRATION].as<double>());
-      ctx->launches++;
-      CUDA_TRY(ctx, cudaGetLastError());
+  DeviceRunState *r = ctx->run;
+  const int nC = r->geo.nContacts;
+  std::vector<int32_t> hCounters((size_t)kRunChunk * 2 * std::max(1, nC)), hSweeps(kRunChunk);
+  for (int done = 0; done < nSteps;) {
+    const int chunk = std::min(kRunChunk, nSteps - done);
+    // head room for the particles the contacts may inject during the chunk (checked again on the device)
+    if (ctx->capacity < ctx->n + ctx->n / 4 + 4096 || ctx->capacity < r->reserve)
+      if (int rc = growEnsemble(ctx, std::max<int64_t>(ctx->n + ctx->n / 2 + 8192, r->reserve))) return rc;
+    if (int rc = pushCtl(ctx, std::max(0, (nSteps - nAverage) - done))) return rc;
+    for (int s = 0; s < chunk; s++) {
+      // performEMCStep (emcSimulation.hpp:177-192)
+      if (int rc = doPoisson(ctx, false, accuracyVolt, omega, resetBCFirst && done + s == 0, true, true)) return rc;
+      if (int rc = doStep(ctx, dt)) return rc;
+      if (int rc = doContacts(ctx, true, nullptr, 0)) return rc;
+      if (int rc = doAssign(ctx, true, true)) return rc;
     }
+    if (counters)
+      CUDA_TRY(ctx, cudaMemcpyAsync(hCounters.data(), r->dCounters.ptr, (size_t)chunk * 2 * nC * sizeof(int32_t),
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+    if (sweeps)
+      CUDA_TRY(ctx, cudaMemcpyAsync(hSweeps.data(), r->dSweepsPerStep.ptr, (size_t)chunk * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                    ctx->stream));
+    if (int rc = pullCtl(ctx)) return rc;
+    if (int rc = readStatus(ctx)) return rc;
+    if (counters) std::copy(hCounters.begin(), hCounters.begin() + (size_t)chunk * 2 * nC, counters + (size_t)done * 2 * nC);
+    if (sweeps) std::copy(hSweeps.begin(), hSweeps.begin() + chunk, sweeps + done);
+    done += chunk;
   }
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return EMCGPU_OK;
 }
 

@@ -46,6 +46,9 @@ struct emcgpu_ctx {
   int optKernel = 0;       // one-step kernel: 0 = TMA pipeline when it fits, 1 = plain streaming kernel
   int optStages = 0;       // cap on the TMA ring depth (0 = as many as fit)
   int optTablesGlobal = 0; // 1 = leave the rate tables in global memory / L2 (more ring stages)
+  int optSorKernel = 0;    // 0 = row-per-thread wavefront when it fits, 1 = hyperplane loop
+  int optSorOrder = 0;     // 0 = the reference's lexicographic order (bit-identical iterates), 1 = red-black
+  int optPoissonInterval = 1; // device run: solve Poisson every n-th step (emcSimulation::setPoissonInterval)
   cudaStream_t stream = nullptr;
   std::string error;
   int64_t launches = 0;

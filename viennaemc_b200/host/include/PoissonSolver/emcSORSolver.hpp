@@ -26,6 +26,7 @@ class emcSORSolver : public emcAbstractSolver<T, DeviceType, ParticleHandler> {
   emcgpu_ctx *ctx = nullptr;
   bool ownsContext = false;
   int lastSweeps = 0;
+  bool redBlack = false;
 
   void needContext() {
     if (ctx)
@@ -46,6 +47,7 @@ class emcSORSolver : public emcAbstractSolver<T, DeviceType, ParticleHandler> {
     if (eConc)
       emcgpu::require(ctx, emcgpu_device_set_grid(ctx, EMCGPU_GRID_CONCENTRATION, eConc->raw()), "emcgpu_device_set_grid");
     int32_t sweeps = 0;
+    emcgpu::require(ctx, emcgpu_set_option(ctx, "sor_order", redBlack ? 1 : 0), "emcgpu_set_option");
     emcgpu::require(ctx, emcgpu_device_poisson(ctx, eConc ? 0 : 1, accuracyVolt, omega, resetBC ? 1 : 0, &sweeps),
                     "emcgpu_device_poisson");
     lastSweeps = sweeps;
@@ -79,6 +81,11 @@ public:
   T getAccuracy() const { return accuracyVolt; } // [V]
   T getOmega() const { return omega; }
   int getLastNrSweeps() const { return lastSweeps; }
+  // order of the relaxation sweeps.  false (default): the reference's lexicographic Gauss-Seidel order -- iterates and
+  // sweep counts are the reference's.  true: red-black ordering -- same equation, relaxation factor and stopping rule,
+  // fully parallel; the potential agrees with the lexicographic one to about the accuracy of the solver.
+  void setRedBlackOrdering(bool on) { redBlack = on; }
+  bool getRedBlackOrdering() const { return redBlack; }
   // use (not own) the context of a GPU particle handler that was configured for the same device
   void attach(emcgpu_ctx *shared) {
     if (ownsContext && ctx)
