@@ -107,3 +107,73 @@ def test_host_built_model_gives_the_same_trajectories_as_the_oracle_built_model(
     for f in po.Ensemble.F64[:5] + po.Ensemble.F64[6:] + po.Ensemble.I32:
         assert np.array_equal(getattr(a, f), getattr(b, f)), f
     assert np.array_equal(oa[:, :, 2], ob[:, :, 2])
+
+
+# ---- device run: emcSimulation + emcBasicParticleHandler + emcNGPScheme + emcSORSolver (config 3) --------------
+def _resistor_stats():
+    with open(os.path.join(GOLDEN_DIR, "ref_resistor_stats.json")) as f:
+        return json.load(f)
+
+
+def _read_grid(path):
+    with open(path) as f:
+        extent = [int(v) for v in f.readline().split()]
+        a = np.loadtxt(f)
+    assert list(a.shape) == extent[::-1]
+    return a
+
+
+def _check_resistor(workdir, prefix, n_sigma=3.0):
+    st = _resistor_stats()
+    cur = np.loadtxt(os.path.join(workdir, prefix + "ElectronsCurrent.txt"))
+    assert cur.shape == (30000, 5)  # time, netto particles per contact (2), running mean current per contact (2)
+    widen = np.sqrt(1 + 1 / st["n_runs"])
+    for c in range(2):
+        assert abs(cur[-1, 3 + c] - st["current_mean"][c]) <= n_sigma * st["current_std"][c] * widen, \
+            (c, cur[-1, 3 + c], st["current_mean"][c], st["current_std"][c])
+    # electrons leave through the positive XMIN contact (index 1) and enter through the grounded one
+    assert cur[-1, 3] > 0 > cur[-1, 4]
+    pot = _read_grid(os.path.join(workdir, prefix + "PotentialAvg.txt")).mean(axis=0)
+    conc = _read_grid(os.path.join(workdir, prefix + "ElectronsConcAvg.txt")).mean(axis=0)
+    pot_ref, pot_std = np.array(st["pot_x_mean"]), np.array(st["pot_x_std"])
+    conc_ref, conc_std = np.array(st["conc_x_mean"]), np.array(st["conc_x_std"])
+    # profiles along the bar.  The per-point scatter of the reference is estimated from a handful of runs, so a small
+    # per-point estimate is replaced by the median over the bar (the noise is homogeneous along it); 4.5 sigma per
+    # point keeps the chance of a false alarm over 101 points negligible.  The Dirichlet / reservoir end points have
+    # (almost) no scatter: absolute floors.
+    pot_sig = np.maximum(pot_std, np.median(pot_std)) * widen
+    conc_sig = np.maximum(conc_std, np.median(conc_std)) * widen
+    assert np.all(np.abs(pot - pot_ref) <= 4.5 * pot_sig + 2e-4), np.abs(pot - pot_ref).max()
+    assert np.all(np.abs(conc - conc_ref) <= 4.5 * conc_sig + 1e-3 * conc_ref), np.abs(conc / conc_ref - 1).max()
+    # and the bar as a whole: mean carrier density within 3 sigma of the reference's
+    ref_means = np.array([np.mean(r["conc_x"]) for r in st["runs"]])
+    assert abs(conc.mean() - ref_means.mean()) <= n_sigma * ref_means.std(ddof=1) * widen + 1e-3 * ref_means.mean()
+    return cur[-1, 3:]
+
+
+def test_unmodified_reference_resistor_main_runs_on_the_gpu_path(tmp_path):
+    """examples/resistor2D/resistor2D.cpp of the reference, compiled unchanged against our headers: 50 000 self-consistent
+    steps on the GPU, terminal currents and averaged profiles within the reference's own run-to-run scatter."""
+    exe = os.path.join(BIN, "reference_resistor2D_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("reference_resistor2D_gpu is built only where the reference tree is mounted")
+    r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "Nr. Iteration: \t\t50000 / 50000" in r.stdout
+    _check_resistor(str(tmp_path), "resistorV50as1000")
+
+
+@pytest.mark.parametrize("red_black", [0, 1], ids=["lexicographic", "redblack"])
+def test_own_resistor_driver_matches_reference_within_3_sigma(tmp_path, red_black):
+    exe = os.path.join(BIN, "resistor2D")
+    assert os.path.exists(exe), "build with python -m viennaemc_b200.build"
+    r = subprocess.run([exe, "--seed", "20261017", "--red-black", str(red_black)], cwd=tmp_path, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    _check_resistor(str(tmp_path), "resistor")
+    # a seeded run is reproducible bit for bit (Philox streams, ordered compaction, exact charge assignment)
+    r2 = subprocess.run([exe, "--seed", "20261017", "--red-black", str(red_black), "--prefix", "again"], cwd=tmp_path,
+                        capture_output=True, text=True, timeout=900)
+    assert r2.returncode == 0
+    for f in ("ElectronsCurrent.txt", "PotentialAvg.txt", "ElectronsFinal.txt"):
+        assert open(os.path.join(tmp_path, "resistor" + f)).read() == open(os.path.join(tmp_path, "again" + f)).read(), f
