@@ -1025,13 +1025,33 @@ void orc_efield(const orc_device_t *d, const double *pot, double *e) {
   const int dim = d->dim;
   const int64_t n = orc_dev_cells(d);
   int64_t stride[3] = {1, d->extent[0], (int64_t)d->extent[0] * d->extent[1]};
+  if (d->pmScheme == ORC_PM_NEC_VWD) {
+    /* NECSchemeVWD.hpp:82-99: forward difference everywhere but on the max face, where E = 0; no contact rule */
+    for (int i = 0; i < dim; i++) {
+      double *ed = e + (int64_t)i * n;
+      for (int64_t cell = 0; cell < n; cell++) {
+        int64_t c[3];
+        dev_coord(d, cell, c);
+        if (c[i] != d->extent[i] - 1)
+          ed[cell] = ((pot[cell] - pot[cell + stride[i]]) * d->thermalVoltage) / d->spacing[i];
+        else
+          ed[cell] = 0;
+      }
+    }
+    return;
+  }
+  const int midPts = d->pmScheme == ORC_PM_NEC; /* calcEFieldAtEdgeMidPts :35-53 instead of calcEFieldAtGridPts :13-30 */
   for (int i = 0; i < dim; i++) {
     double *ed = e + (int64_t)i * n;
     for (int64_t cell = 0; cell < n; cell++) {
       int64_t c[3];
       dev_coord(d, cell, c);
-      if (c[i] != 0 && c[i] != d->extent[i] - 1)
-        ed[cell] = ((pot[cell - stride[i]] - pot[cell + stride[i]]) * d->thermalVoltage) / (2 * d->spacing[i]);
+      if (c[i] != 0 && c[i] != d->extent[i] - 1) {
+        if (midPts)
+          ed[cell] = ((pot[cell] - pot[cell + stride[i]]) * d->thermalVoltage) / d->spacing[i];
+        else
+          ed[cell] = ((pot[cell - stride[i]] - pot[cell + stride[i]]) * d->thermalVoltage) / (2 * d->spacing[i]);
+      }
     }
     /* setEFieldBoundaryValues :58-82: normal component 0 on artificial boundaries, copied from the
      * inner neighbour at contacts */
@@ -1047,6 +1067,58 @@ void orc_efield(const orc_device_t *d, const double *pot, double *e) {
       }
     }
   }
+}
+
+/* lower-left grid point of the cell a position lies in: floor(pos / spacing) */
+static void dev_floor_coord(const orc_device_t *d, const double pos[3], int64_t c[3], double w[3]) {
+  c[0] = c[1] = c[2] = 0;
+  w[0] = w[1] = w[2] = 0;
+  for (int i = 0; i < d->dim; i++) {
+    c[i] = (int64_t)floor(pos[i] / d->spacing[i]);
+    w[i] = pos[i] / d->spacing[i] - (double)c[i];
+  }
+}
+
+int orc_assign(const orc_device_t *d, int64_t n, const double *x, const double *y, const double *z, double nrCarriers,
+               double *count) {
+  const int64_t sx = 1, sy = d->extent[0], sz = (int64_t)d->extent[0] * d->extent[1];
+  for (int64_t p = 0; p < n; p++) {
+    const double pos[3] = {x[p], y[p], d->dim > 2 ? z[p] : 0.};
+    if (d->pmScheme == ORC_PM_NGP) {
+      count[dev_pos_to_cell(d, pos)] += nrCarriers;
+      continue;
+    }
+    int64_t c[3];
+    double w[3];
+    dev_floor_coord(d, pos, c, w);
+    const int64_t base = dev_cell(d, c);
+    if (d->pmScheme == ORC_PM_CIC) {
+      /* emcCICScheme.hpp:43-118: the weight w (distance from the LOWER point) goes to the lower point */
+      const double wX = w[0], wY = w[1], wZ = w[2];
+      if (d->dim == 2) {
+        count[base] += wX * wY * nrCarriers;
+        count[base + sx] += (1 - wX) * wY * nrCarriers;
+        count[base + sy] += wX * (1 - wY) * nrCarriers;
+        count[base + sx + sy] += (1 - wX) * (1 - wY) * nrCarriers;
+      } else {
+        count[base] += wX * wY * wZ * nrCarriers;
+        count[base + sx] += (1 - wX) * wY * wZ * nrCarriers;
+        count[base + sy] += wX * (1 - wY) * wZ * nrCarriers;
+        count[base + sx + sy] += (1 - wX) * (1 - wY) * wZ * nrCarriers;
+        count[base + sz] += wX * wY * (1 - wZ) * nrCarriers;
+        count[base + sx + sz] += (1 - wX) * wY * (1 - wZ) * nrCarriers;
+        count[base + sy + sz] += wX * (1 - wY) * (1 - wZ) * nrCarriers;
+        count[base + sx + sy + sz] += (1 - wX) * (1 - wY) * (1 - wZ) * nrCarriers;
+      }
+    } else { /* NEC, NEC-VWD: equal shares (emcNECScheme.hpp:33-96, NECSchemeVWD.hpp:25-52) */
+      const double weight = (d->dim == 2 ? 0.25 : 0.125) * nrCarriers;
+      for (int dz = 0; dz < (d->dim > 2 ? 2 : 1); dz++)
+        for (int dy = 0; dy < 2; dy++)
+          for (int dx = 0; dx < 2; dx++)
+            count[base + dx * sx + dy * sy + dz * sz] += weight;
+    }
+  }
+  return 0;
 }
 
 int orc_ngp_assign(const orc_device_t *d, int64_t n, const double *x, const double *y, const double *z,
@@ -1084,8 +1156,20 @@ void orc_expected_at_contact(const orc_device_t *d, double *expected) {
     for (int i = 0; i < d->dim; i++)
       if (c[i] == 0 || c[i] == d->extent[i] - 1)
         v *= 0.5;
-    expected[cell] = v;
+    expected[cell] = d->electronKind == 1 ? round(v) : v; /* electronVWD.hpp:53-62 */
   }
+}
+
+double orc_initial_nr_particles(const orc_device_t *d, int64_t cell, const double *pot) {
+  int64_t c[3];
+  dev_coord(d, cell, c);
+  /* emcElectron.hpp:48-61 / electronVWD.hpp:40-49 */
+  double dens = pot ? exp(pot[cell]) * d->ni : d->doping[cell]; /* electronVWD: pot must be given */
+  for (int i = 0; i < d->dim; i++)
+    if (c[i] == 0 || c[i] == d->extent[i] - 1)
+      dens *= 0.5;
+  double nr = dens * d->cellVolume;
+  return d->electronKind == 1 ? round(nr) : nr;
 }
 
 /* emcBasicParticleHandler.hpp:239-253 addParticle: position (emcParticleInitialization.hpp:14-29), then
@@ -1102,9 +1186,11 @@ static void dev_create_particle(const orc_model_t *m, const orc_device_t *d, con
       pos[i] = ((double)c[i] + rng_u01(rng) - 0.5) * d->spacing[i];
   }
   const int region = d->region[dev_cell(d, c)];
-  const int valley = (int)floor(m->nValleys * rng_ulog(rng));
+  /* emcElectron draws valley / sub-valley from U[1e-6, 1), electronVWD from U[0, 1) (electronVWD.hpp:25, :69-72) */
+  const int vwd = d->electronKind == 1;
+  const int valley = (int)floor(m->nValleys * (vwd ? rng_u01(rng) : rng_ulog(rng)));
   const orc_valley_t *v = &m->valleys[valley];
-  const int sub = (int)floor(v->deg * rng_ulog(rng));
+  const int sub = (int)floor(v->deg * (vwd ? rng_u01(rng) : rng_ulog(rng)));
   const double energy = -1.5 * d->thermalVoltage * log(rng_ulog(rng));
   const double r2 = rng_u01(rng);
   const double r1 = rng_u01(rng);
@@ -1113,7 +1199,8 @@ static void dev_create_particle(const orc_model_t *m, const orc_device_t *d, con
   for (int i = 0; i < d->dim; i++)
     if ((c[i] == 0 && k[i] < 0) || (c[i] == d->extent[i] - 1 && k[i] > 0))
       k[i] *= -1;
-  const double tau = -log(rng_ulog(rng)) * orc_tau(m, valley, region);
+  /* electronVWD passes the valley index where the region index belongs (electronVWD.hpp:74, :87) */
+  const double tau = -log(rng_ulog(rng)) * orc_tau(m, valley, vwd ? valley : region);
   const double gtau = -log(rng_ulog(rng)) * 1.;
   if (slot >= 0) {
     out->kx[slot] = k[0]; out->ky[slot] = k[1]; out->kz[slot] = k[2];
@@ -1128,8 +1215,8 @@ static void dev_create_particle(const orc_model_t *m, const orc_device_t *d, con
   }
 }
 
-int64_t orc_device_generate_initial(const orc_model_t *m, const orc_device_t *d, double nrCarriers, uint64_t *mtState,
-                                    orc_ensemble_t *out, int64_t capacity) {
+int64_t orc_device_generate_initial_pot(const orc_model_t *m, const orc_device_t *d, double nrCarriers, uint64_t *mtState,
+                                        const double *pot, orc_ensemble_t *out, int64_t capacity) {
   orc_rng_cfg_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.mode = ORC_RNG_MT_GLOBAL;
@@ -1142,11 +1229,7 @@ int64_t orc_device_generate_initial(const orc_model_t *m, const orc_device_t *d,
   for (int64_t cell = 0; cell < cells; cell++) {
     int64_t c[3];
     dev_coord(d, cell, c);
-    double dens = d->doping[cell]; /* emcElectron.hpp:48-61, usePotentialForInit == false */
-    for (int i = 0; i < d->dim; i++)
-      if (c[i] == 0 || c[i] == d->extent[i] - 1)
-        dens *= 0.5;
-    double nr = dens * d->cellVolume;
+    double nr = orc_initial_nr_particles(d, cell, pot);
     while (nr >= 1) { /* emcAbstractParticleHandler.hpp:139-146 */
       dev_create_particle(m, d, c, &rng, out, n < capacity ? n : -1);
       n++;
@@ -1160,11 +1243,78 @@ int64_t orc_device_generate_initial(const orc_model_t *m, const orc_device_t *d,
   out->n = n <= capacity ? n : capacity;
   return n <= capacity ? n : -n;
 }
+int64_t orc_device_generate_initial(const orc_model_t *m, const orc_device_t *d, double nrCarriers, uint64_t *mtState,
+                                    orc_ensemble_t *out, int64_t capacity) {
+  return orc_device_generate_initial_pot(m, d, nrCarriers, mtState, NULL, out, capacity);
+}
 
 /* emcAbstractParticleHandler.hpp:238-249 driftParticle = drift + handleParticleAtBoundary
  * (emcParticleDrift.hpp:42-66, default specular reflection emcScatterHandler.hpp:172-191) + region update */
+/* emcSurfaceScatterMechanism::scatterParticleSpecularly (:81-93): unlike the default reflection of the scatter handler,
+ * k is only turned when it points out of the device */
+static void surface_specular(const orc_device_t *d, double pos[3], double k[3]) {
+  for (int i = 0; i < d->dim; i++) {
+    if (pos[i] < 0) {
+      pos[i] *= -1;
+      if (k[i] < 0)
+        k[i] *= -1;
+    } else if (pos[i] > d->maxPos[i]) {
+      pos[i] = 2 * d->maxPos[i] - pos[i];
+      if (k[i] > 0)
+        k[i] *= -1;
+    }
+  }
+}
+/* emcMomentumDependentSurfaceScatterMechanism::solveForTheta (:39-68) */
+static double surface_solve_theta(double r, double height, double speed) {
+  double c = pow(2 * height * speed, 2);
+  double ee = exp(-c);
+  double x = sqrt(r * (1 / (1 - ee) - 1 / c));
+  double error = 1, tol = 1e-10;
+  int it = 0;
+  while (error > tol && it < 10000) {
+    double co = cos(x), si = sin(x);
+    double ecos = exp(-c * pow(co, 2));
+    double esin = exp(-c * pow(si, 2));
+    double x1 = x - (((ee - ecos) / c + pow(si, 2) - r * (1 - (1 - ee) / c)) * (2 * esin * c * si * co * (ecos - 1)) /
+                     (ee * (c - 1) - 1));
+    error = fabs(x1 - x);
+    x = x1;
+    it++;
+  }
+  return x;
+}
+/* emcSurfaceScatterMechanism::scatterParticle (:40-46) for the mechanism set on `face` */
+static void surface_scatter(const orc_device_t *d, int face, double pos[3], double k[3], rng_t *rng) {
+  const int kind = d->surfaceKind[face];
+  const int perp = face / 2;
+  double pDiff;
+  if (kind == ORC_SURFACE_CONSTANT)
+    pDiff = 1 - d->surfaceParam[face];
+  else
+    pDiff = 1 - (exp(-pow(2 * d->surfaceParam[face] * k[perp], 2)));
+  if (rng_u01(rng) < pDiff) {
+    double theta, phi;
+    if (kind == ORC_SURFACE_CONSTANT) {
+      theta = asin(sqrt(rng_u01(rng)));
+      phi = 2 * C_PI * rng_u01(rng);
+    } else {
+      double speed = sqrt(k[0] * k[0] + k[1] * k[1] + k[2] * k[2]);
+      theta = surface_solve_theta(rng_u01(rng), d->surfaceParam[face], speed);
+      phi = 2 * C_PI * rng_u01(rng);
+    }
+    /* calculateAndAssignKAndPos (:127-147) */
+    double speed = sqrt(k[0] * k[0] + k[1] * k[1] + k[2] * k[2]);
+    double sign = face % 2 == 1 ? -1 : 1;
+    k[perp] = speed * cos(theta) * sign;
+    k[(perp + 1) % 3] = speed * sin(theta) * cos(phi);
+    k[(perp + 2) % 3] = speed * sin(theta) * sin(phi);
+  }
+  surface_specular(d, pos, k);
+}
+
 static int dev_drift_particle(const orc_model_t *m, const orc_device_t *d, orc_ensemble_t *e, int64_t p, double dt,
-                              const double force[3]) {
+                              const double force[3], rng_t *rng) {
   double k[3] = {e->kx[p], e->ky[p], e->kz[p]};
   double pos[3] = {e->x[p], e->y[p], d->dim > 2 ? e->z[p] : 0.};
   orc_drift(&m->valleys[e->valley[p]], dt, k, &e->energy[p], e->sub[p], pos, d->dim, force);
@@ -1178,10 +1328,14 @@ static int dev_drift_particle(const orc_model_t *m, const orc_device_t *d, orc_e
       double lo = pos[i] < d->maxPos[i] ? pos[i] : d->maxPos[i]; /* std::max(0., std::min(pos, max)) */
       clamped[i] = 0. > lo ? 0. : lo;
     }
-    if (orc_dev_is_ohmic(d, dev_pos_to_cell(d, clamped))) {
+    const int64_t wallCell = dev_pos_to_cell(d, clamped);
+    const int face = dev_first_face(d, wallCell);
+    if (orc_dev_is_ohmic(d, wallCell)) {
       removed = 1;
       for (int i = 0; i < d->dim; i++)
         pos[i] = clamped[i];
+    } else if (face >= 0 && d->surfaceKind[face] != ORC_SURFACE_SPECULAR) {
+      surface_scatter(d, face, pos, k, rng);
     } else {
       for (int i = 0; i < d->dim; i++) {
         if (pos[i] < 0) {
@@ -1203,14 +1357,50 @@ static int dev_drift_particle(const orc_model_t *m, const orc_device_t *d, orc_e
   return removed;
 }
 
-/* emcNGPScheme.hpp:51-66 */
+/* interpolateForce of the device's PM scheme: emcNGPScheme.hpp:51-66, emcCICScheme.hpp:122-173 (with its
+ * (1 - wY)(1 - wY) weight of the upper-right point), emcNECScheme.hpp:99-113, NECSchemeVWD.hpp:57-76 */
 static void dev_force(const orc_device_t *d, const orc_ensemble_t *e, int64_t p, const double *ef, double charge,
                       double force[3]) {
   const double pos[3] = {e->x[p], e->y[p], d->dim > 2 ? e->z[p] : 0.};
-  const int64_t cell = dev_pos_to_cell(d, pos), n = orc_dev_cells(d);
+  const int64_t n = orc_dev_cells(d);
+  const int64_t sx = 1, sy = d->extent[0], sz = (int64_t)d->extent[0] * d->extent[1];
   force[2] = 0;
-  for (int i = 0; i < d->dim; i++)
-    force[i] = charge * ef[(int64_t)i * n + cell];
+  if (d->pmScheme == ORC_PM_NGP) {
+    const int64_t cell = dev_pos_to_cell(d, pos);
+    for (int i = 0; i < d->dim; i++)
+      force[i] = charge * ef[(int64_t)i * n + cell];
+    return;
+  }
+  int64_t c[3];
+  double w[3];
+  dev_floor_coord(d, pos, c, w);
+  if (d->pmScheme == ORC_PM_CIC) {
+    const int64_t base = dev_cell(d, c);
+    const double wX = w[0], wY = w[1], wZ = w[2];
+    for (int i = 0; i < d->dim; i++) {
+      const double *E = ef + (int64_t)i * n;
+      if (d->dim == 2)
+        force[i] = charge * (E[base] * wX * wY + E[base + sx] * (1 - wX) * wY + E[base + sy] * wX * (1 - wY) +
+                             E[base + sx + sy] * (1 - wY) * (1 - wY));
+      else
+        force[i] = (E[base] * wX * wY * wZ + E[base + sx] * (1 - wX) * wY * wZ + E[base + sy] * wX * (1 - wY) * wZ +
+                    E[base + sx + sy] * (1 - wY) * (1 - wY) * wZ + E[base + sz] * wX * wY * (1 - wZ) +
+                    E[base + sx + sz] * (1 - wX) * wY * (1 - wZ) + E[base + sy + sz] * wX * (1 - wY) * (1 - wZ) +
+                    E[base + sx + sy + sz] * (1 - wY) * (1 - wY) * (1 - wZ)) *
+                   charge;
+    }
+    return;
+  }
+  /* NEC (2-D only in the reference) */
+  if (d->pmScheme == ORC_PM_NEC_VWD)
+    c[0] = (int64_t)round(pos[0] / d->spacing[0]); /* "round x-position, instead of floor" */
+  const int64_t base = dev_cell(d, c);
+  const double *Ex = ef, *Ey = ef + n;
+  force[0] = charge * (Ex[base] + Ex[base + sy]) / 2;
+  if (d->pmScheme == ORC_PM_NEC_VWD && c[0] == d->extent[0] - 1)
+    force[1] = charge * Ey[base];
+  else
+    force[1] = charge * (Ey[base] + Ey[base + sx]) / 2;
 }
 
 int orc_device_step(const orc_model_t *m, const orc_device_t *d, orc_ensemble_t *e, const double *ef, double charge,
@@ -1235,9 +1425,9 @@ int orc_device_step(const orc_model_t *m, const orc_device_t *d, orc_ensemble_t 
     int removed = 0;
     double tau = e->tau[p];
     if (tau >= dt) {
-      removed = dev_drift_particle(m, d, e, p, dt, force);
+      removed = dev_drift_particle(m, d, e, p, dt, force, &rng);
     } else {
-      removed = dev_drift_particle(m, d, e, p, tau, force);
+      removed = dev_drift_particle(m, d, e, p, tau, force, &rng);
       double tRem = dt - tau;
       while (tRem > 0 && !removed) {
         int si = find_set(m, e->valley[p], e->region[p]);
@@ -1260,7 +1450,7 @@ int orc_device_step(const orc_model_t *m, const orc_device_t *d, orc_ensemble_t 
         double newTau = -log(rng_ulog(&rng)) * orc_tau(m, e->valley[p], e->region[p]);
         tau += newTau;
         dev_force(d, e, p, ef, charge, force);
-        removed = dev_drift_particle(m, d, e, p, tRem < newTau ? tRem : newTau, force);
+        removed = dev_drift_particle(m, d, e, p, tRem < newTau ? tRem : newTau, force, &rng);
         tRem -= newTau;
       }
     }

@@ -171,7 +171,17 @@ typedef struct {
   const int32_t *region;     /* [cells], x fastest */
   const int8_t *faceContact; /* [cells][2*dim]: -2 cell not on that face, -1 artificial boundary, >= 0 contact */
   const double *doping;      /* [cells], 1/m^3 */
+  /* --- plug-in variants; all zero = emcNGPScheme + emcElectron + default specular walls --- */
+  int32_t pmScheme;       /* ORC_PM_* */
+  int32_t electronKind;   /* 0 emcElectron (ParticleType/emcElectron.hpp), 1 electronVWD (examples/mosfet2D/electronVWD.hpp) */
+  int32_t surfaceKind[6]; /* per face XMIN..ZMAX: ORC_SURFACE_* (emcScatterHandler.hpp:172-191) */
+  double surfaceParam[6]; /* specularity parameter (constant) / rms roughness height [m] (momentum dependent) */
 } orc_device_t;
+
+/* PMSchemes/emcNGPScheme.hpp, emcCICScheme.hpp, emcNECScheme.hpp, examples/mosfet2D/NECSchemeVWD.hpp */
+enum { ORC_PM_NGP = 0, ORC_PM_CIC = 1, ORC_PM_NEC = 2, ORC_PM_NEC_VWD = 3 };
+/* SurfaceScatterMechanisms/emcConstantSurfaceScatterMechanism.hpp, emcMomentumDependentSurfaceScatterMechanism.hpp */
+enum { ORC_SURFACE_SPECULAR = 0, ORC_SURFACE_CONSTANT = 1, ORC_SURFACE_MOMENTUM = 2 };
 
 int64_t orc_dev_cells(const orc_device_t *d);
 int orc_dev_is_ohmic(const orc_device_t *d, int64_t cell);     /* emcSurface.hpp isOhmicContact */
@@ -183,16 +193,26 @@ void orc_initial_potential(const orc_device_t *d, double *pot);
 /* emcSORSolver.hpp:49-128 (conc == NULL) / :131-197; returns the number of sweeps */
 int orc_sor(const orc_device_t *d, double *pot, const double *conc, double accuracyVolt, double omega, int resetBC,
             int maxSweeps);
-/* emcEFieldCalculation.hpp:13-30, :58-82; e[dim][cells] */
+/* calcEField of the device's PM scheme; e[dim][cells].  NGP / CIC: calcEFieldAtGridPts, NEC: calcEFieldAtEdgeMidPts
+ * (emcEFieldCalculation.hpp:13-82); NEC-VWD: mosfet2D/NECSchemeVWD.hpp:82-99 */
 void orc_efield(const orc_device_t *d, const double *pot, double *e);
-/* emcNGPScheme.hpp:36-47 (adds to count) */
+/* assignToMesh of the device's PM scheme (adds to count): emcNGPScheme.hpp:36-47, emcCICScheme.hpp:71-118,
+ * emcNECScheme.hpp:62-96, mosfet2D/NECSchemeVWD.hpp:39-52 */
+int orc_assign(const orc_device_t *d, int64_t n, const double *x, const double *y, const double *z, double nrCarriers,
+               double *count);
+/* the same for ORC_PM_NGP only (kept for older callers) */
 int orc_ngp_assign(const orc_device_t *d, int64_t n, const double *x, const double *y, const double *z,
                    double nrCarriers, double *count);
 /* emcSimulationResults.hpp:98-116 */
 void orc_concentration(const orc_device_t *d, const double *count, double *conc);
 /* emcAbstractParticleHandler.hpp:263-277 + emcElectron.hpp:63-73 */
 void orc_expected_at_contact(const orc_device_t *d, double *expected);
-/* emcAbstractParticleHandler.hpp:133-148 with density from the doping (usePotentialForInit = false) */
+/* particles per cell at start / expected per contact cell: emcElectron.hpp:48-73 (pot == NULL: density from the
+ * doping) or electronVWD.hpp:40-62 (rounded, always from the potential) */
+double orc_initial_nr_particles(const orc_device_t *d, int64_t cell, const double *pot);
+/* emcAbstractParticleHandler.hpp:133-148; pot == NULL: density from the doping (usePotentialForInit = false) */
+int64_t orc_device_generate_initial_pot(const orc_model_t *m, const orc_device_t *d, double nrCarriers, uint64_t *mtState,
+                                        const double *pot, orc_ensemble_t *out, int64_t capacity);
 int64_t orc_device_generate_initial(const orc_model_t *m, const orc_device_t *d, double nrCarriers, uint64_t *mtState,
                                     orc_ensemble_t *out, int64_t capacity);
 /* emcBasicParticleHandler.hpp:76-145 for one step: per-particle removed flags and per-contact counts; the

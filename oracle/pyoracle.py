@@ -364,7 +364,14 @@ class DeviceC(C.Structure):
                 ("maxPos", C.c_double * 3), ("thermalVoltage", C.c_double), ("debyeLength", C.c_double),
                 ("ni", C.c_double), ("cellVolume", C.c_double), ("epsR", C.c_double), ("nContacts", C.c_int32),
                 ("contactType", _IP), ("contactVoltage", _DP), ("gateEpsOx", _DP), ("gateThickness", _DP),
-                ("gateBarrier", _DP), ("region", _IP), ("faceContact", _I8P), ("doping", _DP)]
+                ("gateBarrier", _DP), ("region", _IP), ("faceContact", _I8P), ("doping", _DP),
+                ("pmScheme", C.c_int32), ("electronKind", C.c_int32), ("surfaceKind", C.c_int32 * 6),
+                ("surfaceParam", C.c_double * 6)]
+
+
+PM_NGP, PM_CIC, PM_NEC, PM_NEC_VWD = 0, 1, 2, 3
+SURFACE_SPECULAR, SURFACE_CONSTANT, SURFACE_MOMENTUM = 0, 1, 2
+ELECTRON_EMC, ELECTRON_VWD = 0, 1
 
 
 _DEV_BOUND = False
@@ -381,6 +388,12 @@ def _bind_device(L):
     L.orc_sor.argtypes = [dp, _DP, _DP, C.c_double, C.c_double, C.c_int, C.c_int]
     L.orc_efield.argtypes = [dp, _DP, _DP]
     L.orc_ngp_assign.argtypes = [dp, C.c_int64, _DP, _DP, _DP, C.c_double, _DP]
+    L.orc_assign.argtypes = [dp, C.c_int64, _DP, _DP, _DP, C.c_double, _DP]
+    L.orc_initial_nr_particles.restype = C.c_double
+    L.orc_initial_nr_particles.argtypes = [dp, C.c_int64, _DP]
+    L.orc_device_generate_initial_pot.restype = C.c_int64
+    L.orc_device_generate_initial_pot.argtypes = [C.c_void_p, dp, C.c_double, C.POINTER(C.c_uint64), _DP,
+                                                  C.POINTER(EnsembleC), C.c_int64]
     L.orc_concentration.argtypes = [dp, _DP, _DP]
     L.orc_expected_at_contact.argtypes = [dp, _DP]
     L.orc_device_generate_initial.restype = C.c_int64
@@ -431,6 +444,11 @@ class Device:
             self.face_contact[coords[:, d] == self.extent[d] - 1, 2 * d + 1] = -1
         self.contact_type, self.contact_voltage = [], []
         self.gate_eps, self.gate_thick, self.gate_barrier = [], [], []
+        # plug-in variants: particle-mesh scheme, electron flavour, surface scatter mechanism per face
+        self.pm_scheme = PM_NGP
+        self.electron_kind = ELECTRON_EMC
+        self.surface_kind = [SURFACE_SPECULAR] * 6
+        self.surface_param = [0.0] * 6
 
     def coords(self):
         idx = np.arange(self.cells)
@@ -493,6 +511,10 @@ class Device:
         k = self._keep
         d.contactType, d.contactVoltage, d.gateEpsOx, d.gateThickness, d.gateBarrier = _ip(k[0]), _dp(k[1]), _dp(k[2]), _dp(k[3]), _dp(k[4])
         d.region, d.faceContact, d.doping = _ip(k[5]), k[6].ctypes.data_as(_I8P), _dp(k[7])
+        d.pmScheme, d.electronKind = self.pm_scheme, self.electron_kind
+        for f in range(6):
+            d.surfaceKind[f] = self.surface_kind[f]
+            d.surfaceParam[f] = self.surface_param[f]
         return d
 
     # ---- grid operations
@@ -516,6 +538,12 @@ class Device:
         self.L.orc_ngp_assign(C.byref(self.c()), ens.n, _dp(ens.x), _dp(ens.y), _dp(ens.z), nr_carriers, _dp(count))
         return count
 
+    def assign(self, ens, nr_carriers=1.0):
+        """assignToMesh of the device's PM scheme"""
+        count = np.zeros(self.cells)
+        self.L.orc_assign(C.byref(self.c()), ens.n, _dp(ens.x), _dp(ens.y), _dp(ens.z), nr_carriers, _dp(count))
+        return count
+
     def concentration(self, count):
         conc = np.zeros(self.cells)
         self.L.orc_concentration(C.byref(self.c()), _dp(count), _dp(conc))
@@ -526,12 +554,19 @@ class Device:
         self.L.orc_expected_at_contact(C.byref(self.c()), _dp(e))
         return e
 
-    def generate_initial(self, model, mt, nr_carriers=1.0, capacity=None):
-        cap = capacity or int(self.doping.sum() * self.cell_volume * 1.2) + 1000
+    def generate_initial(self, model, mt, nr_carriers=1.0, capacity=None, pot=None):
+        """pot: normalised potential for the potential-based initial density (always used by electronVWD)"""
+        if capacity is None:
+            dev = self.c()
+            total = sum(self.L.orc_initial_nr_particles(C.byref(dev), i, _dp(pot) if pot is not None else None)
+                        for i in range(self.cells))
+            capacity = int(abs(total) * 1.2) + 1000
+        cap = capacity
         ens = Ensemble(cap)
         c = ens.c()
-        n = self.L.orc_device_generate_initial(model.h, C.byref(self.c()), nr_carriers, C.cast(mt, C.POINTER(C.c_uint64)),
-                                               C.byref(c), cap)
+        n = self.L.orc_device_generate_initial_pot(model.h, C.byref(self.c()), nr_carriers,
+                                                   C.cast(mt, C.POINTER(C.c_uint64)),
+                                                   _dp(pot) if pot is not None else None, C.byref(c), cap)
         assert n >= 0, "capacity too small"
         ens.n = int(n)
         return ens

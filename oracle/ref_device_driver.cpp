@@ -8,6 +8,10 @@
 // Built like ref_bulk_driver (overlay emcUtil.hpp with the recording RNG, -fno-access-control, no
 // OpenMP) into oracle/_ref/.  Every intermediate grid and ensemble of every step is dumped.
 //
+// Plug-in variants (--scheme ngp|cic|nec|vwd, --electron emc|vwd, --surface-ymin-const p, --surface-ymax-mom h):
+// emcNGPScheme / emcCICScheme / emcNECScheme / examples/mosfet2D/NECSchemeVWD.hpp, emcElectron /
+// examples/mosfet2D/electronVWD.hpp, emcConstantSurfaceScatterMechanism / emcMomentumDependentSurfaceScatterMechanism.
+//
 // Scenario: a 2-D silicon bar (resistor2D.cpp:73-115 with its sizes as options) with ohmic contacts
 // on the full XMIN / XMAX faces, optionally a gate on a YMIN segment and a second doping region (so
 // that the Robin boundary term, region look-ups and Coulomb tables per region are exercised).
@@ -23,20 +27,24 @@
 
 #include <SiliconFunctions.hpp> // -I $(REF)/examples
 
+#include <PMSchemes/emcCICScheme.hpp>
+#include <PMSchemes/emcNECScheme.hpp>
 #include <PMSchemes/emcNGPScheme.hpp>
 #include <ParticleHandler/emcBasicParticleHandler.hpp>
+#include <SurfaceScatterMechanisms/emcConstantSurfaceScatterMechanism.hpp>
+#include <SurfaceScatterMechanisms/emcMomentumDependentSurfaceScatterMechanism.hpp>
 #include <ParticleType/emcElectron.hpp>
 #include <PoissonSolver/emcSORSolver.hpp>
 #include <emcDevice.hpp>
 #include <emcSimulationParameter.hpp>
 #include <emcSimulationResults.hpp>
 
+#include <mosfet2D/NECSchemeVWD.hpp> // -I $(REF)/examples
+#include <mosfet2D/electronVWD.hpp>
+
 using T = double;
 const SizeType Dim = 2;
 using DeviceType = emcDevice<T, Dim>;
-using PMScheme = emcNGPScheme<T, DeviceType>;
-using Handler = emcBasicParticleHandler<T, DeviceType, PMScheme>;
-using Solver = emcSORSolver<T, DeviceType, Handler>;
 using Grid = emcGrid<T, Dim>;
 
 struct Blob {
@@ -75,7 +83,7 @@ struct Blob {
   }
 };
 
-static void dumpEnsemble(Blob &b, const std::string &p, Handler &h) {
+template <class Handler> static void dumpEnsemble(Blob &b, const std::string &p, Handler &h) {
   const auto &parts = h.particles[0];
   const auto &pos = h.positionsParticles[0];
   const size_t n = parts.size();
@@ -98,37 +106,30 @@ static void dumpEnsemble(Blob &b, const std::string &p, Handler &h) {
   b.i64(p + "idx", idx, {n, 3});
 }
 
-int main(int argc, char **argv) {
+struct Options {
   double lx = 2e-7, ly = 1e-7, hx = 1e-8, hy = 2.5e-8, width = 1e-6, doping = 1e22, doping2 = 0, voltage = 0.05,
-         dt = 1e-15, acc = 1e-4, omega = 1.8, emax = 4.0, gateVoltage = 0.5;
+         dt = 1e-15, acc = 1e-4, omega = 1.8, emax = 4.0, gateVoltage = 0.5, surfYminConst = -1, surfYmaxMom = -1;
   int steps = 10, levels = 1000, gate = 0;
   unsigned long seed = 5;
-  std::string out = "device.blob";
-  for (int i = 1; i + 1 < argc; i += 2) {
-    std::string k = argv[i], v = argv[i + 1];
-    if (k == "--lx") lx = std::stod(v);
-    else if (k == "--ly") ly = std::stod(v);
-    else if (k == "--hx") hx = std::stod(v);
-    else if (k == "--hy") hy = std::stod(v);
-    else if (k == "--width") width = std::stod(v);
-    else if (k == "--doping") doping = std::stod(v);
-    else if (k == "--doping2") doping2 = std::stod(v); // right half of the bar, second region
-    else if (k == "--voltage") voltage = std::stod(v);
-    else if (k == "--dt") dt = std::stod(v);
-    else if (k == "--acc") acc = std::stod(v);
-    else if (k == "--omega") omega = std::stod(v);
-    else if (k == "--steps") steps = std::stoi(v);
-    else if (k == "--levels") levels = std::stoi(v);
-    else if (k == "--emax") emax = std::stod(v);
-    else if (k == "--gate") gate = std::stoi(v); // 1: gate contact on the middle third of YMIN
-    else if (k == "--gate-voltage") gateVoltage = std::stod(v);
-    else if (k == "--seed") seed = std::stoul(v);
-    else if (k == "--out") out = v;
-    else {
-      std::cerr << "unknown option " << k << "\n";
-      return 2;
-    }
-  }
+  std::string out = "device.blob", scheme = "ngp", electron = "emc";
+};
+
+template <class Electron> std::unique_ptr<Electron> makeElectron(const Options &o);
+template <> std::unique_ptr<emcElectron<T, DeviceType>> makeElectron(const Options &o) {
+  return std::make_unique<emcElectron<T, DeviceType>>(o.levels, o.emax, false);
+}
+template <> std::unique_ptr<electronVWD<T, DeviceType>> makeElectron(const Options &o) {
+  return std::make_unique<electronVWD<T, DeviceType>>(o.levels, o.emax);
+}
+
+template <class PMScheme, class Electron> int run(const Options &o) {
+  using Handler = emcBasicParticleHandler<T, DeviceType, PMScheme>;
+  using Solver = emcSORSolver<T, DeviceType, Handler>;
+  const double lx = o.lx, ly = o.ly, hx = o.hx, hy = o.hy, width = o.width, doping = o.doping, doping2 = o.doping2,
+               voltage = o.voltage, dt = o.dt, acc = o.acc, omega = o.omega, emax = o.emax, gateVoltage = o.gateVoltage;
+  const int steps = o.steps, levels = o.levels, gate = o.gate;
+  const unsigned long seed = o.seed;
+  const std::string out = o.out;
   std::vector<std::uint64_t> draws;
   RecordingRNG::sink() = &draws;
   std::streambuf *oldBuf = std::cout.rdbuf();
@@ -153,12 +154,20 @@ int main(int argc, char **argv) {
   emcSimulationParameter<T, DeviceType> param;
   param.setTimes(steps * dt, dt, 0);
   param.setNrStepsForFinalAvg(0);
-  auto electrons = std::make_unique<emcElectron<T, DeviceType>>(levels, emax, false);
+  auto electrons = makeElectron<Electron>(o);
   Silicon::addXValley(electrons);
   Silicon::addAcousticScattering(0, electrons, device, regions);
   Silicon::addZeroOrderInterValleyScattering(0, electrons, device, regions);
   Silicon::addFirstOrderInterValleyScattering(0, electrons, device, regions);
   Silicon::addCoulombScattering(0, electrons, device, regions);
+  if (o.surfYminConst >= 0)
+    electrons->setSurfaceScatterMechanism(
+        emcBoundaryPos::YMIN,
+        std::make_unique<emcConstantSurfaceScatterMechanism<T, DeviceType>>(o.surfYminConst, device.getMaxPos()));
+  if (o.surfYmaxMom >= 0)
+    electrons->setSurfaceScatterMechanism(
+        emcBoundaryPos::YMAX,
+        std::make_unique<emcMomentumDependentSurfaceScatterMechanism<T, DeviceType>>(o.surfYmaxMom, device.getMaxPos()));
   param.addParticleType(std::move(electrons));
   Handler handler(device, pmScheme, param.particleTypes, param.nrCarriersPerPart, seed);
   emcSimulationResults<T, DeviceType> results(device, param);
@@ -273,9 +282,51 @@ int main(int argc, char **argv) {
   blob.u64("draw_marks", drawMarks);
   blob.u64("draws", draws);
   blob.f64("params", {lx, ly, hx, hy, width, doping, doping2, voltage, dt, acc, omega, (double)steps, (double)levels,
-                      emax, (double)gate, gateVoltage, (double)seed});
+                      emax, (double)gate, gateVoltage, (double)seed, o.surfYminConst, o.surfYmaxMom});
   std::cout.rdbuf(oldBuf);
   std::cout << "ref_device_driver: grid " << nx << "x" << ny << ", " << handler.getNrParticles(0) << " particles after "
             << steps << " steps, " << draws.size() << " draws -> " << out << "\n";
   return 0;
+}
+
+int main(int argc, char **argv) {
+  Options o;
+  for (int i = 1; i + 1 < argc; i += 2) {
+    std::string k = argv[i], v = argv[i + 1];
+    if (k == "--lx") o.lx = std::stod(v);
+    else if (k == "--ly") o.ly = std::stod(v);
+    else if (k == "--hx") o.hx = std::stod(v);
+    else if (k == "--hy") o.hy = std::stod(v);
+    else if (k == "--width") o.width = std::stod(v);
+    else if (k == "--doping") o.doping = std::stod(v);
+    else if (k == "--doping2") o.doping2 = std::stod(v); // right half of the bar, second region
+    else if (k == "--voltage") o.voltage = std::stod(v);
+    else if (k == "--dt") o.dt = std::stod(v);
+    else if (k == "--acc") o.acc = std::stod(v);
+    else if (k == "--omega") o.omega = std::stod(v);
+    else if (k == "--steps") o.steps = std::stoi(v);
+    else if (k == "--levels") o.levels = std::stoi(v);
+    else if (k == "--emax") o.emax = std::stod(v);
+    else if (k == "--gate") o.gate = std::stoi(v); // 1: gate contact on the middle third of YMIN
+    else if (k == "--gate-voltage") o.gateVoltage = std::stod(v);
+    else if (k == "--seed") o.seed = std::stoul(v);
+    else if (k == "--out") o.out = v;
+    else if (k == "--scheme") o.scheme = v;
+    else if (k == "--electron") o.electron = v;
+    else if (k == "--surface-ymin-const") o.surfYminConst = std::stod(v); // specularity parameter
+    else if (k == "--surface-ymax-mom") o.surfYmaxMom = std::stod(v);     // rms roughness height [m]
+    else {
+      std::cerr << "unknown option " << k << "\n";
+      return 2;
+    }
+  }
+  using E = emcElectron<T, DeviceType>;
+  using V = electronVWD<T, DeviceType>;
+  const bool vwd = o.electron == "vwd";
+  if (o.scheme == "ngp") return vwd ? run<emcNGPScheme<T, DeviceType>, V>(o) : run<emcNGPScheme<T, DeviceType>, E>(o);
+  if (o.scheme == "cic") return vwd ? run<emcCICScheme<T, DeviceType>, V>(o) : run<emcCICScheme<T, DeviceType>, E>(o);
+  if (o.scheme == "nec") return vwd ? run<emcNECScheme<T, DeviceType>, V>(o) : run<emcNECScheme<T, DeviceType>, E>(o);
+  if (o.scheme == "vwd") return vwd ? run<emcNECSchemeVWD<T, DeviceType>, V>(o) : run<emcNECSchemeVWD<T, DeviceType>, E>(o);
+  std::cerr << "unknown scheme " << o.scheme << "\n";
+  return 2;
 }

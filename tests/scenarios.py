@@ -107,7 +107,18 @@ DEVICE_CASES = {
                        steps=10, levels=1000, emax=4.0, gate=0, seed=5),
     "device_gate": dict(lx=3e-7, ly=1e-7, hx=1e-8, hy=2e-8, doping=2e22, doping2=5e21, voltage=0.3, dt=5e-16,
                         steps=6, levels=500, emax=4.0, gate=1, seed=9),
+    # plug-in variants: particle-mesh scheme (emcCICScheme / emcNECScheme / mosfet2D's NECSchemeVWD), the electron
+    # flavour of mosfet2D (electronVWD) and rough walls (constant specularity on YMIN, momentum dependent on YMAX)
+    "device_cic": {"lx": 2e-7, "ly": 1e-7, "hx": 1e-8, "hy": 2.5e-8, "doping": 1e22, "doping2": 0, "voltage": 0.05,
+                   "dt": 1e-15, "steps": 6, "levels": 1000, "emax": 4.0, "gate": 0, "seed": 21, "scheme": "cic",
+                   "surface-ymin-const": 0.3, "surface-ymax-mom": 2e-9},
+    "device_nec": {"lx": 3e-7, "ly": 1e-7, "hx": 1e-8, "hy": 2e-8, "doping": 2e22, "doping2": 5e21, "voltage": 0.3,
+                   "dt": 5e-16, "steps": 5, "levels": 500, "emax": 4.0, "gate": 1, "seed": 22, "scheme": "nec"},
+    "device_vwd": {"lx": 3e-7, "ly": 1e-7, "hx": 1e-8, "hy": 2e-8, "doping": 2e22, "doping2": 5e21, "voltage": 0.3,
+                   "dt": 5e-16, "steps": 5, "levels": 500, "emax": 4.0, "gate": 1, "seed": 23, "scheme": "vwd",
+                   "electron": "vwd", "surface-ymin-const": 0.5},
 }
+PM_SCHEMES = {"ngp": po.PM_NGP, "cic": po.PM_CIC, "nec": po.PM_NEC, "vwd": po.PM_NEC_VWD}
 
 
 def build_device(case: str):
@@ -122,6 +133,12 @@ def build_device(case: str):
     dev.add_contact(0, po.CONTACT_OHMIC, a["voltage"], [0.0], [a["ly"]])
     if a["gate"]:
         dev.add_contact(2, po.CONTACT_GATE, 0.5, [a["lx"] / 3], [2 * a["lx"] / 3], 3.9, 1.2e-9, 1.15 / 2)
+    dev.pm_scheme = PM_SCHEMES[a.get("scheme", "ngp")]
+    dev.electron_kind = po.ELECTRON_VWD if a.get("electron") == "vwd" else po.ELECTRON_EMC
+    if "surface-ymin-const" in a:
+        dev.surface_kind[2], dev.surface_param[2] = po.SURFACE_CONSTANT, a["surface-ymin-const"]
+    if "surface-ymax-mom" in a:
+        dev.surface_kind[3], dev.surface_param[3] = po.SURFACE_MOMENTUM, a["surface-ymax-mom"]
     m = po.Model(a["levels"], a["emax"], 300.0, 2329.0, 9040.0)
     m.add_valley(po.VALLEY_NONPARABOLIC_ANISO, [0.916, 0.196, 0.196], 3, 0.5, 0.0, SI_DIRS)
     dop = [a["doping"], a["doping2"]]

@@ -61,11 +61,12 @@ def test_equilibrium_chain_bit_for_bit(case):
     e = dev.efield(pot)
     assert np.array_equal(e[0], g["ex_eq"].ravel()) and np.array_equal(e[1], g["ey_eq"].ravel())
     mt = po.mt_state(a["seed"])
-    ens = dev.generate_initial(m, mt)
+    # electronVWD always starts from the equilibrium potential; emcElectron(usePotentialForInit = false) from the doping
+    ens = dev.generate_initial(m, mt, pot=pot if a.get("electron") == "vwd" else None)
     ref = ens_from(g, "init_")
     assert_same_ensemble(ens, ref, "initial ensemble")
-    count = dev.ngp_assign(ens)
-    assert np.array_equal(count, g["count_eq"].ravel()) and count.sum() == ens.n
+    count = dev.assign(ens)
+    assert np.array_equal(count, g["count_eq"].ravel()) and abs(count.sum() - ens.n) <= 1e-9 * ens.n
     assert np.array_equal(dev.concentration(count), g["conc_eq"].ravel())
 
 
@@ -85,7 +86,7 @@ def test_emc_steps_bit_for_bit(case):
     for _ in range(int(g["draws_init_count"][0])):
         po.lib().orc_mt_next(mt)
     ens = ens_from(g, "init_")
-    cap = ens.n + 200
+    cap = ens.n + 2000
     big = po.Ensemble(cap)
     for f in po.Ensemble.F64 + po.Ensemble.I32:
         getattr(big, f)[: ens.n] = getattr(ens, f)
@@ -107,7 +108,7 @@ def test_emc_steps_bit_for_bit(case):
         net = dev.contacts(m, ens, expected, mt)
         assert np.array_equal(net, g[p + "net_injected_per_contact"]), f"step {s}: contacts"
         assert_same_ensemble(ens, ens_from(g, p + "post_"), f"step {s}: after contacts")
-        count = dev.ngp_assign(ens)
+        count = dev.assign(ens)
         assert np.array_equal(count, g[p + "count"].ravel())
         conc = dev.concentration(count)
         assert np.array_equal(conc, g[p + "conc"].ravel())
