@@ -229,11 +229,23 @@ int64_t emcgpu_get_step_index(const emcgpu_ctx *ctx);
  * The box device with its doping regions and contacts crosses the boundary as flat arrays: */
 #define EMCGPU_MAX_CONTACTS 16
 typedef enum { EMCGPU_CONTACT_OHMIC = 0, EMCGPU_CONTACT_SCHOTTKY = 1, EMCGPU_CONTACT_GATE = 2 } emcgpu_contact_type;
+/* particle-mesh schemes: include/PMSchemes/emcNGPScheme.hpp, emcCICScheme.hpp, emcNECScheme.hpp (2-D) and
+ * examples/mosfet2D/NECSchemeVWD.hpp (2-D).  The scheme selects the variants of the charge-assignment kernel, of the
+ * force gather in the particle step and of E = -grad(phi). */
+typedef enum { EMCGPU_PM_NGP = 0, EMCGPU_PM_CIC = 1, EMCGPU_PM_NEC = 2, EMCGPU_PM_NEC_VWD = 3 } emcgpu_pm_scheme;
+/* wall mechanisms per face: none = the specular reflection of emcScatterHandler.hpp:172-191;
+ * SurfaceScatterMechanisms/emcConstantSurfaceScatterMechanism.hpp (parameter: specularity),
+ * emcMomentumDependentSurfaceScatterMechanism.hpp (parameter: rms roughness height [m]) */
+typedef enum { EMCGPU_SURFACE_SPECULAR = 0, EMCGPU_SURFACE_CONSTANT = 1, EMCGPU_SURFACE_MOMENTUM_DEPENDENT = 2 } emcgpu_surface_kind;
+/* creation rules of injected particles: ParticleType/emcElectron.hpp:92-104 or examples/mosfet2D/electronVWD.hpp:78-90
+ * (valley draws from U[0,1), tau looked up with the valley index as region) */
+typedef enum { EMCGPU_PARTICLE_ELECTRON = 0, EMCGPU_PARTICLE_ELECTRON_VWD = 1 } emcgpu_particle_kind;
+
 typedef struct {
   int32_t dim; /* 2 or 3 */
   int32_t nContacts;
   int32_t extent[3];   /* grid points per dimension (emcDevice::getGridExtent) */
-  int32_t reserved;
+  int32_t pmScheme;    /* emcgpu_pm_scheme */
   double spacing[3];   /* [m] */
   double maxPos[3];    /* [m] */
   double thermalVoltage, debyeLength, ni, cellVolume, epsR; /* emcDevice.hpp:87-90, :333-343 */
@@ -266,6 +278,11 @@ typedef enum {
  * emcElectron.hpp:63-73) is the population the contact cells are kept at. */
 int emcgpu_device_configure(emcgpu_ctx *ctx, const emcgpu_device_t *device, double charge, double nrCarriersPerParticle,
                             const double *expected, int mathMode);
+/* emcParticleType::setSurfaceScatterMechanism (emcParticleType.hpp:159-166): wall mechanism of one face
+ * (0 XMIN, 1 XMAX, 2 YMIN, 3 YMAX, 4 ZMIN, 5 ZMAX) */
+int emcgpu_device_set_surface(emcgpu_ctx *ctx, int face, int kind, double parameter);
+/* which generateInjectedParticle the contacts use (emcgpu_particle_kind) */
+int emcgpu_device_set_particle_kind(emcgpu_ctx *ctx, int kind);
 int emcgpu_device_set_grid(emcgpu_ctx *ctx, int grid, const double *host);
 int emcgpu_device_get_grid(emcgpu_ctx *ctx, int grid, double *host);
 /* room for particles injected at contacts: the ensemble is re-allocated for at least this many */

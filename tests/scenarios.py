@@ -115,7 +115,7 @@ DEVICE_CASES = {
     "device_nec": {"lx": 3e-7, "ly": 1e-7, "hx": 1e-8, "hy": 2e-8, "doping": 2e22, "doping2": 5e21, "voltage": 0.3,
                    "dt": 5e-16, "steps": 5, "levels": 500, "emax": 4.0, "gate": 1, "seed": 22, "scheme": "nec"},
     "device_vwd": {"lx": 3e-7, "ly": 1e-7, "hx": 1e-8, "hy": 2e-8, "doping": 2e22, "doping2": 5e21, "voltage": 0.3,
-                   "dt": 5e-16, "steps": 5, "levels": 500, "emax": 4.0, "gate": 1, "seed": 23, "scheme": "vwd",
+                   "dt": 2e-15, "steps": 4, "levels": 500, "emax": 4.0, "gate": 1, "seed": 23, "scheme": "vwd",
                    "electron": "vwd", "surface-ymin-const": 0.5},
 }
 PM_SCHEMES = {"ngp": po.PM_NGP, "cic": po.PM_CIC, "nec": po.PM_NEC, "vwd": po.PM_NEC_VWD}

@@ -23,6 +23,9 @@ STREAM_NAMES = ("kx", "ky", "kz", "energy", "tau", "x", "y", "z")
 OK, E_INVALID, E_CUDA, E_UNSUPPORTED_MECHANISM, E_UNSUPPORTED_VALLEY, E_CAPACITY, E_REPLAY_EXHAUSTED = range(7)
 SAMPLER_NONE, SAMPLER_ISOTROPIC_ELASTIC, SAMPLER_INTERVALLEY, SAMPLER_COULOMB = range(4)
 MATH_EXACT, MATH_FAST = 0, 1
+PM_NGP, PM_CIC, PM_NEC, PM_NEC_VWD = 0, 1, 2, 3
+SURFACE_SPECULAR, SURFACE_CONSTANT, SURFACE_MOMENTUM_DEPENDENT = 0, 1, 2
+PARTICLE_ELECTRON, PARTICLE_ELECTRON_VWD = 0, 1
 
 _DP = C.POINTER(C.c_double)
 
@@ -96,6 +99,8 @@ def load():
     L.emcgpu_event_log_read.restype = C.c_int64
     IP32 = C.POINTER(C.c_int32)
     L.emcgpu_device_configure.argtypes = [vp, C.POINTER(DeviceC), C.c_double, C.c_double, _DP, C.c_int]
+    L.emcgpu_device_set_surface.argtypes = [vp, C.c_int, C.c_int, C.c_double]
+    L.emcgpu_device_set_particle_kind.argtypes = [vp, C.c_int]
     L.emcgpu_device_set_grid.argtypes = [vp, C.c_int, _DP]
     L.emcgpu_device_get_grid.argtypes = [vp, C.c_int, _DP]
     L.emcgpu_device_reserve.argtypes = [vp, C.c_int64]
@@ -113,7 +118,7 @@ def load():
 
 
 class DeviceC(C.Structure):
-    _fields_ = [("dim", C.c_int32), ("nContacts", C.c_int32), ("extent", C.c_int32 * 3), ("reserved", C.c_int32),
+    _fields_ = [("dim", C.c_int32), ("nContacts", C.c_int32), ("extent", C.c_int32 * 3), ("pmScheme", C.c_int32),
                 ("spacing", C.c_double * 3), ("maxPos", C.c_double * 3), ("thermalVoltage", C.c_double),
                 ("debyeLength", C.c_double), ("ni", C.c_double), ("cellVolume", C.c_double), ("epsR", C.c_double),
                 ("contactType", C.POINTER(C.c_int32)), ("contactVoltage", _DP), ("gateEpsOx", _DP),
@@ -132,7 +137,7 @@ EXPORTED_SYMBOLS = [
     "emcgpu_ensemble_device_ptrs", "emcgpu_rng_philox", "emcgpu_rng_replay", "emcgpu_bulk_configure",
     "emcgpu_bulk_step", "emcgpu_bulk_step_device", "emcgpu_bulk_observables", "emcgpu_set_step_index",
     "emcgpu_get_step_index", "emcgpu_event_log_enable", "emcgpu_event_log_read",
-    "emcgpu_device_configure", "emcgpu_device_set_grid", "emcgpu_device_get_grid", "emcgpu_device_reserve",
+    "emcgpu_device_configure", "emcgpu_device_set_surface", "emcgpu_device_set_particle_kind", "emcgpu_device_set_grid", "emcgpu_device_get_grid", "emcgpu_device_reserve",
     "emcgpu_device_poisson", "emcgpu_device_efield", "emcgpu_device_assign", "emcgpu_device_concentration",
     "emcgpu_device_step", "emcgpu_device_contacts", "emcgpu_device_run", "emcgpu_device_run_averaging",
 ]
@@ -294,9 +299,9 @@ class Context:
     # -- device run
     def device_configure(self, dim, extent, spacing, max_pos, thermal_voltage, debye_length, ni, cell_volume, eps_r,
                          contact_type, contact_voltage, gate_eps, gate_thickness, gate_barrier, region, face_contact,
-                         doping, charge=-1.60219e-19, nr_carriers=1.0, expected=None, math_mode=MATH_EXACT):
+                         doping, charge=-1.60219e-19, nr_carriers=1.0, expected=None, math_mode=MATH_EXACT, pm_scheme=PM_NGP):
         d = DeviceC()
-        d.dim, d.nContacts = dim, len(contact_type)
+        d.dim, d.nContacts, d.pmScheme = dim, len(contact_type), pm_scheme
         for i in range(3):
             d.extent[i] = extent[i] if i < dim else 1
             d.spacing[i] = spacing[i] if i < dim else 1.0
@@ -316,6 +321,12 @@ class Context:
                                                  exp.ctypes.data_as(_DP) if exp is not None else None, math_mode))
         self.n_cells = int(np.prod(extent[:dim]))
         self.n_contacts = len(contact_type)
+
+    def device_set_surface(self, face, kind, parameter):
+        self._chk(self.L.emcgpu_device_set_surface(self.h, face, kind, parameter))
+
+    def device_set_particle_kind(self, kind):
+        self._chk(self.L.emcgpu_device_set_particle_kind(self.h, kind))
 
     def device_set_grid(self, grid, values):
         v = np.ascontiguousarray(values, dtype=np.float64).ravel()

@@ -38,7 +38,14 @@ struct DevGeometry {
   const double *doping;      // [cells], 1/m^3
   const double *dopingNorm;  // [cells], doping / Ni (emcDevice::normalizeDoping)
   const uint8_t *cellKind;   // [cells]: bit 0 reservoir contact cell (ohmic / Schottky), bit 1 has a gate face
+  // plug-in variants (include/emcgpu.h): particle-mesh scheme, particle creation rules, wall mechanisms per face
+  int32_t pmScheme;          // EMCGPU_PM_*
+  int32_t particleKind;      // EMCGPU_PARTICLE_*
+  int32_t surfaceKind[6];    // EMCGPU_SURFACE_* per face XMIN .. ZMAX
+  double surfaceParam[6];
 };
+enum { PM_NGP = 0, PM_CIC = 1, PM_NEC = 2, PM_NEC_VWD = 3 };
+enum { SURFACE_SPECULAR = 0, SURFACE_CONSTANT = 1, SURFACE_MOMENTUM = 2 };
 
 __device__ __forceinline__ void cellCoord(const DevGeometry &g, int cell, int c[3]) {
   c[0] = cell % g.extent[0];
@@ -50,6 +57,12 @@ __device__ __forceinline__ int cellContact(const DevGeometry &g, int cell) {
   const int8_t *fc = g.faceContact + cell * 2 * g.dim;
   for (int f = 0; f < 2 * g.dim; f++)
     if (fc[f] != -2) return fc[f];
+  return -1;
+}
+__device__ __forceinline__ int cellFirstFace(const DevGeometry &g, int cell) {
+  const int8_t *fc = g.faceContact + cell * 2 * g.dim;
+  for (int f = 0; f < 2 * g.dim; f++)
+    if (fc[f] != -2) return f;
   return -1;
 }
 __device__ __forceinline__ bool cellIsOhmic(const DevGeometry &g, int cell) {
@@ -64,6 +77,23 @@ __device__ __forceinline__ bool cellIsReservoir(const DevGeometry &g, int cell) 
 __device__ __forceinline__ int posToCell(const DevGeometry &g, double x, double y, double z) {
   int cell = (int)round(__ddiv_rn(x, g.spacing[0])) + g.extent[0] * (int)round(__ddiv_rn(y, g.spacing[1]));
   if (g.dim > 2) cell += g.extent[0] * g.extent[1] * (int)round(__ddiv_rn(z, g.spacing[2]));
+  return cell;
+}
+// lower grid point of the mesh cell a position lies in (floor(pos / spacing)) and the distance from it in cell units:
+// CIC / NEC schemes.  The index is kept inside the grid so that the upper neighbours exist (the reference aborts for a
+// particle exactly on the max face).
+__device__ __forceinline__ int posToLowerCell(const DevGeometry &g, const double pos[3], double w[3], int c[3]) {
+  int cell = 0, stride = 1;
+  c[0] = c[1] = c[2] = 0;
+  w[0] = w[1] = w[2] = 0.0;
+  for (int i = 0; i < g.dim; i++) {
+    const double q = __ddiv_rn(pos[i], g.spacing[i]);
+    const double f = floor(q);
+    w[i] = __dsub_rn(q, f);
+    c[i] = max(0, min((int)f, g.extent[i] - 2));
+    cell += stride * c[i];
+    stride *= g.extent[i];
+  }
   return cell;
 }
 
@@ -153,27 +183,38 @@ __global__ void concentrationKernel(const __grid_constant__ DevGeometry G, const
   if (cell < G.cells) conc[cell] = cellConcentration(G, cell, count[cell]);
 }
 
-// E = -grad(phi) with the reference's boundary rules (calcEFieldAtGridPts + setEFieldBoundaryValues,
-// emcEFieldCalculation.hpp:13-30, :58-82).  Interior: Vt (phi[prev] - phi[next]) / (2 h); on a face: 0
-// (artificial boundary) or the inner neighbour's value (contact).
+// E = -grad(phi), calcEField of the particle-mesh scheme.
+//   NGP, CIC: calcEFieldAtGridPts (emcEFieldCalculation.hpp:13-30): Vt (phi[prev] - phi[next]) / (2 h) in the interior;
+//   NEC:      calcEFieldAtEdgeMidPts (:35-53): Vt (phi[here] - phi[next]) / h in the interior;
+//   both with setEFieldBoundaryValues (:58-82): on a face 0 (artificial boundary) or the inner neighbour's value (contact);
+//   NEC-VWD:  examples/mosfet2D/NECSchemeVWD.hpp:82-99: forward difference everywhere, 0 on the max face.
 __device__ __forceinline__ void cellEField(const DevGeometry &G, int cell, const double *pot, double *e) {
   int c[3];
   cellCoord(G, cell, c);
   const int stride[3] = {1, G.extent[0], G.extent[0] * G.extent[1]};
   for (int i = 0; i < G.dim; i++) {
-    int at = cell; // the cell whose central difference this cell reports
-    bool zero = false;
-    if (c[i] == 0) {
-      zero = G.faceContact[cell * 2 * G.dim + 2 * i] == -1;
-      at = cell + stride[i];
-    } else if (c[i] == G.extent[i] - 1) {
-      zero = G.faceContact[cell * 2 * G.dim + 2 * i + 1] == -1;
-      at = cell - stride[i];
-    }
     double v = 0.0;
-    if (!zero)
-      v = __ddiv_rn(__dmul_rn(__dsub_rn(pot[at - stride[i]], pot[at + stride[i]]), G.thermalVoltage),
-                    __dmul_rn(2.0, G.spacing[i]));
+    if (G.pmScheme == PM_NEC_VWD) {
+      if (c[i] != G.extent[i] - 1)
+        v = __ddiv_rn(__dmul_rn(__dsub_rn(pot[cell], pot[cell + stride[i]]), G.thermalVoltage), G.spacing[i]);
+    } else {
+      int at = cell; // the cell whose difference quotient this cell reports
+      bool zero = false;
+      if (c[i] == 0) {
+        zero = G.faceContact[cell * 2 * G.dim + 2 * i] == -1;
+        at = cell + stride[i];
+      } else if (c[i] == G.extent[i] - 1) {
+        zero = G.faceContact[cell * 2 * G.dim + 2 * i + 1] == -1;
+        at = cell - stride[i];
+      }
+      if (!zero) {
+        if (G.pmScheme == PM_NEC)
+          v = __ddiv_rn(__dmul_rn(__dsub_rn(pot[at], pot[at + stride[i]]), G.thermalVoltage), G.spacing[i]);
+        else
+          v = __ddiv_rn(__dmul_rn(__dsub_rn(pot[at - stride[i]], pot[at + stride[i]]), G.thermalVoltage),
+                        __dmul_rn(2.0, G.spacing[i]));
+      }
+    }
     e[(size_t)i * G.cells + cell] = v;
   }
 }
@@ -212,16 +253,48 @@ __global__ void __launch_bounds__(256) ngpAssignKernel(const __grid_constant__ D
   const int lane = threadIdx.x & 31;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t nRounded = (n + 31) & ~int64_t(31);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nRounded; i += stride) {
-    const bool live = i < n;
-    const int cell = live ? posToCell(G, A.x[i], A.y[i], G.dim > 2 ? A.z[i] : 0.0) : -1;
-    const unsigned peers = __match_any_sync(0xffffffffu, cell);
-    if (live && lane == __ffs(peers) - 1) {
-      const double add = A.nrCarriers * __popc(peers);
-      if (A.useSmem)
-        atomicAdd(&sCount[cell], add);
-      else
-        atomicAdd(&A.count[cell], add);
+  double *target = A.useSmem ? sCount : A.count;
+  if (G.pmScheme == PM_NGP) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nRounded; i += stride) {
+      const bool live = i < n;
+      const int cell = live ? posToCell(G, A.x[i], A.y[i], G.dim > 2 ? A.z[i] : 0.0) : -1;
+      const unsigned peers = __match_any_sync(0xffffffffu, cell);
+      if (live && lane == __ffs(peers) - 1) atomicAdd(&target[cell], A.nrCarriers * __popc(peers));
+    }
+  } else {
+    // CIC (emcCICScheme.hpp:71-118: the distance from the LOWER point weights the lower point) and NEC / NEC-VWD
+    // (emcNECScheme.hpp:62-96, NECSchemeVWD.hpp:39-52: equal shares) deposit on the 2^dim corners of the mesh cell.
+    // NEC shares are multiples of 1/8, so those sums are exact in any order; CIC sums depend on the order of the
+    // atomics in the last bits.
+    const int sy = G.extent[0], sz = G.extent[0] * G.extent[1];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      const double pos[3] = {A.x[i], A.y[i], G.dim > 2 ? A.z[i] : 0.0};
+      double w[3];
+      int c[3];
+      const int base = posToLowerCell(G, pos, w, c);
+      if (G.pmScheme == PM_CIC) {
+        const double wX = w[0], wY = w[1], wZ = w[2], uX = __dsub_rn(1.0, wX), uY = __dsub_rn(1.0, wY), uZ = __dsub_rn(1.0, wZ);
+        if (G.dim == 2) {
+          atomicAdd(&target[base], __dmul_rn(__dmul_rn(wX, wY), A.nrCarriers));
+          atomicAdd(&target[base + 1], __dmul_rn(__dmul_rn(uX, wY), A.nrCarriers));
+          atomicAdd(&target[base + sy], __dmul_rn(__dmul_rn(wX, uY), A.nrCarriers));
+          atomicAdd(&target[base + 1 + sy], __dmul_rn(__dmul_rn(uX, uY), A.nrCarriers));
+        } else {
+          atomicAdd(&target[base], __dmul_rn(__dmul_rn(__dmul_rn(wX, wY), wZ), A.nrCarriers));
+          atomicAdd(&target[base + 1], __dmul_rn(__dmul_rn(__dmul_rn(uX, wY), wZ), A.nrCarriers));
+          atomicAdd(&target[base + sy], __dmul_rn(__dmul_rn(__dmul_rn(wX, uY), wZ), A.nrCarriers));
+          atomicAdd(&target[base + 1 + sy], __dmul_rn(__dmul_rn(__dmul_rn(uX, uY), wZ), A.nrCarriers));
+          atomicAdd(&target[base + sz], __dmul_rn(__dmul_rn(__dmul_rn(wX, wY), uZ), A.nrCarriers));
+          atomicAdd(&target[base + 1 + sz], __dmul_rn(__dmul_rn(__dmul_rn(uX, wY), uZ), A.nrCarriers));
+          atomicAdd(&target[base + sy + sz], __dmul_rn(__dmul_rn(__dmul_rn(wX, uY), uZ), A.nrCarriers));
+          atomicAdd(&target[base + 1 + sy + sz], __dmul_rn(__dmul_rn(__dmul_rn(uX, uY), uZ), A.nrCarriers));
+        }
+      } else {
+        const double share = __dmul_rn(G.dim == 2 ? 0.25 : 0.125, A.nrCarriers);
+        for (int dz = 0; dz < (G.dim > 2 ? 2 : 1); dz++)
+          for (int dy = 0; dy < 2; dy++)
+            for (int dx = 0; dx < 2; dx++) atomicAdd(&target[base + dx + dy * sy + dz * sz], share);
+      }
     }
   }
   if (A.useSmem) {
@@ -783,9 +856,74 @@ struct DeviceStepParams {
   RunCtl *ctl;       // n, step index, removedPerContact
 };
 
-template <bool EXACT, int DIM>
+// emcSurfaceScatterMechanism (SurfaceScatterMechanisms/emcSurfaceScatterMechanism.hpp): with probability pDiff the
+// particle leaves the wall in a new direction (polar angle theta from the wall normal, azimuth phi), otherwise -- and
+// after that in any case -- it is reflected; unlike the default reflection of the scatter handler this one only turns
+// k where it points out of the device (:81-93).
+//   constant (emcConstantSurfaceScatterMechanism.hpp):  pDiff = 1 - specularity, theta = asin(sqrt(r))
+//   momentum dependent (emcMomentumDependentSurfaceScatterMechanism.hpp): pDiff = 1 - exp(-(2 h k_perp)^2),
+//     theta from a Newton iteration on the cumulative distribution (:39-68)
+__device__ __forceinline__ double surfaceSolveTheta(double r, double height, double speed) {
+  const double t = 2.0 * height * speed, c = t * t;
+  const double ee = exp(-c);
+  double x = sqrt(r * (1.0 / (1.0 - ee) - 1.0 / c));
+  double error = 1.0;
+  int it = 0;
+  while (error > 1e-10 && it < 10000) {
+    double si, co;
+    sincos(x, &si, &co);
+    const double ecos = exp(-c * (co * co));
+    const double esin = exp(-c * (si * si));
+    const double x1 = x - (((ee - ecos) / c + si * si - r * (1.0 - (1.0 - ee) / c)) * (2.0 * esin * c * si * co * (ecos - 1.0)) /
+                           (ee * (c - 1.0) - 1.0));
+    error = fabs(x1 - x);
+    x = x1;
+    it++;
+  }
+  return x;
+}
+
+template <int RNG_MODE, int DIM>
+__device__ __forceinline__ void surfaceScatter(const DevGeometry &G, int face, double pos[3], double k[3], Rng &rng) {
+  const int kind = G.surfaceKind[face];
+  const int perp = face >> 1;
+  double pDiff;
+  if (kind == SURFACE_CONSTANT) {
+    pDiff = 1.0 - G.surfaceParam[face];
+  } else {
+    const double t = 2.0 * G.surfaceParam[face] * k[perp];
+    pDiff = 1.0 - exp(-(t * t));
+  }
+  if (uniform01(rng.raw<RNG_MODE>()) < pDiff) {
+    const double speed = sqrt(k[0] * k[0] + k[1] * k[1] + k[2] * k[2]);
+    double theta;
+    if (kind == SURFACE_CONSTANT)
+      theta = asin(sqrt(uniform01(rng.raw<RNG_MODE>())));
+    else
+      theta = surfaceSolveTheta(uniform01(rng.raw<RNG_MODE>()), G.surfaceParam[face], speed);
+    const double phi = 2.0 * 3.14159265358979323846 * uniform01(rng.raw<RNG_MODE>());
+    double st, ct, sp, cp;
+    sincos(theta, &st, &ct);
+    sincos(phi, &sp, &cp);
+    k[perp] = speed * ct * ((face & 1) ? -1.0 : 1.0);
+    k[(perp + 1) % 3] = speed * st * cp;
+    k[(perp + 2) % 3] = speed * st * sp;
+  }
+#pragma unroll
+  for (int i = 0; i < DIM; i++) {
+    if (pos[i] < 0.0) {
+      pos[i] = -pos[i];
+      if (k[i] < 0.0) k[i] = -k[i];
+    } else if (pos[i] > G.maxPos[i]) {
+      pos[i] = 2.0 * G.maxPos[i] - pos[i];
+      if (k[i] > 0.0) k[i] = -k[i];
+    }
+  }
+}
+
+template <bool EXACT, int RNG_MODE, int DIM>
 __device__ __forceinline__ bool deviceDriftParticle(const DevGeometry &G, const DevModel &model, Particle &p, double dt,
-                                                    const Vec3 &force) {
+                                                    const Vec3 &force, Rng &rng) {
   drift<EXACT, DIM>(model.valleys[p.valley], p, dt, force);
   double pos[3] = {p.pos.x, p.pos.y, p.pos.z};
   double k[3] = {p.k.x, p.k.y, p.k.z};
@@ -797,10 +935,14 @@ __device__ __forceinline__ bool deviceDriftParticle(const DevGeometry &G, const 
     double cl[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int i = 0; i < DIM; i++) cl[i] = fmax(0.0, fmin(pos[i], G.maxPos[i]));
-    if (cellIsOhmic(G, posToCell(G, cl[0], cl[1], cl[2]))) {
+    const int wallCell = posToCell(G, cl[0], cl[1], cl[2]);
+    const int face = cellFirstFace(G, wallCell);
+    if (cellIsOhmic(G, wallCell)) {
       removed = true;
 #pragma unroll
       for (int i = 0; i < DIM; i++) pos[i] = cl[i];
+    } else if (face >= 0 && G.surfaceKind[face] != SURFACE_SPECULAR) {
+      surfaceScatter<RNG_MODE, DIM>(G, face, pos, k, rng);
     } else {
 #pragma unroll
       for (int i = 0; i < DIM; i++) {
@@ -820,13 +962,55 @@ __device__ __forceinline__ bool deviceDriftParticle(const DevGeometry &G, const 
   return removed;
 }
 
+// interpolateForce of the particle-mesh scheme: emcNGPScheme.hpp:51-66 (field of the nearest grid point),
+// emcCICScheme.hpp:122-173 (corner fields weighted like the deposit -- including the reference's (1 - wY)(1 - wY)
+// weight of the upper-right corner), emcNECScheme.hpp:99-113 (mean of the two edge mid-point fields of the mesh cell,
+// 2-D), NECSchemeVWD.hpp:57-76 (the same with the x index rounded instead of floored).
 template <int DIM>
-__device__ __forceinline__ Vec3 ngpForce(const DevGeometry &G, const double *e, const Particle &p, double charge) {
-  const int cell = posToCell(G, p.pos.x, p.pos.y, p.pos.z);
+__device__ __forceinline__ Vec3 pmForce(const DevGeometry &G, const double *e, const Particle &p, double charge) {
   Vec3 f;
-  f.x = __dmul_rn(charge, e[cell]);
-  f.y = __dmul_rn(charge, e[(size_t)G.cells + cell]);
-  f.z = DIM > 2 ? __dmul_rn(charge, e[2 * (size_t)G.cells + cell]) : 0.0;
+  f.z = 0.0;
+  const size_t n = (size_t)G.cells;
+  if (G.pmScheme == PM_NGP) {
+    const int cell = posToCell(G, p.pos.x, p.pos.y, p.pos.z);
+    f.x = __dmul_rn(charge, e[cell]);
+    f.y = __dmul_rn(charge, e[n + cell]);
+    if (DIM > 2) f.z = __dmul_rn(charge, e[2 * n + cell]);
+    return f;
+  }
+  const double pos[3] = {p.pos.x, p.pos.y, DIM > 2 ? p.pos.z : 0.0};
+  double w[3];
+  int c[3];
+  int base = posToLowerCell(G, pos, w, c);
+  const int sy = G.extent[0], sz = G.extent[0] * G.extent[1];
+  if (G.pmScheme == PM_CIC) {
+    const double wX = w[0], wY = w[1], wZ = w[2], uX = 1.0 - wX, uY = 1.0 - wY, uZ = 1.0 - wZ;
+    double out[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < DIM; i++) {
+      const double *E = e + (size_t)i * n;
+      if (DIM == 2)
+        out[i] = charge * (E[base] * wX * wY + E[base + 1] * uX * wY + E[base + sy] * wX * uY + E[base + 1 + sy] * uY * uY);
+      else
+        out[i] = (E[base] * wX * wY * wZ + E[base + 1] * uX * wY * wZ + E[base + sy] * wX * uY * wZ +
+                  E[base + 1 + sy] * uY * uY * wZ + E[base + sz] * wX * wY * uZ + E[base + 1 + sz] * uX * wY * uZ +
+                  E[base + sy + sz] * wX * uY * uZ + E[base + 1 + sy + sz] * uY * uY * uZ) *
+                 charge;
+    }
+    f.x = out[0];
+    f.y = out[1];
+    f.z = out[2];
+    return f;
+  }
+  // NEC / NEC-VWD (2-D)
+  bool lastColumn = false;
+  if (G.pmScheme == PM_NEC_VWD) {
+    const int cx = (int)round(__ddiv_rn(pos[0], G.spacing[0]));
+    base += cx - c[0];
+    lastColumn = cx == G.extent[0] - 1;
+  }
+  f.x = charge * (e[base] + e[base + sy]) / 2.0;
+  f.y = lastColumn ? charge * e[n + base] : charge * (e[n + base] + e[n + base + 1]) / 2.0;
   return f;
 }
 
@@ -851,12 +1035,12 @@ __global__ void __launch_bounds__(kBulkThreads, 2)
     attachReplay<RNG_MODE>(P, i, rng);
     rng.step = (uint32_t)step;
     const double dt = P.dt;
-    Vec3 force = ngpForce<DIM>(G, D.e, p, D.charge);
+    Vec3 force = pmForce<DIM>(G, D.e, p, D.charge);
     bool removed;
     if (p.tau >= dt) {
-      removed = deviceDriftParticle<EXACT, DIM>(G, model, p, dt, force);
+      removed = deviceDriftParticle<EXACT, RNG_MODE, DIM>(G, model, p, dt, force, rng);
     } else {
-      removed = deviceDriftParticle<EXACT, DIM>(G, model, p, p.tau, force);
+      removed = deviceDriftParticle<EXACT, RNG_MODE, DIM>(G, model, p, p.tau, force, rng);
       double tRem = A::sub(dt, p.tau);
       while (tRem > 0.0 && !removed) {
         const int set = (p.region < kMaxRegions) ? model.setOf[p.valley][p.region] : -1;
@@ -890,8 +1074,8 @@ __global__ void __launch_bounds__(kBulkThreads, 2)
         }
         const double newTau = A::mul(-log(uniformLog(rng.raw<RNG_MODE>())), tauTab);
         p.tau = A::add(p.tau, newTau);
-        force = ngpForce<DIM>(G, D.e, p, D.charge); // re-interpolated after every scattering (:112)
-        removed = deviceDriftParticle<EXACT, DIM>(G, model, p, fmin(tRem, newTau), force);
+        force = pmForce<DIM>(G, D.e, p, D.charge); // re-interpolated after every scattering (:112)
+        removed = deviceDriftParticle<EXACT, RNG_MODE, DIM>(G, model, p, fmin(tRem, newTau), force, rng);
         tRem = A::sub(tRem, newTau);
       }
     }
@@ -1140,9 +1324,12 @@ __global__ void __launch_bounds__(128) contactInjectKernel(const __grid_constant
         pos[i] = __dmul_rn(__dsub_rn(__dadd_rn((double)c[i], u), 0.5), G.spacing[i]);
     }
     const int region = G.region[cell];
-    const int valley = (int)floor(__dmul_rn((double)model.nValleys, uniformLog(raw[d++])));
+    // emcElectron draws valley / sub-valley from U[1e-6, 1), mosfet2D's electronVWD from U[0, 1) (electronVWD.hpp:25, :82-85)
+    const bool vwd = G.particleKind == 1;
+    const uint64_t rawValley = raw[d++], rawSub = raw[d++];
+    const int valley = (int)floor(__dmul_rn((double)model.nValleys, vwd ? uniform01(rawValley) : uniformLog(rawValley)));
     const DevValley &v = model.valleys[valley];
-    const int sub = (int)floor(__dmul_rn((double)v.deg, uniformLog(raw[d++])));
+    const int sub = (int)floor(__dmul_rn((double)v.deg, vwd ? uniform01(rawSub) : uniformLog(rawSub)));
     const double energy = __dmul_rn(__dmul_rn(-1.5, G.thermalVoltage), log(uniformLog(raw[d++])));
     const double r2 = uniform01(raw[d++]);
     const double r1 = uniform01(raw[d++]);
@@ -1150,7 +1337,9 @@ __global__ void __launch_bounds__(128) contactInjectKernel(const __grid_constant
     double kk[3] = {k.x, k.y, k.z};
     for (int i = 0; i < DIM; i++)
       if ((c[i] == 0 && kk[i] < 0.0) || (c[i] == G.extent[i] - 1 && kk[i] > 0.0)) kk[i] = -kk[i];
-    const int set = (region >= 0 && region < kMaxRegions) ? model.setOf[valley][region] : -1;
+    // electronVWD passes the valley index where the region index belongs (electronVWD.hpp:87)
+    const int tauRegion = vwd ? valley : region;
+    const int set = (tauRegion >= 0 && tauRegion < kMaxRegions) ? model.setOf[valley][tauRegion] : -1;
     const double tau0 = set >= 0 ? model.sets[set].tau : model.defaultTau;
     const double tau = __dmul_rn(-log(uniformLog(raw[d++])), tau0);
     const int64_t at = first + j;

@@ -403,6 +403,10 @@ int emcgpu_device_configure(emcgpu_ctx *ctx, const emcgpu_device_t *dev, double 
   if (!dev->region || !dev->faceContact || !dev->doping || (dev->nContacts && (!dev->contactType || !dev->contactVoltage)))
     return fail(ctx, EMCGPU_E_INVALID, "NULL device array");
   if (mathMode != EMCGPU_MATH_EXACT && mathMode != EMCGPU_MATH_FAST) return fail(ctx, EMCGPU_E_INVALID, "unknown math mode");
+  if (dev->pmScheme < EMCGPU_PM_NGP || dev->pmScheme > EMCGPU_PM_NEC_VWD)
+    return fail(ctx, EMCGPU_E_INVALID, "unknown particle-mesh scheme %d", dev->pmScheme);
+  if (dev->dim == 3 && (dev->pmScheme == EMCGPU_PM_NEC || dev->pmScheme == EMCGPU_PM_NEC_VWD))
+    return fail(ctx, EMCGPU_E_INVALID, "the NEC schemes interpolate forces in 2-D only (emcNECScheme.hpp:99-113)");
   if (!(nrCarriers > 0)) return fail(ctx, EMCGPU_E_INVALID, "nrCarriersPerParticle must be positive");
   if (int r = emc::bindDevice(ctx)) return r;
   int64_t cells = 1;
@@ -419,6 +423,7 @@ int emcgpu_device_configure(emcgpu_ctx *ctx, const emcgpu_device_t *dev, double 
   G.dim = r->dim = dev->dim;
   G.nContacts = dev->nContacts;
   G.cells = (int32_t)cells;
+  G.pmScheme = dev->pmScheme;
   for (int i = 0; i < 3; i++) {
     G.extent[i] = i < dev->dim ? dev->extent[i] : 1;
     G.spacing[i] = i < dev->dim ? dev->spacing[i] : 1.0;
@@ -527,6 +532,24 @@ static double *gridPtr(emcgpu_ctx *ctx, int grid) {
   if (grid == EMCGPU_GRID_EFIELD_Y) return r->grid[EMCGPU_GRID_EFIELD_X].as<double>() + r->geo.cells;
   if (grid == EMCGPU_GRID_EFIELD_Z) return r->grid[EMCGPU_GRID_EFIELD_X].as<double>() + 2 * (size_t)r->geo.cells;
   return r->grid[grid].as<double>();
+}
+
+int emcgpu_device_set_surface(emcgpu_ctx *ctx, int face, int kind, double parameter) {
+  if (int r = needRun(ctx)) return r;
+  if (face < 0 || face >= 2 * ctx->run->dim) return fail(ctx, EMCGPU_E_INVALID, "face %d does not exist in a %d-D device", face, ctx->run->dim);
+  if (kind < EMCGPU_SURFACE_SPECULAR || kind > EMCGPU_SURFACE_MOMENTUM_DEPENDENT)
+    return fail(ctx, EMCGPU_E_UNSUPPORTED_MECHANISM, "surface scatter mechanism %d has no device implementation", kind);
+  ctx->run->geo.surfaceKind[face] = kind;
+  ctx->run->geo.surfaceParam[face] = parameter;
+  return EMCGPU_OK;
+}
+
+int emcgpu_device_set_particle_kind(emcgpu_ctx *ctx, int kind) {
+  if (int r = needRun(ctx)) return r;
+  if (kind != EMCGPU_PARTICLE_ELECTRON && kind != EMCGPU_PARTICLE_ELECTRON_VWD)
+    return fail(ctx, EMCGPU_E_INVALID, "unknown particle kind %d", kind);
+  ctx->run->geo.particleKind = kind;
+  return EMCGPU_OK;
 }
 
 int emcgpu_device_set_grid(emcgpu_ctx *ctx, int grid, const double *host) {
