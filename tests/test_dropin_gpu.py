@@ -177,3 +177,68 @@ def test_own_resistor_driver_matches_reference_within_3_sigma(tmp_path, red_blac
     assert r2.returncode == 0
     for f in ("ElectronsCurrent.txt", "PotentialAvg.txt", "ElectronsFinal.txt"):
         assert open(os.path.join(tmp_path, "resistor" + f)).read() == open(os.path.join(tmp_path, "again" + f)).read(), f
+
+
+# ---- MOSFET (config 4): NEC-VWD scheme, electronVWD, gate contact, four doping regions ------------------------
+def _mosfet_stats():
+    with open(os.path.join(GOLDEN_DIR, "ref_mosfet_stats.json")) as f:
+        return json.load(f)
+
+
+def _check_mosfet(workdir, prefix, st, n_sigma=3.0):
+    widen = np.sqrt(1 + 1 / st["n_runs"])
+    cur = np.loadtxt(os.path.join(workdir, prefix + "ElectronsCurrent.txt"))
+    assert cur.shape == (st["steps"] - st["transient"], 9)  # time, 4 netto counts, 4 running mean currents
+    for c in range(4):  # substrate, source, gate, drain
+        tol = n_sigma * st["current_std"][c] * widen + 1e-12
+        assert abs(cur[-1, 5 + c] - st["current_mean"][c]) <= tol, (c, cur[-1, 5 + c], st["current_mean"][c], tol)
+    assert cur[-1, 6] > 0 > cur[-1, 8]  # electrons enter at the source, leave at the drain
+    with open(os.path.join(workdir, prefix + "ElectronsFinal.txt")) as f:
+        n_final = sum(1 for _ in f) - 1
+    assert abs(n_final - st["n_final_mean"]) <= n_sigma * st["n_final_std"] * widen + 0.001 * st["n_final_mean"]
+    pot = _read_grid(os.path.join(workdir, prefix + "PotentialAvg.txt"))
+    conc = _read_grid(os.path.join(workdir, prefix + "ElectronsConcAvg.txt"))
+    profiles = dict(pot_surface=pot[1], pot_depth=pot[:, 63], conc_surface=conc[1:4].mean(axis=0))
+    for key, got in profiles.items():
+        ref, std = np.array(st[key + "_mean"]), np.array(st[key + "_std"])
+        sig = np.maximum(std, np.median(std)) * widen
+        floor = 2e-3 if key.startswith("pot") else 2e-2 * np.abs(ref) + 1e-3 * np.abs(ref).max()
+        assert np.all(np.abs(got - ref) <= 4.5 * sig + floor), (key, float(np.abs(got - ref).max()))
+    assert abs(conc.sum() - st["conc_total_mean"]) <= n_sigma * st["conc_total_std"] * widen + 2e-3 * st["conc_total_mean"]
+    # inversion charge under the middle of the gate: the density column integrated over the depth (single cells of the
+    # depleted bulk hold a handful of particles in 500 steps -- too noisy to compare point by point)
+    sheet = np.array([np.sum(r["conc_depth"]) for r in st["runs"]])
+    assert abs(conc[:, 63].sum() - sheet.mean()) <= n_sigma * sheet.std(ddof=1) * widen + 0.03 * sheet.mean(), \
+        (conc[:, 63].sum(), sheet.mean(), sheet.std(ddof=1))
+
+
+@pytest.mark.parametrize("red_black", [0, 1], ids=["lexicographic", "redblack"])
+def test_own_mosfet_driver_matches_reference_within_3_sigma(tmp_path, red_black):
+    """the reference's MOSFET example with its run length cut to 2000 steps (oracle/make_ref_mosfet_stats.py) against
+    our driver at the same run length: currents, ensemble size, potential and density profiles"""
+    st = _mosfet_stats()
+    exe = os.path.join(BIN, "mosfet2D")
+    assert os.path.exists(exe), "build with python -m viennaemc_b200.build"
+    r = subprocess.run([exe, "--seed", "20261017", "--steps", str(st["steps"]), "--transient", str(st["transient"]), "--avg",
+                        str(st["avg"]), "--red-black", str(red_black)], cwd=tmp_path, capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    _check_mosfet(str(tmp_path), "mosfet", st)
+
+
+def test_unmodified_reference_mosfet_main_starts_on_the_gpu_path(tmp_path):
+    """examples/mosfet2D/mosfet2D.cpp of the reference compiled unchanged (its sibling headers NECSchemeVWD.hpp /
+    electronVWD.hpp resolved to the GPU-backed ones): the full example is 66 667 steps, so only the start is run here --
+    equilibrium solve, initial ensemble of the reference's size, first steps of the Monte Carlo loop."""
+    exe = os.path.join(BIN, "reference_mosfet2D_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("reference_mosfet2D_gpu is built only where the reference tree is mounted")
+    try:
+        out = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=25).stdout
+    except subprocess.TimeoutExpired as e:
+        out = (e.stdout or b"").decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
+    assert "Nr. of Steps:\t\t66667" in out and "Monte Carlo Procedure" in out, out[-1500:]
+    n = int(out.split(" Electrons")[0].split()[-1])
+    st = _mosfet_stats()
+    assert abs(n - st["n_final_mean"]) < 0.02 * st["n_final_mean"]
+    assert "Nr. Iteration: \t\t1000 / 66667" in out

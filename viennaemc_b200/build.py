@@ -77,8 +77,9 @@ def build_examples(force: bool = False) -> dict:
     common = ["g++", *HOST_FLAGS, "-I", HOST_INC, "-I", os.path.join(ROOT, "include")]
     link = ["-L", LIBDIR, "-lemcgpu", "-Wl,-rpath,$ORIGIN/../lib"]
     deps = _sources(os.path.join(PKG, "host"), os.path.join(ROOT, "include")) + [os.path.join(LIBDIR, "libemcgpu.so")]
-    for name in ("bulkSimulation", "resistor2D"):
+    for name in ("bulkSimulation", "resistor2D", os.path.join("mosfet2D", "mosfet2D")):
         own = os.path.join(PKG, "host", "examples", name + ".cpp")
+        name = os.path.basename(name)
         if os.path.exists(own):
             target = os.path.join(bindir, name)
             if force or _newer(target, deps):
@@ -100,6 +101,20 @@ def build_examples(force: bool = False) -> dict:
             subprocess.check_call([*common, "-o", target, ref_main, *link])
         if os.path.exists(target):
             out[name] = target
+    # mosfet2D.cpp of the reference brings its own particle-mesh scheme and particle type as sibling headers
+    # ("NECSchemeVWD.hpp", "electronVWD.hpp": host code).  Their GPU-backed counterparts of the same names live in
+    # host/examples/mosfet2D; -I- makes the quote-includes of the unmodified main() find those first.
+    ref_main = os.path.join(REFERENCE, "examples", "mosfet2D", "mosfet2D.cpp")
+    target = os.path.join(bindir, "reference_mosfet2D_gpu")
+    if os.path.exists(ref_main) and (force or _newer(target, deps)):
+        # (-I- also switches off the current-directory look-up inside libstdc++'s pstl headers: list that directory too)
+        import glob
+        pstl = [a for d in glob.glob("/usr/include/c++/*/pstl") for a in ("-I", d)]
+        subprocess.check_call(["g++", *HOST_FLAGS, "-I", os.path.join(PKG, "host", "examples", "mosfet2D"), "-I",
+                               os.path.dirname(ref_main), *pstl, "-I-", "-I", HOST_INC, "-I", os.path.join(ROOT, "include"),
+                               "-o", target, ref_main, *link], stderr=subprocess.DEVNULL)
+    if os.path.exists(target):
+        out["reference_mosfet2D_gpu"] = target
     return out
 
 

@@ -74,7 +74,7 @@ public:
   emcBasicParticleHandler(const DeviceType &inDevice, PMScheme &inPMScheme, MapIdxToParticleTypes &inTypes,
                           SizeType inNrCarriersPerParticle, SizeType inSeed)
       : Base(inDevice, inPMScheme, inNrCarriersPerParticle, inTypes), hostRng(inSeed), seed(inSeed) {
-    if (inPMScheme.deviceSchemeId() != 1)
+    if (inPMScheme.deviceSchemeId() < 1)
       emcMessage::getInstance()
           .addError("The particle-mesh scheme has no device implementation (deviceSchemeId() == 0); it cannot run on "
                     "the GPU path and there is no CPU fallback.")
@@ -104,10 +104,33 @@ public:
     auto &type = *this->idxTypeToPartType.at(gpuType);
     emcgpu::uploadParticleType(ctx, type);
     emcdetail::FlatDevice<T, Dim> flat(this->device);
+    flat.desc.pmScheme = inPMScheme.deviceSchemeId() - 1;
     emcgpu::require(ctx,
                     emcgpu_device_configure(ctx, &flat.desc, type.getCharge(), static_cast<double>(this->nrCarriersPerPart),
                                             this->expNrPart[gpuType].raw(), EMCGPU_MATH_FAST),
                     "emcgpu_device_configure");
+    // plug-ins of the particle type that act inside the device kernels: wall mechanisms, creation rules at contacts
+    for (SizeType face = 0; face < 2 * Dim; face++) {
+      const auto *wall = type.scatterHandler.getSurfaceScatterMechanism(face);
+      if (!wall)
+        continue;
+      if (wall->deviceSurfaceKind() < 0)
+        emcMessage::getInstance()
+            .addError("The surface scatter mechanism of face " + std::to_string(face) + " of " + type.getName() +
+                      " has no device implementation (deviceSurfaceKind() < 0); it cannot run on the GPU path and there "
+                      "is no CPU fallback.")
+            .print();
+      emcgpu::require(ctx, emcgpu_device_set_surface(ctx, static_cast<int>(face), wall->deviceSurfaceKind(), wall->deviceSurfaceParameter()),
+                      "emcgpu_device_set_surface");
+    }
+    if (type.isInjected()) {
+      if (type.deviceParticleKind() < 0)
+        emcMessage::getInstance()
+            .addError(type.getName() + " is injected at contacts but has no device creation rule (deviceParticleKind() < 0); "
+                      "it cannot run on the GPU path and there is no CPU fallback.")
+            .print();
+      emcgpu::require(ctx, emcgpu_device_set_particle_kind(ctx, type.deviceParticleKind()), "emcgpu_device_set_particle_kind");
+    }
   }
   ~emcBasicParticleHandler() override {
     if (ctx)

@@ -5,6 +5,8 @@
 #ifndef EMC_ELECTRON_HPP
 #define EMC_ELECTRON_HPP
 
+#include <emcgpu.h>
+
 #include <ParticleType/emcParticleType.hpp>
 #include <emcConstants.hpp>
 #include <emcParticleInitialization.hpp>
@@ -29,6 +31,7 @@ template <class T, class DeviceType> struct emcElectron : public emcParticleType
   T getCharge() const override { return -constants::q; }
   bool isMoved() const override { return true; }
   bool isInjected() const override { return true; }
+  int deviceParticleKind() const override { return EMCGPU_PARTICLE_ELECTRON; }
 
   T getInitialNrParticles(const SizeVec &coord, const DeviceType &device, const emcGrid<T, Dim> &potential) override {
     T density = usePotentialForInit ? std::exp(potential[coord]) * device.getMaterial().getNi()

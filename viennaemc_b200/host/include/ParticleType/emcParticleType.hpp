@@ -47,6 +47,10 @@ template <class T, class DeviceType> struct emcParticleType {
   virtual T getInitialNrParticles(const SizeVec &coord, const DeviceType &device,
                                   const emcGrid<T, Dim> &potential) = 0;
 
+  // --- additive: the creation rules the contacts use on the device (emcgpu_particle_kind); -1 = none, such a type
+  // cannot be injected on the GPU path ---
+  virtual int deviceParticleKind() const { return -1; }
+
   virtual T getMass() const { return unimplemented("getMass", "isMoved"), T(0); }
   virtual emcParticle<T> generateInitialParticle(const SizeVec &, const DeviceType &, emcRNG &) {
     return unimplemented("generateInitialParticle", "isMoved"), emcParticle<T>();
@@ -79,6 +83,13 @@ template <class T, class DeviceType> struct emcParticleType {
     newMechanism->setPtrValley(valleys);
     newMechanism->check();
     scatterHandler.addScatterMechanism(std::move(newMechanism), regions);
+  }
+
+  template <class DerivedSurfaceScatterMechanism>
+  typename std::enable_if<
+      std::is_base_of<emcSurfaceScatterMechanism<T, DeviceType>, DerivedSurfaceScatterMechanism>::value>::type
+  setSurfaceScatterMechanism(emcBoundaryPos boundaryPosition, std::unique_ptr<DerivedSurfaceScatterMechanism> &&newMechanism) {
+    scatterHandler.setSurfaceScatterMechanism(std::move(newMechanism), boundaryPosition);
   }
 
   void setGrainScatterMechanism(std::unique_ptr<emcGrainScatterMechanism<T>> &&newMechanism) {

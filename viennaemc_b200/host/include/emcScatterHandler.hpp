@@ -7,7 +7,8 @@
 // getTau :79-84, getGrainTau :87, initScatterTables :91-95, reinitScatterTables
 // :100-108, addScatterMechanism :131-145, per-mechanism rate files :198-217,
 // table fill :220-235 (rate at (level+1) dE, mechanisms in insertion order), cumulative
-// sum + normalisation by the largest total rate :248-273, the "tau =" report :275-287.
+// sum + normalisation by the largest total rate :248-273, the "tau =" report :275-287,
+// setSurfaceScatterMechanism :118-125 (one wall mechanism per face of the box).
 // Not here on purpose: scatterParticle() (:148-170) -- the reference's CPU selection
 // loop.  Its replacement is the device code behind emcgpu_bulk_step.
 #ifndef EMC_SCATTER_HANDLER_HPP
@@ -23,7 +24,9 @@
 #include <vector>
 
 #include <ScatterMechanisms/emcScatterMechanism.hpp>
+#include <SurfaceScatterMechanisms/emcSurfaceScatterMechanism.hpp>
 #include <emcGrainScatterMechanism.hpp>
+#include <emcMessage.hpp>
 #include <emcUtil.hpp>
 
 template <class T, class DeviceType> class emcScatterHandler {
@@ -45,6 +48,7 @@ private:
   std::map<ValleyRegion, TableSet> sets;
   T grainTau = 1.;
   std::unique_ptr<emcGrainScatterMechanism<T>> grainMechanism;
+  std::vector<std::unique_ptr<emcSurfaceScatterMechanism<T, DeviceType>>> surfaceMechanisms; // [2 * Dim], null = specular
 
   void tabulate() {
     for (auto &[key, set] : sets) {
@@ -92,7 +96,8 @@ public:
 
   emcScatterHandler() : emcScatterHandler(1000, 4.) {}
   emcScatterHandler(SizeType inNrEnergyLevels, T inMaxEnergy)
-      : nrEnergyLevels(inNrEnergyLevels), maxEnergy(inMaxEnergy), dE(inMaxEnergy / inNrEnergyLevels) {}
+      : nrEnergyLevels(inNrEnergyLevels), maxEnergy(inMaxEnergy), dE(inMaxEnergy / inNrEnergyLevels),
+        surfaceMechanisms(2 * DeviceType::Dimension) {}
 
   T getTau(SizeType idxRegion, SizeType idxValley) const {
     auto it = sets.find(ValleyRegion(idxValley, idxRegion));
@@ -114,6 +119,20 @@ public:
     grainMechanism = std::move(newMechanism);
   }
   bool hasGrainScatterMechanism() const { return static_cast<bool>(grainMechanism); }
+
+  template <class DerivedSurfaceScatterMechanism>
+  typename std::enable_if<std::is_base_of<emcSurfaceScatterMechanism<T, DeviceType>, DerivedSurfaceScatterMechanism>::value>::type
+  setSurfaceScatterMechanism(std::unique_ptr<DerivedSurfaceScatterMechanism> &&newMechanism, emcBoundaryPos boundaryPosition) {
+    const SizeType face = toUnderlying(boundaryPosition);
+    if (face >= surfaceMechanisms.size())
+      emcMessage::getInstance().addError("Index for Boundary is out of bounds.").print();
+    newMechanism->setBoundaryPosition(boundaryPosition);
+    surfaceMechanisms[face].reset(newMechanism.release());
+  }
+  // wall mechanism of a face or nullptr (default specular reflection)
+  const emcSurfaceScatterMechanism<T, DeviceType> *getSurfaceScatterMechanism(SizeType face) const {
+    return face < surfaceMechanisms.size() ? surfaceMechanisms[face].get() : nullptr;
+  }
 
   void initScatterTables() {
     tabulate();
