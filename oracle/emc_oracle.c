@@ -18,6 +18,7 @@ static const double C_Q = 1.60219e-19;
 static const double C_KB = 1.38066e-23;
 static const double C_HBAR = 1.05459e-34;
 static const double C_EPS0 = 8.85419e-12;
+static const double C_ME = 9.11e-31;
 
 /* ------------------------------------------------------------------ RNG */
 /* std::mt19937_64 (reference: include/emcUtil.hpp:15).  Published MT19937-64
@@ -275,13 +276,27 @@ void orc_random_direction_wrt_k(const double k[3], double cosTheta, double rnd, 
 }
 
 /* ------------------------------------------------------------------ model */
-enum { MK_ACOUSTIC = 1, MK_ZERO = 2, MK_FIRST = 3, MK_COULOMB = 4 };
+enum { MK_ACOUSTIC = 1, MK_ZERO = 2, MK_FIRST = 3, MK_COULOMB = 4, MK_FROEHLICH = 5 };
 
 typedef struct {
   int kind, valley, finalValley, region, emission, nFinal, nInitSub;
   double scatterConst, scatterConst2, phononEnergy, regionDoping;
   int32_t finalSub[ORC_MAX_SUB][ORC_MAX_FINAL];
+  /* Froehlich family */
+  int variant, bath, qResolved, qResolvedAngle;
+  double effMass, nBose;
 } mech_t;
+
+/* emcPhononBath.hpp */
+struct orc_bath {
+  int nBins;
+  double dq, tauLO, N0, Vsim;
+  double *Nq, *nEm, *nAbs, *cumW, *cumWN;
+  double qs2;
+  double loE, latT;
+  int hasAc, hasRidley;
+  double acE, tauAc, Nac, NacEq, wRidley, toE, tauTO, Nto, NtoEq;
+};
 
 typedef struct {
   int valley, region, nMech;
@@ -299,6 +314,9 @@ struct orc_model {
   mech_t mech[256];
   int nSets;
   tableset_t sets[64];
+  int nBaths;
+  orc_bath_t *baths[16];
+  double qs2; /* emcPlasmonScreening::getQs2() */
 };
 
 orc_model_t *orc_model_create(int nLevels, double maxEnergy, double temperature,
@@ -428,6 +446,55 @@ static double delta_valley(const orc_model_t *m, const mech_t *x) {
   return m->valleys[x->finalValley].eBottom - m->valleys[x->valley].eBottom;
 }
 
+/* emcScreenedFroehlichInteraction.hpp:54-63 */
+static double screened_log_factor(double kI, double kF, double qs2) {
+  const double qPlus2 = (kI + kF) * (kI + kF);
+  const double qMinus2 = (kI - kF) * (kI - kF);
+  if (qs2 <= 0) {
+    if (qMinus2 <= 0)
+      return 0;
+    return 0.5 * log(qPlus2 / qMinus2);
+  }
+  return 0.5 * log((qPlus2 + qs2) / (qMinus2 + qs2));
+}
+
+/* emcFroehlichInteraction.hpp:33-50 */
+int orc_add_froehlich(orc_model_t *m, int variant, int emission, int valley, int region, double phononEnergy,
+                      double relEffMass, double epsHi, double epsLo, double temperature, int bath, int qResolved,
+                      int qResolvedAngle) {
+  if ((variant == 1 || variant == 3) && (bath < 0 || bath >= m->nBaths))
+    return -1;
+  mech_t *x = &m->mech[m->nMech];
+  memset(x, 0, sizeof *x);
+  x->kind = MK_FROEHLICH;
+  x->variant = variant;
+  x->valley = x->finalValley = valley;
+  x->region = region;
+  x->emission = emission;
+  x->phononEnergy = phononEnergy;
+  x->effMass = relEffMass * C_ME;
+  x->bath = (variant == 1 || variant == 3) ? bath : -1;
+  x->qResolved = qResolved;
+  x->qResolvedAngle = qResolvedAngle;
+  double omega0 = phononEnergy * C_Q / C_HBAR;
+  x->scatterConst = C_Q * C_Q * omega0 * x->effMass / (4. * C_PI * C_HBAR * C_HBAR) * (1. / epsHi - 1. / epsLo) / C_EPS0;
+  double xx = C_Q * phononEnergy / (C_KB * temperature);
+  x->nBose = 1. / (exp(xx) - 1.);
+  return m->nMech++;
+}
+int orc_model_add_bath(orc_model_t *m, orc_bath_t *b) {
+  if (m->nBaths >= 16)
+    return -1;
+  m->baths[m->nBaths] = b;
+  return m->nBaths++;
+}
+void orc_model_set_qs2(orc_model_t *m, double qs2) { m->qs2 = qs2; }
+double orc_plasmon_qs2(double density, double carrierTemp, double epsStatic) {
+  if (density <= 0 || carrierTemp <= 0)
+    return 0;
+  return density * C_Q * C_Q / (epsStatic * C_EPS0 * C_KB * carrierTemp);
+}
+
 /* getScatterRate of each built-in mechanism */
 double orc_raw_rate(const orc_model_t *m, int g, double energy) {
   const mech_t *x = &m->mech[g];
@@ -463,6 +530,32 @@ double orc_raw_rate(const orc_model_t *m, int g, double energy) {
              (gamma + gammaF);
     }
     return 0;
+  }
+  case MK_FROEHLICH: {
+    /* emcFroehlichInteraction.hpp:96-107 / :168-181, emcHotPhononFroehlichMechanism.hpp:79-92 / :158-173,
+     * emcScreenedFroehlichInteraction.hpp:127-138 ... :339-352 */
+    if (x->emission && energy <= x->phononEnergy)
+      return 0;
+    double gammaI = orc_gamma(vi, energy);
+    double gammaF = orc_gamma(vi, x->emission ? energy - x->phononEnergy : energy + x->phononEnergy);
+    if (gammaI <= 0 || gammaF <= 0)
+      return 0;
+    double kI = sqrt(2 * x->effMass * gammaI * C_Q) / C_HBAR;
+    double kF = sqrt(2 * x->effMass * gammaF * C_Q) / C_HBAR;
+    double occ;
+    if (x->variant == 0 || x->variant == 2)
+      occ = x->nBose;
+    else if (x->variant == 3 && x->qResolved)
+      occ = orc_bath_nq_window(m->baths[x->bath], fabs(kI - kF), kI + kF);
+    else
+      occ = orc_bath_mean_nq(m->baths[x->bath]);
+    if (x->emission)
+      occ = occ + 1;
+    if (x->variant < 2) {
+      double lnFactor = x->emission ? log((kI + kF) / (kI - kF)) : log((kI + kF) / (kF - kI));
+      return x->scatterConst * occ / kI * lnFactor;
+    }
+    return x->scatterConst * occ / kI * screened_log_factor(kI, kF, m->qs2);
   }
   case MK_COULOMB: { /* emcCoulombScatterMechanism.hpp:36-46 */
     double md = dos_mass_at_zero(vi);
@@ -571,6 +664,13 @@ static void fill_mech_desc(const orc_model_t *m, int g, orc_mech_t *d) {
     d->p[0] = x->emission ? -(x->phononEnergy + dV) : (x->phononEnergy - dV);
     break;
   }
+  case MK_FROEHLICH:
+    d->sampler = x->variant < 2 ? ORC_SAMPLER_FROEHLICH : ORC_SAMPLER_SCREENED_FROEHLICH;
+    d->p[0] = x->emission ? -x->phononEnergy : x->phononEnergy;
+    d->p[1] = m->qs2;
+    d->p[2] = (double)x->bath;
+    d->p[3] = (x->variant == 3 && x->qResolved && x->qResolvedAngle) ? 1. : 0.;
+    break;
   case MK_COULOMB: {
     d->sampler = ORC_SAMPLER_COULOMB;
     double mc = orc_eff_mass_cond(&m->valleys[x->valley], 0.);
@@ -669,12 +769,273 @@ static void scatter_with(const orc_model_t *m, const orc_mech_t *d, orc_ensemble
     orc_random_direction_wrt_k(k, cosTheta, r, out);
     break;
   }
+  case ORC_SAMPLER_FROEHLICH: {
+    /* emcFroehlichInteraction.hpp:109-128 / :183-201 (+ the bath record of the hot-phonon classes) */
+    const orc_valley_t *v = &m->valleys[e->valley[p]];
+    double initEnergy = e->energy[p];
+    e->energy[p] += d->p[0];
+    double finalEnergy = e->energy[p];
+    double f = 2 * sqrt(initEnergy * finalEnergy) / (sqrt(initEnergy) - sqrt(finalEnergy)) /
+               (sqrt(initEnergy) - sqrt(finalEnergy));
+    double cosTheta = (1 + f - pow(1 + 2 * f, rng_u01(rng))) / f;
+    cosTheta = fmax(-1., fmin(1., cosTheta));
+    double kNew = orc_norm_wave_vec(v, e->energy[p]);
+    orc_random_direction_wrt_k(k, cosTheta, rng_u01(rng), out);
+    double kCurr = sqrt(sq3(out));
+    if (kCurr > 0) {
+      double s = kNew / kCurr;
+      for (int i = 0; i < 3; i++)
+        out[i] = out[i] * s;
+    }
+    if (d->p[2] >= 0) {
+      double q[3] = {out[0] - k[0], out[1] - k[1], out[2] - k[2]};
+      orc_bath_record(m->baths[(int)d->p[2]], sqrt(sq3(q)), d->p[0] < 0);
+    }
+    break;
+  }
+  case ORC_SAMPLER_SCREENED_FROEHLICH: {
+    /* emcScreenedFroehlichInteraction.hpp:140-153, :199-213, :272-294, :354-374; helpers :66-97 */
+    const orc_valley_t *v = &m->valleys[e->valley[p]];
+    const int emission = d->p[0] < 0;
+    double kI = orc_norm_wave_vec(v, e->energy[p]);
+    e->energy[p] += d->p[0];
+    double kF = orc_norm_wave_vec(v, e->energy[p]);
+    double r = rng_u01(rng);
+    double cosTheta;
+    const double B = 2 * kI * kF;
+    if (B <= 0) {
+      cosTheta = 1 - 2 * r;
+    } else if (d->p[3] != 0) {
+      double q = orc_bath_sample_q(m->baths[(int)d->p[2]], fabs(kI - kF), kI + kF, emission, r);
+      cosTheta = fmax(-1., fmin(1., (kI * kI + kF * kF - q * q) / B));
+    } else {
+      const double Ap = kI * kI + kF * kF + d->p[1];
+      const double num = Ap - B, den = Ap + B;
+      if (num <= 0 || den <= 0)
+        cosTheta = 1 - 2 * r;
+      else
+        cosTheta = fmax(-1., fmin(1., (Ap - den * pow(num / den, r)) / B));
+    }
+    orc_random_direction_wrt_k(k, cosTheta, rng_u01(rng), out);
+    double kCurr = sqrt(sq3(out));
+    if (kCurr > 0) {
+      double s = kF / kCurr;
+      for (int i = 0; i < 3; i++)
+        out[i] = out[i] * s;
+    }
+    if (d->p[2] >= 0) {
+      double q[3] = {out[0] - k[0], out[1] - k[1], out[2] - k[2]};
+      orc_bath_record(m->baths[(int)d->p[2]], sqrt(sq3(q)), emission);
+    }
+    break;
+  }
   default:
     return;
   }
   e->kx[p] = out[0];
   e->ky[p] = out[1];
   e->kz[p] = out[2];
+}
+
+/* ------------------------------------------------------- phonon bath (emcPhononBath.hpp) */
+static double bath_planck(double energyEV, double tempK) {
+  double x = C_Q * energyEV / (C_KB * tempK);
+  return 1. / (exp(x) - 1.);
+}
+static double bath_planck_temp(double energyEV, double N) {
+  if (N <= 0)
+    return 0;
+  return C_Q * energyEV / (C_KB * log(1. + 1. / N));
+}
+static void bath_rebuild_sums(orc_bath_t *b) { /* :122-135 */
+  b->cumW[0] = b->cumWN[0] = 0;
+  for (int i = 0; i < b->nBins; i++) {
+    const double q = ((double)i + 0.5) * b->dq;
+    const double denom = q * q + b->qs2;
+    const double w = (denom > 0) ? q / denom : 0;
+    b->cumW[i + 1] = b->cumW[i] + w;
+    b->cumWN[i + 1] = b->cumWN[i] + w * b->Nq[i];
+  }
+}
+orc_bath_t *orc_bath_create(int nBins, double dq, double tauLO, double phononEnergy, double latticeTemp, double Vsim,
+                            int enableAcoustic, double acPhononEnergy, double tauAcoustic, double wRidley,
+                            double toPhononEnergy, double tauTO) {
+  orc_bath_t *b = (orc_bath_t *)calloc(1, sizeof *b);
+  b->nBins = nBins;
+  b->dq = dq;
+  b->tauLO = tauLO;
+  b->Vsim = Vsim;
+  b->loE = phononEnergy;
+  b->latT = latticeTemp;
+  b->Nq = (double *)calloc((size_t)nBins, sizeof(double));
+  b->nEm = (double *)calloc((size_t)nBins, sizeof(double));
+  b->nAbs = (double *)calloc((size_t)nBins, sizeof(double));
+  b->cumW = (double *)calloc((size_t)nBins + 1, sizeof(double));
+  b->cumWN = (double *)calloc((size_t)nBins + 1, sizeof(double));
+  b->N0 = bath_planck(phononEnergy, latticeTemp);
+  for (int i = 0; i < nBins; i++)
+    b->Nq[i] = b->N0;
+  if (enableAcoustic) {
+    b->hasAc = 1;
+    b->acE = acPhononEnergy;
+    b->tauAc = tauAcoustic;
+    b->NacEq = bath_planck(acPhononEnergy, latticeTemp);
+    b->Nac = b->NacEq;
+  }
+  if (enableAcoustic && wRidley > 0 && toPhononEnergy > 0) {
+    b->hasRidley = 1;
+    b->wRidley = wRidley > 1 ? 1 : wRidley;
+    b->toE = toPhononEnergy;
+    b->tauTO = tauTO;
+    b->NtoEq = bath_planck(toPhononEnergy, latticeTemp);
+    b->Nto = b->NtoEq;
+  }
+  bath_rebuild_sums(b);
+  return b;
+}
+void orc_bath_destroy(orc_bath_t *b) {
+  if (!b)
+    return;
+  free(b->Nq); free(b->nEm); free(b->nAbs); free(b->cumW); free(b->cumWN);
+  free(b);
+}
+void orc_bath_set_qs2(orc_bath_t *b, double qs2) {
+  if (qs2 == b->qs2)
+    return;
+  b->qs2 = qs2;
+  bath_rebuild_sums(b);
+}
+static int bath_bin(const orc_bath_t *b, double q) { /* binOf :228-231 */
+  uint64_t idx = (uint64_t)(q / b->dq);
+  return idx >= (uint64_t)b->nBins ? b->nBins - 1 : (int)idx;
+}
+void orc_bath_record(orc_bath_t *b, double q, int emission) {
+  if (emission)
+    b->nEm[bath_bin(b, q)] += 1.;
+  else
+    b->nAbs[bath_bin(b, q)] += 1.;
+}
+void orc_bath_add_counts(orc_bath_t *b, const int64_t *emission, const int64_t *absorption) {
+  for (int i = 0; i < b->nBins; i++) {
+    b->nEm[i] += (double)emission[i];
+    b->nAbs[i] += (double)absorption[i];
+  }
+}
+double orc_bath_mean_nq(const orc_bath_t *b) {
+  double sumW = 0, sumWN = 0;
+  for (int i = 0; i < b->nBins; i++) {
+    double q = ((double)i + 0.5) * b->dq;
+    double w = q * q;
+    sumW += w;
+    sumWN += w * b->Nq[i];
+  }
+  return sumW > 0 ? sumWN / sumW : b->N0;
+}
+void orc_bath_update(orc_bath_t *b, double dt) {
+  double N_target = b->N0;
+  if (b->hasAc) {
+    double N_klemens = b->N0;
+    if (b->Nac > b->NacEq)
+      N_klemens = bath_planck(b->loE, bath_planck_temp(b->acE, b->Nac));
+    if (b->hasRidley) {
+      double N_ridley = b->N0;
+      if (b->Nto > b->NtoEq)
+        N_ridley = bath_planck(b->loE, bath_planck_temp(b->toE, b->Nto));
+      N_target = (1. - b->wRidley) * N_klemens + b->wRidley * N_ridley;
+    } else {
+      N_target = N_klemens;
+    }
+  }
+  double sumW = 0, sumWdN = 0;
+  for (int i = 0; i < b->nBins; i++) {
+    double q = ((double)i + 0.5) * b->dq;
+    double Dph = q * q * b->dq * b->Vsim / (2. * C_PI * C_PI);
+    double g = (Dph > 0) ? (b->nEm[i] - b->nAbs[i]) / (Dph * dt) : 0;
+    const double tau_i = b->tauLO; /* no tauLOProfile in the configs */
+    if (b->hasAc) {
+      double w = q * q;
+      sumW += w;
+      sumWdN += w * (b->Nq[i] - N_target);
+    }
+    b->Nq[i] += g * dt - (dt / tau_i) * (b->Nq[i] - N_target);
+    if (b->Nq[i] < 0)
+      b->Nq[i] = 0;
+    b->nEm[i] = 0;
+    b->nAbs[i] = 0;
+  }
+  if (b->hasAc) {
+    double fKlemens = b->hasRidley ? (1. - b->wRidley) : 1.;
+    double dN_LO_mean = (sumW > 0) ? sumWdN / sumW : 0;
+    b->Nac += dt * fKlemens * dN_LO_mean / b->tauLO - dt * (b->Nac - b->NacEq) / b->tauAc;
+    if (b->Nac < b->NacEq)
+      b->Nac = b->NacEq;
+    if (b->hasRidley) {
+      b->Nto += dt * b->wRidley * dN_LO_mean / b->tauLO - dt * (b->Nto - b->NtoEq) / b->tauTO;
+      if (b->Nto < b->NtoEq)
+        b->Nto = b->NtoEq;
+    }
+  }
+  bath_rebuild_sums(b);
+}
+double orc_bath_nq_window(const orc_bath_t *b, double qMin, double qMax) {
+  if (b->nBins < 2 || qMax <= qMin)
+    return orc_bath_mean_nq(b);
+  long lo = (long)floor(qMin / b->dq);
+  long hi = (long)ceil(qMax / b->dq);
+  if (lo < 0)
+    lo = 0;
+  if (hi > (long)b->nBins)
+    hi = (long)b->nBins;
+  if (hi - lo < 1)
+    return orc_bath_mean_nq(b);
+  const double wSum = b->cumW[hi] - b->cumW[lo];
+  if (wSum <= 0)
+    return orc_bath_mean_nq(b);
+  return (b->cumWN[hi] - b->cumWN[lo]) / wSum;
+}
+double orc_bath_sample_q(const orc_bath_t *b, double qMin, double qMax, int emission, double r) {
+  if (b->nBins < 2 || qMax <= qMin)
+    return qMin;
+  long lo = (long)floor(qMin / b->dq);
+  long hi = (long)ceil(qMax / b->dq);
+  if (lo < 0)
+    lo = 0;
+  if (hi > (long)b->nBins)
+    hi = (long)b->nBins;
+  if (hi - lo < 1)
+    return qMin;
+#define BATH_S(i) (emission ? (b->cumWN[i] + b->cumW[i]) : b->cumWN[i])
+  const double sLo = BATH_S(lo), sHi = BATH_S(hi);
+  const double span = sHi - sLo;
+  if (!(span > 0))
+    return 0.5 * (qMin + qMax);
+  const double target = sLo + r * span;
+  long a = lo, bb = hi;
+  while (bb - a > 1) {
+    const long mid = (a + bb) / 2;
+    if (BATH_S(mid) <= target)
+      a = mid;
+    else
+      bb = mid;
+  }
+  const double sA = BATH_S(a), sB = BATH_S(a + 1);
+#undef BATH_S
+  const double frac = (sB > sA) ? (target - sA) / (sB - sA) : 0.5;
+  const double q = ((double)a + frac) * b->dq;
+  return fmax(qMin, fmin(qMax, q));
+}
+double orc_bath_acoustic_temp(const orc_bath_t *b) {
+  if (!b->hasAc || b->Nac <= b->NacEq)
+    return b->latT;
+  return bath_planck_temp(b->acE, b->Nac);
+}
+double orc_bath_n0(const orc_bath_t *b) { return b->N0; }
+int orc_bath_copy(const orc_bath_t *b, int which, double *out) {
+  const double *src[5] = {b->Nq, b->nEm, b->nAbs, b->cumW, b->cumWN};
+  if (which < 0 || which > 4)
+    return -1;
+  memcpy(out, src[which], sizeof(double) * (size_t)(b->nBins + (which >= 3 ? 1 : 0)));
+  return 0;
 }
 
 static void drift_wrap(const orc_model_t *m, orc_ensemble_t *e, int64_t p, double dt,

@@ -26,7 +26,13 @@ enum { ORC_VALLEY_PARABOLIC_ISO = 0, ORC_VALLEY_NONPARABOLIC_ISO = 1,
        ORC_VALLEY_PARABOLIC_ANISO = 2, ORC_VALLEY_NONPARABOLIC_ANISO = 3 };
 
 enum { ORC_SAMPLER_NONE = 0, ORC_SAMPLER_ISOTROPIC_ELASTIC = 1,
-       ORC_SAMPLER_INTERVALLEY = 2, ORC_SAMPLER_COULOMB = 3 };
+       ORC_SAMPLER_INTERVALLEY = 2, ORC_SAMPLER_COULOMB = 3,
+       /* emcFroehlichInteraction.hpp:109-128 / :183-201, emcHotPhononFroehlichMechanism.hpp:94-117 / :175-199:
+        * p[0] = signed phonon energy, p[2] = phonon bath index or -1 */
+       ORC_SAMPLER_FROEHLICH = 4,
+       /* emcScreenedFroehlichInteraction.hpp:140-153 ... :354-374: p[0] = signed phonon energy, p[1] = qs^2,
+        * p[2] = phonon bath index or -1, p[3] = 1: polar angle through bath.sampleQ (q-resolved) */
+       ORC_SAMPLER_SCREENED_FROEHLICH = 5 };
 
 enum { ORC_RNG_MT_GLOBAL = 0, ORC_RNG_STREAMS = 1, ORC_RNG_PHILOX = 2 };
 
@@ -80,6 +86,36 @@ int orc_add_intervalley(orc_model_t *m, int order, int emission, int valley,
 int orc_add_coulomb(orc_model_t *m, int valley, int region, double epsR,
                     double regionDoping);
 int orc_build_tables(orc_model_t *m);
+
+/* ---- polar-optical (Froehlich) family and the phonon bath (config 5, rows a11 / a21) ----------------------------
+ * emcPhononBath (include/emcPhononBath.hpp): q-binned LO occupation, event counters, relaxation. */
+typedef struct orc_bath orc_bath_t;
+orc_bath_t *orc_bath_create(int nBins, double dq, double tauLO, double phononEnergy, double latticeTemp, double Vsim,
+                            int enableAcoustic, double acPhononEnergy, double tauAcoustic, double wRidley,
+                            double toPhononEnergy, double tauTO);             /* ctor :161-196 */
+void orc_bath_destroy(orc_bath_t *b);
+void orc_bath_set_qs2(orc_bath_t *b, double qs2);                               /* setScreeningQ2 :200-205 */
+void orc_bath_record(orc_bath_t *b, double q, int emission);                     /* :237-253 */
+void orc_bath_update(orc_bath_t *b, double dt);                                 /* :264-358 */
+double orc_bath_mean_nq(const orc_bath_t *b);                                    /* :461-470 */
+double orc_bath_nq_window(const orc_bath_t *b, double qMin, double qMax);        /* :378-394 */
+double orc_bath_sample_q(const orc_bath_t *b, double qMin, double qMax, int emission, double r); /* :423-458 */
+double orc_bath_acoustic_temp(const orc_bath_t *b);                             /* :477-481 */
+double orc_bath_n0(const orc_bath_t *b);
+/* which: 0 Nq, 1 nEm, 2 nAbs (nBins doubles); 3 cumW, 4 cumWN (nBins + 1 doubles) */
+int orc_bath_copy(const orc_bath_t *b, int which, double *out);
+/* add event counts gathered elsewhere (the device) to nEm / nAbs */
+void orc_bath_add_counts(orc_bath_t *b, const int64_t *emission, const int64_t *absorption);
+/* the model refers to baths by index; the caller keeps ownership */
+int orc_model_add_bath(orc_model_t *m, orc_bath_t *b);
+/* emcPlasmonScreening::getQs2 as seen by the screened mechanisms */
+void orc_model_set_qs2(orc_model_t *m, double qs2);
+double orc_plasmon_qs2(double density, double carrierTemp, double epsStatic); /* emcPlasmonScreening.hpp:69-76 */
+/* variant: 0 emcFroehlich{Absorption,Emission}3D, 1 emcHotPhononFroehlich*, 2 emcScreenedFroehlich*,
+ * 3 emcScreenedHotPhononFroehlich* (qResolved / qResolvedAngle as its ctor); bath: index or -1 */
+int orc_add_froehlich(orc_model_t *m, int variant, int emission, int valley, int region, double phononEnergy,
+                      double relEffMass, double epsHi, double epsLo, double temperature, int bath, int qResolved,
+                      int qResolvedAngle);
 
 int orc_n_valleys(const orc_model_t *m);
 int orc_get_valley(const orc_model_t *m, int v, orc_valley_t *out);

@@ -18,7 +18,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from scenarios import DEVICE_CASES, GOLDEN_CASES  # noqa: E402
+from scenarios import DEVICE_CASES, GA2O3_CASES, GOLDEN_CASES, ga2o3_args  # noqa: E402
 
 DT = {"d": np.float64, "q": np.int64, "Q": np.uint64}
 
@@ -75,8 +75,27 @@ def main_device():
         print(name, "->", dst, os.path.getsize(dst) // 1024, "KiB; draws", len(blob["draws"]))
 
 
+def main_ga2o3():
+    subprocess.check_call(["make", "-C", HERE, "_ref/ref_ga2o3_driver"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    drv = os.path.join(HERE, "_ref", "ref_ga2o3_driver")
+    for name in GA2O3_CASES:
+        with tempfile.TemporaryDirectory() as tmp:
+            out = os.path.join(tmp, "ref.bin")
+            cmd = [drv, "--out", out]
+            for k, v in ga2o3_args(name).items():
+                cmd += ["--" + k.replace("_", "-"), str(v)]
+            subprocess.check_call(cmd, cwd=tmp, stdout=subprocess.DEVNULL)
+            blob = read_blob(out)
+        dst = os.path.join(ROOT, "tests", "golden", name + ".npz")
+        np.savez_compressed(dst, **blob)
+        print(name, "->", dst, os.path.getsize(dst) // 1024, "KiB; particles", int(blob["params"][-1]), "draws", len(blob["draws"]))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) < 2 or sys.argv[1] != "device":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "bulk"):
         main()
-    if len(sys.argv) < 2 or sys.argv[1] == "device":
+    if which in ("all", "device"):
         main_device()
+    if which in ("all", "ga2o3"):
+        main_ga2o3()

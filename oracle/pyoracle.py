@@ -75,6 +75,28 @@ def lib():
                                           C.c_double, C.c_int, C.c_int, _IP]
         L.orc_add_coulomb.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
         L.orc_build_tables.argtypes = [C.c_void_p]
+        # Froehlich family + phonon bath
+        L.orc_bath_create.restype = C.c_void_p
+        L.orc_bath_create.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double,
+                                      C.c_double, C.c_double, C.c_double, C.c_double]
+        L.orc_bath_destroy.argtypes = [C.c_void_p]
+        L.orc_bath_set_qs2.argtypes = [C.c_void_p, C.c_double]
+        L.orc_bath_update.argtypes = [C.c_void_p, C.c_double]
+        for name in ("orc_bath_mean_nq", "orc_bath_acoustic_temp", "orc_bath_n0"):
+            getattr(L, name).restype = C.c_double
+            getattr(L, name).argtypes = [C.c_void_p]
+        L.orc_bath_nq_window.restype = C.c_double
+        L.orc_bath_nq_window.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.orc_bath_sample_q.restype = C.c_double
+        L.orc_bath_sample_q.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double]
+        L.orc_bath_copy.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+        L.orc_bath_add_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.orc_model_add_bath.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_model_set_qs2.argtypes = [C.c_void_p, C.c_double]
+        L.orc_plasmon_qs2.restype = C.c_double
+        L.orc_plasmon_qs2.argtypes = [C.c_double, C.c_double, C.c_double]
+        L.orc_add_froehlich.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                                        C.c_double, C.c_double, C.c_int, C.c_int, C.c_int]
         L.orc_n_valleys.argtypes = [C.c_void_p]
         L.orc_get_valley.argtypes = [C.c_void_p, C.c_int, C.POINTER(Valley)]
         L.orc_n_mechanisms.argtypes = [C.c_void_p]
@@ -212,6 +234,23 @@ class Model:
     def add_coulomb(self, valley, region, eps_r, region_doping):
         return self.L.orc_add_coulomb(self.h, valley, region, eps_r, region_doping)
 
+    def add_froehlich(self, variant, emission, valley, region, phonon_energy, rel_eff_mass, eps_hi, eps_lo, temperature=300.0,
+                      bath=-1, q_resolved=False, q_resolved_angle=True):
+        """variant: FROEHLICH_EQ / _HOT / _SCREENED_EQ / _SCREENED_HOT"""
+        r = self.L.orc_add_froehlich(self.h, variant, int(emission), valley, region, phonon_energy, rel_eff_mass, eps_hi,
+                                     eps_lo, temperature, bath, int(q_resolved), int(q_resolved_angle))
+        assert r >= 0
+        return r
+
+    def add_bath(self, bath: "PhononBath"):
+        self._baths = getattr(self, "_baths", []) + [bath]  # keep alive
+        r = self.L.orc_model_add_bath(self.h, bath.h)
+        assert r >= 0
+        return r
+
+    def set_qs2(self, qs2):
+        self.L.orc_model_set_qs2(self.h, qs2)
+
     def build_tables(self):
         assert self.L.orc_build_tables(self.h) == 0
 
@@ -304,6 +343,67 @@ class Model:
             assert ec.value <= ev_cap
             res["events"] = ev[: ec.value]
         return res
+
+
+FROEHLICH_EQ, FROEHLICH_HOT, FROEHLICH_SCREENED_EQ, FROEHLICH_SCREENED_HOT = 0, 1, 2, 3
+
+
+class PhononBath:
+    """emcPhononBath (include/emcPhononBath.hpp)"""
+
+    def __init__(self, n_bins, dq, tau_lo, phonon_energy, lattice_temp, v_sim, acoustic=False, ac_energy=0.0, tau_ac=0.0,
+                 w_ridley=0.0, to_energy=0.0, tau_to=0.0):
+        self.L = lib()
+        self.n_bins, self.dq = n_bins, dq
+        self.h = self.L.orc_bath_create(n_bins, dq, tau_lo, phonon_energy, lattice_temp, v_sim, int(acoustic), ac_energy,
+                                        tau_ac, w_ridley, to_energy, tau_to)
+
+    def __del__(self):
+        try:
+            self.L.orc_bath_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_qs2(self, qs2):
+        self.L.orc_bath_set_qs2(self.h, qs2)
+
+    def update(self, dt):
+        self.L.orc_bath_update(self.h, dt)
+
+    def mean_nq(self):
+        return self.L.orc_bath_mean_nq(self.h)
+
+    def acoustic_temp(self):
+        return self.L.orc_bath_acoustic_temp(self.h)
+
+    def n0(self):
+        return self.L.orc_bath_n0(self.h)
+
+    def nq_window(self, q_min, q_max):
+        return self.L.orc_bath_nq_window(self.h, q_min, q_max)
+
+    def sample_q(self, q_min, q_max, emission, r):
+        return self.L.orc_bath_sample_q(self.h, q_min, q_max, int(emission), r)
+
+    def _copy(self, which, n):
+        out = np.zeros(n)
+        assert self.L.orc_bath_copy(self.h, which, _dp(out)) == 0
+        return out
+
+    nq = property(lambda self: self._copy(0, self.n_bins))
+    n_em = property(lambda self: self._copy(1, self.n_bins))
+    n_abs = property(lambda self: self._copy(2, self.n_bins))
+    cum_w = property(lambda self: self._copy(3, self.n_bins + 1))
+    cum_wn = property(lambda self: self._copy(4, self.n_bins + 1))
+
+    def add_counts(self, emission, absorption):
+        em = np.ascontiguousarray(emission, dtype=np.int64)
+        ab = np.ascontiguousarray(absorption, dtype=np.int64)
+        self.L.orc_bath_add_counts(self.h, em.ctypes.data_as(C.POINTER(C.c_int64)), ab.ctypes.data_as(C.POINTER(C.c_int64)))
+
+
+def plasmon_qs2(density, carrier_temp, eps_static):
+    return lib().orc_plasmon_qs2(density, carrier_temp, eps_static)
 
 
 def mt_state(seed: int):

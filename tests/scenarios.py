@@ -156,3 +156,72 @@ def build_device(case: str):
         m.add_coulomb(0, reg, 11.8, dop[reg])
     m.build_tables()
     return m, dev
+
+
+# ---- config 5: beta-Ga2O3 bulk with polar-optical (Froehlich) scattering and hot phonons -------------------------
+# (oracle/_ref/ref_ga2o3_driver around examples/hotPhononGa2O3/Ga2O3Functions.hpp).  Parameter values:
+# Ga2O3Functions.hpp:45-88.
+GA2O3 = dict(eps_lo=10.2, eps_hi=3.573, rho=5880.0, v_sound=6800.0, rel_mass=0.284, alpha=0.106, hw_pop=0.044,
+             mode_energy=[0.0302, 0.0429, 0.0646, 0.0796, 0.0936], mode_weight=[0.1382, 0.0326, 0.2448, 0.1510, 0.4334],
+             hw_npo=0.090, d_npo=8.05e10, sigma_ac=4.8, n_bins=300, dq=1e7)
+GA2O3_CASES = {
+    # the shipped default of hotPhononGa2O3.cpp: screened-hot classes with screening off, mean-field occupation
+    "ga2o3_hot": dict(polar="screened_hot", steps=160, field=2e7, seed=1),
+    # everything on: 5 polar modes, Debye screening updated from the carrier temperature, q-resolved rate and angle
+    "ga2o3_qres": dict(polar="screened_hot", steps=60, field=3e7, seed=2, multimode=1, screening=1, qresolved=1, impurity=1,
+                       box=2e-7),
+    # the unscreened classes: emcHotPhononFroehlich*3D and emcFroehlich*3D
+    "ga2o3_plain_hot": dict(polar="hot", steps=80, field=2e7, seed=3, box=2e-7),
+    "ga2o3_eq": dict(polar="eq", steps=60, field=1e7, seed=4, box=2e-7),
+    "ga2o3_screened_eq": dict(polar="screened_eq", steps=60, field=1e7, seed=5, box=2e-7, screening=1),
+}
+GA2O3_DEFAULTS = dict(box=3e-7, doping=1e23, dt=1e-16, temperature=300.0, tau_lo=5e-12, tau_ac=20e-12, emax=5.0, levels=2000,
+                      multimode=0, screening=0, qresolved=0, qres_angle=1, acoustic_bath=1, impurity=0, reinit_every=1)
+
+
+def ga2o3_args(case):
+    a = dict(GA2O3_DEFAULTS)
+    a.update(GA2O3_CASES[case])
+    return a
+
+
+def build_ga2o3(case):
+    """oracle-side model + phonon baths of a GA2O3_CASES entry (mirrors oracle/ref_ga2o3_driver.cpp)"""
+    a = ga2o3_args(case)
+    g = GA2O3
+    m = po.Model(a["levels"], a["emax"], a["temperature"], g["rho"], g["v_sound"])
+    m.add_valley(po.VALLEY_NONPARABOLIC_ISO, g["rel_mass"], 1, g["alpha"], 0.0)
+    m.add_acoustic(0, 0, g["sigma_ac"])
+    m.add_intervalley(0, False, 0, 0, 0, g["d_npo"], g["hw_npo"], [[0]])
+    m.add_intervalley(0, True, 0, 0, 0, g["d_npo"], g["hw_npo"], [[0]])
+    if a["impurity"]:
+        m.add_coulomb(0, 0, g["eps_lo"], a["doping"])
+    if a["multimode"]:
+        energies = g["mode_energy"]
+        inv_hi = 1.0 / g["eps_hi"]
+        total = inv_hi - 1.0 / g["eps_lo"]
+        eps_lo = [1.0 / (inv_hi - w * total) for w in g["mode_weight"]]
+    else:
+        energies, eps_lo = [g["hw_pop"]], [g["eps_lo"]]
+    qs2 = po.plasmon_qs2(a["doping"], a["temperature"], g["eps_lo"]) if a["screening"] else 0.0
+    m.set_qs2(qs2)
+    hot = a["polar"] in ("hot", "screened_hot")
+    baths = []
+    if hot:
+        v_sim = a["box"] * a["box"] * a["box"]
+        for hw in energies:
+            b = po.PhononBath(g["n_bins"], g["dq"], a["tau_lo"], hw, a["temperature"], v_sim, bool(a["acoustic_bath"]), hw / 2.0,
+                              a["tau_ac"])
+            b.set_qs2(qs2)
+            m.add_bath(b)
+            baths.append(b)
+    variant = {"eq": po.FROEHLICH_EQ, "hot": po.FROEHLICH_HOT, "screened_eq": po.FROEHLICH_SCREENED_EQ,
+               "screened_hot": po.FROEHLICH_SCREENED_HOT}[a["polar"]]
+    for i, hw in enumerate(energies):
+        # the unscreened helpers of Ga2O3Functions.hpp always use the full static permittivity (:173-187, :206-222)
+        el = eps_lo[i] if variant >= po.FROEHLICH_SCREENED_EQ else g["eps_lo"]
+        for emission in (False, True):
+            m.add_froehlich(variant, emission, 0, 0, hw, g["rel_mass"], g["eps_hi"], el, a["temperature"], i if hot else -1,
+                            bool(a["qresolved"]), bool(a["qres_angle"]))
+    m.build_tables()
+    return m, baths, a
