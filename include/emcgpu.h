@@ -89,8 +89,18 @@ typedef enum {
   EMCGPU_SAMPLER_INTERVALLEY = 2,
   /* emcCoulombScatterMechanism.hpp:48-59 (Brooks-Herring); param[0] = Debye
    * energy N_D/(c2 m_c) of the table set's region */
-  EMCGPU_SAMPLER_COULOMB = 3
+  EMCGPU_SAMPLER_COULOMB = 3,
+  /* emcFroehlichInteraction.hpp:109-128, :183-201 and emcHotPhononFroehlichMechanism.hpp:94-117, :175-199 (polar optical,
+   * unscreened): E += param[0] (signed phonon energy), cos(theta) = (1 + f - (1 + 2f)^r) / f with
+   * f = 2 sqrt(E E') / (sqrt(E) - sqrt(E'))^2, new direction about the current k, |k| <- k_norm(E').
+   * param[2] >= 0: phonon bath that counts the event in its |k' - k| bin (emission if param[0] < 0) */
+  EMCGPU_SAMPLER_FROEHLICH = 4,
+  /* emcScreenedFroehlichInteraction.hpp:140-153, :199-213, :272-294, :354-374: the same with the screened polar angle
+   * (helpers :66-97): param[1] = qs^2 [1/m^2]; param[3] != 0: |q| drawn from the occupation-weighted window of bath
+   * param[2] (emcPhononBath::sampleQ, q-resolved) instead of the closed form */
+  EMCGPU_SAMPLER_SCREENED_FROEHLICH = 5
 } emcgpu_sampler_id;
+#define EMCGPU_MAX_BATHS 8
 
 /* One emcScatterMechanism (include/ScatterMechanisms/emcScatterMechanism.hpp:17-53)
  * as seen by the device: which sampler, its parameters, its name for errors. */
@@ -168,6 +178,16 @@ int emcgpu_set_valleys(emcgpu_ctx *ctx, const emcgpu_valley_t *valleys, int nVal
  * again at any time (emcScatterHandler::reinitScatterTables, :100-108). */
 int emcgpu_set_tables(emcgpu_ctx *ctx, const emcgpu_tableset_t *sets, int nSets,
                       int nLevels, double maxEnergy);
+
+/* emcPhononBath (include/emcPhononBath.hpp): |q|-binned occupation of a polar phonon mode coupled to the ensemble.  The
+ * bath itself (update :264-358, occupations, relaxation) stays a host object of the drop-in API; the device side is
+ *   - the event counters of recordEmission / recordAbsorption (:237-253), one pair per bin and bath, and
+ *   - for the q-resolved polar angle, the prefix sums cumW / cumWN (:122-135) that sampleQ (:423-458) searches.
+ * cumW / cumWN: HOST [nBaths][nBins + 1], may be NULL when no mechanism samples |q| from the bath.  Call again whenever
+ * the bath was updated (like emcgpu_set_tables after reinitScatterTables). */
+int emcgpu_set_phonon_baths(emcgpu_ctx *ctx, int nBaths, int nBins, double dq, const double *cumW, const double *cumWN);
+/* event counts since the last call with reset != 0: HOST [nBaths][nBins] each */
+int emcgpu_get_phonon_counts(emcgpu_ctx *ctx, int64_t *emission, int64_t *absorption, int reset);
 
 /* ---- ensemble --------------------------------------------------------- */
 /* upload n particles; soa[EMCGPU_N_STREAMS] are HOST arrays of length n.

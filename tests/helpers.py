@@ -23,13 +23,21 @@ def golden_ensemble(g, prefix):
                                    g[prefix + "grainTau"], g[prefix + "idx"])
 
 
-def upload_model(ctx: capi.Context, model: po.Model):
+def upload_baths(ctx: capi.Context, baths):
+    """oracle phonon baths -> emcgpu_set_phonon_baths (prefix sums included: q-resolved angles may need them)"""
+    if baths:
+        ctx.set_phonon_baths(len(baths), baths[0].n_bins, baths[0].dq, np.stack([b.cum_w for b in baths]),
+                             np.stack([b.cum_wn for b in baths]))
+
+
+def upload_model(ctx: capi.Context, model: po.Model, valleys_too=True):
     """oracle model -> emcgpu_set_valleys / emcgpu_set_tables"""
     valleys = []
     for v in model.valleys():
         rot = np.array([list(v.rot[s]) for s in range(po.MAX_SUB)])
         valleys.append(capi.make_valley(v.kind, v.deg, v.mCond, v.mDos, v.alpha, v.eBottom, list(v.vogt), rot))
-    ctx.set_valleys(valleys)
+    if valleys_too:
+        ctx.set_valleys(valleys)
     sets = []
     for ts in model.tablesets():
         mechs = []
@@ -37,7 +45,7 @@ def upload_model(ctx: capi.Context, model: po.Model):
             fs = np.array([[m.finalSub[s][f] for f in range(max(1, m.nFinal))] for s in range(po.MAX_SUB)])
             mechs.append(capi.make_mech(m.sampler, name=f"mech{m.globalId}", mech_id=m.globalId,
                                         final_valley=m.finalValley, final_sub=fs if m.nFinal > 0 else None,
-                                        params=[m.p[0], m.p[1]]))
+                                        params=[m.p[0], m.p[1], m.p[2], m.p[3]]))
         sets.append(dict(valley=ts["valley"], region=ts["region"], tau=ts["tau"], cum=ts["cum"], mech=mechs))
     ctx.set_tables(sets, model.n_levels, model.max_energy)
 

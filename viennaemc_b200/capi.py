@@ -79,6 +79,8 @@ def load():
     L.emcgpu_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.emcgpu_set_valleys.argtypes = [vp, C.POINTER(ValleyC), C.c_int]
     L.emcgpu_set_tables.argtypes = [vp, C.POINTER(TableSetC), C.c_int, C.c_int, C.c_double]
+    L.emcgpu_set_phonon_baths.argtypes = [vp, C.c_int, C.c_int, C.c_double, _DP, _DP]
+    L.emcgpu_get_phonon_counts.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]
     L.emcgpu_set_ensemble.argtypes = [vp, C.c_int64, C.POINTER(_DP), C.POINTER(C.c_uint32), C.c_int64]
     L.emcgpu_get_ensemble.argtypes = [vp, C.POINTER(_DP), C.POINTER(C.c_uint32)]
     L.emcgpu_ensemble_size.argtypes = [vp]
@@ -132,7 +134,7 @@ CONTACT_OHMIC, CONTACT_SCHOTTKY, CONTACT_GATE = range(3)
 
 EXPORTED_SYMBOLS = [
     "emcgpu_abi_version", "emcgpu_create", "emcgpu_destroy", "emcgpu_last_error", "emcgpu_launch_count",
-    "emcgpu_set_stream", "emcgpu_synchronize", "emcgpu_set_option", "emcgpu_set_valleys", "emcgpu_set_tables", "emcgpu_set_ensemble",
+    "emcgpu_set_stream", "emcgpu_synchronize", "emcgpu_set_option", "emcgpu_set_valleys", "emcgpu_set_tables", "emcgpu_set_phonon_baths", "emcgpu_get_phonon_counts", "emcgpu_set_ensemble",
     "emcgpu_get_ensemble", "emcgpu_ensemble_size", "emcgpu_generate_bulk_ensemble",
     "emcgpu_ensemble_device_ptrs", "emcgpu_rng_philox", "emcgpu_rng_replay", "emcgpu_bulk_configure",
     "emcgpu_bulk_step", "emcgpu_bulk_step_device", "emcgpu_bulk_observables", "emcgpu_set_step_index",
@@ -219,6 +221,22 @@ class Context:
         self._chk(self.L.emcgpu_set_tables(self.h, arr, len(sets), int(n_levels), float(max_energy)))
 
     # -- ensemble
+    def set_phonon_baths(self, n_baths, n_bins, dq, cum_w=None, cum_wn=None):
+        """cum_w / cum_wn: [n_baths][n_bins + 1] prefix sums of emcPhononBath (only needed for q-resolved angles)"""
+        cw = np.ascontiguousarray(cum_w, dtype=np.float64) if cum_w is not None else None
+        cwn = np.ascontiguousarray(cum_wn, dtype=np.float64) if cum_wn is not None else None
+        self._chk(self.L.emcgpu_set_phonon_baths(self.h, n_baths, n_bins, dq, cw.ctypes.data_as(_DP) if cw is not None else None,
+                                                 cwn.ctypes.data_as(_DP) if cwn is not None else None))
+        self._bath_shape = (n_baths, n_bins)
+
+    def get_phonon_counts(self, reset=True):
+        nb, bins = self._bath_shape
+        em = np.zeros((nb, bins), dtype=np.int64)
+        ab = np.zeros((nb, bins), dtype=np.int64)
+        self._chk(self.L.emcgpu_get_phonon_counts(self.h, em.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                  ab.ctypes.data_as(C.POINTER(C.c_int64)), int(reset)))
+        return em, ab
+
     def set_ensemble(self, streams, packed, particle_id_base=0):
         streams = [np.ascontiguousarray(a, dtype=np.float64) for a in streams]
         packed = np.ascontiguousarray(packed, dtype=np.uint32)

@@ -44,6 +44,7 @@ struct BulkParams {
   long long evCap;
   unsigned long long *evCount;
   int *status;
+  BathView baths; // phonon baths of polar-optical mechanisms (counts == nullptr: none)
 };
 
 constexpr int kBulkThreads = 256;
@@ -241,7 +242,7 @@ __device__ __forceinline__ void scatterLoop(const CtaState &C, const BulkParams 
       if (m >= 0) {
         const DevMech &mech = C.mechs[ts.mechOffset + m];
         mechId = mech.mechId;
-        sampleFinalState<EXACT, RNG_MODE>(model, mech, p, rng);
+        sampleFinalState<EXACT, RNG_MODE>(model, mech, p, rng, P.baths);
       }
       if (P.evCap > 0) {
         const unsigned long long e = atomicAdd(P.evCount, 1ull);

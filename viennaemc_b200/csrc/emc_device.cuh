@@ -443,9 +443,38 @@ __device__ __forceinline__ int selectMechanism(const double *row, int nMech, dou
 }
 
 // Final-state samplers, selected by mechanism ID.
+// emcPhononBath::recordEmission / recordAbsorption (:237-253): one event in the |q| bin of the bath
+__device__ __forceinline__ void bathRecord(const BathView &B, int bath, double q, bool emission) {
+  if (!B.counts || bath < 0 || bath >= B.nBaths) return;
+  const unsigned long long idx = (unsigned long long)(q / B.dq);
+  const int bin = idx >= (unsigned long long)B.nBins ? B.nBins - 1 : (int)idx;
+  atomicAdd(&B.counts[((size_t)bath * 2 + (emission ? 0 : 1)) * B.nBins + bin], 1ull);
+}
+// emcPhononBath::sampleQ (:423-458)
+__device__ __forceinline__ double bathSampleQ(const BathView &B, int bath, double qMin, double qMax, bool emission, double r) {
+  if (B.nBins < 2 || qMax <= qMin) return qMin;
+  long lo = (long)floor(qMin / B.dq), hi = (long)ceil(qMax / B.dq);
+  if (lo < 0) lo = 0;
+  if (hi > (long)B.nBins) hi = (long)B.nBins;
+  if (hi - lo < 1) return qMin;
+  const double *cw = B.cumW + (size_t)bath * (B.nBins + 1), *cwn = B.cumWN + (size_t)bath * (B.nBins + 1);
+  auto S = [&](long i) { return emission ? cwn[i] + cw[i] : cwn[i]; };
+  const double sLo = S(lo), sHi = S(hi), span = sHi - sLo;
+  if (!(span > 0.0)) return 0.5 * (qMin + qMax);
+  const double target = sLo + r * span;
+  long a = lo, b = hi;
+  while (b - a > 1) {
+    const long mid = (a + b) / 2;
+    if (S(mid) <= target) a = mid; else b = mid;
+  }
+  const double sA = S(a), sB = S(a + 1);
+  const double frac = (sB > sA) ? (target - sA) / (sB - sA) : 0.5;
+  return fmax(qMin, fmin(qMax, ((double)a + frac) * B.dq));
+}
+
 template <bool EXACT, int RNG_MODE>
 __device__ __forceinline__ void sampleFinalState(const DevModel &model, const DevMech &mech, Particle &p,
-                                                 Rng &rng) {
+                                                 Rng &rng, const BathView &baths) {
   using A = Arith<EXACT>;
   switch (mech.sampler) {
   case EMCGPU_SAMPLER_ISOTROPIC_ELASTIC: {
@@ -478,6 +507,59 @@ __device__ __forceinline__ void sampleFinalState(const DevModel &model, const De
     const double c = A::sub(1.0, A::div(A::mul(rnd, 2.0), den));
     const double r = uniform01(rng.raw<RNG_MODE>());
     p.k = randomDirectionWrtK<EXACT>(p.k, c, r);
+    break;
+  }
+  case EMCGPU_SAMPLER_FROEHLICH:
+  case EMCGPU_SAMPLER_SCREENED_FROEHLICH: {
+    // polar-optical family (emcFroehlichInteraction.hpp, emcHotPhononFroehlichMechanism.hpp,
+    // emcScreenedFroehlichInteraction.hpp); plain IEEE operations in the reference's order (-fmad=false)
+    const DevValley &v = model.valleys[p.valley];
+    const Vec3 kOld = p.k;
+    const bool emission = mech.param[0] < 0.0;
+    double cosTheta, kNew;
+    if (mech.sampler == EMCGPU_SAMPLER_FROEHLICH) {
+      const double initEnergy = p.energy;
+      p.energy = p.energy + mech.param[0];
+      const double finalEnergy = p.energy;
+      const double d = sqrt(initEnergy) - sqrt(finalEnergy);
+      const double f = 2.0 * sqrt(initEnergy * finalEnergy) / d / d;
+      cosTheta = (1.0 + f - pow(1.0 + 2.0 * f, uniform01(rng.raw<RNG_MODE>()))) / f;
+      cosTheta = fmax(-1.0, fmin(1.0, cosTheta));
+      kNew = normWaveVec<true>(v, p.energy);
+    } else {
+      const double kI = normWaveVec<true>(v, p.energy);
+      p.energy = p.energy + mech.param[0];
+      const double kF = normWaveVec<true>(v, p.energy);
+      const double r = uniform01(rng.raw<RNG_MODE>());
+      const double B = 2.0 * kI * kF;
+      if (B <= 0.0) {
+        cosTheta = 1.0 - 2.0 * r;
+      } else if (mech.flags & 1) {
+        const double q = bathSampleQ(baths, mech.bath, fabs(kI - kF), kI + kF, emission, r);
+        cosTheta = fmax(-1.0, fmin(1.0, (kI * kI + kF * kF - q * q) / B));
+      } else {
+        const double Ap = kI * kI + kF * kF + mech.param[1];
+        const double num = Ap - B, den = Ap + B;
+        if (num <= 0.0 || den <= 0.0)
+          cosTheta = 1.0 - 2.0 * r;
+        else
+          cosTheta = fmax(-1.0, fmin(1.0, (Ap - den * pow(num / den, r)) / B));
+      }
+      kNew = kF;
+    }
+    Vec3 k = randomDirectionWrtK<true>(p.k, cosTheta, uniform01(rng.raw<RNG_MODE>()));
+    const double kCurr = sqrt(sqNorm<true>(k));
+    if (kCurr > 0.0) {
+      const double s = kNew / kCurr;
+      k.x = k.x * s;
+      k.y = k.y * s;
+      k.z = k.z * s;
+    }
+    p.k = k;
+    if (mech.bath >= 0) {
+      const Vec3 q = Vec3{k.x - kOld.x, k.y - kOld.y, k.z - kOld.z};
+      bathRecord(baths, mech.bath, sqrt(sqNorm<true>(q)), emission);
+    }
     break;
   }
   default:

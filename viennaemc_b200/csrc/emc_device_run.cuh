@@ -1055,7 +1055,7 @@ __global__ void __launch_bounds__(kBulkThreads, 2)
           if (m >= 0) {
             const DevMech &mech = C.mechs[ts.mechOffset + m];
             mechId = mech.mechId;
-            sampleFinalState<EXACT, RNG_MODE>(model, mech, p, rng);
+            sampleFinalState<EXACT, RNG_MODE>(model, mech, p, rng, P.baths);
           }
           if (P.evCap > 0) {
             const unsigned long long ev = atomicAdd(P.evCount, 1ull);

@@ -40,6 +40,8 @@ struct DevValley {
 struct DevMech {
   int32_t sampler, finalValley, nFinal, mechId;
   double param[2];
+  int32_t bath;  // phonon bath of a polar-optical mechanism or -1
+  int32_t flags; // bit 0: polar angle through the bath's |q| distribution
   uint8_t finalSub[EMCGPU_MAX_SUBVALLEYS][EMCGPU_MAX_FINAL];
 };
 
@@ -52,6 +54,14 @@ struct DevTableSet {
 };
 
 constexpr int kMaxRegions = 16;
+
+// phonon baths as the kernels see them (emcgpu_set_phonon_baths)
+struct BathView {
+  unsigned long long *counts; // [nBaths][2][nBins]: emission, absorption
+  const double *cumW, *cumWN; // [nBaths][nBins + 1] or nullptr
+  int32_t nBaths, nBins;
+  double dq;
+};
 
 // Everything the kernels need besides the tables themselves; one copy in
 // global memory, staged to shared memory per CTA (a few KB).

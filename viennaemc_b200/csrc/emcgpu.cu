@@ -103,6 +103,7 @@ void fillBulkParams(emcgpu_ctx *ctx, BulkParams &P) {
   P.evCap = ctx->evCap;
   P.evCount = static_cast<unsigned long long *>(ctx->dEvCount.ptr);
   P.status = static_cast<int *>(ctx->dStatus.ptr);
+  emc::fillBathView(ctx, P.baths);
 }
 
 template <typename K>
@@ -304,6 +305,47 @@ int emcgpu_set_option(emcgpu_ctx *ctx, const char *name, int64_t value) {
   return fail(ctx, EMCGPU_E_INVALID, "unknown option '%s'", name);
 }
 
+int emcgpu_set_phonon_baths(emcgpu_ctx *ctx, int nBaths, int nBins, double dq, const double *cumW, const double *cumWN) {
+  if (!ctx) return EMCGPU_E_INVALID;
+  if (int r = bind(ctx)) return r;
+  if (nBaths < 0 || nBaths > EMCGPU_MAX_BATHS) return fail(ctx, EMCGPU_E_CAPACITY, "%d phonon baths exceed EMCGPU_MAX_BATHS=%d", nBaths, EMCGPU_MAX_BATHS);
+  if (nBaths > 0 && (nBins < 1 || !(dq > 0))) return fail(ctx, EMCGPU_E_INVALID, "bad phonon bath binning");
+  if ((cumW == nullptr) != (cumWN == nullptr)) return fail(ctx, EMCGPU_E_INVALID, "cumW and cumWN go together");
+  const bool sameShape = nBaths == ctx->nBaths && nBins == ctx->nBathBins;
+  const size_t countBytes = (size_t)std::max(1, nBaths) * 2 * std::max(1, nBins) * sizeof(unsigned long long);
+  CUDA_TRY(ctx, ctx->dBathCounts.ensure(countBytes));
+  if (!sameShape) CUDA_TRY(ctx, cudaMemsetAsync(ctx->dBathCounts.ptr, 0, countBytes, ctx->stream)); // counters survive an update of the sums
+  ctx->nBaths = nBaths;
+  ctx->nBathBins = nBins;
+  ctx->bathDq = dq;
+  ctx->bathHasCum = cumW != nullptr && nBaths > 0;
+  if (ctx->bathHasCum) {
+    const size_t n = (size_t)nBaths * (nBins + 1);
+    CUDA_TRY(ctx, ctx->dBathCum.ensure(2 * n * sizeof(double)));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dBathCum.ptr, cumW, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dBathCum.as<double>() + n, cumWN, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return EMCGPU_OK;
+}
+
+int emcgpu_get_phonon_counts(emcgpu_ctx *ctx, int64_t *emission, int64_t *absorption, int reset) {
+  if (!ctx || !emission || !absorption) return EMCGPU_E_INVALID;
+  if (int r = bind(ctx)) return r;
+  if (ctx->nBaths == 0) return EMCGPU_OK;
+  const size_t per = (size_t)ctx->nBathBins;
+  std::vector<unsigned long long> h((size_t)ctx->nBaths * 2 * per);
+  CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), ctx->dBathCounts.ptr, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  if (reset) CUDA_TRY(ctx, cudaMemsetAsync(ctx->dBathCounts.ptr, 0, h.size() * sizeof(unsigned long long), ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int b = 0; b < ctx->nBaths; b++)
+    for (size_t i = 0; i < per; i++) {
+      emission[b * per + i] = (int64_t)h[((size_t)b * 2 + 0) * per + i];
+      absorption[b * per + i] = (int64_t)h[((size_t)b * 2 + 1) * per + i];
+    }
+  return EMCGPU_OK;
+}
+
 int emcgpu_synchronize(emcgpu_ctx *ctx) {
   if (!ctx) return EMCGPU_E_INVALID;
   if (int r = bind(ctx)) return r;
@@ -410,7 +452,7 @@ int emcgpu_set_tables(emcgpu_ctx *ctx, const emcgpu_tableset_t *sets, int nSets,
       char name[EMCGPU_NAME_LEN + 1];
       memcpy(name, mi.name, EMCGPU_NAME_LEN);
       name[EMCGPU_NAME_LEN] = 0;
-      if (mi.sampler <= EMCGPU_SAMPLER_NONE || mi.sampler > EMCGPU_SAMPLER_COULOMB)
+      if (mi.sampler <= EMCGPU_SAMPLER_NONE || mi.sampler > EMCGPU_SAMPLER_SCREENED_FROEHLICH)
         return fail(ctx, EMCGPU_E_UNSUPPORTED_MECHANISM,
                     "scatter mechanism '%s' (valley %d, region %d) has no device sampler; it cannot run on "
                     "the GPU path and there is no CPU fallback",
@@ -423,6 +465,16 @@ int emcgpu_set_tables(emcgpu_ctx *ctx, const emcgpu_tableset_t *sets, int nSets,
       d.mechId = mi.mechId;
       d.param[0] = mi.param[0];
       d.param[1] = mi.param[1];
+      d.bath = -1;
+      if (mi.sampler == EMCGPU_SAMPLER_FROEHLICH || mi.sampler == EMCGPU_SAMPLER_SCREENED_FROEHLICH) {
+        d.bath = mi.param[2] >= 0 ? (int32_t)mi.param[2] : -1;
+        d.flags = mi.param[3] != 0 ? 1 : 0;
+        if (d.bath >= ctx->nBaths)
+          return fail(ctx, EMCGPU_E_INVALID, "mechanism '%s' refers to phonon bath %d: call emcgpu_set_phonon_baths first", name,
+                      d.bath);
+        if ((d.flags & 1) && (d.bath < 0 || !ctx->bathHasCum))
+          return fail(ctx, EMCGPU_E_INVALID, "mechanism '%s' samples |q| from a phonon bath whose prefix sums were not given", name);
+      }
       if (mi.sampler == EMCGPU_SAMPLER_INTERVALLEY) {
         if (mi.finalValley < 0 || mi.finalValley >= M.nValleys)
           return fail(ctx, EMCGPU_E_INVALID, "mechanism '%s': final valley %d does not exist", name, mi.finalValley);

@@ -114,6 +114,7 @@ void fillParams(emcgpu_ctx *ctx, BulkParams &P) {
   P.evCap = ctx->evCap;
   P.evCount = ctx->dEvCount.as<unsigned long long>();
   P.status = ctx->dStatus.as<int>();
+  emc::fillBathView(ctx, P.baths);
 }
 
 int readStatus(emcgpu_ctx *ctx) {

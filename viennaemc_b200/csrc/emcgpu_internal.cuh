@@ -76,6 +76,12 @@ struct emcgpu_ctx {
   int mathMode = EMCGPU_MATH_EXACT;
   int64_t nextStep = 1;
 
+  // phonon baths of polar-optical mechanisms (emcgpu_set_phonon_baths)
+  int nBaths = 0, nBathBins = 0;
+  double bathDq = 0;
+  bool bathHasCum = false;
+  emc::DeviceBuffer dBathCounts, dBathCum;
+
   // outputs
   emc::DeviceBuffer dObs, dStatus, dEvents, dEvCount;
   int64_t evCap = 0;
@@ -94,6 +100,15 @@ int failWith(emcgpu_ctx *ctx, int code, const char *fmt, ...);
     if (_e != cudaSuccess)                                                                    \
       return emc::failWith(ctx, EMCGPU_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
   } while (0)
+
+inline void fillBathView(const emcgpu_ctx *ctx, BathView &B) {
+  B.counts = ctx->nBaths ? ctx->dBathCounts.as<unsigned long long>() : nullptr;
+  B.cumW = ctx->bathHasCum ? ctx->dBathCum.as<const double>() : nullptr;
+  B.cumWN = ctx->bathHasCum ? ctx->dBathCum.as<const double>() + (size_t)ctx->nBaths * (ctx->nBathBins + 1) : nullptr;
+  B.nBaths = ctx->nBaths;
+  B.nBins = ctx->nBathBins;
+  B.dq = ctx->bathDq;
+}
 
 inline int bindDevice(emcgpu_ctx *ctx) {
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
