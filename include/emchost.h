@@ -50,6 +50,27 @@ int emchost_si_tables(const emchost_si_spec *spec, double *cum, int64_t cumCapac
 int64_t emchost_si_initial_ensemble(const emchost_si_spec *spec, uint64_t seed, int64_t capacity, double *const *soa,
                                     uint32_t *packed, double *grainTau);
 
+/* ---- beta-Ga2O3 with polar-optical scattering and phonon baths (config 5) -------------------------------------
+ * The set-up of examples/hotPhononGa2O3 (Ga2O3Functions.hpp parameters; one region, Gamma valley, acoustic + non-polar
+ * optical [+ Brooks-Herring] + polar optical) built with the drop-in host classes emcPhononBath, emcPlasmonScreening and
+ * the eight Froehlich mechanism classes. */
+typedef struct {
+  int32_t polar;      /* 0 emcFroehlich*3D, 1 emcHotPhononFroehlich*3D, 2 emcScreenedFroehlich*3D, 3 emcScreenedHotPhononFroehlich*3D */
+  int32_t multimode, screening, qResolved, qResolvedAngle, acousticBath, impurity, nLevels;
+  double maxEnergy, temperature, doping, box, tauLO, tauAc;
+} emchost_ga2o3_spec;
+
+/* CPU only: drives the HOST side of the hot-phonon loop (hotPhononGa2O3.cpp:270-282) with given inputs -- per step the
+ * event counts per bath and |q| bin (counts: [nSteps][nBaths][2][nBins], emission then absorption; may be NULL without
+ * baths) and the mean carrier energy (meanEnergy: [nSteps], used by the screening update) -- and returns what the
+ * reference would have: cumulative tables before the first step and after the last one ([nMech][nLevels] each), tau
+ * after every table rebuild, <N_q> of every bath after every update ([nSteps][nBaths]) and the final occupations
+ * ([nBaths][nBins]).  Any output may be NULL.  Returns the number of mechanisms or a negative emcgpu_status. */
+int emchost_ga2o3_host_loop(const emchost_ga2o3_spec *spec, int nSteps, double dt, const double *counts, const double *meanEnergy,
+                            double *cumInitial, double *cumFinal, double *tauSeries, double *meanNq, double *finalNq);
+/* emcgpu_set_valleys + emcgpu_set_phonon_baths + emcgpu_set_tables for that model (initial state) */
+int emchost_ga2o3_upload(emcgpu_ctx *ctx, const emchost_ga2o3_spec *spec);
+
 #ifdef __cplusplus
 }
 #endif

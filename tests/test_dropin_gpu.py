@@ -242,3 +242,50 @@ def test_unmodified_reference_mosfet_main_starts_on_the_gpu_path(tmp_path):
     st = _mosfet_stats()
     assert abs(n - st["n_final_mean"]) < 0.02 * st["n_final_mean"]
     assert "Nr. Iteration: \t\t1000 / 66667" in out
+
+
+# ---- hot-phonon Ga2O3 bulk (config 5): phonon baths fed by device counters, Froehlich tables rebuilt every step ----------
+def _ga2o3_stats():
+    with open(os.path.join(GOLDEN_DIR, "ref_ga2o3_stats.json")) as f:
+        return json.load(f)
+
+
+def _check_ga2o3(path, key, n_sigma=3.0):
+    st = _ga2o3_stats()
+    got = np.loadtxt(path)  # F[kV/cm] v[cm/s] <E>[eV] N_LO N_LO/N_0 T_LO[K] T_ac[K]
+    ref, std = np.array(st[key]["mean"]), np.array(st[key]["std"])
+    widen = np.sqrt(1 + 1 / len(st["seeds"]))
+    # the scatter itself is estimated from a handful of seeds: "3 sigma" (99.73 %) of a normal variable becomes the same
+    # quantile of Student's t with n - 1 degrees of freedom
+    from scipy import stats
+    n_sigma = float(stats.t.ppf(stats.norm.cdf(n_sigma), df=len(st["seeds"]) - 1))
+    assert got.shape == ref.shape and np.array_equal(got[:, 0], ref[:, 0])
+    for col, name, floor in ((1, "velocity", 0.005), (2, "energy", 0.01), (3, "N_LO", 0.002)):
+        tol = n_sigma * std[:, col] * widen + floor * np.abs(ref[:, col])  # the files hold 4-5 significant digits
+        assert np.all(np.abs(got[:, col] - ref[:, col]) <= tol), (name, got[:, col], ref[:, col], tol)
+    return got
+
+
+def test_unmodified_reference_hot_phonon_main_runs_on_the_gpu_path(tmp_path):
+    """examples/hotPhononGa2O3/hotPhononGa2O3.cpp of the reference (its own Ga2O3Functions.hpp and CLI) compiled against
+    our headers: v, <E> and the LO occupation at 100 / 300 kV/cm within the reference's seed-to-seed scatter"""
+    exe = os.path.join(BIN, "reference_hotPhononGa2O3_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("reference_hotPhononGa2O3_gpu is built only where the reference tree is mounted")
+    st = _ga2o3_stats()
+    r = subprocess.run([exe, "--fields", "100,300", "--time", str(st["time"]), "--seed", "11", "--use_hpb", "1"], cwd=tmp_path,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    got = _check_ga2o3(os.path.join(tmp_path, "ga2o3_vE_hpb.txt"), "hpb")
+    assert np.all(got[:, 4] > 1.0)  # the LO mode heats up above its equilibrium occupation
+
+
+@pytest.mark.parametrize("hpb", [1, 0], ids=["hot_phonons", "equilibrium"])
+def test_own_hot_phonon_driver_matches_reference_within_3_sigma(tmp_path, hpb):
+    exe = os.path.join(BIN, "hotPhononGa2O3")
+    assert os.path.exists(exe), "build with python -m viennaemc_b200.build"
+    st = _ga2o3_stats()
+    r = subprocess.run([exe, "--fields", "100,300", "--time", str(st["time"]), "--seed", "12", "--use-hpb", str(hpb), "--outdir",
+                        str(tmp_path)], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    _check_ga2o3(os.path.join(tmp_path, "ga2o3_vE_" + ("hpb" if hpb else "eq") + ".txt"), "hpb" if hpb else "eq")

@@ -89,3 +89,25 @@ def test_unmodified_reference_example_compiles_against_the_dropin_headers():
                         os.path.join(REFERENCE, "examples", "bulkSimulation", "bulkSimulation.cpp")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[:4000]
+
+
+# ---- config 5: host side of the hot-phonon loop (emcPhononBath, emcPlasmonScreening, Froehlich rate classes) ----------
+@pytest.mark.parametrize("case", ["ga2o3_hot", "ga2o3_qres", "ga2o3_plain_hot", "ga2o3_eq", "ga2o3_screened_eq"])
+def test_ga2o3_host_loop_reproduces_the_reference_bit_for_bit(case):
+    """The drop-in host classes driven with the event counts and mean energies the UNMODIFIED reference recorded
+    (tests/golden/ga2o3_*.npz): rate tables before the first and after the last step, tau after every rebuild, <N_q> after
+    every bath update and the final occupations are the reference's, bit for bit."""
+    from helpers import load_golden
+    from scenarios import ga2o3_args
+    g = load_golden(case)
+    a = ga2o3_args(case)
+    spec = hostapi.ga2o3_spec(**a)
+    n_baths = g["mean_nq"].shape[1] if "mean_nq" in g.files else 0
+    counts = g["bath_counts"] if n_baths else None
+    out = hostapi.ga2o3_host_loop(spec, a["dt"], counts, g["obs"][:, 0], n_baths)
+    assert np.array_equal(out["cum_initial"], g["init_cum_v0_r0"])
+    assert np.array_equal(out["tau"], g["tau_series"])
+    assert np.array_equal(out["cum_final"], g["final_cum_v0_r0"])
+    if n_baths:
+        assert np.array_equal(out["mean_nq"], g["mean_nq"])
+        assert np.array_equal(out["final_nq"], g["final_nq"])

@@ -77,7 +77,8 @@ def build_examples(force: bool = False) -> dict:
     common = ["g++", *HOST_FLAGS, "-I", HOST_INC, "-I", os.path.join(ROOT, "include")]
     link = ["-L", LIBDIR, "-lemcgpu", "-Wl,-rpath,$ORIGIN/../lib"]
     deps = _sources(os.path.join(PKG, "host"), os.path.join(ROOT, "include")) + [os.path.join(LIBDIR, "libemcgpu.so")]
-    for name in ("bulkSimulation", "resistor2D", os.path.join("mosfet2D", "mosfet2D")):
+    for name in ("bulkSimulation", "resistor2D", os.path.join("mosfet2D", "mosfet2D"),
+                 os.path.join("hotPhononGa2O3", "hotPhononGa2O3")):
         own = os.path.join(PKG, "host", "examples", name + ".cpp")
         name = os.path.basename(name)
         if os.path.exists(own):
@@ -92,6 +93,14 @@ def build_examples(force: bool = False) -> dict:
                                ref_main, *link])
     if os.path.exists(target):
         out["reference_bulkSimulation_gpu"] = target
+    # the UNMODIFIED hot-phonon example (its own Ga2O3Functions.hpp included; the handler swapped like above)
+    ref_main = os.path.join(REFERENCE, "examples", "hotPhononGa2O3", "hotPhononGa2O3.cpp")
+    target = os.path.join(bindir, "reference_hotPhononGa2O3_gpu")
+    if os.path.exists(ref_main) and (force or _newer(target, deps)):
+        subprocess.check_call([*common, "-include", os.path.join(HOST_INC, "basicBulkParticleHandler.hpp"), "-o", target,
+                               ref_main, *link])
+    if os.path.exists(target):
+        out["reference_hotPhononGa2O3_gpu"] = target
     # the UNMODIFIED device-run examples of the reference (emcSimulation + emcBasicParticleHandler + emcSORSolver +
     # PM scheme) compiled against OUR headers: every object they create is the GPU-backed drop-in
     for name, rel in (("reference_resistor2D_gpu", ("examples", "resistor2D", "resistor2D.cpp")),):

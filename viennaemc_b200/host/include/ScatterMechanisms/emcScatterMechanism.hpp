@@ -31,6 +31,8 @@ struct emcDeviceSamplerDesc {
   double param[4] = {0., 0., 0., 0.};
 };
 
+template <class T> class emcPhononBath; // emcPhononBath.hpp
+
 template <class T> struct emcScatterMechanism {
   typedef emcAbstractValley<T> AbstractValley;
 
@@ -51,6 +53,9 @@ public:
 
   // device final-state sampler of this mechanism in a region; valid after the tables were built
   virtual emcDeviceSamplerDesc deviceSampler(SizeType /*idxRegion*/) const { return emcDeviceSamplerDesc(); }
+
+  // phonon bath whose event counters this mechanism feeds on the device (polar-optical hot-phonon mechanisms)
+  virtual emcPhononBath<T> *devicePhononBath() const { return nullptr; }
 
   void setPtrValley(std::vector<std::unique_ptr<AbstractValley>> &inPtrValley) {
     for (auto &v : inPtrValley)

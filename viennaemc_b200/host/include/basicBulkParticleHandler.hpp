@@ -37,6 +37,7 @@
 #include <ParticleType/emcParticleType.hpp>
 #include <detail/emcBulkEnsembleBuilder.hpp>
 #include <emcGpuBinding.hpp>
+#include <emcPhononBath.hpp>
 #include <emcGrid.hpp>
 #include <emcParticleInitialization.hpp>
 #include <emcUtil.hpp>
@@ -57,6 +58,8 @@ private:
     bool uploaded = false;
     std::vector<double> lastObs; // [valley][3] sums of the last step (or of the resting ensemble)
     bool obsValid = false;
+    SizeType tableVersion = 0;                    // version of the scatter tables on the device
+    std::vector<emcPhononBath<T> *> phononBaths;  // baths fed by the polar-optical mechanisms of the type
   };
 
   DeviceType &device;
@@ -112,6 +115,19 @@ private:
       emcgpu::require(st.ctx, emcgpu_get_ensemble(st.ctx, ptrs, out.packed.data()), "emcgpu_get_ensemble");
   }
 
+  // tables rebuilt on the host since the last upload (reinitScatterTables, e.g. after a phonon-bath update): upload
+  // them again; the prefix sums of the baths follow the baths in any case (the q-resolved angle reads them)
+  void refreshModel(SizeType idxType) {
+    auto &st = state[idxType];
+    auto &type = *idxTypeToPartType[idxType];
+    if (type.scatterHandler.getTableVersion() != st.tableVersion) {
+      emcgpu::uploadParticleType(st.ctx, type);
+      st.tableVersion = type.scatterHandler.getTableVersion();
+    } else {
+      emcgpu::uploadPhononBaths(st.ctx, st.phononBaths);
+    }
+  }
+
   const std::vector<double> &observables(SizeType idxType) {
     auto &st = state.at(idxType);
     if (!st.obsValid) {
@@ -154,6 +170,8 @@ public:
                       emcgpu_last_error(nullptr))
             .print();
       emcgpu::uploadParticleType(st.ctx, *type);
+      st.tableVersion = type->scatterHandler.getTableVersion();
+      st.phononBaths = emcgpu::collectPhononBaths(*type);
       configure(idxType);
     }
   }
@@ -223,8 +241,10 @@ public:
       if (st.nrParticles == 0)
         continue;
       upload(idxType);
+      refreshModel(idxType);
       st.lastObs.assign(type->getNrValleys() * 3, 0.);
       emcgpu::require(st.ctx, emcgpu_bulk_step(st.ctx, tStep, 1, 1, st.lastObs.data()), "emcgpu_bulk_step");
+      emcgpu::collectPhononCounts(st.ctx, st.phononBaths); // recordEmission / recordAbsorption of this step
       st.obsValid = true;
     }
   }
@@ -235,13 +255,23 @@ public:
   void moveParticles(T tStep, SizeType nSteps, SizeType stepsPerLaunch, SizeType idxType, std::vector<double> &series) {
     auto &st = state.at(idxType);
     upload(idxType);
+    refreshModel(idxType);
     const SizeType nV = idxTypeToPartType[idxType]->getNrValleys();
     series.assign(nSteps * nV * 3, 0.);
     emcgpu::require(st.ctx,
                     emcgpu_bulk_step(st.ctx, tStep, static_cast<int>(nSteps), static_cast<int>(stepsPerLaunch), series.data()),
                     "emcgpu_bulk_step");
+    emcgpu::collectPhononCounts(st.ctx, st.phononBaths);
     st.lastObs.assign(series.end() - nV * 3, series.end());
     st.obsValid = true;
+  }
+
+  // band filling (reference :380-470) serialises the particle loop: not on the GPU path, and never run on the CPU here
+  template <class PauliExclusion> void moveParticleTypeWithBandFilling(T, SizeType, PauliExclusion &) {
+    emcMessage::getInstance()
+        .addError("moveParticleTypeWithBandFilling: Pauli exclusion makes the particle loop sequential; it has no GPU "
+                  "implementation and there is no CPU fallback.")
+        .print();
   }
 
   // "<prefix><TypeName><suffix>.txt": box extent, then per particle: index, position[, k, energy, sub-valley, valley]

@@ -10,6 +10,7 @@
 #ifndef EMC_GPU_BINDING_HPP
 #define EMC_GPU_BINDING_HPP
 
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -18,6 +19,7 @@
 
 #include <ParticleType/emcParticleType.hpp>
 #include <emcMessage.hpp>
+#include <emcPhononBath.hpp>
 
 namespace emcgpu {
 
@@ -29,7 +31,51 @@ inline void require(emcgpu_ctx *ctx, int status, const std::string &what) {
       .print();
 }
 
-// emcgpu_set_valleys + emcgpu_set_tables for one particle type.  To be called after
+// the phonon baths the mechanisms of a particle type feed, in the order of first appearance (= device bath index)
+template <class T, class DeviceType>
+std::vector<emcPhononBath<T> *> collectPhononBaths(const emcParticleType<T, DeviceType> &type) {
+  std::vector<emcPhononBath<T> *> baths;
+  const auto &handler = type.scatterHandler;
+  for (SizeType m = 0; m < handler.getNrMechanisms(); m++) {
+    auto *bath = handler.getMechanism(m).devicePhononBath();
+    if (bath && std::find(baths.begin(), baths.end(), bath) == baths.end())
+      baths.push_back(bath);
+  }
+  return baths;
+}
+
+// emcgpu_set_phonon_baths: binning and the prefix sums the q-resolved polar angle is drawn from
+template <class T> void uploadPhononBaths(emcgpu_ctx *ctx, const std::vector<emcPhononBath<T> *> &baths) {
+  if (baths.empty())
+    return;
+  std::vector<double> cumW, cumWN;
+  for (const auto *b : baths) {
+    if (b->nrBins != baths[0]->nrBins || b->dq != baths[0]->dq)
+      emcMessage::getInstance().addError("All phonon baths of a particle type must share one |q| binning on the GPU path.").print();
+    cumW.insert(cumW.end(), b->cumW.begin(), b->cumW.end());
+    cumWN.insert(cumWN.end(), b->cumWN.begin(), b->cumWN.end());
+  }
+  require(ctx,
+          emcgpu_set_phonon_baths(ctx, static_cast<int>(baths.size()), static_cast<int>(baths[0]->nrBins), baths[0]->dq,
+                                  cumW.data(), cumWN.data()),
+          "emcgpu_set_phonon_baths");
+}
+
+// recordEmission / recordAbsorption of the step(s) since the last call: device counters -> nEm / nAbs of the baths
+template <class T> void collectPhononCounts(emcgpu_ctx *ctx, const std::vector<emcPhononBath<T> *> &baths) {
+  if (baths.empty())
+    return;
+  const SizeType bins = baths[0]->nrBins;
+  std::vector<int64_t> em(baths.size() * bins), ab(baths.size() * bins);
+  require(ctx, emcgpu_get_phonon_counts(ctx, em.data(), ab.data(), 1), "emcgpu_get_phonon_counts");
+  for (SizeType b = 0; b < baths.size(); b++)
+    for (SizeType i = 0; i < bins; i++) {
+      baths[b]->nEm[i] += static_cast<T>(em[b * bins + i]);
+      baths[b]->nAbs[i] += static_cast<T>(ab[b * bins + i]);
+    }
+}
+
+// emcgpu_set_valleys + emcgpu_set_phonon_baths + emcgpu_set_tables for one particle type.  To be called after
 // init/reinitScatterTables(); may be repeated whenever the tables were rebuilt.
 template <class T, class DeviceType> void uploadParticleType(emcgpu_ctx *ctx, const emcParticleType<T, DeviceType> &type) {
   const SizeType nValleys = type.getNrValleys();
@@ -69,6 +115,8 @@ template <class T, class DeviceType> void uploadParticleType(emcgpu_ctx *ctx, co
   require(ctx, emcgpu_set_valleys(ctx, valleys.data(), static_cast<int>(nValleys)), "emcgpu_set_valleys");
 
   const auto &handler = type.scatterHandler;
+  const auto baths = collectPhononBaths(type);
+  uploadPhononBaths(ctx, baths);
   const SizeType nLevels = handler.getNrEnergyLevels();
   std::vector<emcgpu_tableset_t> sets;
   std::vector<std::vector<double>> cumStore;
@@ -91,6 +139,8 @@ template <class T, class DeviceType> void uploadParticleType(emcgpu_ctx *ctx, co
       out.mechId = static_cast<int32_t>(set.mechanisms[m]);
       for (int i = 0; i < 4; i++)
         out.param[i] = desc.param[i];
+      if (auto *bath = mech.devicePhononBath())
+        out.param[2] = static_cast<double>(std::find(baths.begin(), baths.end(), bath) - baths.begin());
       std::strncpy(out.name, mech.getName().c_str(), EMCGPU_NAME_LEN - 1);
       if (!desc.finalSubValleys.empty()) {
         out.nFinal = static_cast<int32_t>(desc.finalSubValleys.begin()->second.size());

@@ -47,6 +47,7 @@ private:
   std::vector<std::unique_ptr<ScatterMechanism>> mechanismList;
   std::map<ValleyRegion, TableSet> sets;
   T grainTau = 1.;
+  SizeType tableVersion = 0;
   std::unique_ptr<emcGrainScatterMechanism<T>> grainMechanism;
   std::vector<std::unique_ptr<emcSurfaceScatterMechanism<T, DeviceType>>> surfaceMechanisms; // [2 * Dim], null = specular
 
@@ -134,13 +135,18 @@ public:
     return face < surfaceMechanisms.size() ? surfaceMechanisms[face].get() : nullptr;
   }
 
+  // incremented by every (re)build of the tables: lets a GPU particle handler notice that it has to upload them again
+  SizeType getTableVersion() const { return tableVersion; }
+
   void initScatterTables() {
+    tableVersion++;
     tabulate();
     if (writeRateFiles)
       writeTablesToFiles();
     accumulateAndNormalise();
   }
   void reinitScatterTables() {
+    tableVersion++;
     tabulate();
     accumulateAndNormalise();
   }

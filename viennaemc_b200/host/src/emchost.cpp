@@ -12,6 +12,7 @@
 #include <emcGpuBinding.hpp>
 
 #include "../examples/SiliconModel.hpp"
+#include "../examples/hotPhononGa2O3/Ga2O3Model.hpp"
 
 namespace {
 
@@ -34,9 +35,123 @@ struct Model {
   }
 };
 
+struct Ga2O3 {
+  Device device;
+  std::unique_ptr<Electron> electrons;
+  std::vector<std::shared_ptr<emcPhononBath<double>>> baths;
+  std::shared_ptr<emcPlasmonScreening<double>> screening;
+  explicit Ga2O3(const emchost_ga2o3_spec &s)
+      : device(Ga2O3Model::material<double>(), {s.box, s.box, s.box}, {s.box / 2., s.box / 2., s.box / 2.}, s.temperature),
+        electrons(std::make_unique<Electron>(s.nLevels, s.maxEnergy, false)) {
+    const Ga2O3Model::Parameters p;
+    device.addConstantDopingRegion({0, 0, 0}, {s.box, s.box, s.box}, s.doping);
+    electrons->scatterHandler.writeRateFiles = false;
+    electrons->scatterHandler.reportTau = false;
+    if (s.polar >= 2) {
+      Ga2O3Model::Parameters q = p;
+      q.tauLO = s.tauLO;
+      q.tauAc = s.tauAc;
+      auto setup = Ga2O3Model::addBandAndScattering<double>(electrons, device, s.polar == 3, s.multimode != 0, s.screening != 0,
+                                                            s.qResolved != 0, s.qResolvedAngle != 0, s.impurity != 0,
+                                                            s.acousticBath != 0, s.temperature, s.box * s.box * s.box, q);
+      baths = setup.baths;
+      screening = setup.screening;
+    } else {
+      // the unscreened classes, assembled like Ga2O3Functions.hpp:173-222 (full static permittivity for every mode)
+      typedef std::map<SizeType, std::vector<SizeType>> SubValleyMap;
+      electrons->addValley(std::make_unique<emcNonParabolicIsotropValley<double>>(p.relEffMass, electrons->getMass(), 1, p.alpha));
+      const std::vector<int> regions = {0};
+      electrons->addScatterMechanism(regions, std::make_unique<emcAcousticScatterMechanism<double>>(0, p.sigmaAc, device));
+      const SubValleyMap same = {{0, {0}}};
+      electrons->addScatterMechanism(regions, std::make_unique<emcZeroOrderInterValleyAbsorptionScatterMechanism<double>>(
+                                                  "NPO", 0, same, p.defPotNPO, p.hwNPO, device));
+      electrons->addScatterMechanism(regions, std::make_unique<emcZeroOrderInterValleyEmissionScatterMechanism<double>>(
+                                                  "NPO", 0, same, p.defPotNPO, p.hwNPO, device));
+      if (s.impurity)
+        electrons->addScatterMechanism(regions, std::make_unique<emcCoulombScatterMechanism<double, Device>>(0, p.epsLo, device));
+      const std::vector<double> modes = s.multimode ? p.hwModes : std::vector<double>{p.hwPOP};
+      screening = std::make_shared<emcPlasmonScreening<double>>(p.epsLo, s.screening != 0);
+      for (SizeType m = 0; m < modes.size(); m++) {
+        const std::string suffix = "Ga2O3-" + std::to_string(m);
+        if (s.polar == 1) {
+          baths.push_back(std::make_shared<emcPhononBath<double>>(p.nrPhononBins, p.dqBin, s.tauLO, modes[m], s.temperature,
+                                                                  s.box * s.box * s.box, s.acousticBath != 0, modes[m] / 2., s.tauAc));
+          electrons->addScatterMechanism(regions, std::make_unique<emcHotPhononFroehlichAbsorption3D<double>>(
+                                                      0, modes[m], p.relEffMass, p.epsHi, p.epsLo, baths[m], suffix));
+          electrons->addScatterMechanism(regions, std::make_unique<emcHotPhononFroehlichEmission3D<double>>(
+                                                      0, modes[m], p.relEffMass, p.epsHi, p.epsLo, baths[m], suffix));
+        } else {
+          electrons->addScatterMechanism(regions, std::make_unique<emcFroehlichAbsorption3D<double>>(
+                                                      0, modes[m], p.relEffMass, p.epsHi, p.epsLo, s.temperature, "Ga2O3"));
+          electrons->addScatterMechanism(regions, std::make_unique<emcFroehlichEmission3D<double>>(
+                                                      0, modes[m], p.relEffMass, p.epsHi, p.epsLo, s.temperature, "Ga2O3"));
+        }
+      }
+    }
+    screening->update(s.doping, s.temperature);
+    for (auto &b : baths)
+      b->setScreeningQ2(screening->getQs2());
+    electrons->initScatterTables();
+  }
+  void copyTables(double *cum, int nLevels) const {
+    const auto &set = electrons->scatterHandler.getTableSets().at({0, 0});
+    for (size_t i = 0; i < set.cum.size(); i++)
+      std::copy(set.cum[i].begin(), set.cum[i].end(), cum + i * nLevels);
+  }
+};
+
 } // namespace
 
 extern "C" {
+
+int emchost_ga2o3_host_loop(const emchost_ga2o3_spec *spec, int nSteps, double dt, const double *counts, const double *meanEnergy,
+                            double *cumInitial, double *cumFinal, double *tauSeries, double *meanNq, double *finalNq) {
+  if (!spec || nSteps < 0)
+    return -EMCGPU_E_INVALID;
+  Ga2O3 g(*spec);
+  const size_t nB = g.baths.size(), bins = nB ? g.baths[0]->nrBins : 0;
+  if (cumInitial)
+    g.copyTables(cumInitial, spec->nLevels);
+  for (int s = 0; s < nSteps; s++) {
+    bool stale = false;
+    if (spec->screening) {
+      g.screening->update(spec->doping, 2. * meanEnergy[s] * constants::q / (3. * constants::kB));
+      for (auto &b : g.baths)
+        b->setScreeningQ2(g.screening->getQs2());
+      stale = true;
+    }
+    for (size_t b = 0; b < nB; b++) {
+      const double *em = counts + ((size_t)(s * nB + b) * 2 + 0) * bins, *ab = em + bins;
+      for (size_t i = 0; i < bins; i++) {
+        g.baths[b]->nEm[i] += em[i];
+        g.baths[b]->nAbs[i] += ab[i];
+      }
+      g.baths[b]->update(dt);
+      stale = true;
+    }
+    if (stale)
+      g.electrons->reinitScatterTables();
+    if (tauSeries)
+      tauSeries[s] = g.electrons->getTau(0, 0);
+    if (meanNq)
+      for (size_t b = 0; b < nB; b++)
+        meanNq[s * nB + b] = g.baths[b]->getMeanNq();
+  }
+  if (cumFinal)
+    g.copyTables(cumFinal, spec->nLevels);
+  if (finalNq)
+    for (size_t b = 0; b < nB; b++)
+      std::copy(g.baths[b]->Nq.begin(), g.baths[b]->Nq.end(), finalNq + b * bins);
+  return static_cast<int>(g.electrons->scatterHandler.getTableSets().at({0, 0}).cum.size());
+}
+
+int emchost_ga2o3_upload(emcgpu_ctx *ctx, const emchost_ga2o3_spec *spec) {
+  if (!ctx || !spec)
+    return EMCGPU_E_INVALID;
+  Ga2O3 g(*spec);
+  emcgpu::uploadParticleType(ctx, *g.electrons);
+  return EMCGPU_OK;
+}
 
 int emchost_si_upload(emcgpu_ctx *ctx, const emchost_si_spec *spec) {
   if (!ctx || !spec)
