@@ -338,6 +338,17 @@ int emcgpu_device_run(emcgpu_ctx *ctx, double dt, int nSteps, double accuracyVol
 int emcgpu_device_run_averaging(emcgpu_ctx *ctx, double dt, int nSteps, int nAverage, double accuracyVolt, double omega,
                                 int resetBCFirst, int32_t *counters, int32_t *sweeps);
 
+/* ---- device run on an ensemble sharded over several GPUs ------------------------------------------
+ * One context per GPU holds a block of the particles; potential, field and concentration are replicated.  Per step the
+ * ranks exchange (a) how many reservoir particles each holds per cell -- handleOhmicContacts keeps the FIRST particles of
+ * a cell in global index order, rank r's particles counting before rank r+1's, and the particles a cell is missing are
+ * injected by the ranks in even shares -- and (b) the carriers per grid point after the charge assignment.  Both are
+ * in-place sums over the ranks of a DEVICE buffer of doubles, done by the callback on the given stream (ncclAllReduce
+ * over NVLink in production).  The Poisson solve that follows is replicated and bitwise identical on
+ * every rank.  Counters returned by emcgpu_device_run* are this rank's; sum them over the ranks. */
+typedef void (*emcgpu_allreduce_fn)(void *user, double *deviceBuffer, int64_t count, void *cudaStream);
+int emcgpu_device_set_sharding(emcgpu_ctx *ctx, int rank, int world, emcgpu_allreduce_fn allreduceSum, void *user);
+
 /* ---- diagnostics used by the parity tests ------------------------------ */
 /* log up to capacity scatter selections as (step, particleId, tableIndex or -1
  * for self-scattering, mechId or -1); 0 disables. */

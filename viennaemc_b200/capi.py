@@ -103,6 +103,7 @@ def load():
     L.emcgpu_device_configure.argtypes = [vp, C.POINTER(DeviceC), C.c_double, C.c_double, _DP, C.c_int]
     L.emcgpu_device_set_surface.argtypes = [vp, C.c_int, C.c_int, C.c_double]
     L.emcgpu_device_set_particle_kind.argtypes = [vp, C.c_int]
+    L.emcgpu_device_set_sharding.argtypes = [vp, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.emcgpu_device_set_grid.argtypes = [vp, C.c_int, _DP]
     L.emcgpu_device_get_grid.argtypes = [vp, C.c_int, _DP]
     L.emcgpu_device_reserve.argtypes = [vp, C.c_int64]
@@ -139,7 +140,7 @@ EXPORTED_SYMBOLS = [
     "emcgpu_ensemble_device_ptrs", "emcgpu_rng_philox", "emcgpu_rng_replay", "emcgpu_bulk_configure",
     "emcgpu_bulk_step", "emcgpu_bulk_step_device", "emcgpu_bulk_observables", "emcgpu_set_step_index",
     "emcgpu_get_step_index", "emcgpu_event_log_enable", "emcgpu_event_log_read",
-    "emcgpu_device_configure", "emcgpu_device_set_surface", "emcgpu_device_set_particle_kind", "emcgpu_device_set_grid", "emcgpu_device_get_grid", "emcgpu_device_reserve",
+    "emcgpu_device_configure", "emcgpu_device_set_surface", "emcgpu_device_set_particle_kind", "emcgpu_device_set_sharding", "emcgpu_device_set_grid", "emcgpu_device_get_grid", "emcgpu_device_reserve",
     "emcgpu_device_poisson", "emcgpu_device_efield", "emcgpu_device_assign", "emcgpu_device_concentration",
     "emcgpu_device_step", "emcgpu_device_contacts", "emcgpu_device_run", "emcgpu_device_run_averaging",
 ]
@@ -342,6 +343,11 @@ class Context:
 
     def device_set_surface(self, face, kind, parameter):
         self._chk(self.L.emcgpu_device_set_surface(self.h, face, kind, parameter))
+
+    def device_set_sharding(self, rank, world, callback):
+        """callback: ctypes CFUNCTYPE(None, c_void_p user, c_void_p deviceBuffer, c_int64 count, c_void_p stream)"""
+        self._sharding_cb = callback
+        self._chk(self.L.emcgpu_device_set_sharding(self.h, rank, world, C.cast(callback, C.c_void_p) if callback else None, None))
 
     def device_set_particle_kind(self, kind):
         self._chk(self.L.emcgpu_device_set_particle_kind(self.h, kind))

@@ -239,7 +239,7 @@ struct AssignParams {
   double *sumPot, *sumConc;
   RunCtl *ctl;
   int32_t *counters; // [slots][2][nContacts] or nullptr
-  int32_t closeStep; // 1: the ensemble is ctl->nKept + ctl->toInject particles and the step ends here
+  int32_t closeStep; // 1: the ensemble is ctl->nKept + ctl->toInject particles and the step ends here; 2: only the former
   int32_t useSmem;
 };
 
@@ -302,9 +302,9 @@ __global__ void __launch_bounds__(256) ngpAssignKernel(const __grid_constant__ D
     for (int i = threadIdx.x; i < G.cells; i += blockDim.x)
       if (sCount[i] != 0.0) atomicAdd(&A.count[i], sCount[i]);
   }
-  if (!A.conc && !A.closeStep) return;
+  if (!A.conc && A.closeStep != 1) return;
   if (!lastBlockDone(&A.ctl->ticket[3])) return;
-  const bool average = A.closeStep && A.ctl->slot >= A.ctl->avgFromSlot;
+  const bool average = A.closeStep == 1 && A.ctl->slot >= A.ctl->avgFromSlot;
   if (A.conc)
     for (int cell = threadIdx.x; cell < G.cells; cell += blockDim.x) {
       const double v = cellConcentration(G, cell, __ldcg(A.count + cell));
@@ -314,7 +314,35 @@ __global__ void __launch_bounds__(256) ngpAssignKernel(const __grid_constant__ D
         A.sumConc[cell] = __dadd_rn(A.sumConc[cell], v);
       }
     }
-  if (A.closeStep && threadIdx.x == 0) {
+  if (A.closeStep == 1 && threadIdx.x == 0) {
+    RunCtl &c = *A.ctl;
+    if (A.counters)
+      for (int k = 0; k < G.nContacts; k++) {
+        A.counters[(c.slot * 2 + 0) * G.nContacts + k] = c.removedPerContact[k];
+        A.counters[(c.slot * 2 + 1) * G.nContacts + k] = c.net[k];
+      }
+    for (int k = 0; k < kMaxContacts; k++) c.removedPerContact[k] = c.net[k] = 0;
+    c.n = c.nKept + c.toInject;
+    c.slot++;
+    c.step++;
+    c.runSteps++;
+  }
+}
+
+// Sharded ensembles: the counts of all ranks are summed between the deposit and this kernel (one block), which then does
+// what the last block of ngpAssignKernel does on a single GPU.
+__global__ void __launch_bounds__(1024) concentrationCloseKernel(const __grid_constant__ DevGeometry G, const AssignParams A) {
+  const bool average = A.ctl->slot >= A.ctl->avgFromSlot;
+  for (int cell = threadIdx.x; cell < G.cells; cell += blockDim.x) {
+    const double v = cellConcentration(G, cell, A.count[cell]);
+    A.conc[cell] = v;
+    if (average) {
+      A.sumPot[cell] = __dadd_rn(A.sumPot[cell], A.pot[cell]);
+      A.sumConc[cell] = __dadd_rn(A.sumConc[cell], v);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
     RunCtl &c = *A.ctl;
     if (A.counters)
       for (int k = 0; k < G.nContacts; k++) {
@@ -1213,7 +1241,25 @@ struct ContactParams {
   int32_t *cellCount;      // [cells] scratch, all zero between launches
   int32_t *injectCount;    // [cells + 1] out: particles to inject per cell as an exclusive scan, total at [cells]
   RunCtl *ctl;
+  // ensemble sharded over several GPUs (emcgpu_device_set_sharding): share[r][cell] = reservoir particles of rank r in
+  // that cell, summed over the ranks before this kernel runs; nullptr on a single GPU
+  const double *share;
+  int32_t rank, world;
 };
+
+// How many of the `missing` particles of a reservoir cell this rank injects: an even split whose remainder rotates with
+// the cell and the time step, so that no rank keeps collecting the injected particles (viennaemc_b200/sharding.py holds
+// the same function for the host-side tests).
+__host__ __device__ __forceinline__ int injectShareOfRank(int missing, int rank, int world, int cell, long long step) {
+  const int rotated = (int)((rank + world - (int)((cell + step) % world)) % world);
+  return missing / world + (rotated < missing % world ? 1 : 0);
+}
+
+// reservoir particles of this rank per cell -> its row of the share table
+__global__ void __launch_bounds__(256) contactShareKernel(const ContactParams K, double *shareRow) {
+  const int m = K.ctl->nReservoir;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) atomicAdd(&shareRow[K.listCell[j]], 1.0);
+}
 
 __device__ __forceinline__ int reservoirSlots(double expected, double nrCarriers) {
   return expected > 0.0 ? (int)ceil(expected / nrCarriers) : 0;
@@ -1225,7 +1271,11 @@ __global__ void __launch_bounds__(256) contactRankKernel(const __grid_constant__
     const int cell = K.listCell[j];
     int rank = 0;
     for (int i = 0; i < j; i++) rank += K.listCell[i] == cell;
-    atomicAdd(&K.cellCount[cell], 1);
+    if (K.share) { // particles of the lower ranks come first in the global index order
+      for (int r = 0; r < K.rank; r++) rank += (int)K.share[(size_t)r * G.cells + cell];
+    } else {
+      atomicAdd(&K.cellCount[cell], 1);
+    }
     if (rank >= reservoirSlots(K.expected[cell], K.nrCarriers)) {
       K.flag[K.listParticle[j]] = kGone;
       atomicAdd(&K.ctl->net[cellContact(G, cell)], -1);
@@ -1235,12 +1285,19 @@ __global__ void __launch_bounds__(256) contactRankKernel(const __grid_constant__
   for (int c = threadIdx.x; c < G.cells; c += blockDim.x) {
     int cnt = 0;
     if (G.cellKind[c] & 1u) {
-      const int group = __ldcg(K.cellCount + c);
+      int group;
+      if (K.share) {
+        group = 0;
+        for (int r = 0; r < K.world; r++) group += (int)K.share[(size_t)r * G.cells + c];
+      } else {
+        group = __ldcg(K.cellCount + c);
+        K.cellCount[c] = 0;
+      }
       const int kept = min(group, reservoirSlots(K.expected[c], K.nrCarriers));
       const double diff = K.expected[c] - kept * K.nrCarriers;
       cnt = diff > 0.0 ? (int)ceil(diff / K.nrCarriers) : 0;
+      if (K.share) cnt = injectShareOfRank(cnt, K.rank, K.world, c, K.ctl->step);
       if (cnt) atomicAdd(&K.ctl->net[cellContact(G, c)], cnt);
-      K.cellCount[c] = 0;
     }
     K.injectCount[c] = cnt;
   }
@@ -1266,6 +1323,7 @@ struct InjectParams {
   const uint64_t *replay; // flat draw stream of the contact phase or nullptr
   int64_t replayCount;
   int *status;
+  uint32_t rank; // of a sharded ensemble: keeps the streams of the ranks apart
 };
 
 template <int DIM>
@@ -1306,7 +1364,7 @@ __global__ void __launch_bounds__(128) contactInjectKernel(const __grid_constant
     } else {
       for (int d = 0; d < kDraws; d += 2) {
         uint32_t o[4];
-        philox4x32_10((uint32_t)j, 0xC0117AC7u, (uint32_t)step, (uint32_t)(d >> 1), (uint32_t)J.seed,
+        philox4x32_10((uint32_t)j, 0xC0117AC7u + J.rank, (uint32_t)step, (uint32_t)(d >> 1), (uint32_t)J.seed,
                       (uint32_t)(J.seed >> 32), o);
         raw[d] = (uint64_t)o[1] << 32 | o[0];
         if (d + 1 < kDraws) raw[d + 1] = (uint64_t)o[3] << 32 | o[2];

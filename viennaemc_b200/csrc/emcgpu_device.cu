@@ -22,6 +22,10 @@ struct DeviceRunState {
   DeviceBuffer dCounters, dSweepsPerStep; // per-step outputs of a chunk of the step loop
   DeviceBuffer altEnsemble, altCursor; // second ensemble buffer for the order-preserving compaction
   int64_t reserve = 0;
+  int rank = 0, world = 1; // emcgpu_device_set_sharding
+  emcgpu_allreduce_fn allreduce = nullptr;
+  void *allreduceUser = nullptr;
+  DeviceBuffer dShare; // [world][cells] reservoir particles per rank and cell
   int64_t maxInject = -1; // upper bound of the particles the contacts inject in one step
   int64_t runSteps = 0; // steps done by emcgpu_device_run* since configure (frozen-field sub-cycling)
 };
@@ -31,7 +35,7 @@ void releaseDeviceRun(emcgpu_ctx *ctx) {
   DeviceRunState *r = ctx->run;
   for (DeviceBuffer *b : {&r->dRegion, &r->dFace, &r->dDoping, &r->dDopingNorm, &r->dCellKind, &r->dSorHistory, &r->dCtl, &r->dFlag, &r->dChunkCount, &r->dListParticle,
                           &r->dListCell, &r->dCellCount, &r->dInjectCount, &r->dSweeps, &r->dReplay, &r->dCounters,
-                          &r->dSweepsPerStep, &r->altEnsemble, &r->altCursor})
+                          &r->dSweepsPerStep, &r->altEnsemble, &r->altCursor, &r->dShare})
     b->release();
   for (auto &g : r->grid) g.release();
   delete r;
@@ -255,12 +259,31 @@ int doAssign(emcgpu_ctx *ctx, bool withConc, bool closeStep) {
   A.ctl = r->dCtl.as<RunCtl>();
   A.counters = r->dCounters.as<int32_t>();
   A.closeStep = closeStep ? 1 : 0;
+  const bool sharded = r->world > 1 && withConc;
+  if (sharded) { // deposit only; the counts of all ranks are summed before the concentration is formed
+    A.conc = nullptr;
+    A.closeStep = 0;
+  }
   const size_t smem = (size_t)G.cells * sizeof(double);
   A.useSmem = smem <= 96 * 1024 ? 1 : 0;
   if (A.useSmem) CUDA_TRY(ctx, cudaFuncSetAttribute(ngpAssignKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (sharded && closeStep) { // the ensemble of this step is the survivors plus the injected particles
+    A.closeStep = 2;
+  }
   ngpAssignKernel<<<particleGrid(ctx, 256, 1), 256, A.useSmem ? smem : 0, ctx->stream>>>(G, A);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
+  if (sharded) {
+    r->allreduce(r->allreduceUser, count, G.cells, ctx->stream);
+    A.conc = r->grid[EMCGPU_GRID_CONCENTRATION].as<double>();
+    if (closeStep) {
+      concentrationCloseKernel<<<1, 1024, 0, ctx->stream>>>(G, A);
+    } else {
+      concentrationKernel<<<gridBlocks(G.cells), 256, 0, ctx->stream>>>(G, count, A.conc);
+    }
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+  }
   return EMCGPU_OK;
 }
 
@@ -362,6 +385,18 @@ int doContacts(emcgpu_ctx *ctx, bool fromStep, const uint64_t *replayDraws, int6
   K.cellCount = r->dCellCount.as<int32_t>();
   K.injectCount = r->dInjectCount.as<int32_t>();
   K.ctl = ctl;
+  K.share = nullptr;
+  K.rank = r->rank;
+  K.world = r->world;
+  if (r->world > 1) {
+    const size_t n = (size_t)r->world * G.cells;
+    CUDA_TRY(ctx, r->dShare.ensure(n * sizeof(double)));
+    CUDA_TRY(ctx, cudaMemsetAsync(r->dShare.ptr, 0, n * sizeof(double), ctx->stream));
+    contactShareKernel<<<std::min(grid, 2 * ctx->smCount), 256, 0, ctx->stream>>>(K, r->dShare.as<double>() + (size_t)r->rank * G.cells);
+    ctx->launches++;
+    r->allreduce(r->allreduceUser, r->dShare.as<double>(), (int64_t)n, ctx->stream);
+    K.share = r->dShare.as<const double>();
+  }
   contactRankKernel<<<std::min(grid, 2 * ctx->smCount), 256, 0, ctx->stream>>>(G, K);
   ctx->launches += 3;
   CUDA_TRY(ctx, cudaGetLastError());
@@ -375,6 +410,7 @@ int doContacts(emcgpu_ctx *ctx, bool fromStep, const uint64_t *replayDraws, int6
   J.replay = nullptr;
   J.replayCount = 0;
   J.status = ctx->dStatus.as<int>();
+  J.rank = (uint32_t)r->rank;
   if (replayDraws) {
     CUDA_TRY(ctx, r->dReplay.ensure((size_t)std::max<int64_t>(1, nReplay) * sizeof(uint64_t)));
     CUDA_TRY(ctx, cudaMemcpyAsync(r->dReplay.ptr, replayDraws, nReplay * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -542,6 +578,17 @@ int emcgpu_device_set_surface(emcgpu_ctx *ctx, int face, int kind, double parame
     return fail(ctx, EMCGPU_E_UNSUPPORTED_MECHANISM, "surface scatter mechanism %d has no device implementation", kind);
   ctx->run->geo.surfaceKind[face] = kind;
   ctx->run->geo.surfaceParam[face] = parameter;
+  return EMCGPU_OK;
+}
+
+int emcgpu_device_set_sharding(emcgpu_ctx *ctx, int rank, int world, emcgpu_allreduce_fn allreduceSum, void *user) {
+  if (int r = needRun(ctx)) return r;
+  if (world < 1 || rank < 0 || rank >= world) return fail(ctx, EMCGPU_E_INVALID, "rank %d of %d", rank, world);
+  if (world > 1 && !allreduceSum) return fail(ctx, EMCGPU_E_INVALID, "a sharded run needs the all-reduce callback");
+  ctx->run->rank = rank;
+  ctx->run->world = world;
+  ctx->run->allreduce = allreduceSum;
+  ctx->run->allreduceUser = user;
   return EMCGPU_OK;
 }
 

@@ -1,6 +1,7 @@
-"""Multi-GPU plumbing of the bulk path: block partition of the particle ids and the one collective a
-bulk run needs (sum of the per-step observable series).  torch.distributed only; works with nccl (GPU)
-and gloo (CPU tests)."""
+"""Multi-GPU plumbing: block partition of the particle ids; for bulk runs the one collective they need (sum of the
+per-step observable series); for device runs the per-step all-reduce callback of emcgpu_device_set_sharding (reservoir
+particles per rank and cell, carriers per grid point) and the host mirrors of the rules the kernels use to split the
+contact handling between the ranks.  torch.distributed only; works with nccl (GPU) and gloo (CPU tests)."""
 from __future__ import annotations
 
 import numpy as np
@@ -36,3 +37,64 @@ def finalize_observables(series, n_total=None):
         v = np.where(cnt > 0, s[..., 1] / cnt, 0.0)
         occ = cnt / total
     return e, v, occ
+
+
+# ---- device runs: particles sharded, grids replicated -------------------------------------------------
+def inject_share_of_rank(missing: int, rank: int, world: int, cell: int, step: int) -> int:
+    """How many of the `missing` particles of a reservoir cell a rank injects (injectShareOfRank in
+    viennaemc_b200/csrc/emc_device_run.cuh): an even split whose remainder rotates with cell and step."""
+    rotated = (rank + world - (cell + step) % world) % world
+    return missing // world + (1 if rotated < missing % world else 0)
+
+
+def reservoir_decisions(share, expected, nr_carriers, rank, step):
+    """What rank `rank` does in the reservoir cells given share[r][cell] = reservoir particles of rank r in that cell (the
+    table the ranks all-reduce every step): (kept, dropped, injected) per cell.  Global index order = rank 0's particles,
+    then rank 1's, ...; the first `slots` of a cell survive (handleOhmicContacts, emcBasicParticleHandler.hpp:158-192)."""
+    share = np.asarray(share, dtype=np.int64)
+    world, cells = share.shape
+    slots = np.where(np.asarray(expected) > 0, np.ceil(np.asarray(expected) / nr_carriers), 0).astype(np.int64)
+    lower = share[:rank].sum(axis=0)
+    mine = share[rank]
+    kept = np.clip(slots - lower, 0, mine)
+    total_kept = np.minimum(share.sum(axis=0), slots)
+    diff = np.asarray(expected) - total_kept * nr_carriers
+    missing = np.where(diff > 0, np.ceil(diff / nr_carriers), 0).astype(np.int64)
+    injected = np.array([inject_share_of_rank(int(m), rank, world, c, step) for c, m in enumerate(missing)], dtype=np.int64)
+    return kept, mine - kept, injected
+
+
+class DeviceRunSharding:
+    """Binds a capi.Context to a torch.distributed process group for a sharded device run: installs the all-reduce callback
+    (torch.distributed.all_reduce on a zero-copy view of the library's device buffer, on the same stream)."""
+
+    def __init__(self, ctx, group=None):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        self.ctx, self.group = ctx, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.calls = 0
+
+        class _View:  # __cuda_array_interface__ of a raw device pointer
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = dict(shape=(n,), typestr="<f8", data=(ptr, False), version=2)
+
+        def _allreduce(user, ptr, count, stream):
+            t = torch.as_tensor(_View(ptr, int(count)), device=f"cuda:{torch.cuda.current_device()}")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            self.calls += 1
+
+        self._cb = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)(_allreduce)  # keep alive
+        ctx.device_set_sharding(self.rank, self.world, self._cb)
+
+    def sum_counters(self, counters):
+        """per-contact counters of a run are per rank: the terminal currents need their sum"""
+        import torch
+        import torch.distributed as dist
+
+        t = torch.as_tensor(np.ascontiguousarray(counters, dtype=np.int64)).cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy()
