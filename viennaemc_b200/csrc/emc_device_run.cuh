@@ -18,6 +18,8 @@
 // are latency- not bandwidth-bound, so they are written for few launches and few
 // synchronisations rather than for streaming throughput.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "emc_bulk_kernel.cuh"
 
 namespace emc {
@@ -219,6 +221,12 @@ __device__ __forceinline__ void cellEField(const DevGeometry &G, int cell, const
   }
 }
 __global__ void efieldKernel(const __grid_constant__ DevGeometry G, const double *pot, double *e) {
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell < G.cells) cellEField(G, cell, pot, e);
+}
+// the same after a Poisson solve inside the step loop: skipped together with the solve (frozen-field sub-cycling)
+__global__ void efieldAfterSolveKernel(const __grid_constant__ DevGeometry G, const double *pot, double *e, const RunCtl *ctl) {
+  if (ctl && ctl->runSteps % ctl->poissonInterval != 0) return;
   const int cell = blockIdx.x * blockDim.x + threadIdx.x;
   if (cell < G.cells) cellEField(G, cell, pot, e);
 }
@@ -855,6 +863,164 @@ __global__ void __launch_bounds__(kSorThreads) sorRedBlackKernel(const __grid_co
     __syncthreads();
     for (int i = tid; i < G.cells; i += blockDim.x) cellEField(G, i, S.pot, S.efield);
   }
+}
+
+// Red-black relaxation spread over a thread-block CLUSTER: the grid rows (y, z) are dealt out in contiguous bands to the
+// CTAs of one cluster (8 SMs), each CTA keeps its band of the potential in its own shared memory and reads the
+// neighbour rows of the adjacent bands through distributed shared memory; a cluster barrier separates the two colours
+// and the per-sweep error maxima are exchanged through DSMEM as well.  Same iterates as sorRedBlackKernel (a colour only
+// reads the other colour, so the order inside a half sweep does not matter), but a half sweep costs one pass of
+// 1/8 of the cells plus a ~0.2 us cluster barrier instead of a single-SM pass over all of them.
+constexpr int kSorClusterSize = 8;
+constexpr int kSorClusterThreads = 1024;
+
+template <int DIM>
+__global__ void __launch_bounds__(kSorClusterThreads) sorRedBlackClusterKernel(const __grid_constant__ DevGeometry G, const SorParams S) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ double sBand[]; // [rowsPerCta][ex] potential, then electron density, normalised doping, cell kinds
+  __shared__ double sWarpErr[kSorClusterThreads / 32];
+  __shared__ double sCtaErr; // this CTA's max |delta| of the sweep, read by the whole cluster
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cta = (int)cluster.block_rank(), nCta = (int)cluster.num_blocks();
+  if (S.ctl && S.ctl->runSteps % S.ctl->poissonInterval != 0) { // uniform over the cluster
+    if (cta == 0 && tid == 0 && S.sweepsPerStep) S.sweepsPerStep[S.ctl->slot] = 0;
+    return;
+  }
+  double h[3] = {1, 1, 1}, hF[3] = {0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < DIM; i++) h[i] = __ddiv_rn(G.spacing[i], G.debyeLength);
+  if (DIM == 2) {
+    hF[0] = __ddiv_rn(h[1], h[0]);
+    hF[1] = __ddiv_rn(h[0], h[1]);
+  } else {
+    hF[0] = __ddiv_rn(__dmul_rn(h[1], h[2]), h[0]);
+    hF[1] = __ddiv_rn(__dmul_rn(h[0], h[2]), h[1]);
+    hF[2] = __ddiv_rn(__dmul_rn(h[0], h[1]), h[2]);
+  }
+  double hFSum = 0.0, hProd = 1.0;
+#pragma unroll
+  for (int i = 0; i < DIM; i++) {
+    hFSum = __dadd_rn(hFSum, hF[i]);
+    hProd = __dmul_rn(hProd, h[i]);
+  }
+  const double twoHFSum = __dmul_rn(2.0, hFSum);
+  const int ex = G.extent[0], ey = G.extent[1], ez = DIM > 2 ? G.extent[2] : 1;
+  const int nRows = ey * ez;
+  const int rowsPerCta = (nRows + nCta - 1) / nCta;
+  const int row0 = cta * rowsPerCta, row1 = min(nRows, row0 + rowsPerCta);
+  const int myRows = max(0, row1 - row0);
+  const bool nonEq = S.conc != nullptr;
+  // everything a cell update reads besides the neighbours stays in shared memory as well: cluster barriers invalidate
+  // the L1 cache, so per-sweep global loads would go to L2 every time
+  double *sConc = sBand + (size_t)rowsPerCta * ex, *sDop = sConc + (size_t)rowsPerCta * ex;
+  unsigned char *sKind = reinterpret_cast<unsigned char *>(sDop + (size_t)rowsPerCta * ex);
+  for (int i = tid; i < myRows * ex; i += blockDim.x) {
+    sBand[i] = S.pot[row0 * ex + i];
+    sConc[i] = nonEq ? S.conc[row0 * ex + i] : 0.0;
+    sDop[i] = G.dopingNorm[row0 * ex + i];
+    sKind[i] = G.cellKind[row0 * ex + i];
+  }
+  // the row above / below a band edge lives in the neighbouring CTA (its last / first row)
+  const double *bandBelow = cta > 0 ? cluster.map_shared_rank(sBand, cta - 1) + (size_t)(rowsPerCta - 1) * ex : sBand;
+  const double *bandAbove = cta + 1 < nCta ? cluster.map_shared_rank(sBand, cta + 1) : sBand;
+  // value of any cell (3-D: the z neighbours are ey rows away, possibly several bands)
+  auto potAt = [&](int row, int x) -> double {
+    const int owner = row / rowsPerCta;
+    const double *band = owner == cta ? sBand : cluster.map_shared_rank(sBand, owner);
+    return band[(row - owner * rowsPerCta) * ex + x];
+  };
+  // fixed thread -> (column pair, row) assignment: no index arithmetic inside the sweeps
+  const int halfX = (ex + 1) / 2;
+  const int tx = tid % halfX, ty = tid / halfX, rowStep = max(1, (int)blockDim.x / halfX);
+  const bool worker = ty < rowStep;
+  const double *errOfPeer = cluster.map_shared_rank(&sCtaErr, lane % nCta);
+  cluster.sync();
+  int sweeps = 0;
+  for (;;) {
+    double myErr = 0.0;
+#pragma unroll 1
+    for (int colour = 0; colour < 2; colour++) {
+      for (int local = ty; worker && local < myRows; local += rowStep) {
+        const int row = row0 + local;
+        const int y = DIM == 2 ? row : row % ey, z = DIM == 2 ? 0 : row / ey;
+        const int x = 2 * tx + ((y + z + colour) & 1);
+        if (x >= ex) continue;
+        const int at = local * ex + x;
+        const unsigned kind = sKind[at];
+        if (kind & 1u) continue;
+        const double cur = sBand[at];
+        double p, n;
+        if (nonEq) {
+          p = exp(-cur);
+          n = sConc[at];
+        } else {
+          n = exp(cur);
+          p = __ddiv_rn(1.0, n);
+        }
+        double num = __dmul_rn(hProd, __dadd_rn(__dadd_rn(__dsub_rn(p, n), sDop[at]), __dmul_rn(cur, __dadd_rn(p, n))));
+        double den = __dadd_rn(twoHFSum, __dmul_rn(hProd, __dadd_rn(n, p)));
+        const int c[3] = {x, y, z};
+        const int last[3] = {ex - 1, ey - 1, ez - 1};
+#pragma unroll
+        for (int i = 0; i < DIM; i++) {
+#pragma unroll
+          for (int side = 0; side < 2; side++) {
+            const bool atFace = side == 0 ? c[i] == 0 : c[i] == last[i];
+            const int dir = (side == 0) != atFace ? -1 : 1; // towards the neighbour, mirrored at a face
+            double nb;
+            if (i == 0) {
+              nb = sBand[at + dir];
+            } else if (i == 1) {
+              const int nl = local + dir;
+              nb = nl < 0 ? bandBelow[x] : nl >= myRows ? bandAbove[x] : sBand[nl * ex + x];
+            } else {
+              nb = potAt(row + dir * ey, x);
+            }
+            num = __dadd_rn(num, __dmul_rn(nb, hF[i]));
+            if (atFace && (kind & 2u)) {
+              const int cell = x + ex * row;
+              const int ct = G.faceContact[cell * 2 * DIM + 2 * i + side];
+              if (ct >= 0 && G.contactType[ct] == 2) {
+                const SorGate g = sorGateTerm(G, ct, nonEq, hF[i], h[i]);
+                num = __dadd_rn(num, g.numTerm);
+                den = __dadd_rn(den, g.denTerm);
+              }
+            }
+          }
+        }
+        const double delta = __dmul_rn(S.omega, __dsub_rn(__ddiv_rn(num, den), cur));
+        sBand[at] = __dadd_rn(cur, delta);
+        myErr = fmax(myErr, fabs(delta));
+      }
+      if (colour == 1) { // publish this CTA's maximum before the barrier that ends the sweep
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) myErr = fmax(myErr, __shfl_xor_sync(0xffffffffu, myErr, o));
+        if (lane == 0) sWarpErr[warp] = myErr;
+        __syncthreads();
+        if (warp == 0) {
+          double m = sWarpErr[lane];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+          if (lane == 0) sCtaErr = m;
+        }
+      }
+      cluster.sync();
+    }
+    // every warp gathers the maxima of all CTAs: lane l reads CTA l % nCta
+    double err = *errOfPeer;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) err = fmax(err, __shfl_xor_sync(0xffffffffu, err, o));
+    sweeps++;
+    if (!(err > S.accuracy) || (S.maxSweeps > 0 && sweeps >= S.maxSweeps)) break;
+  }
+  for (int i = tid; i < myRows * ex; i += blockDim.x) S.pot[row0 * ex + i] = sBand[i];
+  if (cta == 0 && tid == 0) {
+    *S.sweepsOut = sweeps;
+    if (S.ctl && S.sweepsPerStep) S.sweepsPerStep[S.ctl->slot] = sweeps;
+  }
+  // keep the bands alive until every peer has read the last error value
+  cluster.sync();
 }
 
 // Dirichlet values at ohmic contacts (emcSORSolver.hpp:57-73, :139-155); faces in the reference's order

@@ -216,8 +216,40 @@ int doPoisson(emcgpu_ctx *ctx, bool equilibrium, double accuracyVolt, double ome
     return cudaGetLastError();
   };
   const int ipt = 16 * nYZ <= kSorPairs ? 1 : 16 * nYZ <= 2 * kSorPairs ? 2 : 4;
-  if (ctx->optSorOrder == 1)
-    CUDA_TRY(ctx, G.dim == 2 ? launch(sorRedBlackKernel<2>, 0) : launch(sorRedBlackKernel<3>, 0));
+  if (ctx->optSorOrder == 1) {
+    // red-black: a cluster of 8 CTAs with the potential banded over their shared memories when the device offers it;
+    // the E field of the result is a separate (tiny) kernel then
+    const int nRowsRb = G.extent[1] * (G.dim > 2 ? G.extent[2] : 1);
+    const int rowsPerCta = (nRowsRb + kSorClusterSize - 1) / kSorClusterSize;
+    const size_t bandBytes = (size_t)rowsPerCta * G.extent[0] * (3 * sizeof(double) + 1) + 16;
+    if (ctx->optSorKernel != 1 && nRowsRb >= kSorClusterSize && bandBytes <= (size_t)ctx->maxSmemOptin - 4096 &&
+        (G.extent[0] + 1) / 2 <= kSorClusterThreads) {
+      auto kernel = G.dim == 2 ? sorRedBlackClusterKernel<2> : sorRedBlackClusterKernel<3>;
+      CUDA_TRY(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bandBytes));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(kSorClusterSize);
+      cfg.blockDim = dim3(kSorClusterThreads);
+      cfg.dynamicSmemBytes = bandBytes;
+      cfg.stream = ctx->stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = kSorClusterSize;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      SorParams S2 = S;
+      S2.efield = nullptr;
+      CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, kernel, G, S2));
+      if (S.efield) {
+        // the field follows the potential; inside the step loop it must skip with the solve (frozen-field sub-cycling)
+        efieldAfterSolveKernel<<<gridBlocks(G.cells), 256, 0, ctx->stream>>>(G, S.pot, S.efield, S.ctl);
+        ctx->launches++;
+      }
+    } else {
+      CUDA_TRY(ctx, G.dim == 2 ? launch(sorRedBlackKernel<2>, 0) : launch(sorRedBlackKernel<3>, 0));
+    }
+  }
   else if (ctx->optSorKernel == 1 || 12 * nYZ > 4 * kSorPairs)
     CUDA_TRY(ctx, launch(sorPlanesKernel, 0));
   else if (ipt == 1)

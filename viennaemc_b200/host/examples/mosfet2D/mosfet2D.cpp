@@ -107,7 +107,8 @@ int main(int argc, char **argv) {
   std::cout << "currents: substrate " << simulation.getAvgCurrent(0, 0) << " A, source " << simulation.getAvgCurrent(0, 1)
             << " A, gate " << simulation.getAvgCurrent(0, 2) << " A, drain " << simulation.getAvgCurrent(0, 3) << " A\n"
             << "wall time " << seconds << " s, " << steps << " steps, " << n << " particles at the end, "
-            << n * steps / seconds << " particle-steps/s, " << double(simulation.getTotalNrSorSweeps()) / steps
+            << n * steps / seconds << " particle-steps/s (Monte Carlo loop alone: " << simulation.getLoopSeconds() << " s, "
+            << n * steps / simulation.getLoopSeconds() << " particle-steps/s), " << double(simulation.getTotalNrSorSweeps()) / steps
             << " SOR sweeps per step\n";
   return 0;
 }

@@ -95,7 +95,8 @@ int main(int argc, char **argv) {
   std::cout << "current XMAX contact: " << simulation.getAvgCurrent(0, 0) << " A, XMIN contact: " << simulation.getAvgCurrent(0, 1)
             << " A\n"
             << "wall time " << seconds << " s, " << steps << " steps, " << n << " particles at the end, "
-            << n * steps / seconds << " particle-steps/s, " << double(simulation.getTotalNrSorSweeps()) / steps
+            << n * steps / seconds << " particle-steps/s (Monte Carlo loop alone: " << simulation.getLoopSeconds() << " s, "
+            << n * steps / simulation.getLoopSeconds() << " particle-steps/s), " << double(simulation.getTotalNrSorSweeps()) / steps
             << " SOR sweeps per step\n";
   return 0;
 }

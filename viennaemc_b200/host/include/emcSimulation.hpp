@@ -15,6 +15,7 @@
 #define EMC_SIMULATION_HPP
 
 #include <algorithm>
+#include <chrono>
 #include <iostream>
 #include <string>
 #include <type_traits>
@@ -54,6 +55,7 @@ template <class T, class DeviceType, class PoissonSolver, class ParticleHandler,
   SizeType driftCurrentCount = 0;
   SizeType poissonInterval = 1;
   long long totalSorSweeps = 0;
+  double loopSeconds = 0; // wall time of the Monte Carlo loop alone (without equilibrium set-up and file output)
 
   emcgpu_ctx *ctx() { return particleHandler.gpuContext(); }
   void fetch(int grid, emcGrid<T, Dim> &into) {
@@ -98,6 +100,7 @@ public:
   const emcSimulationResults<T, DeviceType> &getResults() const { return results; }
   T getAvgCurrent(SizeType idxType, SizeType idxContact) const { return results.getAvgCurrent(idxType, idxContact); }
   long long getTotalNrSorSweeps() const { return totalSorSweeps; }
+  double getLoopSeconds() const { return loopSeconds; }
 
   void execute() {
     const SizeType totalSteps = param.getNrSteps();
@@ -118,6 +121,7 @@ public:
     std::vector<int32_t> counters, sweeps;
     auto rem = zeroCounter(), inj = zeroCounter();
     SizeType step = 0;
+    const auto loopStart = std::chrono::steady_clock::now();
     while (step < totalSteps) {
       // a chunk ends after a step whose index is a multiple of the progress interval (where the reference
       // reports progress, :118-121); with the channel-current tally on, every non-transient step is its own chunk
@@ -154,6 +158,7 @@ public:
       if ((step - 1) % progress == 0)
         showProgress(step - 1);
     }
+    loopSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - loopStart).count();
     showProgress(totalSteps);
     fetchCurrentGrids();
     fetch(EMCGPU_GRID_SUM_POTENTIAL, results.avgPot);
