@@ -179,6 +179,16 @@ int emcgpu_set_valleys(emcgpu_ctx *ctx, const emcgpu_valley_t *valleys, int nVal
 int emcgpu_set_tables(emcgpu_ctx *ctx, const emcgpu_tableset_t *sets, int nSets,
                       int nLevels, double maxEnergy);
 
+/* emcGrainScatterMechanism (include/emcGrainScatterMechanism.hpp) + the grain clock of the particle handlers
+ * (basicBulkParticleHandler.hpp:216-220, emcBasicParticleHandler.hpp:134-138): every particle carries a second exponential
+ * clock; when it runs out the particle is reflected into the opposite (probability 1 - transmissionProbability) or
+ * transmitted into the same hemisphere about its k (:40-77) and draws a new clock with mean 1 / scatterRate.
+ * scatterRate <= 0 removes the mechanism.  The clocks (emcParticle::grainTau, HOST [n]) are uploaded after the ensemble;
+ * with a grain mechanism bulk steps run on the general step kernel (the streaming one-step kernels do not carry the clock). */
+int emcgpu_set_grain(emcgpu_ctx *ctx, double transmissionProbability, double scatterRate);
+int emcgpu_set_grain_clock(emcgpu_ctx *ctx, const double *grainTau);
+int emcgpu_get_grain_clock(emcgpu_ctx *ctx, double *grainTau);
+
 /* emcPhononBath (include/emcPhononBath.hpp): |q|-binned occupation of a polar phonon mode coupled to the ensemble.  The
  * bath itself (update :264-358, occupations, relaxation) stays a host object of the drop-in API; the device side is
  *   - the event counters of recordEmission / recordAbsorption (:237-253), one pair per bin and bath, and

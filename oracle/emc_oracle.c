@@ -317,6 +317,8 @@ struct orc_model {
   int nBaths;
   orc_bath_t *baths[16];
   double qs2; /* emcPlasmonScreening::getQs2() */
+  int hasGrain;
+  double grainProb, grainTau; /* grainTau = 1 / rate (emcScatterHandler.hpp:234), 1 s without a mechanism */
 };
 
 orc_model_t *orc_model_create(int nLevels, double maxEnergy, double temperature,
@@ -328,6 +330,7 @@ orc_model_t *orc_model_create(int nLevels, double maxEnergy, double temperature,
   m->temperature = temperature;
   m->rho = rho;
   m->vSound = vSound;
+  m->grainTau = 1.;
   return m;
 }
 void orc_model_destroy(orc_model_t *m) {
@@ -481,6 +484,11 @@ int orc_add_froehlich(orc_model_t *m, int variant, int emission, int valley, int
   double xx = C_Q * phononEnergy / (C_KB * temperature);
   x->nBose = 1. / (exp(xx) - 1.);
   return m->nMech++;
+}
+void orc_model_set_grain(orc_model_t *m, double transmissionProb, double scatterRate) {
+  m->hasGrain = scatterRate > 0;
+  m->grainProb = transmissionProb;
+  m->grainTau = m->hasGrain ? 1. / scatterRate : 1.;
 }
 int orc_model_add_bath(orc_model_t *m, orc_bath_t *b) {
   if (m->nBaths >= 16)
@@ -1038,6 +1046,29 @@ int orc_bath_copy(const orc_bath_t *b, int which, double *out) {
   return 0;
 }
 
+/* emcGrainScatterMechanism::scatterParticle (:40-77): reflected into the opposite or transmitted into the same hemisphere
+ * about the current k; then the new clock (emcParticleType.hpp:191-193) */
+static void grain_event(const orc_model_t *m, orc_ensemble_t *e, int64_t p, rng_t *rng) {
+  if (m->hasGrain) {
+    double k[3] = {e->kx[p], e->ky[p], e->kz[p]}, out[3];
+    double rand;
+    if (rng_u01(rng) > m->grainProb) {
+      rand = rng_u01(rng);
+      if (rand < 0.5)
+        rand += 0.5;
+    } else {
+      rand = rng_u01(rng);
+      if (rand > 0.5)
+        rand -= 0.5;
+    }
+    orc_random_direction_wrt_k(k, 1 - 2 * rand, rng_u01(rng), out);
+    e->kx[p] = out[0];
+    e->ky[p] = out[1];
+    e->kz[p] = out[2];
+  }
+  e->grainTau[p] = -log(rng_ulog(rng)) * m->grainTau;
+}
+
 static void drift_wrap(const orc_model_t *m, orc_ensemble_t *e, int64_t p, double dt,
                        const double force[3], const double box[3]) {
   /* basicBulkParticleHandler.hpp:600-613 */
@@ -1132,7 +1163,7 @@ int orc_bulk_steps(const orc_model_t *m, orc_ensemble_t *e, const double box[3],
       if (e->grainTau) {
         e->grainTau[p] -= dt;
         if (e->grainTau[p] <= 0)
-          e->grainTau[p] = -log(rng_ulog(&rng)) * 1.;
+          grain_event(m, e, p, &rng);
       }
     }
     if (obs)
@@ -1214,7 +1245,7 @@ int64_t orc_generate_initial(const orc_model_t *m, const double box[3], const in
               if ((c[d] == 0 && k[d] < 0) || (c[d] == ext[d] - 1 && k[d] > 0))
                 k[d] *= -1;
             double tau = -log(rng_ulog(&rng)) * orc_tau(m, valley, 0);
-            double gtau = -log(rng_ulog(&rng)) * 1.;
+            double gtau = -log(rng_ulog(&rng)) * m->grainTau;
             out->kx[n] = k[0]; out->ky[n] = k[1]; out->kz[n] = k[2];
             out->energy[n] = energy;
             out->tau[n] = tau;
@@ -1562,7 +1593,7 @@ static void dev_create_particle(const orc_model_t *m, const orc_device_t *d, con
       k[i] *= -1;
   /* electronVWD passes the valley index where the region index belongs (electronVWD.hpp:74, :87) */
   const double tau = -log(rng_ulog(rng)) * orc_tau(m, valley, vwd ? valley : region);
-  const double gtau = -log(rng_ulog(rng)) * 1.;
+  const double gtau = -log(rng_ulog(rng)) * m->grainTau;
   if (slot >= 0) {
     out->kx[slot] = k[0]; out->ky[slot] = k[1]; out->kz[slot] = k[2];
     out->energy[slot] = energy;
@@ -1822,8 +1853,11 @@ int orc_device_step(const orc_model_t *m, const orc_device_t *d, orc_ensemble_t 
       const double pos[3] = {e->x[p], e->y[p], d->dim > 2 ? e->z[p] : 0.};
       removedPerContact[orc_dev_contact_idx(d, dev_pos_to_cell(d, pos))]++;
     }
-    if (e->grainTau)
-      e->grainTau[p] -= dt; /* no grain mechanism in the device configs: the clock never fires (1 s) */
+    if (e->grainTau) { /* emcBasicParticleHandler.hpp:134-138 */
+      e->grainTau[p] -= dt;
+      if (e->grainTau[p] <= 0 && !removed)
+        grain_event(m, e, p, &rng);
+    }
   }
   if (recCount)
     *recCount = rng.recCount;

@@ -86,6 +86,9 @@ int orc_add_intervalley(orc_model_t *m, int order, int emission, int valley,
 int orc_add_coulomb(orc_model_t *m, int valley, int region, double epsR,
                     double regionDoping);
 int orc_build_tables(orc_model_t *m);
+/* emcGrainScatterMechanism (include/emcGrainScatterMechanism.hpp): transmission probability, scatter rate [1/s];
+ * rate <= 0: no grain mechanism (the clock still runs with grainTau = 1 s, emcScatterHandler.hpp:62) */
+void orc_model_set_grain(orc_model_t *m, double transmissionProb, double scatterRate);
 
 /* ---- polar-optical (Froehlich) family and the phonon bath (config 5, rows a11 / a21) ----------------------------
  * emcPhononBath (include/emcPhononBath.hpp): q-binned LO occupation, event counters, relaxation. */

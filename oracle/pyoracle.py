@@ -75,6 +75,7 @@ def lib():
                                           C.c_double, C.c_int, C.c_int, _IP]
         L.orc_add_coulomb.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
         L.orc_build_tables.argtypes = [C.c_void_p]
+        L.orc_model_set_grain.argtypes = [C.c_void_p, C.c_double, C.c_double]
         # Froehlich family + phonon bath
         L.orc_bath_create.restype = C.c_void_p
         L.orc_bath_create.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double,
@@ -247,6 +248,11 @@ class Model:
         r = self.L.orc_model_add_bath(self.h, bath.h)
         assert r >= 0
         return r
+
+    def set_grain(self, transmission_prob, scatter_rate):
+        """emcGrainScatterMechanism(transmissionProb, scatterRate); rate <= 0 removes it"""
+        self.grain = (transmission_prob, scatter_rate) if scatter_rate > 0 else None
+        self.L.orc_model_set_grain(self.h, transmission_prob, scatter_rate)
 
     def set_qs2(self, qs2):
         self.L.orc_model_set_qs2(self.h, qs2)

@@ -36,6 +36,7 @@
 #include <ValleyTypes/emcParabolicAnisotropValley.hpp>
 #include <ValleyTypes/emcParabolicIsotropValley.hpp>
 #include <emcDevice.hpp>
+#include <emcGrainScatterMechanism.hpp>
 
 #include <basicBulkParticleHandler.hpp> // -I $(REF)/examples/bulkSimulation
 
@@ -126,7 +127,7 @@ struct Args {
   std::string out = "ref.bin", material = "si", mechs = "acoustic,zero,first";
   int cells = 2, steps = 100, levels = 1000, snapEvery = 0;
   double box = 1e-7, doping = 1e23, field = 1e6, dt = 1e-16, emax = 1.0,
-         temperature = 300;
+         temperature = 300, grainRate = 0, grainProb = 0.5;
   double fdir[3] = {-1, 0, 0};
   unsigned long seed = 7;
 };
@@ -295,6 +296,8 @@ int main(int argc, char **argv) {
     else if (key == "--emax") a.emax = std::stod(val);
     else if (key == "--temperature") a.temperature = std::stod(val);
     else if (key == "--seed") a.seed = std::stoul(val);
+    else if (key == "--grain-rate") a.grainRate = std::stod(val); // emcGrainScatterMechanism, [1/s]; 0: none
+    else if (key == "--grain-prob") a.grainProb = std::stod(val); // its transmission probability
     else if (key == "--fdir")
       std::sscanf(val.c_str(), "%lf,%lf,%lf", &a.fdir[0], &a.fdir[1], &a.fdir[2]);
     else {
@@ -321,6 +324,9 @@ int main(int argc, char **argv) {
     std::cerr << "unknown material\n";
     return 2;
   }
+
+  if (a.grainRate > 0)
+    types[0]->setGrainScatterMechanism(std::make_unique<emcGrainScatterMechanism<T>>(a.grainProb, a.grainRate));
 
   Handler handler(device, types, {a.fdir[0], a.fdir[1], a.fdir[2]}, a.field,
                   a.seed);

@@ -36,6 +36,7 @@
 #include <ParticleType/emcElectron.hpp>
 #include <PoissonSolver/emcSORSolver.hpp>
 #include <emcDevice.hpp>
+#include <emcGrainScatterMechanism.hpp>
 #include <emcSimulationParameter.hpp>
 #include <emcSimulationResults.hpp>
 
@@ -108,7 +109,8 @@ template <class Handler> static void dumpEnsemble(Blob &b, const std::string &p,
 
 struct Options {
   double lx = 2e-7, ly = 1e-7, hx = 1e-8, hy = 2.5e-8, width = 1e-6, doping = 1e22, doping2 = 0, voltage = 0.05,
-         dt = 1e-15, acc = 1e-4, omega = 1.8, emax = 4.0, gateVoltage = 0.5, surfYminConst = -1, surfYmaxMom = -1;
+         dt = 1e-15, acc = 1e-4, omega = 1.8, emax = 4.0, gateVoltage = 0.5, surfYminConst = -1, surfYmaxMom = -1, grainRate = 0,
+         grainProb = 0.5;
   int steps = 10, levels = 1000, gate = 0;
   unsigned long seed = 5;
   std::string out = "device.blob", scheme = "ngp", electron = "emc";
@@ -168,6 +170,8 @@ template <class PMScheme, class Electron> int run(const Options &o) {
     electrons->setSurfaceScatterMechanism(
         emcBoundaryPos::YMAX,
         std::make_unique<emcMomentumDependentSurfaceScatterMechanism<T, DeviceType>>(o.surfYmaxMom, device.getMaxPos()));
+  if (o.grainRate > 0)
+    electrons->setGrainScatterMechanism(std::make_unique<emcGrainScatterMechanism<T>>(o.grainProb, o.grainRate));
   param.addParticleType(std::move(electrons));
   Handler handler(device, pmScheme, param.particleTypes, param.nrCarriersPerPart, seed);
   emcSimulationResults<T, DeviceType> results(device, param);
@@ -258,9 +262,11 @@ template <class PMScheme, class Electron> int run(const Options &o) {
     blob.grid(p + "pot", results.currPot);
     blob.grid(p + "ex", results.eField[0]);
     blob.grid(p + "ey", results.eField[1]);
-    // label the particles through the (dynamically inert) grain clock so that removals can be traced
-    for (size_t i = 0; i < handler.particles[0].size(); i++)
-      handler.particles[0][i].grainTau = 1000. + i;
+    // label the particles through the (dynamically inert) grain clock so that removals can be traced -- unless a grain
+    // mechanism is set: then the clock is live and is recorded as it is
+    if (!(o.grainRate > 0))
+      for (size_t i = 0; i < handler.particles[0].size(); i++)
+        handler.particles[0][i].grainTau = 1000. + i;
     dumpEnsemble(blob, p + "pre_", handler);
     drawMarks.push_back(draws.size());
     auto nrRem = handler.driftScatterParticles(dt, results.eField);
@@ -315,6 +321,8 @@ int main(int argc, char **argv) {
     else if (k == "--electron") o.electron = v;
     else if (k == "--surface-ymin-const") o.surfYminConst = std::stod(v); // specularity parameter
     else if (k == "--surface-ymax-mom") o.surfYmaxMom = std::stod(v);     // rms roughness height [m]
+    else if (k == "--grain-rate") o.grainRate = std::stod(v);             // emcGrainScatterMechanism, [1/s]
+    else if (k == "--grain-prob") o.grainProb = std::stod(v);
     else {
       std::cerr << "unknown option " << k << "\n";
       return 2;

@@ -48,11 +48,16 @@ def upload_model(ctx: capi.Context, model: po.Model, valleys_too=True):
                                         params=[m.p[0], m.p[1], m.p[2], m.p[3]]))
         sets.append(dict(valley=ts["valley"], region=ts["region"], tau=ts["tau"], cum=ts["cum"], mech=mechs))
     ctx.set_tables(sets, model.n_levels, model.max_energy)
+    grain = getattr(model, "grain", None)
+    if grain:
+        ctx.set_grain(*grain)
 
 
 def upload_ensemble(ctx: capi.Context, ens: po.Ensemble, particle_id_base=0):
     ctx.set_ensemble([ens.kx, ens.ky, ens.kz, ens.energy, ens.tau, ens.x, ens.y, ens.z], ens.packed(),
                      particle_id_base)
+    if getattr(ctx, "grain_on", False):
+        ctx.set_grain_clock(ens.grainTau[: ens.n])
 
 
 def download_ensemble(ctx: capi.Context) -> po.Ensemble:
@@ -63,6 +68,8 @@ def download_ensemble(ctx: capi.Context) -> po.Ensemble:
     e.valley = (packed & 0xFF).astype(np.int32)
     e.sub = ((packed >> 8) & 0xFF).astype(np.int32)
     e.region = (packed >> 16).astype(np.int32)
+    if getattr(ctx, "grain_on", False):
+        e.grainTau = ctx.get_grain_clock()
     return e
 
 

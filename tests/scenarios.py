@@ -91,12 +91,21 @@ GOLDEN_CASES = {
         args=dict(material="mixed", mechs="acoustic,zero,first,coulomb", cells=2, box=1e-7, doping=1e23,
                   field=2e6, fdir="0.3,-1,0.2", dt=2e-15, steps=80, seed=11, levels=250, emax=2.0),
         builder="mixed", kwargs=dict(mechs=("acoustic", "zero", "first", "coulomb"), n_levels=250, max_energy=2.0)),
+    # grain boundaries: a second free-flight clock with a reflect / transmit hemisphere sampler (emcGrainScatterMechanism)
+    "si_grain": dict(
+        args={"material": "si", "mechs": "acoustic,zero,first", "cells": 2, "box": 1e-7, "doping": 1e23, "field": 2e6,
+              "fdir": "-1,0.5,0", "dt": 2e-16, "steps": 300, "seed": 31, "levels": 1000, "emax": 1.0, "grain-rate": 2e13,
+              "grain-prob": 0.4},
+        builder="si", kwargs=dict(mechs=("acoustic", "zero", "first"), n_levels=1000, max_energy=1.0), grain=(0.4, 2e13)),
 }
 
 
 def build_model(case: str):
     c = GOLDEN_CASES[case]
-    return (build_si if c["builder"] == "si" else build_mixed)(**c["kwargs"])
+    m = (build_si if c["builder"] == "si" else build_mixed)(**c["kwargs"])
+    if "grain" in c:
+        m.set_grain(*c["grain"])
+    return m
 
 
 # device-run golden cases (oracle/_ref/ref_device_driver): name -> driver args.  2-D silicon bars with ohmic
@@ -118,6 +127,9 @@ DEVICE_CASES = {
                    "dt": 2e-15, "steps": 4, "levels": 500, "emax": 4.0, "gate": 1, "seed": 23, "scheme": "vwd",
                    "electron": "vwd", "surface-ymin-const": 0.5},
 }
+DEVICE_CASES["device_grain"] = {"lx": 2e-7, "ly": 1e-7, "hx": 1e-8, "hy": 2.5e-8, "doping": 1e22, "doping2": 0, "voltage": 0.05,
+                               "dt": 1e-15, "steps": 8, "levels": 1000, "emax": 4.0, "gate": 0, "seed": 41, "grain-rate": 3e13,
+                               "grain-prob": 0.6}
 PM_SCHEMES = {"ngp": po.PM_NGP, "cic": po.PM_CIC, "nec": po.PM_NEC, "vwd": po.PM_NEC_VWD}
 
 
@@ -155,6 +167,8 @@ def build_device(case: str):
     for reg in regions:
         m.add_coulomb(0, reg, 11.8, dop[reg])
     m.build_tables()
+    if "grain-rate" in a:
+        m.set_grain(a["grain-prob"], a["grain-rate"])
     return m, dev
 
 

@@ -52,6 +52,8 @@ def test_replay_of_reference_draws(gpu_ctx_factory, case, steps_per_launch, math
     want = golden_ensemble(g, "final_")
     # state: indices exact, fp64 within 1e-12 relative -- against the REFERENCE's final ensemble
     assert_state_close(got, want, box, STATE_RTOL, f"{case}/replay")
+    if getattr(m, "grain", None):  # the grain clocks (a new one is drawn at every grain event) agree as well
+        assert np.allclose(got.grainTau, want.grainTau[: want.n], rtol=1e-11, atol=1e-27)
     # every scatter event: same step, same particle, same mechanism as the reference logged
     ev, n_ev = ctx.event_log_read(1 << 20)
     assert n_ev == len(ev)

@@ -48,7 +48,7 @@ def assert_counts(dev, got, want, what):
         assert np.array_equal(got, np.asarray(want).ravel()), what
 
 
-def assert_ensemble_close(got: po.Ensemble, want: po.Ensemble, dev, what):
+def assert_ensemble_close(got: po.Ensemble, want: po.Ensemble, dev, what, check_grain=False):
     assert got.n == want.n, what
     n = want.n
     for f in ("valley", "sub", "region"):
@@ -59,6 +59,8 @@ def assert_ensemble_close(got: po.Ensemble, want: po.Ensemble, dev, what):
     errs["tau"] = rel_err(got.tau[:n], want.tau[:n])
     errs["x"] = rel_err(got.x[:n], want.x[:n], dev.max_pos[0])
     errs["y"] = rel_err(got.y[:n], want.y[:n], dev.max_pos[1])
+    if check_grain:
+        errs["grainTau"] = rel_err(got.grainTau[:n], want.grainTau[:n])
     bad = {k: v for k, v in errs.items() if not v <= STATE_RTOL}
     assert not bad, f"{what}: {bad}"
 
@@ -144,7 +146,7 @@ def test_particle_step_replays_the_reference(gpu_ctx_factory, case, math_mode):
         removed = ctx.device_step(a["dt"])
         assert np.array_equal(removed, g[p + "removed_per_contact"]), f"step {s}"
         got = download_ensemble(ctx)
-        assert_ensemble_close(got, ens_from(g, p + "drift_"), dev, f"{case} step {s}")
+        assert_ensemble_close(got, ens_from(g, p + "drift_"), dev, f"{case} step {s}", check_grain="grain-rate" in a)
         ev, n_ev = ctx.event_log_read(1 << 16)
         dev_ev = ev[np.lexsort((ev[:, 3], ev[:, 2], ev[:, 1], ev[:, 0]))]
         cpu_ev = res["events"][np.lexsort((res["events"][:, 3], res["events"][:, 2], res["events"][:, 1], res["events"][:, 0]))]
@@ -174,7 +176,8 @@ def test_contacts_replay_the_reference(gpu_ctx_factory, case):
         draws = g["draws"][int(marks[s, 1]):int(marks[s, 2])]
         net = ctx.device_contacts(replay_draws=draws)
         assert np.array_equal(net, g[p + "net_injected_per_contact"]), f"step {s}"
-        assert_ensemble_close(download_ensemble(ctx), ens_from(g, p + "post_"), dev, f"{case} contacts {s}")
+        assert_ensemble_close(download_ensemble(ctx), ens_from(g, p + "post_"), dev, f"{case} contacts {s}",
+                              check_grain="grain-rate" in a)
         injected_total += len(draws) // 9
         ctx.device_assign()
         assert_counts(dev, ctx.device_get_grid(capi.GRID_COUNT), g[p + "count"], f"counts {s}")

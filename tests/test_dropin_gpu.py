@@ -289,3 +289,37 @@ def test_own_hot_phonon_driver_matches_reference_within_3_sigma(tmp_path, hpb):
                         str(tmp_path)], cwd=tmp_path, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     _check_ga2o3(os.path.join(tmp_path, "ga2o3_vE_" + ("hpb" if hpb else "eq") + ".txt"), "hpb" if hpb else "eq")
+
+
+# ---- grain-boundary scattering through the drop-in handler (no example of the reference switches it on) -----------------
+def test_grain_scattering_through_the_drop_in_handler_matches_the_cpu_restatement(tmp_path):
+    """own bulk driver with an emcGrainScatterMechanism (GPU, Philox streams) against the oracle's run of the same set-up
+    (CPU, mt19937_64; the oracle's grain events are pinned bit for bit against the reference, tests/golden/si_grain.npz):
+    steady-state drift velocity and mean energy within 3 sigma of the block-averaged noise; grain scattering randomises k,
+    so the drift velocity drops well below the grain-free value"""
+    exe = os.path.join(BIN, "bulkSimulation")
+    n, steps, dt, field, rate, prob = 12500, 6000, 2e-16, 1e6, 3e13, 0.3
+    args = [exe, "--seed", "77", "--particles", str(n), "--steps", str(steps), "--dt", str(dt), "--field", str(field)]
+    r = subprocess.run(args + ["--grain-rate", str(rate), "--grain-prob", str(prob), "--prefix", "grain"], cwd=tmp_path,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    r0 = subprocess.run(args + ["--prefix", "plain"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r0.returncode == 0
+    v_gpu = np.loadtxt(os.path.join(tmp_path, "grainAvgDriftVelocity.txt"))[steps // 2:, 1]
+    e_gpu = np.loadtxt(os.path.join(tmp_path, "grainAvgEnergy.txt"))[steps // 2:, 1]
+    v_plain = np.loadtxt(os.path.join(tmp_path, "plainAvgDriftVelocity.txt"))[steps // 2:, 1]
+    m = build_si()
+    m.set_grain(prob, rate)
+    edge = (n / 1e23) ** (1 / 3)
+    st = po.mt_state(5)
+    ens, _ = m.generate_initial([edge] * 3, [5, 5, 5], 1e23, st)
+    res = m.bulk_steps(ens, [edge] * 3, [-1, 0, 0], field, dt, steps, po.rng_mt(st), first_step=1)
+    obs = res["obs"][steps // 2:, 0, :]
+    v_cpu, e_cpu = obs[:, 1] / obs[:, 2], obs[:, 0] / obs[:, 2]
+
+    def block_sigma(x, blocks=10):
+        return np.std([b.mean() for b in np.array_split(x, blocks)], ddof=1) / np.sqrt(blocks)
+
+    assert abs(v_gpu.mean() - v_cpu.mean()) <= 3 * np.hypot(block_sigma(v_gpu), block_sigma(v_cpu)) + 0.01 * abs(v_cpu.mean())
+    assert abs(e_gpu.mean() - e_cpu.mean()) <= 3 * np.hypot(block_sigma(e_gpu), block_sigma(e_cpu)) + 0.005 * e_cpu.mean()
+    assert abs(v_gpu.mean()) < 0.8 * abs(v_plain.mean())

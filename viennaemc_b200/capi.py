@@ -79,6 +79,9 @@ def load():
     L.emcgpu_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.emcgpu_set_valleys.argtypes = [vp, C.POINTER(ValleyC), C.c_int]
     L.emcgpu_set_tables.argtypes = [vp, C.POINTER(TableSetC), C.c_int, C.c_int, C.c_double]
+    L.emcgpu_set_grain.argtypes = [vp, C.c_double, C.c_double]
+    L.emcgpu_set_grain_clock.argtypes = [vp, _DP]
+    L.emcgpu_get_grain_clock.argtypes = [vp, _DP]
     L.emcgpu_set_phonon_baths.argtypes = [vp, C.c_int, C.c_int, C.c_double, _DP, _DP]
     L.emcgpu_get_phonon_counts.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]
     L.emcgpu_set_ensemble.argtypes = [vp, C.c_int64, C.POINTER(_DP), C.POINTER(C.c_uint32), C.c_int64]
@@ -135,7 +138,7 @@ CONTACT_OHMIC, CONTACT_SCHOTTKY, CONTACT_GATE = range(3)
 
 EXPORTED_SYMBOLS = [
     "emcgpu_abi_version", "emcgpu_create", "emcgpu_destroy", "emcgpu_last_error", "emcgpu_launch_count",
-    "emcgpu_set_stream", "emcgpu_synchronize", "emcgpu_set_option", "emcgpu_set_valleys", "emcgpu_set_tables", "emcgpu_set_phonon_baths", "emcgpu_get_phonon_counts", "emcgpu_set_ensemble",
+    "emcgpu_set_stream", "emcgpu_synchronize", "emcgpu_set_option", "emcgpu_set_valleys", "emcgpu_set_tables", "emcgpu_set_grain", "emcgpu_set_grain_clock", "emcgpu_get_grain_clock", "emcgpu_set_phonon_baths", "emcgpu_get_phonon_counts", "emcgpu_set_ensemble",
     "emcgpu_get_ensemble", "emcgpu_ensemble_size", "emcgpu_generate_bulk_ensemble",
     "emcgpu_ensemble_device_ptrs", "emcgpu_rng_philox", "emcgpu_rng_replay", "emcgpu_bulk_configure",
     "emcgpu_bulk_step", "emcgpu_bulk_step_device", "emcgpu_bulk_observables", "emcgpu_set_step_index",
@@ -222,6 +225,20 @@ class Context:
         self._chk(self.L.emcgpu_set_tables(self.h, arr, len(sets), int(n_levels), float(max_energy)))
 
     # -- ensemble
+    def set_grain(self, transmission_prob, scatter_rate):
+        self._chk(self.L.emcgpu_set_grain(self.h, transmission_prob, scatter_rate))
+        self.grain_on = scatter_rate > 0
+
+    def set_grain_clock(self, grain_tau):
+        g = np.ascontiguousarray(grain_tau, dtype=np.float64)
+        assert g.size == self.size
+        self._chk(self.L.emcgpu_set_grain_clock(self.h, g.ctypes.data_as(_DP)))
+
+    def get_grain_clock(self):
+        g = np.zeros(self.size)
+        self._chk(self.L.emcgpu_get_grain_clock(self.h, g.ctypes.data_as(_DP)))
+        return g
+
     def set_phonon_baths(self, n_baths, n_bins, dq, cum_w=None, cum_wn=None):
         """cum_w / cum_wn: [n_baths][n_bins + 1] prefix sums of emcPhononBath (only needed for q-resolved angles)"""
         cw = np.ascontiguousarray(cum_w, dtype=np.float64) if cum_w is not None else None

@@ -45,7 +45,26 @@ struct BulkParams {
   unsigned long long *evCount;
   int *status;
   BathView baths; // phonon baths of polar-optical mechanisms (counts == nullptr: none)
+  // grain boundaries (emcGrainScatterMechanism): second free-flight clock per particle, nullptr = no grain mechanism
+  double *grainTau;
+  double grainProb, grainTau0;
 };
+
+// emcGrainScatterMechanism::scatterParticle (include/emcGrainScatterMechanism.hpp:40-77) + emcParticleType::getNewGrainTau
+// (emcParticleType.hpp:191-193): with probability (1 - transmission) the particle is reflected into the opposite hemisphere
+// about its k, otherwise transmitted into the same one; elastic; then a new exponential clock.  Returns the new clock.
+template <int RNG_MODE> __device__ __forceinline__ double grainEvent(const BulkParams &P, Particle &p, Rng &rng) {
+  double rnd;
+  if (uniform01(rng.raw<RNG_MODE>()) > P.grainProb) {
+    rnd = uniform01(rng.raw<RNG_MODE>());
+    if (rnd < 0.5) rnd += 0.5;
+  } else {
+    rnd = uniform01(rng.raw<RNG_MODE>());
+    if (rnd > 0.5) rnd -= 0.5;
+  }
+  p.k = randomDirectionWrtK<true>(p.k, 1.0 - 2.0 * rnd, uniform01(rng.raw<RNG_MODE>()));
+  return __dmul_rn(-log(uniformLog(rng.raw<RNG_MODE>())), P.grainTau0);
+}
 
 constexpr int kBulkThreads = 256;
 #ifndef EMC_STREAM_THREADS
@@ -1037,9 +1056,11 @@ __global__ void __launch_bounds__(kBulkThreads, 2) bulkStepKernel(const __grid_c
     const bool live = i < P.n;
     Particle p;
     Rng rng;
+    double grain = 0.0;
     if (live) {
       loadParticle(P, i, p, rng);
       attachReplay<RNG_MODE>(P, i, rng);
+      if (P.grainTau) grain = P.grainTau[i];
     } else {
       p.valley = 0;
       p.sub = 0;
@@ -1051,6 +1072,13 @@ __global__ void __launch_bounds__(kBulkThreads, 2) bulkStepKernel(const __grid_c
         rng.step = (uint32_t)(P.step0 + s);
         rng.n = 0;
         vd = bulkParticleStep<EXACT, RNG_MODE>(C, P, p, rng, P.idBase + i, P.step0 + s);
+        if (P.grainTau) { // basicBulkParticleHandler.hpp:216-220
+          grain = __dsub_rn(grain, P.dt);
+          if (grain <= 0.0) {
+            grain = grainEvent<RNG_MODE>(P, p, rng);
+            vd = driftVelocity<EXACT>(C.model->valleys[p.valley], p.sub, p.k, p.energy, P.dir);
+          }
+        }
         e = p.energy;
       }
       // per-valley block partial sums (basicBulkParticleHandler.hpp:289-347)
@@ -1067,7 +1095,10 @@ __global__ void __launch_bounds__(kBulkThreads, 2) bulkStepKernel(const __grid_c
         accumulateObsWarp(o, nV, live, p.valley, e, vd);
       }
     }
-    if (live) storeParticle<RNG_MODE>(P, i, p, rng);
+    if (live) {
+      storeParticle<RNG_MODE>(P, i, p, rng);
+      if (P.grainTau) P.grainTau[i] = grain;
+    }
   }
   __syncthreads();
   for (int j = tid; j < P.nSteps * obsPerStep; j += blockDim.x) {

@@ -1274,6 +1274,11 @@ __global__ void __launch_bounds__(kBulkThreads, 2)
       }
     }
     p.tau = A::sub(p.tau, dt);
+    if (P.grainTau) { // emcBasicParticleHandler.hpp:134-138
+      double grain = __dsub_rn(P.grainTau[i], dt);
+      if (grain <= 0.0 && !removed) grain = grainEvent<RNG_MODE>(P, p, rng);
+      P.grainTau[i] = grain;
+    }
     storeParticle<RNG_MODE>(P, i, p, rng);
     const int cell = posToCell(G, p.pos.x, p.pos.y, p.pos.z);
     if (removed) {
@@ -1365,6 +1370,7 @@ struct EnsemblePtrs {
   double *stream[EMCGPU_N_STREAMS];
   uint32_t *packed;
   uint32_t *cursor; // replay cursors travel with their particle (may be null)
+  double *grain;    // grain clocks travel with their particle (may be null)
 };
 
 __global__ void __launch_bounds__(kChunk)
@@ -1387,6 +1393,7 @@ __global__ void __launch_bounds__(kChunk)
       for (int c = 0; c < EMCGPU_N_STREAMS; c++) dst.stream[c][j] = src.stream[c][i];
       dst.packed[j] = src.packed[i];
       if (src.cursor) dst.cursor[j] = src.cursor[i];
+      if (src.grain) dst.grain[j] = src.grain[i];
     }
     __syncthreads();
   }
@@ -1490,6 +1497,7 @@ struct InjectParams {
   int64_t replayCount;
   int *status;
   uint32_t rank; // of a sharded ensemble: keeps the streams of the ranks apart
+  double grainTau0; // mean time between grain events (1 s without a grain mechanism)
 };
 
 template <int DIM>
@@ -1577,6 +1585,7 @@ __global__ void __launch_bounds__(128) contactInjectKernel(const __grid_constant
     J.ens.stream[EMCGPU_Z][at] = pos[2];
     J.ens.packed[at] = (uint32_t)valley | ((uint32_t)sub << 8) | ((uint32_t)region << 16);
     if (J.ens.cursor) J.ens.cursor[at] = 0;
+    if (J.ens.grain) J.ens.grain[at] = __dmul_rn(-log(uniformLog(raw[d++])), J.grainTau0);
   }
 }
 

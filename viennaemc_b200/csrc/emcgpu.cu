@@ -104,6 +104,7 @@ void fillBulkParams(emcgpu_ctx *ctx, BulkParams &P) {
   P.evCount = static_cast<unsigned long long *>(ctx->dEvCount.ptr);
   P.status = static_cast<int *>(ctx->dStatus.ptr);
   emc::fillBathView(ctx, P.baths);
+  emc::fillGrain(ctx, P);
 }
 
 template <typename K>
@@ -303,6 +304,36 @@ int emcgpu_set_option(emcgpu_ctx *ctx, const char *name, int64_t value) {
     return EMCGPU_OK;
   }
   return fail(ctx, EMCGPU_E_INVALID, "unknown option '%s'", name);
+}
+
+int emcgpu_set_grain(emcgpu_ctx *ctx, double transmissionProbability, double scatterRate) {
+  if (!ctx) return EMCGPU_E_INVALID;
+  if (transmissionProbability < 0 || transmissionProbability > 1) return fail(ctx, EMCGPU_E_INVALID, "transmission probability outside [0, 1]");
+  ctx->grainOn = scatterRate > 0;
+  ctx->grainProb = transmissionProbability;
+  ctx->grainTau0 = ctx->grainOn ? 1.0 / scatterRate : 1.0;
+  return EMCGPU_OK;
+}
+
+int emcgpu_set_grain_clock(emcgpu_ctx *ctx, const double *grainTau) {
+  if (!ctx || !grainTau) return EMCGPU_E_INVALID;
+  if (int r = bind(ctx)) return r;
+  CUDA_TRY(ctx, ctx->dGrain.ensure((size_t)std::max<int64_t>(1, ctx->capacity) * sizeof(double)));
+  if (ctx->n)
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dGrain.ptr, grainTau, (size_t)ctx->n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->grainClockSet = true;
+  return EMCGPU_OK;
+}
+
+int emcgpu_get_grain_clock(emcgpu_ctx *ctx, double *grainTau) {
+  if (!ctx || !grainTau) return EMCGPU_E_INVALID;
+  if (int r = bind(ctx)) return r;
+  if (!ctx->grainClockSet) return fail(ctx, EMCGPU_E_INVALID, "no grain clocks on the device");
+  if (ctx->n)
+    CUDA_TRY(ctx, cudaMemcpyAsync(grainTau, ctx->dGrain.ptr, (size_t)ctx->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return EMCGPU_OK;
 }
 
 int emcgpu_set_phonon_baths(emcgpu_ctx *ctx, int nBaths, int nBins, double dq, const double *cumW, const double *cumWN) {
@@ -518,6 +549,7 @@ int emcgpu_set_ensemble(emcgpu_ctx *ctx, int64_t n, const double *const *soa, co
     ctx->n = 0;
     return EMCGPU_OK;
   }
+  ctx->grainClockSet = false; // clocks belong to an ensemble
   if (int r = allocEnsemble(ctx, n)) return r;
   for (int s = 0; s < EMCGPU_N_STREAMS; s++) {
     if (!soa[s]) return fail(ctx, EMCGPU_E_INVALID, "stream %d is NULL", s);
@@ -656,7 +688,10 @@ int emcgpu_bulk_step_device(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPer
     P.nSteps = chunk;
     P.step0 = ctx->nextStep + done;
     P.obs = obsDevice + (size_t)done * nV * 3;
-    const bool stream = chunk == 1;
+    if (ctx->grainOn && !ctx->grainClockSet)
+      return fail(ctx, EMCGPU_E_INVALID, "a grain mechanism is set but the grain clocks were not uploaded (emcgpu_set_grain_clock)");
+    // the streaming one-step kernels do not carry the grain clock: with a grain mechanism the general kernel runs
+    const bool stream = chunk == 1 && !ctx->grainOn;
     if (stream && ctx->optKernel != 1) {
       // preferred: the TMA pipeline (tables in shared memory if they fit beside >= kMinStages ring stages)
       size_t smem = 0;

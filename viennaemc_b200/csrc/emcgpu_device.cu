@@ -20,7 +20,7 @@ struct DeviceRunState {
   DeviceBuffer grid[EMCGPU_N_GRIDS];
   DeviceBuffer dCtl, dFlag, dChunkCount, dListParticle, dListCell, dCellCount, dInjectCount, dSweeps, dReplay;
   DeviceBuffer dCounters, dSweepsPerStep; // per-step outputs of a chunk of the step loop
-  DeviceBuffer altEnsemble, altCursor; // second ensemble buffer for the order-preserving compaction
+  DeviceBuffer altEnsemble, altCursor, altGrain; // second ensemble buffer for the order-preserving compaction
   int64_t reserve = 0;
   int rank = 0, world = 1; // emcgpu_device_set_sharding
   emcgpu_allreduce_fn allreduce = nullptr;
@@ -35,7 +35,7 @@ void releaseDeviceRun(emcgpu_ctx *ctx) {
   DeviceRunState *r = ctx->run;
   for (DeviceBuffer *b : {&r->dRegion, &r->dFace, &r->dDoping, &r->dDopingNorm, &r->dCellKind, &r->dSorHistory, &r->dCtl, &r->dFlag, &r->dChunkCount, &r->dListParticle,
                           &r->dListCell, &r->dCellCount, &r->dInjectCount, &r->dSweeps, &r->dReplay, &r->dCounters,
-                          &r->dSweepsPerStep, &r->altEnsemble, &r->altCursor, &r->dShare})
+                          &r->dSweepsPerStep, &r->altEnsemble, &r->altCursor, &r->altGrain, &r->dShare})
     b->release();
   for (auto &g : r->grid) g.release();
   delete r;
@@ -57,14 +57,17 @@ int needRun(emcgpu_ctx *ctx) {
 int needModel(emcgpu_ctx *ctx) {
   if (!ctx->haveValleys || !ctx->haveTables)
     return fail(ctx, EMCGPU_E_INVALID, "set valleys and tables before running the device path");
+  if (ctx->grainOn && !ctx->grainClockSet)
+    return fail(ctx, EMCGPU_E_INVALID, "a grain mechanism is set but the grain clocks were not uploaded (emcgpu_set_grain_clock)");
   return EMCGPU_OK;
 }
 
 size_t streamStrideD(int64_t cap) { return ((size_t)cap * sizeof(double) + 255) & ~size_t(255); }
 size_t streamStrideP(int64_t cap) { return ((size_t)cap * sizeof(uint32_t) + 255) & ~size_t(255); }
 
-EnsemblePtrs ptrsOf(void *base, int64_t cap, uint32_t *cursor) {
+EnsemblePtrs ptrsOf(void *base, int64_t cap, uint32_t *cursor, double *grain = nullptr) {
   EnsemblePtrs p;
+  p.grain = grain;
   unsigned char *b = static_cast<unsigned char *>(base);
   for (int s = 0; s < EMCGPU_N_STREAMS; s++) p.stream[s] = reinterpret_cast<double *>(b + streamStrideD(cap) * s);
   p.packed = reinterpret_cast<uint32_t *>(b + streamStrideD(cap) * EMCGPU_N_STREAMS);
@@ -75,7 +78,9 @@ EnsemblePtrs ptrsOf(void *base, int64_t cap, uint32_t *cursor) {
 // make sure the ensemble allocation (and its twin) can hold `cap` particles, keeping the current content
 int growEnsemble(emcgpu_ctx *ctx, int64_t cap) {
   DeviceRunState *r = ctx->run;
-  if (cap <= ctx->capacity && r->altEnsemble.bytes >= ctx->dEnsemble.bytes) return EMCGPU_OK;
+  const bool grainReady = !ctx->grainOn || (ctx->dGrain.bytes >= (size_t)ctx->capacity * sizeof(double) &&
+                                            r->altGrain.bytes >= (size_t)ctx->capacity * sizeof(double));
+  if (cap <= ctx->capacity && r->altEnsemble.bytes >= ctx->dEnsemble.bytes && grainReady) return EMCGPU_OK;
   cap = std::max<int64_t>(cap, ctx->capacity);
   const size_t bytes = streamStrideD(cap) * EMCGPU_N_STREAMS + streamStrideP(cap);
   if (cap > ctx->capacity) {
@@ -97,6 +102,20 @@ int growEnsemble(emcgpu_ctx *ctx, int64_t cap) {
     ctx->capacity = cap;
   }
   CUDA_TRY(ctx, r->altEnsemble.ensure(ctx->dEnsemble.bytes));
+  if (ctx->grainOn) { // grain clocks: one per particle slot, content kept when the allocation grows
+    const size_t need = (size_t)ctx->capacity * sizeof(double);
+    if (ctx->dGrain.bytes < need) {
+      DeviceBuffer bigger;
+      CUDA_TRY(ctx, bigger.ensure(need));
+      if (ctx->dGrain.ptr && ctx->n)
+        CUDA_TRY(ctx, cudaMemcpyAsync(bigger.ptr, ctx->dGrain.ptr, std::min(ctx->dGrain.bytes, (size_t)ctx->n * sizeof(double)),
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      ctx->dGrain.release();
+      ctx->dGrain = bigger;
+    }
+    CUDA_TRY(ctx, r->altGrain.ensure(need));
+  }
   return EMCGPU_OK;
 }
 
@@ -119,6 +138,7 @@ void fillParams(emcgpu_ctx *ctx, BulkParams &P) {
   P.evCount = ctx->dEvCount.as<unsigned long long>();
   P.status = ctx->dStatus.as<int>();
   emc::fillBathView(ctx, P.baths);
+  emc::fillGrain(ctx, P);
 }
 
 int readStatus(emcgpu_ctx *ctx) {
@@ -379,13 +399,17 @@ int doCompaction(emcgpu_ctx *ctx) {
   selectCountKernel<SELECT_KEPT><<<grid, kChunk, 0, ctx->stream>>>(flag, ctl, chunkCount);
   const bool replay = ctx->rngMode == RNG_REPLAY;
   if (replay) CUDA_TRY(ctx, r->altCursor.ensure((size_t)ctx->capacity * sizeof(uint32_t)));
-  EnsemblePtrs src = ptrsOf(ctx->dEnsemble.ptr, ctx->capacity, replay ? ctx->dCursor.as<uint32_t>() : nullptr);
-  EnsemblePtrs dst = ptrsOf(r->altEnsemble.ptr, ctx->capacity, replay ? r->altCursor.as<uint32_t>() : nullptr);
+  const bool grain = ctx->grainOn;
+  EnsemblePtrs src = ptrsOf(ctx->dEnsemble.ptr, ctx->capacity, replay ? ctx->dCursor.as<uint32_t>() : nullptr,
+                            grain ? ctx->dGrain.as<double>() : nullptr);
+  EnsemblePtrs dst = ptrsOf(r->altEnsemble.ptr, ctx->capacity, replay ? r->altCursor.as<uint32_t>() : nullptr,
+                            grain ? r->altGrain.as<double>() : nullptr);
   compactScatterKernel<<<grid, kChunk, 0, ctx->stream>>>(flag, ctl, chunkCount, src, dst);
   ctx->launches += 2;
   CUDA_TRY(ctx, cudaGetLastError());
   std::swap(ctx->dEnsemble, r->altEnsemble);
   if (replay) std::swap(ctx->dCursor, r->altCursor);
+  if (grain) std::swap(ctx->dGrain, r->altGrain);
   for (int s = 0; s < EMCGPU_N_STREAMS; s++) ctx->dStream[s] = dst.stream[s];
   ctx->dPacked = dst.packed;
   return EMCGPU_OK;
@@ -434,7 +458,9 @@ int doContacts(emcgpu_ctx *ctx, bool fromStep, const uint64_t *replayDraws, int6
   CUDA_TRY(ctx, cudaGetLastError());
   if (int rc = doCompaction(ctx)) return rc;
   InjectParams J;
-  J.ens = ptrsOf(ctx->dEnsemble.ptr, ctx->capacity, ctx->rngMode == RNG_REPLAY ? ctx->dCursor.as<uint32_t>() : nullptr);
+  J.ens = ptrsOf(ctx->dEnsemble.ptr, ctx->capacity, ctx->rngMode == RNG_REPLAY ? ctx->dCursor.as<uint32_t>() : nullptr,
+                 ctx->grainOn ? ctx->dGrain.as<double>() : nullptr);
+  J.grainTau0 = ctx->grainTau0;
   J.injectCount = K.injectCount;
   J.model = ctx->dModel.as<const DevModel>();
   J.seed = ctx->seed;

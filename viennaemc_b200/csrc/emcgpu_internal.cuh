@@ -82,6 +82,11 @@ struct emcgpu_ctx {
   bool bathHasCum = false;
   emc::DeviceBuffer dBathCounts, dBathCum;
 
+  // grain boundaries (emcgpu_set_grain): clock per particle
+  bool grainOn = false, grainClockSet = false;
+  double grainProb = 0.5, grainTau0 = 1.0;
+  emc::DeviceBuffer dGrain;
+
   // outputs
   emc::DeviceBuffer dObs, dStatus, dEvents, dEvCount;
   int64_t evCap = 0;
@@ -100,6 +105,12 @@ int failWith(emcgpu_ctx *ctx, int code, const char *fmt, ...);
     if (_e != cudaSuccess)                                                                    \
       return emc::failWith(ctx, EMCGPU_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
   } while (0)
+
+inline void fillGrain(const emcgpu_ctx *ctx, BulkParams &P) {
+  P.grainTau = ctx->grainOn ? ctx->dGrain.as<double>() : nullptr;
+  P.grainProb = ctx->grainProb;
+  P.grainTau0 = ctx->grainTau0;
+}
 
 inline void fillBathView(const emcgpu_ctx *ctx, BathView &B) {
   B.counts = ctx->nBaths ? ctx->dBathCounts.as<unsigned long long>() : nullptr;

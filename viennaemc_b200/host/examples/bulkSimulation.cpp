@@ -6,6 +6,7 @@
 //
 //   bulkSimulation [--particles N] [--field V/m] [--steps K] [--dt s] [--seed S]
 //                  [--steps-per-launch L] [--prefix name] [--temperature K] [--doping 1/m3]
+//                  [--grain-rate 1/s --grain-prob p]   (grain-boundary scattering, emcGrainScatterMechanism)
 //
 // --steps-per-launch > 1 uses the handler's fused entry point (several time steps per kernel
 // launch, particle state kept in registers in between); 1 is the reference's call pattern
@@ -28,7 +29,7 @@ using DeviceType = emcDevice<NumType, 3>;
 using ParticleHandler = basicBulkParticleHandler<NumType, DeviceType>;
 
 int main(int argc, char **argv) {
-  double particles = 12500, field = 1e6, dt = 1e-16, temperature = 300, doping = 1e23;
+  double particles = 12500, field = 1e6, dt = 1e-16, temperature = 300, doping = 1e23, grainRate = 0, grainProb = 0.5;
   long steps = 40000, stepsPerLaunch = 1;
   unsigned long seed = 0;
   std::string prefix = "bulkSimulation";
@@ -43,6 +44,8 @@ int main(int argc, char **argv) {
     else if (key == "--prefix") prefix = val;
     else if (key == "--temperature") temperature = std::stod(val);
     else if (key == "--doping") doping = std::stod(val);
+    else if (key == "--grain-rate") grainRate = std::stod(val);
+    else if (key == "--grain-prob") grainProb = std::stod(val);
     else {
       std::cerr << "unknown option " << key << "\n";
       return 2;
@@ -60,6 +63,9 @@ int main(int argc, char **argv) {
   SiliconModel::addXValley<NumType>(particleTypes[0]);
   SiliconModel::addScattering<NumType>(particleTypes[0], device, {0},
                                        SiliconModel::ACOUSTIC | SiliconModel::ZERO_ORDER | SiliconModel::FIRST_ORDER);
+
+  if (grainRate > 0)
+    particleTypes[0]->setGrainScatterMechanism(std::make_unique<emcGrainScatterMechanism<NumType>>(grainProb, grainRate));
 
   ParticleHandler handler(device, particleTypes, {-1, 0, 0}, field, seed);
   std::cout << "Creating Particles...\n";

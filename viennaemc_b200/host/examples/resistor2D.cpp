@@ -5,7 +5,7 @@
 //
 //   resistor2D [--voltage V] [--steps K] [--transient K] [--avg K] [--dt s] [--seed S] [--doping 1/m3]
 //              [--lx m] [--ly m] [--hx m] [--hy m] [--width m] [--carriers-per-particle n]
-//              [--poisson-interval n] [--red-black 0|1] [--progress K] [--prefix name]
+//              [--poisson-interval n] [--red-black 0|1] [--progress K] [--prefix name] [--grain-rate 1/s --grain-prob p]
 //
 // Prints the terminal currents, the particle-steps per second of the Monte Carlo loop and the mean
 // number of SOR sweeps per step.
@@ -18,6 +18,7 @@
 #include <ParticleHandler/emcBasicParticleHandler.hpp>
 #include <ParticleType/emcElectron.hpp>
 #include <PoissonSolver/emcSORSolver.hpp>
+#include <emcGrainScatterMechanism.hpp>
 #include <emcSimulation.hpp>
 
 #include "SiliconModel.hpp"
@@ -30,7 +31,8 @@ using PoissonSolver = emcSORSolver<NumType, DeviceType, ParticleHandler>;
 using SimulationType = emcSimulation<NumType, DeviceType, PoissonSolver, ParticleHandler, PMScheme>;
 
 int main(int argc, char **argv) {
-  double voltage = 0.05, dt = 1e-15, doping = 1e22, lx = 1e-6, ly = 1e-6, hx = 1e-8, hy = 5e-8, width = 1e-6;
+  double voltage = 0.05, dt = 1e-15, doping = 1e22, lx = 1e-6, ly = 1e-6, hx = 1e-8, hy = 5e-8, width = 1e-6, grainRate = 0,
+         grainProb = 1;
   long steps = 50000, transient = 20000, avg = 20000, carriers = 1, poissonInterval = 1, progress = 5000, redBlack = 0;
   unsigned long seed = 0;
   bool seeded = false;
@@ -54,6 +56,8 @@ int main(int argc, char **argv) {
     else if (key == "--progress") progress = std::stol(val);
     else if (key == "--red-black") redBlack = std::stol(val);
     else if (key == "--prefix") prefix = val;
+    else if (key == "--grain-rate") grainRate = std::stod(val);
+    else if (key == "--grain-prob") grainProb = std::stod(val);
     else {
       std::cerr << "unknown option " << key << "\n";
       return 2;
@@ -84,6 +88,8 @@ int main(int argc, char **argv) {
   SiliconModel::addXValley<NumType>(electrons);
   using namespace SiliconModel;
   addScattering<NumType>(electrons, device, {0}, ACOUSTIC | ZERO_ORDER | FIRST_ORDER | COULOMB);
+  if (grainRate > 0)
+    electrons->setGrainScatterMechanism(std::make_unique<emcGrainScatterMechanism<NumType>>(grainProb, grainRate));
   param.addParticleType(std::move(electrons));
 
   SimulationType simulation(param, device, solver, pmScheme);

@@ -38,6 +38,7 @@ private:
   SizeType seed;
   emcdetail::HostEnsemble staging;
   bool uploaded = false;
+  bool grain = false; // the type carries a grain mechanism: its clocks live on the device
 
   SizeType nrOnGpu() const { return uploaded ? static_cast<SizeType>(emcgpu_ensemble_size(ctx)) : staging.size(); }
 
@@ -49,6 +50,8 @@ private:
       ptrs[s] = staging.stream[s].data();
     emcgpu::require(ctx, emcgpu_set_ensemble(ctx, static_cast<int64_t>(staging.size()), ptrs, staging.packed.data(), 0),
                     "emcgpu_set_ensemble");
+    if (grain && staging.size())
+      emcgpu::require(ctx, emcgpu_set_grain_clock(ctx, staging.grainTau.data()), "emcgpu_set_grain_clock");
     emcgpu::require(ctx, emcgpu_rng_philox(ctx, seed), "emcgpu_rng_philox");
     emcgpu::require(ctx, emcgpu_set_step_index(ctx, 1), "emcgpu_set_step_index");
     // head room for injected particles: avoids re-allocations during the run
@@ -86,11 +89,6 @@ public:
       gpuType = idxType;
       moved++;
       type->initScatterTables(); // host, exactly as the reference (emcAbstractParticleHandler.hpp:99-101)
-      if (type->scatterHandler.hasGrainScatterMechanism())
-        emcMessage::getInstance()
-            .addError("Grain scattering has no device implementation yet; it cannot run on the GPU path and there is "
-                      "no CPU fallback.")
-            .print();
     }
     if (moved != 1)
       emcMessage::getInstance()
@@ -103,6 +101,7 @@ public:
           .print();
     auto &type = *this->idxTypeToPartType.at(gpuType);
     emcgpu::uploadParticleType(ctx, type);
+    grain = emcgpu::uploadGrainMechanism(ctx, type);
     emcdetail::FlatDevice<T, Dim> flat(this->device);
     flat.desc.pmScheme = inPMScheme.deviceSchemeId() - 1;
     emcgpu::require(ctx,

@@ -58,6 +58,7 @@ private:
     bool uploaded = false;
     std::vector<double> lastObs; // [valley][3] sums of the last step (or of the resting ensemble)
     bool obsValid = false;
+    bool grain = false;                           // the type carries a grain mechanism: clocks live on the device
     SizeType tableVersion = 0;                    // version of the scatter tables on the device
     std::vector<emcPhononBath<T> *> phononBaths;  // baths fed by the polar-optical mechanisms of the type
   };
@@ -96,6 +97,8 @@ private:
     emcgpu::require(st.ctx,
                     emcgpu_set_ensemble(st.ctx, static_cast<int64_t>(st.staging.size()), ptrs, st.staging.packed.data(), 0),
                     "emcgpu_set_ensemble");
+    if (st.grain && st.staging.size())
+      emcgpu::require(st.ctx, emcgpu_set_grain_clock(st.ctx, st.staging.grainTau.data()), "emcgpu_set_grain_clock");
     emcgpu::require(st.ctx, emcgpu_rng_philox(st.ctx, stepSeed), "emcgpu_rng_philox");
     emcgpu::require(st.ctx, emcgpu_set_step_index(st.ctx, 1), "emcgpu_set_step_index");
     st.uploaded = true;
@@ -170,6 +173,7 @@ public:
                       emcgpu_last_error(nullptr))
             .print();
       emcgpu::uploadParticleType(st.ctx, *type);
+      st.grain = emcgpu::uploadGrainMechanism(st.ctx, *type);
       st.tableVersion = type->scatterHandler.getTableVersion();
       st.phononBaths = emcgpu::collectPhononBaths(*type);
       configure(idxType);

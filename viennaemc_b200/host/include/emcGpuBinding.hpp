@@ -31,6 +31,14 @@ inline void require(emcgpu_ctx *ctx, int status, const std::string &what) {
       .print();
 }
 
+// emcgpu_set_grain for the grain mechanism of a particle type (none: the clock is inert and stays on the host)
+template <class T, class DeviceType> bool uploadGrainMechanism(emcgpu_ctx *ctx, const emcParticleType<T, DeviceType> &type) {
+  const auto *grain = type.scatterHandler.getGrainScatterMechanism();
+  require(ctx, emcgpu_set_grain(ctx, grain ? grain->getTransmissionProbability() : 0.5, grain ? grain->getScatterRate() : 0.),
+          "emcgpu_set_grain");
+  return grain != nullptr;
+}
+
 // the phonon baths the mechanisms of a particle type feed, in the order of first appearance (= device bath index)
 template <class T, class DeviceType>
 std::vector<emcPhononBath<T> *> collectPhononBaths(const emcParticleType<T, DeviceType> &type) {

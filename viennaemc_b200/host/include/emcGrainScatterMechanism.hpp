@@ -1,7 +1,8 @@
 // Grain-boundary scattering (second exponential clock).  Interface mirrored: reference
 // include/emcGrainScatterMechanism.hpp (ctor: transmission probability, scatter rate [1/s];
-// getScatterRate()).  No device sampler exists yet: a particle type that carries one is rejected
-// when it is handed to a GPU particle handler (it is off in every example configuration).
+// getScatterRate()).  The event itself -- reflection into the opposite or transmission into the same hemisphere about
+// the current k (:40-77) -- and the clock run on the device (grainEvent, viennaemc_b200/csrc/emc_bulk_kernel.cuh); the
+// GPU particle handlers hand transmission probability and rate over with emcgpu_set_grain.
 #ifndef EMC_GRAIN_SCATTER_MECHANISM_HPP
 #define EMC_GRAIN_SCATTER_MECHANISM_HPP
 

@@ -120,6 +120,7 @@ public:
     grainMechanism = std::move(newMechanism);
   }
   bool hasGrainScatterMechanism() const { return static_cast<bool>(grainMechanism); }
+  const emcGrainScatterMechanism<T> *getGrainScatterMechanism() const { return grainMechanism.get(); }
 
   template <class DerivedSurfaceScatterMechanism>
   typename std::enable_if<std::is_base_of<emcSurfaceScatterMechanism<T, DeviceType>, DerivedSurfaceScatterMechanism>::value>::type
