@@ -1438,45 +1438,68 @@ __device__ __forceinline__ int reservoirSlots(double expected, double nrCarriers
   return expected > 0.0 ? (int)ceil(expected / nrCarriers) : 0;
 }
 
-__global__ void __launch_bounds__(256) contactRankKernel(const __grid_constant__ DevGeometry G, const ContactParams K) {
+// One CTA.  The rank of a particle among the particles of its cell -- in index order -- is (particles of the cell in
+// earlier tiles and earlier warps of this tile) + (earlier lanes of its warp with the same cell): per-cell counters (shared
+// memory when the grid fits, else the zeroed global scratch) are advanced warp by warp in index order, lanes of a warp
+// that share a cell are ranked with __match_any_sync.  O(M) instead of comparing every pair of list entries.
+constexpr int kRankThreads = 1024;
+
+__global__ void __launch_bounds__(kRankThreads) contactRankKernel(const __grid_constant__ DevGeometry G, const ContactParams K,
+                                                                   const int countersInSmem) {
+  extern __shared__ int sCellCount[];
+  int *cnt = countersInSmem ? sCellCount : K.cellCount;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (countersInSmem)
+    for (int c = tid; c < G.cells; c += blockDim.x) sCellCount[c] = 0;
+  __syncthreads();
   const int m = K.ctl->nReservoir;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
-    const int cell = K.listCell[j];
-    int rank = 0;
-    for (int i = 0; i < j; i++) rank += K.listCell[i] == cell;
-    if (K.share) { // particles of the lower ranks come first in the global index order
-      for (int r = 0; r < K.rank; r++) rank += (int)K.share[(size_t)r * G.cells + cell];
-    } else {
-      atomicAdd(&K.cellCount[cell], 1);
+  for (int base = 0; base < m; base += kRankThreads) {
+    const int j = base + tid;
+    const int cell = j < m ? K.listCell[j] : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, cell);
+    const int leaderLane = __ffs(peers) - 1;
+    int before = 0; // particles of the cell ahead of this warp
+    for (int w = 0; w < kRankThreads / 32; w++) {
+      if (warp == w && cell >= 0) {
+        if (lane == leaderLane) {
+          before = cnt[cell];
+          cnt[cell] = before + __popc(peers);
+        }
+        before = __shfl_sync(peers, before, leaderLane);
+      }
+      __syncthreads();
     }
-    if (rank >= reservoirSlots(K.expected[cell], K.nrCarriers)) {
-      K.flag[K.listParticle[j]] = kGone;
-      atomicAdd(&K.ctl->net[cellContact(G, cell)], -1);
+    if (cell >= 0) {
+      int rank = before + __popc(peers & ((1u << lane) - 1u));
+      if (K.share) // particles of the lower ranks come first in the global index order
+        for (int r = 0; r < K.rank; r++) rank += (int)K.share[(size_t)r * G.cells + cell];
+      if (rank >= reservoirSlots(K.expected[cell], K.nrCarriers)) {
+        K.flag[K.listParticle[j]] = kGone;
+        atomicAdd(&K.ctl->net[cellContact(G, cell)], -1);
+      }
     }
   }
-  if (!lastBlockDone(&K.ctl->ticket[2])) return;
-  for (int c = threadIdx.x; c < G.cells; c += blockDim.x) {
-    int cnt = 0;
+  __syncthreads();
+  for (int c = tid; c < G.cells; c += blockDim.x) {
+    int n = 0;
     if (G.cellKind[c] & 1u) {
-      int group;
+      int group = cnt[c];
       if (K.share) {
         group = 0;
         for (int r = 0; r < K.world; r++) group += (int)K.share[(size_t)r * G.cells + c];
-      } else {
-        group = __ldcg(K.cellCount + c);
-        K.cellCount[c] = 0;
       }
+      if (!countersInSmem) cnt[c] = 0; // the global scratch stays zero between launches
       const int kept = min(group, reservoirSlots(K.expected[c], K.nrCarriers));
       const double diff = K.expected[c] - kept * K.nrCarriers;
-      cnt = diff > 0.0 ? (int)ceil(diff / K.nrCarriers) : 0;
-      if (K.share) cnt = injectShareOfRank(cnt, K.rank, K.world, c, K.ctl->step);
-      if (cnt) atomicAdd(&K.ctl->net[cellContact(G, c)], cnt);
+      n = diff > 0.0 ? (int)ceil(diff / K.nrCarriers) : 0;
+      if (K.share) n = injectShareOfRank(n, K.rank, K.world, c, K.ctl->step);
+      if (n) atomicAdd(&K.ctl->net[cellContact(G, c)], n);
     }
-    K.injectCount[c] = cnt;
+    K.injectCount[c] = n;
   }
   __syncthreads();
   const int total = blockExclusiveScan(K.injectCount, G.cells);
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     K.injectCount[G.cells] = total;
     K.ctl->toInject = total;
   }

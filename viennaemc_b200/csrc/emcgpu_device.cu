@@ -453,7 +453,12 @@ int doContacts(emcgpu_ctx *ctx, bool fromStep, const uint64_t *replayDraws, int6
     r->allreduce(r->allreduceUser, r->dShare.as<double>(), (int64_t)n, ctx->stream);
     K.share = r->dShare.as<const double>();
   }
-  contactRankKernel<<<std::min(grid, 2 * ctx->smCount), 256, 0, ctx->stream>>>(G, K);
+  {
+    const size_t counterBytes = (size_t)G.cells * sizeof(int);
+    const int inSmem = counterBytes <= (size_t)ctx->maxSmemOptin - 4096 ? 1 : 0;
+    if (inSmem) CUDA_TRY(ctx, cudaFuncSetAttribute(contactRankKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)counterBytes));
+    contactRankKernel<<<1, kRankThreads, inSmem ? counterBytes : 0, ctx->stream>>>(G, K, inSmem);
+  }
   ctx->launches += 3;
   CUDA_TRY(ctx, cudaGetLastError());
   if (int rc = doCompaction(ctx)) return rc;
