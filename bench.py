@@ -170,6 +170,36 @@ def cpu_reference(steps, warmup, budget_s):
             "seconds": res["move_s"] + res["obs_s"]}, res
 
 
+def device_run_numbers(budget_s=60.0):
+    """Configs 3 and 4 (parity-test cases, not the bench metric): Monte Carlo loop of the self-consistent device runs through
+    the drop-in C++ API (viennaemc_b200/bin example drivers), reported next to the headline line.  Untimed region of bench.py."""
+    import re
+    import tempfile
+    out = {}
+    runs = (("resistor2D", "reference_order", ["--steps", "3000", "--transient", "1000", "--avg", "1000", "--red-black", "0"]),
+            ("resistor2D", "red_black", ["--steps", "3000", "--transient", "1000", "--avg", "1000", "--red-black", "1"]),
+            ("mosfet2D", "reference_order", ["--steps", "300", "--transient", "100", "--avg", "100", "--red-black", "0"]),
+            ("mosfet2D", "red_black", ["--steps", "600", "--transient", "200", "--avg", "200", "--red-black", "1"]))
+    t_end = time.time() + budget_s
+    for exe, order, extra in runs:
+        path = os.path.join(ROOT, "viennaemc_b200", "bin", exe)
+        if not os.path.exists(path) or time.time() > t_end:
+            continue
+        with tempfile.TemporaryDirectory() as tmp:
+            try:
+                r = subprocess.run([path, "--seed", "5", "--progress", "100000", *extra], cwd=tmp, capture_output=True, text=True,
+                                   timeout=max(5.0, t_end - time.time()))
+            except subprocess.TimeoutExpired:
+                continue
+        m = re.search(r"(\d+) steps, (\d+) particles at the end.*Monte Carlo loop alone: ([0-9.eE+-]+) s, ([0-9.eE+-]+) "
+                      r"particle-steps/s\), ([0-9.eE+-]+) SOR sweeps", r.stdout)
+        if r.returncode == 0 and m:
+            steps, n, secs, rate, sweeps = int(m.group(1)), int(m.group(2)), float(m.group(3)), float(m.group(4)), float(m.group(5))
+            out.setdefault(exe, {})[order] = {"particle_steps_per_s": rate, "us_per_step": secs / steps * 1e6, "particles": n,
+                                              "steps": steps, "sor_sweeps_per_step": sweeps}
+    return out
+
+
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -345,6 +375,11 @@ def main_ours(args):
             except Exception as exc:  # the baseline is reported, never required
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": host_cores(), "kind": "reference",
                                         "sample": f"failed: {exc}"}
+        if world == 1 and not args.no_device_runs:
+            try:
+                line["device_runs"] = device_run_numbers()
+            except Exception as exc:
+                line["device_runs"] = {"failed": str(exc)}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
@@ -362,6 +397,7 @@ def main():
     ap.add_argument("--settle", type=int, default=2000, help="untimed time steps before the measurement")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-device-runs", action="store_true", help="skip the (untimed) device-run numbers of configs 3 / 4")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -641,7 +641,10 @@ __global__ void __launch_bounds__(kStreamThreads, 2) bulkStreamKernel(const __gr
 // Loads run S-1 tiles ahead of the arithmetic independent of occupancy and
 // register pressure; dynamic sub-tile claiming keeps the pipeline moving while
 // some warp is busy with an event batch.
-constexpr int kTmaConsumerWarps = 10;
+#ifndef EMC_TMA_CONSUMER_WARPS
+#define EMC_TMA_CONSUMER_WARPS 10
+#endif
+constexpr int kTmaConsumerWarps = EMC_TMA_CONSUMER_WARPS;
 constexpr int kTmaThreads = (kTmaConsumerWarps + 2) * 32; // + loader warp + storer warp
 constexpr int kTile = 256; // particles per tile
 constexpr int kSubTile = 64;
