@@ -61,8 +61,10 @@ def main():
 def main_device():
     subprocess.check_call(["make", "-C", HERE, "_ref/ref_device_driver"], stdout=subprocess.DEVNULL,
                           stderr=subprocess.DEVNULL)
-    drv = os.path.join(HERE, "_ref", "ref_device_driver")
+    subprocess.check_call(["make", "-C", HERE, "_ref/ref_device3d_driver"], stdout=subprocess.DEVNULL,
+                          stderr=subprocess.DEVNULL)
     for name, args in DEVICE_CASES.items():
+        drv = os.path.join(HERE, "_ref", "ref_device3d_driver" if "lz" in args else "ref_device_driver")
         with tempfile.TemporaryDirectory() as tmp:
             out = os.path.join(tmp, "ref.bin")
             cmd = [drv, "--out", out]

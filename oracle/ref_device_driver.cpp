@@ -15,6 +15,9 @@
 // Scenario: a 2-D silicon bar (resistor2D.cpp:73-115 with its sizes as options) with ohmic contacts
 // on the full XMIN / XMAX faces, optionally a gate on a YMIN segment and a second doping region (so
 // that the Robin boundary term, region look-ups and Coulomb tables per region are exercised).
+#ifndef DEVICE_DIM
+#define DEVICE_DIM 2
+#endif
 #include <cstdint>
 #include <cstdio>
 #include <fstream>
@@ -40,11 +43,15 @@
 #include <emcSimulationParameter.hpp>
 #include <emcSimulationResults.hpp>
 
+#if DEVICE_DIM == 2
 #include <mosfet2D/NECSchemeVWD.hpp> // -I $(REF)/examples
+#endif
 #include <mosfet2D/electronVWD.hpp>
 
+// -DDEVICE_DIM=3 builds the 3-D recorder (box lx x ly x lz, the contacts cover whole faces / a strip of YMIN over the full
+// depth); the NEC schemes interpolate forces in 2-D only and exist in the 2-D build alone
 using T = double;
-const SizeType Dim = 2;
+const SizeType Dim = DEVICE_DIM;
 using DeviceType = emcDevice<T, Dim>;
 using Grid = emcGrid<T, Dim>;
 
@@ -80,7 +87,10 @@ struct Blob {
   template <class G> void grid(const std::string &n, const G &g) {
     std::vector<double> v(g.begin(), g.end());
     auto e = g.getExtent();
-    f64(n, v, {e[1], e[0]}); // x fastest
+    std::vector<std::uint64_t> dims;
+    for (size_t d = e.size(); d-- > 0;)
+      dims.push_back(e[d]); // x fastest
+    f64(n, v, dims);
   }
 };
 
@@ -100,7 +110,7 @@ template <class Handler> static void dumpEnsemble(Blob &b, const std::string &p,
                            (std::int64_t)parts[i].region});
   }
   b.f64(p + "k", k, {n, 3});
-  b.f64(p + "pos", x, {n, 2});
+  b.f64(p + "pos", x, {n, Dim});
   b.f64(p + "energy", e);
   b.f64(p + "tau", tau);
   b.f64(p + "label", g);
@@ -108,6 +118,7 @@ template <class Handler> static void dumpEnsemble(Blob &b, const std::string &p,
 }
 
 struct Options {
+  double lz = 6e-8, hz = 2e-8; // 3-D build only
   double lx = 2e-7, ly = 1e-7, hx = 1e-8, hy = 2.5e-8, width = 1e-6, doping = 1e22, doping2 = 0, voltage = 0.05,
          dt = 1e-15, acc = 1e-4, omega = 1.8, emax = 4.0, gateVoltage = 0.5, surfYminConst = -1, surfYmaxMom = -1, grainRate = 0,
          grainProb = 0.5;
@@ -138,6 +149,7 @@ template <class PMScheme, class Electron> int run(const Options &o) {
   std::ostringstream sink;
   std::cout.rdbuf(sink.rdbuf());
 
+#if DEVICE_DIM == 2
   DeviceType device{Silicon::getSiliconMaterial<T>(), {lx, ly}, {hx, hy}};
   device.setDeviceWidth(width);
   device.addConstantDopingRegion({0, 0}, {lx, ly}, doping);
@@ -150,6 +162,20 @@ template <class PMScheme, class Electron> int run(const Options &o) {
   device.addOhmicContact(emcBoundaryPos::XMIN, voltage, {0}, {ly});
   if (gate)
     device.addGateContact(emcBoundaryPos::YMIN, gateVoltage, {lx / 3}, {2 * lx / 3}, 3.9, 1.2e-9, 1.15 / 2);
+#else
+  const double lz = o.lz, hz = o.hz;
+  DeviceType device{Silicon::getSiliconMaterial<T>(), {lx, ly, lz}, {hx, hy, hz}};
+  device.addConstantDopingRegion({0, 0, 0}, {lx, ly, lz}, doping);
+  std::vector<int> regions = {0};
+  if (doping2 != 0) {
+    device.addConstantDopingRegion({lx / 2, 0, 0}, {lx, ly, lz}, doping2);
+    regions.push_back(1);
+  }
+  device.addOhmicContact(emcBoundaryPos::XMAX, 0, {0, 0}, {ly, lz});
+  device.addOhmicContact(emcBoundaryPos::XMIN, voltage, {0, 0}, {ly, lz});
+  if (gate)
+    device.addGateContact(emcBoundaryPos::YMIN, gateVoltage, {lx / 3, 0}, {2 * lx / 3, lz}, 3.9, 1.2e-9, 1.15 / 2);
+#endif
 
   Solver solver(device, acc, omega);
   PMScheme pmScheme;
@@ -191,7 +217,7 @@ template <class PMScheme, class Electron> int run(const Options &o) {
       reservoir.push_back(surf.isReservoirContact(c));
       contactIdx.push_back(surf.getContactIdx(c));
       face.push_back((std::int64_t)toUnderlying(surf.getBoundaryPos(c)));
-      for (int f = 0; f < 4; f++) { // contact index per face this cell lies on (-1: none / not on the face)
+      for (int f = 0; f < 2 * (int)Dim; f++) { // contact index per face this cell lies on (-1: none / not on the face)
         auto bp = static_cast<emcBoundaryPos>(f);
         std::int64_t id = -2;
         if (surf.isOnBoundary(c, bp))
@@ -199,12 +225,17 @@ template <class PMScheme, class Electron> int run(const Options &o) {
         gateIdx.push_back(id);
       }
     }
-    blob.i64("region", region, {ny, nx});
-    blob.i64("is_ohmic", ohmic, {ny, nx});
-    blob.i64("is_reservoir", reservoir, {ny, nx});
-    blob.i64("contact_idx", contactIdx, {ny, nx});
-    blob.i64("first_face", face, {ny, nx});
-    blob.i64("face_contact", gateIdx, {ny, nx, 4});
+    std::vector<std::uint64_t> cellDims;
+    for (size_t d = Dim; d-- > 0;)
+      cellDims.push_back(extent[d]);
+    auto withFaces = cellDims;
+    withFaces.push_back(2 * Dim);
+    blob.i64("region", region, cellDims);
+    blob.i64("is_ohmic", ohmic, cellDims);
+    blob.i64("is_reservoir", reservoir, cellDims);
+    blob.i64("contact_idx", contactIdx, cellDims);
+    blob.i64("first_face", face, cellDims);
+    blob.i64("face_contact", gateIdx, withFaces);
     std::vector<double> contacts; // type, voltage, epsOx, thickness, barrier
     for (size_t i = 0; i < surf.getNrContacts(); i++) {
       const bool isGate = surf.getContactType(i) == emcContactType::GATE;
@@ -242,6 +273,8 @@ template <class PMScheme, class Electron> int run(const Options &o) {
   pmScheme.calcEField(results.eField, results.currPot, device);
   blob.grid("ex_eq", results.eField[0]);
   blob.grid("ey_eq", results.eField[1]);
+  if (Dim > 2)
+    blob.grid("ez_eq", results.eField[Dim - 1]);
   handler.generateInitialParticles(results.currPot);
   blob.u64("draws_init_count", {draws.size()});
   dumpEnsemble(blob, "init_", handler);
@@ -262,6 +295,8 @@ template <class PMScheme, class Electron> int run(const Options &o) {
     blob.grid(p + "pot", results.currPot);
     blob.grid(p + "ex", results.eField[0]);
     blob.grid(p + "ey", results.eField[1]);
+    if (Dim > 2)
+      blob.grid(p + "ez", results.eField[Dim - 1]);
     // label the particles through the (dynamically inert) grain clock so that removals can be traced -- unless a grain
     // mechanism is set: then the clock is live and is recorded as it is
     if (!(o.grainRate > 0))
@@ -304,6 +339,8 @@ int main(int argc, char **argv) {
     else if (k == "--hx") o.hx = std::stod(v);
     else if (k == "--hy") o.hy = std::stod(v);
     else if (k == "--width") o.width = std::stod(v);
+    else if (k == "--lz") o.lz = std::stod(v);
+    else if (k == "--hz") o.hz = std::stod(v);
     else if (k == "--doping") o.doping = std::stod(v);
     else if (k == "--doping2") o.doping2 = std::stod(v); // right half of the bar, second region
     else if (k == "--voltage") o.voltage = std::stod(v);
@@ -333,8 +370,10 @@ int main(int argc, char **argv) {
   const bool vwd = o.electron == "vwd";
   if (o.scheme == "ngp") return vwd ? run<emcNGPScheme<T, DeviceType>, V>(o) : run<emcNGPScheme<T, DeviceType>, E>(o);
   if (o.scheme == "cic") return vwd ? run<emcCICScheme<T, DeviceType>, V>(o) : run<emcCICScheme<T, DeviceType>, E>(o);
+#if DEVICE_DIM == 2
   if (o.scheme == "nec") return vwd ? run<emcNECScheme<T, DeviceType>, V>(o) : run<emcNECScheme<T, DeviceType>, E>(o);
   if (o.scheme == "vwd") return vwd ? run<emcNECSchemeVWD<T, DeviceType>, V>(o) : run<emcNECSchemeVWD<T, DeviceType>, E>(o);
+#endif
   std::cerr << "unknown scheme " << o.scheme << "\n";
   return 2;
 }

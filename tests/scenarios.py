@@ -130,6 +130,12 @@ DEVICE_CASES = {
 DEVICE_CASES["device_grain"] = {"lx": 2e-7, "ly": 1e-7, "hx": 1e-8, "hy": 2.5e-8, "doping": 1e22, "doping2": 0, "voltage": 0.05,
                                "dt": 1e-15, "steps": 8, "levels": 1000, "emax": 4.0, "gate": 0, "seed": 41, "grain-rate": 3e13,
                                "grain-prob": 0.6}
+# 3-D boxes (oracle/_ref/ref_device3d_driver): contacts over whole faces, gate strip over the full depth
+DEVICE_CASES["device_3d_ngp"] = {"lx": 1.6e-7, "ly": 8e-8, "lz": 6e-8, "hx": 1e-8, "hy": 2e-8, "hz": 2e-8, "doping": 3e22, "doping2": 1e22,
+                                 "voltage": 0.2, "dt": 1e-15, "steps": 5, "levels": 500, "emax": 4.0, "gate": 1, "seed": 51}
+DEVICE_CASES["device_3d_cic"] = {"lx": 1.6e-7, "ly": 8e-8, "lz": 6e-8, "hx": 1e-8, "hy": 2e-8, "hz": 2e-8, "doping": 3e22, "doping2": 0,
+                                 "voltage": 0.1, "dt": 1e-15, "steps": 4, "levels": 500, "emax": 4.0, "gate": 0, "seed": 52,
+                                 "scheme": "cic", "surface-ymin-const": 0.4}
 PM_SCHEMES = {"ngp": po.PM_NGP, "cic": po.PM_CIC, "nec": po.PM_NEC, "vwd": po.PM_NEC_VWD}
 
 
@@ -137,14 +143,25 @@ def build_device(case: str):
     """oracle-side model + device of a DEVICE_CASES entry (mirrors oracle/ref_device_driver.cpp)"""
     a = DEVICE_CASES[case]
     regions = (0, 1) if a["doping2"] else (0,)
-    dev = po.Device([a["lx"], a["ly"]], [a["hx"], a["hy"]], device_width=1e-6)
-    dev.add_doping_region([0, 0], [a["lx"], a["ly"]], a["doping"])
-    if a["doping2"]:
-        dev.add_doping_region([a["lx"] / 2, 0], [a["lx"], a["ly"]], a["doping2"])
-    dev.add_contact(1, po.CONTACT_OHMIC, 0.0, [0.0], [a["ly"]])
-    dev.add_contact(0, po.CONTACT_OHMIC, a["voltage"], [0.0], [a["ly"]])
-    if a["gate"]:
-        dev.add_contact(2, po.CONTACT_GATE, 0.5, [a["lx"] / 3], [2 * a["lx"] / 3], 3.9, 1.2e-9, 1.15 / 2)
+    if "lz" in a:  # 3-D box
+        size, h = [a["lx"], a["ly"], a["lz"]], [a["hx"], a["hy"], a["hz"]]
+        dev = po.Device(size, h)
+        dev.add_doping_region([0, 0, 0], size, a["doping"])
+        if a["doping2"]:
+            dev.add_doping_region([a["lx"] / 2, 0, 0], size, a["doping2"])
+        dev.add_contact(1, po.CONTACT_OHMIC, 0.0, [0.0, 0.0], [a["ly"], a["lz"]])
+        dev.add_contact(0, po.CONTACT_OHMIC, a["voltage"], [0.0, 0.0], [a["ly"], a["lz"]])
+        if a["gate"]:
+            dev.add_contact(2, po.CONTACT_GATE, 0.5, [a["lx"] / 3, 0.0], [2 * a["lx"] / 3, a["lz"]], 3.9, 1.2e-9, 1.15 / 2)
+    else:
+        dev = po.Device([a["lx"], a["ly"]], [a["hx"], a["hy"]], device_width=1e-6)
+        dev.add_doping_region([0, 0], [a["lx"], a["ly"]], a["doping"])
+        if a["doping2"]:
+            dev.add_doping_region([a["lx"] / 2, 0], [a["lx"], a["ly"]], a["doping2"])
+        dev.add_contact(1, po.CONTACT_OHMIC, 0.0, [0.0], [a["ly"]])
+        dev.add_contact(0, po.CONTACT_OHMIC, a["voltage"], [0.0], [a["ly"]])
+        if a["gate"]:
+            dev.add_contact(2, po.CONTACT_GATE, 0.5, [a["lx"] / 3], [2 * a["lx"] / 3], 3.9, 1.2e-9, 1.15 / 2)
     dev.pm_scheme = PM_SCHEMES[a.get("scheme", "ngp")]
     dev.electron_kind = po.ELECTRON_VWD if a.get("electron") == "vwd" else po.ELECTRON_EMC
     if "surface-ymin-const" in a:

@@ -32,9 +32,9 @@ def configure(ctx, dev: po.Device, expected=None, math_mode=capi.MATH_EXACT):
     ctx.device_set_particle_kind(dev.electron_kind)
 
 
-def assert_grid_close(got, want, what, rtol=STATE_RTOL):
+def assert_grid_close(got, want, what, rtol=STATE_RTOL, scale=None):
     want = np.asarray(want).ravel()
-    scale = float(np.abs(want).max()) or 1.0
+    scale = scale or float(np.abs(want).max()) or 1.0
     err = float(np.max(np.abs(got - want))) / scale
     assert err <= rtol, f"{what}: {err:.3e}"
 
@@ -59,6 +59,8 @@ def assert_ensemble_close(got: po.Ensemble, want: po.Ensemble, dev, what, check_
     errs["tau"] = rel_err(got.tau[:n], want.tau[:n])
     errs["x"] = rel_err(got.x[:n], want.x[:n], dev.max_pos[0])
     errs["y"] = rel_err(got.y[:n], want.y[:n], dev.max_pos[1])
+    if dev.dim > 2:
+        errs["z"] = rel_err(got.z[:n], want.z[:n], dev.max_pos[2])
     if check_grain:
         errs["grainTau"] = rel_err(got.grainTau[:n], want.grainTau[:n])
     bad = {k: v for k, v in errs.items() if not v <= STATE_RTOL}
@@ -84,6 +86,9 @@ def test_grid_chain_against_the_reference(gpu_ctx_factory, case):
     ctx.device_efield()
     assert_grid_close(ctx.device_get_grid(capi.GRID_EFIELD_X), g["ex_eq"], "Ex")
     assert_grid_close(ctx.device_get_grid(capi.GRID_EFIELD_Y), g["ey_eq"], "Ey")
+    if dev.dim > 2:
+        # the box is uniform along z: Ez is a difference of (almost) equal potentials, compared on the scale of the field
+        assert_grid_close(ctx.device_get_grid(capi.GRID_EFIELD_Z), g["ez_eq"], "Ez", scale=float(np.abs(g["ex_eq"]).max()))
     # particles of the reference -> counts (exact) -> concentration
     upload_ensemble(ctx, ens_from(g, "init_"))
     ctx.device_assign()
@@ -106,7 +111,7 @@ def _step_streams(g, a, m, dev, s):
     p = f"s{s}_"
     marks = g["draw_marks"].reshape(-1, 3)
     ens = ens_from(g, p + "pre_")
-    e = np.stack([g[p + "ex"].ravel(), g[p + "ey"].ravel()])
+    e = np.stack([g[p + "e" + ax].ravel() for ax in "xyz"[: dev.dim]])
     draws = g["draws"][int(marks[s, 0]):int(marks[s, 1])]
     mt = np.zeros(0)
     # replay through the oracle with a flat stream to learn who consumed what
@@ -141,6 +146,8 @@ def test_particle_step_replays_the_reference(gpu_ctx_factory, case, math_mode):
         ctx.rng_replay(sd, offsets)
         ctx.device_set_grid(capi.GRID_EFIELD_X, e[0])
         ctx.device_set_grid(capi.GRID_EFIELD_Y, e[1])
+        if dev.dim > 2:
+            ctx.device_set_grid(capi.GRID_EFIELD_Z, e[2])
         ctx.set_step_index(s + 1)
         ctx.event_log_enable(1 << 16)
         removed = ctx.device_step(a["dt"])
@@ -178,7 +185,7 @@ def test_contacts_replay_the_reference(gpu_ctx_factory, case):
         assert np.array_equal(net, g[p + "net_injected_per_contact"]), f"step {s}"
         assert_ensemble_close(download_ensemble(ctx), ens_from(g, p + "post_"), dev, f"{case} contacts {s}",
                               check_grain="grain-rate" in a)
-        injected_total += len(draws) // 9
+        injected_total += len(draws) // (dev.dim + 7)
         ctx.device_assign()
         assert_counts(dev, ctx.device_get_grid(capi.GRID_COUNT), g[p + "count"], f"counts {s}")
         ctx.device_concentration()

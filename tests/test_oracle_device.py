@@ -13,13 +13,15 @@ CASES = list(DEVICE_CASES)
 
 
 def ens_from(g, p):
-    pos = np.concatenate([g[p + "pos"], np.zeros((len(g[p + "energy"]), 1))], axis=1)
+    pos = g[p + "pos"]
+    if pos.shape[1] == 2:
+        pos = np.concatenate([pos, np.zeros((len(g[p + "energy"]), 1))], axis=1)
     return po.Ensemble.from_arrays(g[p + "k"], pos, g[p + "energy"], g[p + "tau"], g[p + "label"], g[p + "idx"])
 
 
 def assert_same_ensemble(a, b, what):
     assert a.n == b.n, what
-    for f in ("kx", "ky", "kz", "energy", "tau", "x", "y", "valley", "sub", "region"):
+    for f in ("kx", "ky", "kz", "energy", "tau", "x", "y", "z", "valley", "sub", "region"):
         assert np.array_equal(getattr(a, f)[: a.n], getattr(b, f)[: b.n]), f"{what}: {f}"
 
 
@@ -27,11 +29,10 @@ def assert_same_ensemble(a, b, what):
 def test_flattened_device_description_equals_the_reference(case):
     g = load_golden(case)
     m, dev = build_device(case)
-    ny, nx = g["region"].shape
-    assert dev.extent == [nx, ny]
+    assert dev.extent == list(g["region"].shape[::-1])
     assert np.array_equal(dev.region, g["region"].ravel())
     assert np.array_equal(dev.doping / dev.ni, g["doping_norm"].ravel())
-    assert np.array_equal(dev.face_contact, g["face_contact"].reshape(-1, 4))
+    assert np.array_equal(dev.face_contact, g["face_contact"].reshape(-1, 2 * dev.dim))
     vt, debye, vol, ni = g["device_consts"][:4]
     assert (dev.vt, dev.debye, dev.cell_volume, dev.ni) == (vt, debye, vol, ni)
     d = dev.c()
@@ -60,6 +61,7 @@ def test_equilibrium_chain_bit_for_bit(case):
     assert np.array_equal(pot, g["pot_eq"].ravel())
     e = dev.efield(pot)
     assert np.array_equal(e[0], g["ex_eq"].ravel()) and np.array_equal(e[1], g["ey_eq"].ravel())
+    assert dev.dim == 2 or np.array_equal(e[2], g["ez_eq"].ravel())
     mt = po.mt_state(a["seed"])
     # electronVWD always starts from the equilibrium potential; emcElectron(usePotentialForInit = false) from the doping
     ens = dev.generate_initial(m, mt, pot=pot if a.get("electron") == "vwd" else None)
@@ -98,6 +100,7 @@ def test_emc_steps_bit_for_bit(case):
         assert np.array_equal(pot, g[p + "pot"].ravel()), f"step {s}: potential"
         e = dev.efield(pot)
         assert np.array_equal(e[0], g[p + "ex"].ravel()) and np.array_equal(e[1], g[p + "ey"].ravel())
+        assert dev.dim == 2 or np.array_equal(e[2], g[p + "ez"].ravel())
         assert_same_ensemble(ens, ens_from(g, p + "pre_"), f"step {s}: pre")
         assert int(marks[s, 0]) == int(g["draws_init_count"][0]) + sum(
             int(marks[j, 2] - marks[j, 0]) for j in range(s))
