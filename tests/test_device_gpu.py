@@ -271,3 +271,53 @@ def test_sor_variants_agree(gpu_ctx_factory, case):
         diff = float(np.abs(results["redblack"][k][1] - results["rows"][k][1]).max()) * vt
         assert diff <= tol_volt, (k, diff)
         assert results["redblack"][k][0] >= 1
+
+
+def test_large_grid_poisson_and_empty_ensemble(gpu_ctx_factory):
+    """A grid that does not fit into the shared memory of a CTA (201 x 201 points, gate strip, two ohmic contacts): the
+    lexicographic solver falls back to the hyperplane kernel on global memory, red-black to the single-CTA form; both against
+    the oracle's sequential sweep.  Then a device run with NO particles: contacts fill the reservoir cells from nothing."""
+    lx = 2e-7
+    dev = po.Device([lx, lx], [1e-9, 1e-9], device_width=1e-6)
+    dev.add_doping_region([0, 0], [lx, lx], 2e23)
+    dev.add_doping_region([lx / 2, 0], [lx, lx], -1e23)
+    dev.add_contact(1, po.CONTACT_OHMIC, 0.0, [0.0], [lx])
+    dev.add_contact(0, po.CONTACT_OHMIC, 0.2, [0.0], [lx])
+    dev.add_contact(2, po.CONTACT_GATE, 0.4, [lx / 3], [2 * lx / 3], 3.9, 1.2e-9, 1.15 / 2)
+    m = build_device("device_bar")[0]
+    pot_ref = dev.initial_potential()
+    sweeps_ref = dev.sor(pot_ref, None, 1e-4, 1.8, True)
+    ctx = gpu_ctx_factory()
+    upload_model(ctx, m)
+    configure(ctx, dev)
+    assert ctx.device_poisson(True, 1e-4, 1.8, True) == sweeps_ref
+    assert_grid_close(ctx.device_get_grid(capi.GRID_POTENTIAL), pot_ref, "equilibrium potential, 201 x 201")
+    conc = np.exp(pot_ref) * (1 + 0.05 * np.sin(np.arange(dev.cells)))  # some non-equilibrium density
+    pot2 = pot_ref.copy()
+    sweeps2 = dev.sor(pot2, conc.copy(), 1e-4, 1.8, True)
+    ctx.device_set_grid(capi.GRID_CONCENTRATION, conc)
+    assert ctx.device_poisson(False, 1e-4, 1.8, True) == sweeps2
+    assert_grid_close(ctx.device_get_grid(capi.GRID_POTENTIAL), pot2, "non-equilibrium potential, 201 x 201")
+    # red-black converges to the same potential; on a grid this large the stopping rule (max |delta| of a sweep) leaves both
+    # orders well short of the fixed point at 1e-4 V, so compare them where they have converged
+    pot3 = pot_ref.copy()
+    dev.sor(pot3, conc.copy(), 1e-7, 1.8, True)
+    ctx.set_option("sor_order", 1)
+    ctx.device_set_grid(capi.GRID_POTENTIAL, pot_ref)
+    assert ctx.device_poisson(False, 1e-7, 1.8, True) >= 1
+    assert float(np.abs(ctx.device_get_grid(capi.GRID_POTENTIAL) - pot3).max()) * dev.vt <= 1e-4
+    # empty ensemble
+    small = build_device("device_bar")[1]
+    ctx2 = gpu_ctx_factory()
+    upload_model(ctx2, m)
+    configure(ctx2, small, math_mode=capi.MATH_FAST)
+    empty = po.Ensemble(0)
+    empty.n = 0
+    upload_ensemble(ctx2, empty)
+    ctx2.device_reserve(4096)
+    ctx2.rng_philox(1)
+    counters, sweeps = ctx2.device_run(1e-15, 3, 1e-4, 1.8, True)
+    expected = small.expected_at_contact()
+    assert counters[0, 1, :].sum() == int(np.ceil(expected[expected > 0]).sum()) and counters[:, 0, :].sum() >= 0
+    assert ctx2.size == counters[:, 1, :].sum() - counters[:, 0, :].sum()
+    assert ctx2.device_get_grid(capi.GRID_COUNT).sum() == ctx2.size
