@@ -35,11 +35,13 @@ def _reference_replay_streams(case):
 
 
 @pytest.mark.parametrize("math_mode", [capi.MATH_EXACT, capi.MATH_FAST], ids=["exact", "fast"])
-@pytest.mark.parametrize("steps_per_launch", [1, 7])
+@pytest.mark.parametrize("steps_per_launch,multi_kernel", [(1, 0), (7, 1), (7, 2), (16, 2)],
+                         ids=["spl1", "spl7-inplace", "spl7-deferred", "spl16-deferred"])
 @pytest.mark.parametrize("case", CASES)
-def test_replay_of_reference_draws(gpu_ctx_factory, case, steps_per_launch, math_mode):
+def test_replay_of_reference_draws(gpu_ctx_factory, case, steps_per_launch, multi_kernel, math_mode):
     g, a, m, draws, offsets = _reference_replay_streams(case)
     ctx = gpu_ctx_factory()
+    ctx.set_option("multi_kernel", multi_kernel)  # 1: K1b (events in place), 2: K1c (deferred events)
     upload_model(ctx, m)
     upload_ensemble(ctx, golden_ensemble(g, "init_"))
     ctx.rng_replay(draws, offsets)
@@ -75,8 +77,9 @@ def test_replay_of_reference_draws(gpu_ctx_factory, case, steps_per_launch, math
 
 
 @pytest.mark.parametrize("math_mode", [capi.MATH_EXACT, capi.MATH_FAST], ids=["exact", "fast"])
+@pytest.mark.parametrize("multi_kernel", [1, 2], ids=["inplace", "deferred"])
 @pytest.mark.parametrize("case", ["si_bulk", "mixed"])
-def test_philox_against_oracle(gpu_ctx_factory, case, math_mode):
+def test_philox_against_oracle(gpu_ctx_factory, case, math_mode, multi_kernel):
     """Independent (counter-based) RNG: GPU and oracle consume identical Philox streams."""
     a = dict(GOLDEN_CASES[case]["args"])
     m = build_model(case)
@@ -85,6 +88,7 @@ def test_philox_against_oracle(gpu_ctx_factory, case, math_mode):
     ens, _ = m.generate_initial(box, [4, 4, 4], 1e23, st)  # 6400 particles
     n_steps, dt, seed, base = 150, 4 * a["dt"], 0xC0FFEE1234, 1000
     ctx = gpu_ctx_factory()
+    ctx.set_option("multi_kernel", multi_kernel)
     upload_model(ctx, m)
     upload_ensemble(ctx, ens, particle_id_base=base)
     ctx.rng_philox(seed)
@@ -109,7 +113,8 @@ def test_philox_against_oracle(gpu_ctx_factory, case, math_mode):
     assert np.max(np.abs(obs[:, :, 1] - res["obs"][:, :, 1])) <= 1e-11 * np.abs(res["obs"][:, :, 1]).max()
 
 
-def test_sharding_invariance_and_determinism(gpu_ctx_factory):
+@pytest.mark.parametrize("multi_kernel", [1, 2], ids=["inplace", "deferred"])
+def test_sharding_invariance_and_determinism(gpu_ctx_factory, multi_kernel):
     """Philox key = global particle id: a shard [lo,hi) evolves exactly as inside the full ensemble,
     and two runs give bit-identical particle state."""
     m = build_si()
@@ -120,6 +125,7 @@ def test_sharding_invariance_and_determinism(gpu_ctx_factory):
 
     def run(sub: po.Ensemble, base):
         ctx = gpu_ctx_factory()
+        ctx.set_option("multi_kernel", multi_kernel)
         upload_model(ctx, m)
         upload_ensemble(ctx, sub, particle_id_base=base)
         ctx.rng_philox(42)
@@ -238,8 +244,9 @@ def test_large_ensemble_properties(gpu_ctx_factory):
     n = 1 << 24
     box = [1e-6] * 3
     res = []
-    for spl in (1, 8):
+    for spl, mk in ((1, 0), (8, 0), (8, 1)):  # one step per launch (K1a), deferred events (K1c), in place (K1b)
         ctx = gpu_ctx_factory()
+        ctx.set_option("multi_kernel", mk)
         upload_model(ctx, m)
         ctx.generate_bulk_ensemble(n, box, 300.0, 0, seed=3)
         ctx.rng_philox(11)
@@ -249,11 +256,13 @@ def test_large_ensemble_properties(gpu_ctx_factory):
         e = download_ensemble(ctx)
         res.append((e, obs))
         ctx.close()
-    (e1, o1), (e8, o8) = res
+    (e1, o1), (e8, o8), (e8b, o8b) = res
     for f in po.Ensemble.F64[:5] + po.Ensemble.F64[6:] + po.Ensemble.I32:
         assert np.array_equal(getattr(e1, f), getattr(e8, f)), f
+        assert np.array_equal(getattr(e1, f), getattr(e8b, f)), f
     assert np.all(o1[:, :, 2].sum(axis=1) == n)
-    assert np.allclose(o1, o8, rtol=1e-12)
+    assert np.array_equal(o1[:, :, 2], o8[:, :, 2]) and np.array_equal(o1[:, :, 2], o8b[:, :, 2])
+    assert np.allclose(o1, o8, rtol=1e-12) and np.allclose(o1, o8b, rtol=1e-12)
     for arr in (e1.x, e1.y, e1.z):
         assert arr.min() >= 0 and arr.max() <= 1e-6
     assert e1.energy.min() > 0 and np.isfinite(e1.energy).all()

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "emcgpu_internal.cuh"
+#include "emc_bulk_defer.cuh"
 
 using namespace emc;
 
@@ -125,6 +126,23 @@ cudaError_t launchFused(emcgpu_ctx *ctx, const BulkParams &P, size_t smem, int g
                  : launchKernel(ctx, bulkStepKernel<false, RNG_PHILOX>, P, smem, grid);
   return exact ? launchKernel(ctx, bulkStepKernel<true, RNG_REPLAY>, P, smem, grid)
                : launchKernel(ctx, bulkStepKernel<false, RNG_REPLAY>, P, smem, grid);
+}
+
+// K1c, several steps per launch, scattering events deferred into a CTA-wide queue
+cudaError_t launchDefer(emcgpu_ctx *ctx, const BulkParams &P, size_t smem, int grid) {
+  const bool exact = ctx->mathMode == EMCGPU_MATH_EXACT;
+  if (ctx->rngMode == RNG_PHILOX)
+    return exact ? launchKernel(ctx, bulkDeferKernel<true, RNG_PHILOX>, P, smem, grid, kDeferThreads)
+                 : launchKernel(ctx, bulkDeferKernel<false, RNG_PHILOX>, P, smem, grid, kDeferThreads);
+  return exact ? launchKernel(ctx, bulkDeferKernel<true, RNG_REPLAY>, P, smem, grid, kDeferThreads)
+               : launchKernel(ctx, bulkDeferKernel<false, RNG_REPLAY>, P, smem, grid, kDeferThreads);
+}
+// shared memory of K1c for `steps` steps per launch; 0 = does not fit
+size_t deferSmem(const emcgpu_ctx *ctx, int steps, bool tablesInSmem) {
+  const BulkSmem L(kDeferWarps * steps * ctx->hModel.nValleys * 3, ctx->hModel.nValleys, (int)ctx->hMechs.size(),
+                   ctx->hModel.tableDoubles, tablesInSmem, kDeferQueueWords);
+  const size_t b = deferSmemBytes(L, steps, ctx->hModel.nValleys);
+  return b <= (size_t)ctx->maxSmemOptin ? b : 0;
 }
 
 // K1a, one step per launch
@@ -301,6 +319,12 @@ int emcgpu_set_option(emcgpu_ctx *ctx, const char *name, int64_t value) {
   }
   if (!strcmp(name, "stages")) {
     ctx->optStages = (int)value;
+    return EMCGPU_OK;
+  }
+  if (!strcmp(name, "multi_kernel")) {
+    if (value != 0 && value != 1 && value != 2)
+      return fail(ctx, EMCGPU_E_INVALID, "multi_kernel must be 0 (deferred events when the ensemble is large), 1 (in place) or 2 (deferred events always)");
+    ctx->optMultiKernel = (int)value;
     return EMCGPU_OK;
   }
   return fail(ctx, EMCGPU_E_INVALID, "unknown option '%s'", name);
@@ -684,12 +708,33 @@ int emcgpu_bulk_step_device(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPer
   P.dt = dt;
   if (ctx->n >= (int64_t)1 << 32) return fail(ctx, EMCGPU_E_CAPACITY, "at most 2^32-1 particles per context");
   for (int done = 0; done < nSteps;) {
-    const int chunk = std::min(stepsPerLaunch, nSteps - done);
+    int chunk = std::min(stepsPerLaunch, nSteps - done);
+    // several steps per launch: deferred-event kernel (K1c) for ensembles that fill the machine
+    const int64_t nChunks = ctx->n / kDeferChunk;
+    const bool defer = chunk > 1 && !ctx->grainOn &&
+                       (ctx->optMultiKernel == 2 || (ctx->optMultiKernel == 0 && nChunks >= (int64_t)ctx->smCount * kDeferWarps));
+    if (defer) chunk = std::min(chunk, kDeferMaxSteps);
     P.nSteps = chunk;
     P.step0 = ctx->nextStep + done;
     P.obs = obsDevice + (size_t)done * nV * 3;
     if (ctx->grainOn && !ctx->grainClockSet)
       return fail(ctx, EMCGPU_E_INVALID, "a grain mechanism is set but the grain clocks were not uploaded (emcgpu_set_grain_clock)");
+    if (defer) {
+      bool inSmem = !ctx->optTablesGlobal;
+      size_t smem = inSmem ? deferSmem(ctx, chunk, true) : 0;
+      if (!smem) {
+        inSmem = false;
+        smem = deferSmem(ctx, chunk, false);
+      }
+      if (smem) {
+        P.tablesInSmem = inSmem ? 1 : 0;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nChunks + kDeferWarps - 1) / kDeferWarps, ctx->smCount));
+        cudaError_t e = launchDefer(ctx, P, smem, grid);
+        if (e != cudaSuccess) return fail(ctx, EMCGPU_E_CUDA, "bulk step launch failed: %s", cudaGetErrorString(e));
+        done += chunk;
+        continue;
+      }
+    }
     // the streaming one-step kernels do not carry the grain clock: with a grain mechanism the general kernel runs
     const bool stream = chunk == 1 && !ctx->grainOn;
     if (stream && ctx->optKernel != 1) {
