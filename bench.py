@@ -7,9 +7,12 @@ Workload (configs[1] of BASELINE.json): Si electrons, the shipped bulkSimulation
 (acoustic + zero- and first-order intervalley, 1000 energy levels of 1 meV), 300 K, 10 kV/cm along
 -x, dt = 1e-16 s; 1e8 particles PER GPU (weak scaling), generated on the device from the
 reference's initial distributions and advanced out of the initial transient before timing.
-One "step" = one time step of every particle of the shard = ONE launch of the step kernel, which
-also reduces the per-valley observables of that step (the reference's moveParticles(dt) + the three
-getAvg* passes, bulkSimulation.cpp:150-157).  The rate tables are built on the host by the drop-in
+One "step" = one time step of every particle of the shard including the per-valley observables of
+that step (the reference's moveParticles(dt) + the three getAvg* passes, bulkSimulation.cpp:150-157).
+The headline runs the deferred-event kernel (K1c, bulkDeferKernel): SPL = 8 consecutive time steps per
+launch, the particle state crosses HBM once per launch, the per-step observables of all 8 steps are
+delivered.  The one-step-per-launch streaming kernel (K1a, bulkTmaKernel, HBM-bound) is timed next to
+it ("one_step_per_launch").  The rate tables are built on the host by the drop-in
 C++ API (libemchost) -- not by the oracle.
 
 N > 1: one process per GPU (torchrun), the ensemble is block-partitioned, no per-step communication;
@@ -41,6 +44,7 @@ DT = 1e-16
 FIELD = 1e6
 DOPING = 1e23
 SEED = 12345
+SPL = 8  # time steps per launch of the headline kernel (K1c)
 
 
 def workload_config(particles_per_gpu, n_gpus, extra=None):
@@ -49,8 +53,8 @@ def workload_config(particles_per_gpu, n_gpus, extra=None):
                     "intervalley phonons (shipped bulkSimulation set), 300 K, 10 kV/cm, dt=1e-16 s",
         "particles_per_gpu": int(particles_per_gpu),
         "particles_total": int(particles_per_gpu) * n_gpus,
-        "steps_per_launch": 1,
-        "observables": "per-step per-valley <E>, <v.E>, occupation fused into the step kernel",
+        "steps_per_launch": SPL,
+        "observables": "per-step per-valley <E>, <v.E>, occupation of EVERY time step, fused into the step kernel",
         "l2": "no flush needed: state per GPU (%.1f GB) is far larger than L2" % (particles_per_gpu * 68 / 1e9),
         "parallelism": f"particles block-partitioned over {n_gpus} GPU(s), one all-reduce of the observable series",
     }
@@ -287,16 +291,16 @@ def main_ours(args):
         barrier()
         return max_over_ranks(e0.elapsed_time(e1))
 
-    # ---- headline: K steps, one launch per step, inputs resident in HBM -------------------------
+    # ---- headline: K time steps, SPL per launch (K1c), inputs resident in HBM --------------------
     if W > 0:
-        ctx.bulk_step_device(DT, W, 1, warm.data_ptr())
+        ctx.bulk_step_device(DT, W, SPL, warm.data_ptr())
     launches0 = ctx.launch_count
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
 
     def run_steps():
-        ctx.bulk_step_device(DT, K, 1, obs.data_ptr())
+        ctx.bulk_step_device(DT, K, SPL, obs.data_ptr())
         sharding.allreduce_observables(obs)  # the only communication of a bulk run (no-op for one rank)
 
     ms = timed(run_steps)
@@ -308,11 +312,10 @@ def main_ours(args):
     mean_e = float((series[:, 0, 0] / series[:, 0, 2]).mean())
     mean_v = float((series[:, 0, 1] / series[:, 0, 2]).mean())
 
-    # ---- informational: the same K steps with 16 time steps fused per launch -------------------
-    fused_ms = timed(lambda: ctx.bulk_step_device(DT, K, 16, obs.data_ptr()))
-    fused = {"steps_per_launch": 16, "value": n_total * K / (fused_ms * 1e-3), "unit": UNIT,
-             "ms_per_step": fused_ms / K,
-             "note": "state stays in registers for 16 steps: 136 B of HBM traffic per particle per 16 steps"}
+    # ---- the same K steps with ONE time step per launch (K1a, the HBM-bound streaming kernel) ---
+    ctx.bulk_step_device(DT, max(3, W), 1, warm.data_ptr() if W >= 3 else obs.data_ptr())
+    one_ms = timed(lambda: ctx.bulk_step_device(DT, K, 1, obs.data_ptr()))
+    one_value = n_total * K / (one_ms * 1e-3)
 
     # ---- end to end through the C ABI with HOST buffers ----------------------------------------
     e2e = None
@@ -327,8 +330,8 @@ def main_ours(args):
 
         def run_e2e():
             ctx.set_ensemble_from(streams, packed, base_id)  # H2D, 68 B per particle
-            for s in range(K):  # per step: kernel + D2H of that step's observables (24 B per valley)
-                ctx.L.emcgpu_bulk_step(ctx.h, DT, 1, 1, obs_host[s].ctypes.data_as(capi._DP))
+            for s in range(0, K, SPL):  # per launch: SPL time steps + D2H of their observables (24 B per valley and step)
+                ctx.L.emcgpu_bulk_step(ctx.h, DT, min(SPL, K - s), SPL, obs_host[s].ctypes.data_as(capi._DP))
             ctx.get_ensemble_into(streams, packed)  # D2H, 68 B per particle
 
         e2e_ms = timed(run_e2e)
@@ -336,8 +339,8 @@ def main_ours(args):
         e2e = {"value": n_total * K / (e2e_ms * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": 68.0 * n_local / K, "d2h_bytes_per_step": 68.0 * n_local / K + 24.0 * n_v,
                "ms_total": e2e_ms,
-               "what": "emcgpu_set_ensemble from pinned host arrays + K x emcgpu_bulk_step(1 step, host observables) "
-                       "+ emcgpu_get_ensemble to pinned host arrays, all inside the timed region (per rank)"}
+               "what": f"emcgpu_set_ensemble from pinned host arrays + K/{SPL} x emcgpu_bulk_step({SPL} steps, host "
+                       "observables) + emcgpu_get_ensemble to pinned host arrays, all inside the timed region (per rank)"}
         del host, host_packed
 
     # ---- roofline of the step kernel -------------------------------------------------------------
@@ -346,26 +349,42 @@ def main_ours(args):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    n_launch = max(1, launches)
+    launch_ms = ms / n_launch
     achieved = BYTES_PER_PARTICLE_STEP * n_local * K / (ms * 1e-3) / 1e9
-    traffic = None
+    traffic = traffic_one = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         t = json.load(open(tpath))
         if int(t.get("particles", 0)) == n_local:
-            traffic = t["dram_bytes_per_launch"]
-    roofline = {"bound": "hbm", "kernel": "bulkTmaKernel<FAST, PHILOX> (one time step per launch)",
+            traffic = t.get("bulkDeferKernel", {}).get("dram_bytes_per_launch")
+            traffic_one = t.get("bulkTmaKernel", {}).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": f"bulkDeferKernel<FAST, PHILOX> ({SPL} time steps per launch, deferred events)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": BYTES_PER_PARTICLE_STEP * n_local,
-                "avg_launch_ms": ms / K,
-                "note": "per GPU; launch duration = CUDA-event time of the K-step region / K"}
+                "algorithmic_bytes_per_launch": BYTES_PER_PARTICLE_STEP * n_local * K / n_launch,
+                "avg_launch_ms": launch_ms,
+                "dram_gbs_measured": (traffic / (launch_ms * 1e-3) / 1e9) if traffic else None,
+                "note": f"per GPU. algorithmic = 136 B x particle-steps of a launch (SURVEY 8d); frac > 1 because the particle "
+                        f"state crosses HBM once per {SPL} time steps (ncu DRAM traffic per launch in 'traffic', the "
+                        "DRAM rate it implies in 'dram_gbs_measured'): this kernel is bound by the FP64 pipe and instruction "
+                        "issue, not by HBM (profiles/r1_n_defer_v4_spl8.txt). The HBM-bound one-step kernel is in "
+                        "'one_step_per_launch'."}
+    one_achieved = BYTES_PER_PARTICLE_STEP * n_local * K / (one_ms * 1e-3) / 1e9
+    one_step = {"kernel": "bulkTmaKernel<FAST, PHILOX> (one time step per launch, TMA pipeline)", "value": one_value,
+                "unit": UNIT, "ms_per_step": one_ms / K,
+                "roofline": {"bound": "hbm", "achieved": one_achieved, "peak": peak, "unit": "GB/s",
+                             "frac": one_achieved / peak, "traffic": traffic_one,
+                             "algorithmic_bytes_per_launch": BYTES_PER_PARTICLE_STEP * n_local,
+                             "avg_launch_ms": one_ms / K}}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": workload_config(n_local, world, {"settle_steps": args.settle, "math": "FAST (FMA, hoisted constants)",
                                                        "rng": "Philox4x32-10 keyed by global particle id and step"}),
-            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "fused": fused,
+            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "one_step_per_launch": one_step,
             "observables": {"mean_energy_eV": mean_e, "mean_drift_velocity_m_s": mean_v}}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

@@ -36,7 +36,7 @@ namespace emc {
 constexpr int kDeferWarps = EMC_DEFER_WARPS;
 constexpr int kDeferThreads = kDeferWarps * 32;
 constexpr int kDeferChunk = 64;    // particles per warp and pass (2 per lane)
-constexpr int kDeferMaxSteps = 16; // time steps per launch
+constexpr int kDeferMaxSteps = 8;  // time steps per launch
 constexpr int kDeferDense = 16;    // frozen particles per chunk from which the chunk is finished in place
 constexpr int kDeferQueueCap = 32 + kDeferWarps * 32 + 64; // > 31 + kDeferWarps * 32 (see the capacity argument at pushFrozen)
 constexpr int kDeferStreams = 7;   // kx ky kz tau x y z (the energy is recomputed by the first drift)
@@ -44,6 +44,8 @@ constexpr int kDeferStreams = 7;   // kx ky kz tau x y z (the energy is recomput
 struct DeferControl {
   uint64_t tableBar;
   unsigned qTail, qHead;
+  unsigned nextChunk; // chunks of this CTA handed out so far (dynamic claiming)
+  uint32_t packBase;  // shared-memory address of the FastPack table, 0 = the packed fast step does not apply
 };
 struct DeferQueue {
   double f[kDeferStreams][kDeferQueueCap];
@@ -55,8 +57,19 @@ struct DeferQueue {
 constexpr int kDeferQueueWords = (int)((sizeof(DeferControl) + sizeof(DeferQueue) + 3) / 4);
 
 __host__ __device__ inline size_t deferObsOffset(const BulkSmem &L) { return (L.total + 15) & ~size_t(15); }
+// particles that left the main pass of a chunk, staged per warp until the chunk is done (one queue reservation per chunk)
+struct DeferStage {
+  double f[kDeferStreams][kDeferDense];
+  uint32_t w[kDeferDense];
+  uint32_t idx[kDeferDense];
+  uint32_t step[kDeferDense];
+};
+// per-thread observable slots: [nSteps][2 (sum E, sum v.E)][kDeferThreads]
+__host__ __device__ inline size_t deferStageOffset(const BulkSmem &L, int nSteps) {
+  return deferObsOffset(L) + (size_t)nSteps * 2 * kDeferThreads * sizeof(double);
+}
 __host__ __device__ inline size_t deferPackOffset(const BulkSmem &L, int nSteps) {
-  return deferObsOffset(L) + (size_t)nSteps * kDeferThreads * sizeof(double);
+  return deferStageOffset(L, nSteps) + (size_t)kDeferWarps * sizeof(DeferStage);
 }
 __host__ __device__ inline size_t deferSmemBytes(const BulkSmem &L, int nSteps, int nValleys) {
   return deferPackOffset(L, nSteps) + (size_t)nValleys * EMCGPU_MAX_SUBVALLEYS * 96;
@@ -113,25 +126,100 @@ __device__ __forceinline__ void pushFrozen(DeferControl *ctl, DeferQueue *Q, boo
   __syncwarp();
 }
 
-__device__ __forceinline__ void addObsLane(double *sObs, int obsPerStep, bool single, int s, int valley, double e,
-                                           double vd) {
-  double *o = sObs + s * obsPerStep + 3 * valley;
-  atomicAdd(o + 0, e);
-  atomicAdd(o + 1, vd);
-  if (!single) atomicAdd(o + 2, 1.0);
+// Constants of the full-dt flight per (valley, sub-valley) for the branch-free main pass (valleys whose rotations are
+// signed permutations: M is diagonal), packed for 16-byte shared-memory loads.
+struct FastPack {
+  double dk[3], md[3], c[3], fE, c2a, pad;
+};
+static_assert(sizeof(FastPack) == 96, "FastPack is read with 16-byte loads");
+
+__device__ __forceinline__ void ldsPair(uint32_t addr, double &a, double &b) {
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
+
+// fastStep (emc_device.cuh) operation for operation, constants from a FastPack in shared memory; no branches
+struct Lite {
+  double kx, ky, kz, tau, x, y, z, e;
+};
+// periodic wrap (basicBulkParticleHandler.hpp:600-613) as two compares and two predicated adds
+__device__ __forceinline__ double wrapFast(double x, double b) {
+  asm("{\n\t.reg .pred p, q;\n\tsetp.lt.f64 p, %0, 0d0000000000000000;\n\tsetp.gt.f64 q, %0, %1;\n\t"
+      "@p add.rn.f64 %0, %0, %1;\n\t@q sub.rn.f64 %0, %0, %1;\n\t}"
+      : "+d"(x)
+      : "d"(b));
+  return x;
+}
+__device__ __forceinline__ double fastStepPacked(uint32_t fp, double dt, double bx, double by, double bz, Lite &q) {
+  double dk0, dk1, dk2, m0, m1, m2, c0, c1, c2, fE, c2a, pad;
+  ldsPair(fp, dk0, dk1);
+  ldsPair(fp + 16, dk2, m0);
+  ldsPair(fp + 32, m1, m2);
+  ldsPair(fp + 48, c0, c1);
+  ldsPair(fp + 64, c2, fE);
+  ldsPair(fp + 80, c2a, pad);
+  const double nx = q.kx + dk0, ny = q.ky + dk1, nz = q.kz + dk2;
+  const double sq = fma(nz, nz, fma(ny, ny, nx * nx));
+  const double g = fE * sq;
+  const double x = fma(c2a, sq, 1.0);
+  const double r = rsqrtNormal(x); // 1/S
+  const double d = fma(x, r, 1.0); // 1 + S
+  const double y = rcpNormal(d);
+  double e = g * y;
+  e = fma(fma(-d, e, g), y, e);
+  const double w = dt * r;
+  const double sx = (nx + q.kx) * w, sy = (ny + q.ky) * w, sz = (nz + q.kz) * w;
+  const double px = q.x + m0 * sx, py = q.y + m1 * sy, pz = q.z + m2 * sz;
+  q.x = wrapFast(px, bx);
+  q.y = wrapFast(py, by);
+  q.z = wrapFast(pz, bz);
+  q.kx = nx;
+  q.ky = ny;
+  q.kz = nz;
+  q.e = e;
+  q.tau -= dt;
+  return fma(c2, nz, fma(c1, ny, c0 * nx)) * r;
+}
+
+__device__ __forceinline__ Particle toParticle(const Lite &q, uint32_t w) {
+  Particle p;
+  p.k = Vec3{q.kx, q.ky, q.kz};
+  p.energy = q.e;
+  p.tau = q.tau;
+  p.pos = Vec3{q.x, q.y, q.z};
+  p.valley = w & 0xffu;
+  p.sub = (w >> 8) & 0xffu;
+  p.region = w >> 16;
+  return p;
+}
+
+// One particle-step of an event lane into the per-step sums: one valley -> the thread's own slots (no atomics);
+// several valleys -> atomics on the warp's copy of the per-valley sums.
+__device__ __forceinline__ void addObsLane(double *wObs, double *myObs, int obsPerStep, bool single, int s, int valley,
+                                           double e, double vd) {
+  if (single) {
+    myObs[(2 * s) * kDeferThreads] += e;
+    myObs[(2 * s + 1) * kDeferThreads] += vd;
+  } else {
+    double *o = wObs + s * obsPerStep + 3 * valley;
+    atomicAdd(o + 0, e);
+    atomicAdd(o + 1, vd);
+    atomicAdd(o + 2, 1.0);
+  }
 }
 
 // Advance the lane's particle from step s (relative to P.step0) to the end of the launch or, with `repush`, to its
 // next event, where it is queued again.  Warp-collective; lanes may be at different steps.
 template <bool EXACT, int RNG_MODE>
 __device__ __forceinline__ void runEvents(const CtaState &C, const BulkParams &P, DeferControl *ctl, DeferQueue *Q,
-                                          Particle &p, uint32_t idx, int s, bool active, bool repush) {
+                                          double *obsT, Particle &p, uint32_t idx, int s, bool active, bool repush) {
   const int nV = C.model->nValleys;
   const int obsPerStep = nV * 3;
   const bool single = nV == 1;
   const int nSteps = P.nSteps;
   const double dt = P.dt;
   double *const wObs = C.obs + (threadIdx.x >> 5) * nSteps * obsPerStep; // the warp's own copy of the per-step sums
+  double *const myObs = obsT + threadIdx.x;
+  const uint32_t packBase = ctl->packBase;
   for (;;) {
     if (active) {
       Rng rng;
@@ -146,12 +234,27 @@ __device__ __forceinline__ void runEvents(const CtaState &C, const BulkParams &P
       attachReplay<RNG_MODE>(P, idx, rng);
       double vd = bulkParticleStep<EXACT, RNG_MODE>(C, P, p, rng, P.idBase + idx, P.step0 + s);
       if constexpr (RNG_MODE == RNG_REPLAY) storeCursor(P, idx, rng);
-      addObsLane(wObs, obsPerStep, single, s, p.valley, p.energy, vd);
+      addObsLane(wObs, myObs, obsPerStep, single, s, p.valley, p.energy, vd);
       s++;
-      while (s < nSteps && p.tau >= dt) {
-        vd = fullDtStep<EXACT>(C, P, p);
-        addObsLane(wObs, obsPerStep, single, s, p.valley, p.energy, vd);
-        s++;
+      if (!EXACT && packBase) {
+        // same arithmetic as the main pass (fastStepPacked == fastStep operation for operation)
+        const uint32_t fp = packBase + (uint32_t)sizeof(FastPack) * (p.valley * EMCGPU_MAX_SUBVALLEYS + p.sub);
+        Lite q{p.k.x, p.k.y, p.k.z, p.tau, p.pos.x, p.pos.y, p.pos.z, p.energy};
+        while (s < nSteps && q.tau >= dt) {
+          vd = fastStepPacked(fp, dt, P.box.x, P.box.y, P.box.z, q);
+          addObsLane(wObs, myObs, obsPerStep, single, s, p.valley, q.e, vd);
+          s++;
+        }
+        p.k = Vec3{q.kx, q.ky, q.kz};
+        p.tau = q.tau;
+        p.pos = Vec3{q.x, q.y, q.z};
+        p.energy = q.e;
+      } else {
+        while (s < nSteps && p.tau >= dt) {
+          vd = fullDtStep<EXACT>(C, P, p);
+          addObsLane(wObs, myObs, obsPerStep, single, s, p.valley, p.energy, vd);
+          s++;
+        }
       }
       if (s == nSteps) {
         storeParticleState(P, idx, p);
@@ -170,7 +273,7 @@ __device__ __forceinline__ void runEvents(const CtaState &C, const BulkParams &P
 // Up to 32 queued particles, one per lane.
 template <bool EXACT, int RNG_MODE>
 __device__ __noinline__ void eventBatch(const CtaState &C, const BulkParams &P, DeferControl *ctl, DeferQueue *Q,
-                                        unsigned head, int count, bool repush) {
+                                        double *obsT, unsigned head, int count, bool repush) {
   const int lane = threadIdx.x & 31;
   const bool active = lane < count;
   Particle p;
@@ -200,14 +303,14 @@ __device__ __noinline__ void eventBatch(const CtaState &C, const BulkParams &P, 
     p.region = w >> 16;
   }
   __syncwarp();
-  runEvents<EXACT, RNG_MODE>(C, P, ctl, Q, p, idx, s, active, repush);
+  runEvents<EXACT, RNG_MODE>(C, P, ctl, Q, obsT, p, idx, s, active, repush);
 }
 
 // The lane's particle idx, whose state is in global memory, from step s to the end of the launch, in place (rare paths:
 // chunks in which most particles scatter, the particles behind the last whole chunk).  Only scalars cross the call.
 template <bool EXACT, int RNG_MODE>
 __device__ __noinline__ void runFromGlobal(const CtaState &C, const BulkParams &P, DeferControl *ctl, DeferQueue *Q,
-                                           uint32_t idx, int s, bool active) {
+                                           double *obsT, uint32_t idx, int s, bool active) {
   Particle p;
   Rng rng;
   p.k = Vec3{0.0, 0.0, 0.0};
@@ -215,73 +318,51 @@ __device__ __noinline__ void runFromGlobal(const CtaState &C, const BulkParams &
   p.energy = p.tau = 0.0;
   p.valley = p.sub = p.region = 0;
   if (active) loadParticle(P, idx, p, rng);
-  runEvents<EXACT, RNG_MODE>(C, P, ctl, Q, p, idx, s, active, false);
+  runEvents<EXACT, RNG_MODE>(C, P, ctl, Q, obsT, p, idx, s, active, false);
 }
 
-// Constants of the full-dt flight per (valley, sub-valley) for the branch-free main pass (valleys whose rotations are
-// signed permutations: M is diagonal), packed for 16-byte shared-memory loads.
-struct FastPack {
-  double dk[3], md[3], c[3], fE, c2a, pad;
-};
-static_assert(sizeof(FastPack) == 96, "FastPack is read with 16-byte loads");
-
-__device__ __forceinline__ void ldsPair(uint32_t addr, double &a, double &b) {
-  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+__device__ __forceinline__ void stageParticle(DeferStage *st, int slot, const Lite &q, uint32_t w, uint32_t idx, int step) {
+  st->f[0][slot] = q.kx;
+  st->f[1][slot] = q.ky;
+  st->f[2][slot] = q.kz;
+  st->f[3][slot] = q.tau;
+  st->f[4][slot] = q.x;
+  st->f[5][slot] = q.y;
+  st->f[6][slot] = q.z;
+  st->w[slot] = w;
+  st->idx[slot] = idx;
+  st->step[slot] = (uint32_t)step;
 }
-
-// fastStep (emc_device.cuh) operation for operation, constants from a FastPack in shared memory; no branches
-struct Lite {
-  double kx, ky, kz, tau, x, y, z, e;
-};
-__device__ __forceinline__ double fastStepPacked(uint32_t fp, double dt, double bx, double by, double bz, Lite &q) {
-  double dk0, dk1, dk2, m0, m1, m2, c0, c1, c2, fE, c2a, pad;
-  ldsPair(fp, dk0, dk1);
-  ldsPair(fp + 16, dk2, m0);
-  ldsPair(fp + 32, m1, m2);
-  ldsPair(fp + 48, c0, c1);
-  ldsPair(fp + 64, c2, fE);
-  ldsPair(fp + 80, c2a, pad);
-  const double nx = q.kx + dk0, ny = q.ky + dk1, nz = q.kz + dk2;
-  const double sq = fma(nz, nz, fma(ny, ny, nx * nx));
-  const double g = fE * sq;
-  const double x = fma(c2a, sq, 1.0);
-  const double r = rsqrtNormal(x); // 1/S
-  const double d = fma(x, r, 1.0); // 1 + S
-  const double y = rcpNormal(d);
-  double e = g * y;
-  e = fma(fma(-d, e, g), y, e);
-  const double w = dt * r;
-  const double sx = (nx + q.kx) * w, sy = (ny + q.ky) * w, sz = (nz + q.kz) * w;
-  double px = q.x + m0 * sx, py = q.y + m1 * sy, pz = q.z + m2 * sz;
-  px += px < 0.0 ? bx : (px > bx ? -bx : 0.0);
-  py += py < 0.0 ? by : (py > by ? -by : 0.0);
-  pz += pz < 0.0 ? bz : (pz > bz ? -bz : 0.0);
-  q.x = px;
-  q.y = py;
-  q.z = pz;
-  q.kx = nx;
-  q.ky = ny;
-  q.kz = nz;
-  q.e = e;
-  q.tau -= dt;
-  return fma(c2, nz, fma(c1, ny, c0 * nx)) * r;
-}
-
-__device__ __forceinline__ Particle toParticle(const Lite &q, uint32_t w) {
-  Particle p;
-  p.k = Vec3{q.kx, q.ky, q.kz};
-  p.energy = q.e;
-  p.tau = q.tau;
-  p.pos = Vec3{q.x, q.y, q.z};
-  p.valley = w & 0xffu;
-  p.sub = (w >> 8) & 0xffu;
-  p.region = w >> 16;
-  return p;
+// the warp's n (< 32) staged particles into the CTA queue: one reservation, lane i moves entry i (warp-collective;
+// capacity argument as at pushFrozen)
+__device__ __forceinline__ void flushStage(DeferControl *ctl, DeferQueue *Q, const DeferStage *st, int n) {
+  if (n == 0) return;
+  __syncwarp();
+  const int lane = threadIdx.x & 31;
+  unsigned base = 0;
+  if (lane == 0) base = atomicAdd(&ctl->qTail, (unsigned)n);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (lane < n) {
+    const unsigned pos = base + lane;
+    const unsigned slot = pos % kDeferQueueCap;
+    const uint32_t epoch = pos / kDeferQueueCap + 1;
+    while (*reinterpret_cast<volatile uint32_t *>(&Q->flag[slot]) != 2 * (epoch - 1)) { // previous tenant read
+    }
+#pragma unroll
+    for (int c = 0; c < kDeferStreams; c++) Q->f[c][slot] = st->f[c][lane];
+    Q->w[slot] = st->w[lane];
+    Q->idx[slot] = st->idx[lane];
+    Q->step[slot] = st->step[lane];
+    __threadfence_block();
+    *reinterpret_cast<volatile uint32_t *>(&Q->flag[slot]) = 2 * epoch - 1;
+  }
+  __syncwarp();
 }
 
 // serve full batches of the event queue (warp-collective)
 template <bool EXACT, int RNG_MODE>
-__device__ __forceinline__ void serveBatches(const CtaState &C, const BulkParams &P, DeferControl *ctl, DeferQueue *Q) {
+__device__ __forceinline__ void serveBatches(const CtaState &C, const BulkParams &P, DeferControl *ctl, DeferQueue *Q,
+                                             double *obsT) {
   const int lane = threadIdx.x & 31;
   for (;;) {
     unsigned h = 0;
@@ -295,7 +376,7 @@ __device__ __forceinline__ void serveBatches(const CtaState &C, const BulkParams
     if (got == 0) break;
     if (got == 2) continue; // lost the race, look again
     h = __shfl_sync(0xffffffffu, h, 0);
-    eventBatch<EXACT, RNG_MODE>(C, P, ctl, Q, h, 32, true);
+    eventBatch<EXACT, RNG_MODE>(C, P, ctl, Q, obsT, h, 32, true);
   }
 }
 
@@ -309,15 +390,18 @@ __global__ void __launch_bounds__(kDeferThreads, 1) bulkDeferKernel(const __grid
                    kDeferQueueWords);
   DeferControl *ctl = reinterpret_cast<DeferControl *>(smemRaw + L.queue);
   DeferQueue *Q = reinterpret_cast<DeferQueue *>(smemRaw + L.queue + sizeof(DeferControl));
-  double *obsT = reinterpret_cast<double *>(smemRaw + deferObsOffset(L)); // [nSteps][kDeferThreads]
+  double *obsT = reinterpret_cast<double *>(smemRaw + deferObsOffset(L)); // [nSteps][2][kDeferThreads]
+  DeferStage *stage = reinterpret_cast<DeferStage *>(smemRaw + deferStageOffset(L, nSteps)) + (threadIdx.x >> 5);
   FastPack *packs = reinterpret_cast<FastPack *>(smemRaw + deferPackOffset(L, nSteps)); // [nV][EMCGPU_MAX_SUBVALLEYS]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     ctl->qTail = 0;
     ctl->qHead = 0;
+    ctl->nextChunk = 0;
+    ctl->packBase = 0;
   }
   for (int i = tid; i < kDeferQueueCap; i += kDeferThreads) Q->flag[i] = 0;
-  for (int s = 0; s < nSteps; s++) obsT[s * kDeferThreads + tid] = 0.0;
+  for (int s = 0; s < 2 * nSteps; s++) obsT[s * kDeferThreads + tid] = 0.0;
   const CtaState C = stageCta(P, smemRaw, &ctl->tableBar, kDeferWarps * nSteps * obsPerStep, kDeferQueueWords); // __syncthreads inside
   const bool single = nV == 1;
   bool allDiag = true;
@@ -336,17 +420,39 @@ __global__ void __launch_bounds__(kDeferThreads, 1) bulkDeferKernel(const __grid
     fp.pad = 0.0;
     packs[i] = fp;
   }
+  if (tid == 0 && !EXACT && allDiag) ctl->packBase = smemAddr(packs);
   __syncthreads();
   const double dt = P.dt;
-  const bool lower = lane < 16;
   const int64_t nChunks = P.n / kDeferChunk;
+  // chunks blockIdx.x + k * gridDim.x belong to this CTA; its warps claim them one by one and prefetch the next one
+  auto claimChunk = [&]() -> int64_t {
+    unsigned k = 0;
+    if (lane == 0) k = atomicAdd(&ctl->nextChunk, 1u);
+    k = __shfl_sync(0xffffffffu, k, 0);
+    return (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
+  };
+  auto prefetchChunk = [&](int64_t ch) {
+    if (ch >= nChunks) return;
+    const int64_t i0 = ch * kDeferChunk + 2 * lane;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.stream[EMCGPU_KX] + i0));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.stream[EMCGPU_KY] + i0));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.stream[EMCGPU_KZ] + i0));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.stream[EMCGPU_TAU] + i0));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.stream[EMCGPU_X] + i0));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.stream[EMCGPU_Y] + i0));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.stream[EMCGPU_Z] + i0));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.packed + i0));
+  };
 
   if (!EXACT && single && allDiag) {
     // ================= branch-free main pass (the production case) =================
     const uint32_t packBase = smemAddr(packs);
     const uint32_t obsAddr = smemAddr(obsT) + tid * 8;
     const double bx = P.box.x, by = P.box.y, bz = P.box.z;
-    for (int64_t ch = (int64_t)blockIdx.x * kDeferWarps + warp; ch < nChunks; ch += (int64_t)gridDim.x * kDeferWarps) {
+    const unsigned ltMask = (1u << lane) - 1u;
+    for (int64_t ch = claimChunk(), chNext; ch < nChunks; ch = chNext) {
+      chNext = claimChunk();
+      prefetchChunk(chNext);
       const int64_t i0 = ch * kDeferChunk + 2 * lane;
       Lite a, b;
       uint32_t wa, wb;
@@ -380,8 +486,8 @@ __global__ void __launch_bounds__(kDeferThreads, 1) bulkDeferKernel(const __grid
             denseAt = s;
             break;
           }
-          pushFrozen(ctl, Q, evA, toParticle(a, wa), (uint32_t)i0, s);
-          pushFrozen(ctl, Q, evB, toParticle(b, wb), (uint32_t)(i0 + 1), s);
+          if (evA) stageParticle(stage, pushed + __popc(mA & ltMask), a, wa, (uint32_t)i0, s);
+          if (evB) stageParticle(stage, pushed + __popc(mA) + __popc(mB & ltMask), b, wb, (uint32_t)(i0 + 1), s);
           pushed += nNew;
           liveA = liveA && !evA;
           liveB = liveB && !evB;
@@ -392,13 +498,14 @@ __global__ void __launch_bounds__(kDeferThreads, 1) bulkDeferKernel(const __grid
         const double vB = fastStepPacked(fpb, dt, bx, by, bz, b);
         const double sumE = (liveA ? a.e : 0.0) + (liveB ? b.e : 0.0);
         const double sumV = (liveA ? vA : 0.0) + (liveB ? vB : 0.0);
-        // lanes l and l^16 share their sums: the lower lane keeps the energies, the upper one the velocities
-        const double got = __shfl_xor_sync(0xffffffffu, lower ? sumV : sumE, 16);
-        const uint32_t oa = obsAddr + (uint32_t)s * (kDeferThreads * 8);
-        double acc;
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(acc) : "r"(oa));
-        acc += (lower ? sumE : sumV) + got;
-        asm volatile("st.shared.f64 [%0], %1;" ::"r"(oa), "d"(acc) : "memory");
+        const uint32_t oa = obsAddr + (uint32_t)s * (2 * kDeferThreads * 8);
+        double accE, accV;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(accE) : "r"(oa));
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(accV) : "r"(oa + kDeferThreads * 8));
+        accE += sumE;
+        accV += sumV;
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(oa), "d"(accE) : "memory");
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(oa + kDeferThreads * 8), "d"(accV) : "memory");
       }
       if (liveA && liveB) {
         __stcs(reinterpret_cast<double2 *>(P.stream[EMCGPU_KX] + i0), make_double2(a.kx, b.kx));
@@ -413,16 +520,19 @@ __global__ void __launch_bounds__(kDeferThreads, 1) bulkDeferKernel(const __grid
         if (liveA) storeParticleState(P, i0, toParticle(a, wa));
         if (liveB) storeParticleState(P, i0 + 1, toParticle(b, wb));
       }
+      flushStage(ctl, Q, stage, pushed);
       if (denseAt >= 0) { // the live particles continue from their (just stored) state at step denseAt
         __syncwarp();
-        runFromGlobal<EXACT, RNG_MODE>(C, P, ctl, Q, (uint32_t)i0, denseAt, liveA);
-        runFromGlobal<EXACT, RNG_MODE>(C, P, ctl, Q, (uint32_t)(i0 + 1), denseAt, liveB);
+        runFromGlobal<EXACT, RNG_MODE>(C, P, ctl, Q, obsT, (uint32_t)i0, denseAt, liveA);
+        runFromGlobal<EXACT, RNG_MODE>(C, P, ctl, Q, obsT, (uint32_t)(i0 + 1), denseAt, liveB);
       }
-      serveBatches<EXACT, RNG_MODE>(C, P, ctl, Q);
+      serveBatches<EXACT, RNG_MODE>(C, P, ctl, Q, obsT);
     }
   } else {
     // ================= general main pass (EXACT arithmetic, several valleys, general rotations) =================
-    for (int64_t ch = (int64_t)blockIdx.x * kDeferWarps + warp; ch < nChunks; ch += (int64_t)gridDim.x * kDeferWarps) {
+    for (int64_t ch = claimChunk(), chNext; ch < nChunks; ch = chNext) {
+      chNext = claimChunk();
+      prefetchChunk(chNext);
       const int64_t i0 = ch * kDeferChunk + 2 * lane;
       Particle p[2];
       int fz[2] = {-1, -1};
@@ -467,9 +577,8 @@ __global__ void __launch_bounds__(kDeferThreads, 1) bulkDeferKernel(const __grid
           }
         }
         if (single) {
-          const double sumE = e[0] + e[1], sumV = vd[0] + vd[1];
-          const double got = __shfl_xor_sync(0xffffffffu, lower ? sumV : sumE, 16);
-          obsT[s * kDeferThreads + tid] += (lower ? sumE : sumV) + got;
+          obsT[(2 * s) * kDeferThreads + tid] += e[0] + e[1];
+          obsT[(2 * s + 1) * kDeferThreads + tid] += vd[0] + vd[1];
         } else {
 #pragma unroll
           for (int j = 0; j < 2; j++)
@@ -499,13 +608,13 @@ __global__ void __launch_bounds__(kDeferThreads, 1) bulkDeferKernel(const __grid
         if (fz[0] >= 0) storeParticleState(P, i0, p[0]);
         if (fz[1] >= 0) storeParticleState(P, i0 + 1, p[1]);
         __syncwarp();
-        runFromGlobal<EXACT, RNG_MODE>(C, P, ctl, Q, (uint32_t)i0, fz[0] >= 0 ? fz[0] : 0, fz[0] >= 0);
-        runFromGlobal<EXACT, RNG_MODE>(C, P, ctl, Q, (uint32_t)(i0 + 1), fz[1] >= 0 ? fz[1] : 0, fz[1] >= 0);
+        runFromGlobal<EXACT, RNG_MODE>(C, P, ctl, Q, obsT, (uint32_t)i0, fz[0] >= 0 ? fz[0] : 0, fz[0] >= 0);
+        runFromGlobal<EXACT, RNG_MODE>(C, P, ctl, Q, obsT, (uint32_t)(i0 + 1), fz[1] >= 0 ? fz[1] : 0, fz[1] >= 0);
       } else if (nFz > 0) {
         pushFrozen(ctl, Q, fz[0] >= 0, p[0], (uint32_t)i0, fz[0]);
         pushFrozen(ctl, Q, fz[1] >= 0, p[1], (uint32_t)(i0 + 1), fz[1]);
       }
-      serveBatches<EXACT, RNG_MODE>(C, P, ctl, Q);
+      serveBatches<EXACT, RNG_MODE>(C, P, ctl, Q, obsT);
     }
   }
   // every push of the main phase is complete once all warps are here; what is left is finished in place
@@ -524,23 +633,21 @@ __global__ void __launch_bounds__(kDeferThreads, 1) bulkDeferKernel(const __grid
     take = __shfl_sync(0xffffffffu, take, 0);
     if (take == 0) break;
     h = __shfl_sync(0xffffffffu, h, 0);
-    eventBatch<EXACT, RNG_MODE>(C, P, ctl, Q, h, take, false);
+    eventBatch<EXACT, RNG_MODE>(C, P, ctl, Q, obsT, h, take, false);
   }
   // the n % kDeferChunk particles behind the last whole chunk
   if (blockIdx.x == 0 && warp < kDeferChunk / 32) {
     const int64_t i = nChunks * kDeferChunk + tid;
-    runFromGlobal<EXACT, RNG_MODE>(C, P, ctl, Q, (uint32_t)i, 0, i < P.n);
+    runFromGlobal<EXACT, RNG_MODE>(C, P, ctl, Q, obsT, (uint32_t)i, 0, i < P.n);
   }
   __syncthreads();
   // ---- per-step sums of the CTA -> global ----
   if (single) {
-    for (int s = warp; s < nSteps; s += kDeferWarps) {
+    for (int r = warp; r < 2 * nSteps; r += kDeferWarps) { // row r = 2 * step + (0: sum E, 1: sum v.E)
       double a = 0.0;
-      for (int k = 0; k < kDeferWarps; k++) a += obsT[s * kDeferThreads + 32 * k + lane];
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      if (lane == 0) atomicAdd(C.obs + s * 3 + 0, a);
-      if (lane == 16) atomicAdd(C.obs + s * 3 + 1, a);
+      for (int k = 0; k < kDeferWarps; k++) a += obsT[r * kDeferThreads + 32 * k + lane];
+      a = warpSum(a);
+      if (lane == 0) atomicAdd(C.obs + (r >> 1) * 3 + (r & 1), a);
     }
     __syncthreads();
   }
