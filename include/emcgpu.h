@@ -166,7 +166,10 @@ int emcgpu_synchronize(emcgpu_ctx *ctx);
  * "sor_order" = 0: the reference's lexicographic Gauss-Seidel order (default; iterates and sweep counts
  * are the reference's), 1: red-black ordering (same equation and stopping rule, parallel, converges to
  * the same potential within the solver's accuracy); "sor_kernel" = 1 forces the general hyperplane
- * form of the lexicographic solver (no effect on results) */
+ * form of the lexicographic solver (no effect on results); "multi_kernel": kernel of emcgpu_bulk_step*
+ * with stepsPerLaunch > 1 -- 0 (default): deferred scattering events (up to 8 steps per launch) for
+ * ensembles that fill the GPU, events in place otherwise; 1: always in place; 2: always deferred
+ * (no effect on results: the trajectories are bit-identical) */
 int emcgpu_set_option(emcgpu_ctx *ctx, const char *name, int64_t value);
 
 /* ---- physics model (built on the host by the reference-compatible API) - */
