@@ -72,7 +72,7 @@ __host__ __device__ inline size_t deferPackOffset(const BulkSmem &L, int nSteps)
   return deferStageOffset(L, nSteps) + (size_t)kDeferWarps * sizeof(DeferStage);
 }
 __host__ __device__ inline size_t deferSmemBytes(const BulkSmem &L, int nSteps, int nValleys) {
-  return deferPackOffset(L, nSteps) + (size_t)nValleys * EMCGPU_MAX_SUBVALLEYS * 96;
+  return deferPackOffset(L, nSteps) + ((size_t)nValleys * EMCGPU_MAX_SUBVALLEYS + 1) * 96; // + the all-zero pack
 }
 
 // A whole time step of a particle whose flight outlasts it (tau >= dt): drift(dt), periodic wrap, tau -= dt
@@ -420,6 +420,12 @@ __global__ void __launch_bounds__(kDeferThreads, 1) bulkDeferKernel(const __grid
     fp.pad = 0.0;
     packs[i] = fp;
   }
+  if (tid == 0) { // a particle that left the pass computes on this: energy and velocity contributions come out as 0
+    FastPack z;
+    for (int a = 0; a < 3; a++) z.dk[a] = z.md[a] = z.c[a] = 0.0;
+    z.fE = z.c2a = z.pad = 0.0;
+    packs[nV * EMCGPU_MAX_SUBVALLEYS] = z;
+  }
   if (tid == 0 && !EXACT && allDiag) ctl->packBase = smemAddr(packs);
   __syncthreads();
   const double dt = P.dt;
@@ -450,6 +456,7 @@ __global__ void __launch_bounds__(kDeferThreads, 1) bulkDeferKernel(const __grid
     const uint32_t obsAddr = smemAddr(obsT) + tid * 8;
     const double bx = P.box.x, by = P.box.y, bz = P.box.z;
     const unsigned ltMask = (1u << lane) - 1u;
+    const uint32_t nullPack = packBase + (uint32_t)sizeof(FastPack) * (nV * EMCGPU_MAX_SUBVALLEYS);
     for (int64_t ch = claimChunk(), chNext; ch < nChunks; ch = chNext) {
       chNext = claimChunk();
       prefetchChunk(chNext);
@@ -470,8 +477,8 @@ __global__ void __launch_bounds__(kDeferThreads, 1) bulkDeferKernel(const __grid
         wa = w.x;
         wb = w.y;
       }
-      const uint32_t fpa = packBase + (uint32_t)sizeof(FastPack) * ((wa & 0xffu) * EMCGPU_MAX_SUBVALLEYS + ((wa >> 8) & 0xffu));
-      const uint32_t fpb = packBase + (uint32_t)sizeof(FastPack) * ((wb & 0xffu) * EMCGPU_MAX_SUBVALLEYS + ((wb >> 8) & 0xffu));
+      uint32_t fpa = packBase + (uint32_t)sizeof(FastPack) * ((wa & 0xffu) * EMCGPU_MAX_SUBVALLEYS + ((wa >> 8) & 0xffu));
+      uint32_t fpb = packBase + (uint32_t)sizeof(FastPack) * ((wb & 0xffu) * EMCGPU_MAX_SUBVALLEYS + ((wb >> 8) & 0xffu));
       bool liveA = true, liveB = true;
       int pushed = 0, denseAt = -1; // warp-uniform
 #pragma unroll 1
@@ -486,8 +493,16 @@ __global__ void __launch_bounds__(kDeferThreads, 1) bulkDeferKernel(const __grid
             denseAt = s;
             break;
           }
-          if (evA) stageParticle(stage, pushed + __popc(mA & ltMask), a, wa, (uint32_t)i0, s);
-          if (evB) stageParticle(stage, pushed + __popc(mA) + __popc(mB & ltMask), b, wb, (uint32_t)(i0 + 1), s);
+          if (evA) {
+            stageParticle(stage, pushed + __popc(mA & ltMask), a, wa, (uint32_t)i0, s);
+            a.kx = a.ky = a.kz = 0.0; // from here on the lane's slot contributes exact zeros (all-zero pack)
+            fpa = nullPack;
+          }
+          if (evB) {
+            stageParticle(stage, pushed + __popc(mA) + __popc(mB & ltMask), b, wb, (uint32_t)(i0 + 1), s);
+            b.kx = b.ky = b.kz = 0.0;
+            fpb = nullPack;
+          }
           pushed += nNew;
           liveA = liveA && !evA;
           liveB = liveB && !evB;
@@ -496,8 +511,7 @@ __global__ void __launch_bounds__(kDeferThreads, 1) bulkDeferKernel(const __grid
         // both particles move (the ones that left compute on dead values)
         const double vA = fastStepPacked(fpa, dt, bx, by, bz, a);
         const double vB = fastStepPacked(fpb, dt, bx, by, bz, b);
-        const double sumE = (liveA ? a.e : 0.0) + (liveB ? b.e : 0.0);
-        const double sumV = (liveA ? vA : 0.0) + (liveB ? vB : 0.0);
+        const double sumE = a.e + b.e, sumV = vA + vB; // particles that left contribute 0
         const uint32_t oa = obsAddr + (uint32_t)s * (2 * kDeferThreads * 8);
         double accE, accV;
         asm volatile("ld.shared.f64 %0, [%1];" : "=d"(accE) : "r"(oa));

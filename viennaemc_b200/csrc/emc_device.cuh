@@ -477,26 +477,26 @@ __device__ __forceinline__ void sampleFinalState(const DevModel &model, const De
                                                  Rng &rng, const BathView &baths) {
   using A = Arith<EXACT>;
   switch (mech.sampler) {
-  case EMCGPU_SAMPLER_ISOTROPIC_ELASTIC: {
-    // emcAcousticScatterMechanism.hpp:70-72; g++ evaluates the two dist(rng)
-    // arguments right to left: first draw = cos(theta) variate
-    const double nrm = A::sqrt(sqNorm<EXACT>(p.k));
+  case EMCGPU_SAMPLER_ISOTROPIC_ELASTIC:
+  case EMCGPU_SAMPLER_INTERVALLEY: {
+    // one body for both so that a warp with lanes of either kind walks the common tail (two draws, sincos,
+    // sqrt) once.  Elastic (emcAcousticScatterMechanism.hpp:70-72): |k| kept.  Intervalley
+    // (emcZeroOrderInterValleyScatterMechanism.hpp:119-129 / :262-272, emcFirstOrderInterValleyScatterMechanism.hpp
+    // :121-131 / :269-279): final sub-valley drawn first, energy shifted, |k| of the new energy.
+    double nrm;
+    if (mech.sampler == EMCGPU_SAMPLER_INTERVALLEY) {
+      const uint64_t raw = rng.raw<RNG_MODE>();
+      p.sub = mech.finalSub[p.sub][raw % (uint64_t)mech.nFinal];
+      p.valley = mech.finalValley;
+      p.energy = A::add(p.energy, mech.param[0]);
+      nrm = normWaveVec<EXACT>(model.valleys[p.valley], p.energy);
+    } else {
+      nrm = A::sqrt(sqNorm<EXACT>(p.k));
+    }
+    // g++ evaluates the two dist(rng) arguments right to left: first draw = cos(theta) variate
     const double r2 = uniform01(rng.raw<RNG_MODE>());
     const double r1 = uniform01(rng.raw<RNG_MODE>());
     p.k = randomDirection<EXACT>(nrm, r1, r2);
-    break;
-  }
-  case EMCGPU_SAMPLER_INTERVALLEY: {
-    // emcZeroOrderInterValleyScatterMechanism.hpp:119-129 / :262-272,
-    // emcFirstOrderInterValleyScatterMechanism.hpp:121-131 / :269-279
-    const uint64_t raw = rng.raw<RNG_MODE>();
-    p.sub = mech.finalSub[p.sub][raw % (uint64_t)mech.nFinal];
-    p.valley = mech.finalValley;
-    p.energy = A::add(p.energy, mech.param[0]);
-    const double kn = normWaveVec<EXACT>(model.valleys[p.valley], p.energy);
-    const double r2 = uniform01(rng.raw<RNG_MODE>());
-    const double r1 = uniform01(rng.raw<RNG_MODE>());
-    p.k = randomDirection<EXACT>(kn, r1, r2);
     break;
   }
   case EMCGPU_SAMPLER_COULOMB: {
