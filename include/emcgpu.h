@@ -169,7 +169,8 @@ int emcgpu_synchronize(emcgpu_ctx *ctx);
  * form of the lexicographic solver (no effect on results); "multi_kernel": kernel of emcgpu_bulk_step*
  * with stepsPerLaunch > 1 -- 0 (default): deferred scattering events (up to 8 steps per launch) for
  * ensembles that fill the GPU, events in place otherwise; 1: always in place; 2: always deferred
- * (no effect on results: the trajectories are bit-identical) */
+ * (no effect on results: the trajectories are bit-identical); "defer_tables_smem" = 1: the deferred-event kernel
+ * stages the rate tables in shared memory instead of reading them through L1/L2 (slower, no effect on results) */
 int emcgpu_set_option(emcgpu_ctx *ctx, const char *name, int64_t value);
 
 /* ---- physics model (built on the host by the reference-compatible API) - */

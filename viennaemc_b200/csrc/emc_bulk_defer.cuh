@@ -36,7 +36,7 @@ namespace emc {
 constexpr int kDeferWarps = EMC_DEFER_WARPS;
 constexpr int kDeferThreads = kDeferWarps * 32;
 constexpr int kDeferChunk = 64;    // particles per warp and pass (2 per lane)
-constexpr int kDeferMaxSteps = 8;  // time steps per launch
+constexpr int kDeferMaxSteps = 8;  // time steps per launch (measured optimum; more steps cost L1 through the observable slots)
 constexpr int kDeferDense = 16;    // frozen particles per chunk from which the chunk is finished in place
 constexpr int kDeferQueueCap = 32 + kDeferWarps * 32 + 64; // > 31 + kDeferWarps * 32 (see the capacity argument at pushFrozen)
 constexpr int kDeferStreams = 7;   // kx ky kz tau x y z (the energy is recomputed by the first drift)

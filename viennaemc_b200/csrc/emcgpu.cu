@@ -321,6 +321,10 @@ int emcgpu_set_option(emcgpu_ctx *ctx, const char *name, int64_t value) {
     ctx->optStages = (int)value;
     return EMCGPU_OK;
   }
+  if (!strcmp(name, "defer_tables_smem")) {
+    ctx->optDeferTablesSmem = value != 0;
+    return EMCGPU_OK;
+  }
   if (!strcmp(name, "multi_kernel")) {
     if (value != 0 && value != 1 && value != 2)
       return fail(ctx, EMCGPU_E_INVALID, "multi_kernel must be 0 (deferred events when the ensemble is large), 1 (in place) or 2 (deferred events always)");
@@ -720,7 +724,9 @@ int emcgpu_bulk_step_device(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPer
     if (ctx->grainOn && !ctx->grainClockSet)
       return fail(ctx, EMCGPU_E_INVALID, "a grain mechanism is set but the grain clocks were not uploaded (emcgpu_set_grain_clock)");
     if (defer) {
-      bool inSmem = !ctx->optTablesGlobal;
+      // K1c reads a table row once per event (1.1 % of the particle-steps): the 80 KB set stays L1/L2-resident and the
+      // shared memory it would take is worth more as L1 (measured: +7.6 %); "defer_tables_smem" = 1 stages it anyway
+      bool inSmem = ctx->optDeferTablesSmem && !ctx->optTablesGlobal;
       size_t smem = inSmem ? deferSmem(ctx, chunk, true) : 0;
       if (!smem) {
         inSmem = false;

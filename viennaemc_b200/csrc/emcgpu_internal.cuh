@@ -45,6 +45,7 @@ struct emcgpu_ctx {
   int optVec = 2;          // particles per lane and iteration of the streaming step kernel (1, 2, 4)
   int optKernel = 0;       // one-step kernel: 0 = TMA pipeline when it fits, 1 = plain streaming kernel
   int optStages = 0;       // cap on the TMA ring depth (0 = as many as fit)
+  int optDeferTablesSmem = 0; // K1c: 1 = stage the rate tables in shared memory (default: read them through L1/L2)
   int optMultiKernel = 0;  // several steps per launch: 0 = deferred events (K1c) when eligible, 1 = in-place (K1b)
   int optTablesGlobal = 0; // 1 = leave the rate tables in global memory / L2 (more ring stages)
   int optSorKernel = 0;    // 0 = row-per-thread wavefront when it fits, 1 = hyperplane loop
