@@ -368,7 +368,7 @@ def main_ours(args):
                 "note": f"per GPU. algorithmic = 136 B x particle-steps of a launch (SURVEY 8d); frac > 1 because the particle "
                         f"state crosses HBM once per {SPL} time steps (ncu DRAM traffic per launch in 'traffic', the "
                         "DRAM rate it implies in 'dram_gbs_measured'): this kernel is bound by the FP64 pipe and instruction "
-                        "issue, not by HBM (profiles/r1_n_defer_v4_spl8.txt). The HBM-bound one-step kernel is in "
+                        "issue, not by HBM (profiles/r1_p_defer_v7_spl8.txt). The HBM-bound one-step kernel is in "
                         "'one_step_per_launch'."}
     one_achieved = BYTES_PER_PARTICLE_STEP * n_local * K / (one_ms * 1e-3) / 1e9
     one_step = {"kernel": "bulkTmaKernel<FAST, PHILOX> (one time step per launch, TMA pipeline)", "value": one_value,
