@@ -270,10 +270,29 @@ __device__ __forceinline__ void runEvents(const CtaState &C, const BulkParams &P
   }
 }
 
+// The CTA's staged model, rebuilt from the shared-memory symbol itself so that the compiler knows the address space
+// (shared-memory loads instead of generic ones in the out-of-line event routines).
+__device__ __forceinline__ CtaState localCtaState(const BulkParams &P) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  const int nV = P.model->nValleys;
+  const BulkSmem L(kDeferWarps * P.nSteps * nV * 3, nV, P.nMechTotal, P.model->tableDoubles, P.tablesInSmem != 0,
+                   kDeferQueueWords);
+  CtaState c;
+  c.model = reinterpret_cast<const DevModel *>(smemRaw + L.model);
+  c.obs = reinterpret_cast<double *>(smemRaw + L.obs);
+  c.mechs = reinterpret_cast<const DevMech *>(smemRaw + L.mechs);
+  c.fastV = reinterpret_cast<const FastValley *>(smemRaw + L.fastV);
+  c.fast = reinterpret_cast<const FastSub *>(smemRaw + L.fast);
+  c.queue = reinterpret_cast<uint32_t *>(smemRaw + L.queue);
+  c.tables = P.tablesInSmem ? reinterpret_cast<const double *>(smemRaw + L.tables) : P.tables;
+  return c;
+}
+
 // Up to 32 queued particles, one per lane.
 template <bool EXACT, int RNG_MODE>
-__device__ __noinline__ void eventBatch(const CtaState &C, const BulkParams &P, DeferControl *ctl, DeferQueue *Q,
+__device__ __noinline__ void eventBatch(const CtaState &, const BulkParams &P, DeferControl *ctl, DeferQueue *Q,
                                         double *obsT, unsigned head, int count, bool repush) {
+  const CtaState C = localCtaState(P);
   const int lane = threadIdx.x & 31;
   const bool active = lane < count;
   Particle p;
@@ -309,8 +328,9 @@ __device__ __noinline__ void eventBatch(const CtaState &C, const BulkParams &P, 
 // The lane's particle idx, whose state is in global memory, from step s to the end of the launch, in place (rare paths:
 // chunks in which most particles scatter, the particles behind the last whole chunk).  Only scalars cross the call.
 template <bool EXACT, int RNG_MODE>
-__device__ __noinline__ void runFromGlobal(const CtaState &C, const BulkParams &P, DeferControl *ctl, DeferQueue *Q,
+__device__ __noinline__ void runFromGlobal(const CtaState &, const BulkParams &P, DeferControl *ctl, DeferQueue *Q,
                                            double *obsT, uint32_t idx, int s, bool active) {
+  const CtaState C = localCtaState(P);
   Particle p;
   Rng rng;
   p.k = Vec3{0.0, 0.0, 0.0};
