@@ -249,6 +249,15 @@ int emcgpu_bulk_step(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPerLaunch,
  * on the context's stream. */
 int emcgpu_bulk_step_device(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPerLaunch,
                             double *obsDevice);
+/* the same nSteps x { moveParticles ; observables } for an ensemble that lives in HOST memory (soa / packed as
+ * emcgpu_set_ensemble, updated IN PLACE; pinned memory makes the copies asynchronous): the ensemble is cut into
+ * slices of sliceParticles (<= 0: about n/16) and slice i runs its nSteps steps while slice i+1 is copied to the
+ * device and slice i-1 back, so the PCIe transfers hide behind the step kernels and n is not limited by the HBM
+ * size. Results equal emcgpu_set_ensemble + emcgpu_bulk_step + emcgpu_get_ensemble (particle states bit for bit,
+ * the Philox stream of a particle is keyed by particleIdBase + index; obs = the same sums in another order).
+ * Philox streams only; the context's resident ensemble is not touched; the step index advances by nSteps. */
+int emcgpu_bulk_run_host(emcgpu_ctx *ctx, int64_t n, double *const *soa, uint32_t *packed, int64_t particleIdBase,
+                         double dt, int nSteps, int stepsPerLaunch, int64_t sliceParticles, double *obs);
 /* observables of the current state without moving (:289-347), HOST out [nValleys][3] */
 int emcgpu_bulk_observables(emcgpu_ctx *ctx, double *obs);
 /* index of the next time step (Philox counter word); starts at 1 like

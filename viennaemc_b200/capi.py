@@ -94,6 +94,8 @@ def load():
     L.emcgpu_rng_replay.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_int64), C.c_int64]
     L.emcgpu_bulk_configure.argtypes = [vp, _DP, _DP, C.c_double, C.c_double, C.c_int]
     L.emcgpu_bulk_step.argtypes = [vp, C.c_double, C.c_int, C.c_int, _DP]
+    L.emcgpu_bulk_run_host.argtypes = [vp, C.c_int64, C.POINTER(_DP), C.POINTER(C.c_uint32), C.c_int64, C.c_double,
+                                       C.c_int, C.c_int, C.c_int64, _DP]
     L.emcgpu_bulk_step_device.argtypes = [vp, C.c_double, C.c_int, C.c_int, vp]
     L.emcgpu_bulk_observables.argtypes = [vp, _DP]
     L.emcgpu_set_step_index.argtypes = [vp, C.c_int64]
@@ -141,7 +143,7 @@ EXPORTED_SYMBOLS = [
     "emcgpu_set_stream", "emcgpu_synchronize", "emcgpu_set_option", "emcgpu_set_valleys", "emcgpu_set_tables", "emcgpu_set_grain", "emcgpu_set_grain_clock", "emcgpu_get_grain_clock", "emcgpu_set_phonon_baths", "emcgpu_get_phonon_counts", "emcgpu_set_ensemble",
     "emcgpu_get_ensemble", "emcgpu_ensemble_size", "emcgpu_generate_bulk_ensemble",
     "emcgpu_ensemble_device_ptrs", "emcgpu_rng_philox", "emcgpu_rng_replay", "emcgpu_bulk_configure",
-    "emcgpu_bulk_step", "emcgpu_bulk_step_device", "emcgpu_bulk_observables", "emcgpu_set_step_index",
+    "emcgpu_bulk_step", "emcgpu_bulk_run_host", "emcgpu_bulk_step_device", "emcgpu_bulk_observables", "emcgpu_set_step_index",
     "emcgpu_get_step_index", "emcgpu_event_log_enable", "emcgpu_event_log_read",
     "emcgpu_device_configure", "emcgpu_device_set_surface", "emcgpu_device_set_particle_kind", "emcgpu_device_set_sharding", "emcgpu_device_set_grid", "emcgpu_device_get_grid", "emcgpu_device_reserve",
     "emcgpu_device_poisson", "emcgpu_device_efield", "emcgpu_device_assign", "emcgpu_device_concentration",
@@ -324,6 +326,20 @@ class Context:
                                           obs.ctypes.data_as(_DP) if want_obs else None))
         return obs
 
+    def bulk_run_host(self, streams, packed, dt, n_steps, steps_per_launch=8, slice_particles=0, particle_id_base=0,
+                      want_obs=True):
+        """advance a HOST-resident ensemble in place, slice by slice (copies overlap the step kernels when the
+        arrays are views of pinned memory)"""
+        n = len(packed)
+        assert all(a.dtype == np.float64 and a.flags.c_contiguous and len(a) == n for a in streams)
+        assert packed.dtype == np.uint32 and packed.flags.c_contiguous
+        ptrs = (_DP * N_STREAMS)(*[a.ctypes.data_as(_DP) for a in streams])
+        obs = np.zeros((n_steps, self.n_valleys, 3)) if want_obs else None
+        self._chk(self.L.emcgpu_bulk_run_host(self.h, n, ptrs, packed.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                              particle_id_base, dt, n_steps, steps_per_launch, slice_particles,
+                                              obs.ctypes.data_as(_DP) if want_obs else None))
+        return obs
+
     def bulk_step_device(self, dt, n_steps, steps_per_launch, obs_device_ptr):
         self._chk(self.L.emcgpu_bulk_step_device(self.h, dt, n_steps, steps_per_launch, obs_device_ptr))
 
@@ -421,6 +437,10 @@ class Context:
 
     def set_step_index(self, s):
         self._chk(self.L.emcgpu_set_step_index(self.h, s))
+
+    @property
+    def step_index(self):
+        return int(self.L.emcgpu_get_step_index(self.h))
 
     def set_stream(self, cuda_stream_ptr):
         self._chk(self.L.emcgpu_set_stream(self.h, cuda_stream_ptr))

@@ -268,8 +268,10 @@ void emcgpu_destroy(emcgpu_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (DeviceBuffer *b : {&ctx->dModel, &ctx->dMechs, &ctx->dTables, &ctx->dEnsemble, &ctx->dDraws,
                           &ctx->dOffsets, &ctx->dCursor, &ctx->dObs, &ctx->dStatus, &ctx->dEvents,
-                          &ctx->dEvCount})
+                          &ctx->dEvCount, &ctx->dSlices})
     b->release();
+  if (ctx->copyIn) cudaStreamDestroy(ctx->copyIn);
+  if (ctx->copyOut) cudaStreamDestroy(ctx->copyOut);
   emc::releaseDeviceRun(ctx);
   delete ctx;
 }
@@ -706,7 +708,8 @@ int emcgpu_bulk_step_device(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPer
   if (stepsPerLaunch < 1) stepsPerLaunch = 1;
   if (stepsPerLaunch > kMaxStepsPerLaunch) stepsPerLaunch = kMaxStepsPerLaunch;
   const int nV = ctx->hModel.nValleys;
-  CUDA_TRY(ctx, cudaMemsetAsync(obsDevice, 0, (size_t)nSteps * nV * 3 * sizeof(double), ctx->stream));
+  if (!ctx->obsAccumulate)
+    CUDA_TRY(ctx, cudaMemsetAsync(obsDevice, 0, (size_t)nSteps * nV * 3 * sizeof(double), ctx->stream));
   BulkParams P;
   fillBulkParams(ctx, P);
   P.dt = dt;
@@ -809,6 +812,103 @@ int emcgpu_bulk_step(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPerLaunch,
   if (int r = emcgpu_bulk_step_device(ctx, dt, nSteps, stepsPerLaunch, static_cast<double *>(ctx->dObs.ptr)))
     return r;
   if (obs) CUDA_TRY(ctx, cudaMemcpyAsync(obs, ctx->dObs.ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return checkStatusWord(ctx); // synchronises
+}
+
+// Host-resident ensemble advanced slice by slice: while slice i runs its nSteps time steps, slice i+1 is on its way
+// to the device and slice i-1 on its way back (particles of a bulk run are independent: the Philox stream of a
+// particle is keyed by its global id, the observables are sums). The resident ensemble of ctx is left untouched.
+int emcgpu_bulk_run_host(emcgpu_ctx *ctx, int64_t n, double *const *soa, uint32_t *packed, int64_t particleIdBase,
+                         double dt, int nSteps, int stepsPerLaunch, int64_t sliceParticles, double *obs) {
+  if (int r = checkReady(ctx, false)) return r;
+  if (n < 0 || (n > 0 && (!soa || !packed)) || !(dt > 0) || nSteps < 1)
+    return fail(ctx, EMCGPU_E_INVALID, "bad arguments of emcgpu_bulk_run_host");
+  if (ctx->rngMode != RNG_PHILOX) return fail(ctx, EMCGPU_E_INVALID, "emcgpu_bulk_run_host needs the Philox streams (replay streams belong to a resident ensemble)");
+  if (ctx->grainOn) return fail(ctx, EMCGPU_E_INVALID, "emcgpu_bulk_run_host does not carry grain clocks");
+  if (int r = bind(ctx)) return r;
+  for (int s = 0; s < EMCGPU_N_STREAMS && n > 0; s++)
+    if (!soa[s]) return fail(ctx, EMCGPU_E_INVALID, "stream %d is NULL", s);
+  const int nV = ctx->hModel.nValleys;
+  const size_t obsBytes = (size_t)nSteps * nV * 3 * sizeof(double);
+  CUDA_TRY(ctx, ctx->dObs.ensure(obsBytes));
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->dObs.ptr, 0, obsBytes, ctx->stream));
+  if (n > 0) {
+    // slice: a multiple of what one pass of the deferred-event kernel takes (all SMs x warps x chunk), about n/16
+    const int64_t quantum = (int64_t)ctx->smCount * kDeferWarps * kDeferChunk;
+    int64_t slice = sliceParticles > 0 ? sliceParticles : std::max<int64_t>((n / 16 + quantum - 1) / quantum * quantum, 16 * quantum);
+    slice = std::min(slice, n);
+    if (slice >= (int64_t)1 << 32) return fail(ctx, EMCGPU_E_CAPACITY, "at most 2^32-1 particles per slice");
+    const int nBuf = 3;
+    const size_t strideD = ((size_t)slice * sizeof(double) + 255) & ~size_t(255);
+    const size_t strideP = ((size_t)slice * sizeof(uint32_t) + 255) & ~size_t(255);
+    const size_t bufBytes = strideD * EMCGPU_N_STREAMS + strideP;
+    CUDA_TRY(ctx, ctx->dSlices.ensure(bufBytes * nBuf));
+    if (!ctx->copyIn) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copyIn, cudaStreamNonBlocking));
+    if (!ctx->copyOut) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copyOut, cudaStreamNonBlocking));
+    cudaEvent_t evIn[nBuf], evRun[nBuf], evOut[nBuf];
+    for (int b = 0; b < nBuf; b++) {
+      CUDA_TRY(ctx, cudaEventCreateWithFlags(&evIn[b], cudaEventDisableTiming));
+      CUDA_TRY(ctx, cudaEventCreateWithFlags(&evRun[b], cudaEventDisableTiming));
+      CUDA_TRY(ctx, cudaEventCreateWithFlags(&evOut[b], cudaEventDisableTiming));
+    }
+    // the step routine works on whatever ensemble the context points at
+    double *savedStream[EMCGPU_N_STREAMS];
+    for (int s = 0; s < EMCGPU_N_STREAMS; s++) savedStream[s] = ctx->dStream[s];
+    uint32_t *savedPacked = ctx->dPacked;
+    const int64_t savedN = ctx->n, savedBase = ctx->idBase, step0 = ctx->nextStep;
+    const bool savedAcc = ctx->obsAccumulate;
+    ctx->obsAccumulate = true;
+    int rc = EMCGPU_OK;
+    cudaError_t ce = cudaSuccess;
+    const int64_t nSlices = (n + slice - 1) / slice;
+    for (int64_t i = 0; i < nSlices && rc == EMCGPU_OK && ce == cudaSuccess; i++) {
+      const int b = (int)(i % nBuf);
+      const int64_t first = i * slice, m = std::min(slice, n - first);
+      unsigned char *base = static_cast<unsigned char *>(ctx->dSlices.ptr) + bufBytes * b;
+      if (i >= nBuf) ce = cudaStreamWaitEvent(ctx->copyIn, evOut[b], 0); // the slice that used this buffer is back on the host
+      for (int s = 0; s < EMCGPU_N_STREAMS && ce == cudaSuccess; s++)
+        ce = cudaMemcpyAsync(base + strideD * s, soa[s] + first, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, ctx->copyIn);
+      if (ce == cudaSuccess)
+        ce = cudaMemcpyAsync(base + strideD * EMCGPU_N_STREAMS, packed + first, (size_t)m * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copyIn);
+      if (ce == cudaSuccess) ce = cudaEventRecord(evIn[b], ctx->copyIn);
+      if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->stream, evIn[b], 0);
+      if (ce != cudaSuccess) break;
+      for (int s = 0; s < EMCGPU_N_STREAMS; s++) ctx->dStream[s] = reinterpret_cast<double *>(base + strideD * s);
+      ctx->dPacked = reinterpret_cast<uint32_t *>(base + strideD * EMCGPU_N_STREAMS);
+      ctx->n = m;
+      ctx->idBase = particleIdBase + first;
+      ctx->nextStep = step0;
+      rc = emcgpu_bulk_step_device(ctx, dt, nSteps, stepsPerLaunch, static_cast<double *>(ctx->dObs.ptr));
+      if (rc != EMCGPU_OK) break;
+      ce = cudaEventRecord(evRun[b], ctx->stream);
+      if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->copyOut, evRun[b], 0);
+      for (int s = 0; s < EMCGPU_N_STREAMS && ce == cudaSuccess; s++)
+        ce = cudaMemcpyAsync(soa[s] + first, base + strideD * s, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, ctx->copyOut);
+      if (ce == cudaSuccess)
+        ce = cudaMemcpyAsync(packed + first, base + strideD * EMCGPU_N_STREAMS, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copyOut);
+      if (ce == cudaSuccess) ce = cudaEventRecord(evOut[b], ctx->copyOut);
+    }
+    cudaStreamSynchronize(ctx->copyIn);
+    cudaStreamSynchronize(ctx->stream);
+    cudaError_t ce2 = cudaStreamSynchronize(ctx->copyOut);
+    for (int b = 0; b < nBuf; b++) {
+      cudaEventDestroy(evIn[b]);
+      cudaEventDestroy(evRun[b]);
+      cudaEventDestroy(evOut[b]);
+    }
+    for (int s = 0; s < EMCGPU_N_STREAMS; s++) ctx->dStream[s] = savedStream[s];
+    ctx->dPacked = savedPacked;
+    ctx->n = savedN;
+    ctx->idBase = savedBase;
+    ctx->obsAccumulate = savedAcc;
+    ctx->nextStep = step0 + (rc == EMCGPU_OK ? nSteps : 0);
+    if (rc != EMCGPU_OK) return rc;
+    if (ce == cudaSuccess) ce = ce2;
+    if (ce != cudaSuccess) return fail(ctx, EMCGPU_E_CUDA, "emcgpu_bulk_run_host: %s", cudaGetErrorString(ce));
+  } else {
+    ctx->nextStep += nSteps;
+  }
+  if (obs) CUDA_TRY(ctx, cudaMemcpyAsync(obs, ctx->dObs.ptr, obsBytes, cudaMemcpyDeviceToHost, ctx->stream));
   return checkStatusWord(ctx); // synchronises
 }
 

@@ -67,6 +67,11 @@ struct emcgpu_ctx {
   double *dStream[EMCGPU_N_STREAMS] = {};
   uint32_t *dPacked = nullptr;
 
+  // slice ring of emcgpu_bulk_run_host (three slices: upload / advance / download)
+  emc::DeviceBuffer dSlices;
+  cudaStream_t copyIn = nullptr, copyOut = nullptr;
+  bool obsAccumulate = false; // emcgpu_bulk_step_device adds to obsDevice instead of zeroing it first
+
   // rng
   int rngMode = emc::RNG_PHILOX;
   uint64_t seed = 0;
