@@ -251,7 +251,7 @@ int emcgpu_bulk_step_device(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPer
                             double *obsDevice);
 /* the same nSteps x { moveParticles ; observables } for an ensemble that lives in HOST memory (soa / packed as
  * emcgpu_set_ensemble, updated IN PLACE; pinned memory makes the copies asynchronous): the ensemble is cut into
- * slices of sliceParticles (<= 0: about n/16) and slice i runs its nSteps steps while slice i+1 is copied to the
+ * slices of sliceParticles (<= 0: about n/8) and slice i runs its nSteps steps while slice i+1 is copied to the
  * device and slice i-1 back, so the PCIe transfers hide behind the step kernels and n is not limited by the HBM
  * size. Results equal emcgpu_set_ensemble + emcgpu_bulk_step + emcgpu_get_ensemble (particle states bit for bit,
  * the Philox stream of a particle is keyed by particleIdBase + index; obs = the same sums in another order).
