@@ -132,6 +132,9 @@ def _read_grid(path):
     return a
 
 
+PROFILE_SIGMA = 6.0  # per-point bar of the averaged potential / concentration profiles (see _check_resistor)
+
+
 def _check_resistor(workdir, prefix, n_sigma=3.0):
     st = _resistor_stats()
     n_sigma = _t_sigma(n_sigma, st["n_runs"])
@@ -153,8 +156,11 @@ def _check_resistor(workdir, prefix, n_sigma=3.0):
     # (almost) no scatter: absolute floors.
     pot_sig = np.maximum(pot_std, np.median(pot_std)) * widen
     conc_sig = np.maximum(conc_std, np.median(conc_std)) * widen
-    assert np.all(np.abs(pot - pot_ref) <= 4.5 * pot_sig + 2e-4), np.abs(pot - pot_ref).max()
-    assert np.all(np.abs(conc - conc_ref) <= 4.5 * conc_sig + 1e-3 * conc_ref), np.abs(conc / conc_ref - 1).max()
+    # PROFILE_SIGMA = 6: one run in about twenty of the 4.5-sigma version failed on B200 although a rerun of the same
+    # binary passed (neighbouring points of an averaged profile are strongly correlated and the scatter comes from a
+    # handful of reference runs); the terminal currents above keep the 3-sigma bar.
+    assert np.all(np.abs(pot - pot_ref) <= PROFILE_SIGMA * pot_sig + 2e-4), np.abs(pot - pot_ref).max()
+    assert np.all(np.abs(conc - conc_ref) <= PROFILE_SIGMA * conc_sig + 1e-3 * conc_ref), np.abs(conc / conc_ref - 1).max()
     # and the bar as a whole: mean carrier density within 3 sigma of the reference's
     ref_means = np.array([np.mean(r["conc_x"]) for r in st["runs"]])
     assert abs(conc.mean() - ref_means.mean()) <= n_sigma * ref_means.std(ddof=1) * widen + 1e-3 * ref_means.mean()
@@ -214,7 +220,7 @@ def _check_mosfet(workdir, prefix, st, n_sigma=3.0):
         ref, std = np.array(st[key + "_mean"]), np.array(st[key + "_std"])
         sig = np.maximum(std, np.median(std)) * widen
         floor = 2e-3 if key.startswith("pot") else 2e-2 * np.abs(ref) + 1e-3 * np.abs(ref).max()
-        assert np.all(np.abs(got - ref) <= 4.5 * sig + floor), (key, float(np.abs(got - ref).max()))
+        assert np.all(np.abs(got - ref) <= PROFILE_SIGMA * sig + floor), (key, float(np.abs(got - ref).max()))
     assert abs(conc.sum() - st["conc_total_mean"]) <= n_sigma * st["conc_total_std"] * widen + 2e-3 * st["conc_total_mean"]
     # inversion charge under the middle of the gate: the density column integrated over the depth (single cells of the
     # depleted bulk hold a handful of particles in 500 steps -- too noisy to compare point by point)
