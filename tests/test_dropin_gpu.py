@@ -156,7 +156,7 @@ def _check_resistor(workdir, prefix, n_sigma=3.0):
     # (almost) no scatter: absolute floors.
     pot_sig = np.maximum(pot_std, np.median(pot_std)) * widen
     conc_sig = np.maximum(conc_std, np.median(conc_std)) * widen
-    # PROFILE_SIGMA = 6: one run in about twenty of the 4.5-sigma version failed on B200 although a rerun of the same
+    # PROFILE_SIGMA = 6: the 4.5-sigma version failed once among the full-suite runs of round 1 on B200 while a rerun of the same
     # binary passed (neighbouring points of an averaged profile are strongly correlated and the scatter comes from a
     # handful of reference runs); the terminal currents above keep the 3-sigma bar.
     assert np.all(np.abs(pot - pot_ref) <= PROFILE_SIGMA * pot_sig + 2e-4), np.abs(pot - pot_ref).max()
