@@ -15,7 +15,7 @@ ROOT = os.path.dirname(PKG)
 LIBDIR = os.path.join(PKG, "lib")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-shared"]
 
 
 def _newer(target: str, sources) -> bool:

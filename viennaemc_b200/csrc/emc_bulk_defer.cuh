@@ -45,7 +45,6 @@ struct DeferControl {
   uint64_t tableBar;
   unsigned qTail, qHead;
   unsigned nextChunk; // chunks of this CTA handed out so far (dynamic claiming)
-  uint32_t packBase;  // shared-memory address of the FastPack table, 0 = the packed fast step does not apply
 };
 struct DeferQueue {
   double f[kDeferStreams][kDeferQueueCap];
@@ -57,22 +56,9 @@ struct DeferQueue {
 constexpr int kDeferQueueWords = (int)((sizeof(DeferControl) + sizeof(DeferQueue) + 3) / 4);
 
 __host__ __device__ inline size_t deferObsOffset(const BulkSmem &L) { return (L.total + 15) & ~size_t(15); }
-// particles that left the main pass of a chunk, staged per warp until the chunk is done (one queue reservation per chunk)
-struct DeferStage {
-  double f[kDeferStreams][kDeferDense];
-  uint32_t w[kDeferDense];
-  uint32_t idx[kDeferDense];
-  uint32_t step[kDeferDense];
-};
 // per-thread observable slots: [nSteps][2 (sum E, sum v.E)][kDeferThreads]
-__host__ __device__ inline size_t deferStageOffset(const BulkSmem &L, int nSteps) {
+__host__ __device__ inline size_t deferSmemBytes(const BulkSmem &L, int nSteps, int /*nValleys*/) {
   return deferObsOffset(L) + (size_t)nSteps * 2 * kDeferThreads * sizeof(double);
-}
-__host__ __device__ inline size_t deferPackOffset(const BulkSmem &L, int nSteps) {
-  return deferStageOffset(L, nSteps) + (size_t)kDeferWarps * sizeof(DeferStage);
-}
-__host__ __device__ inline size_t deferSmemBytes(const BulkSmem &L, int nSteps, int nValleys) {
-  return deferPackOffset(L, nSteps) + ((size_t)nValleys * EMCGPU_MAX_SUBVALLEYS + 1) * 96; // + the all-zero pack
 }
 
 // A whole time step of a particle whose flight outlasts it (tau >= dt): drift(dt), periodic wrap, tau -= dt
@@ -126,72 +112,6 @@ __device__ __forceinline__ void pushFrozen(DeferControl *ctl, DeferQueue *Q, boo
   __syncwarp();
 }
 
-// Constants of the full-dt flight per (valley, sub-valley) for the branch-free main pass (valleys whose rotations are
-// signed permutations: M is diagonal), packed for 16-byte shared-memory loads.
-struct FastPack {
-  double dk[3], md[3], c[3], fE, c2a, pad;
-};
-static_assert(sizeof(FastPack) == 96, "FastPack is read with 16-byte loads");
-
-__device__ __forceinline__ void ldsPair(uint32_t addr, double &a, double &b) {
-  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
-}
-
-// fastStep (emc_device.cuh) operation for operation, constants from a FastPack in shared memory; no branches
-struct Lite {
-  double kx, ky, kz, tau, x, y, z, e;
-};
-// periodic wrap (basicBulkParticleHandler.hpp:600-613) as two compares and two predicated adds
-__device__ __forceinline__ double wrapFast(double x, double b) {
-  asm("{\n\t.reg .pred p, q;\n\tsetp.lt.f64 p, %0, 0d0000000000000000;\n\tsetp.gt.f64 q, %0, %1;\n\t"
-      "@p add.rn.f64 %0, %0, %1;\n\t@q sub.rn.f64 %0, %0, %1;\n\t}"
-      : "+d"(x)
-      : "d"(b));
-  return x;
-}
-__device__ __forceinline__ double fastStepPacked(uint32_t fp, double dt, double bx, double by, double bz, Lite &q) {
-  double dk0, dk1, dk2, m0, m1, m2, c0, c1, c2, fE, c2a, pad;
-  ldsPair(fp, dk0, dk1);
-  ldsPair(fp + 16, dk2, m0);
-  ldsPair(fp + 32, m1, m2);
-  ldsPair(fp + 48, c0, c1);
-  ldsPair(fp + 64, c2, fE);
-  ldsPair(fp + 80, c2a, pad);
-  const double nx = q.kx + dk0, ny = q.ky + dk1, nz = q.kz + dk2;
-  const double sq = fma(nz, nz, fma(ny, ny, nx * nx));
-  const double g = fE * sq;
-  const double x = fma(c2a, sq, 1.0);
-  const double r = rsqrtNormal(x); // 1/S
-  const double d = fma(x, r, 1.0); // 1 + S
-  const double y = rcpNormal(d);
-  double e = g * y;
-  e = fma(fma(-d, e, g), y, e);
-  const double w = dt * r;
-  const double sx = (nx + q.kx) * w, sy = (ny + q.ky) * w, sz = (nz + q.kz) * w;
-  const double px = q.x + m0 * sx, py = q.y + m1 * sy, pz = q.z + m2 * sz;
-  q.x = wrapFast(px, bx);
-  q.y = wrapFast(py, by);
-  q.z = wrapFast(pz, bz);
-  q.kx = nx;
-  q.ky = ny;
-  q.kz = nz;
-  q.e = e;
-  q.tau -= dt;
-  return fma(c2, nz, fma(c1, ny, c0 * nx)) * r;
-}
-
-__device__ __forceinline__ Particle toParticle(const Lite &q, uint32_t w) {
-  Particle p;
-  p.k = Vec3{q.kx, q.ky, q.kz};
-  p.energy = q.e;
-  p.tau = q.tau;
-  p.pos = Vec3{q.x, q.y, q.z};
-  p.valley = w & 0xffu;
-  p.sub = (w >> 8) & 0xffu;
-  p.region = w >> 16;
-  return p;
-}
-
 // One particle-step of an event lane into the per-step sums: one valley -> the thread's own slots (no atomics);
 // several valleys -> atomics on the warp's copy of the per-valley sums.
 __device__ __forceinline__ void addObsLane(double *wObs, double *myObs, int obsPerStep, bool single, int s, int valley,
@@ -219,7 +139,6 @@ __device__ __forceinline__ void runEvents(const CtaState &C, const BulkParams &P
   const double dt = P.dt;
   double *const wObs = C.obs + (threadIdx.x >> 5) * nSteps * obsPerStep; // the warp's own copy of the per-step sums
   double *const myObs = obsT + threadIdx.x;
-  const uint32_t packBase = ctl->packBase;
   for (;;) {
     if (active) {
       Rng rng;
@@ -236,25 +155,10 @@ __device__ __forceinline__ void runEvents(const CtaState &C, const BulkParams &P
       if constexpr (RNG_MODE == RNG_REPLAY) storeCursor(P, idx, rng);
       addObsLane(wObs, myObs, obsPerStep, single, s, p.valley, p.energy, vd);
       s++;
-      if (!EXACT && packBase) {
-        // same arithmetic as the main pass (fastStepPacked == fastStep operation for operation)
-        const uint32_t fp = packBase + (uint32_t)sizeof(FastPack) * (p.valley * EMCGPU_MAX_SUBVALLEYS + p.sub);
-        Lite q{p.k.x, p.k.y, p.k.z, p.tau, p.pos.x, p.pos.y, p.pos.z, p.energy};
-        while (s < nSteps && q.tau >= dt) {
-          vd = fastStepPacked(fp, dt, P.box.x, P.box.y, P.box.z, q);
-          addObsLane(wObs, myObs, obsPerStep, single, s, p.valley, q.e, vd);
-          s++;
-        }
-        p.k = Vec3{q.kx, q.ky, q.kz};
-        p.tau = q.tau;
-        p.pos = Vec3{q.x, q.y, q.z};
-        p.energy = q.e;
-      } else {
-        while (s < nSteps && p.tau >= dt) {
-          vd = fullDtStep<EXACT>(C, P, p);
-          addObsLane(wObs, myObs, obsPerStep, single, s, p.valley, p.energy, vd);
-          s++;
-        }
+      while (s < nSteps && p.tau >= dt) {
+        vd = fullDtStep<EXACT>(C, P, p);
+        addObsLane(wObs, myObs, obsPerStep, single, s, p.valley, p.energy, vd);
+        s++;
       }
       if (s == nSteps) {
         storeParticleState(P, idx, p);
@@ -341,44 +245,6 @@ __device__ __noinline__ void runFromGlobal(const CtaState &, const BulkParams &P
   runEvents<EXACT, RNG_MODE>(C, P, ctl, Q, obsT, p, idx, s, active, false);
 }
 
-__device__ __forceinline__ void stageParticle(DeferStage *st, int slot, const Lite &q, uint32_t w, uint32_t idx, int step) {
-  st->f[0][slot] = q.kx;
-  st->f[1][slot] = q.ky;
-  st->f[2][slot] = q.kz;
-  st->f[3][slot] = q.tau;
-  st->f[4][slot] = q.x;
-  st->f[5][slot] = q.y;
-  st->f[6][slot] = q.z;
-  st->w[slot] = w;
-  st->idx[slot] = idx;
-  st->step[slot] = (uint32_t)step;
-}
-// the warp's n (< 32) staged particles into the CTA queue: one reservation, lane i moves entry i (warp-collective;
-// capacity argument as at pushFrozen)
-__device__ __forceinline__ void flushStage(DeferControl *ctl, DeferQueue *Q, const DeferStage *st, int n) {
-  if (n == 0) return;
-  __syncwarp();
-  const int lane = threadIdx.x & 31;
-  unsigned base = 0;
-  if (lane == 0) base = atomicAdd(&ctl->qTail, (unsigned)n);
-  base = __shfl_sync(0xffffffffu, base, 0);
-  if (lane < n) {
-    const unsigned pos = base + lane;
-    const unsigned slot = pos % kDeferQueueCap;
-    const uint32_t epoch = pos / kDeferQueueCap + 1;
-    while (*reinterpret_cast<volatile uint32_t *>(&Q->flag[slot]) != 2 * (epoch - 1)) { // previous tenant read
-    }
-#pragma unroll
-    for (int c = 0; c < kDeferStreams; c++) Q->f[c][slot] = st->f[c][lane];
-    Q->w[slot] = st->w[lane];
-    Q->idx[slot] = st->idx[lane];
-    Q->step[slot] = st->step[lane];
-    __threadfence_block();
-    *reinterpret_cast<volatile uint32_t *>(&Q->flag[slot]) = 2 * epoch - 1;
-  }
-  __syncwarp();
-}
-
 // serve full batches of the event queue (warp-collective)
 template <bool EXACT, int RNG_MODE>
 __device__ __forceinline__ void serveBatches(const CtaState &C, const BulkParams &P, DeferControl *ctl, DeferQueue *Q,
@@ -411,43 +277,16 @@ __global__ void __launch_bounds__(kDeferThreads, 1) bulkDeferKernel(const __grid
   DeferControl *ctl = reinterpret_cast<DeferControl *>(smemRaw + L.queue);
   DeferQueue *Q = reinterpret_cast<DeferQueue *>(smemRaw + L.queue + sizeof(DeferControl));
   double *obsT = reinterpret_cast<double *>(smemRaw + deferObsOffset(L)); // [nSteps][2][kDeferThreads]
-  DeferStage *stage = reinterpret_cast<DeferStage *>(smemRaw + deferStageOffset(L, nSteps)) + (threadIdx.x >> 5);
-  FastPack *packs = reinterpret_cast<FastPack *>(smemRaw + deferPackOffset(L, nSteps)); // [nV][EMCGPU_MAX_SUBVALLEYS]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     ctl->qTail = 0;
     ctl->qHead = 0;
     ctl->nextChunk = 0;
-    ctl->packBase = 0;
   }
   for (int i = tid; i < kDeferQueueCap; i += kDeferThreads) Q->flag[i] = 0;
   for (int s = 0; s < 2 * nSteps; s++) obsT[s * kDeferThreads + tid] = 0.0;
   const CtaState C = stageCta(P, smemRaw, &ctl->tableBar, kDeferWarps * nSteps * obsPerStep, kDeferQueueWords); // __syncthreads inside
   const bool single = nV == 1;
-  bool allDiag = true;
-  for (int v = 0; v < nV; v++) allDiag = allDiag && C.fastV[v].diag != 0;
-  for (int i = tid; i < nV * EMCGPU_MAX_SUBVALLEYS; i += kDeferThreads) {
-    const FastSub &fs = C.fast[i];
-    const FastValley &fv = C.fastV[i / EMCGPU_MAX_SUBVALLEYS];
-    FastPack fp;
-    for (int a = 0; a < 3; a++) {
-      fp.dk[a] = fs.dk[a];
-      fp.md[a] = fs.m[4 * a];
-      fp.c[a] = fs.c[a];
-    }
-    fp.fE = fv.fE;
-    fp.c2a = fv.c2a;
-    fp.pad = 0.0;
-    packs[i] = fp;
-  }
-  if (tid == 0) { // a particle that left the pass computes on this: energy and velocity contributions come out as 0
-    FastPack z;
-    for (int a = 0; a < 3; a++) z.dk[a] = z.md[a] = z.c[a] = 0.0;
-    z.fE = z.c2a = z.pad = 0.0;
-    packs[nV * EMCGPU_MAX_SUBVALLEYS] = z;
-  }
-  if (tid == 0 && !EXACT && allDiag) ctl->packBase = smemAddr(packs);
-  __syncthreads();
   const double dt = P.dt;
   const int64_t nChunks = P.n / kDeferChunk;
   // chunks blockIdx.x + k * gridDim.x belong to this CTA; its warps claim them one by one and prefetch the next one
@@ -470,99 +309,7 @@ __global__ void __launch_bounds__(kDeferThreads, 1) bulkDeferKernel(const __grid
     asm volatile("prefetch.global.L2 [%0];" ::"l"(P.packed + i0));
   };
 
-  if (!EXACT && single && allDiag) {
-    // ================= branch-free main pass (the production case) =================
-    const uint32_t packBase = smemAddr(packs);
-    const uint32_t obsAddr = smemAddr(obsT) + tid * 8;
-    const double bx = P.box.x, by = P.box.y, bz = P.box.z;
-    const unsigned ltMask = (1u << lane) - 1u;
-    const uint32_t nullPack = packBase + (uint32_t)sizeof(FastPack) * (nV * EMCGPU_MAX_SUBVALLEYS);
-    for (int64_t ch = claimChunk(), chNext; ch < nChunks; ch = chNext) {
-      chNext = claimChunk();
-      prefetchChunk(chNext);
-      const int64_t i0 = ch * kDeferChunk + 2 * lane;
-      Lite a, b;
-      uint32_t wa, wb;
-      {
-        const double2 kx = __ldcs(reinterpret_cast<const double2 *>(P.stream[EMCGPU_KX] + i0));
-        const double2 ky = __ldcs(reinterpret_cast<const double2 *>(P.stream[EMCGPU_KY] + i0));
-        const double2 kz = __ldcs(reinterpret_cast<const double2 *>(P.stream[EMCGPU_KZ] + i0));
-        const double2 ta = __ldcs(reinterpret_cast<const double2 *>(P.stream[EMCGPU_TAU] + i0));
-        const double2 px = __ldcs(reinterpret_cast<const double2 *>(P.stream[EMCGPU_X] + i0));
-        const double2 py = __ldcs(reinterpret_cast<const double2 *>(P.stream[EMCGPU_Y] + i0));
-        const double2 pz = __ldcs(reinterpret_cast<const double2 *>(P.stream[EMCGPU_Z] + i0));
-        const uint2 w = __ldcs(reinterpret_cast<const uint2 *>(P.packed + i0));
-        a = Lite{kx.x, ky.x, kz.x, ta.x, px.x, py.x, pz.x, 0.0};
-        b = Lite{kx.y, ky.y, kz.y, ta.y, px.y, py.y, pz.y, 0.0};
-        wa = w.x;
-        wb = w.y;
-      }
-      uint32_t fpa = packBase + (uint32_t)sizeof(FastPack) * ((wa & 0xffu) * EMCGPU_MAX_SUBVALLEYS + ((wa >> 8) & 0xffu));
-      uint32_t fpb = packBase + (uint32_t)sizeof(FastPack) * ((wb & 0xffu) * EMCGPU_MAX_SUBVALLEYS + ((wb >> 8) & 0xffu));
-      bool liveA = true, liveB = true;
-      int pushed = 0, denseAt = -1; // warp-uniform
-#pragma unroll 1
-      for (int s = 0; s < nSteps; s++) {
-        // a particle whose flight ends inside this step leaves the pass with its state as it is
-        const bool evA = liveA && !(a.tau >= dt), evB = liveB && !(b.tau >= dt);
-        const unsigned mA = __ballot_sync(0xffffffffu, evA), mB = __ballot_sync(0xffffffffu, evB);
-        if (mA | mB) {
-          const int nNew = __popc(mA) + __popc(mB);
-          if (pushed + nNew >= kDeferDense) {
-            // dt >~ tau regime: what is left of the chunk is finished in place, behind the loop (no calls in here)
-            denseAt = s;
-            break;
-          }
-          if (evA) {
-            stageParticle(stage, pushed + __popc(mA & ltMask), a, wa, (uint32_t)i0, s);
-            a.kx = a.ky = a.kz = 0.0; // from here on the lane's slot contributes exact zeros (all-zero pack)
-            fpa = nullPack;
-          }
-          if (evB) {
-            stageParticle(stage, pushed + __popc(mA) + __popc(mB & ltMask), b, wb, (uint32_t)(i0 + 1), s);
-            b.kx = b.ky = b.kz = 0.0;
-            fpb = nullPack;
-          }
-          pushed += nNew;
-          liveA = liveA && !evA;
-          liveB = liveB && !evB;
-          if (!__any_sync(0xffffffffu, liveA || liveB)) break;
-        }
-        // both particles move (the ones that left compute on dead values)
-        const double vA = fastStepPacked(fpa, dt, bx, by, bz, a);
-        const double vB = fastStepPacked(fpb, dt, bx, by, bz, b);
-        const double sumE = a.e + b.e, sumV = vA + vB; // particles that left contribute 0
-        const uint32_t oa = obsAddr + (uint32_t)s * (2 * kDeferThreads * 8);
-        double accE, accV;
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(accE) : "r"(oa));
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(accV) : "r"(oa + kDeferThreads * 8));
-        accE += sumE;
-        accV += sumV;
-        asm volatile("st.shared.f64 [%0], %1;" ::"r"(oa), "d"(accE) : "memory");
-        asm volatile("st.shared.f64 [%0], %1;" ::"r"(oa + kDeferThreads * 8), "d"(accV) : "memory");
-      }
-      if (liveA && liveB) {
-        __stcs(reinterpret_cast<double2 *>(P.stream[EMCGPU_KX] + i0), make_double2(a.kx, b.kx));
-        __stcs(reinterpret_cast<double2 *>(P.stream[EMCGPU_KY] + i0), make_double2(a.ky, b.ky));
-        __stcs(reinterpret_cast<double2 *>(P.stream[EMCGPU_KZ] + i0), make_double2(a.kz, b.kz));
-        __stcs(reinterpret_cast<double2 *>(P.stream[EMCGPU_ENERGY] + i0), make_double2(a.e, b.e));
-        __stcs(reinterpret_cast<double2 *>(P.stream[EMCGPU_TAU] + i0), make_double2(a.tau, b.tau));
-        __stcs(reinterpret_cast<double2 *>(P.stream[EMCGPU_X] + i0), make_double2(a.x, b.x));
-        __stcs(reinterpret_cast<double2 *>(P.stream[EMCGPU_Y] + i0), make_double2(a.y, b.y));
-        __stcs(reinterpret_cast<double2 *>(P.stream[EMCGPU_Z] + i0), make_double2(a.z, b.z));
-      } else {
-        if (liveA) storeParticleState(P, i0, toParticle(a, wa));
-        if (liveB) storeParticleState(P, i0 + 1, toParticle(b, wb));
-      }
-      flushStage(ctl, Q, stage, pushed);
-      if (denseAt >= 0) { // the live particles continue from their (just stored) state at step denseAt
-        __syncwarp();
-        runFromGlobal<EXACT, RNG_MODE>(C, P, ctl, Q, obsT, (uint32_t)i0, denseAt, liveA);
-        runFromGlobal<EXACT, RNG_MODE>(C, P, ctl, Q, obsT, (uint32_t)(i0 + 1), denseAt, liveB);
-      }
-      serveBatches<EXACT, RNG_MODE>(C, P, ctl, Q, obsT);
-    }
-  } else {
+  {
     // ================= general main pass (EXACT arithmetic, several valleys, general rotations) =================
     for (int64_t ch = claimChunk(), chNext; ch < nChunks; ch = chNext) {
       chNext = claimChunk();

@@ -48,6 +48,12 @@ struct BulkParams {
   // grain boundaries (emcGrainScatterMechanism): second free-flight clock per particle, nullptr = no grain mechanism
   double *grainTau;
   double grainProb, grainTau0;
+  // launch-uniform flight constants per valley (host-built: emcgpu.cu buildFlightConsts), read from the constant bank
+  FlightConst fc[EMCGPU_MAX_VALLEYS];
+  // split step (emc_bulk_split.cuh): per-particle byte "step at which the particle left the flight kernel" (0xFF: finished),
+  // claim counter of the event kernel
+  uint8_t *frozen;
+  unsigned *claim;
 };
 
 // emcGrainScatterMechanism::scatterParticle (include/emcGrainScatterMechanism.hpp:40-77) + emcParticleType::getNewGrainTau
@@ -219,14 +225,7 @@ __device__ __forceinline__ CtaState stageCta(const BulkParams &P, unsigned char 
     const DevValley &v = sModel->valleys[i / EMCGPU_MAX_SUBVALLEYS];
     const int s = i % EMCGPU_MAX_SUBVALLEYS;
     buildFastSub(v, s < v.deg ? s : 0, P.force, P.dir, P.dt, sFast[i]);
-    if (s == 0) {
-      FastValley fv;
-      fv.fE = v.nonParabolic ? v.fE : 2.0 * v.fE;
-      fv.c2a = 2.0 * v.alpha * fv.fE;
-      fv.diag = v.rotKind != ROT_GENERAL;
-      fv.pad = 0;
-      sFastV[i / EMCGPU_MAX_SUBVALLEYS] = fv;
-    }
+    if (s == 0) sFastV[i / EMCGPU_MAX_SUBVALLEYS].f = P.fc[i / EMCGPU_MAX_SUBVALLEYS];
   }
   __syncthreads();
   if (P.tablesInSmem) mbarWait(tableBar, 0);
@@ -241,11 +240,40 @@ __device__ __forceinline__ CtaState stageCta(const BulkParams &P, unsigned char 
   return c;
 }
 
+// One free flight of duration t followed by the periodic wrap (drift() emcParticleDrift.hpp:12-36 + the wrap of
+// basicBulkParticleHandler.hpp:600-613).  FAST arithmetic in a valley with signed-permutation rotations: the division-free
+// flight of emc_device.cuh (leaves r = 1/S of the new state in rInv); otherwise the reference's operation order.
+template <bool EXACT>
+__device__ __forceinline__ void flightAndWrap(const CtaState &C, const BulkParams &P, Particle &p, double t, double &rInv) {
+  if constexpr (!EXACT) {
+    const FlightConst &f = C.fastV[p.valley].f;
+    if (f.diag) {
+      const FastSub &fs = C.fast[p.valley * EMCGPU_MAX_SUBVALLEYS + p.sub];
+      FlightAux o;
+      flightCore(fs.a[0], fs.a[1], fs.a[2], f.Fh[0] * t, f.Fh[1] * t, f.Fh[2] * t, f.KP * t, f.c2a, p.k.x, p.k.y, p.k.z,
+                 p.pos.x, p.pos.y, p.pos.z, o);
+      if (mayNeedWrap(p.pos.x, (uint32_t)__double2hiint(P.box.x)) || mayNeedWrap(p.pos.y, (uint32_t)__double2hiint(P.box.y)) ||
+          mayNeedWrap(p.pos.z, (uint32_t)__double2hiint(P.box.z))) {
+        p.pos.x = wrapExact(p.pos.x, P.box.x);
+        p.pos.y = wrapExact(p.pos.y, P.box.y);
+        p.pos.z = wrapExact(p.pos.z, P.box.z);
+      }
+      p.energy = flightEnergy(f.fE, o);
+      rInv = o.r;
+      return;
+    }
+  }
+  drift<EXACT, 3>(C.model->valleys[p.valley], p, t, P.force);
+  p.pos.x = wrap1<EXACT>(p.pos.x, P.box.x);
+  p.pos.y = wrap1<EXACT>(p.pos.y, P.box.y);
+  p.pos.z = wrap1<EXACT>(p.pos.z, P.box.z);
+}
+
 // The scattering part of a time step (A.5 of SURVEY.md): entered with the
 // particle already drifted to its first scattering time; tRem = dt - tau_old.
 template <bool EXACT, int RNG_MODE>
 __device__ __forceinline__ void scatterLoop(const CtaState &C, const BulkParams &P, Particle &p, Rng &rng,
-                                            int64_t particleId, int64_t step, double tRem) {
+                                            int64_t particleId, int64_t step, double tRem, double &rInv) {
   using A = Arith<EXACT>;
   const DevModel &model = *C.model;
   while (tRem > 0.0) {
@@ -282,11 +310,7 @@ __device__ __forceinline__ void scatterLoop(const CtaState &C, const BulkParams 
     }
     const double newTau = A::mul(-log(uniformLog(rng.raw<RNG_MODE>())), tauTab);
     p.tau = A::add(p.tau, newTau);
-    const DevValley &v = model.valleys[p.valley];
-    drift<EXACT, 3>(v, p, fmin(tRem, newTau), P.force);
-    p.pos.x = wrap1<EXACT>(p.pos.x, P.box.x);
-    p.pos.y = wrap1<EXACT>(p.pos.y, P.box.y);
-    p.pos.z = wrap1<EXACT>(p.pos.z, P.box.z);
+    flightAndWrap<EXACT>(C, P, p, fmin(tRem, newTau), rInv);
     tRem = A::sub(tRem, newTau);
   }
 }
@@ -303,15 +327,15 @@ __device__ __forceinline__ double bulkParticleStep(const CtaState &C, const Bulk
       return fastStep(C.fast[p.valley * EMCGPU_MAX_SUBVALLEYS + p.sub], C.fastV[p.valley], dt, P.box, p.k.x, p.k.y,
                       p.k.z, p.energy, p.tau, p.pos.x, p.pos.y, p.pos.z);
   }
-  {
-    const DevValley &v = C.model->valleys[p.valley];
-    drift<EXACT, 3>(v, p, fmin(p.tau, dt), P.force);
-    p.pos.x = wrap1<EXACT>(p.pos.x, P.box.x);
-    p.pos.y = wrap1<EXACT>(p.pos.y, P.box.y);
-    p.pos.z = wrap1<EXACT>(p.pos.z, P.box.z);
-  }
-  scatterLoop<EXACT, RNG_MODE>(C, P, p, rng, particleId, step, A::sub(dt, p.tau));
+  double rInv = 0.0;
+  flightAndWrap<EXACT>(C, P, p, fmin(p.tau, dt), rInv);
+  scatterLoop<EXACT, RNG_MODE>(C, P, p, rng, particleId, step, A::sub(dt, p.tau), rInv);
   p.tau = A::sub(p.tau, dt);
+  if constexpr (!EXACT) {
+    const FlightConst &f = C.fastV[p.valley].f;
+    if (f.diag) // the step always ends with a flight: rInv belongs to the final state
+      return flightVelocity(f, C.fast[p.valley * EMCGPU_MAX_SUBVALLEYS + p.sub], p.k.x, p.k.y, p.k.z, rInv);
+  }
   return driftVelocity<EXACT>(C.model->valleys[p.valley], p.sub, p.k, p.energy, P.dir);
 }
 

@@ -294,11 +294,26 @@ struct FastSub {
   double dk[3];
   double m[9];
   double c[3];
+  double a[3]; // diagonal of R^T diag(vogt) R: the Herring-Vogt factor seen along each DEVICE axis (signed permutations)
+};
+// Launch-uniform constants of the flights of one valley.  Built on the host (emcgpu.cu: buildFlightConst) and passed as kernel
+// parameters, so that every kernel -- and the flight kernel, which reads them straight from the constant bank -- uses the
+// same numbers.  With a signed-permutation rotation the collapsed step above becomes, per device axis i,
+//   k'_i = k_i + a_i G_i      pos'_i = pos_i + (k'_i + k_i) a_i K2 / S      v.Ê = sum_i K4_i k'_i a_i K2 / S
+struct FlightConst {
+  double fE;    // hbar^2/(m q)  (parabolic: hbar^2/(2 m q) * 2, see stageCta)
+  double c2a;   // 2 alpha fE
+  double inv2a; // 1/(2 alpha) (0 for parabolic valleys)
+  double Fh[3]; // force / hbar
+  double G[3];  // Fh dt
+  double KP;    // hbar/(2 m)
+  double K2;    // KP dt
+  double KV[3]; // Ê 2 KP   (v.Ê = r sum_i KV_i a_i k'_i)
+  double K4[3]; // KV / K2
+  int32_t diag, nonParabolic;
 };
 struct FastValley {
-  double fE;  // hbar^2/(m q)
-  double c2a; // 2 alpha fE
-  int32_t diag, pad;
+  FlightConst f;
 };
 
 __device__ __forceinline__ void buildFastSub(const DevValley &v, int s, const Vec3 &force, const Vec3 &dir,
@@ -315,6 +330,8 @@ __device__ __forceinline__ void buildFastSub(const DevValley &v, int s, const Ve
     o.c[a] = r[a] * de[0] + r[3 + a] * de[1] + r[6 + a] * de[2];
     for (int b = 0; b < 3; b++)
       o.m[3 * a + b] = r[a] * v.fPos[0] * r[b] + r[3 + a] * v.fPos[1] * r[3 + b] + r[6 + a] * v.fPos[2] * r[6 + b];
+    // exact for signed permutations: one term, (+-1)^2 vogt
+    o.a[a] = r[a] * r[a] * v.vogt[0] + r[3 + a] * r[3 + a] * v.vogt[1] + r[6 + a] * r[6 + a] * v.vogt[2];
   }
 }
 
@@ -336,16 +353,81 @@ __device__ __forceinline__ double rcpNormal(double x) {
   return fma(y, t, y);
 }
 
+// ---- flights through a valley whose rotations are signed permutations (FlightConst::diag) ----------------------
+// The core of drift() (emcParticleDrift.hpp:12-36) for one flight: k' = k + a g (g = force/hbar * duration), the
+// position advance with the conduction mass of the NEW energy (kp = hbar/(2m) * duration).  Leaves |k'|^2, x = 1 + 2 a g
+// = S^2 and r = 1/S for the energy / velocity forms below.  One MUFU + 25 FP64 instructions; no divisions, no branches.
+struct FlightAux {
+  double sq, x, r, w0, w1, w2;
+};
+__device__ __forceinline__ void flightCore(double a0, double a1, double a2, double g0, double g1, double g2, double kp,
+                                           double c2a, double &kx, double &ky, double &kz, double &px, double &py,
+                                           double &pz, FlightAux &o) {
+  const double nx = fma(a0, g0, kx), ny = fma(a1, g1, ky), nz = fma(a2, g2, kz);
+  o.sq = fma(nz, nz, fma(ny, ny, nx * nx));
+  o.x = fma(c2a, o.sq, 1.0);
+  o.r = rsqrtNormal(o.x);
+  const double w = kp * o.r;
+  o.w0 = a0 * w;
+  o.w1 = a1 * w;
+  o.w2 = a2 * w;
+  px = fma(nx + kx, o.w0, px);
+  py = fma(ny + ky, o.w1, py);
+  pz = fma(nz + kz, o.w2, pz);
+  kx = nx;
+  ky = ny;
+  kz = nz;
+}
+// E = g/(1 + S), g = fE |k|^2 (getEnergy, emcNonParabolicAnistropValley.hpp:109-113), to the last bit or two
+__device__ __forceinline__ double flightEnergy(double fE, const FlightAux &o) {
+  const double g = fE * o.sq;
+  const double d = fma(o.x, o.r, 1.0); // 1 + S
+  const double y = rcpNormal(d);
+  const double e = g * y;
+  return fma(fma(-d, e, g), y, e);
+}
+// S - 1 = 2 alpha E with one rounding (the per-step energy observable of the flight kernel sums this)
+__device__ __forceinline__ double flightSm1(const FlightAux &o) { return fma(o.x, o.r, -1.0); }
+// v.Ê of the state after a full-dt flight: sum_i K4_i k'_i a_i K2 / S
+__device__ __forceinline__ double flightVelocityDt(double k40, double k41, double k42, double kx, double ky, double kz,
+                                                   const FlightAux &o) {
+  return fma(k42 * kz, o.w2, fma(k41 * ky, o.w1, (k40 * kx) * o.w0));
+}
+// v.Ê of a state with known r = 1/S: r sum_i KV_i a_i k_i
+__device__ __forceinline__ double flightVelocity(const FlightConst &f, const FastSub &fs, double kx, double ky, double kz,
+                                                 double r) {
+  return fma(f.KV[2] * fs.a[2], kz, fma(f.KV[1] * fs.a[1], ky, (f.KV[0] * fs.a[0]) * kx)) * r;
+}
+// exact periodic wrap (basicBulkParticleHandler.hpp:600-613) behind one unsigned compare of the high words: a coordinate in
+// [0, box) with a high word below the box's needs nothing; negative values (sign bit) and values near or beyond the box go on
+// to the exact test.
+__device__ __forceinline__ bool mayNeedWrap(double x, uint32_t boxHi) { return (uint32_t)__double2hiint(x) >= boxHi; }
+__device__ __forceinline__ double wrapExact(double x, double b) { return x < 0.0 ? x + b : (x > b ? x - b : x); }
+
 // One whole time step of a particle that does not scatter (tau >= dt):
 // drift(dt), periodic wrap, tau -= dt; returns v.Ê for the drift-velocity
 // observable (basicBulkParticleHandler.hpp:195-213, :326-347).
 __device__ __forceinline__ double fastStep(const FastSub &fs, const FastValley &fv, double dt, const Vec3 &box,
                                            double &kx, double &ky, double &kz, double &energy, double &tau,
                                            double &px, double &py, double &pz) {
+  const FlightConst &f = fv.f;
+  if (f.diag) {
+    FlightAux o;
+    flightCore(fs.a[0], fs.a[1], fs.a[2], f.G[0], f.G[1], f.G[2], f.K2, f.c2a, kx, ky, kz, px, py, pz, o);
+    if (mayNeedWrap(px, (uint32_t)__double2hiint(box.x)) || mayNeedWrap(py, (uint32_t)__double2hiint(box.y)) ||
+        mayNeedWrap(pz, (uint32_t)__double2hiint(box.z))) {
+      px = wrapExact(px, box.x);
+      py = wrapExact(py, box.y);
+      pz = wrapExact(pz, box.z);
+    }
+    energy = flightEnergy(f.fE, o);
+    tau -= dt;
+    return flightVelocityDt(f.K4[0], f.K4[1], f.K4[2], kx, ky, kz, o);
+  }
   const double nx = kx + fs.dk[0], ny = ky + fs.dk[1], nz = kz + fs.dk[2];
   const double sq = fma(nz, nz, fma(ny, ny, nx * nx));
-  const double g = fv.fE * sq;
-  const double x = fma(fv.c2a, sq, 1.0);
+  const double g = f.fE * sq;
+  const double x = fma(f.c2a, sq, 1.0);
   const double r = rsqrtNormal(x); // 1/S
   const double d = fma(x, r, 1.0); // 1 + S
   const double y = rcpNormal(d);
@@ -353,16 +435,9 @@ __device__ __forceinline__ double fastStep(const FastSub &fs, const FastValley &
   e = fma(fma(-d, e, g), y, e);
   const double w = dt * r;
   const double sx = (nx + kx) * w, sy = (ny + ky) * w, sz = (nz + kz) * w;
-  double dx, dy, dz;
-  if (fv.diag) {
-    dx = fs.m[0] * sx;
-    dy = fs.m[4] * sy;
-    dz = fs.m[8] * sz;
-  } else {
-    dx = fma(fs.m[2], sz, fma(fs.m[1], sy, fs.m[0] * sx));
-    dy = fma(fs.m[5], sz, fma(fs.m[4], sy, fs.m[3] * sx));
-    dz = fma(fs.m[8], sz, fma(fs.m[7], sy, fs.m[6] * sx));
-  }
+  const double dx = fma(fs.m[2], sz, fma(fs.m[1], sy, fs.m[0] * sx));
+  const double dy = fma(fs.m[5], sz, fma(fs.m[4], sy, fs.m[3] * sx));
+  const double dz = fma(fs.m[8], sz, fma(fs.m[7], sy, fs.m[6] * sx));
   px += dx;
   py += dy;
   pz += dz;

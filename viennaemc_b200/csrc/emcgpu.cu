@@ -12,6 +12,7 @@
 
 #include "emcgpu_internal.cuh"
 #include "emc_bulk_defer.cuh"
+#include "emc_bulk_split.cuh"
 
 using namespace emc;
 
@@ -108,6 +109,29 @@ void fillBulkParams(emcgpu_ctx *ctx, BulkParams &P) {
   emc::fillGrain(ctx, P);
 }
 
+// Launch-uniform flight constants of every valley (FlightConst, emc_device.cuh).  Plain IEEE products and quotients on
+// the host (this file is compiled with -ffp-contract=off): every kernel of a launch reads the same numbers.
+void buildFlightConsts(const emcgpu_ctx *ctx, BulkParams &P) {
+  for (int v = 0; v < ctx->hModel.nValleys && v < EMCGPU_MAX_VALLEYS; v++) {
+    const DevValley &dv = ctx->hModel.valleys[v];
+    FlightConst &f = P.fc[v];
+    f.fE = dv.nonParabolic ? dv.fE : 2.0 * dv.fE;
+    f.c2a = 2.0 * dv.alpha * f.fE;
+    f.inv2a = dv.nonParabolic && dv.alpha != 0.0 ? 1.0 / (2.0 * dv.alpha) : 0.0;
+    const double force[3] = {P.force.x, P.force.y, P.force.z}, dir[3] = {P.dir.x, P.dir.y, P.dir.z};
+    f.KP = kHbar / (2.0 * dv.mCond);
+    f.K2 = f.KP * P.dt;
+    for (int i = 0; i < 3; i++) {
+      f.Fh[i] = force[i] / kHbar;
+      f.G[i] = f.Fh[i] * P.dt;
+      f.KV[i] = dir[i] * (2.0 * f.KP);
+      f.K4[i] = f.KV[i] / f.K2;
+    }
+    f.diag = dv.rotKind != ROT_GENERAL;
+    f.nonParabolic = dv.nonParabolic;
+  }
+}
+
 template <typename K>
 cudaError_t launchKernel(emcgpu_ctx *ctx, K kernel, const BulkParams &P, size_t smem, int grid,
                          int threads = kBulkThreads) {
@@ -143,6 +167,26 @@ size_t deferSmem(const emcgpu_ctx *ctx, int steps, bool tablesInSmem) {
                    ctx->hModel.tableDoubles, tablesInSmem, kDeferQueueWords);
   const size_t b = deferSmemBytes(L, steps, ctx->hModel.nValleys);
   return b <= (size_t)ctx->maxSmemOptin ? b : 0;
+}
+
+// K1d, several steps per launch pair: flight kernel + event kernel (emc_bulk_split.cuh)
+bool splitEligible(const emcgpu_ctx *ctx) {
+  const DevValley &v = ctx->hModel.valleys[0];
+  return ctx->mathMode == EMCGPU_MATH_FAST && ctx->hModel.nValleys == 1 && v.rotKind != ROT_GENERAL && v.nonParabolic &&
+         v.alpha > 0.0 && !ctx->grainOn;
+}
+size_t splitEventSmem(const emcgpu_ctx *ctx, int steps) {
+  const BulkSmem L(0, 1, (int)ctx->hMechs.size(), ctx->hModel.tableDoubles, false, 0);
+  const size_t b = splitEventSmemBytes(L, steps);
+  return b <= (size_t)ctx->maxSmemOptin ? b : 0;
+}
+cudaError_t launchSplit(emcgpu_ctx *ctx, const BulkParams &P, int gridFlight, int gridEvent, size_t smemEvent) {
+  const size_t smemFlight = SplitFlightSmem::bytes(P.nSteps);
+  cudaError_t e = ctx->optSplitPpl == 2 ? launchKernel(ctx, bulkFlightKernel<2>, P, smemFlight, gridFlight, kFlightThreads)
+                                        : launchKernel(ctx, bulkFlightKernel<4>, P, smemFlight, gridFlight, kFlightThreads);
+  if (e != cudaSuccess) return e;
+  return ctx->rngMode == RNG_PHILOX ? launchKernel(ctx, bulkEventKernel<RNG_PHILOX>, P, smemEvent, gridEvent, kEventThreads)
+                                    : launchKernel(ctx, bulkEventKernel<RNG_REPLAY>, P, smemEvent, gridEvent, kEventThreads);
 }
 
 // K1a, one step per launch
@@ -268,7 +312,7 @@ void emcgpu_destroy(emcgpu_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (DeviceBuffer *b : {&ctx->dModel, &ctx->dMechs, &ctx->dTables, &ctx->dEnsemble, &ctx->dDraws,
                           &ctx->dOffsets, &ctx->dCursor, &ctx->dObs, &ctx->dStatus, &ctx->dEvents,
-                          &ctx->dEvCount, &ctx->dSlices})
+                          &ctx->dEvCount, &ctx->dSlices, &ctx->dFrozen, &ctx->dClaim, &ctx->dBathCounts, &ctx->dBathCum, &ctx->dGrain})
     b->release();
   if (ctx->copyIn) cudaStreamDestroy(ctx->copyIn);
   if (ctx->copyOut) cudaStreamDestroy(ctx->copyOut);
@@ -328,9 +372,14 @@ int emcgpu_set_option(emcgpu_ctx *ctx, const char *name, int64_t value) {
     return EMCGPU_OK;
   }
   if (!strcmp(name, "multi_kernel")) {
-    if (value != 0 && value != 1 && value != 2)
-      return fail(ctx, EMCGPU_E_INVALID, "multi_kernel must be 0 (deferred events when the ensemble is large), 1 (in place) or 2 (deferred events always)");
+    if (value < 0 || value > 3)
+      return fail(ctx, EMCGPU_E_INVALID, "multi_kernel must be 0 (flight + event kernels / deferred events when the ensemble is large), 1 (in place), 2 (deferred events always) or 3 (flight + event kernels always, where the model allows)");
     ctx->optMultiKernel = (int)value;
+    return EMCGPU_OK;
+  }
+  if (!strcmp(name, "split_ppl")) {
+    if (value != 2 && value != 4) return fail(ctx, EMCGPU_E_INVALID, "split_ppl must be 2 or 4 (particles per lane of the flight kernel)");
+    ctx->optSplitPpl = (int)value;
     return EMCGPU_OK;
   }
   return fail(ctx, EMCGPU_E_INVALID, "unknown option '%s'", name);
@@ -713,13 +762,46 @@ int emcgpu_bulk_step_device(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPer
   BulkParams P;
   fillBulkParams(ctx, P);
   P.dt = dt;
+  buildFlightConsts(ctx, P);
   if (ctx->n >= (int64_t)1 << 32) return fail(ctx, EMCGPU_E_CAPACITY, "at most 2^32-1 particles per context");
   for (int done = 0; done < nSteps;) {
     int chunk = std::min(stepsPerLaunch, nSteps - done);
+    // several steps per launch, plain model: flight kernel + event kernel (K1d) for ensembles that fill the machine
+    const int ppl = ctx->optSplitPpl == 2 ? 2 : 4;
+    const bool split = chunk > 1 && splitEligible(ctx) &&
+                       (ctx->optMultiKernel == 3 ||
+                        (ctx->optMultiKernel == 0 && ctx->n / (32 * ppl) >= (int64_t)ctx->smCount * (kFlightThreads / 32)));
+    if (split) {
+      chunk = std::min(chunk, kSplitMaxSteps);
+      size_t smemEvent = 0;
+      while (chunk > 1 && ((smemEvent = splitEventSmem(ctx, chunk)) == 0 ||
+                           SplitFlightSmem::bytes(chunk) > (size_t)ctx->maxSmemOptin))
+        chunk--;
+      if (chunk > 1 && smemEvent) {
+        const size_t flagBytes = ((size_t)ctx->n + 255) & ~size_t(255);
+        CUDA_TRY(ctx, ctx->dFrozen.ensure(flagBytes));
+        CUDA_TRY(ctx, ctx->dClaim.ensure(256));
+        P.frozen = ctx->dFrozen.as<uint8_t>();
+        P.claim = ctx->dClaim.as<unsigned>();
+        P.nSteps = chunk;
+        P.step0 = ctx->nextStep + done;
+        P.obs = obsDevice + (size_t)done * nV * 3;
+        P.tablesInSmem = 0;
+        const int64_t nChunks = ctx->n / (32 * ppl);
+        const int gridFlight = (int)std::max<int64_t>(1, std::min<int64_t>((nChunks + kFlightThreads / 32 - 1) / (kFlightThreads / 32), ctx->smCount));
+        const int64_t claims = (ctx->n + kEventClaim - 1) / kEventClaim;
+        const int gridEvent = (int)std::max<int64_t>(1, std::min<int64_t>((claims + kEventThreads / 32 - 1) / (kEventThreads / 32), ctx->smCount));
+        cudaError_t e = launchSplit(ctx, P, gridFlight, gridEvent, smemEvent);
+        if (e != cudaSuccess) return fail(ctx, EMCGPU_E_CUDA, "bulk step launch failed: %s", cudaGetErrorString(e));
+        done += chunk;
+        continue;
+      }
+      chunk = std::min(stepsPerLaunch, nSteps - done);
+    }
     // several steps per launch: deferred-event kernel (K1c) for ensembles that fill the machine
     const int64_t nChunks = ctx->n / kDeferChunk;
     const bool defer = chunk > 1 && !ctx->grainOn &&
-                       (ctx->optMultiKernel == 2 || (ctx->optMultiKernel == 0 && nChunks >= (int64_t)ctx->smCount * kDeferWarps));
+                       (ctx->optMultiKernel >= 2 || (ctx->optMultiKernel == 0 && nChunks >= (int64_t)ctx->smCount * kDeferWarps));
     if (defer) chunk = std::min(chunk, kDeferMaxSteps);
     P.nSteps = chunk;
     P.step0 = ctx->nextStep + done;

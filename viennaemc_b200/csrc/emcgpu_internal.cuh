@@ -46,7 +46,8 @@ struct emcgpu_ctx {
   int optKernel = 0;       // one-step kernel: 0 = TMA pipeline when it fits, 1 = plain streaming kernel
   int optStages = 0;       // cap on the TMA ring depth (0 = as many as fit)
   int optDeferTablesSmem = 0; // K1c: 1 = stage the rate tables in shared memory (default: read them through L1/L2)
-  int optMultiKernel = 0;  // several steps per launch: 0 = deferred events (K1c) when eligible, 1 = in-place (K1b)
+  int optMultiKernel = 0;  // several steps per launch: 0 = auto (K1d / K1c when the ensemble fills the machine), 1 = in place (K1b), 2 = K1c, 3 = K1d
+  int optSplitPpl = 4;     // K1d flight kernel: particles per lane (2 or 4)
   int optTablesGlobal = 0; // 1 = leave the rate tables in global memory / L2 (more ring stages)
   int optSorKernel = 0;    // 0 = row-per-thread wavefront when it fits, 1 = hyperplane loop
   int optSorOrder = 0;     // 0 = the reference's lexicographic order (bit-identical iterates), 1 = red-black
@@ -96,6 +97,7 @@ struct emcgpu_ctx {
 
   // outputs
   emc::DeviceBuffer dObs, dStatus, dEvents, dEvCount;
+  emc::DeviceBuffer dFrozen, dClaim; // split step (K1d): byte per particle, claim counter of the event kernel
   int64_t evCap = 0;
 
   // device-run path (emcgpu_device.cu), created by emcgpu_device_configure
