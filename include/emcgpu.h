@@ -167,9 +167,11 @@ int emcgpu_synchronize(emcgpu_ctx *ctx);
  * are the reference's), 1: red-black ordering (same equation and stopping rule, parallel, converges to
  * the same potential within the solver's accuracy); "sor_kernel" = 1 forces the general hyperplane
  * form of the lexicographic solver (no effect on results); "multi_kernel": kernel of emcgpu_bulk_step*
- * with stepsPerLaunch > 1 -- 0 (default): deferred scattering events (up to 8 steps per launch) for
- * ensembles that fill the GPU, events in place otherwise; 1: always in place; 2: always deferred
- * (no effect on results: the trajectories are bit-identical); "defer_tables_smem" = 1: the deferred-event kernel
+ * with stepsPerLaunch > 1 -- 0 (default): for ensembles that fill the GPU the flight + event kernel pair (up to 24 steps
+ * per launch pair; FAST arithmetic, one non-parabolic valley with signed-permutation rotations) or else the deferred-event
+ * kernel (up to 8 steps per launch), events in place otherwise; 1: always in place; 2: always deferred; 3: always the
+ * flight + event pair where the model allows (no effect on results: the trajectories are bit-identical);
+ * "split_ppl" = 2 | 4: particles per lane of the flight kernel; "kernel_timing" = 1: see emcgpu_kernel_times; "defer_tables_smem" = 1: the deferred-event kernel
  * stages the rate tables in shared memory instead of reading them through L1/L2 (slower, no effect on results) */
 int emcgpu_set_option(emcgpu_ctx *ctx, const char *name, int64_t value);
 
@@ -249,6 +251,18 @@ int emcgpu_bulk_step(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPerLaunch,
  * on the context's stream. */
 int emcgpu_bulk_step_device(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPerLaunch,
                             double *obsDevice);
+/* Look-ahead for drivers that call one step at a time (basicBulkParticleHandler::moveParticles(dt),
+ * examples/bulkSimulation/bulkSimulation.cpp:150-157): advances nSteps like emcgpu_bulk_step AND keeps the ensemble as it
+ * was before the call, so that a host which turns out to need the state of an earlier step can emcgpu_bulk_rewind and
+ * step again (the Philox streams are keyed by particle id and step: the same steps give the same trajectories).  With
+ * the flight / event kernels the first flight launch simply writes a second set of streams (no copy); other kernels copy
+ * the ensemble device-to-device first.  Philox streams only, no grain clocks.  Doubles the device memory of the ensemble. */
+int emcgpu_bulk_step_ahead(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPerLaunch, double *obs);
+/* back to the ensemble and step index before the last emcgpu_bulk_step_ahead (valid once, and only directly after it) */
+int emcgpu_bulk_rewind(emcgpu_ctx *ctx);
+/* with emcgpu_set_option("kernel_timing", 1): device time (cudaEvents on the launching stream) and launch counts of the
+ * flight kernel [0], the event kernel [1] and all other bulk kernels [2] since the last reset; synchronises */
+int emcgpu_kernel_times(emcgpu_ctx *ctx, double *ms, int64_t *launches, int reset);
 /* the same nSteps x { moveParticles ; observables } for an ensemble that lives in HOST memory (soa / packed as
  * emcgpu_set_ensemble, updated IN PLACE; pinned memory makes the copies asynchronous): the ensemble is cut into
  * slices of sliceParticles (<= 0: about n/8) and slice i runs its nSteps steps while slice i+1 is copied to the

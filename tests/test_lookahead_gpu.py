@@ -1,0 +1,92 @@
+"""GPU tests of the look-ahead that lets the reference's one-step-per-call driver loop
+(examples/bulkSimulation/bulkSimulation.cpp:150-157: moveParticles(dt), getAvgEnergy, getAvgDriftVelocity,
+getValleyOccupationProbability per time step) run on the several-steps-per-launch kernels:
+
+  * C ABI: emcgpu_bulk_step_ahead advances like emcgpu_bulk_step and keeps the ensemble it started from;
+    emcgpu_bulk_rewind + stepping the first k steps again gives bit for bit the state of a run that only ever did k steps
+    (flight + event kernels: the first flight launch writes a second set of streams; other kernels copy first);
+  * drop-in handler: the driver's results do not depend on the look-ahead depth, also when the driver asks for the
+    ensemble in the middle of a look-ahead window (handler.print) -- the handler rewinds and repeats the served steps.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import download_ensemble, upload_model
+from oracle import pyoracle as po
+from scenarios import build_si
+from viennaemc_b200 import capi
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "viennaemc_b200", "bin")
+FIELDS = po.Ensemble.F64[:5] + po.Ensemble.F64[6:] + po.Ensemble.I32  # everything but the never-read grain clock
+
+
+def _ctx(gpu_ctx_factory, m, n, box, multi_kernel):
+    ctx = gpu_ctx_factory()
+    ctx.set_option("multi_kernel", multi_kernel)
+    upload_model(ctx, m)
+    ctx.generate_bulk_ensemble(n, box, 300.0, 0, seed=21)
+    ctx.rng_philox(77)
+    ctx.bulk_configure(box, [-1, 0, 0], 1e6, math_mode=capi.MATH_FAST)
+    ctx.set_step_index(1)
+    return ctx
+
+
+@pytest.mark.parametrize("multi_kernel,n", [(3, 200_003), (1, 30_011), (2, 70_001), (0, 3_000_017)],
+                         ids=["split", "inplace", "deferred", "auto-large"])
+def test_step_ahead_then_rewind_reproduces_the_earlier_state(gpu_ctx_factory, multi_kernel, n):
+    m = build_si()
+    box = [1e-6] * 3
+    dt, ahead, served = 1e-15, 24, 9
+    a = _ctx(gpu_ctx_factory, m, n, box, multi_kernel)
+    obs_ahead = a.bulk_step_ahead(dt, ahead, ahead)
+    assert a.L.emcgpu_get_step_index(a.h) == 1 + ahead
+    full = download_ensemble(a)  # the ensemble after all the steps the device ran ahead
+    a.bulk_rewind()
+    assert a.L.emcgpu_get_step_index(a.h) == 1
+    obs_again = a.bulk_step(dt, served, served)
+    part = download_ensemble(a)
+    # the same steps without any look-ahead
+    b = _ctx(gpu_ctx_factory, m, n, box, multi_kernel)
+    obs_b = b.bulk_step(dt, ahead, ahead)
+    ref_full = download_ensemble(b)
+    c = _ctx(gpu_ctx_factory, m, n, box, multi_kernel)
+    obs_c = c.bulk_step(dt, served, served)
+    ref_part = download_ensemble(c)
+    for f in FIELDS:
+        assert np.array_equal(getattr(full, f), getattr(ref_full, f)), f
+        assert np.array_equal(getattr(part, f), getattr(ref_part, f)), f
+    assert np.array_equal(obs_ahead[:, :, 2], obs_b[:, :, 2])
+    assert np.allclose(obs_ahead, obs_b, rtol=1e-12) and np.allclose(obs_again, obs_c, rtol=1e-12)
+    assert np.allclose(obs_ahead[:served], obs_again, rtol=1e-12)  # what was handed out ahead is what the steps give
+    # a second rewind has nothing to go back to
+    with pytest.raises(capi.EmcGpuError):
+        a.bulk_rewind()
+    for x in (a, b, c):
+        x.close()
+
+
+def _run_driver(tmp, prefix, *extra):
+    r = subprocess.run([os.path.join(BIN, "bulkSimulation"), "--seed", "11", "--particles", "20000", "--steps", "150",
+                        "--dt", "1e-15", "--prefix", prefix, *extra], cwd=tmp, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = {k: np.loadtxt(os.path.join(tmp, prefix + k + ".txt")) for k in ("AvgEnergy", "AvgDriftVelocity",
+                                                                          "valleyOccupation")}
+    return out
+
+
+def test_driver_results_do_not_depend_on_the_lookahead(tmp_path):
+    tmp = str(tmp_path)
+    base = _run_driver(tmp, "la1", "--lookahead", "1", "--print-at", "37")
+    for la in ("16", "7", "24"):
+        got = _run_driver(tmp, "la" + la, "--lookahead", la, "--print-at", "37")
+        for k, ref in base.items():
+            assert got[k].shape == ref.shape == (151, 2)
+            assert np.allclose(got[k], ref, rtol=1e-5 if k != "valleyOccupation" else 0, atol=0), (la, k)  # 6 digits in the files
+        # the ensemble the driver printed in the middle of a look-ahead window is the ensemble of THAT step
+        with open(os.path.join(tmp, "la1Electrons37.txt")) as f, open(os.path.join(tmp, f"la{la}Electrons37.txt")) as g:
+            assert f.read() == g.read(), la

@@ -97,6 +97,9 @@ def load():
     L.emcgpu_bulk_run_host.argtypes = [vp, C.c_int64, C.POINTER(_DP), C.POINTER(C.c_uint32), C.c_int64, C.c_double,
                                        C.c_int, C.c_int, C.c_int64, _DP]
     L.emcgpu_bulk_step_device.argtypes = [vp, C.c_double, C.c_int, C.c_int, vp]
+    L.emcgpu_bulk_step_ahead.argtypes = [vp, C.c_double, C.c_int, C.c_int, _DP]
+    L.emcgpu_bulk_rewind.argtypes = [vp]
+    L.emcgpu_kernel_times.argtypes = [vp, _DP, C.POINTER(C.c_int64), C.c_int]
     L.emcgpu_bulk_observables.argtypes = [vp, _DP]
     L.emcgpu_set_step_index.argtypes = [vp, C.c_int64]
     L.emcgpu_get_step_index.argtypes = [vp]
@@ -143,7 +146,7 @@ EXPORTED_SYMBOLS = [
     "emcgpu_set_stream", "emcgpu_synchronize", "emcgpu_set_option", "emcgpu_set_valleys", "emcgpu_set_tables", "emcgpu_set_grain", "emcgpu_set_grain_clock", "emcgpu_get_grain_clock", "emcgpu_set_phonon_baths", "emcgpu_get_phonon_counts", "emcgpu_set_ensemble",
     "emcgpu_get_ensemble", "emcgpu_ensemble_size", "emcgpu_generate_bulk_ensemble",
     "emcgpu_ensemble_device_ptrs", "emcgpu_rng_philox", "emcgpu_rng_replay", "emcgpu_bulk_configure",
-    "emcgpu_bulk_step", "emcgpu_bulk_run_host", "emcgpu_bulk_step_device", "emcgpu_bulk_observables", "emcgpu_set_step_index",
+    "emcgpu_bulk_step", "emcgpu_bulk_run_host", "emcgpu_bulk_step_device", "emcgpu_bulk_step_ahead", "emcgpu_bulk_rewind", "emcgpu_kernel_times", "emcgpu_bulk_observables", "emcgpu_set_step_index",
     "emcgpu_get_step_index", "emcgpu_event_log_enable", "emcgpu_event_log_read",
     "emcgpu_device_configure", "emcgpu_device_set_surface", "emcgpu_device_set_particle_kind", "emcgpu_device_set_sharding", "emcgpu_device_set_grid", "emcgpu_device_get_grid", "emcgpu_device_reserve",
     "emcgpu_device_poisson", "emcgpu_device_efield", "emcgpu_device_assign", "emcgpu_device_concentration",
@@ -325,6 +328,23 @@ class Context:
         self._chk(self.L.emcgpu_bulk_step(self.h, dt, n_steps, steps_per_launch,
                                           obs.ctypes.data_as(_DP) if want_obs else None))
         return obs
+
+    def bulk_step_ahead(self, dt, n_steps, steps_per_launch):
+        """like bulk_step, and the ensemble as it was before the call survives (see bulk_rewind)"""
+        obs = np.zeros((n_steps, self.n_valleys, 3))
+        self._chk(self.L.emcgpu_bulk_step_ahead(self.h, dt, n_steps, steps_per_launch, obs.ctypes.data_as(_DP)))
+        return obs
+
+    def bulk_rewind(self):
+        self._chk(self.L.emcgpu_bulk_rewind(self.h))
+
+    def kernel_times(self, reset=True):
+        """(ms, launches) of the flight kernel, the event kernel and the other bulk kernels (option kernel_timing)"""
+        ms = np.zeros(3)
+        n = np.zeros(3, dtype=np.int64)
+        self._chk(self.L.emcgpu_kernel_times(self.h, ms.ctypes.data_as(_DP), n.ctypes.data_as(C.POINTER(C.c_int64)),
+                                             1 if reset else 0))
+        return ms, n
 
     def bulk_run_host(self, streams, packed, dt, n_steps, steps_per_launch=8, slice_particles=0, particle_id_base=0,
                       want_obs=True):

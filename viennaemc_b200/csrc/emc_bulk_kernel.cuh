@@ -54,6 +54,9 @@ struct BulkParams {
   // claim counter of the event kernel
   uint8_t *frozen;
   unsigned *claim;
+  // flight kernel out of place (emcgpu_bulk_step_ahead: the input ensemble stays as it was): nullptr = in place
+  double *streamOut[EMCGPU_N_STREAMS];
+  uint32_t *packedOut;
 };
 
 // emcGrainScatterMechanism::scatterParticle (include/emcGrainScatterMechanism.hpp:40-77) + emcParticleType::getNewGrainTau

@@ -27,17 +27,19 @@
 namespace emc {
 
 constexpr int kSplitMaxSteps = 24;     // time steps per launch pair (shared memory of the per-thread observable slots)
-constexpr int kFlightThreads = 512;    // flight kernel: 16 warps x PPL particles per lane
-constexpr int kEventThreads = 512;     // event kernel
+constexpr int kFlightThreadsAlone = 512; // flight kernel: 16 warps x PPL particles per lane
+constexpr int kEventThreadsAlone = 512;  // event kernel
 constexpr int kEventScan = 256;        // bytes of the frozen array a warp scans per refill (8 per lane)
 constexpr int kEventListCap = 32 + kEventScan; // a refill starts with fewer than 32 entries
 constexpr int kEventDense = 12;        // lanes still busy after an event step from which the batch goes on in place
 constexpr int64_t kEventClaim = 8192;  // particles per claim of a warp of the event kernel
 
 struct SplitFlightSmem {
-  // [nSteps][2][kFlightThreads] doubles, then the Herring-Vogt factors [EMCGPU_MAX_SUBVALLEYS][4], then the control word
-  static __host__ __device__ size_t obsBytes(int nSteps) { return (size_t)nSteps * 2 * kFlightThreads * sizeof(double); }
-  static __host__ __device__ size_t bytes(int nSteps) { return obsBytes(nSteps) + EMCGPU_MAX_SUBVALLEYS * 4 * sizeof(double) + 16; }
+  // [nSteps][2][threads] doubles, then the Herring-Vogt factors [EMCGPU_MAX_SUBVALLEYS][4], then the control word
+  static __host__ __device__ size_t obsBytes(int nSteps, int threads) { return (size_t)nSteps * 2 * threads * sizeof(double); }
+  static __host__ __device__ size_t bytes(int nSteps, int threads) {
+    return obsBytes(nSteps, threads) + EMCGPU_MAX_SUBVALLEYS * 4 * sizeof(double) + 16;
+  }
 };
 
 // signed compare of the bit patterns: for finite doubles with b >= 0 exactly (a < b), including a < 0 and a = -0
@@ -61,24 +63,29 @@ template <> struct VecLd<2> {
     const uint2 t = __ldcs(reinterpret_cast<const uint2 *>(p));
     v[0] = t.x; v[1] = t.y;
   }
+  static __device__ __forceinline__ void stw(uint32_t *p, const uint32_t (&v)[2]) {
+    __stcs(reinterpret_cast<uint2 *>(p), make_uint2(v[0], v[1]));
+  }
   static __device__ __forceinline__ void stFrozen(uint8_t *p, uint32_t f) { *reinterpret_cast<uint16_t *>(p) = (uint16_t)f; }
 };
 template <> struct VecLd<4> {
   static __device__ __forceinline__ void ld(const double *p, double (&v)[4]) { VecIO<4>::ld(p, v); }
   static __device__ __forceinline__ void st(double *p, const double (&v)[4]) { VecIO<4>::st(p, v); }
   static __device__ __forceinline__ void ldw(const uint32_t *p, uint32_t (&v)[4]) { VecIO<4>::ldw(p, v); }
+  static __device__ __forceinline__ void stw(uint32_t *p, const uint32_t (&v)[4]) { VecIO<4>::stw(p, v); }
   static __device__ __forceinline__ void stFrozen(uint8_t *p, uint32_t f) { *reinterpret_cast<uint32_t *>(p) = f; }
 };
 
 // ---------------------------------------------------------------------------------------------------------------
 // Flight kernel.  Applies to FAST arithmetic, one non-parabolic valley whose sub-valley rotations are signed
 // permutations (the Si / Ga2O3 bulk models); everything else runs K1c.
-template <int PPL>
-__global__ void __launch_bounds__(kFlightThreads, 1) bulkFlightKernel(const __grid_constant__ BulkParams P) {
+// AXIS: the device axis of a field along a coordinate axis (v.Ê has one term), -1 = any direction.
+template <int PPL, int AXIS, int kFlightThreads>
+__device__ __forceinline__ void flightRole(const BulkParams &P, const int cta, const int nCta) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   const int nSteps = P.nSteps;
   double *obsT = reinterpret_cast<double *>(smemRaw);
-  double *aTab = reinterpret_cast<double *>(smemRaw + SplitFlightSmem::obsBytes(nSteps));
+  double *aTab = reinterpret_cast<double *>(smemRaw + SplitFlightSmem::obsBytes(nSteps, kFlightThreads));
   unsigned *nextChunk = reinterpret_cast<unsigned *>(aTab + EMCGPU_MAX_SUBVALLEYS * 4);
   const int tid = threadIdx.x, lane = tid & 31;
   for (int s = 0; s < 2 * nSteps; s++) obsT[s * kFlightThreads + tid] = 0.0;
@@ -93,11 +100,12 @@ __global__ void __launch_bounds__(kFlightThreads, 1) bulkFlightKernel(const __gr
   }
   if (tid == 0) {
     *nextChunk = 0;
-    if (blockIdx.x == 0) *P.claim = 0; // the event kernel of this launch pair starts claiming at 0
+    if (cta == 0) *P.claim = 0; // the event kernel of this launch pair starts claiming at 0
   }
   __syncthreads();
   // launch constants: operands from the constant bank
   const FlightConst &f = P.fc[0];
+  double *const *const out = P.packedOut ? P.streamOut : P.stream; // out of place: the input ensemble is left as it was
   const double dt = P.dt;
   const long long dtBits = __double_as_longlong(dt);
   const uint32_t hiBx = (uint32_t)__double2hiint(P.box.x), hiBy = (uint32_t)__double2hiint(P.box.y),
@@ -109,7 +117,7 @@ __global__ void __launch_bounds__(kFlightThreads, 1) bulkFlightKernel(const __gr
     unsigned k = 0;
     if (lane == 0) k = atomicAdd(nextChunk, 1u);
     k = __shfl_sync(0xffffffffu, k, 0);
-    return (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
+    return (int64_t)cta + (int64_t)k * nCta;
   };
   auto prefetchChunk = [&](int64_t ch) {
     if (ch >= nChunks) return;
@@ -141,6 +149,7 @@ __global__ void __launch_bounds__(kFlightThreads, 1) bulkFlightKernel(const __gr
       VecLd<PPL>::ld(P.stream[EMCGPU_Y] + i0, py);
       VecLd<PPL>::ld(P.stream[EMCGPU_Z] + i0, pz);
       VecLd<PPL>::ldw(P.packed + i0, w);
+      if (P.packedOut) VecLd<PPL>::stw(P.packedOut + i0, w);
 #pragma unroll
       for (int j = 0; j < PPL; j++) {
         const double *a = aTab + 4 * ((w[j] >> 8) & 0xffu);
@@ -173,7 +182,10 @@ __global__ void __launch_bounds__(kFlightThreads, 1) bulkFlightKernel(const __gr
         if (j == 0) sumT = live[j] ? t : 0.0;
         else addIf(sumT, t, live[j]);
         addIf(tau[j], -dt, live[j]);
-        const double v = flightVelocityDt(f.K4[0], f.K4[1], f.K4[2], kx[j], ky[j], kz[j], o);
+        const double v = AXIS == 0   ? (f.K4[0] * kx[j]) * o.w0
+                         : AXIS == 1 ? (f.K4[1] * ky[j]) * o.w1
+                         : AXIS == 2 ? (f.K4[2] * kz[j]) * o.w2
+                                     : flightVelocityDt(f.K4[0], f.K4[1], f.K4[2], kx[j], ky[j], kz[j], o);
         if (j == 0) sumV = v;
         else sumV += v;
       }
@@ -204,20 +216,26 @@ __global__ void __launch_bounds__(kFlightThreads, 1) bulkFlightKernel(const __gr
       o.r = rsqrtNormal(o.x);
       en[j] = flightEnergy(f.fE, o);
     }
-    VecLd<PPL>::st(P.stream[EMCGPU_KX] + i0, kx);
-    VecLd<PPL>::st(P.stream[EMCGPU_KY] + i0, ky);
-    VecLd<PPL>::st(P.stream[EMCGPU_KZ] + i0, kz);
-    VecLd<PPL>::st(P.stream[EMCGPU_ENERGY] + i0, en);
-    VecLd<PPL>::st(P.stream[EMCGPU_TAU] + i0, tau);
-    VecLd<PPL>::st(P.stream[EMCGPU_X] + i0, px);
-    VecLd<PPL>::st(P.stream[EMCGPU_Y] + i0, py);
-    VecLd<PPL>::st(P.stream[EMCGPU_Z] + i0, pz);
+    VecLd<PPL>::st(out[EMCGPU_KX] + i0, kx);
+    VecLd<PPL>::st(out[EMCGPU_KY] + i0, ky);
+    VecLd<PPL>::st(out[EMCGPU_KZ] + i0, kz);
+    VecLd<PPL>::st(out[EMCGPU_ENERGY] + i0, en);
+    VecLd<PPL>::st(out[EMCGPU_TAU] + i0, tau);
+    VecLd<PPL>::st(out[EMCGPU_X] + i0, px);
+    VecLd<PPL>::st(out[EMCGPU_Y] + i0, py);
+    VecLd<PPL>::st(out[EMCGPU_Z] + i0, pz);
     VecLd<PPL>::stFrozen(P.frozen + i0, frz);
   }
   // the particles behind the last whole chunk are left to the event kernel, from step 0
-  if (blockIdx.x == 0) {
+  if (cta == 0) {
     const int64_t i = nChunks * kChunk + tid;
-    if (tid < kChunk && i < P.n) P.frozen[i] = 0;
+    if (tid < kChunk && i < P.n) {
+      P.frozen[i] = 0;
+      if (P.packedOut) {
+        for (int c = 0; c < EMCGPU_N_STREAMS; c++) P.streamOut[c][i] = P.stream[c][i];
+        P.packedOut[i] = P.packed[i];
+      }
+    }
   }
   __syncthreads();
   // ---- per-step sums of the CTA -> global: sum E = sum (S - 1) / (2 alpha) ----
@@ -233,7 +251,11 @@ __global__ void __launch_bounds__(kFlightThreads, 1) bulkFlightKernel(const __gr
     }
   }
   // one valley: every particle contributes to every step
-  if (blockIdx.x == 0 && tid < nSteps) atomicAdd(P.obs + tid * 3 + 2, (double)P.n);
+  if (cta == 0 && tid < nSteps) atomicAdd(P.obs + tid * 3 + 2, (double)P.n);
+}
+template <int PPL, int AXIS>
+__global__ void __launch_bounds__(kFlightThreadsAlone, 1) bulkFlightKernel(const __grid_constant__ BulkParams P) {
+  flightRole<PPL, AXIS, kFlightThreadsAlone>(P, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -243,8 +265,8 @@ struct EventWarpList {
   uint8_t step[kEventListCap];
 };
 
-template <int RNG_MODE>
-__global__ void __launch_bounds__(kEventThreads, 1) bulkEventKernel(const __grid_constant__ BulkParams P) {
+template <int RNG_MODE, int kEventThreads>
+__device__ __forceinline__ void eventRole(const BulkParams &P) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   __shared__ uint64_t tableBar;
   const int nSteps = P.nSteps;
@@ -375,10 +397,14 @@ __global__ void __launch_bounds__(kEventThreads, 1) bulkEventKernel(const __grid
     if (lane == 0 && a != 0.0) atomicAdd(P.obs + (r >> 1) * 3 + (r & 1), a);
   }
 }
+template <int RNG_MODE>
+__global__ void __launch_bounds__(kEventThreadsAlone, 1) bulkEventKernel(const __grid_constant__ BulkParams P) {
+  eventRole<RNG_MODE, kEventThreadsAlone>(P);
+}
 
-__host__ __device__ inline size_t splitEventSmemBytes(const BulkSmem &L, int nSteps) {
-  return ((L.total + 15) & ~size_t(15)) + (size_t)nSteps * 2 * kEventThreads * sizeof(double) +
-         (kEventThreads / 32) * sizeof(EventWarpList);
+__host__ __device__ inline size_t splitEventSmemBytes(const BulkSmem &L, int nSteps, int threads) {
+  return ((L.total + 15) & ~size_t(15)) + (size_t)nSteps * 2 * threads * sizeof(double) +
+         (threads / 32) * sizeof(EventWarpList);
 }
 
 } // namespace emc

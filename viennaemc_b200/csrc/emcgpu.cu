@@ -3,7 +3,9 @@
 // needs a CUDA device and fails with EMCGPU_E_CUDA otherwise.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
+#include <type_traits>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -132,12 +134,27 @@ void buildFlightConsts(const emcgpu_ctx *ctx, BulkParams &P) {
   }
 }
 
+// "kernel_timing": a pair of events around a launch, folded into per-kind totals by emcgpu_kernel_times
+cudaError_t timedBegin(emcgpu_ctx *ctx, int tag) {
+  if (!ctx->optTiming) return cudaSuccess;
+  emcgpu_ctx::TimedLaunch t{tag, nullptr, nullptr};
+  cudaError_t e = cudaEventCreate(&t.a);
+  if (e == cudaSuccess) e = cudaEventCreate(&t.b);
+  if (e == cudaSuccess) e = cudaEventRecord(t.a, ctx->stream);
+  if (e == cudaSuccess) ctx->timed.push_back(t);
+  return e;
+}
+void timedEnd(emcgpu_ctx *ctx) {
+  if (ctx->optTiming && !ctx->timed.empty()) cudaEventRecord(ctx->timed.back().b, ctx->stream);
+}
 template <typename K>
 cudaError_t launchKernel(emcgpu_ctx *ctx, K kernel, const BulkParams &P, size_t smem, int grid,
-                         int threads = kBulkThreads) {
+                         int threads = kBulkThreads, int tag = 2) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
+  if ((e = timedBegin(ctx, tag)) != cudaSuccess) return e;
   kernel<<<grid, threads, smem, ctx->stream>>>(P);
+  timedEnd(ctx);
   ctx->launches++;
   return cudaGetLastError();
 }
@@ -175,18 +192,93 @@ bool splitEligible(const emcgpu_ctx *ctx) {
   return ctx->mathMode == EMCGPU_MATH_FAST && ctx->hModel.nValleys == 1 && v.rotKind != ROT_GENERAL && v.nonParabolic &&
          v.alpha > 0.0 && !ctx->grainOn;
 }
-size_t splitEventSmem(const emcgpu_ctx *ctx, int steps) {
+size_t splitEventSmem(const emcgpu_ctx *ctx, int steps, int threads) {
   const BulkSmem L(0, 1, (int)ctx->hMechs.size(), ctx->hModel.tableDoubles, false, 0);
-  const size_t b = splitEventSmemBytes(L, steps);
-  return b <= (size_t)ctx->maxSmemOptin ? b : 0;
+  return splitEventSmemBytes(L, steps, threads);
 }
-cudaError_t launchSplit(emcgpu_ctx *ctx, const BulkParams &P, int gridFlight, int gridEvent, size_t smemEvent) {
-  const size_t smemFlight = SplitFlightSmem::bytes(P.nSteps);
-  cudaError_t e = ctx->optSplitPpl == 2 ? launchKernel(ctx, bulkFlightKernel<2>, P, smemFlight, gridFlight, kFlightThreads)
-                                        : launchKernel(ctx, bulkFlightKernel<4>, P, smemFlight, gridFlight, kFlightThreads);
+// a field along a coordinate axis: the drift-velocity observable of the flight kernel has one term
+int fieldAxis(const BulkParams &P) {
+  const double d[3] = {P.dir.x, P.dir.y, P.dir.z};
+  int axis = -1;
+  for (int i = 0; i < 3; i++)
+    if (d[i] != 0.0 && d[(i + 1) % 3] == 0.0 && d[(i + 2) % 3] == 0.0) axis = i;
+  return axis;
+}
+template <typename F> cudaError_t dispatchFlight(int ppl, int axis, F &&go) {
+  if (ppl == 2)
+    return axis == 0 ? go(std::integral_constant<int, 2>{}, std::integral_constant<int, 0>{})
+           : axis == 1 ? go(std::integral_constant<int, 2>{}, std::integral_constant<int, 1>{})
+           : axis == 2 ? go(std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{})
+                       : go(std::integral_constant<int, 2>{}, std::integral_constant<int, -1>{});
+  return axis == 0 ? go(std::integral_constant<int, 4>{}, std::integral_constant<int, 0>{})
+         : axis == 1 ? go(std::integral_constant<int, 4>{}, std::integral_constant<int, 1>{})
+         : axis == 2 ? go(std::integral_constant<int, 4>{}, std::integral_constant<int, 2>{})
+                     : go(std::integral_constant<int, 4>{}, std::integral_constant<int, -1>{});
+}
+// the streams of an ensemble of n particles inside one allocation: every stream starts on a 256-byte boundary
+void layoutStreams(void *basePtr, int64_t n, double **streams, uint32_t **packed) {
+  const size_t strideD = ((size_t)n * sizeof(double) + 255) & ~size_t(255);
+  unsigned char *base = static_cast<unsigned char *>(basePtr);
+  for (int s = 0; s < EMCGPU_N_STREAMS; s++) streams[s] = reinterpret_cast<double *>(base + strideD * s);
+  *packed = reinterpret_cast<uint32_t *>(base + strideD * EMCGPU_N_STREAMS);
+}
+size_t ensembleBytes(int64_t n) {
+  const size_t strideD = ((size_t)n * sizeof(double) + 255) & ~size_t(255);
+  const size_t strideP = ((size_t)n * sizeof(uint32_t) + 255) & ~size_t(255);
+  return strideD * EMCGPU_N_STREAMS + strideP;
+}
+// the resident ensemble and the look-ahead copy change places
+void swapEnsembles(emcgpu_ctx *ctx) {
+  std::swap(ctx->dEnsemble, ctx->dEnsembleAlt);
+  for (int s = 0; s < EMCGPU_N_STREAMS; s++) std::swap(ctx->dStream[s], ctx->dStreamAlt[s]);
+  std::swap(ctx->dPacked, ctx->dPackedAlt);
+}
+// one launch pair on the whole shard: flight kernel, then event kernel.  outOfPlace: the flight kernel writes the
+// look-ahead copy (which becomes the resident ensemble), the input stays as it was.
+cudaError_t launchSplit(emcgpu_ctx *ctx, BulkParams &P, bool outOfPlace) {
+  const int ppl = ctx->optSplitPpl == 2 ? 2 : 4;
+  const size_t smemFlight = SplitFlightSmem::bytes(P.nSteps, kFlightThreadsAlone);
+  const size_t smemEvent = splitEventSmem(ctx, P.nSteps, kEventThreadsAlone);
+  const int64_t nChunks = P.n / (32 * ppl);
+  const int warps = kFlightThreadsAlone / 32;
+  const int gridFlight = (int)std::max<int64_t>(1, std::min<int64_t>((nChunks + warps - 1) / warps, ctx->smCount));
+  const int64_t claims = (P.n + kEventClaim - 1) / kEventClaim;
+  const int gridEvent = (int)std::max<int64_t>(1, std::min<int64_t>((claims + warps - 1) / warps, ctx->smCount));
+  for (int s = 0; s < EMCGPU_N_STREAMS; s++) P.streamOut[s] = outOfPlace ? ctx->dStreamAlt[s] : nullptr;
+  P.packedOut = outOfPlace ? ctx->dPackedAlt : nullptr;
+  cudaError_t e = dispatchFlight(ppl, fieldAxis(P), [&](auto p, auto a) {
+    return launchKernel(ctx, bulkFlightKernel<decltype(p)::value, decltype(a)::value>, P, smemFlight, gridFlight,
+                        kFlightThreadsAlone, 0);
+  });
   if (e != cudaSuccess) return e;
-  return ctx->rngMode == RNG_PHILOX ? launchKernel(ctx, bulkEventKernel<RNG_PHILOX>, P, smemEvent, gridEvent, kEventThreads)
-                                    : launchKernel(ctx, bulkEventKernel<RNG_REPLAY>, P, smemEvent, gridEvent, kEventThreads);
+  if (outOfPlace) {
+    swapEnsembles(ctx);
+    for (int s = 0; s < EMCGPU_N_STREAMS; s++) P.stream[s] = ctx->dStream[s];
+    P.packed = ctx->dPacked;
+    P.packedOut = nullptr;
+  }
+  return ctx->rngMode == RNG_PHILOX
+             ? launchKernel(ctx, bulkEventKernel<RNG_PHILOX>, P, smemEvent, gridEvent, kEventThreadsAlone, 1)
+             : launchKernel(ctx, bulkEventKernel<RNG_REPLAY>, P, smemEvent, gridEvent, kEventThreadsAlone, 1);
+}
+// K steps of the whole shard with the flight / event kernels, `window` steps per launch pair
+int runSplit(emcgpu_ctx *ctx, BulkParams &P, int nSteps, int window, double *obsDevice, bool keep) {
+  const size_t flagBytes = ((size_t)ctx->n + 255) & ~size_t(255);
+  CUDA_TRY(ctx, ctx->dFrozen.ensure(flagBytes));
+  CUDA_TRY(ctx, ctx->dClaim.ensure(256));
+  P.frozen = ctx->dFrozen.as<uint8_t>();
+  P.claim = ctx->dClaim.as<unsigned>();
+  P.tablesInSmem = 0;
+  for (int done = 0; done < nSteps;) {
+    const int w = std::min(window, nSteps - done);
+    P.nSteps = w;
+    P.step0 = ctx->nextStep + done;
+    P.obs = obsDevice + (size_t)done * 3; // one valley
+    cudaError_t e = launchSplit(ctx, P, keep && done == 0);
+    if (e != cudaSuccess) return fail(ctx, EMCGPU_E_CUDA, "bulk step launch failed: %s", cudaGetErrorString(e));
+    done += w;
+  }
+  return EMCGPU_OK;
 }
 
 // K1a, one step per launch
@@ -246,6 +338,7 @@ int emc::allocEnsembleStreams(emcgpu_ctx *ctx, int64_t n) {
   ctx->dPacked = reinterpret_cast<uint32_t *>(base + strideD * EMCGPU_N_STREAMS);
   ctx->n = n;
   ctx->capacity = n;
+  ctx->rewindValid = false;
   return EMCGPU_OK;
 }
 namespace {
@@ -312,7 +405,7 @@ void emcgpu_destroy(emcgpu_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (DeviceBuffer *b : {&ctx->dModel, &ctx->dMechs, &ctx->dTables, &ctx->dEnsemble, &ctx->dDraws,
                           &ctx->dOffsets, &ctx->dCursor, &ctx->dObs, &ctx->dStatus, &ctx->dEvents,
-                          &ctx->dEvCount, &ctx->dSlices, &ctx->dFrozen, &ctx->dClaim, &ctx->dBathCounts, &ctx->dBathCum, &ctx->dGrain})
+                          &ctx->dEvCount, &ctx->dSlices, &ctx->dEnsembleAlt, &ctx->dFrozen, &ctx->dClaim, &ctx->dBathCounts, &ctx->dBathCum, &ctx->dGrain})
     b->release();
   if (ctx->copyIn) cudaStreamDestroy(ctx->copyIn);
   if (ctx->copyOut) cudaStreamDestroy(ctx->copyOut);
@@ -375,6 +468,10 @@ int emcgpu_set_option(emcgpu_ctx *ctx, const char *name, int64_t value) {
     if (value < 0 || value > 3)
       return fail(ctx, EMCGPU_E_INVALID, "multi_kernel must be 0 (flight + event kernels / deferred events when the ensemble is large), 1 (in place), 2 (deferred events always) or 3 (flight + event kernels always, where the model allows)");
     ctx->optMultiKernel = (int)value;
+    return EMCGPU_OK;
+  }
+  if (!strcmp(name, "kernel_timing")) {
+    ctx->optTiming = value != 0;
     return EMCGPU_OK;
   }
   if (!strcmp(name, "split_ppl")) {
@@ -750,7 +847,10 @@ int emcgpu_set_step_index(emcgpu_ctx *ctx, int64_t nextStep) {
 }
 int64_t emcgpu_get_step_index(const emcgpu_ctx *ctx) { return ctx ? ctx->nextStep : 0; }
 
-int emcgpu_bulk_step_device(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPerLaunch, double *obsDevice) {
+} // extern "C"
+namespace {
+// keep: the ensemble as it is now survives the call (emcgpu_bulk_step_ahead), see emcgpu_bulk_rewind
+int bulkStepDevice(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPerLaunch, double *obsDevice, bool keep) {
   if (int r = checkReady(ctx, true)) return r;
   if (!(dt > 0) || nSteps < 1 || !obsDevice) return fail(ctx, EMCGPU_E_INVALID, "bad step arguments");
   if (int r = bind(ctx)) return r;
@@ -764,40 +864,30 @@ int emcgpu_bulk_step_device(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPer
   P.dt = dt;
   buildFlightConsts(ctx, P);
   if (ctx->n >= (int64_t)1 << 32) return fail(ctx, EMCGPU_E_CAPACITY, "at most 2^32-1 particles per context");
+  // several steps per launch, plain model: flight kernel + event kernel (K1d) for ensembles that fill the machine
+  {
+    const int ppl = ctx->optSplitPpl == 2 ? 2 : 4;
+    const bool split = stepsPerLaunch > 1 && nSteps > 1 && splitEligible(ctx) &&
+                       (ctx->optMultiKernel == 3 ||
+                        (ctx->optMultiKernel == 0 && ctx->n / (32 * ppl) >= (int64_t)ctx->smCount * (kFlightThreadsAlone / 32)));
+    if (split) {
+      int window = std::min(stepsPerLaunch, kSplitMaxSteps);
+      while (window > 1 && std::max(SplitFlightSmem::bytes(window, kFlightThreadsAlone),
+                                    splitEventSmem(ctx, window, kEventThreadsAlone)) > (size_t)ctx->maxSmemOptin)
+        window--;
+      if (window > 1) {
+        if (int r = runSplit(ctx, P, nSteps, window, obsDevice, keep)) return r;
+        ctx->nextStep += nSteps;
+        return EMCGPU_OK;
+      }
+    }
+  }
+  if (keep) { // the other step kernels work in place: copy first
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dEnsembleAlt.ptr, ctx->dEnsemble.ptr, ensembleBytes(ctx->n), cudaMemcpyDeviceToDevice,
+                                  ctx->stream));
+  }
   for (int done = 0; done < nSteps;) {
     int chunk = std::min(stepsPerLaunch, nSteps - done);
-    // several steps per launch, plain model: flight kernel + event kernel (K1d) for ensembles that fill the machine
-    const int ppl = ctx->optSplitPpl == 2 ? 2 : 4;
-    const bool split = chunk > 1 && splitEligible(ctx) &&
-                       (ctx->optMultiKernel == 3 ||
-                        (ctx->optMultiKernel == 0 && ctx->n / (32 * ppl) >= (int64_t)ctx->smCount * (kFlightThreads / 32)));
-    if (split) {
-      chunk = std::min(chunk, kSplitMaxSteps);
-      size_t smemEvent = 0;
-      while (chunk > 1 && ((smemEvent = splitEventSmem(ctx, chunk)) == 0 ||
-                           SplitFlightSmem::bytes(chunk) > (size_t)ctx->maxSmemOptin))
-        chunk--;
-      if (chunk > 1 && smemEvent) {
-        const size_t flagBytes = ((size_t)ctx->n + 255) & ~size_t(255);
-        CUDA_TRY(ctx, ctx->dFrozen.ensure(flagBytes));
-        CUDA_TRY(ctx, ctx->dClaim.ensure(256));
-        P.frozen = ctx->dFrozen.as<uint8_t>();
-        P.claim = ctx->dClaim.as<unsigned>();
-        P.nSteps = chunk;
-        P.step0 = ctx->nextStep + done;
-        P.obs = obsDevice + (size_t)done * nV * 3;
-        P.tablesInSmem = 0;
-        const int64_t nChunks = ctx->n / (32 * ppl);
-        const int gridFlight = (int)std::max<int64_t>(1, std::min<int64_t>((nChunks + kFlightThreads / 32 - 1) / (kFlightThreads / 32), ctx->smCount));
-        const int64_t claims = (ctx->n + kEventClaim - 1) / kEventClaim;
-        const int gridEvent = (int)std::max<int64_t>(1, std::min<int64_t>((claims + kEventThreads / 32 - 1) / (kEventThreads / 32), ctx->smCount));
-        cudaError_t e = launchSplit(ctx, P, gridFlight, gridEvent, smemEvent);
-        if (e != cudaSuccess) return fail(ctx, EMCGPU_E_CUDA, "bulk step launch failed: %s", cudaGetErrorString(e));
-        done += chunk;
-        continue;
-      }
-      chunk = std::min(stepsPerLaunch, nSteps - done);
-    }
     // several steps per launch: deferred-event kernel (K1c) for ensembles that fill the machine
     const int64_t nChunks = ctx->n / kDeferChunk;
     const bool defer = chunk > 1 && !ctx->grainOn &&
@@ -882,6 +972,68 @@ int emcgpu_bulk_step_device(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPer
     done += chunk;
   }
   ctx->nextStep += nSteps;
+  return EMCGPU_OK;
+}
+} // namespace
+extern "C" {
+
+int emcgpu_bulk_step_device(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPerLaunch, double *obsDevice) {
+  if (ctx) ctx->rewindValid = false;
+  return bulkStepDevice(ctx, dt, nSteps, stepsPerLaunch, obsDevice, false);
+}
+
+int emcgpu_bulk_step_ahead(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPerLaunch, double *obs) {
+  if (int r = checkReady(ctx, true)) return r;
+  if (nSteps < 1) return fail(ctx, EMCGPU_E_INVALID, "nSteps must be >= 1");
+  if (ctx->rngMode != RNG_PHILOX || ctx->grainOn)
+    return fail(ctx, EMCGPU_E_INVALID, "emcgpu_bulk_step_ahead needs the Philox streams and carries no grain clocks");
+  if (int r = bind(ctx)) return r;
+  const size_t bytes = (size_t)nSteps * ctx->hModel.nValleys * 3 * sizeof(double);
+  CUDA_TRY(ctx, ctx->dObs.ensure(bytes));
+  CUDA_TRY(ctx, ctx->dEnsembleAlt.ensure(ctx->dEnsemble.bytes));
+  layoutStreams(ctx->dEnsembleAlt.ptr, ctx->n, ctx->dStreamAlt, &ctx->dPackedAlt);
+  const int64_t stepBefore = ctx->nextStep;
+  ctx->rewindValid = false;
+  if (int r = bulkStepDevice(ctx, dt, nSteps, stepsPerLaunch, static_cast<double *>(ctx->dObs.ptr), true)) return r;
+  ctx->rewindValid = true;
+  ctx->rewindStep = stepBefore;
+  if (obs) CUDA_TRY(ctx, cudaMemcpyAsync(obs, ctx->dObs.ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return checkStatusWord(ctx); // synchronises
+}
+
+int emcgpu_bulk_rewind(emcgpu_ctx *ctx) {
+  if (!ctx) return EMCGPU_E_INVALID;
+  if (!ctx->rewindValid) return fail(ctx, EMCGPU_E_INVALID, "nothing to rewind: the last step call was not emcgpu_bulk_step_ahead");
+  if (int r = bind(ctx)) return r;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  swapEnsembles(ctx);
+  ctx->nextStep = ctx->rewindStep;
+  ctx->rewindValid = false;
+  return EMCGPU_OK;
+}
+
+int emcgpu_kernel_times(emcgpu_ctx *ctx, double *ms, int64_t *launches, int reset) {
+  if (!ctx) return EMCGPU_E_INVALID;
+  if (int r = bind(ctx)) return r;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto &t : ctx->timed) {
+    float f = 0;
+    if (cudaEventElapsedTime(&f, t.a, t.b) == cudaSuccess && t.tag >= 0 && t.tag < 3) {
+      ctx->timedMs[t.tag] += f;
+      ctx->timedLaunches[t.tag]++;
+    }
+    cudaEventDestroy(t.a);
+    cudaEventDestroy(t.b);
+  }
+  ctx->timed.clear();
+  for (int k = 0; k < 3; k++) {
+    if (ms) ms[k] = ctx->timedMs[k];
+    if (launches) launches[k] = ctx->timedLaunches[k];
+    if (reset) {
+      ctx->timedMs[k] = 0;
+      ctx->timedLaunches[k] = 0;
+    }
+  }
   return EMCGPU_OK;
 }
 

@@ -67,6 +67,21 @@ struct emcgpu_ctx {
   emc::DeviceBuffer dEnsemble;
   double *dStream[EMCGPU_N_STREAMS] = {};
   uint32_t *dPacked = nullptr;
+  // emcgpu_bulk_step_ahead / emcgpu_bulk_rewind: the ensemble as it was before the last look-ahead call
+  emc::DeviceBuffer dEnsembleAlt;
+  double *dStreamAlt[EMCGPU_N_STREAMS] = {};
+  uint32_t *dPackedAlt = nullptr;
+  bool rewindValid = false;
+  int64_t rewindStep = 0;
+  // "kernel_timing": cudaEvents around the launches of the flight (0) and event (1) kernels, other kernels (2)
+  bool optTiming = false;
+  struct TimedLaunch {
+    int tag;
+    cudaEvent_t a, b;
+  };
+  std::vector<TimedLaunch> timed;
+  double timedMs[3] = {0, 0, 0};
+  int64_t timedLaunches[3] = {0, 0, 0};
 
   // slice ring of emcgpu_bulk_run_host (three slices: upload / advance / download)
   emc::DeviceBuffer dSlices;

@@ -7,6 +7,8 @@
 //   bulkSimulation [--particles N] [--field V/m] [--steps K] [--dt s] [--seed S]
 //                  [--steps-per-launch L] [--prefix name] [--temperature K] [--doping 1/m3]
 //                  [--grain-rate 1/s --grain-prob p]   (grain-boundary scattering, emcGrainScatterMechanism)
+//                  [--lookahead N]   time steps a moveParticles(dt) call runs ahead on the device (default 16, 1 = none)
+//                  [--print-at S]    write the ensemble after step S (handler.print, "<prefix>Electrons<S>.txt")
 //
 // --steps-per-launch > 1 uses the handler's fused entry point (several time steps per kernel
 // launch, particle state kept in registers in between); 1 is the reference's call pattern
@@ -30,7 +32,7 @@ using ParticleHandler = basicBulkParticleHandler<NumType, DeviceType>;
 
 int main(int argc, char **argv) {
   double particles = 12500, field = 1e6, dt = 1e-16, temperature = 300, doping = 1e23, grainRate = 0, grainProb = 0.5;
-  long steps = 40000, stepsPerLaunch = 1;
+  long steps = 40000, stepsPerLaunch = 1, lookahead = 0, printAt = -1;
   unsigned long seed = 0;
   std::string prefix = "bulkSimulation";
   for (int i = 1; i + 1 < argc; i += 2) {
@@ -42,6 +44,8 @@ int main(int argc, char **argv) {
     else if (key == "--seed") seed = std::stoul(val);
     else if (key == "--steps-per-launch") stepsPerLaunch = std::stol(val);
     else if (key == "--prefix") prefix = val;
+    else if (key == "--lookahead") lookahead = std::stol(val);
+    else if (key == "--print-at") printAt = std::stol(val);
     else if (key == "--temperature") temperature = std::stod(val);
     else if (key == "--doping") doping = std::stod(val);
     else if (key == "--grain-rate") grainRate = std::stod(val);
@@ -68,6 +72,8 @@ int main(int argc, char **argv) {
     particleTypes[0]->setGrainScatterMechanism(std::make_unique<emcGrainScatterMechanism<NumType>>(grainProb, grainRate));
 
   ParticleHandler handler(device, particleTypes, {-1, 0, 0}, field, seed);
+  if (lookahead > 0)
+    handler.setLookahead(lookahead);
   std::cout << "Creating Particles...\n";
   handler.generateInitialParticles();
   handler.printNrParticles();
@@ -85,6 +91,8 @@ int main(int argc, char **argv) {
       avgEnergy[s] = handler.getAvgEnergy(0);
       avgDriftVel[s] = handler.getAvgDriftVelocity(0);
       valleyOcc[s] = handler.getValleyOccupationProbability(0);
+      if (s == printAt)
+        handler.print(prefix, std::to_string(s));
     }
   } else {
     std::vector<double> series;

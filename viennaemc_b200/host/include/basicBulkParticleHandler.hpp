@@ -15,9 +15,17 @@
 //   * the ensemble lives in GPU memory as SoA streams (one emcgpu context per moved
 //     particle type); generateInitialParticles() creates it on the host with the
 //     reference's draw sequence (same seed -> same initial ensemble) and uploads it;
-//   * moveParticles(dt) is one launch of the bulk step kernel, which also reduces the
-//     per-valley observables of that step; getAvgEnergy / getAvgDriftVelocity /
+//   * moveParticles(dt) is a launch of the bulk step kernels, which also reduce the
+//     per-valley observables of every step; getAvgEnergy / getAvgDriftVelocity /
 //     getValleyOccupationProbability return those without another pass;
+//   * LOOK-AHEAD: the reference's driver loop calls moveParticles(dt) and the three getAvg* once per time step
+//     (bulkSimulation.cpp:150-157).  One step per call would pin the GPU to one launch and one host round trip per
+//     step, so a call runs `lookahead` steps at once (emcgpu_bulk_step_ahead, default 16, setLookahead()) and the next
+//     lookahead-1 calls -- and their getAvg* -- are served from the series that launch delivered.  Whatever needs the
+//     ensemble of the driver's current step (print, printVelocities, a new field, seed, table rebuild, ...) first
+//     rewinds to the state before the launch and repeats exactly the steps served so far: the random numbers are keyed
+//     by particle id and step, so this reproduces them bit for bit.  Types with phonon baths or a grain mechanism
+//     (per-step host feedback) keep one step per call;
 //   * random numbers in the step are counter-based Philox streams keyed by particle
 //     id and step (not one mt19937_64 per OpenMP thread), seeded from the handler seed;
 //   * nothing is moved on the CPU: without a CUDA device, or with a mechanism /
@@ -61,6 +69,10 @@ private:
     bool grain = false;                           // the type carries a grain mechanism: clocks live on the device
     SizeType tableVersion = 0;                    // version of the scatter tables on the device
     std::vector<emcPhononBath<T> *> phononBaths;  // baths fed by the polar-optical mechanisms of the type
+    // look-ahead: per-step sums of the steps the device has already done, and how many of them the driver has asked for
+    std::vector<double> ahead;
+    SizeType aheadN = 0, aheadServed = 0;
+    T aheadDt = 0;
   };
 
   DeviceType &device;
@@ -68,7 +80,8 @@ private:
   ValueVec appliedFieldDir;
   ValueVec appliedField;
   T fieldStrength = 0;
-  std::map<SizeType, TypeState> state;
+  mutable std::map<SizeType, TypeState> state;
+  SizeType lookahead = defaultLookahead();
   emcRNG hostRng; // particle creation only (the reference's rngs[0])
   unsigned long stepSeed = 0;
   int mathMode = EMCGPU_MATH_FAST;
@@ -77,9 +90,39 @@ private:
     const char *e = std::getenv("EMCGPU_DEVICE");
     return e ? std::atoi(e) : 0;
   }
+  static SizeType defaultLookahead() {
+    const char *e = std::getenv("EMCGPU_LOOKAHEAD");
+    const long v = e ? std::atol(e) : 16;
+    return v < 1 ? 1 : static_cast<SizeType>(v);
+  }
+
+  // The device is ahead of the driver (steps done but not yet asked for): back to the ensemble of the driver's current
+  // step.  Rewind to the state before the look-ahead launch and repeat the steps served so far -- same particle ids, same
+  // step indices, same tables (a rebuilt table set has not been uploaded yet at this point), hence the same trajectories.
+  void materialize(SizeType idxType) const {
+    auto &st = state.at(idxType);
+    if (st.ctx && st.aheadServed < st.aheadN) {
+      emcgpu::require(st.ctx, emcgpu_bulk_rewind(st.ctx), "emcgpu_bulk_rewind");
+      if (st.aheadServed > 0) {
+        std::vector<double> again(st.aheadServed * idxTypeToPartType.at(idxType)->getNrValleys() * 3);
+        emcgpu::require(st.ctx,
+                        emcgpu_bulk_step(st.ctx, st.aheadDt, static_cast<int>(st.aheadServed), static_cast<int>(st.aheadServed),
+                                         again.data()),
+                        "emcgpu_bulk_step");
+      }
+    }
+    st.aheadN = st.aheadServed = 0;
+  }
+  void materializeAll() const {
+    for (auto &[idxType, st] : state) {
+      (void)st;
+      materialize(idxType);
+    }
+  }
 
   void configure(SizeType idxType) {
     auto &st = state[idxType];
+    materialize(idxType);
     const auto box = device.getMaxPos();
     const double b[3] = {box[0], box[1], box[2]}, d[3] = {appliedFieldDir[0], appliedFieldDir[1], appliedFieldDir[2]};
     emcgpu::require(st.ctx,
@@ -106,6 +149,7 @@ private:
   }
 
   void download(SizeType idxType, HostEnsemble &out) const {
+    materialize(idxType);
     const auto &st = state.at(idxType);
     const SizeType n = st.nrParticles;
     double *ptrs[EMCGPU_N_STREAMS];
@@ -134,6 +178,7 @@ private:
   const std::vector<double> &observables(SizeType idxType) {
     auto &st = state.at(idxType);
     if (!st.obsValid) {
+      materialize(idxType);
       upload(idxType);
       st.lastObs.assign(idxTypeToPartType[idxType]->getNrValleys() * 3, 0.);
       if (st.nrParticles)
@@ -197,9 +242,19 @@ public:
         configure(idxType);
   }
   // the C-ABI context of a particle type (multi-GPU drivers, tests)
-  emcgpu_ctx *getGpuContext(SizeType idxType) { return state.at(idxType).ctx; }
+  emcgpu_ctx *getGpuContext(SizeType idxType) {
+    materialize(idxType);
+    return state.at(idxType).ctx;
+  }
+  // time steps a moveParticles(dt) call runs at once on the device (1 = one launch per call); see the header comment
+  void setLookahead(SizeType nSteps) {
+    materializeAll();
+    lookahead = nSteps < 1 ? 1 : nSteps;
+  }
+  SizeType getLookahead() const { return lookahead; }
 
   void setSeed(SizeType inSeed) {
+    materializeAll();
     hostRng.seed(inSeed);
     stepSeed = inSeed;
     for (auto &[idxType, st] : state)
@@ -219,6 +274,7 @@ public:
   void generateInitialParticles() {
     for (const auto &[idxType, type] : idxTypeToPartType) {
       auto &st = state[idxType];
+      st.aheadN = st.aheadServed = 0;
       emcdetail::generateBulkEnsemble(st.staging, *type, device, hostRng);
       st.nrParticles = st.staging.size();
       st.uploaded = false;
@@ -244,11 +300,32 @@ public:
       auto &st = state[idxType];
       if (st.nrParticles == 0)
         continue;
+      const SizeType nObs = type->getNrValleys() * 3;
+      // this step is already done on the device: hand out its sums
+      if (st.aheadServed < st.aheadN && tStep == st.aheadDt && type->scatterHandler.getTableVersion() == st.tableVersion) {
+        st.lastObs.assign(st.ahead.begin() + st.aheadServed * nObs, st.ahead.begin() + (st.aheadServed + 1) * nObs);
+        st.aheadServed++;
+        st.obsValid = true;
+        continue;
+      }
+      materialize(idxType);
       upload(idxType);
       refreshModel(idxType);
-      st.lastObs.assign(type->getNrValleys() * 3, 0.);
-      emcgpu::require(st.ctx, emcgpu_bulk_step(st.ctx, tStep, 1, 1, st.lastObs.data()), "emcgpu_bulk_step");
-      emcgpu::collectPhononCounts(st.ctx, st.phononBaths); // recordEmission / recordAbsorption of this step
+      const SizeType nAhead = (st.phononBaths.empty() && !st.grain) ? lookahead : 1;
+      if (nAhead > 1) {
+        st.ahead.assign(nAhead * nObs, 0.);
+        emcgpu::require(st.ctx,
+                        emcgpu_bulk_step_ahead(st.ctx, tStep, static_cast<int>(nAhead), static_cast<int>(nAhead), st.ahead.data()),
+                        "emcgpu_bulk_step_ahead");
+        st.aheadN = nAhead;
+        st.aheadServed = 1;
+        st.aheadDt = tStep;
+        st.lastObs.assign(st.ahead.begin(), st.ahead.begin() + nObs);
+      } else {
+        st.lastObs.assign(nObs, 0.);
+        emcgpu::require(st.ctx, emcgpu_bulk_step(st.ctx, tStep, 1, 1, st.lastObs.data()), "emcgpu_bulk_step");
+        emcgpu::collectPhononCounts(st.ctx, st.phononBaths); // recordEmission / recordAbsorption of this step
+      }
       st.obsValid = true;
     }
   }
@@ -258,6 +335,7 @@ public:
   // device side and fuse several steps per kernel launch)
   void moveParticles(T tStep, SizeType nSteps, SizeType stepsPerLaunch, SizeType idxType, std::vector<double> &series) {
     auto &st = state.at(idxType);
+    materialize(idxType);
     upload(idxType);
     refreshModel(idxType);
     const SizeType nV = idxTypeToPartType[idxType]->getNrValleys();
@@ -323,6 +401,7 @@ public:
   void deleteParticles() {
     for (auto &[idxType, st] : state) {
       (void)idxType;
+      st.aheadN = st.aheadServed = 0;
       st.staging.clear();
       st.nrParticles = 0;
       st.uploaded = false;
