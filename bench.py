@@ -9,10 +9,11 @@ Workload (configs[1] of BASELINE.json): Si electrons, the shipped bulkSimulation
 reference's initial distributions and advanced out of the initial transient before timing.
 One "step" = one time step of every particle of the shard including the per-valley observables of
 that step (the reference's moveParticles(dt) + the three getAvg* passes, bulkSimulation.cpp:150-157).
-The headline runs the deferred-event kernel (K1c, bulkDeferKernel): SPL = 8 consecutive time steps per
-launch, the particle state crosses HBM once per launch, the per-step observables of all 8 steps are
-delivered.  The one-step-per-launch streaming kernel (K1a, bulkTmaKernel, HBM-bound) is timed next to
-it ("one_step_per_launch").  The rate tables are built on the host by the drop-in
+The headline runs the flight + event kernel pair (K1d, bulkFlightKernel / bulkEventKernel): up to SPL = 24
+consecutive time steps per launch pair, the particle state crosses HBM once per pair, the per-step
+observables of all steps are delivered.  The one-step-per-launch streaming kernel (K1a, bulkTmaKernel,
+HBM-bound) is timed next to it ("one_step_per_launch"), and so is the reference's own driver loop
+(moveParticles(dt) + getAvg* per step) through the drop-in C++ handler ("dropin_loop").  The rate tables are built on the host by the drop-in
 C++ API (libemchost) -- not by the oracle.
 
 N > 1: one process per GPU (torchrun), the ensemble is block-partitioned, no per-step communication;
@@ -44,7 +45,12 @@ DT = 1e-16
 FIELD = 1e6
 DOPING = 1e23
 SEED = 12345
-SPL = 8  # time steps per launch of the headline kernel (K1c)
+SPL = 24  # time steps per launch pair of the headline kernels (K1d)
+# FP64 instructions of the flight kernel per particle-step (SASS of bulkFlightKernel<4, AXIS>, hot loop: 13 DFMA + 9 DMUL +
+# 6 DADD; cross-checked against ncu's executed-opcode counts, profiles/r2_*flight*.txt)
+FLIGHT_FP64_PER_PARTICLE_STEP = 28.0
+FLIGHT_FLOP_PER_PARTICLE_STEP = 13 * 2 + 9 + 6
+FP64_LANES_PER_SM = 64
 
 
 def workload_config(particles_per_gpu, n_gpus, extra=None):
@@ -54,6 +60,7 @@ def workload_config(particles_per_gpu, n_gpus, extra=None):
         "particles_per_gpu": int(particles_per_gpu),
         "particles_total": int(particles_per_gpu) * n_gpus,
         "steps_per_launch": SPL,
+        "kernels": "bulkFlightKernel + bulkEventKernel (K1d), one launch pair per steps_per_launch time steps",
         "observables": "per-step per-valley <E>, <v.E>, occupation of EVERY time step, fused into the step kernel",
         "l2": "no flush needed: state per GPU (%.1f GB) is far larger than L2" % (particles_per_gpu * 68 / 1e9),
         "parallelism": f"particles block-partitioned over {n_gpus} GPU(s), one all-reduce of the observable series",
@@ -152,16 +159,33 @@ def run_port_bench(particles, steps):
             "move_s": dt, "obs_s": 0.0}
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_reference(steps, warmup, budget_s):
     """Time the reference on a bounded sample: calibrate briefly, then size the ensemble so that
     steps+warmup time steps take about budget_s."""
     cores = host_cores()
+    one_thread = None
     if os.path.exists(REF_BENCH):
         cal = run_ref_bench(100000, 20, 5, cores)
         rate = cal["psteps_per_s"]
         particles = max(20000, min(5_000_000, int(rate * budget_s / max(1, steps + warmup))))
         res = run_ref_bench(particles, steps, warmup, cores)
         kind = "reference"
+        try:  # BASELINE.md 4: also one thread (small sample, a few seconds)
+            one = run_ref_bench(100000, 20, 3, 1)
+            one_thread = {"value": one["psteps_per_s"], "move_only_value": one.get("psteps_per_s_move_only"),
+                          "sample": f"{one['particles']} particles x 20 time steps, 1 thread"}
+        except Exception:
+            one_thread = None
     else:
         particles = 2000
         res = run_port_bench(particles, min(steps, 20))
@@ -170,8 +194,36 @@ def cpu_reference(steps, warmup, budget_s):
     sample = (f"{res['particles']} particles x {steps} time steps of the same workload "
               f"(moveParticles + 3 observable passes per step), {res['threads']} OpenMP thread(s)")
     return {"value": res["psteps_per_s"], "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
-            "move_only_value": res.get("psteps_per_s_move_only"),
+            "move_only_value": res.get("psteps_per_s_move_only"), "one_thread": one_thread, "cpu": cpu_model(),
+            "build": "g++ -O3 -march=x86-64-v3 -fopenmp (the reference's Release flags with -march=native replaced so "
+                     "that the binary built in the dev container runs on the GPU box's host CPU)",
             "seconds": res["move_s"] + res["obs_s"]}, res
+
+
+CPU_KEYS = ("value", "unit", "cores", "kind", "sample", "move_only_value", "one_thread", "cpu", "build")
+
+
+def dropin_loop(particles, steps, lookahead, device_index):
+    """The reference's own driver loop -- handler.moveParticles(dt) followed by getAvgEnergy / getAvgDriftVelocity /
+    getValleyOccupationProbability, once per time step (bulkSimulation.cpp:150-157) -- through the drop-in C++ handler
+    (viennaemc_b200/bin/bulkSimulation, steps-per-launch 1 = that loop verbatim).  The handler runs `lookahead` steps per
+    launch pair ahead and serves the following calls from the series."""
+    import re
+    path = os.path.join(ROOT, "viennaemc_b200", "bin", "bulkSimulation")
+    if not os.path.exists(path):
+        return {"failed": "driver binary missing"}
+    with tempfile.TemporaryDirectory() as tmp:
+        r = subprocess.run([path, "--particles", str(int(particles)), "--steps", str(int(steps)), "--seed", str(SEED),
+                            "--lookahead", str(int(lookahead)), "--dt", str(DT), "--field", str(FIELD)], cwd=tmp,
+                           capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, EMCGPU_DEVICE=str(device_index)))
+    m = re.search(r"Wall time: ([0-9.eE+-]+) s  \(([0-9.eE+-]+) particle-steps/s\)", r.stdout)
+    if r.returncode != 0 or not m:
+        return {"failed": (r.stdout + r.stderr)[-300:]}
+    return {"value": float(m.group(2)), "unit": UNIT, "seconds": float(m.group(1)), "particles": int(particles),
+            "steps": int(steps), "lookahead": int(lookahead),
+            "what": "host wall clock around the reference's driver loop (one moveParticles(dt) + three getAvg* calls per time "
+                    "step, host-generated ensemble uploaded before the loop) through basicBulkParticleHandler on the GPU path"}
 
 
 def device_run_numbers(budget_s=60.0):
@@ -216,7 +268,7 @@ def main_reference(args):
             "config": workload_config(args.particles, args.gpus,
                                       {"reference_sample": base["sample"],
                                        "note": "reference CPU path: throughput does not depend on the GPU count"}),
-            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_baseline": {k: base[k] for k in CPU_KEYS},
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -291,9 +343,11 @@ def main_ours(args):
         barrier()
         return max_over_ranks(e0.elapsed_time(e1))
 
-    # ---- headline: K time steps, SPL per launch (K1c), inputs resident in HBM --------------------
+    # ---- headline: K time steps, SPL per launch pair (K1d), inputs resident in HBM ---------------
     if W > 0:
         ctx.bulk_step_device(DT, W, SPL, warm.data_ptr())
+    ctx.set_option("kernel_timing", 1)  # cudaEvents around every kernel launch, on the launching stream
+    ctx.kernel_times(reset=True)
     launches0 = ctx.launch_count
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -306,6 +360,8 @@ def main_ours(args):
     ms = timed(run_steps)
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.launch_count - launches0
+    kernel_ms, kernel_launches = ctx.kernel_times(reset=True)  # [flight, event, other] inside the timed region
+    ctx.set_option("kernel_timing", 0)
     value = n_total * K / (ms * 1e-3)
     series = obs.view(K, n_v, 3).cpu().numpy()
     assert np.all(series[:, :, 2].sum(axis=1) == n_total), "particle count not conserved"
@@ -362,6 +418,24 @@ def main_ours(args):
             sys.stderr.write(f"emcgpu_bulk_run_host failed ({exc}); e2e is the unpipelined set/step/get sequence\n")
             e2e = {"value": unpipelined["value"], "unit": UNIT, **e2e_bytes, "ms_total": e2e_res_ms,
                    "what": unpipelined["what"], "bulk_run_host_error": str(exc)}
+        # what the host link allows: the same bytes copied in and copied out with no compute at all.  With both PCIe
+        # directions perfectly overlapped a job on host buffers cannot finish before max(t_in, t_out).
+        t_in = timed(lambda: ctx.set_ensemble_from(streams, packed, base_id))
+        t_out = timed(lambda: ctx.get_ensemble_into(streams, packed))
+        ceiling = n_total * K / (max(t_in, t_out) * 1e-3)
+        e2e["copy_ceiling"] = {"value": ceiling, "unit": UNIT, "h2d_ms": t_in, "d2h_ms": t_out,
+                               "h2d_gbs_per_rank": 68.0 * n_local / (t_in * 1e-3) / 1e9,
+                               "d2h_gbs_per_rank": 68.0 * n_local / (t_out * 1e-3) / 1e9,
+                               "frac": e2e["value"] / ceiling,
+                               "what": f"68 B per particle each way over the host link and nothing else (max over ranks, all {world} "
+                                       f"rank(s) copying at once), expressed in the metric for K = {K}: the bound of any run on host "
+                                       "buffers at this K; 'frac' = e2e / this"}
+        if K < 200 and not args.no_e2e_long:
+            # the same call on a run long enough to amortise the two copies (K = 1000 time steps)
+            KL = 1000
+            long_ms = timed(lambda: ctx.bulk_run_host(streams, packed, DT, KL, SPL, 0, particle_id_base=base_id, want_obs=False))
+            e2e["long_run"] = {"steps": KL, "value": n_total * KL / (long_ms * 1e-3), "unit": UNIT, "ms_total": long_ms,
+                               "h2d_bytes_per_step": 68.0 * n_local / KL, "d2h_bytes_per_step": 68.0 * n_local / KL}
         del host, host_packed
 
     # ---- roofline of the step kernel -------------------------------------------------------------
@@ -370,27 +444,50 @@ def main_ours(args):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    n_launch = max(1, launches)
-    launch_ms = ms / n_launch
-    achieved = BYTES_PER_PARTICLE_STEP * n_local * K / (ms * 1e-3) / 1e9
-    traffic = traffic_one = None
+    traffic_flight = traffic_event = traffic_one = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         t = json.load(open(tpath))
         if int(t.get("particles", 0)) == n_local:
-            traffic = t.get("bulkDeferKernel", {}).get("dram_bytes_per_launch")
+            traffic_flight = t.get("bulkFlightKernel", {}).get("dram_bytes_per_launch")
+            traffic_event = t.get("bulkEventKernel", {}).get("dram_bytes_per_launch")
             traffic_one = t.get("bulkTmaKernel", {}).get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": f"bulkDeferKernel<FAST, PHILOX> ({SPL} time steps per launch, deferred events)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": BYTES_PER_PARTICLE_STEP * n_local * K / n_launch,
-                "avg_launch_ms": launch_ms,
-                "dram_gbs_measured": (traffic / (launch_ms * 1e-3) / 1e9) if traffic else None,
-                "note": f"per GPU. algorithmic = 136 B x particle-steps of a launch (SURVEY 8d); frac > 1 because the particle "
-                        f"state crosses HBM once per {SPL} time steps (ncu DRAM traffic per launch in 'traffic', the "
-                        "DRAM rate it implies in 'dram_gbs_measured'): this kernel is bound by the FP64 pipe and instruction "
-                        "issue, not by HBM (profiles/r1_p_defer_v7_spl8.txt). The HBM-bound one-step kernel is in "
-                        "'one_step_per_launch'."}
+    n_pairs = max(1, int(kernel_launches[0]))
+    flight_ms = float(kernel_ms[0]) / n_pairs          # average duration of a flight launch (CUDA events, this run)
+    event_ms = float(kernel_ms[1]) / max(1, int(kernel_launches[1]))
+    steps_per_pair = K / n_pairs
+    psteps_per_launch = n_local * steps_per_pair
+    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    sm_mhz = float((clocks or {}).get("sm_mhz") or 0.0) or float((clocks or {}).get("sm_max_mhz") or 1965.0)
+    fp64_peak = sm_count * FP64_LANES_PER_SM * sm_mhz * 1e6 / 1e12          # T lane-instructions/s of the FP64 pipe
+    fp64_ach = FLIGHT_FP64_PER_PARTICLE_STEP * psteps_per_launch / (flight_ms * 1e-3) / 1e12
+    algorithmic = BYTES_PER_PARTICLE_STEP * n_local * K / (ms * 1e-3) / 1e9
+    moved = ((traffic_flight or 0) + (traffic_event or 0)) / ((flight_ms + event_ms) * 1e-3) / 1e9 if traffic_flight else None
+    roofline = {"bound": "fp64",
+                "kernel": f"bulkFlightKernel<4, axis> (dominant kernel: {kernel_ms[0] / max(1e-9, kernel_ms[0] + kernel_ms[1]):.0%} "
+                          f"of the device time of a launch pair; {steps_per_pair:g} time steps per launch)",
+                "achieved": fp64_ach, "peak": fp64_peak, "unit": "T fp64 lane-instructions/s (FP64 pipe: 64 lanes/clk/SM)",
+                "frac": fp64_ach / fp64_peak, "traffic": traffic_flight,
+                "tflops": FLIGHT_FLOP_PER_PARTICLE_STEP * psteps_per_launch / (flight_ms * 1e-3) / 1e12,
+                "peak_source": f"{sm_count} SMs x {FP64_LANES_PER_SM} FP64 lanes x {sm_mhz:.0f} MHz (median SM clock sampled "
+                               "during the timed region)",
+                "fp64_instructions_per_particle_step": FLIGHT_FP64_PER_PARTICLE_STEP,
+                "avg_launch_ms": flight_ms, "particle_steps_per_launch": psteps_per_launch,
+                "flight_only_particle_steps_per_s": psteps_per_launch / (flight_ms * 1e-3),
+                "event_kernel": {"avg_launch_ms": event_ms, "traffic": traffic_event,
+                                 "share_of_pair": kernel_ms[1] / max(1e-9, kernel_ms[0] + kernel_ms[1]),
+                                 "note": "latency-bound (gathers of the frozen particles, table rows through L2, dependent "
+                                         "fp64 chains of the samplers): FP64 pipe 22 %, issue slots 35 % (profiles/r2_*event*.txt)"},
+                "hbm": {"algorithmic_gbs": algorithmic, "algorithmic_frac": algorithmic / peak,
+                        "moved_gbs": moved, "moved_frac": (moved / peak) if moved else None, "peak": peak,
+                        "peak_source": peak_src,
+                        "note": "algorithmic = 136 B x particle-steps (SURVEY 8d) over the whole timed region; moved = ncu DRAM "
+                                "bytes of one flight + one event launch (profiles/traffic.json) over their measured "
+                                "durations: the state crosses HBM once per launch pair, so the step is bound by the FP64 "
+                                "pipe, not by HBM; the HBM-bound one-step kernel is in 'one_step_per_launch'"},
+                "note": "per GPU. achieved = 28 FP64 instructions per particle-step (SASS of the flight loop) x particle-steps of "
+                        "a launch / average flight-launch duration measured with CUDA events in this run; frac = share of the "
+                        "FP64 pipe's issue rate (the binding resource, ncu: sm__pipe_fp64_cycles_active)"}
     one_achieved = BYTES_PER_PARTICLE_STEP * n_local * K / (one_ms * 1e-3) / 1e9
     one_step = {"kernel": "bulkTmaKernel<FAST, PHILOX> (one time step per launch, TMA pipeline)", "value": one_value,
                 "unit": UNIT, "ms_per_step": one_ms / K,
@@ -411,10 +508,16 @@ def main_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             try:
                 base, _ = cpu_reference(steps=50, warmup=5, budget_s=15.0)
-                line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                line["cpu_baseline"] = {k: base[k] for k in CPU_KEYS}
             except Exception as exc:  # the baseline is reported, never required
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": host_cores(), "kind": "reference",
                                         "sample": f"failed: {exc}"}
+        if world == 1 and not args.no_dropin_loop:
+            try:
+                line["dropin_loop"] = dropin_loop(n_local, 8 * SPL, SPL, local_rank)
+                line["dropin_loop"]["frac_of_value"] = line["dropin_loop"].get("value", 0.0) / value
+            except Exception as exc:
+                line["dropin_loop"] = {"failed": str(exc)}
         if world == 1 and not args.no_device_runs:
             try:
                 line["device_runs"] = device_run_numbers()
@@ -436,6 +539,8 @@ def main():
     ap.add_argument("--particles", type=float, default=1e8, help="particles per GPU")
     ap.add_argument("--settle", type=int, default=2000, help="untimed time steps before the measurement")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-long", action="store_true", help="skip the 1000-step end-to-end run")
+    ap.add_argument("--no-dropin-loop", action="store_true", help="skip the reference-driver-loop leg (C++ handler)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-device-runs", action="store_true", help="skip the (untimed) device-run numbers of configs 3 / 4")
     args = ap.parse_args()

@@ -264,7 +264,9 @@ int emcgpu_bulk_rewind(emcgpu_ctx *ctx);
  * flight kernel [0], the event kernel [1] and all other bulk kernels [2] since the last reset; synchronises */
 int emcgpu_kernel_times(emcgpu_ctx *ctx, double *ms, int64_t *launches, int reset);
 /* the same nSteps x { moveParticles ; observables } for an ensemble that lives in HOST memory (soa / packed as
- * emcgpu_set_ensemble, updated IN PLACE; pinned memory makes the copies asynchronous): the ensemble is cut into
+ * emcgpu_set_ensemble, updated IN PLACE).  The arrays should be PINNED (cudaHostAlloc / cudaHostRegister): only then
+ * are the copies asynchronous and overlap the kernels; with pageable arrays the call is still correct, but every
+ * cudaMemcpyAsync blocks the host thread and the copies and kernels run one after the other.  The ensemble is cut into
  * slices of sliceParticles (<= 0: about n/8) and slice i runs its nSteps steps while slice i+1 is copied to the
  * device and slice i-1 back, so the PCIe transfers hide behind the step kernels and n is not limited by the HBM
  * size. Results equal emcgpu_set_ensemble + emcgpu_bulk_step + emcgpu_get_ensemble (particle states bit for bit,

@@ -192,6 +192,7 @@ class Context:
         if rc != OK:
             raise EmcGpuError(rc, self.L.emcgpu_last_error(None).decode())
         self.h = h
+        self.device = int(device)
         self.n_valleys = 0
         self._keep = []
 

@@ -407,6 +407,12 @@ void emcgpu_destroy(emcgpu_ctx *ctx) {
                           &ctx->dOffsets, &ctx->dCursor, &ctx->dObs, &ctx->dStatus, &ctx->dEvents,
                           &ctx->dEvCount, &ctx->dSlices, &ctx->dEnsembleAlt, &ctx->dFrozen, &ctx->dClaim, &ctx->dBathCounts, &ctx->dBathCum, &ctx->dGrain})
     b->release();
+  for (cudaEvent_t &e : ctx->sliceEvents)
+    if (e) cudaEventDestroy(e);
+  for (auto &t : ctx->timed) {
+    cudaEventDestroy(t.a);
+    cudaEventDestroy(t.b);
+  }
   if (ctx->copyIn) cudaStreamDestroy(ctx->copyIn);
   if (ctx->copyOut) cudaStreamDestroy(ctx->copyOut);
   emc::releaseDeviceRun(ctx);
@@ -1080,12 +1086,10 @@ int emcgpu_bulk_run_host(emcgpu_ctx *ctx, int64_t n, double *const *soa, uint32_
     CUDA_TRY(ctx, ctx->dSlices.ensure(bufBytes * nBuf));
     if (!ctx->copyIn) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copyIn, cudaStreamNonBlocking));
     if (!ctx->copyOut) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copyOut, cudaStreamNonBlocking));
-    cudaEvent_t evIn[nBuf], evRun[nBuf], evOut[nBuf];
-    for (int b = 0; b < nBuf; b++) {
-      CUDA_TRY(ctx, cudaEventCreateWithFlags(&evIn[b], cudaEventDisableTiming));
-      CUDA_TRY(ctx, cudaEventCreateWithFlags(&evRun[b], cudaEventDisableTiming));
-      CUDA_TRY(ctx, cudaEventCreateWithFlags(&evOut[b], cudaEventDisableTiming));
-    }
+    // the nine events of the slice ring live with the context (created once, destroyed by emcgpu_destroy)
+    for (int b = 0; b < 3 * nBuf; b++)
+      if (!ctx->sliceEvents[b]) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->sliceEvents[b], cudaEventDisableTiming));
+    cudaEvent_t *const evIn = ctx->sliceEvents, *const evRun = ctx->sliceEvents + nBuf, *const evOut = ctx->sliceEvents + 2 * nBuf;
     // the step routine works on whatever ensemble the context points at
     double *savedStream[EMCGPU_N_STREAMS];
     for (int s = 0; s < EMCGPU_N_STREAMS; s++) savedStream[s] = ctx->dStream[s];
@@ -1126,11 +1130,6 @@ int emcgpu_bulk_run_host(emcgpu_ctx *ctx, int64_t n, double *const *soa, uint32_
     cudaStreamSynchronize(ctx->copyIn);
     cudaStreamSynchronize(ctx->stream);
     cudaError_t ce2 = cudaStreamSynchronize(ctx->copyOut);
-    for (int b = 0; b < nBuf; b++) {
-      cudaEventDestroy(evIn[b]);
-      cudaEventDestroy(evRun[b]);
-      cudaEventDestroy(evOut[b]);
-    }
     for (int s = 0; s < EMCGPU_N_STREAMS; s++) ctx->dStream[s] = savedStream[s];
     ctx->dPacked = savedPacked;
     ctx->n = savedN;

@@ -516,6 +516,21 @@ int emcgpu_device_configure(emcgpu_ctx *ctx, const emcgpu_device_t *dev, double 
     cells *= dev->extent[i];
   }
   if (cells > (1 << 28)) return fail(ctx, EMCGPU_E_CAPACITY, "grid too large");
+  // every argument is checked BEFORE the previous configuration is given up
+  for (int c = 0; c < dev->nContacts; c++)
+    if (dev->contactType[c] == EMCGPU_CONTACT_GATE && !(dev->gateThickness && dev->gateThickness[c] > 0))
+      return fail(ctx, EMCGPU_E_INVALID, "gate contact %d needs an oxide thickness", c);
+  for (int64_t i = 0; i < cells * 2 * dev->dim; i++)
+    if (dev->faceContact[i] < -2 || dev->faceContact[i] >= dev->nContacts)
+      return fail(ctx, EMCGPU_E_INVALID, "faceContact entry %lld out of range", (long long)i);
+  // a failed allocation below leaves NO configuration (needRun() then rejects the run calls) rather than half of one
+  struct Guard {
+    emcgpu_ctx *ctx;
+    bool ok = false;
+    ~Guard() {
+      if (!ok) emc::releaseDeviceRun(ctx);
+    }
+  } guard{ctx};
   emc::releaseDeviceRun(ctx);
   DeviceRunState *r = ctx->run = new DeviceRunState();
   DevGeometry &G = r->geo;
@@ -540,12 +555,7 @@ int emcgpu_device_configure(emcgpu_ctx *ctx, const emcgpu_device_t *dev, double 
     G.gateEpsOx[c] = dev->gateEpsOx ? dev->gateEpsOx[c] : 0.0;
     G.gateThickness[c] = dev->gateThickness ? dev->gateThickness[c] : 0.0;
     G.gateBarrier[c] = dev->gateBarrier ? dev->gateBarrier[c] : 0.0;
-    if (G.contactType[c] == EMCGPU_CONTACT_GATE && !(G.gateThickness[c] > 0))
-      return fail(ctx, EMCGPU_E_INVALID, "gate contact %d needs an oxide thickness", c);
   }
-  for (int64_t i = 0; i < cells * 2 * dev->dim; i++)
-    if (dev->faceContact[i] < -2 || dev->faceContact[i] >= dev->nContacts)
-      return fail(ctx, EMCGPU_E_INVALID, "faceContact entry %lld out of range", (long long)i);
   r->charge = charge;
   r->nrCarriers = nrCarriers;
   ctx->mathMode = mathMode;
@@ -624,6 +634,7 @@ int emcgpu_device_configure(emcgpu_ctx *ctx, const emcgpu_device_t *dev, double 
   }
   CUDA_TRY(ctx, cudaMemcpy(r->grid[EMCGPU_GRID_POTENTIAL].ptr, pot.data(), cells * sizeof(double), cudaMemcpyHostToDevice));
   CUDA_TRY(ctx, cudaMemcpy(r->grid[EMCGPU_GRID_EXPECTED].ptr, exp.data(), cells * sizeof(double), cudaMemcpyHostToDevice));
+  guard.ok = true;
   return EMCGPU_OK;
 }
 
@@ -731,19 +742,32 @@ int emcgpu_device_step(emcgpu_ctx *ctx, double dt, int32_t *removedPerContact) {
   return readStatus(ctx);
 }
 
+} // extern "C"
+namespace {
+// Upper bound of the particles the contacts inject in ONE step: a reservoir cell never misses more than its expected
+// population (handleOhmicContacts, emcBasicParticleHandler.hpp:158-192).  The ensemble therefore grows by at most this
+// many particles per step, whatever the bias or the initial population.
+int updateMaxInject(emcgpu_ctx *ctx) {
+  DeviceRunState *r = ctx->run;
+  if (r->maxInject >= 0) return EMCGPU_OK;
+  std::vector<double> exp(r->geo.cells);
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpy(exp.data(), r->grid[EMCGPU_GRID_EXPECTED].ptr, exp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  double total = 0;
+  for (double v : exp) total += std::ceil(std::max(0.0, v) / r->nrCarriers);
+  r->maxInject = (int64_t)total;
+  return EMCGPU_OK;
+}
+} // namespace
+extern "C" {
+
 int emcgpu_device_contacts(emcgpu_ctx *ctx, int32_t *netPerContact, const uint64_t *replayDraws, int64_t nReplayDraws) {
   if (int r = needRun(ctx)) return r;
   if (int r = needModel(ctx)) return r;
   // one reservoir cell never misses more than its expected population: room for the worst case
   {
     DeviceRunState *r = ctx->run;
-    if (r->maxInject < 0) {
-      std::vector<double> exp(r->geo.cells);
-      CUDA_TRY(ctx, cudaMemcpy(exp.data(), r->grid[EMCGPU_GRID_EXPECTED].ptr, exp.size() * sizeof(double), cudaMemcpyDeviceToHost));
-      double total = 0;
-      for (double v : exp) total += std::ceil(std::max(0.0, v) / r->nrCarriers);
-      r->maxInject = (int64_t)total;
-    }
+    if (int rc = updateMaxInject(ctx)) return rc;
     if (int rc = growEnsemble(ctx, std::max<int64_t>(ctx->n + r->maxInject, r->reserve))) return rc;
   }
   ctx->nextStep--; // the contacts belong to the step that was just done (Philox counter of the injected particles)
@@ -775,10 +799,16 @@ int emcgpu_device_run_averaging(emcgpu_ctx *ctx, double dt, int nSteps, int nAve
   const int nC = r->geo.nContacts;
   std::vector<int32_t> hCounters((size_t)kRunChunk * 2 * std::max(1, nC)), hSweeps(kRunChunk);
   for (int done = 0; done < nSteps;) {
-    const int chunk = std::min(kRunChunk, nSteps - done);
-    // head room for the particles the contacts may inject during the chunk (checked again on the device)
-    if (ctx->capacity < ctx->n + ctx->n / 4 + 4096 || ctx->capacity < r->reserve)
-      if (int rc = growEnsemble(ctx, std::max<int64_t>(ctx->n + ctx->n / 2 + 8192, r->reserve))) return rc;
+    // Head room for the particles the contacts may inject during the chunk.  The ensemble grows by at most maxInject per
+    // step (see updateMaxInject), so capacity >= n + chunk * maxInject cannot overflow inside the chunk: grow to a whole
+    // chunk's worth when that is cheap (a few times the ensemble), otherwise shorten the chunk to what the room allows.
+    if (int rc = updateMaxInject(ctx)) return rc;
+    const int64_t perStep = std::max<int64_t>(1, r->maxInject);
+    const int64_t wholeChunk = ctx->n + (int64_t)kRunChunk * perStep;
+    const int64_t want = std::max<int64_t>(std::min<int64_t>(wholeChunk, 4 * ctx->n + ((int64_t)1 << 20)), ctx->n + perStep);
+    if (ctx->capacity < want || ctx->capacity < r->reserve)
+      if (int rc = growEnsemble(ctx, std::max<int64_t>(want + want / 8, r->reserve))) return rc;
+    const int chunk = (int)std::min<int64_t>(std::min(kRunChunk, nSteps - done), std::max<int64_t>(1, (ctx->capacity - ctx->n) / perStep));
     if (int rc = pushCtl(ctx, std::max(0, (nSteps - nAverage) - done))) return rc;
     for (int s = 0; s < chunk; s++) {
       // performEMCStep (emcSimulation.hpp:177-192)

@@ -86,6 +86,7 @@ struct emcgpu_ctx {
   // slice ring of emcgpu_bulk_run_host (three slices: upload / advance / download)
   emc::DeviceBuffer dSlices;
   cudaStream_t copyIn = nullptr, copyOut = nullptr;
+  cudaEvent_t sliceEvents[9] = {};
   bool obsAccumulate = false; // emcgpu_bulk_step_device adds to obsDevice instead of zeroing it first
 
   // rng

@@ -82,9 +82,15 @@ class DeviceRunSharding:
             def __init__(self, ptr, n):
                 self.__cuda_array_interface__ = dict(shape=(n,), typestr="<f8", data=(ptr, False), version=2)
 
+        device = torch.device("cuda", getattr(ctx, "device", torch.cuda.current_device()))
+
         def _allreduce(user, ptr, count, stream):
-            t = torch.as_tensor(_View(ptr, int(count)), device=f"cuda:{torch.cuda.current_device()}")
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            # on the LIBRARY's stream (the kernels before and after the reduce are ordered on it), whatever torch's
+            # current stream is; the default stream (0) is torch's default stream of that device
+            t = torch.as_tensor(_View(ptr, int(count)), device=device)
+            ext = torch.cuda.ExternalStream(int(stream), device=device) if stream else torch.cuda.default_stream(device)
+            with torch.cuda.stream(ext):
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
             self.calls += 1
 
         self._cb = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)(_allreduce)  # keep alive
