@@ -253,6 +253,27 @@ def device_run_numbers(budget_s=60.0):
             steps, n, secs, rate, sweeps = int(m.group(1)), int(m.group(2)), float(m.group(3)), float(m.group(4)), float(m.group(5))
             out.setdefault(exe, {})[order] = {"particle_steps_per_s": rate, "us_per_step": secs / steps * 1e6, "particles": n,
                                               "steps": steps, "sor_sweeps_per_step": sweeps}
+    # the reference's own CPU run of the same devices on this box: the UNMODIFIED example mains with only
+    # their run length shortened (oracle/Makefile: _ref/ref_resistor2D_short 3000 steps, _ref/ref_mosfet2D_short 300 steps),
+    # 4 OpenMP threads as the examples hard-code; "CPU time" is the examples' own clock around simulation.execute()
+    # (whole seconds, includes the initial equilibrium solve and particle creation)
+    for exe, steps in (("resistor2D", 3000), ("mosfet2D", 300)):
+        path = os.path.join(ROOT, "oracle", "_ref", f"ref_{exe}_short")
+        if exe not in out or not os.path.exists(path) or time.time() > t_end + 60.0:
+            continue
+        with tempfile.TemporaryDirectory() as tmp:
+            try:
+                r = subprocess.run([path], cwd=tmp, capture_output=True, text=True, timeout=180.0)
+            except subprocess.TimeoutExpired:
+                continue
+        m = re.search(r"CPU time: (\d+) s", r.stdout)
+        if r.returncode == 0 and m and int(m.group(1)) > 0:
+            secs = float(m.group(1))
+            n = next(iter(out[exe].values()))["particles"]
+            out[exe]["cpu_reference"] = {"particle_steps_per_s": n * steps / secs, "us_per_step": secs / steps * 1e6, "steps": steps,
+                                         "threads": 4, "seconds": secs, "cores": host_cores(), "kind": "reference",
+                                         "what": f"unmodified reference examples/{exe} main(), run length shortened to {steps} "
+                                                 "steps, on this box's host cores (the example fixes 4 OpenMP threads)"}
     return out
 
 

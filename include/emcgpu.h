@@ -260,6 +260,13 @@ int emcgpu_bulk_step_device(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPer
 int emcgpu_bulk_step_ahead(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPerLaunch, double *obs);
 /* back to the ensemble and step index before the last emcgpu_bulk_step_ahead (valid once, and only directly after it) */
 int emcgpu_bulk_rewind(emcgpu_ctx *ctx);
+/* Per-particle velocities of every time step, streamed to the host (printDriftVelocities / printVelocities,
+ * examples/bulkSimulation/basicBulkParticleHandler.hpp:251-285; consumed by examples/singleLayerMoS2/
+ * calcMobilityFromVACF.py).  components = 1: v.Ê (projection on the field direction), 3: the velocity vector, 0: off.
+ * While on, emcgpu_bulk_step / emcgpu_bulk_step_ahead write host[step][particle][component] for the steps of the call
+ * (at most capacitySteps per call): the general step kernel stores them into one of two device buffers whose download
+ * overlaps the next steps (asynchronous when `host` is pinned). */
+int emcgpu_bulk_record_velocities(emcgpu_ctx *ctx, int components, double *host, int64_t capacitySteps);
 /* with emcgpu_set_option("kernel_timing", 1): device time (cudaEvents on the launching stream) and launch counts of the
  * flight kernel [0], the event kernel [1] and all other bulk kernels [2] since the last reset; synchronises */
 int emcgpu_kernel_times(emcgpu_ctx *ctx, double *ms, int64_t *launches, int reset);

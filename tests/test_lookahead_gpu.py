@@ -90,3 +90,54 @@ def test_driver_results_do_not_depend_on_the_lookahead(tmp_path):
         # the ensemble the driver printed in the middle of a look-ahead window is the ensemble of THAT step
         with open(os.path.join(tmp, "la1Electrons37.txt")) as f, open(os.path.join(tmp, f"la{la}Electrons37.txt")) as g:
             assert f.read() == g.read(), la
+
+
+@pytest.mark.parametrize("components", [1, 3])
+def test_recorded_velocities_against_the_oracle(gpu_ctx_factory, components):
+    """emcgpu_bulk_record_velocities: the per-particle velocities of every step (printDriftVelocities / printVelocities,
+    basicBulkParticleHandler.hpp:251-285) as the step kernel streams them to the host, against the oracle stepping the same
+    Philox streams one step at a time and evaluating getVelocity on its ensemble."""
+    import ctypes as C
+    m = build_si()
+    box = [4e-7] * 3
+    ens, _ = m.generate_initial(box, [4, 4, 4], 1e23, po.mt_state(5))
+    n_steps, dt, seed = 23, 4e-16, 99
+    ctx = gpu_ctx_factory()
+    upload_model(ctx, m)
+    from helpers import upload_ensemble
+    upload_ensemble(ctx, ens)
+    ctx.rng_philox(seed)
+    ctx.bulk_configure(box, [-1, 0, 0], 1e6, math_mode=capi.MATH_FAST)
+    ctx.set_step_index(1)
+    vel = ctx.record_velocities(components, n_steps, ens.n)
+    ctx.bulk_step(dt, n_steps, 8)
+    ctx.record_velocities(0)
+    ref = ens.copy()
+    v = m.valley(0)
+    out = np.zeros(3)
+    scale = None
+    for s in range(n_steps):
+        m.bulk_steps(ref, box, [-1, 0, 0], 1e6, dt, 1, po.rng_philox(seed), first_step=1 + s)
+        want = np.zeros((ens.n, 3))
+        for i in range(ens.n):
+            k = np.array([ref.kx[i], ref.ky[i], ref.kz[i]])
+            po.lib().orc_velocity(C.byref(v), po._dp(k), float(ref.energy[i]), int(ref.sub[i]), po._dp(out))
+            want[i] = out
+        scale = scale or float(np.sqrt((want ** 2).sum(axis=1).mean()))
+        if components == 1:
+            assert np.max(np.abs(vel[s, :, 0] + want[:, 0])) <= 1e-12 * scale, s  # field direction (-1, 0, 0)
+        else:
+            assert np.max(np.abs(vel[s] - want)) <= 1e-12 * scale, s
+
+
+def test_driver_velocity_lines_do_not_depend_on_the_lookahead(tmp_path):
+    tmp = str(tmp_path)
+    for comps in ("1", "3"):
+        _run_driver(tmp, "v1_" + comps, "--lookahead", "1", "--velocities", comps)
+        ref = np.loadtxt(os.path.join(tmp, "v1_" + comps + "Velocities.txt"))
+        assert ref.shape[0] == 150 and ref.shape[1] % int(comps) == 0
+        for la in ("16", "7"):
+            _run_driver(tmp, f"v{la}_{comps}", "--lookahead", la, "--velocities", comps)
+            got = np.loadtxt(os.path.join(tmp, f"v{la}_{comps}Velocities.txt"))
+            assert got.shape == ref.shape
+            assert np.allclose(got, ref, rtol=2e-5, atol=1e-3), (comps, la)  # 6 significant digits in the file

@@ -100,6 +100,7 @@ def load():
     L.emcgpu_bulk_step_ahead.argtypes = [vp, C.c_double, C.c_int, C.c_int, _DP]
     L.emcgpu_bulk_rewind.argtypes = [vp]
     L.emcgpu_kernel_times.argtypes = [vp, _DP, C.POINTER(C.c_int64), C.c_int]
+    L.emcgpu_bulk_record_velocities.argtypes = [vp, C.c_int, _DP, C.c_int64]
     L.emcgpu_bulk_observables.argtypes = [vp, _DP]
     L.emcgpu_set_step_index.argtypes = [vp, C.c_int64]
     L.emcgpu_get_step_index.argtypes = [vp]
@@ -146,7 +147,7 @@ EXPORTED_SYMBOLS = [
     "emcgpu_set_stream", "emcgpu_synchronize", "emcgpu_set_option", "emcgpu_set_valleys", "emcgpu_set_tables", "emcgpu_set_grain", "emcgpu_set_grain_clock", "emcgpu_get_grain_clock", "emcgpu_set_phonon_baths", "emcgpu_get_phonon_counts", "emcgpu_set_ensemble",
     "emcgpu_get_ensemble", "emcgpu_ensemble_size", "emcgpu_generate_bulk_ensemble",
     "emcgpu_ensemble_device_ptrs", "emcgpu_rng_philox", "emcgpu_rng_replay", "emcgpu_bulk_configure",
-    "emcgpu_bulk_step", "emcgpu_bulk_run_host", "emcgpu_bulk_step_device", "emcgpu_bulk_step_ahead", "emcgpu_bulk_rewind", "emcgpu_kernel_times", "emcgpu_bulk_observables", "emcgpu_set_step_index",
+    "emcgpu_bulk_step", "emcgpu_bulk_run_host", "emcgpu_bulk_step_device", "emcgpu_bulk_step_ahead", "emcgpu_bulk_rewind", "emcgpu_kernel_times", "emcgpu_bulk_record_velocities", "emcgpu_bulk_observables", "emcgpu_set_step_index",
     "emcgpu_get_step_index", "emcgpu_event_log_enable", "emcgpu_event_log_read",
     "emcgpu_device_configure", "emcgpu_device_set_surface", "emcgpu_device_set_particle_kind", "emcgpu_device_set_sharding", "emcgpu_device_set_grid", "emcgpu_device_get_grid", "emcgpu_device_reserve",
     "emcgpu_device_poisson", "emcgpu_device_efield", "emcgpu_device_assign", "emcgpu_device_concentration",
@@ -338,6 +339,16 @@ class Context:
 
     def bulk_rewind(self):
         self._chk(self.L.emcgpu_bulk_rewind(self.h))
+
+    def record_velocities(self, components, n_steps=0, n_particles=0):
+        """per-particle velocities of the steps of the following step calls; returns the host array they land in"""
+        if not components:
+            self._chk(self.L.emcgpu_bulk_record_velocities(self.h, 0, None, 0))
+            self._vel = None
+            return None
+        self._vel = np.zeros((n_steps, n_particles, components))
+        self._chk(self.L.emcgpu_bulk_record_velocities(self.h, components, self._vel.ctypes.data_as(_DP), n_steps))
+        return self._vel
 
     def kernel_times(self, reset=True):
         """(ms, launches) of the flight kernel, the event kernel and the other bulk kernels (option kernel_timing)"""

@@ -57,6 +57,10 @@ struct BulkParams {
   // flight kernel out of place (emcgpu_bulk_step_ahead: the input ensemble stays as it was): nullptr = in place
   double *streamOut[EMCGPU_N_STREAMS];
   uint32_t *packedOut;
+  // per-particle velocities of every step (printDriftVelocities / printVelocities, basicBulkParticleHandler.hpp:251-285):
+  // [nSteps][n][velComponents], velComponents = 1 (v.Ê) or 3 (v); nullptr = not recorded.  General step kernel only.
+  double *velOut;
+  int32_t velComponents;
 };
 
 // emcGrainScatterMechanism::scatterParticle (include/emcGrainScatterMechanism.hpp:40-77) + emcParticleType::getNewGrainTau
@@ -1110,6 +1114,17 @@ __global__ void __launch_bounds__(kBulkThreads, 2) bulkStepKernel(const __grid_c
           }
         }
         e = p.energy;
+        if (P.velOut) {
+          if (P.velComponents == 1) {
+            P.velOut[(size_t)s * P.n + i] = vd;
+          } else {
+            const Vec3 vel = velocityVector(C.model->valleys[p.valley], p.sub, p.k, p.energy);
+            double *o = P.velOut + ((size_t)s * P.n + i) * 3;
+            o[0] = vel.x;
+            o[1] = vel.y;
+            o[2] = vel.z;
+          }
+        }
       }
       // per-valley block partial sums (basicBulkParticleHandler.hpp:289-347)
       double *o = sObs + s * obsPerStep;

@@ -233,6 +233,25 @@ __device__ __forceinline__ double driftVelocity(const DevValley &v, int s, const
   }
 }
 
+// getVelocity(k, E, s) in the device frame (emcNonParabolicAnistropValley.hpp:126-136 and the three sibling classes), in the
+// reference's operation order (printVelocities, basicBulkParticleHandler.hpp:251-285)
+__device__ __forceinline__ Vec3 velocityVector(const DevValley &v, int s, const Vec3 &k, double e) {
+  using A = Arith<true>;
+  double npf = 1.0;
+  if (v.nonParabolic) npf = A::sqrt(A::add(1.0, A::mul(A::mul(4.0, v.alpha), gammaOf<true>(v, e))));
+  if (v.kind >= EMCGPU_VALLEY_PARABOLIC_ANISOTROP) {
+    const Vec3 ke = toEllipse<true>(v, s, k);
+    const double den = v.nonParabolic ? A::mul(v.mCond, npf) : v.mCond;
+    Vec3 ve;
+    ve.x = A::div(A::mul(A::mul(kHbar, v.vogt[0]), ke.x), den);
+    ve.y = A::div(A::mul(A::mul(kHbar, v.vogt[1]), ke.y), den);
+    ve.z = A::div(A::mul(A::mul(kHbar, v.vogt[2]), ke.z), den);
+    return toDevice<true>(v, s, ve);
+  }
+  const double f = v.nonParabolic ? A::div(kHbar, A::mul(v.mCond, npf)) : A::div(kHbar, v.mCond);
+  return Vec3{A::mul(k.x, f), A::mul(k.y, f), A::mul(k.z, f)};
+}
+
 // ---------------------------------------------------------------------------
 // Particle state held in registers during a step.
 struct Particle {

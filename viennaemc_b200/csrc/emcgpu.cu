@@ -409,6 +409,11 @@ void emcgpu_destroy(emcgpu_ctx *ctx) {
     b->release();
   for (cudaEvent_t &e : ctx->sliceEvents)
     if (e) cudaEventDestroy(e);
+  for (int b = 0; b < 2; b++) {
+    ctx->dVel[b].release();
+    if (ctx->velDone[b]) cudaEventDestroy(ctx->velDone[b]);
+    if (ctx->velCopied[b]) cudaEventDestroy(ctx->velCopied[b]);
+  }
   for (auto &t : ctx->timed) {
     cudaEventDestroy(t.a);
     cudaEventDestroy(t.b);
@@ -870,8 +875,23 @@ int bulkStepDevice(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPerLaunch, d
   P.dt = dt;
   buildFlightConsts(ctx, P);
   if (ctx->n >= (int64_t)1 << 32) return fail(ctx, EMCGPU_E_CAPACITY, "at most 2^32-1 particles per context");
+  // per-particle velocities of every step go to the host: the general step kernel writes them, chunk by chunk through two
+  // device buffers whose download (copy-out stream) overlaps the next chunk's steps
+  const bool record = ctx->velComponents != 0;
+  int recordChunk = 0;
+  if (record) {
+    if (nSteps > ctx->velHostSteps) return fail(ctx, EMCGPU_E_CAPACITY, "the velocity record holds %lld steps, %d requested", (long long)ctx->velHostSteps, nSteps);
+    const size_t perStep = (size_t)ctx->n * ctx->velComponents * sizeof(double);
+    recordChunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::min(nSteps, kMaxStepsPerLaunch), ((size_t)256 << 20) / std::max<size_t>(1, perStep)));
+    if (!ctx->copyOut) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copyOut, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) {
+      CUDA_TRY(ctx, ctx->dVel[b].ensure(perStep * recordChunk));
+      if (!ctx->velDone[b]) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->velDone[b], cudaEventDisableTiming));
+      if (!ctx->velCopied[b]) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->velCopied[b], cudaEventDisableTiming));
+    }
+  }
   // several steps per launch, plain model: flight kernel + event kernel (K1d) for ensembles that fill the machine
-  {
+  if (!record) {
     const int ppl = ctx->optSplitPpl == 2 ? 2 : 4;
     const bool split = stepsPerLaunch > 1 && nSteps > 1 && splitEligible(ctx) &&
                        (ctx->optMultiKernel == 3 ||
@@ -892,11 +912,19 @@ int bulkStepDevice(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPerLaunch, d
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dEnsembleAlt.ptr, ctx->dEnsemble.ptr, ensembleBytes(ctx->n), cudaMemcpyDeviceToDevice,
                                   ctx->stream));
   }
+  int recordIdx = 0;
   for (int done = 0; done < nSteps;) {
     int chunk = std::min(stepsPerLaunch, nSteps - done);
+    if (record) {
+      chunk = std::min(recordChunk, nSteps - done);
+      const int b = recordIdx & 1;
+      if (recordIdx >= 2) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->velCopied[b], 0)); // its last download is done
+      P.velOut = ctx->dVel[b].as<double>();
+      P.velComponents = ctx->velComponents;
+    }
     // several steps per launch: deferred-event kernel (K1c) for ensembles that fill the machine
     const int64_t nChunks = ctx->n / kDeferChunk;
-    const bool defer = chunk > 1 && !ctx->grainOn &&
+    const bool defer = !record && chunk > 1 && !ctx->grainOn &&
                        (ctx->optMultiKernel >= 2 || (ctx->optMultiKernel == 0 && nChunks >= (int64_t)ctx->smCount * kDeferWarps));
     if (defer) chunk = std::min(chunk, kDeferMaxSteps);
     P.nSteps = chunk;
@@ -923,7 +951,7 @@ int bulkStepDevice(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPerLaunch, d
       }
     }
     // the streaming one-step kernels do not carry the grain clock: with a grain mechanism the general kernel runs
-    const bool stream = chunk == 1 && !ctx->grainOn;
+    const bool stream = chunk == 1 && !ctx->grainOn && !record;
     if (stream && ctx->optKernel != 1) {
       // preferred: the TMA pipeline (tables in shared memory if they fit beside >= kMinStages ring stages)
       size_t smem = 0;
@@ -975,8 +1003,19 @@ int bulkStepDevice(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPerLaunch, d
     else
       e = launchStreamVec<4>(ctx, P, smem, grid);
     if (e != cudaSuccess) return fail(ctx, EMCGPU_E_CUDA, "bulk step launch failed: %s", cudaGetErrorString(e));
+    if (record) {
+      const int b = recordIdx & 1;
+      const size_t perStep = (size_t)ctx->n * ctx->velComponents;
+      CUDA_TRY(ctx, cudaEventRecord(ctx->velDone[b], ctx->stream));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copyOut, ctx->velDone[b], 0));
+      CUDA_TRY(ctx, cudaMemcpyAsync(ctx->velHost + (size_t)done * perStep, ctx->dVel[b].ptr, perStep * chunk * sizeof(double),
+                                    cudaMemcpyDeviceToHost, ctx->copyOut));
+      CUDA_TRY(ctx, cudaEventRecord(ctx->velCopied[b], ctx->copyOut));
+      recordIdx++;
+    }
     done += chunk;
   }
+  if (record) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copyOut));
   ctx->nextStep += nSteps;
   return EMCGPU_OK;
 }
@@ -1015,6 +1054,17 @@ int emcgpu_bulk_rewind(emcgpu_ctx *ctx) {
   swapEnsembles(ctx);
   ctx->nextStep = ctx->rewindStep;
   ctx->rewindValid = false;
+  return EMCGPU_OK;
+}
+
+int emcgpu_bulk_record_velocities(emcgpu_ctx *ctx, int components, double *host, int64_t capacitySteps) {
+  if (!ctx) return EMCGPU_E_INVALID;
+  if (components != 0 && components != 1 && components != 3)
+    return fail(ctx, EMCGPU_E_INVALID, "components must be 0 (off), 1 (v.E) or 3 (v)");
+  if (components && (!host || capacitySteps < 1)) return fail(ctx, EMCGPU_E_INVALID, "the velocity record needs a host buffer");
+  ctx->velComponents = components;
+  ctx->velHost = components ? host : nullptr;
+  ctx->velHostSteps = components ? capacitySteps : 0;
   return EMCGPU_OK;
 }
 

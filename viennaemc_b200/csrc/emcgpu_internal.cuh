@@ -73,6 +73,12 @@ struct emcgpu_ctx {
   uint32_t *dPackedAlt = nullptr;
   bool rewindValid = false;
   int64_t rewindStep = 0;
+  // emcgpu_bulk_record_velocities: per-particle velocities of the steps of the next step calls, streamed to the host
+  int velComponents = 0;
+  double *velHost = nullptr;
+  int64_t velHostSteps = 0;
+  emc::DeviceBuffer dVel[2];
+  cudaEvent_t velDone[2] = {}, velCopied[2] = {};
   // "kernel_timing": cudaEvents around the launches of the flight (0) and event (1) kernels, other kernels (2)
   bool optTiming = false;
   struct TimedLaunch {

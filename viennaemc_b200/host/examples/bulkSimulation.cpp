@@ -9,6 +9,9 @@
 //                  [--grain-rate 1/s --grain-prob p]   (grain-boundary scattering, emcGrainScatterMechanism)
 //                  [--lookahead N]   time steps a moveParticles(dt) call runs ahead on the device (default 16, 1 = none)
 //                  [--print-at S]    write the ensemble after step S (handler.print, "<prefix>Electrons<S>.txt")
+//                  [--velocities 1|3] after every step one line with v.E_dir (1) or v (3) of every particle
+//                                    (handler.printDriftVelocities / printVelocities -> "<prefix>Velocities.txt", the input of
+//                                    examples/singleLayerMoS2/calcMobilityFromVACF.py)
 //
 // --steps-per-launch > 1 uses the handler's fused entry point (several time steps per kernel
 // launch, particle state kept in registers in between); 1 is the reference's call pattern
@@ -32,7 +35,7 @@ using ParticleHandler = basicBulkParticleHandler<NumType, DeviceType>;
 
 int main(int argc, char **argv) {
   double particles = 12500, field = 1e6, dt = 1e-16, temperature = 300, doping = 1e23, grainRate = 0, grainProb = 0.5;
-  long steps = 40000, stepsPerLaunch = 1, lookahead = 0, printAt = -1;
+  long steps = 40000, stepsPerLaunch = 1, lookahead = 0, printAt = -1, velocities = 0;
   unsigned long seed = 0;
   std::string prefix = "bulkSimulation";
   for (int i = 1; i + 1 < argc; i += 2) {
@@ -46,6 +49,7 @@ int main(int argc, char **argv) {
     else if (key == "--prefix") prefix = val;
     else if (key == "--lookahead") lookahead = std::stol(val);
     else if (key == "--print-at") printAt = std::stol(val);
+    else if (key == "--velocities") velocities = std::stol(val);
     else if (key == "--temperature") temperature = std::stod(val);
     else if (key == "--doping") doping = std::stod(val);
     else if (key == "--grain-rate") grainRate = std::stod(val);
@@ -83,6 +87,9 @@ int main(int argc, char **argv) {
   avgDriftVel[0] = handler.getAvgDriftVelocity(0);
   valleyOcc[0] = handler.getValleyOccupationProbability(0);
 
+  std::ofstream velFileOut;
+  if (velocities)
+    velFileOut.open(prefix + "Velocities.txt");
   std::cout << "Starting Simulation ...\n";
   const auto start = std::chrono::high_resolution_clock::now();
   if (stepsPerLaunch <= 1) {
@@ -93,6 +100,10 @@ int main(int argc, char **argv) {
       valleyOcc[s] = handler.getValleyOccupationProbability(0);
       if (s == printAt)
         handler.print(prefix, std::to_string(s));
+      if (velocities == 1)
+        handler.printDriftVelocities(velFileOut);
+      else if (velocities == 3)
+        handler.printVelocities(velFileOut);
     }
   } else {
     std::vector<double> series;

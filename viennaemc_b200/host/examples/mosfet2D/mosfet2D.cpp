@@ -37,7 +37,7 @@ NumType adaptPotential(const NumType &pot, const DeviceType &device) {
 
 int main(int argc, char **argv) {
   double vd = 1., vg = 1., dt = 1.5e-16, roughness = -1;
-  long steps = 66667, transient = 33334, avg = 6667, poissonInterval = 1, progress = 1000, redBlack = 0;
+  long steps = 66667, transient = 33334, avg = 6667, poissonInterval = 1, progress = 1000, redBlack = 1;
   unsigned long seed = 0;
   bool seeded = false;
   std::string prefix = "mosfet";

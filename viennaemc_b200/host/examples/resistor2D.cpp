@@ -33,7 +33,7 @@ using SimulationType = emcSimulation<NumType, DeviceType, PoissonSolver, Particl
 int main(int argc, char **argv) {
   double voltage = 0.05, dt = 1e-15, doping = 1e22, lx = 1e-6, ly = 1e-6, hx = 1e-8, hy = 5e-8, width = 1e-6, grainRate = 0,
          grainProb = 1;
-  long steps = 50000, transient = 20000, avg = 20000, carriers = 1, poissonInterval = 1, progress = 5000, redBlack = 0;
+  long steps = 50000, transient = 20000, avg = 20000, carriers = 1, poissonInterval = 1, progress = 5000, redBlack = 1;
   unsigned long seed = 0;
   bool seeded = false;
   std::string prefix = "resistor";

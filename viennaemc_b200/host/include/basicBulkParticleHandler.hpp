@@ -73,6 +73,11 @@ private:
     std::vector<double> ahead;
     SizeType aheadN = 0, aheadServed = 0;
     T aheadDt = 0;
+    // per-particle velocities of the steps of the current window (printDriftVelocities / printVelocities): recorded by
+    // the step kernels once a driver has asked for them (components: 0 = not yet, 1 = v.E_dir, 3 = v), [step][particle][c]
+    int recordVel = 0;
+    std::vector<double> velAhead;
+    SizeType velSteps = 0; // steps of the current window velAhead holds
   };
 
   DeviceType &device;
@@ -104,6 +109,7 @@ private:
     if (st.ctx && st.aheadServed < st.aheadN) {
       emcgpu::require(st.ctx, emcgpu_bulk_rewind(st.ctx), "emcgpu_bulk_rewind");
       if (st.aheadServed > 0) {
+        emcgpu::require(st.ctx, emcgpu_bulk_record_velocities(st.ctx, 0, nullptr, 0), "emcgpu_bulk_record_velocities");
         std::vector<double> again(st.aheadServed * idxTypeToPartType.at(idxType)->getNrValleys() * 3);
         emcgpu::require(st.ctx,
                         emcgpu_bulk_step(st.ctx, st.aheadDt, static_cast<int>(st.aheadServed), static_cast<int>(st.aheadServed),
@@ -112,6 +118,7 @@ private:
       }
     }
     st.aheadN = st.aheadServed = 0;
+    st.velSteps = 0;
   }
   void materializeAll() const {
     for (auto &[idxType, st] : state) {
@@ -201,9 +208,13 @@ public:
       : device(inDevice), idxTypeToPartType(inTypes), appliedFieldDir(inFieldDirection), fieldStrength(inFieldStrength) {
     normalize(appliedFieldDir);
     appliedField = scale(appliedFieldDir, inFieldStrength);
+    // (EMCGPU_SEED replaces the clock of an unseeded handler: reproducible runs of an unmodified main())
+    const char *envSeed = std::getenv("EMCGPU_SEED");
     const unsigned long seed =
         inSeed != 0 ? inSeed
-                    : static_cast<unsigned long>(std::chrono::high_resolution_clock::now().time_since_epoch().count());
+        : (envSeed && *envSeed)
+            ? std::strtoul(envSeed, nullptr, 10)
+            : static_cast<unsigned long>(std::chrono::high_resolution_clock::now().time_since_epoch().count());
     hostRng.seed(seed);
     stepSeed = seed;
     for (const auto &[idxType, type] : idxTypeToPartType) {
@@ -311,7 +322,18 @@ public:
       materialize(idxType);
       upload(idxType);
       refreshModel(idxType);
-      const SizeType nAhead = (st.phononBaths.empty() && !st.grain) ? lookahead : 1;
+      SizeType nAhead = (st.phononBaths.empty() && !st.grain) ? lookahead : 1;
+      st.velSteps = 0;
+      if (st.recordVel) { // the window's velocities come back with it (at most 1 GB of them per window)
+        const SizeType perStep = st.nrParticles * st.recordVel;
+        nAhead = std::max<SizeType>(1, std::min<SizeType>(nAhead, (SizeType(1) << 27) / std::max<SizeType>(1, perStep)));
+        st.velAhead.resize(nAhead * perStep);
+        emcgpu::require(st.ctx, emcgpu_bulk_record_velocities(st.ctx, st.recordVel, st.velAhead.data(), static_cast<int64_t>(nAhead)),
+                        "emcgpu_bulk_record_velocities");
+        st.velSteps = nAhead;
+      } else {
+        emcgpu::require(st.ctx, emcgpu_bulk_record_velocities(st.ctx, 0, nullptr, 0), "emcgpu_bulk_record_velocities");
+      }
       if (nAhead > 1) {
         st.ahead.assign(nAhead * nObs, 0.);
         emcgpu::require(st.ctx,
@@ -427,7 +449,24 @@ private:
       if (!type->isMoved())
         continue;
       HostEnsemble h;
-      const auto &st = state.at(idxType);
+      auto &st = state.at(idxType);
+      const int comps = projected ? 1 : 3;
+      // the step kernels recorded the velocities of the driver's current step: one line from the record
+      const SizeType cur = st.aheadN ? st.aheadServed : (st.velSteps ? 1 : 0); // 1-based step of the window
+      if (st.recordVel == comps && cur >= 1 && cur <= st.velSteps && st.obsValid) {
+        const double *v = st.velAhead.data() + (cur - 1) * st.nrParticles * comps;
+        for (SizeType i = 0; i < st.nrParticles; i++) {
+          if (projected)
+            os << v[i];
+          else
+            os << std::array<T, 3>{v[3 * i], v[3 * i + 1], v[3 * i + 2]};
+          if (i + 1 < st.nrParticles)
+            os << " ";
+        }
+        os << std::endl;
+        continue;
+      }
+      st.recordVel = comps; // from the next launch on the kernels record them
       const HostEnsemble *src = &st.staging;
       if (st.uploaded) {
         download(idxType, h);

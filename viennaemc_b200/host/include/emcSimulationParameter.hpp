@@ -5,6 +5,7 @@
 #define EMC_SIMULATION_PARAMETER_HPP
 
 #include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <iostream>
 #include <map>
@@ -27,7 +28,15 @@ template <class T, class DeviceType> class emcSimulationParameter {
   T (*adaptPotentialForWrite)(const T &, const DeviceType &) = nullptr;
   MapIdxToParticleTypes particleTypes;
   // unseeded runs differ from run to run, like the reference's
-  SizeType seedRNG = std::chrono::high_resolution_clock::now().time_since_epoch().count();
+  // (the environment variable EMCGPU_SEED replaces the clock: an unmodified main() that never calls setSeed becomes
+  // reproducible, which the statistical tests of the drop-in use)
+  SizeType seedRNG = defaultSeed();
+  static SizeType defaultSeed() {
+    if (const char *e = std::getenv("EMCGPU_SEED"))
+      if (*e)
+        return static_cast<SizeType>(std::strtoull(e, nullptr, 10));
+    return std::chrono::high_resolution_clock::now().time_since_epoch().count();
+  }
 
   static void error(const char *text) { emcMessage::getInstance().addError(text).print(); }
   void checkTimes() const {
