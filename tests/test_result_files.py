@@ -57,11 +57,18 @@ def test_same_layout_as_the_reference_files(ours, theirs, kind):
         assert {len(r) for r in a[1:]} == {len(r) for r in b[1:]}
     else:
         assert {len(r) for r in a} == {len(r) for r in b}
-    # every field parses as the same kind of number (integers stay integers: indices, counts)
-    for ra, rb in zip(a[1:20], b[1:20]):
+    # every field parses as a number; the integer columns are written as integers (particle index, sub-valley, valley;
+    # netto particle counts of the current file)
+    if kind == "particle":  # idx, pos (2 or 3), [k (3), energy, sub-valley, valley[, tau]]
+        dim = len(b[0])
+        int_cols = [0] + ([dim + 5, dim + 6] if len(b[1]) > dim + 1 else [])
+    else:
+        int_cols = [1, 2] if kind == "current" else []
+    for ra, rb in zip(a[1:40], b[1:40]):
         for x, y in zip(ra, rb):
             float(x), float(y)
-            assert x.lstrip("-").isdigit() == y.lstrip("-").isdigit() or float(x) == float(y) == 0.0 or kind in ("grid", "avg", "current")
+        for c in int_cols:
+            assert ra[c].lstrip("-").isdigit() and rb[c].lstrip("-").isdigit(), (c, ra[c], rb[c])
 
 
 def test_rate_files_agree_with_the_reference_to_their_six_digits():
@@ -86,7 +93,16 @@ def test_the_reference_readers_read_our_files(capsys):
     for ours, theirs, kind in PAIRS:
         pa, pb = os.path.join(OUR_DIR, ours), os.path.join(REF_DIR, theirs)
         if kind == "particle":
-            (da, ma), (db, mb) = rr.readParticleFile(pa, return_maxPos=True), rr.readParticleFile(pb, return_maxPos=True)
+            def read(path):
+                try:
+                    return rr.readParticleFile(path, return_maxPos=True)
+                except SystemExit:  # the helper gives up on 3-D files without a tau column -- the reference's own included
+                    return None
+            ra_, rb_ = read(pa), read(pb)
+            assert (ra_ is None) == (rb_ is None), (ours, "the reference's reader treats the two files differently")
+            if ra_ is None:
+                continue
+            (da, ma), (db, mb) = ra_, rb_
             assert list(da.columns) == list(db.columns) and ma.shape == mb.shape and np.allclose(ma, mb)
             assert list(da.dtypes) == list(db.dtypes)
             assert (da["idx"].to_numpy() == np.arange(len(da))).all()

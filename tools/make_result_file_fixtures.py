@@ -22,13 +22,19 @@ def cut(src, dst):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    # one working directory per driver: both write the per-mechanism rate files (tabulated up to the particle type's
+    # maximal energy, 4 eV in the resistor, 1 eV in the bulk example); the resistor's are kept, like in the reference set
     with tempfile.TemporaryDirectory() as work:
         subprocess.check_call([os.path.join(BIN, "resistor2D"), "--steps", "3000", "--transient", "1000", "--avg", "1000", "--seed", "4",
                                "--prefix", "resistorV50as1000"], cwd=work, stdout=subprocess.DEVNULL)
+        for name in sorted(os.listdir(work)):
+            cut(os.path.join(work, name), os.path.join(OUT, name))
+    with tempfile.TemporaryDirectory() as work:
         subprocess.check_call([os.path.join(BIN, "bulkSimulation"), "--steps", "300", "--seed", "4", "--print-at", "300"], cwd=work,
                               stdout=subprocess.DEVNULL)
         for name in sorted(os.listdir(work)):
-            cut(os.path.join(work, name), os.path.join(OUT, name))
+            if name.startswith("bulkSimulation"):
+                cut(os.path.join(work, name), os.path.join(OUT, name))
     print(sorted(os.listdir(OUT)))
 
 

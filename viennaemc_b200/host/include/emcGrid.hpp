@@ -151,12 +151,27 @@ public:
       data[i] -= rhs.data[i];
     return *this;
   }
+  // extent line, then rows of x-values, a blank line between z-planes (the layout of the reference's emcGrid::print,
+  // include/emcGrid.hpp:143-165, which helper/emcPlottingFiles/readResultFile.py:readGridFile reads)
   void print(std::ostream &out = std::cout) const {
+    out << extent << "\n";
     CoordVec c;
     for (c.fill(0); !isEndCoord(c); advanceCoord(c)) {
+      if (c[0] == 0) {
+        bool first = true;
+        for (SizeType d = 1; d < Dim; d++)
+          first = first && c[d] == 0;
+        if (!first) {
+          out << "\n";
+          if (Dim > 2 && c[1] == 0)
+            out << "\n";
+        }
+      }
       out << data[flat(c)];
-      out << (c[0] + 1 == extent[0] ? "\n" : " ");
+      if (c[0] + 1 != extent[0])
+        out << " ";
     }
+    out << "\n";
   }
 };
 
