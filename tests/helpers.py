@@ -15,7 +15,24 @@ STATE_RTOL = 1e-12
 
 
 def load_golden(case):
-    return np.load(os.path.join(GOLDEN_DIR, case + ".npz"))
+    g = np.load(os.path.join(GOLDEN_DIR, case + ".npz"))
+    if "draws" in g.files or "draws_count" not in g.files:
+        return g
+    # large fixture without the raw draws: they are the mt19937_64 stream of the case's seed -- regenerate them and hold them
+    # against the digest of what the reference's recorder saw
+    import hashlib
+    from scenarios import GOLDEN_CASES
+    class _Golden(dict):  # like NpzFile: the names of the arrays in .files
+        @property
+        def files(self):
+            return list(self.keys())
+
+    d = _Golden((k, g[k]) for k in g.files)
+    draws = po.mt_fill(int(GOLDEN_CASES[case]["args"]["seed"]), int(d["draws_count"][0]))
+    assert hashlib.sha256(draws.tobytes()).digest() == d["draws_sha256"].tobytes(), "regenerated draws differ from the recording"
+    d["draws"] = draws
+    d["events"] = d["events"].astype(np.int64)
+    return d
 
 
 def golden_ensemble(g, prefix):

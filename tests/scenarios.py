@@ -91,6 +91,14 @@ GOLDEN_CASES = {
         args=dict(material="mixed", mechs="acoustic,zero,first,coulomb", cells=2, box=1e-7, doping=1e23,
                   field=2e6, fdir="0.3,-1,0.2", dt=2e-15, steps=80, seed=11, levels=250, emax=2.0),
         builder="mixed", kwargs=dict(mechs=("acoustic", "zero", "first", "coulomb"), n_levels=250, max_energy=2.0)),
+    # the shipped bulkSimulation example at its own size: 12 500 electrons (box 5e-7 m, 5 cells per edge), 1000 time steps.
+    # The fixture does not store the ~0.8 million raw draws (incompressible): they ARE the mt19937_64 stream of the seed
+    # (tests/test_oracle_golden.py checks that for every fixture); it stores their count and a digest of the recorded
+    # stream, helpers.load_golden() regenerates and verifies them.
+    "si_bulk_config1": dict(
+        args=dict(material="si", mechs="acoustic,zero,first", cells=5, box=5e-7, doping=1e23, field=1e6,
+                  fdir="-1,0,0", dt=1e-16, steps=1000, seed=2026, levels=1000, emax=1.0),
+        builder="si", kwargs=dict(mechs=("acoustic", "zero", "first"), n_levels=1000, max_energy=1.0), strip_draws=True),
     # grain boundaries: a second free-flight clock with a reflect / transmit hemisphere sampler (emcGrainScatterMechanism)
     "si_grain": dict(
         args={"material": "si", "mechs": "acoustic,zero,first", "cells": 2, "box": 1e-7, "doping": 1e23, "field": 2e6,

@@ -42,9 +42,11 @@ def z_scores(gpu, ref):
     s = pooled_sigma(gpu, ref)
     diff = gpu.mean(axis=0) - ref.mean(axis=0)
     se = s * np.sqrt(1.0 / ng + 1.0 / nr)
+    # a "scatter" at rounding level (means of identical numbers) is no scatter: such points must simply agree
     scale = np.maximum(np.abs(ref.mean(axis=0)), 1e-300)
+    pinned = se <= 1e-12 * scale
     with np.errstate(divide="ignore", invalid="ignore"):
-        z = np.where(se > 0, diff / se, np.where(np.abs(diff) <= 1e-9 * scale, 0.0, np.inf))
+        z = np.where(pinned, np.where(np.abs(diff) <= 1e-9 * scale, 0.0, np.inf), diff / np.where(pinned, 1.0, se))
     return z
 
 

@@ -65,6 +65,17 @@ def build_emchost(force: bool = False) -> str:
     return target
 
 
+def build_emcnccl(force: bool = False) -> str:
+    """libemcnccl.so: ncclAllReduce behind the all-reduce callback of the sharded device run (include/emcnccl.h).  Links the
+    NCCL of the system; in a process that has loaded torch the loader resolves libnccl.so.2 to torch's copy."""
+    target = os.path.join(LIBDIR, "libemcnccl.so")
+    src = os.path.join(PKG, "csrc", "emcnccl.cpp")
+    if force or _newer(target, [src, os.path.join(ROOT, "include", "emcnccl.h")]):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I", "/usr/local/cuda/include", "-o", target, src,
+                               "-L", "/usr/local/cuda/lib64", "-lcudart", "-lnccl"])
+    return target
+
+
 def build_examples(force: bool = False) -> dict:
     """Example drivers on top of the drop-in headers.  `reference_bulkSimulation_gpu` is the UNMODIFIED
     main() of the reference's examples/bulkSimulation/bulkSimulation.cpp compiled against OUR headers
@@ -75,8 +86,9 @@ def build_examples(force: bool = False) -> dict:
     os.makedirs(bindir, exist_ok=True)
     out = {}
     common = ["g++", *HOST_FLAGS, "-I", HOST_INC, "-I", os.path.join(ROOT, "include")]
-    link = ["-L", LIBDIR, "-lemcgpu", "-Wl,-rpath,$ORIGIN/../lib"]
-    deps = _sources(os.path.join(PKG, "host"), os.path.join(ROOT, "include")) + [os.path.join(LIBDIR, "libemcgpu.so")]
+    link = ["-L", LIBDIR, "-lemcgpu", "-lemcnccl", "-Wl,-rpath,$ORIGIN/../lib"]
+    deps = _sources(os.path.join(PKG, "host"), os.path.join(ROOT, "include")) + [os.path.join(LIBDIR, "libemcgpu.so"),
+                                                                                 os.path.join(LIBDIR, "libemcnccl.so")]
     for name in ("bulkSimulation", "resistor2D", os.path.join("mosfet2D", "mosfet2D"),
                  os.path.join("hotPhononGa2O3", "hotPhononGa2O3")):
         own = os.path.join(PKG, "host", "examples", name + ".cpp")
@@ -128,7 +140,7 @@ def build_examples(force: bool = False) -> dict:
 
 
 def build_all(force: bool = False) -> dict:
-    out = {"emcgpu": build_emcgpu(force), "emchost": build_emchost(force)}
+    out = {"emcgpu": build_emcgpu(force), "emcnccl": build_emcnccl(force), "emchost": build_emchost(force)}
     out.update(build_examples(force))
     return out
 

@@ -409,10 +409,12 @@ class Context:
     def device_set_surface(self, face, kind, parameter):
         self._chk(self.L.emcgpu_device_set_surface(self.h, face, kind, parameter))
 
-    def device_set_sharding(self, rank, world, callback):
-        """callback: ctypes CFUNCTYPE(None, c_void_p user, c_void_p deviceBuffer, c_int64 count, c_void_p stream)"""
+    def device_set_sharding(self, rank, world, callback, user=None):
+        """callback: ctypes CFUNCTYPE(None, c_void_p user, c_void_p deviceBuffer, c_int64 count, c_void_p stream), or the
+        address of a C function with that signature (libemcnccl: emcnccl_allreduce_sum_f64, user = the communicator)"""
         self._sharding_cb = callback
-        self._chk(self.L.emcgpu_device_set_sharding(self.h, rank, world, C.cast(callback, C.c_void_p) if callback else None, None))
+        fn = callback if isinstance(callback, (int, C.c_void_p)) or callback is None else C.cast(callback, C.c_void_p)
+        self._chk(self.L.emcgpu_device_set_sharding(self.h, rank, world, fn, user))
 
     def device_set_particle_kind(self, kind):
         self._chk(self.L.emcgpu_device_set_particle_kind(self.h, kind))

@@ -20,7 +20,14 @@
 #include <detail/emcBulkEnsembleBuilder.hpp>
 #include <detail/emcDeviceFlatten.hpp>
 #include <emcGpuBinding.hpp>
+#include <emcnccl.h>
 
+// SEVERAL GPUs: started once per GPU with EMCGPU_SHARD=1 and the usual launcher variables RANK, WORLD_SIZE,
+// LOCAL_RANK (torchrun --no-python, mpirun, a shell loop) plus EMCNCCL_ID_FILE (a path all ranks can reach), every process
+// creates the same initial ensemble (same seed), keeps its block of the particles and joins one NCCL communicator
+// (libemcnccl).  Potential, field and concentration are replicated; per step the library all-reduces the reservoir share
+// table and the carriers-per-grid-point grid over NVLink (emcgpu_device_set_sharding).  Counters and ensemble sizes the
+// host sees are sums over the ranks; grid and current files are written by rank 0, particle files per rank.
 template <class T, class DeviceType, class PMScheme, SizeType Dim = DeviceType::Dimension>
 class emcBasicParticleHandler : public emcAbstractParticleHandler<T, DeviceType, PMScheme, Dim> {
   typedef emcAbstractParticleHandler<T, DeviceType, PMScheme, Dim> Base;
@@ -39,23 +46,39 @@ private:
   emcdetail::HostEnsemble staging;
   bool uploaded = false;
   bool grain = false; // the type carries a grain mechanism: its clocks live on the device
+  // several GPUs: this process holds the particles [shardFirst, shardFirst + shardCount) of the initial ensemble
+  int shardRank = 0, shardWorld = 1;
+  emcnccl_comm *comm = nullptr;
+  SizeType shardFirst = 0, shardCount = 0;
+
+  static int envInt(const char *name, int def) {
+    const char *e = std::getenv(name);
+    return (e && *e) ? std::atoi(e) : def;
+  }
 
   SizeType nrOnGpu() const { return uploaded ? static_cast<SizeType>(emcgpu_ensemble_size(ctx)) : staging.size(); }
 
   void upload() {
     if (uploaded)
       return;
+    // contiguous blocks whose sizes differ by at most one (viennaemc_b200/sharding.py: shard_range)
+    const SizeType base = staging.size() / shardWorld, rem = staging.size() % shardWorld;
+    shardFirst = shardRank * base + std::min<SizeType>(shardRank, rem);
+    shardCount = base + (static_cast<SizeType>(shardRank) < rem ? 1 : 0);
     const double *ptrs[EMCGPU_N_STREAMS];
     for (int s = 0; s < EMCGPU_N_STREAMS; s++)
-      ptrs[s] = staging.stream[s].data();
-    emcgpu::require(ctx, emcgpu_set_ensemble(ctx, static_cast<int64_t>(staging.size()), ptrs, staging.packed.data(), 0),
+      ptrs[s] = staging.stream[s].data() + shardFirst;
+    // particle ids (they key the Philox streams) of different ranks never meet: rank << 40
+    emcgpu::require(ctx,
+                    emcgpu_set_ensemble(ctx, static_cast<int64_t>(shardCount), ptrs, staging.packed.data() + shardFirst,
+                                        static_cast<int64_t>(shardRank) << 40),
                     "emcgpu_set_ensemble");
-    if (grain && staging.size())
-      emcgpu::require(ctx, emcgpu_set_grain_clock(ctx, staging.grainTau.data()), "emcgpu_set_grain_clock");
+    if (grain && shardCount)
+      emcgpu::require(ctx, emcgpu_set_grain_clock(ctx, staging.grainTau.data() + shardFirst), "emcgpu_set_grain_clock");
     emcgpu::require(ctx, emcgpu_rng_philox(ctx, seed), "emcgpu_rng_philox");
     emcgpu::require(ctx, emcgpu_set_step_index(ctx, 1), "emcgpu_set_step_index");
     // head room for injected particles: avoids re-allocations during the run
-    emcgpu::require(ctx, emcgpu_device_reserve(ctx, static_cast<int64_t>(staging.size() * 1.25) + 1024),
+    emcgpu::require(ctx, emcgpu_device_reserve(ctx, static_cast<int64_t>(shardCount * 1.25) + 1024),
                     "emcgpu_device_reserve");
     uploaded = true;
   }
@@ -94,11 +117,25 @@ public:
       emcMessage::getInstance()
           .addError("The GPU particle handler moves exactly one particle type (found " + std::to_string(moved) + ").")
           .print();
-    const char *e = std::getenv("EMCGPU_DEVICE");
-    if (emcgpu_create(e ? std::atoi(e) : 0, &ctx) != EMCGPU_OK)
+    if (envInt("EMCGPU_SHARD", 0)) {
+      shardWorld = std::max(1, envInt("WORLD_SIZE", 1));
+      shardRank = envInt("RANK", 0);
+    }
+    const int ordinal = envInt("EMCGPU_DEVICE", shardWorld > 1 ? envInt("LOCAL_RANK", shardRank) : 0);
+    if (emcgpu_create(ordinal, &ctx) != EMCGPU_OK)
       emcMessage::getInstance()
           .addError(std::string("cannot create the GPU context: ") + emcgpu_last_error(nullptr))
           .print();
+    if (shardWorld > 1) {
+      const char *idFile = std::getenv("EMCNCCL_ID_FILE");
+      if (!idFile || emcnccl_init_from_file(idFile, shardRank, shardWorld, ordinal, 120., &comm) != 0)
+        emcMessage::getInstance()
+            .addError(std::string("sharded run: cannot join the NCCL communicator (EMCNCCL_ID_FILE must name a file all "
+                                  "ranks can reach): ") + emcnccl_last_error())
+            .print();
+      emcgpu::require(ctx, emcgpu_device_set_sharding(ctx, shardRank, shardWorld, emcnccl_allreduce_sum_f64, comm),
+                      "emcgpu_device_set_sharding");
+    }
     auto &type = *this->idxTypeToPartType.at(gpuType);
     emcgpu::uploadParticleType(ctx, type);
     grain = emcgpu::uploadGrainMechanism(ctx, type);
@@ -134,14 +171,68 @@ public:
   ~emcBasicParticleHandler() override {
     if (ctx)
       emcgpu_destroy(ctx);
+    if (comm)
+      emcnccl_destroy(comm);
   }
+
+  // --- several GPUs ---
+  bool isSharded() const { return shardWorld > 1; }
+  int shardRankOf() const { return shardRank; }
+  int shardWorldSize() const { return shardWorld; }
+  bool isShardRoot() const { return shardRank == 0; }
+  // in-place sum over the ranks of a small host array (no-op on one GPU)
+  void sumOverRanks(std::vector<double> &v) const {
+    if (comm && !v.empty() && emcnccl_allreduce_sum_host_f64(comm, v.data(), static_cast<int64_t>(v.size())) != 0)
+      emcMessage::getInstance().addError(std::string("sharded run: all-reduce failed: ") + emcnccl_last_error()).print();
+  }
+  void sumOverRanks(std::vector<int32_t> &v) const {
+    if (!comm)
+      return;
+    std::vector<double> d(v.begin(), v.end());
+    sumOverRanks(d);
+    for (SizeType i = 0; i < v.size(); i++)
+      v[i] = static_cast<int32_t>(d[i]);
+  }
+  // true if `data` is bit for bit the same on every rank (the replicated grids must be): the ranks compare 16-bit pieces
+  // of a checksum through sum and sum of squares -- sum(p^2) * W == sum(p)^2 holds only if all p are equal (integers, exact)
+  bool identicalOnAllRanks(const double *data, SizeType n) const {
+    if (!comm)
+      return true;
+    uint64_t h = 1469598103934665603ull;
+    const unsigned char *b = reinterpret_cast<const unsigned char *>(data);
+    for (SizeType i = 0; i < n * sizeof(double); i++)
+      h = (h ^ b[i]) * 1099511628211ull;
+    std::vector<double> v(8);
+    for (int k = 0; k < 4; k++) {
+      const double p = static_cast<double>((h >> (16 * k)) & 0xffffu);
+      v[k] = p;
+      v[4 + k] = p * p;
+    }
+    sumOverRanks(v);
+    for (int k = 0; k < 4; k++)
+      if (v[4 + k] * shardWorld != v[k] * v[k])
+        return false;
+    return true;
+  }
+  int64_t allReduceCalls() const { return comm ? emcnccl_calls(comm) : 0; }
+  int64_t allReduceBytes() const { return comm ? emcnccl_bytes(comm) : 0; }
 
   // the context that holds the ensemble and the grids of the run (emcSimulation, emcSORSolver::attach, tests)
   emcgpu_ctx *gpuContext() { return ctx; }
   SizeType gpuParticleType() const { return gpuType; }
 
   bool calcsPartPartInteraction() const override { return false; }
-  SizeType getNrParticles(SizeType idxType) const { return idxType == gpuType ? nrOnGpu() : 0; }
+  // particles of the whole simulation (summed over the ranks of a sharded run)
+  SizeType getNrParticles(SizeType idxType) const {
+    if (idxType != gpuType)
+      return 0;
+    if (!comm || !uploaded)
+      return nrOnGpu();
+    std::vector<double> n(1, static_cast<double>(nrOnGpu()));
+    sumOverRanks(n);
+    return static_cast<SizeType>(n[0]);
+  }
+  SizeType getNrParticlesOfThisRank(SizeType idxType) const { return idxType == gpuType ? nrOnGpu() : 0; }
   void printNrParticles() const override {
     for (const auto &[idxType, type] : this->idxTypeToPartType)
       std::cout << "\t" << getNrParticles(idxType) << " " << type->getName() << "\n";
@@ -203,7 +294,8 @@ public:
   // "<prefix><TypeName><suffix>.txt": box extent, then per particle: index, position, k, energy, sub-valley, valley, tau
   void print(std::string namePrefix, std::string nameSuffix) override {
     for (const auto &[idxType, type] : this->idxTypeToPartType) {
-      std::ofstream os(namePrefix + type->getName() + nameSuffix + ".txt");
+      // sharded run: every rank writes the particles it holds, "<...>.rank<r>.txt"
+      std::ofstream os(namePrefix + type->getName() + nameSuffix + (comm ? ".rank" + std::to_string(shardRank) : std::string()) + ".txt");
       os << this->device.getMaxPos() << "\n";
       if (idxType != gpuType)
         continue;
@@ -234,14 +326,16 @@ public:
     emcdetail::HostEnsemble h;
     download(h);
     const auto &type = *this->idxTypeToPartType.at(idxType);
-    T sumVx = 0;
+    double sumVx = 0;
     for (SizeType i = 0; i < h.size(); i++) {
       if (h.stream[EMCGPU_X][i] < x0 || h.stream[EMCGPU_X][i] > x1)
         continue;
       const std::array<T, 3> k = {h.stream[EMCGPU_KX][i], h.stream[EMCGPU_KY][i], h.stream[EMCGPU_KZ][i]};
       sumVx += type.getValley(h.packed[i] & 0xffu)->getVelocity(k, h.stream[EMCGPU_ENERGY][i], (h.packed[i] >> 8) & 0xffu)[0];
     }
-    return constants::q * this->nrCarriersPerPart * sumVx / channelLength;
+    std::vector<double> total(1, sumVx);
+    sumOverRanks(total);
+    return constants::q * this->nrCarriersPerPart * total[0] / channelLength;
   }
 };
 

@@ -138,6 +138,7 @@ public:
                                                   solver.getAccuracy(), solver.getOmega(), step == 0 ? 1 : 0, counters.data(),
                                                   sweeps.data()),
                       "emcgpu_device_run_averaging");
+      particleHandler.sumOverRanks(counters); // sharded run: the terminal currents count the particles of all ranks
       for (SizeType s = 0; s < n; s++) {
         totalSorSweeps += sweeps[s];
         if (step + s < nrTransient)
@@ -163,7 +164,18 @@ public:
     fetchCurrentGrids();
     fetch(EMCGPU_GRID_SUM_POTENTIAL, results.avgPot);
     fetch(EMCGPU_GRID_SUM_CONCENTRATION, results.avgConc[gpuType]);
-    results.writeFinalResults(device);
+    if (particleHandler.isSharded()) {
+      // every rank solved the same Poisson problem on the same (all-reduced) charge: the grids must agree bit for bit
+      const bool same = particleHandler.identicalOnAllRanks(results.currPot.raw(), results.currPot.getSize()) &&
+                        particleHandler.identicalOnAllRanks(results.avgConc[gpuType].raw(), results.avgConc[gpuType].getSize());
+      if (!same)
+        emcMessage::getInstance().addError("sharded run: the replicated potential / concentration differ between the ranks.").print();
+      std::cout << "Sharded run: " << particleHandler.shardWorldSize() << " ranks, potential and averaged concentration "
+                << "identical on all ranks, " << particleHandler.allReduceCalls() << " all-reduces ("
+                << particleHandler.allReduceBytes() << " bytes) on this rank" << std::endl;
+    }
+    if (particleHandler.isShardRoot())
+      results.writeFinalResults(device);
     particleHandler.print(param.namePrefix, "Final");
   }
 
@@ -188,7 +200,8 @@ private:
     std::cout << "\tNr. Iteration: \t\t" << nrStep << " / " << param.getNrSteps() << std::endl;
   }
   void writeCurrentResultsToFiles(std::string nameSuffix) {
-    results.writeCurrentResults(nameSuffix, device);
+    if (particleHandler.isShardRoot()) // the grids are replicated: rank 0 writes them
+      results.writeCurrentResults(nameSuffix, device);
     particleHandler.print(param.namePrefix, nameSuffix);
   }
 

@@ -104,3 +104,61 @@ class DeviceRunSharding:
         t = torch.as_tensor(np.ascontiguousarray(counters, dtype=np.int64)).cuda()
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t.cpu().numpy()
+
+
+class NcclDeviceRunSharding:
+    """Sharded device run with the library's exchange going straight to ncclAllReduce (libemcnccl.so, include/emcnccl.h):
+    the all-reduce callback is a C function, no Python between the step kernels.  torch.distributed only carries the 128-byte
+    unique id from rank 0 to the other ranks (any backend)."""
+
+    def __init__(self, ctx, group=None):
+        import ctypes as C
+        import os
+
+        import torch.distributed as dist
+
+        lib_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libemcnccl.so")
+        if not os.path.exists(lib_path):
+            raise ImportError(f"{lib_path} is missing: build it with `python -m viennaemc_b200.build`")
+        self.L = C.CDLL(lib_path)
+        self.L.emcnccl_last_error.restype = C.c_char_p
+        self.L.emcnccl_init.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        self.L.emcnccl_calls.restype = C.c_int64
+        self.L.emcnccl_calls.argtypes = [C.c_void_p]
+        self.L.emcnccl_bytes.restype = C.c_int64
+        self.L.emcnccl_bytes.argtypes = [C.c_void_p]
+        self.L.emcnccl_destroy.argtypes = [C.c_void_p]
+        self.ctx, self.group = ctx, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        ident = C.create_string_buffer(128)
+        if self.rank == 0 and self.L.emcnccl_unique_id(ident) != 0:
+            raise RuntimeError(self.L.emcnccl_last_error().decode())
+        box = [ident.raw]
+        dist.broadcast_object_list(box, src=0, group=group)
+        self.comm = C.c_void_p()
+        if self.L.emcnccl_init(box[0], self.rank, self.world, ctx.device, C.byref(self.comm)) != 0:
+            raise RuntimeError(self.L.emcnccl_last_error().decode())
+        fn = C.cast(self.L.emcnccl_allreduce_sum_f64, C.c_void_p)
+        ctx.device_set_sharding(self.rank, self.world, fn, self.comm)
+
+    @property
+    def calls(self):
+        return int(self.L.emcnccl_calls(self.comm))
+
+    @property
+    def bytes(self):
+        return int(self.L.emcnccl_bytes(self.comm))
+
+    def sum_counters(self, counters):
+        import torch
+        import torch.distributed as dist
+
+        t = torch.as_tensor(np.ascontiguousarray(counters, dtype=np.int64)).cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy()
+
+    def close(self):
+        if self.comm:
+            self.ctx.device_set_sharding(0, 1, None)
+            self.L.emcnccl_destroy(self.comm)
+            self.comm = None
