@@ -277,6 +277,45 @@ def device_run_numbers(budget_s=60.0):
     return out
 
 
+def sharded_device_runs(rank, world, local_rank, id_dir):
+    """Configs 3 and 4 on ALL GPUs of the run: the drop-in C++ drivers started once per GPU (this process
+    starts the one of its rank), particles split over the ranks, grids replicated, the library's per-step exchange
+    (reservoir share table, carriers-per-grid-point grid) as ncclAllReduce over NVLink through libemcnccl.  emcSimulation
+    itself asserts that the potential and the averaged concentration are bit-identical on all ranks.  Rank 0 reports."""
+    import re
+    out = {}
+    runs = (("resistor2D", ["--steps", "3000", "--transient", "1000", "--avg", "1000"]),
+            ("mosfet2D", ["--steps", "600", "--transient", "200", "--avg", "200"]))
+    for exe, extra in runs:
+        path = os.path.join(ROOT, "viennaemc_b200", "bin", exe)
+        if not os.path.exists(path):
+            continue
+        env = dict(os.environ, EMCGPU_SHARD="1", RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(local_rank),
+                   EMCNCCL_ID_FILE=os.path.join(id_dir, exe + ".id"))
+        env.pop("EMCGPU_DEVICE", None)
+        with tempfile.TemporaryDirectory() as tmp:
+            try:
+                r = subprocess.run([path, "--seed", "5", "--progress", "100000", *extra], cwd=tmp, capture_output=True, text=True,
+                                   timeout=300, env=env)
+            except subprocess.TimeoutExpired:
+                out[exe] = {"failed": "timeout"}
+                continue
+        m = re.search(r"(\d+) steps, (\d+) particles at the end.*Monte Carlo loop alone: ([0-9.eE+-]+) s, ([0-9.eE+-]+) "
+                      r"particle-steps/s\), ([0-9.eE+-]+) SOR sweeps", r.stdout)
+        same = "identical on all ranks" in r.stdout
+        calls = re.search(r"(\d+) all-reduces \((\d+) bytes\)", r.stdout)
+        if r.returncode == 0 and m:
+            steps, n, secs = int(m.group(1)), int(m.group(2)), float(m.group(3))
+            out[exe] = {"particle_steps_per_s": float(m.group(4)), "us_per_step": secs / steps * 1e6, "particles_total": n,
+                        "steps": steps, "sor_sweeps_per_step": float(m.group(5)), "ranks": world,
+                        "grids_identical_on_all_ranks": same,
+                        "allreduces_per_step": (int(calls.group(1)) / steps) if calls else None,
+                        "allreduce_bytes_per_step": (int(calls.group(2)) / steps) if calls else None}
+        else:
+            out[exe] = {"failed": (r.stdout + r.stderr)[-300:]}
+    return out
+
+
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -544,10 +583,19 @@ def main_ours(args):
                 line["device_runs"] = device_run_numbers()
             except Exception as exc:
                 line["device_runs"] = {"failed": str(exc)}
-        print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
+        if not args.no_device_runs:
+            # configs 3 / 4 sharded over all GPUs of the run: every rank starts the C++ driver of its rank
+            box = [tempfile.mkdtemp(prefix="emcnccl") if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            sharded = sharded_device_runs(rank, world, local_rank, box[0])
+            dist.barrier()
+            if rank == 0:
+                line["device_runs_sharded"] = sharded
         dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     return 0
 
 

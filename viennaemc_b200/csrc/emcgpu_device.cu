@@ -335,6 +335,10 @@ int doAssign(emcgpu_ctx *ctx, bool withConc, bool closeStep) {
     }
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
+  } else if (r->world > 1) {
+    // deposit alone (emcgpu_device_assign, e.g. the equilibrium charge before the first step): the grid every rank sees
+    // is the sum over the ranks all the same -- a replicated Poisson solve must never start from a local charge
+    r->allreduce(r->allreduceUser, count, G.cells, ctx->stream);
   }
   return EMCGPU_OK;
 }

@@ -133,8 +133,6 @@ public:
             .addError(std::string("sharded run: cannot join the NCCL communicator (EMCNCCL_ID_FILE must name a file all "
                                   "ranks can reach): ") + emcnccl_last_error())
             .print();
-      emcgpu::require(ctx, emcgpu_device_set_sharding(ctx, shardRank, shardWorld, emcnccl_allreduce_sum_f64, comm),
-                      "emcgpu_device_set_sharding");
     }
     auto &type = *this->idxTypeToPartType.at(gpuType);
     emcgpu::uploadParticleType(ctx, type);
@@ -145,6 +143,9 @@ public:
                     emcgpu_device_configure(ctx, &flat.desc, type.getCharge(), static_cast<double>(this->nrCarriersPerPart),
                                             this->expNrPart[gpuType].raw(), EMCGPU_MATH_FAST),
                     "emcgpu_device_configure");
+    if (comm)
+      emcgpu::require(ctx, emcgpu_device_set_sharding(ctx, shardRank, shardWorld, emcnccl_allreduce_sum_f64, comm),
+                      "emcgpu_device_set_sharding");
     // plug-ins of the particle type that act inside the device kernels: wall mechanisms, creation rules at contacts
     for (SizeType face = 0; face < 2 * Dim; face++) {
       const auto *wall = type.scatterHandler.getSurfaceScatterMechanism(face);

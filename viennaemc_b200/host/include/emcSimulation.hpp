@@ -166,10 +166,16 @@ public:
     fetch(EMCGPU_GRID_SUM_CONCENTRATION, results.avgConc[gpuType]);
     if (particleHandler.isSharded()) {
       // every rank solved the same Poisson problem on the same (all-reduced) charge: the grids must agree bit for bit
-      const bool same = particleHandler.identicalOnAllRanks(results.currPot.raw(), results.currPot.getSize()) &&
-                        particleHandler.identicalOnAllRanks(results.avgConc[gpuType].raw(), results.avgConc[gpuType].getSize());
+      const bool samePot = particleHandler.identicalOnAllRanks(results.currPot.raw(), results.currPot.getSize());
+      const bool sameConc = particleHandler.identicalOnAllRanks(results.avgConc[gpuType].raw(), results.avgConc[gpuType].getSize());
+      const bool sameCount = particleHandler.identicalOnAllRanks(results.nrPart[gpuType].raw(), results.nrPart[gpuType].getSize());
+      const bool same = samePot && sameConc && sameCount;
       if (!same)
-        emcMessage::getInstance().addError("sharded run: the replicated potential / concentration differ between the ranks.").print();
+        emcMessage::getInstance()
+            .addError(std::string("sharded run: replicated grids differ between the ranks (potential ") + (samePot ? "same" : "DIFFERS") +
+                      ", averaged concentration " + (sameConc ? "same" : "DIFFERS") + ", carriers per grid point " +
+                      (sameCount ? "same" : "DIFFERS") + ").")
+            .print();
       std::cout << "Sharded run: " << particleHandler.shardWorldSize() << " ranks, potential and averaged concentration "
                 << "identical on all ranks, " << particleHandler.allReduceCalls() << " all-reduces ("
                 << particleHandler.allReduceBytes() << " bytes) on this rank" << std::endl;
