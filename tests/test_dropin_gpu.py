@@ -87,7 +87,8 @@ def test_bulk_own_driver_mean_over_seeds_within_3_sigma_of_the_reference(tmp_pat
     runs = []
     for seed in range(1, (N_SEEDS if lookahead > 1 else 2) + 1):
         out = _run("bulkSimulation", ["--seed", str(seed), "--prefix", f"s{seed}", "--lookahead", str(lookahead)], tmp_path)
-        assert "12500 Electrons" in out or "1250" in out
+        n = int(out.split(" Electrons")[0].split()[-1])
+        assert abs(n - 12500) <= 3  # floor + one more with probability frac per cell: the shipped example's ensemble
         runs.append(_bulk_summary(str(tmp_path), f"s{seed}"))
     _check_bulk(runs, st, f"own bulk driver, {len(runs)} seeds")
 

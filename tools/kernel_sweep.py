@@ -35,10 +35,12 @@ def main():
     if a.settle:
         ctx.bulk_step_device(1e-16, a.settle, 16, obs.data_ptr())
     for cfg in a.configs.split(","):
-        mk, spl, ppl = (int(x) for x in cfg.split(":"))
+        mk, spl, ppl = (int(x) for x in cfg.split(":")[:3])
         ctx.set_option("multi_kernel", mk)
         ctx.set_option("split_ppl", ppl)
         ctx.bulk_step_device(1e-16, 2 * spl, spl, obs.data_ptr())
+        ctx.set_option("kernel_timing", 1)
+        ctx.kernel_times(reset=True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         l0 = ctx.launch_count
@@ -47,9 +49,11 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
+        kms, kn = ctx.kernel_times(reset=True)
         o = obs[: a.steps * 3].view(a.steps, 3).cpu().numpy()
         print(json.dumps({"multi_kernel": mk, "spl": spl, "ppl": ppl, "ms_per_step": ms / a.steps,
-                          "particle_steps_per_s": n * a.steps / (ms * 1e-3), "launches": ctx.launch_count - l0,
+                          "particle_steps_per_s": n * a.steps / (ms * 1e-3), "launches": ctx.launch_count - l0, "flight_ms": kms[0] / max(1, kn[0]), "event_ms": kms[1] / max(1, kn[1]),
+                          "other_ms": kms[2] / max(1, kn[0]),
                           "mean_E": float((o[:, 0] / o[:, 2]).mean()), "mean_v": float((o[:, 1] / o[:, 2]).mean())}),
               flush=True)
     ctx.close()
