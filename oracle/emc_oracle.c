@@ -319,6 +319,7 @@ struct orc_model {
   double qs2; /* emcPlasmonScreening::getQs2() */
   int hasGrain;
   double grainProb, grainTau; /* grainTau = 1 / rate (emcScatterHandler.hpp:234), 1 s without a mechanism */
+  double initEnergy; /* > 0: mono-energetic initial ensemble (emcElectron / emcHole initEnergyEV), 0: Maxwellian */
 };
 
 orc_model_t *orc_model_create(int nLevels, double maxEnergy, double temperature,
@@ -333,6 +334,8 @@ orc_model_t *orc_model_create(int nLevels, double maxEnergy, double temperature,
   m->grainTau = 1.;
   return m;
 }
+/* emcElectron.hpp:85-88 / emcHole.hpp:95-98: initParticleKSpaceFixed instead of the Maxwellian (no energy draw) */
+void orc_model_set_init_energy(orc_model_t *m, double energyEV) { m->initEnergy = energyEV; }
 void orc_model_destroy(orc_model_t *m) {
   if (!m)
     return;
@@ -740,6 +743,11 @@ int orc_select(const orc_model_t *m, int si, double energy, double r) {
 }
 
 /* ------------------------------------------------------- final states */
+/* test aid: marks the particles whose q-resolved |q| sample came back ON a kinematic limit (forward / backward scattering).
+ * There cos(theta) = (kI^2 + kF^2 - q^2) / (2 kI kF) is 1 - O(eps), so sin(theta) = O(sqrt(eps)) is made of the rounding of
+ * kI and kF: the reference's own result moves by ~1e-8 when its input moves by one ulp (tests/test_oracle_mhp.py shows it) */
+static unsigned char *g_limitFlags = 0;
+void orc_set_limit_flags(unsigned char *flags) { g_limitFlags = flags; }
 static void scatter_with(const orc_model_t *m, const orc_mech_t *d, orc_ensemble_t *e,
                          int64_t p, rng_t *rng) {
   double k[3] = {e->kx[p], e->ky[p], e->kz[p]}, out[3];
@@ -815,6 +823,8 @@ static void scatter_with(const orc_model_t *m, const orc_mech_t *d, orc_ensemble
       cosTheta = 1 - 2 * r;
     } else if (d->p[3] != 0) {
       double q = orc_bath_sample_q(m->baths[(int)d->p[2]], fabs(kI - kF), kI + kF, emission, r);
+      if (g_limitFlags && (q == fabs(kI - kF) || q == kI + kF))
+        g_limitFlags[p] = 1;
       cosTheta = fmax(-1., fmin(1., (kI * kI + kF * kF - q * q) / B));
     } else {
       const double Ap = kI * kI + kF * kF + d->p[1];
@@ -1236,7 +1246,8 @@ int64_t orc_generate_initial(const orc_model_t *m, const double box[3], const in
             const orc_valley_t *v = &m->valleys[valley];
             int sub = (int)floor(v->deg * rng_ulog(&rng));
             /* emcParticleInitialization.hpp:36-51 */
-            double energy = -1.5 * Vt * log(rng_ulog(&rng));
+            /* emcParticleInitialization.hpp:36-51; :60-74 for a fixed start energy (no draw) */
+            double energy = m->initEnergy > 0. ? m->initEnergy : -1.5 * Vt * log(rng_ulog(&rng));
             double r2 = rng_u01(&rng); /* right-to-left: first draw is rand2 */
             double r1 = rng_u01(&rng);
             double k[3];

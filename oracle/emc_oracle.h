@@ -75,6 +75,7 @@ typedef struct orc_model orc_model_t;
 orc_model_t *orc_model_create(int nLevels, double maxEnergy, double temperature,
                               double rho, double vSound);
 void orc_model_destroy(orc_model_t *m);
+void orc_model_set_init_energy(orc_model_t *m, double energyEV); /* emcElectron.hpp:85-88, emcHole.hpp:95-98 */
 int orc_add_valley(orc_model_t *m, int kind, const double relMass[3],
                    double particleMass, int deg, double alpha, double eBottom,
                    const double *dirs /* [deg][3][3] un-normalised or NULL */);
@@ -102,6 +103,7 @@ void orc_bath_record(orc_bath_t *b, double q, int emission);                    
 void orc_bath_update(orc_bath_t *b, double dt);                                 /* :264-358 */
 double orc_bath_mean_nq(const orc_bath_t *b);                                    /* :461-470 */
 double orc_bath_nq_window(const orc_bath_t *b, double qMin, double qMax);        /* :378-394 */
+void orc_set_limit_flags(unsigned char *flags); /* test aid: see emc_oracle.c */
 double orc_bath_sample_q(const orc_bath_t *b, double qMin, double qMax, int emission, double r); /* :423-458 */
 double orc_bath_acoustic_temp(const orc_bath_t *b);                             /* :477-481 */
 double orc_bath_n0(const orc_bath_t *b);

@@ -18,7 +18,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from scenarios import DEVICE_CASES, GA2O3_CASES, GOLDEN_CASES, ga2o3_args  # noqa: E402
+from scenarios import DEVICE_CASES, GA2O3_CASES, GOLDEN_CASES, MHP_CASES, ga2o3_args, mhp_args  # noqa: E402
 
 DT = {"d": np.float64, "q": np.int64, "Q": np.uint64}
 
@@ -103,6 +103,31 @@ def main_ga2o3():
         print(name, "->", dst, os.path.getsize(dst) // 1024, "KiB; particles", int(blob["params"][-1]), "draws", len(blob["draws"]))
 
 
+def main_mhp():
+    subprocess.check_call(["make", "-C", HERE, "_ref/ref_mhp_driver"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    drv = os.path.join(HERE, "_ref", "ref_mhp_driver")
+    keys = ("polar", "box", "density", "dt", "steps", "levels", "emax", "screening", "qresolved", "acoustic_bath", "bins", "dq",
+            "alpha_e", "alpha_h", "seed")
+    for name in MHP_CASES:
+        a = mhp_args(name)
+        with tempfile.TemporaryDirectory() as tmp:
+            out = os.path.join(tmp, "ref.bin")
+            cmd = [drv, "--out", out]
+            for k in keys:
+                cmd += ["--" + k.replace("_", "-"), repr(a[k]) if isinstance(a[k], float) else str(a[k])]
+            subprocess.check_call(cmd, cwd=tmp, stdout=subprocess.DEVNULL)
+            blob = read_blob(out)
+        # the raw draws are the mt19937_64 stream of the seed: keep count + digest (helpers.load_golden regenerates them)
+        import hashlib
+        blob["draws_count"] = np.array([len(blob["draws"])], dtype=np.int64)
+        blob["draws_sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(blob["draws"]).tobytes()).digest(), dtype=np.uint8)
+        n_draws = len(blob.pop("draws"))
+        dst = os.path.join(ROOT, "tests", "golden", name + ".npz")
+        np.savez_compressed(dst, **blob)
+        print(name, "->", dst, os.path.getsize(dst) // 1024, "KiB; electrons", int(blob["params"][-2]), "holes", int(blob["params"][-1]),
+              "draws", n_draws)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which in ("all", "bulk"):
@@ -111,3 +136,5 @@ if __name__ == "__main__":
         main_device()
     if which in ("all", "ga2o3"):
         main_ga2o3()
+    if which in ("all", "mhp"):
+        main_mhp()

@@ -69,6 +69,7 @@ def lib():
         L.orc_model_create.restype = C.c_void_p
         L.orc_model_create.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
         L.orc_model_destroy.argtypes = [C.c_void_p]
+        L.orc_model_set_init_energy.argtypes = [C.c_void_p, C.c_double]
         L.orc_add_valley.argtypes = [C.c_void_p, C.c_int, _DP, C.c_double, C.c_int, C.c_double, C.c_double, _DP]
         L.orc_add_acoustic.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
         L.orc_add_intervalley.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
@@ -88,6 +89,7 @@ def lib():
             getattr(L, name).argtypes = [C.c_void_p]
         L.orc_bath_nq_window.restype = C.c_double
         L.orc_bath_nq_window.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.orc_set_limit_flags.argtypes = [C.c_void_p]
         L.orc_bath_sample_q.restype = C.c_double
         L.orc_bath_sample_q.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double]
         L.orc_bath_copy.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
@@ -176,6 +178,15 @@ class Ensemble:
         o.n = self.n
         for f in self.F64 + self.I32:
             getattr(o, f)[:] = getattr(self, f)
+        return o
+
+    def subset(self, mask):
+        """the particles selected by a boolean mask over [0, n), as an ensemble of their own"""
+        mask = np.asarray(mask, dtype=bool)[: self.n]
+        o = Ensemble(max(1, int(mask.sum())))
+        o.n = int(mask.sum())
+        for f in self.F64 + self.I32:
+            getattr(o, f)[: o.n] = getattr(self, f)[: self.n][mask]
         return o
 
     def trim(self):
@@ -305,6 +316,17 @@ class Model:
         return out
 
     # ---- particle loop
+    def bulk_observables(self, ens: "Ensemble", field_dir):
+        """[valley][sum E, sum v.dir, count] of a resting ensemble (basicBulkParticleHandler.hpp:289-347)"""
+        obs = np.zeros((self.n_valleys, 3))
+        s = ens.c()
+        self.L.orc_bulk_observables(self.h, C.byref(s), _dp(np.asarray(field_dir, dtype=np.float64)), _dp(obs))
+        return obs
+
+    def set_init_energy(self, energy_ev):
+        """mono-energetic initial ensemble (emcElectron / emcHole initEnergyEV)"""
+        self.L.orc_model_set_init_energy(self.h, energy_ev)
+
     def generate_initial(self, box, cells, doping, mt_state, capacity=None):
         box = np.asarray(box, dtype=np.float64)
         cells = np.asarray(cells, dtype=np.int32)
@@ -328,7 +350,7 @@ class Model:
         rec_cap = 0
         rec = None
         if record:
-            rec_cap = max(1024, int(ens.n) * n_steps * 8 + 1024)
+            rec_cap = max(1024, int(ens.n) * n_steps * 64 + 1024)
             rec = np.zeros(rec_cap, dtype=np.int32)
         ev_cap = 0
         ev = None
@@ -422,6 +444,18 @@ def mt_fill(seed: int, n: int) -> np.ndarray:
     out = np.zeros(n, dtype=np.uint64)
     lib().orc_mt_fill(seed, out.ctypes.data_as(C.POINTER(C.c_uint64)), n)
     return out
+
+
+_limit_flags = None
+
+
+def set_limit_flags(n):
+    """test aid: a fresh uint8[n] that the q-resolved sampler marks per particle index when its |q| sample lies ON a
+    kinematic limit (emc_oracle.c:g_limitFlags); n = 0 switches the marking off"""
+    global _limit_flags
+    _limit_flags = np.zeros(int(n), dtype=np.uint8) if n else None
+    lib().orc_set_limit_flags(_limit_flags.ctypes.data if n else None)
+    return _limit_flags
 
 
 def rng_mt(state) -> RngCfg:

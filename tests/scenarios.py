@@ -264,3 +264,58 @@ def build_ga2o3(case):
                             bool(a["qresolved"]), bool(a["qres_angle"]))
     m.build_tables()
     return m, baths, a
+
+
+# ---- hot carriers in a metal-halide perovskite: electrons AND holes on shared phonon baths ---------------
+# oracle/_ref/ref_mhp_driver: the data-parallel part of examples/hotCarrierMHP/hotCarrierMHP.cpp (MAPbI3 preset)
+MHP = dict(eps_hi=5.0, eps_lo=33.5, mass_e=0.20, mass_h=0.25, hw_lo=0.0115, gap=1.60, photon=3.1, rho=4000.0, v_sound=2000.0)
+MHP_CASES = {
+    # the example's default polar model: screened hot-phonon classes, q-resolved rate and angle, Debye screening from both species
+    "mhp_qres": dict(polar="screened_hot", steps=60, seed=1),
+    # unscreened hot-phonon classes, mean-field occupation
+    "mhp_hot": dict(polar="hot", steps=60, seed=2, screening=0, qresolved=0),
+    # parabolic bands (--alpha 0), equilibrium phonons with screening
+    "mhp_parabolic_eq": dict(polar="screened_eq", steps=40, seed=3, qresolved=0, alpha_e=0.0, alpha_h=0.0),
+}
+MHP_DEFAULTS = dict(box=8e-8, density=1e24, dt=5e-15, temperature=300.0, tau_lo=0.6e-12, tau_ac=30e-12, emax=4.0, levels=1000,
+                    screening=1, qresolved=1, acoustic_bath=1, bins=40, dq=5e7, alpha_e=-1.0, alpha_h=-1.0)
+
+
+def mhp_args(case):
+    a = dict(MHP_DEFAULTS)
+    a.update(MHP_CASES[case])
+    g = MHP
+    if a["alpha_e"] < 0:
+        a["alpha_e"] = (1.0 / g["gap"]) * (1.0 - g["mass_e"]) * (1.0 - g["mass_e"])
+    if a["alpha_h"] < 0:
+        a["alpha_h"] = (1.0 / g["gap"]) * (1.0 - g["mass_h"]) * (1.0 - g["mass_h"])
+    excess = g["photon"] - g["gap"]
+    a["energy_e"] = g["mass_h"] / (g["mass_e"] + g["mass_h"]) * excess
+    a["energy_h"] = g["mass_e"] / (g["mass_e"] + g["mass_h"]) * excess
+    return a
+
+
+def build_mhp(case):
+    """oracle-side models of the two species (electrons, holes) + the shared phonon baths (mirrors oracle/ref_mhp_driver.cpp)"""
+    a = mhp_args(case)
+    g = MHP
+    hot = a["polar"] in ("hot", "screened_hot")
+    v_sim = a["box"] * a["box"] * a["box"]
+    baths = []
+    if hot:
+        baths.append(po.PhononBath(a["bins"], a["dq"], a["tau_lo"], g["hw_lo"], a["temperature"], v_sim, bool(a["acoustic_bath"]),
+                                   g["hw_lo"] / 2.0, a["tau_ac"], 0.0, 0.00781, a["tau_ac"]))
+    variant = {"hot": po.FROEHLICH_HOT, "screened_eq": po.FROEHLICH_SCREENED_EQ, "screened_hot": po.FROEHLICH_SCREENED_HOT}[a["polar"]]
+    models = []
+    for mass, alpha, energy in ((g["mass_e"], a["alpha_e"], a["energy_e"]), (g["mass_h"], a["alpha_h"], a["energy_h"])):
+        m = po.Model(a["levels"], a["emax"], a["temperature"], g["rho"], g["v_sound"])
+        m.add_valley(po.VALLEY_NONPARABOLIC_ISO, mass, 1, alpha, 0.0)
+        m.set_init_energy(energy)
+        for b in baths:
+            m.add_bath(b)
+        for emission in (False, True):
+            m.add_froehlich(variant, emission, 0, 0, g["hw_lo"], mass, g["eps_hi"], g["eps_lo"], a["temperature"], 0 if hot else -1,
+                            bool(a["qresolved"]), True)
+        m.build_tables()
+        models.append(m)
+    return models, baths, a

@@ -284,6 +284,48 @@ def test_hot_phonon_own_driver_mean_over_seeds_within_3_sigma_of_the_reference(t
     _check_ga2o3(tables, "hpb" if hpb else "eq", "own hot-phonon driver, 4 seeds")
 
 
+# ---- hot carriers in a metal-halide perovskite: two species on shared phonon baths ---------------------
+def test_unmodified_reference_hot_carrier_main_mean_over_seeds_within_3_sigma_of_the_reference(tmp_path):
+    """examples/hotCarrierMHP/hotCarrierMHP.cpp of the reference compiled unchanged against our headers: electrons AND holes
+    (emcElectron + emcHole, one GPU context each) cooling through screened, q-resolved hot-phonon Froehlich scattering into ONE
+    shared bath; its pairwise host steps switched off on the command line.  Mean energies of both species, LO occupation,
+    acoustic temperature and screening wave vector at 0.5 / 1 / 2 ps: mean over 8 seeds against 32 runs of the reference."""
+    if not os.path.exists(os.path.join(BIN, "reference_hotCarrierMHP_gpu")):
+        pytest.skip("reference_hotCarrierMHP_gpu is built only where the reference tree is mounted")
+    st = _load("ref_mhp_stats.json")
+    assert st["n_runs"] >= 30
+    runs = []
+    for seed in range(101, 101 + N_SEEDS):
+        work = os.path.join(tmp_path, f"s{seed}")
+        os.makedirs(work)
+        out = _run("reference_hotCarrierMHP_gpu", [*st["args"], "--seed", str(seed)], work)
+        assert "HPB enabled" in out and "Holes" in out
+        sfx = st["suffix"]
+        e = np.loadtxt(os.path.join(work, f"avgEnergyElectrons{sfx}.txt"))
+        h = np.loadtxt(os.path.join(work, f"avgEnergyHoles{sfx}.txt"))
+        ph = np.loadtxt(os.path.join(work, f"phononOccupation{sfx}.txt"))
+        rows = [r + 1 for r in st["rows"]]
+        runs.append(dict(energy_e=e[rows, 1], energy_h=h[rows, 1], n_lo=ph[rows, 1], t_ac=ph[rows, 3], q_s=ph[rows, 4]))
+    for key in ("energy_e", "energy_h", "n_lo", "t_ac", "q_s"):
+        for i, t in enumerate(("0.5 ps", "1 ps", "2 ps")):
+            assert_scalar([r[key][i] for r in runs], _ref(st, key)[:, i], f"unmodified hot-carrier main, {N_SEEDS} seeds: {key} at {t}")
+    assert np.mean([r["n_lo"][2] for r in runs]) > 1.5  # the LO mode is driven far above its equilibrium occupation (0.56)
+
+
+def test_hot_carrier_host_steps_are_rejected_by_name(tmp_path):
+    """carrier-carrier scattering, recombination and energy-selective contacts edit the host ensemble pairwise / in sequence:
+    no GPU implementation, no CPU fallback -- the run stops with the name of the mechanism"""
+    if not os.path.exists(os.path.join(BIN, "reference_hotCarrierMHP_gpu")):
+        pytest.skip("reference_hotCarrierMHP_gpu is built only where the reference tree is mounted")
+    for args, name in ((["--use_recomb", "0", "--use_esc", "0"], "emcCarrierCarrierScatter"),
+                       (["--use_cc", "0", "--use_esc", "0"], "emcRecombination"),
+                       (["--use_cc", "0", "--use_recomb", "0"], "emcEnergySelectiveContact"),
+                       (["--use_cc", "0", "--use_recomb", "0", "--use_esc", "0", "--use_bf", "1", "--box", "1e-7"], "Pauli")):
+        r = subprocess.run([os.path.join(BIN, "reference_hotCarrierMHP_gpu"), *args, "--total_time", "1e-13", "--seed", "3"],
+                           cwd=tmp_path, capture_output=True, text=True, timeout=300)
+        assert r.returncode != 0 and name in r.stdout + r.stderr, (args, (r.stdout + r.stderr)[-600:])
+
+
 # ---- grain-boundary scattering through the drop-in handler (no example of the reference switches it on) -----------------
 def test_grain_scattering_through_the_drop_in_handler_matches_the_cpu_restatement(tmp_path):
     """own bulk driver with an emcGrainScatterMechanism (GPU, Philox streams) against the oracle's run of the same set-up

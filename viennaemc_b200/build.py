@@ -113,6 +113,16 @@ def build_examples(force: bool = False) -> dict:
                                ref_main, *link])
     if os.path.exists(target):
         out["reference_hotPhononGa2O3_gpu"] = target
+    # the UNMODIFIED hot-carrier example (two species: emcElectron + emcHole on shared phonon baths).  Its pairwise host
+    # steps (carrier-carrier scattering, recombination, energy-selective contacts, band filling) have no GPU implementation:
+    # run it with --use_cc 0 --use_recomb 0 --use_esc 0, anything else is rejected with the name of the mechanism
+    ref_main = os.path.join(REFERENCE, "examples", "hotCarrierMHP", "hotCarrierMHP.cpp")
+    target = os.path.join(bindir, "reference_hotCarrierMHP_gpu")
+    if os.path.exists(ref_main) and (force or _newer(target, deps)):
+        subprocess.check_call([*common, "-include", os.path.join(HOST_INC, "basicBulkParticleHandler.hpp"), "-o", target,
+                               ref_main, *link])
+    if os.path.exists(target):
+        out["reference_hotCarrierMHP_gpu"] = target
     # the UNMODIFIED device-run examples of the reference (emcSimulation + emcBasicParticleHandler + emcSORSolver +
     # PM scheme) compiled against OUR headers: every object they create is the GPU-backed drop-in
     for name, rel in (("reference_resistor2D_gpu", ("examples", "resistor2D", "resistor2D.cpp")),):

@@ -378,6 +378,14 @@ public:
         .print();
   }
 
+  // Pairwise / host-side ensemble edits of the hot-carrier example (reference :472-640: carrierCarrierScatter,
+  // interCarrierScatter, recombine, extractCarriers).  They walk the host ensemble particle by particle, in pairs, in
+  // sequence -- not part of the data-parallel particle loop and never run on the CPU here: rejected with their names.
+  template <class Scatter> void carrierCarrierScatter(Scatter &, SizeType, T) { rejectHostStep(Scatter::name(), "carrierCarrierScatter"); }
+  template <class Scatter> void interCarrierScatter(Scatter &, SizeType, SizeType, T) { rejectHostStep(Scatter::name(), "interCarrierScatter"); }
+  template <class Recombination> void recombine(Recombination &, SizeType, SizeType, T) { rejectHostStep(Recombination::name(), "recombine"); }
+  template <class Contact> void extractCarriers(Contact &, SizeType, T) { rejectHostStep(Contact::name(), "extractCarriers"); }
+
   // "<prefix><TypeName><suffix>.txt": box extent, then per particle: index, position[, k, energy, sub-valley, valley]
   void print(std::string namePrefix, std::string nameSuffix) const {
     for (const auto &[idxType, type] : idxTypeToPartType) {
@@ -434,6 +442,13 @@ public:
   }
 
 private:
+  static void rejectHostStep(const char *cls, const char *method) {
+    emcMessage::getInstance()
+        .addError(std::string("basicBulkParticleHandler::") + method + ": " + cls +
+                  " edits the host ensemble pairwise / sequentially; it has no GPU implementation and there is no CPU "
+                  "fallback (run the example with this mechanism switched off).")
+        .print();
+  }
   std::vector<T> perValleyMean(SizeType idxType, int which) {
     const auto &obs = observables(idxType);
     const SizeType nV = idxTypeToPartType[idxType]->getNrValleys();

@@ -17,6 +17,8 @@ public:
   T dk, kMax, Vsim;
   emcPauliExclusion() = delete;
   emcPauliExclusion(T inDk, T inKMax, T inVsim) : dk(inDk), kMax(inKMax), Vsim(inVsim) {}
+  // fraction of the attempted events that were blocked (reference :140-144); nothing is ever attempted here
+  T getRejectionRate() const { return nScattered ? T(nRejected) / T(nScattered) : T(0); }
 };
 
 #endif
