@@ -80,7 +80,7 @@ def test_replay_of_reference_draws(gpu_ctx_factory, case, steps_per_launch, mult
 
 @pytest.mark.parametrize("math_mode", [capi.MATH_EXACT, capi.MATH_FAST], ids=["exact", "fast"])
 @pytest.mark.parametrize("multi_kernel", [1, 2, 3], ids=["inplace", "deferred", "split"])
-@pytest.mark.parametrize("case", ["si_bulk", "mixed"])
+@pytest.mark.parametrize("case", ["si_bulk", "mixed", "si_grain"])
 def test_philox_against_oracle(gpu_ctx_factory, case, math_mode, multi_kernel):
     """Independent (counter-based) RNG: GPU and oracle consume identical Philox streams."""
     a = dict(GOLDEN_CASES[case]["args"])

@@ -70,6 +70,47 @@ def test_step_ahead_then_rewind_reproduces_the_earlier_state(gpu_ctx_factory, mu
         x.close()
 
 
+@pytest.mark.parametrize("multi_kernel", [3, 1], ids=["split", "inplace"])
+def test_step_ahead_carries_the_grain_clocks(gpu_ctx_factory, multi_kernel):
+    """a grain mechanism (second free-flight clock per particle): the look-ahead copy has clocks of its own, a rewind brings
+    back the clocks of the state before the launch"""
+    from helpers import upload_ensemble
+    m = build_si()
+    m.set_grain(0.4, 2e13)
+    m.grain = (0.4, 2e13)
+    box = [8e-7] * 3
+    ens, _ = m.generate_initial(box, [8, 8, 8], 1e23, po.mt_state(3))  # 51200 particles
+    dt, ahead, served = 1e-15, 24, 9
+
+    def fresh():
+        ctx = gpu_ctx_factory()
+        ctx.set_option("multi_kernel", multi_kernel)
+        upload_model(ctx, m)
+        upload_ensemble(ctx, ens)
+        ctx.rng_philox(77)
+        ctx.bulk_configure(box, [-1, 0, 0], 1e6, math_mode=capi.MATH_FAST)
+        ctx.set_step_index(1)
+        return ctx
+
+    a = fresh()
+    a.bulk_step_ahead(dt, ahead, ahead)
+    full = download_ensemble(a)
+    a.bulk_rewind()
+    assert np.array_equal(download_ensemble(a).grainTau, ens.grainTau[: ens.n])
+    a.bulk_step(dt, served, served)
+    part = download_ensemble(a)
+    b = fresh()
+    b.bulk_step(dt, ahead, ahead)
+    ref_full = download_ensemble(b)
+    c = fresh()
+    c.bulk_step(dt, served, served)
+    ref_part = download_ensemble(c)
+    assert not np.array_equal(ref_full.grainTau, ens.grainTau[: ens.n])
+    for f in FIELDS + ("grainTau",):
+        assert np.array_equal(getattr(full, f), getattr(ref_full, f)), f
+        assert np.array_equal(getattr(part, f), getattr(ref_part, f)), f
+
+
 def _run_driver(tmp, prefix, *extra):
     r = subprocess.run([os.path.join(BIN, "bulkSimulation"), "--seed", "11", "--particles", "20000", "--steps", "150",
                         "--dt", "1e-15", "--prefix", prefix, *extra], cwd=tmp, capture_output=True, text=True, timeout=300)

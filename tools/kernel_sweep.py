@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--particles", type=float, default=1e8)
     ap.add_argument("--steps", type=int, default=192)
     ap.add_argument("--settle", type=int, default=2000)
+    ap.add_argument("--grain-rate", type=float, default=0.0, help="> 0: a grain mechanism with this event rate [1/s]")
     ap.add_argument("--configs", default="2:8:4,3:8:4,3:16:4,3:24:4,3:16:2,3:8:2")
     a = ap.parse_args()
     n = int(a.particles)
@@ -29,6 +30,10 @@ def main():
     hostapi.si_upload(ctx, hostapi.si_spec(box=box, spacing=[b / 5 for b in box], doping=1e23))
     ctx.generate_bulk_ensemble(n, box, 300.0, 0, seed=12345)
     ctx.rng_philox(12345)
+    if a.grain_rate > 0:
+        import numpy as np
+        ctx.set_grain(0.5, a.grain_rate)
+        ctx.set_grain_clock(np.random.default_rng(1).exponential(1.0 / a.grain_rate, n))
     ctx.bulk_configure(box, [-1, 0, 0], 1e6, math_mode=capi.MATH_FAST)
     ctx.set_step_index(1)
     obs = torch.zeros(max(a.settle, a.steps) * 3, dtype=torch.float64, device="cuda")

@@ -47,6 +47,7 @@ struct BulkParams {
   BathView baths; // phonon baths of polar-optical mechanisms (counts == nullptr: none)
   // grain boundaries (emcGrainScatterMechanism): second free-flight clock per particle, nullptr = no grain mechanism
   double *grainTau;
+  double *grainOut; // K1d out of place: where the flight kernel leaves the clocks
   double grainProb, grainTau0;
   // launch-uniform flight constants per valley (host-built: emcgpu.cu buildFlightConsts), read from the constant bank
   FlightConst fc[EMCGPU_MAX_VALLEYS];

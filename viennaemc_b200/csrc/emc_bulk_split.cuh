@@ -19,6 +19,13 @@
 //                     full-dt flights to the end of the launch or to the particle's next event.  Random numbers are
 //                     Philox(key, particle id, step, draw): the order in which events are served changes nothing.
 //
+// GRAIN (a grain mechanism is set, emcGrainScatterMechanism): the second free-flight clock of the particle is a ninth fp64
+// stream of both kernels (144 B + 1 B of HBM traffic per particle per launch pair instead of 136 + 1).  The reference
+// decrements it AFTER the step and scatters when it is <= 0 (basicBulkParticleHandler.hpp:216-220); the flight kernel forms
+// g - dt first (one more DADD per particle-step) and freezes the particle at a step whose end would see the clock run out
+// (sign test on the high word -- conservative by the subnormals, the event kernel repeats the exact test), so that the
+// event kernel serves the step, the grain event at its end and the draws of both in the order of the general kernel.
+//
 // Observables: per-thread shared-memory slots per step in both kernels (no atomics, no shuffles in the loops); the
 // flight kernel sums S - 1 = 2 alpha E instead of E (one FMA from values the flight needs anyway).
 #pragma once
@@ -80,7 +87,7 @@ template <> struct VecLd<4> {
 // Flight kernel.  Applies to FAST arithmetic, one non-parabolic valley whose sub-valley rotations are signed
 // permutations (the Si / Ga2O3 bulk models); everything else runs K1c.
 // AXIS: the device axis of a field along a coordinate axis (v.Ê has one term), -1 = any direction.
-template <int PPL, int AXIS, int kFlightThreads>
+template <int PPL, int AXIS, int kFlightThreads, bool GRAIN>
 __device__ __forceinline__ void flightRole(const BulkParams &P, const int cta, const int nCta) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   const int nSteps = P.nSteps;
@@ -106,6 +113,7 @@ __device__ __forceinline__ void flightRole(const BulkParams &P, const int cta, c
   // launch constants: operands from the constant bank
   const FlightConst &f = P.fc[0];
   double *const *const out = P.packedOut ? P.streamOut : P.stream; // out of place: the input ensemble is left as it was
+  double *const grainOut = P.packedOut ? P.grainOut : P.grainTau;
   const double dt = P.dt;
   const long long dtBits = __double_as_longlong(dt);
   const uint32_t hiBx = (uint32_t)__double2hiint(P.box.x), hiBy = (uint32_t)__double2hiint(P.box.y),
@@ -129,6 +137,7 @@ __device__ __forceinline__ void flightRole(const BulkParams &P, const int cta, c
     asm volatile("prefetch.global.L2 [%0];" ::"l"(P.stream[EMCGPU_X] + i0));
     asm volatile("prefetch.global.L2 [%0];" ::"l"(P.stream[EMCGPU_Y] + i0));
     asm volatile("prefetch.global.L2 [%0];" ::"l"(P.stream[EMCGPU_Z] + i0));
+    if constexpr (GRAIN) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.grainTau + i0));
     if ((lane & 1) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.packed + i0));
   };
 
@@ -137,6 +146,7 @@ __device__ __forceinline__ void flightRole(const BulkParams &P, const int cta, c
     prefetchChunk(chNext);
     const int64_t i0 = ch * kChunk + PPL * lane;
     double kx[PPL], ky[PPL], kz[PPL], tau[PPL], px[PPL], py[PPL], pz[PPL], a0[PPL], a1[PPL], a2[PPL];
+    double g[GRAIN ? PPL : 1];
     bool live[PPL];
     uint32_t frz = 0xffffffffu; // byte j: step at which particle j froze
     {
@@ -148,6 +158,7 @@ __device__ __forceinline__ void flightRole(const BulkParams &P, const int cta, c
       VecLd<PPL>::ld(P.stream[EMCGPU_X] + i0, px);
       VecLd<PPL>::ld(P.stream[EMCGPU_Y] + i0, py);
       VecLd<PPL>::ld(P.stream[EMCGPU_Z] + i0, pz);
+      if constexpr (GRAIN) VecLd<PPL>::ld(P.grainTau + i0, g);
       VecLd<PPL>::ldw(P.packed + i0, w);
       if (P.packedOut) VecLd<PPL>::stw(P.packedOut + i0, w);
 #pragma unroll
@@ -168,7 +179,12 @@ __device__ __forceinline__ void flightRole(const BulkParams &P, const int cta, c
       for (int j = 0; j < PPL; j++) {
         // a particle whose flight ends inside this step freezes: zero factors leave k and the position exactly as
         // they are and make its contributions to the sums exact zeros
-        const bool ev = live[j] && lessThanBits(tau[j], dtBits);
+        bool ev = live[j] && lessThanBits(tau[j], dtBits);
+        double gNext = 0.0;
+        if constexpr (GRAIN) { // the clock after this step; <= 0 (or a subnormal): the step ends with a grain event
+          gNext = __dsub_rn(g[j], dt);
+          ev = ev || (live[j] && __double2hiint(gNext) <= 0);
+        }
         if (ev) {
           a0[j] = a1[j] = a2[j] = 0.0;
           live[j] = false;
@@ -182,6 +198,7 @@ __device__ __forceinline__ void flightRole(const BulkParams &P, const int cta, c
         if (j == 0) sumT = live[j] ? t : 0.0;
         else addIf(sumT, t, live[j]);
         addIf(tau[j], -dt, live[j]);
+        if constexpr (GRAIN) g[j] = live[j] ? gNext : g[j];
         const double v = AXIS == 0   ? (f.K4[0] * kx[j]) * o.w0
                          : AXIS == 1 ? (f.K4[1] * ky[j]) * o.w1
                          : AXIS == 2 ? (f.K4[2] * kz[j]) * o.w2
@@ -224,6 +241,7 @@ __device__ __forceinline__ void flightRole(const BulkParams &P, const int cta, c
     VecLd<PPL>::st(out[EMCGPU_X] + i0, px);
     VecLd<PPL>::st(out[EMCGPU_Y] + i0, py);
     VecLd<PPL>::st(out[EMCGPU_Z] + i0, pz);
+    if constexpr (GRAIN) VecLd<PPL>::st(grainOut + i0, g);
     VecLd<PPL>::stFrozen(P.frozen + i0, frz);
   }
   // the particles behind the last whole chunk are left to the event kernel, from step 0
@@ -233,6 +251,7 @@ __device__ __forceinline__ void flightRole(const BulkParams &P, const int cta, c
       P.frozen[i] = 0;
       if (P.packedOut) {
         for (int c = 0; c < EMCGPU_N_STREAMS; c++) P.streamOut[c][i] = P.stream[c][i];
+        if constexpr (GRAIN) P.grainOut[i] = P.grainTau[i];
         P.packedOut[i] = P.packed[i];
       }
     }
@@ -253,9 +272,9 @@ __device__ __forceinline__ void flightRole(const BulkParams &P, const int cta, c
   // one valley: every particle contributes to every step
   if (cta == 0 && tid < nSteps) atomicAdd(P.obs + tid * 3 + 2, (double)P.n);
 }
-template <int PPL, int AXIS>
+template <int PPL, int AXIS, bool GRAIN>
 __global__ void __launch_bounds__(kFlightThreadsAlone, 1) bulkFlightKernel(const __grid_constant__ BulkParams P) {
-  flightRole<PPL, AXIS, kFlightThreadsAlone>(P, (int)blockIdx.x, (int)gridDim.x);
+  flightRole<PPL, AXIS, kFlightThreadsAlone, GRAIN>(P, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -265,7 +284,7 @@ struct EventWarpList {
   uint8_t step[kEventListCap];
 };
 
-template <int RNG_MODE, int kEventThreads>
+template <int RNG_MODE, int kEventThreads, bool GRAIN>
 __device__ __forceinline__ void eventRole(const BulkParams &P) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   __shared__ uint64_t tableBar;
@@ -342,16 +361,23 @@ __device__ __forceinline__ void eventRole(const BulkParams &P) {
     p.pos = Vec3{0.0, 0.0, 0.0};
     p.energy = p.tau = 0.0;
     p.valley = p.sub = p.region = 0;
+    double g = 0.0; // grain clock
     if (active) {
       idx = list.idx[count + lane];
       s = list.step[count + lane];
       loadParticle(P, idx, p, rng);
+      if constexpr (GRAIN) g = P.grainTau[idx];
     }
     __syncwarp();
     for (bool first = true;; first = false) {
       if (active) {
         const FastSub &fs = C.fast[p.valley * EMCGPU_MAX_SUBVALLEYS + p.sub];
         while (s < nSteps && p.tau >= dt) {
+          if constexpr (GRAIN) { // a step that ends with a grain event is served below
+            const double gNext = __dsub_rn(g, dt);
+            if (gNext <= 0.0) break;
+            g = gNext;
+          }
           const double vd = fastStep(fs, C.fastV[p.valley], dt, P.box, p.k.x, p.k.y, p.k.z, p.energy, p.tau, p.pos.x,
                                      p.pos.y, p.pos.z);
           myObs[(2 * s) * kEventThreads] += p.energy;
@@ -360,6 +386,7 @@ __device__ __forceinline__ void eventRole(const BulkParams &P) {
         }
         if (s == nSteps) {
           storeParticleState(P, idx, p);
+          if constexpr (GRAIN) P.grainTau[idx] = g;
           active = false;
         }
       }
@@ -369,6 +396,7 @@ __device__ __forceinline__ void eventRole(const BulkParams &P) {
         // few lanes left: their particles wait in the list for a full batch (state parked in global memory)
         if (active) {
           storeParticleState(P, idx, p);
+          if constexpr (GRAIN) P.grainTau[idx] = g;
           const int pos = count + __popc(busy & ltMask);
           list.idx[pos] = idx;
           list.step[pos] = (uint8_t)s;
@@ -376,11 +404,18 @@ __device__ __forceinline__ void eventRole(const BulkParams &P) {
         count += __popc(busy);
         break;
       }
-      if (active) { // every busy lane is at the step in which its flight ends
+      if (active) { // every busy lane is at the step in which its flight ends (or, GRAIN, its grain clock runs out)
         rng.n = 0;
         rng.step = (uint32_t)(P.step0 + s);
         attachReplay<RNG_MODE>(P, idx, rng);
-        const double vd = bulkParticleStep<false, RNG_MODE>(C, P, p, rng, P.idBase + idx, P.step0 + s);
+        double vd = bulkParticleStep<false, RNG_MODE>(C, P, p, rng, P.idBase + idx, P.step0 + s);
+        if constexpr (GRAIN) { // basicBulkParticleHandler.hpp:216-220, as the general kernel does it
+          g = __dsub_rn(g, dt);
+          if (g <= 0.0) {
+            g = grainEvent<RNG_MODE>(P, p, rng);
+            vd = driftVelocity<false>(C.model->valleys[p.valley], p.sub, p.k, p.energy, P.dir);
+          }
+        }
         if constexpr (RNG_MODE == RNG_REPLAY) storeCursor(P, idx, rng);
         myObs[(2 * s) * kEventThreads] += p.energy;
         myObs[(2 * s + 1) * kEventThreads] += vd;
@@ -397,9 +432,9 @@ __device__ __forceinline__ void eventRole(const BulkParams &P) {
     if (lane == 0 && a != 0.0) atomicAdd(P.obs + (r >> 1) * 3 + (r & 1), a);
   }
 }
-template <int RNG_MODE>
+template <int RNG_MODE, bool GRAIN>
 __global__ void __launch_bounds__(kEventThreadsAlone, 1) bulkEventKernel(const __grid_constant__ BulkParams P) {
-  eventRole<RNG_MODE, kEventThreadsAlone>(P);
+  eventRole<RNG_MODE, kEventThreadsAlone, GRAIN>(P);
 }
 
 __host__ __device__ inline size_t splitEventSmemBytes(const BulkSmem &L, int nSteps, int threads) {

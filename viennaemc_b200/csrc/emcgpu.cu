@@ -190,7 +190,7 @@ size_t deferSmem(const emcgpu_ctx *ctx, int steps, bool tablesInSmem) {
 bool splitEligible(const emcgpu_ctx *ctx) {
   const DevValley &v = ctx->hModel.valleys[0];
   return ctx->mathMode == EMCGPU_MATH_FAST && ctx->hModel.nValleys == 1 && v.rotKind != ROT_GENERAL && v.nonParabolic &&
-         v.alpha > 0.0 && !ctx->grainOn;
+         v.alpha > 0.0;
 }
 size_t splitEventSmem(const emcgpu_ctx *ctx, int steps, int threads) {
   const BulkSmem L(0, 1, (int)ctx->hMechs.size(), ctx->hModel.tableDoubles, false, 0);
@@ -232,6 +232,7 @@ void swapEnsembles(emcgpu_ctx *ctx) {
   std::swap(ctx->dEnsemble, ctx->dEnsembleAlt);
   for (int s = 0; s < EMCGPU_N_STREAMS; s++) std::swap(ctx->dStream[s], ctx->dStreamAlt[s]);
   std::swap(ctx->dPacked, ctx->dPackedAlt);
+  if (ctx->grainOn) std::swap(ctx->dGrain, ctx->dGrainAlt);
 }
 // one launch pair on the whole shard: flight kernel, then event kernel.  outOfPlace: the flight kernel writes the
 // look-ahead copy (which becomes the resident ensemble), the input stays as it was.
@@ -246,9 +247,13 @@ cudaError_t launchSplit(emcgpu_ctx *ctx, BulkParams &P, bool outOfPlace) {
   const int gridEvent = (int)std::max<int64_t>(1, std::min<int64_t>((claims + warps - 1) / warps, ctx->smCount));
   for (int s = 0; s < EMCGPU_N_STREAMS; s++) P.streamOut[s] = outOfPlace ? ctx->dStreamAlt[s] : nullptr;
   P.packedOut = outOfPlace ? ctx->dPackedAlt : nullptr;
+  const bool grain = ctx->grainOn;
+  P.grainOut = outOfPlace && grain ? ctx->dGrainAlt.as<double>() : nullptr;
   cudaError_t e = dispatchFlight(ppl, fieldAxis(P), [&](auto p, auto a) {
-    return launchKernel(ctx, bulkFlightKernel<decltype(p)::value, decltype(a)::value>, P, smemFlight, gridFlight,
-                        kFlightThreadsAlone, 0);
+    return grain ? launchKernel(ctx, bulkFlightKernel<decltype(p)::value, decltype(a)::value, true>, P, smemFlight, gridFlight,
+                                kFlightThreadsAlone, 0)
+                 : launchKernel(ctx, bulkFlightKernel<decltype(p)::value, decltype(a)::value, false>, P, smemFlight, gridFlight,
+                                kFlightThreadsAlone, 0);
   });
   if (e != cudaSuccess) return e;
   if (outOfPlace) {
@@ -256,10 +261,12 @@ cudaError_t launchSplit(emcgpu_ctx *ctx, BulkParams &P, bool outOfPlace) {
     for (int s = 0; s < EMCGPU_N_STREAMS; s++) P.stream[s] = ctx->dStream[s];
     P.packed = ctx->dPacked;
     P.packedOut = nullptr;
+    if (grain) P.grainTau = ctx->dGrain.as<double>();
+    P.grainOut = nullptr;
   }
-  return ctx->rngMode == RNG_PHILOX
-             ? launchKernel(ctx, bulkEventKernel<RNG_PHILOX>, P, smemEvent, gridEvent, kEventThreadsAlone, 1)
-             : launchKernel(ctx, bulkEventKernel<RNG_REPLAY>, P, smemEvent, gridEvent, kEventThreadsAlone, 1);
+  auto event = [&](auto kernel) { return launchKernel(ctx, kernel, P, smemEvent, gridEvent, kEventThreadsAlone, 1); };
+  if (ctx->rngMode == RNG_PHILOX) return grain ? event(bulkEventKernel<RNG_PHILOX, true>) : event(bulkEventKernel<RNG_PHILOX, false>);
+  return grain ? event(bulkEventKernel<RNG_REPLAY, true>) : event(bulkEventKernel<RNG_REPLAY, false>);
 }
 // K steps of the whole shard with the flight / event kernels, `window` steps per launch pair
 int runSplit(emcgpu_ctx *ctx, BulkParams &P, int nSteps, int window, double *obsDevice, bool keep) {
@@ -405,7 +412,7 @@ void emcgpu_destroy(emcgpu_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (DeviceBuffer *b : {&ctx->dModel, &ctx->dMechs, &ctx->dTables, &ctx->dEnsemble, &ctx->dDraws,
                           &ctx->dOffsets, &ctx->dCursor, &ctx->dObs, &ctx->dStatus, &ctx->dEvents,
-                          &ctx->dEvCount, &ctx->dSlices, &ctx->dEnsembleAlt, &ctx->dFrozen, &ctx->dClaim, &ctx->dBathCounts, &ctx->dBathCum, &ctx->dGrain})
+                          &ctx->dEvCount, &ctx->dSlices, &ctx->dEnsembleAlt, &ctx->dFrozen, &ctx->dClaim, &ctx->dBathCounts, &ctx->dBathCum, &ctx->dGrain, &ctx->dGrainAlt})
     b->release();
   for (cudaEvent_t &e : ctx->sliceEvents)
     if (e) cudaEventDestroy(e);
@@ -890,6 +897,9 @@ int bulkStepDevice(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPerLaunch, d
       if (!ctx->velCopied[b]) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->velCopied[b], cudaEventDisableTiming));
     }
   }
+  if (ctx->grainOn && !ctx->grainClockSet)
+    return fail(ctx, EMCGPU_E_INVALID, "a grain mechanism is set but the grain clocks were not uploaded (emcgpu_set_grain_clock)");
+  if (keep && ctx->grainOn) CUDA_TRY(ctx, ctx->dGrainAlt.ensure(ctx->dGrain.bytes));
   // several steps per launch, plain model: flight kernel + event kernel (K1d) for ensembles that fill the machine
   if (!record) {
     const int ppl = ctx->optSplitPpl == 2 ? 2 : 4;
@@ -911,6 +921,9 @@ int bulkStepDevice(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPerLaunch, d
   if (keep) { // the other step kernels work in place: copy first
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dEnsembleAlt.ptr, ctx->dEnsemble.ptr, ensembleBytes(ctx->n), cudaMemcpyDeviceToDevice,
                                   ctx->stream));
+    if (ctx->grainOn)
+      CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dGrainAlt.ptr, ctx->dGrain.ptr, (size_t)ctx->n * sizeof(double), cudaMemcpyDeviceToDevice,
+                                    ctx->stream));
   }
   int recordIdx = 0;
   for (int done = 0; done < nSteps;) {
@@ -1030,8 +1043,7 @@ int emcgpu_bulk_step_device(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPer
 int emcgpu_bulk_step_ahead(emcgpu_ctx *ctx, double dt, int nSteps, int stepsPerLaunch, double *obs) {
   if (int r = checkReady(ctx, true)) return r;
   if (nSteps < 1) return fail(ctx, EMCGPU_E_INVALID, "nSteps must be >= 1");
-  if (ctx->rngMode != RNG_PHILOX || ctx->grainOn)
-    return fail(ctx, EMCGPU_E_INVALID, "emcgpu_bulk_step_ahead needs the Philox streams and carries no grain clocks");
+  if (ctx->rngMode != RNG_PHILOX) return fail(ctx, EMCGPU_E_INVALID, "emcgpu_bulk_step_ahead needs the Philox streams");
   if (int r = bind(ctx)) return r;
   const size_t bytes = (size_t)nSteps * ctx->hModel.nValleys * 3 * sizeof(double);
   CUDA_TRY(ctx, ctx->dObs.ensure(bytes));

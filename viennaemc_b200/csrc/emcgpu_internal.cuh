@@ -115,7 +115,7 @@ struct emcgpu_ctx {
   // grain boundaries (emcgpu_set_grain): clock per particle
   bool grainOn = false, grainClockSet = false;
   double grainProb = 0.5, grainTau0 = 1.0;
-  emc::DeviceBuffer dGrain;
+  emc::DeviceBuffer dGrain, dGrainAlt; // Alt: the clocks of the look-ahead copy (emcgpu_bulk_step_ahead)
 
   // outputs
   emc::DeviceBuffer dObs, dStatus, dEvents, dEvCount;
@@ -139,6 +139,7 @@ int failWith(emcgpu_ctx *ctx, int code, const char *fmt, ...);
 
 inline void fillGrain(const emcgpu_ctx *ctx, BulkParams &P) {
   P.grainTau = ctx->grainOn ? ctx->dGrain.as<double>() : nullptr;
+  P.grainOut = nullptr;
   P.grainProb = ctx->grainProb;
   P.grainTau0 = ctx->grainTau0;
 }

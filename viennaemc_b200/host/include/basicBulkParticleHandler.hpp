@@ -24,8 +24,8 @@
 //     lookahead-1 calls -- and their getAvg* -- are served from the series that launch delivered.  Whatever needs the
 //     ensemble of the driver's current step (print, printVelocities, a new field, seed, table rebuild, ...) first
 //     rewinds to the state before the launch and repeats exactly the steps served so far: the random numbers are keyed
-//     by particle id and step, so this reproduces them bit for bit.  Types with phonon baths or a grain mechanism
-//     (per-step host feedback) keep one step per call;
+//     by particle id and step, so this reproduces them bit for bit.  Types with phonon baths (per-step host feedback)
+//     keep one step per call; the grain clocks of a grain mechanism ride along (the look-ahead copy has its own);
 //   * random numbers in the step are counter-based Philox streams keyed by particle
 //     id and step (not one mt19937_64 per OpenMP thread), seeded from the handler seed;
 //   * nothing is moved on the CPU: without a CUDA device, or with a mechanism /
@@ -322,7 +322,7 @@ public:
       materialize(idxType);
       upload(idxType);
       refreshModel(idxType);
-      SizeType nAhead = (st.phononBaths.empty() && !st.grain) ? lookahead : 1;
+      SizeType nAhead = st.phononBaths.empty() ? lookahead : 1;
       st.velSteps = 0;
       if (st.recordVel) { // the window's velocities come back with it (at most 1 GB of them per window)
         const SizeType perStep = st.nrParticles * st.recordVel;
