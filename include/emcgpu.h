@@ -35,7 +35,7 @@ extern "C" {
 #define EMCGPU_MAX_VALLEYS 8
 #define EMCGPU_MAX_SUBVALLEYS 8
 #define EMCGPU_MAX_FINAL 8
-#define EMCGPU_MAX_MECH_PER_SET 16
+#define EMCGPU_MAX_MECH_PER_SET 32
 #define EMCGPU_MAX_TABLESETS 32
 #define EMCGPU_NAME_LEN 48
 
@@ -56,7 +56,17 @@ typedef enum {
   EMCGPU_VALLEY_PARABOLIC_ISOTROP = 0,
   EMCGPU_VALLEY_NONPARABOLIC_ISOTROP = 1,
   EMCGPU_VALLEY_PARABOLIC_ANISOTROP = 2,
-  EMCGPU_VALLEY_NONPARABOLIC_ANISOTROP = 3
+  EMCGPU_VALLEY_NONPARABOLIC_ANISOTROP = 3,
+  /* single-layer (2-D material in the x-y plane) classes: bit 0 non-parabolic, bit 1 anisotropic, bit 2 single layer.
+   *   emcParabolicIsotropSingleLayerValley.hpp, emcNonParabolicIsotropSingleLayerValley.hpp: Herring-Vogt factors
+   *   (1, 1, 0) -- k_z and z never change;
+   *   emcNonParabolicAnisotropSingleLayerValley.hpp: vogt = (sqrt(m_DOS/m_l), sqrt(m_DOS/m_t), 0), m_DOS = sqrt(m_l m_t)
+   *   is the mass of the dispersion, of |k|(E) and of the velocity (:123-148), m_c = 2/(1/m_l + 1/m_t) that of the
+   *   position update (getEffMassCond, :117-119); rot[s] = rows (cos a, -sin a, 0), (sin a, cos a, 0), (0, 0, 0) of the
+   *   sub-valley's in-plane angle (:151-169).  (The reference has no parabolic anisotropic single-layer class.) */
+  EMCGPU_VALLEY_PARABOLIC_ISOTROP_SINGLE_LAYER = 4,
+  EMCGPU_VALLEY_NONPARABOLIC_ISOTROP_SINGLE_LAYER = 5,
+  EMCGPU_VALLEY_NONPARABOLIC_ANISOTROP_SINGLE_LAYER = 7
 } emcgpu_valley_kind;
 
 /* One emcAbstractValley (include/ValleyTypes/emcAbstractValley.hpp:20-91) as the
@@ -98,7 +108,15 @@ typedef enum {
   /* emcScreenedFroehlichInteraction.hpp:140-153, :199-213, :272-294, :354-374: the same with the screened polar angle
    * (helpers :66-97): param[1] = qs^2 [1/m^2]; param[3] != 0: |q| drawn from the occupation-weighted window of bath
    * param[2] (emcPhononBath::sampleQ, q-resolved) instead of the closed form */
-  EMCGPU_SAMPLER_SCREENED_FROEHLICH = 5
+  EMCGPU_SAMPLER_SCREENED_FROEHLICH = 5,
+  /* emcAcousticSingleLayerScatterMechanism.hpp:63-81 (elastic): in-plane angle 2 pi u, direction (cos/vogt_x, sin/vogt_y, 0)
+   * normalised, |k| <- k_norm(E) of the particle's valley */
+  EMCGPU_SAMPLER_SINGLE_LAYER_ELASTIC = 6,
+  /* emcZeroOrderSingleLayerInterValleyScatterMechanism.hpp:116-147, :293-324: valley <- finalValley; nFinal > 0:
+   * subValley <- finalSub[sub][floor(u nFinal)] (nFinal = 0: the one-valley constructor, no draw); E += param[0]
+   * (+(hw - dE_valley) absorption, -(dE_valley + hw) emission); then the direction of SINGLE_LAYER_ELASTIC in the final
+   * valley */
+  EMCGPU_SAMPLER_SINGLE_LAYER_INTERVALLEY = 7
 } emcgpu_sampler_id;
 #define EMCGPU_MAX_BATHS 8
 

@@ -139,7 +139,10 @@ static double sq3(const double k[3]) {
   res += k[2] * k[2];
   return res;
 }
-static int is_aniso(const orc_valley_t *v) { return v->kind >= 2; }
+static int is_aniso(const orc_valley_t *v) { return (v->kind & 2) != 0; }
+/* the mass of the dispersion (getEnergy, getNormWaveVec, getVelocity): the conduction mass in the 3-D classes, the
+ * density-of-states mass sqrt(ml mt) in emcNonParabolicAnisotropSingleLayerValley.hpp:123-148 */
+static double band_mass(const orc_valley_t *v) { return v->kind == ORC_VALLEY_NONPARABOLIC_ANISO_SL ? v->mDos : v->mCond; }
 static int is_nonparabolic(const orc_valley_t *v) { return v->kind & 1; }
 
 /* emcNonParabolicAnistropValley.hpp:122, emcNonParabolicIsotropValley.hpp:99,
@@ -154,8 +157,10 @@ double orc_eff_mass_cond(const orc_valley_t *v, double e) {
 /* emcNonParabolicAnistropValley.hpp:109-113, emcNonParabolicIsotropValley.hpp:78-82,
  * emcParabolicIsotropValley.hpp:62-65, emcParabolicAnisotropValley.hpp:100-103 */
 double orc_energy(const orc_valley_t *v, const double k[3]) {
+  /* single-layer classes (...SingleLayerValley.hpp getEnergy): k[0]*k[0] + k[1]*k[1], which is sq3(k) bit for bit with
+   * k[2] = 0 */
   if (is_nonparabolic(v)) {
-    double gamma = C_HBAR * C_HBAR * sq3(k) / (v->mCond * C_Q);
+    double gamma = C_HBAR * C_HBAR * sq3(k) / (band_mass(v) * C_Q);
     return gamma / (1 + sqrt(1 + 2 * v->alpha * gamma));
   }
   return C_HBAR * C_HBAR * sq3(k) / (2 * v->mCond * C_Q);
@@ -165,7 +170,7 @@ double orc_energy(const orc_valley_t *v, const double k[3]) {
 double orc_norm_wave_vec(const orc_valley_t *v, double e) {
   if (v->kind == ORC_VALLEY_NONPARABOLIC_ANISO)
     return sqrt(2 * v->mCond * orc_gamma(v, e) * C_Q) / C_HBAR;
-  return sqrt(2 * v->mCond * C_Q * orc_gamma(v, e)) / C_HBAR;
+  return sqrt(2 * band_mass(v) * C_Q * orc_gamma(v, e)) / C_HBAR;
 }
 /* :140-153 */
 void orc_to_ellipse(const orc_valley_t *v, int s, const double in[3], double out[3]) {
@@ -194,12 +199,15 @@ void orc_to_device(const orc_valley_t *v, int s, const double in[3], double out[
 /* getVelocity: aniso NP :126-136, iso NP :85-90, iso P :74-77, aniso P :106-114 */
 void orc_velocity(const orc_valley_t *v, const double k[3], double e, int s, double out[3]) {
   switch (v->kind) {
+  case ORC_VALLEY_NONPARABOLIC_ANISO_SL: /* emcNonParabolicAnisotropSingleLayerValley.hpp:137-148: m_DOS; z stays 0 */
   case ORC_VALLEY_NONPARABOLIC_ANISO: {
     double ke[3], ve[3];
     orc_to_ellipse(v, s, k, ke);
     double npf = sqrt(1 + 4 * v->alpha * orc_gamma(v, e));
     for (int i = 0; i < 3; i++)
-      ve[i] = C_HBAR * v->vogt[i] * ke[i] / (v->mCond * npf);
+      ve[i] = C_HBAR * v->vogt[i] * ke[i] / (band_mass(v) * npf);
+    if (v->kind == ORC_VALLEY_NONPARABOLIC_ANISO_SL)
+      ve[2] = 0;
     orc_to_device(v, s, ve, out);
     break;
   }
@@ -211,6 +219,7 @@ void orc_velocity(const orc_valley_t *v, const double k[3], double e, int s, dou
     orc_to_device(v, s, ve, out);
     break;
   }
+  case ORC_VALLEY_NONPARABOLIC_ISO_SL:
   case ORC_VALLEY_NONPARABOLIC_ISO: {
     double f = C_HBAR / (v->mCond * sqrt(1 + 4 * v->alpha * orc_gamma(v, e)));
     for (int i = 0; i < 3; i++)
@@ -276,7 +285,7 @@ void orc_random_direction_wrt_k(const double k[3], double cosTheta, double rnd, 
 }
 
 /* ------------------------------------------------------------------ model */
-enum { MK_ACOUSTIC = 1, MK_ZERO = 2, MK_FIRST = 3, MK_COULOMB = 4, MK_FROEHLICH = 5 };
+enum { MK_ACOUSTIC = 1, MK_ZERO = 2, MK_FIRST = 3, MK_COULOMB = 4, MK_FROEHLICH = 5, MK_ACOUSTIC_SL = 6, MK_ZERO_SL = 7 };
 
 typedef struct {
   int kind, valley, finalValley, region, emission, nFinal, nInitSub;
@@ -320,6 +329,7 @@ struct orc_model {
   int hasGrain;
   double grainProb, grainTau; /* grainTau = 1 / rate (emcScatterHandler.hpp:234), 1 s without a mechanism */
   double initEnergy; /* > 0: mono-energetic initial ensemble (emcElectron / emcHole initEnergyEV), 0: Maxwellian */
+  int electron2D;    /* > 0: examples/singleLayerMoS2/electron2D.hpp -- that many particles per grid point, in-plane k */
 };
 
 orc_model_t *orc_model_create(int nLevels, double maxEnergy, double temperature,
@@ -336,6 +346,8 @@ orc_model_t *orc_model_create(int nLevels, double maxEnergy, double temperature,
 }
 /* emcElectron.hpp:85-88 / emcHole.hpp:95-98: initParticleKSpaceFixed instead of the Maxwellian (no energy draw) */
 void orc_model_set_init_energy(orc_model_t *m, double energyEV) { m->initEnergy = energyEV; }
+/* examples/singleLayerMoS2/electron2D.hpp:38-67 as the particle type of the initial ensemble */
+void orc_model_set_electron2d(orc_model_t *m, int perGridPoint) { m->electron2D = perGridPoint; }
 void orc_model_destroy(orc_model_t *m) {
   if (!m)
     return;
@@ -357,7 +369,28 @@ int orc_add_valley(orc_model_t *m, int kind, const double relMass[3], double par
   v->eBottom = eBottom;
   for (int s = 0; s < ORC_MAX_SUB; s++)
     v->rot[s][0] = v->rot[s][4] = v->rot[s][8] = 1.;
-  if (kind >= 2) {
+  if (kind == ORC_VALLEY_NONPARABOLIC_ANISO_SL) {
+    /* emcNonParabolicAnisotropSingleLayerValley.hpp:79-113: relMass = {longitudinal, transversal, -}; dirs = one
+     * rotation angle per sub-valley (first entry of each 9-block); frame rows (cos, -sin, 0), (sin, cos, 0), (0, 0, 0) */
+    const double mL = relMass[0] * particleMass, mT = relMass[1] * particleMass;
+    v->mCond = 2. / (1. / mL + 1. / mT);
+    v->mDos = sqrt(mL * mT);
+    v->vogt[0] = sqrt(v->mDos / mL);
+    v->vogt[1] = sqrt(v->mDos / mT);
+    v->vogt[2] = 0;
+    for (int s = 0; s < deg; s++) {
+      const double angle = dirs ? dirs[s * 9] : 0.;
+      const double sn = sin(angle), cs = cos(angle);
+      double *r = v->rot[s];
+      memset(r, 0, 9 * sizeof(double));
+      r[0] = cs; r[1] = -sn;
+      r[3] = sn; r[4] = cs;
+    }
+  } else if (kind == ORC_VALLEY_PARABOLIC_ISO_SL || kind == ORC_VALLEY_NONPARABOLIC_ISO_SL) {
+    v->mCond = v->mDos = relMass[0] * particleMass;
+    v->vogt[0] = v->vogt[1] = 1.;
+    v->vogt[2] = 0.;
+  } else if (kind >= 2) {
     double prod = 1.;
     for (int i = 0; i < 3; i++)
       prod = prod * relMass[i];
@@ -430,6 +463,47 @@ int orc_add_intervalley(orc_model_t *m, int order, int emission, int valley, int
              (C_PI * m->rho * pow(C_HBAR, 4) * phE);
   double nrPh = 1. / (exp(C_Q * phE / (C_KB * m->temperature)) - 1.);
   x->scatterConst = emission ? result * (nrPh + 1) : result * nrPh;
+  return m->nMech++;
+}
+
+/* emcAcousticSingleLayerScatterMechanism.hpp:42-50 */
+int orc_add_acoustic_sl(orc_model_t *m, int valley, int region, double sigma, double density2D, double vSound) {
+  mech_t *x = &m->mech[m->nMech];
+  memset(x, 0, sizeof *x);
+  x->kind = MK_ACOUSTIC_SL;
+  x->valley = x->finalValley = valley;
+  x->region = region;
+  double cL = density2D * pow(vSound, 2);
+  x->scatterConst = pow(sigma * C_Q, 2) * C_KB * m->temperature / (cL * pow(C_HBAR, 3));
+  return m->nMech++;
+}
+
+/* emcZeroOrderSingleLayerInterValleyScatterMechanism.hpp:66-88 (absorption), :243-266 (emission); nFinal = 0: the
+ * one-valley constructor (:42-49): nrFinalValleys = 1 and no sub-valley draw */
+int orc_add_intervalley_sl(orc_model_t *m, int emission, int valley, int finalValley, int region, double sigma,
+                           double density2D, double phE, int nInitSub, int nFinal, const int32_t *finalSub) {
+  if (nFinal > ORC_MAX_FINAL || nInitSub > ORC_MAX_SUB)
+    return -1;
+  mech_t *x = &m->mech[m->nMech];
+  memset(x, 0, sizeof *x);
+  x->kind = MK_ZERO_SL;
+  x->valley = valley;
+  x->finalValley = finalValley;
+  x->region = region;
+  x->emission = emission;
+  x->nFinal = nFinal;
+  x->nInitSub = nInitSub;
+  x->phononEnergy = phE;
+  for (int i = 0; i < nInitSub; i++)
+    for (int j = 0; j < nFinal; j++)
+      x->finalSub[i][j] = finalSub[i * nFinal + j];
+  const double nrFinal = nFinal > 0 ? (double)nFinal : 1.;
+  double exponent = phE * C_Q / (C_KB * m->temperature);
+  double omega = phE * C_Q / C_HBAR;
+  if (emission)
+    x->scatterConst = nrFinal * pow(sigma * C_Q / C_HBAR, 2) * exp(exponent) / (2 * density2D * omega * (exp(exponent) - 1));
+  else
+    x->scatterConst = nrFinal * pow(sigma * C_Q / C_HBAR, 2) / (2 * density2D * omega * (exp(exponent) - 1));
   return m->nMech++;
 }
 
@@ -526,6 +600,21 @@ double orc_raw_rate(const orc_model_t *m, int g, double energy) {
       double alpha = vf->alpha;
       double gamma = orc_gamma(vf, ef);
       return x->scatterConst * pow(md, 3. / 2.) * sqrt(gamma) * (2 * alpha * ef + 1.0);
+    }
+    return 0;
+  }
+  case MK_ACOUSTIC_SL: { /* emcAcousticSingleLayerScatterMechanism.hpp:55-60 */
+    double md = dos_mass_at_zero(vi);
+    double alpha = vi->alpha;
+    return md * x->scatterConst * (1 + 2 * alpha * energy);
+  }
+  case MK_ZERO_SL: { /* emcZeroOrderSingleLayer...:96-108, :274-286 */
+    double dV = delta_valley(m, x);
+    double ef = x->emission ? energy - x->phononEnergy - dV : energy + x->phononEnergy - dV;
+    if (ef > 0) {
+      double md = dos_mass_at_zero(vf);
+      double alpha = vf->alpha;
+      return md * x->scatterConst * (1 + 2 * alpha * ef);
     }
     return 0;
   }
@@ -675,6 +764,15 @@ static void fill_mech_desc(const orc_model_t *m, int g, orc_mech_t *d) {
     d->p[0] = x->emission ? -(x->phononEnergy + dV) : (x->phononEnergy - dV);
     break;
   }
+  case MK_ACOUSTIC_SL:
+    d->sampler = ORC_SAMPLER_SL_ELASTIC;
+    break;
+  case MK_ZERO_SL: { /* abs: E += hw - dV (:127); em: E -= (dV + hw) (:304) */
+    d->sampler = ORC_SAMPLER_SL_INTERVALLEY;
+    double dV = delta_valley(m, x);
+    d->p[0] = x->emission ? -(dV + x->phononEnergy) : (x->phononEnergy - dV);
+    break;
+  }
   case MK_FROEHLICH:
     d->sampler = x->variant < 2 ? ORC_SAMPLER_FROEHLICH : ORC_SAMPLER_SCREENED_FROEHLICH;
     d->p[0] = x->emission ? -x->phononEnergy : x->phononEnergy;
@@ -772,6 +870,31 @@ static void scatter_with(const orc_model_t *m, const orc_mech_t *d, orc_ensemble
     double r2 = rng_u01(rng);
     double r1 = rng_u01(rng);
     orc_random_direction(knew, r1, r2, out);
+    break;
+  }
+  case ORC_SAMPLER_SL_ELASTIC:
+  case ORC_SAMPLER_SL_INTERVALLEY: {
+    /* emcAcousticSingleLayerScatterMechanism.hpp:63-81; emcZeroOrderSingleLayerInterValleyScatterMechanism.hpp:116-147,
+     * :293-324 */
+    if (d->sampler == ORC_SAMPLER_SL_INTERVALLEY) {
+      int subOld = e->sub[p];
+      e->valley[p] = d->finalValley;
+      if (d->nFinal > 0)
+        e->sub[p] = d->finalSub[subOld][(int)floor(rng_u01(rng) * d->nFinal)];
+      e->energy[p] += d->p[0];
+    }
+    const orc_valley_t *v = &m->valleys[e->valley[p]];
+    double angle = 2 * C_PI * rng_u01(rng);
+    /* random direction weighted by the Herring-Vogt factors */
+    out[0] = cos(angle) / v->vogt[0];
+    out[1] = sin(angle) / v->vogt[1];
+    out[2] = 0;
+    double factor = 1. / (sqrt(out[0] * out[0] + out[1] * out[1]));
+    out[0] *= factor;
+    out[1] *= factor;
+    double normK = orc_norm_wave_vec(v, e->energy[p]);
+    out[0] *= normK;
+    out[1] *= normK;
     break;
   }
   case ORC_SAMPLER_COULOMB: {
@@ -1219,6 +1342,8 @@ int64_t orc_generate_initial(const orc_model_t *m, const double box[3], const in
           if (c[d] == 0 || c[d] == ext[d] - 1)
             dens *= 0.5;
         double nr = dens * cellVolume;
+        if (m->electron2D > 0)
+          nr = m->electron2D; /* electron2D.hpp:38-41 */
         /* basicBulkParticleHandler.hpp:150-156 */
         for (;;) {
           int create = 0;
@@ -1241,20 +1366,33 @@ int64_t orc_generate_initial(const orc_model_t *m, const double box[3], const in
               else
                 pos[d] = ((double)c[d] + rng_u01(&rng) - 0.5) * h[d];
             }
-            /* emcElectron.hpp:75-90 */
-            int valley = (int)floor(m->nValleys * rng_ulog(&rng));
-            const orc_valley_t *v = &m->valleys[valley];
-            int sub = (int)floor(v->deg * rng_ulog(&rng));
-            /* emcParticleInitialization.hpp:36-51 */
-            /* emcParticleInitialization.hpp:36-51; :60-74 for a fixed start energy (no draw) */
-            double energy = m->initEnergy > 0. ? m->initEnergy : -1.5 * Vt * log(rng_ulog(&rng));
-            double r2 = rng_u01(&rng); /* right-to-left: first draw is rand2 */
-            double r1 = rng_u01(&rng);
-            double k[3];
-            orc_random_direction(orc_norm_wave_vec(v, energy), r1, r2, k);
-            for (int d = 0; d < 3; d++)
-              if ((c[d] == 0 && k[d] < 0) || (c[d] == ext[d] - 1 && k[d] > 0))
-                k[d] *= -1;
+            int valley, sub;
+            double energy, k[3];
+            if (m->electron2D > 0) {
+              /* electron2D.hpp:43-67: first valley, random sub-valley, 2-D thermal energy, in-plane direction */
+              valley = 0;
+              const orc_valley_t *v = &m->valleys[0];
+              sub = (int)floor(v->deg * rng_u01(&rng));
+              energy = -Vt * log(rng_ulog(&rng));
+              double normK = orc_norm_wave_vec(v, energy);
+              double angle = 2 * C_PI * rng_u01(&rng);
+              k[0] = normK * cos(angle);
+              k[1] = normK * sin(angle);
+              k[2] = 0;
+            } else {
+              /* emcElectron.hpp:75-90 */
+              valley = (int)floor(m->nValleys * rng_ulog(&rng));
+              const orc_valley_t *v = &m->valleys[valley];
+              sub = (int)floor(v->deg * rng_ulog(&rng));
+              /* emcParticleInitialization.hpp:36-51; :60-74 for a fixed start energy (no draw) */
+              energy = m->initEnergy > 0. ? m->initEnergy : -1.5 * Vt * log(rng_ulog(&rng));
+              double r2 = rng_u01(&rng); /* right-to-left: first draw is rand2 */
+              double r1 = rng_u01(&rng);
+              orc_random_direction(orc_norm_wave_vec(v, energy), r1, r2, k);
+              for (int d = 0; d < 3; d++)
+                if ((c[d] == 0 && k[d] < 0) || (c[d] == ext[d] - 1 && k[d] > 0))
+                  k[d] *= -1;
+            }
             double tau = -log(rng_ulog(&rng)) * orc_tau(m, valley, 0);
             double gtau = -log(rng_ulog(&rng)) * m->grainTau;
             out->kx[n] = k[0]; out->ky[n] = k[1]; out->kz[n] = k[2];

@@ -22,8 +22,12 @@ extern "C" {
 #define ORC_MAX_SUB 8
 #define ORC_MAX_FINAL 8
 
+/* bit 0: non-parabolic, bit 1: anisotropic (sub-valley frames), bit 2: single layer (2-D material in the x-y plane:
+ * ValleyTypes/emcParabolicIsotropSingleLayerValley.hpp, emcNonParabolicIsotropSingleLayerValley.hpp,
+ * emcNonParabolicAnisotropSingleLayerValley.hpp; the reference has no parabolic anisotropic single-layer class) */
 enum { ORC_VALLEY_PARABOLIC_ISO = 0, ORC_VALLEY_NONPARABOLIC_ISO = 1,
-       ORC_VALLEY_PARABOLIC_ANISO = 2, ORC_VALLEY_NONPARABOLIC_ANISO = 3 };
+       ORC_VALLEY_PARABOLIC_ANISO = 2, ORC_VALLEY_NONPARABOLIC_ANISO = 3,
+       ORC_VALLEY_PARABOLIC_ISO_SL = 4, ORC_VALLEY_NONPARABOLIC_ISO_SL = 5, ORC_VALLEY_NONPARABOLIC_ANISO_SL = 7 };
 
 enum { ORC_SAMPLER_NONE = 0, ORC_SAMPLER_ISOTROPIC_ELASTIC = 1,
        ORC_SAMPLER_INTERVALLEY = 2, ORC_SAMPLER_COULOMB = 3,
@@ -32,7 +36,14 @@ enum { ORC_SAMPLER_NONE = 0, ORC_SAMPLER_ISOTROPIC_ELASTIC = 1,
        ORC_SAMPLER_FROEHLICH = 4,
        /* emcScreenedFroehlichInteraction.hpp:140-153 ... :354-374: p[0] = signed phonon energy, p[1] = qs^2,
         * p[2] = phonon bath index or -1, p[3] = 1: polar angle through bath.sampleQ (q-resolved) */
-       ORC_SAMPLER_SCREENED_FROEHLICH = 5 };
+       ORC_SAMPLER_SCREENED_FROEHLICH = 5,
+       /* emcAcousticSingleLayerScatterMechanism.hpp:63-81: elastic, in-plane angle 2 pi u weighted by the Herring-Vogt
+        * factors of the particle's valley, k_z = 0 */
+       ORC_SAMPLER_SL_ELASTIC = 6,
+       /* emcZeroOrderSingleLayerInterValleyScatterMechanism.hpp:116-147, :293-324: valley <- finalValley; nFinal > 0:
+        * sub <- finalSub[sub][floor(u nFinal)] (one draw; none for the one-valley constructor); E += p[0]; then the
+        * direction of SL_ELASTIC in the FINAL valley */
+       ORC_SAMPLER_SL_INTERVALLEY = 7 };
 
 enum { ORC_RNG_MT_GLOBAL = 0, ORC_RNG_STREAMS = 1, ORC_RNG_PHILOX = 2 };
 
@@ -75,7 +86,12 @@ typedef struct orc_model orc_model_t;
 orc_model_t *orc_model_create(int nLevels, double maxEnergy, double temperature,
                               double rho, double vSound);
 void orc_model_destroy(orc_model_t *m);
+void orc_model_set_electron2d(orc_model_t *m, int perGridPoint); /* examples/singleLayerMoS2/electron2D.hpp */
 void orc_model_set_init_energy(orc_model_t *m, double energyEV); /* emcElectron.hpp:85-88, emcHole.hpp:95-98 */
+/* single-layer mechanisms; density2D [kg/m^2], the model's temperature */
+int orc_add_acoustic_sl(orc_model_t *m, int valley, int region, double sigma, double density2D, double vSound);
+int orc_add_intervalley_sl(orc_model_t *m, int emission, int valley, int finalValley, int region, double sigma,
+                           double density2D, double phE, int nInitSub, int nFinal, const int32_t *finalSub);
 int orc_add_valley(orc_model_t *m, int kind, const double relMass[3],
                    double particleMass, int deg, double alpha, double eBottom,
                    const double *dirs /* [deg][3][3] un-normalised or NULL */);

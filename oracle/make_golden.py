@@ -18,7 +18,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from scenarios import DEVICE_CASES, GA2O3_CASES, GOLDEN_CASES, MHP_CASES, ga2o3_args, mhp_args  # noqa: E402
+from scenarios import DEVICE_CASES, GA2O3_CASES, GOLDEN_CASES, MHP_CASES, MOS2_CASES, ga2o3_args, mhp_args  # noqa: E402
 
 DT = {"d": np.float64, "q": np.int64, "Q": np.uint64}
 
@@ -66,6 +66,34 @@ def main():
         np.savez_compressed(dst, **blob)
         print(name, "->", dst, os.path.getsize(dst) // 1024, "KiB; particles", int(blob["params"][-1]),
               "draws", n_draws, "events", n_events)
+
+
+def main_mos2():
+    """single-layer MoS2 (examples/singleLayerMoS2, Pilotto parameter set) through the same recorder"""
+    import hashlib
+    subprocess.check_call(["make", "-C", HERE, "_ref/ref_bulk_driver"], stdout=subprocess.DEVNULL)
+    drv = os.path.join(HERE, "_ref", "ref_bulk_driver")
+    for name, args in MOS2_CASES.items():
+        with tempfile.TemporaryDirectory() as tmp:
+            out = os.path.join(tmp, "ref.bin")
+            cmd = [drv, "--out", out]
+            for k, v in args.items():
+                cmd += ["--" + k, str(v)]
+            subprocess.check_call(cmd, cwd=tmp, stdout=subprocess.DEVNULL)
+            blob = read_blob(out)
+        n_draws, n_events = len(blob["draws"]), len(blob["events"])
+        blob["draws_count"] = np.array([n_draws], dtype=np.int64)
+        blob["draws_sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(blob["draws"]).tobytes()).digest(), dtype=np.uint8)
+        del blob["draws"]
+        blob["events"] = blob["events"].astype(np.int32)
+        blob["raw_rates"] = blob["raw_rates"][:, ::25].copy()  # every 25th of the 5000 levels: the full tables are in cum_*
+        if name != "mos2_pilotto":  # the same model: the tables are pinned by the first case
+            for k in [k for k in blob if k.startswith("cum_") or k == "raw_rates"]:
+                del blob[k]
+        dst = os.path.join(ROOT, "tests", "golden", name + ".npz")
+        np.savez_compressed(dst, **blob)
+        print(name, "->", dst, os.path.getsize(dst) // 1024, "KiB; particles", int(blob["params"][-1]), "draws", n_draws,
+              "events", n_events)
 
 
 def main_device():
@@ -138,3 +166,5 @@ if __name__ == "__main__":
         main_ga2o3()
     if which in ("all", "mhp"):
         main_mhp()
+    if which in ("all", "mos2"):
+        main_mos2()

@@ -17,6 +17,7 @@ _LIB = None
 MAX_SUB = 8
 MAX_FINAL = 8
 VALLEY_PARABOLIC_ISO, VALLEY_NONPARABOLIC_ISO, VALLEY_PARABOLIC_ANISO, VALLEY_NONPARABOLIC_ANISO = range(4)
+VALLEY_PARABOLIC_ISO_SL, VALLEY_NONPARABOLIC_ISO_SL, VALLEY_NONPARABOLIC_ANISO_SL = 4, 5, 7  # single-layer classes
 SAMPLER_NONE, SAMPLER_ISOTROPIC_ELASTIC, SAMPLER_INTERVALLEY, SAMPLER_COULOMB = range(4)
 RNG_MT_GLOBAL, RNG_STREAMS, RNG_PHILOX = range(3)
 
@@ -70,11 +71,15 @@ def lib():
         L.orc_model_create.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
         L.orc_model_destroy.argtypes = [C.c_void_p]
         L.orc_model_set_init_energy.argtypes = [C.c_void_p, C.c_double]
+        L.orc_model_set_electron2d.argtypes = [C.c_void_p, C.c_int]
         L.orc_add_valley.argtypes = [C.c_void_p, C.c_int, _DP, C.c_double, C.c_int, C.c_double, C.c_double, _DP]
         L.orc_add_acoustic.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
         L.orc_add_intervalley.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
                                           C.c_double, C.c_int, C.c_int, _IP]
         L.orc_add_coulomb.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
+        L.orc_add_acoustic_sl.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
+        L.orc_add_intervalley_sl.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                             C.c_double, C.c_int, C.c_int, _IP]
         L.orc_build_tables.argtypes = [C.c_void_p]
         L.orc_model_set_grain.argtypes = [C.c_void_p, C.c_double, C.c_double]
         # Froehlich family + phonon bath
@@ -223,9 +228,13 @@ class Model:
         except Exception:
             pass
 
-    def add_valley(self, kind, rel_mass, deg, alpha=0.0, e_bottom=0.0, dirs=None, particle_mass=ME):
+    def add_valley(self, kind, rel_mass, deg, alpha=0.0, e_bottom=0.0, dirs=None, particle_mass=ME, angles=None):
+        """angles: the in-plane rotation angle of every sub-valley of the anisotropic single-layer class"""
         rm = np.ascontiguousarray(np.broadcast_to(np.asarray(rel_mass, dtype=np.float64), (3,)))
         d = None
+        if angles is not None:
+            dirs = np.zeros((deg, 3, 3))
+            dirs[:, 0, 0] = angles
         if dirs is not None:
             d = np.ascontiguousarray(np.asarray(dirs, dtype=np.float64).reshape(deg, 3, 3))
         r = self.L.orc_add_valley(self.h, kind, _dp(rm), particle_mass, deg, alpha, e_bottom,
@@ -240,6 +249,22 @@ class Model:
         fs = np.ascontiguousarray(np.asarray(final_sub, dtype=np.int32))
         r = self.L.orc_add_intervalley(self.h, order, int(emission), valley, final_valley, region, def_pot,
                                        phonon_energy, fs.shape[0], fs.shape[1], _ip(fs))
+        assert r >= 0
+        return r
+
+    def add_acoustic_sl(self, valley, region, sigma, density_2d, v_sound):
+        """emcAcousticSingleLayerMechanism"""
+        return self.L.orc_add_acoustic_sl(self.h, valley, region, sigma, density_2d, v_sound)
+
+    def add_intervalley_sl(self, emission, valley, final_valley, region, sigma, density_2d, phonon_energy, final_sub=None):
+        """emcZeroOrderSingleLayerInterValley{Absorption,Emission}ScatterMechanism; final_sub None: the one-valley form"""
+        if final_sub is None:
+            r = self.L.orc_add_intervalley_sl(self.h, int(emission), valley, final_valley, region, sigma, density_2d,
+                                              phonon_energy, 0, 0, None)
+        else:
+            fs = np.ascontiguousarray(np.asarray(final_sub, dtype=np.int32))
+            r = self.L.orc_add_intervalley_sl(self.h, int(emission), valley, final_valley, region, sigma, density_2d,
+                                              phonon_energy, fs.shape[0], fs.shape[1], _ip(fs))
         assert r >= 0
         return r
 
@@ -322,6 +347,10 @@ class Model:
         s = ens.c()
         self.L.orc_bulk_observables(self.h, C.byref(s), _dp(np.asarray(field_dir, dtype=np.float64)), _dp(obs))
         return obs
+
+    def set_electron2d(self, per_grid_point=4):
+        """initial ensemble of examples/singleLayerMoS2/electron2D.hpp"""
+        self.L.orc_model_set_electron2d(self.h, per_grid_point)
 
     def set_init_energy(self, energy_ev):
         """mono-energetic initial ensemble (emcElectron / emcHole initEnergyEV)"""

@@ -39,6 +39,9 @@
 #include <emcGrainScatterMechanism.hpp>
 
 #include <basicBulkParticleHandler.hpp> // -I $(REF)/examples/bulkSimulation
+// single-layer MoS2 (examples/singleLayerMoS2): the example's own particle type and its default parameter set
+#include <electron2D.hpp>       // -I $(REF)/examples/singleLayerMoS2
+#include <parameterPilotto.hpp> //
 
 using T = double;
 using DeviceType = emcDevice<T, 3>;
@@ -251,6 +254,21 @@ void buildMixed(PT &type, DeviceType &device, const std::string &mechs) {
   }
 }
 
+// Single-layer MoS2 exactly as examples/singleLayerMoS2/singleLayerMoS2.cpp:97-104 sets it up with its default parameter
+// set (Pilotto: K valleys isotropic, Q valleys anisotropic with in-plane frames, acoustic + zero-order intervalley
+// mechanisms of the single-layer classes).  The mechanisms are added by the example's own helper functions; the logging
+// decorators are put around them afterwards (private vector, -fno-access-control).
+template <class PT> void buildMoS2Pilotto(PT &type, double temperature) {
+  MoS2Pilotto::addValleys(type);
+  MoS2Pilotto::addAcousticScatterMechanisms(type, {0}, temperature);
+  MoS2Pilotto::addZeroOrderIntervalleyScatterMechanisms(type, {0}, temperature);
+  auto &mechs = type->scatterHandler.scatterMechanisms;
+  for (size_t i = 0; i < mechs.size(); i++) {
+    std::unique_ptr<emcScatterMechanism<T>> inner(mechs[i].release());
+    mechs[i] = std::make_unique<LoggingMechanism>(std::move(inner), (std::int64_t)i);
+  }
+}
+
 // ------------------------------------------------------------------ dumps
 static void dumpEnsemble(Blob &b, const std::string &prefix, Handler &h) {
   auto &parts = h.particles[0];
@@ -310,19 +328,28 @@ int main(int argc, char **argv) {
   RecordingRNG::sink() = &draws;
 
   const T h = a.box / a.cells;
-  DeviceType device{siMaterial(), {a.box, a.box, a.box}, {h, h, h},
-                    a.temperature};
-  device.addConstantDopingRegion({0, 0, 0}, {a.box, a.box, a.box}, a.doping);
+  const bool mos2 = a.material == "mos2";
+  // mos2: one layer of 0.65 nm (singleLayerMoS2.cpp:44-45), the placeholder material and doping of :133-135
+  const T boxZ = mos2 ? 0.65e-9 : a.box, hZ = mos2 ? 0.65e-9 : h;
+  DeviceType device{mos2 ? emcMaterial<T>{1, 1, 1, 1, 1} : siMaterial(), {a.box, a.box, boxZ}, {h, h, hZ}, a.temperature};
+  device.addConstantDopingRegion({0, 0, 0}, {a.box, a.box, boxZ}, mos2 ? 1 : a.doping);
 
   TypeMap types;
-  types[0] = std::make_unique<emcElectron<T, DeviceType>>(a.levels, a.emax, false);
-  if (a.material == "si")
-    buildSilicon(types[0], device, a.mechs);
-  else if (a.material == "mixed")
-    buildMixed(types[0], device, a.mechs);
-  else {
-    std::cerr << "unknown material\n";
-    return 2;
+  if (mos2) {
+    types[0] = std::make_unique<electron2D<T, DeviceType>>(); // 5000 levels up to 0.5 eV, 4 particles per grid point
+    a.levels = 5000;
+    a.emax = 0.5;
+    buildMoS2Pilotto(types[0], a.temperature);
+  } else {
+    types[0] = std::make_unique<emcElectron<T, DeviceType>>(a.levels, a.emax, false);
+    if (a.material == "si")
+      buildSilicon(types[0], device, a.mechs);
+    else if (a.material == "mixed")
+      buildMixed(types[0], device, a.mechs);
+    else {
+      std::cerr << "unknown material\n";
+      return 2;
+    }
   }
 
   if (a.grainRate > 0)

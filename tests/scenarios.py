@@ -77,6 +77,70 @@ def build_mixed(mechs=("acoustic", "zero", "first", "coulomb"), n_levels=250, ma
     return m
 
 
+# ---- single-layer MoS2: examples/singleLayerMoS2 with its default parameter set (parameterPilotto.hpp) ----
+MOS2 = dict(rho=3.1e-6, v_sound=6.6e3, e_qk=0.16,
+            ac_k=(23.1 + 29.1) / 2000., ac_m=(19.2 + 29.2) / 2000., ac_q=(17.9 + 23.6) / 2000.,
+            op_gamma=(48.6 + 48.9 + 50.9) / 3000., op_k=(46.4 + 42.2 + 51.9) / 3000., op_m=(48.2 + 44.3 + 50.1) / 3000.,
+            op_q=(48.0 + 44.2 + 52.2) / 3000.)
+MOS2_SUB = dict(same=[[0], [1], [2], [3], [4], [5]], next=[[1], [2], [3], [4], [5], [0]],
+                nbr=[[1, 5], [0, 2], [1, 3], [2, 4], [3, 5], [4, 0]], nbrnbr=[[2, 4], [3, 5], [4, 0], [5, 1], [0, 2], [1, 3]],
+                opposite=[[3], [4], [5], [0], [1], [2]],
+                slash=[[1, 3, 5], [0, 2, 4], [1, 3, 5], [0, 2, 4], [1, 3, 5], [0, 2, 4]],
+                # (the last row is the reference's: parameterPilotto.hpp:61-62)
+                samekind=[[0, 2, 4], [1, 3, 5], [0, 2, 4], [1, 3, 5], [0, 2, 4], [0, 2, 4]])
+
+
+def build_mos2_pilotto(temperature=300.0):
+    """parameterPilotto.hpp:64-176 on electron2D (5000 energy levels up to 0.5 eV): K valleys (isotropic), Q valleys
+    (anisotropic, six in-plane frames 60 degrees apart), acoustic + zero-order intervalley mechanisms, in the order the
+    example adds them"""
+    import math
+    P, S = MOS2, MOS2_SUB
+    m = po.Model(5000, 0.5, temperature, 1.0, 1.0)
+    m.set_electron2d(4)
+    m.add_valley(po.VALLEY_NONPARABOLIC_ISO_SL, 0.47, 6, 0.94)
+    a60 = math.pi / 3.
+    m.add_valley(po.VALLEY_NONPARABOLIC_ANISO_SL, [0.54, 1.14, 0.0], 6, 1.16, P["e_qk"],
+                 angles=[0, a60, 2 * a60, math.pi, 4 * a60, 5 * a60])
+    m.add_acoustic_sl(0, 0, 4.5, P["rho"], P["v_sound"])
+    m.add_acoustic_sl(1, 0, 2.8, P["rho"], P["v_sound"])
+
+    def pair(vi, vf, sigma, ph, sub):
+        m.add_intervalley_sl(False, vi, vf, 0, sigma, P["rho"], ph, S[sub])
+        m.add_intervalley_sl(True, vi, vf, 0, sigma, P["rho"], ph, S[sub])
+
+    pair(0, 0, 5.8e10, P["op_gamma"], "same")
+    pair(0, 0, 1.4e10, P["ac_k"], "next")
+    pair(0, 0, 2.0e10, P["op_k"], "next")
+    pair(0, 1, 0.93e9, P["ac_q"], "samekind")
+    pair(0, 1, 1.9e10, P["op_q"], "samekind")
+    pair(0, 1, 4.4e10, P["ac_m"], "slash")
+    pair(0, 1, 5.6e10, P["op_m"], "slash")
+    pair(1, 1, 7.1e10, P["op_gamma"], "same")
+    pair(1, 1, 2.1e10, P["ac_q"], "nbr")
+    pair(1, 1, 4.8e10, P["op_q"], "nbr")
+    pair(1, 1, 2.0e10, P["ac_m"], "nbrnbr")
+    pair(1, 1, 4.0e10, P["op_m"], "nbrnbr")
+    pair(1, 1, 4.8e10, P["ac_k"], "opposite")
+    pair(1, 1, 6.5e10, P["op_k"], "opposite")
+    pair(1, 0, 1.5e10, P["ac_q"], "same")
+    pair(1, 0, 2.4e10, P["op_q"], "same")
+    pair(1, 0, 4.4e10, P["ac_m"], "next")
+    pair(1, 0, 6.6e10, P["op_m"], "next")
+    m.build_tables()
+    return m
+
+
+# recorder cases of the single-layer path (oracle/_ref/ref_bulk_driver --material mos2): box = (box, box, 0.65 nm), one cell in z
+MOS2_CASES = {
+    # the example's own time step and a high field (valley transfer K -> Q sets in)
+    "mos2_pilotto": dict(material="mos2", cells=6, box=6e-8, field=4e6, fdir="1,0,0", dt=1e-16, steps=1500, seed=17),
+    # large time step (several events per step), field off the axes
+    "mos2_pilotto_bigdt": dict(material="mos2", cells=5, box=5e-8, field=1e7, fdir="0.6,-1,0", dt=2e-15, steps=120, seed=23),
+}
+MOS2_LZ = 0.65e-9
+
+
 # golden cases: name -> (ref driver args, model builder kwargs)
 GOLDEN_CASES = {
     "si_bulk": dict(

@@ -1,0 +1,72 @@
+"""CPU: the single-layer (2-D material) path -- SURVEY.md 8 f4 -- of the oracle against the UNMODIFIED reference classes as
+examples/singleLayerMoS2/singleLayerMoS2.cpp sets them up with its default parameter set (parameterPilotto.hpp): electron2D,
+emcNonParabolicIsotropSingleLayerValley (K), emcNonParabolicAnisotropSingleLayerValley (Q, six in-plane frames),
+emcAcousticSingleLayerMechanism and the 36 emcZeroOrderSingleLayerInterValley{Absorption,Emission}ScatterMechanism objects.
+Recorded by oracle/_ref/ref_bulk_driver --material mos2 (tests/golden/mos2_*.npz, oracle/make_golden.py mos2).  Valley
+constants, rate tables, initial ensemble, every scatter event, per-step observables and the final ensemble: bit for bit,
+consuming the reference's own mt19937_64 stream."""
+import numpy as np
+import pytest
+
+from helpers import field_dir_of, golden_ensemble, load_golden
+from oracle import pyoracle as po
+from scenarios import MOS2_CASES, MOS2_LZ, build_mos2_pilotto
+
+CASES = list(MOS2_CASES)
+
+
+def box_of(a):
+    return [a["box"], a["box"], MOS2_LZ]
+
+
+def test_valley_constants_and_rate_tables_equal_the_reference():
+    g = load_golden("mos2_pilotto")
+    m = build_mos2_pilotto()
+    for v, val in enumerate(m.valleys()):
+        assert np.array_equal(np.array([val.mCond, val.mDos, val.alpha, val.eBottom, *val.vogt]), g["valley_consts"][v])
+        assert val.deg == g["valley_deg"][v] == 6
+        rot = np.array([list(val.rot[s]) for s in range(val.deg)])
+        if v == 1:  # the in-plane frames of the Q valleys (the isotropic class has none)
+            assert np.array_equal(rot, g["valley_rot"][v][: val.deg])
+    assert np.array_equal(m.raw_rates()[:, ::25], g["raw_rates"])
+    sets = m.tablesets()
+    assert len(sets) == 2
+    for ts in sets:
+        key = f"_v{ts['valley']}_r{ts['region']}"
+        assert np.array_equal(ts["cum"], g["cum" + key])
+        assert ts["tau"] == g["tau" + key][0]
+        assert [x.globalId for x in ts["mech"]] == list(g["mech" + key])
+    assert len(sets[0]["mech"]) == 15 and len(sets[1]["mech"]) == 23
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_initial_ensemble_and_full_run_bit_for_bit(case):
+    g = load_golden(case)
+    a = MOS2_CASES[case]
+    m = build_mos2_pilotto()
+    st = po.mt_state(int(a["seed"]))
+    ens, used = m.generate_initial(box_of(a), [a["cells"], a["cells"], 1], 1.0, st, capacity=4096)
+    assert used == int(g["draws_init_count"][0])
+    ref0 = golden_ensemble(g, "init_")
+    assert ens.n == ref0.n == 4 * 2 * (a["cells"] + 1) ** 2
+    for f in po.Ensemble.F64 + po.Ensemble.I32:
+        assert np.array_equal(getattr(ens, f), getattr(ref0, f)), f
+    assert np.all(ens.kz == 0) and np.all(ens.valley == 0)
+    res = m.bulk_steps(ens, box_of(a), field_dir_of(a), a["field"], a["dt"], a["steps"], po.rng_mt(st), first_step=1,
+                       record=True, log_events=True)
+    assert used + res["n_draws"] == int(g["draws_count"][0])
+    ref1 = golden_ensemble(g, "final_")
+    for f in po.Ensemble.F64 + po.Ensemble.I32:
+        assert np.array_equal(getattr(ens, f), getattr(ref1, f)), f
+    ev = res["events"]
+    real = ev[ev[:, 2] >= 0]
+    assert np.array_equal(real[:, [0, 1, 3]], g["events"])
+    assert len(set(real[:, 3])) > 15 and (ens.valley == 1).sum() > 0  # many of the 38 mechanisms fired, Q valleys populated
+    obs = res["obs"]
+    cnt = obs[:, :, 2]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        avg_e = np.where(cnt > 0, obs[:, :, 0] / cnt, 0.0)
+        avg_v = np.where(cnt > 0, obs[:, :, 1] / cnt, 0.0)
+    assert np.array_equal(avg_e, g["obs"][1:, 0, :])
+    assert np.array_equal(avg_v, g["obs"][1:, 1, :])
+    assert np.array_equal(cnt / ens.n, g["obs"][1:, 2, :])

@@ -15,7 +15,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 # EMCGPU_LIB: developer override to A/B-test another build of the same library (never a CPU path)
 LIB_PATH = os.environ.get("EMCGPU_LIB") or os.path.join(_PKG, "lib", "libemcgpu.so")
 
-MAX_VALLEYS, MAX_SUB, MAX_FINAL, MAX_MECH_PER_SET, MAX_TABLESETS, NAME_LEN = 8, 8, 8, 16, 32, 48
+MAX_VALLEYS, MAX_SUB, MAX_FINAL, MAX_MECH_PER_SET, MAX_TABLESETS, NAME_LEN = 8, 8, 8, 32, 32, 48
 N_STREAMS = 8
 KX, KY, KZ, ENERGY, TAU, X, Y, Z = range(8)
 STREAM_NAMES = ("kx", "ky", "kz", "energy", "tau", "x", "y", "z")

@@ -187,7 +187,7 @@ template <bool EXACT> __device__ __forceinline__ double massFactor(const DevVall
 template <bool EXACT> __device__ __forceinline__ double normWaveVec(const DevValley &v, double e) {
   using A = Arith<EXACT>;
   const double g = gammaOf<EXACT>(v, e);
-  const double twoM = A::mul(2.0, v.mCond);
+  const double twoM = A::mul(2.0, v.mBand);
   double arg;
   if (v.kind == EMCGPU_VALLEY_NONPARABOLIC_ANISOTROP)
     arg = A::mul(A::mul(twoM, g), kQ);
@@ -208,16 +208,16 @@ __device__ __forceinline__ double driftVelocity(const DevValley &v, int s, const
     if (v.nonParabolic)
       npf = A::sqrt(A::add(1.0, A::mul(A::mul(4.0, v.alpha), gammaOf<EXACT>(v, e))));
     Vec3 vel;
-    if (v.kind >= EMCGPU_VALLEY_PARABOLIC_ANISOTROP) {
+    if (v.kind & 2) { // anisotropic classes
       const Vec3 ke = toEllipse<EXACT>(v, s, k);
-      const double den = v.nonParabolic ? A::mul(v.mCond, npf) : v.mCond;
+      const double den = v.nonParabolic ? A::mul(v.mBand, npf) : v.mBand;
       Vec3 ve;
       ve.x = A::div(A::mul(A::mul(kHbar, v.vogt[0]), ke.x), den);
       ve.y = A::div(A::mul(A::mul(kHbar, v.vogt[1]), ke.y), den);
       ve.z = A::div(A::mul(A::mul(kHbar, v.vogt[2]), ke.z), den);
       vel = toDevice<EXACT>(v, s, ve);
     } else {
-      const double f = v.nonParabolic ? A::div(kHbar, A::mul(v.mCond, npf)) : A::div(kHbar, v.mCond);
+      const double f = v.nonParabolic ? A::div(kHbar, A::mul(v.mBand, npf)) : A::div(kHbar, v.mBand);
       vel.x = A::mul(k.x, f);
       vel.y = A::mul(k.y, f);
       vel.z = A::mul(k.z, f);
@@ -239,16 +239,16 @@ __device__ __forceinline__ Vec3 velocityVector(const DevValley &v, int s, const 
   using A = Arith<true>;
   double npf = 1.0;
   if (v.nonParabolic) npf = A::sqrt(A::add(1.0, A::mul(A::mul(4.0, v.alpha), gammaOf<true>(v, e))));
-  if (v.kind >= EMCGPU_VALLEY_PARABOLIC_ANISOTROP) {
+  if (v.kind & 2) {
     const Vec3 ke = toEllipse<true>(v, s, k);
-    const double den = v.nonParabolic ? A::mul(v.mCond, npf) : v.mCond;
+    const double den = v.nonParabolic ? A::mul(v.mBand, npf) : v.mBand;
     Vec3 ve;
     ve.x = A::div(A::mul(A::mul(kHbar, v.vogt[0]), ke.x), den);
     ve.y = A::div(A::mul(A::mul(kHbar, v.vogt[1]), ke.y), den);
     ve.z = A::div(A::mul(A::mul(kHbar, v.vogt[2]), ke.z), den);
     return toDevice<true>(v, s, ve);
   }
-  const double f = v.nonParabolic ? A::div(kHbar, A::mul(v.mCond, npf)) : A::div(kHbar, v.mCond);
+  const double f = v.nonParabolic ? A::div(kHbar, A::mul(v.mBand, npf)) : A::div(kHbar, v.mBand);
   return Vec3{A::mul(k.x, f), A::mul(k.y, f), A::mul(k.z, f)};
 }
 
@@ -591,6 +591,31 @@ __device__ __forceinline__ void sampleFinalState(const DevModel &model, const De
     const double r2 = uniform01(rng.raw<RNG_MODE>());
     const double r1 = uniform01(rng.raw<RNG_MODE>());
     p.k = randomDirection<EXACT>(nrm, r1, r2);
+    break;
+  }
+  case EMCGPU_SAMPLER_SINGLE_LAYER_ELASTIC:
+  case EMCGPU_SAMPLER_SINGLE_LAYER_INTERVALLEY: {
+    // emcAcousticSingleLayerScatterMechanism.hpp:63-81; emcZeroOrderSingleLayerInterValleyScatterMechanism.hpp:116-147 /
+    // :293-324: the final sub-valley (if the mechanism lists any) is finalSub[sub][floor(u nFinal)], then the in-plane
+    // direction weighted by the Herring-Vogt factors of the (final) valley
+    if (mech.sampler == EMCGPU_SAMPLER_SINGLE_LAYER_INTERVALLEY) {
+      if (mech.nFinal > 0) {
+        const double u = uniform01(rng.raw<RNG_MODE>());
+        p.sub = mech.finalSub[p.sub][(int)floor(__dmul_rn(u, (double)mech.nFinal))];
+      }
+      p.valley = mech.finalValley;
+      p.energy = A::add(p.energy, mech.param[0]);
+    }
+    const DevValley &v = model.valleys[p.valley];
+    const double angle = A::mul(2.0 * kPi, uniform01(rng.raw<RNG_MODE>()));
+    double sa, ca;
+    sincos(angle, &sa, &ca);
+    double kx = A::div(ca, v.vogt[0]), ky = A::div(sa, v.vogt[1]);
+    const double factor = A::div(1.0, A::sqrt(A::add(A::mul(kx, kx), A::mul(ky, ky))));
+    const double nrm = normWaveVec<EXACT>(v, p.energy);
+    kx = A::mul(A::mul(kx, factor), nrm);
+    ky = A::mul(A::mul(ky, factor), nrm);
+    p.k = Vec3{kx, ky, 0.0};
     break;
   }
   case EMCGPU_SAMPLER_COULOMB: {

@@ -24,12 +24,14 @@ struct DevValley {
   int32_t rotKind; // RotKind, worst case over the sub-valleys
   int32_t nonParabolic;
   double mCond, alpha, eBottom;
+  double mBand;    // mass of the dispersion, of |k|(E) and of the velocity: mCond, except m_DOS in the anisotropic
+                   // single-layer class (emcNonParabolicAnisotropSingleLayerValley.hpp:123-148)
   double vogt[3];
-  double xMq;      // mCond*q                  (denominator of getEnergy, non-parabolic)
-  double xTwoMq;   // (2*mCond)*q              (denominator of getEnergy, parabolic)
-  double fE;       // hbar^2/(mCond q) or hbar^2/(2 mCond q)
+  double xMq;      // mBand*q                  (denominator of getEnergy, non-parabolic)
+  double xTwoMq;   // (2*mBand)*q              (denominator of getEnergy, parabolic)
+  double fE;       // hbar^2/(mBand q) or hbar^2/(2 mBand q)
   double fPos[3];  // hbar*vogt/(2 mCond)
-  double fVel[3];  // hbar*vogt/mCond
+  double fVel[3];  // hbar*vogt/mBand
   double fDk[3];   // vogt/hbar
   // signed permutations, 4 bits per component: source index | sign bit << 2
   uint16_t permToE[EMCGPU_MAX_SUBVALLEYS];

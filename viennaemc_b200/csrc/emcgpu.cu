@@ -129,7 +129,8 @@ void buildFlightConsts(const emcgpu_ctx *ctx, BulkParams &P) {
       f.KV[i] = dir[i] * (2.0 * f.KP);
       f.K4[i] = f.KV[i] / f.K2;
     }
-    f.diag = dv.rotKind != ROT_GENERAL;
+    // (the diagonal form has one mass; the anisotropic single-layer class moves with m_c and reports velocities with m_DOS)
+    f.diag = dv.rotKind != ROT_GENERAL && dv.mBand == dv.mCond;
     f.nonParabolic = dv.nonParabolic;
   }
 }
@@ -190,7 +191,7 @@ size_t deferSmem(const emcgpu_ctx *ctx, int steps, bool tablesInSmem) {
 bool splitEligible(const emcgpu_ctx *ctx) {
   const DevValley &v = ctx->hModel.valleys[0];
   return ctx->mathMode == EMCGPU_MATH_FAST && ctx->hModel.nValleys == 1 && v.rotKind != ROT_GENERAL && v.nonParabolic &&
-         v.alpha > 0.0;
+         v.alpha > 0.0 && v.mBand == v.mCond;
 }
 size_t splitEventSmem(const emcgpu_ctx *ctx, int steps, int threads) {
   const BulkSmem L(0, 1, (int)ctx->hMechs.size(), ctx->hModel.tableDoubles, false, 0);
@@ -588,7 +589,7 @@ int emcgpu_set_valleys(emcgpu_ctx *ctx, const emcgpu_valley_t *valleys, int nVal
   M.nValleys = nValleys;
   for (int i = 0; i < nValleys; i++) {
     const emcgpu_valley_t &in = valleys[i];
-    if (in.kind < 0 || in.kind > EMCGPU_VALLEY_NONPARABOLIC_ANISOTROP)
+    if (in.kind < 0 || in.kind > EMCGPU_VALLEY_NONPARABOLIC_ANISOTROP_SINGLE_LAYER || in.kind == 6)
       return fail(ctx, EMCGPU_E_UNSUPPORTED_VALLEY, "valley %d: unknown valley class %d", i, in.kind);
     if (in.degeneracy < 1 || in.degeneracy > EMCGPU_MAX_SUBVALLEYS)
       return fail(ctx, EMCGPU_E_CAPACITY, "valley %d: degeneracy %d outside [1,%d]", i, in.degeneracy,
@@ -603,14 +604,20 @@ int emcgpu_set_valleys(emcgpu_ctx *ctx, const emcgpu_valley_t *valleys, int nVal
     v.mCond = in.effMassCond;
     v.alpha = v.nonParabolic ? in.alpha : 0.0;
     v.eBottom = in.bottomEnergy;
-    const bool aniso = in.kind >= EMCGPU_VALLEY_PARABOLIC_ANISOTROP;
+    const bool aniso = (in.kind & 2) != 0, singleLayer = (in.kind & 4) != 0;
     for (int d = 0; d < 3; d++) v.vogt[d] = aniso ? in.vogt[d] : 1.0;
-    v.xMq = v.mCond * kQ;
-    v.xTwoMq = 2 * v.mCond * kQ;
-    v.fE = v.nonParabolic ? kHbar * kHbar / (v.mCond * kQ) : kHbar * kHbar / (2 * v.mCond * kQ);
+    if (singleLayer) v.vogt[2] = 0.0; // no motion out of the plane
+    v.mBand = v.mCond;
+    if (in.kind == EMCGPU_VALLEY_NONPARABOLIC_ANISOTROP_SINGLE_LAYER) {
+      if (!(in.effMassDOS > 0)) return fail(ctx, EMCGPU_E_INVALID, "valley %d: the single-layer class needs effMassDOS > 0", i);
+      v.mBand = in.effMassDOS;
+    }
+    v.xMq = v.mBand * kQ;
+    v.xTwoMq = 2 * v.mBand * kQ;
+    v.fE = v.nonParabolic ? kHbar * kHbar / (v.mBand * kQ) : kHbar * kHbar / (2 * v.mBand * kQ);
     for (int d = 0; d < 3; d++) {
       v.fPos[d] = kHbar * v.vogt[d] / (2 * v.mCond);
-      v.fVel[d] = kHbar * v.vogt[d] / v.mCond;
+      v.fVel[d] = kHbar * v.vogt[d] / v.mBand;
       v.fDk[d] = v.vogt[d] / kHbar;
     }
     int worst = ROT_IDENTITY;
@@ -677,7 +684,7 @@ int emcgpu_set_tables(emcgpu_ctx *ctx, const emcgpu_tableset_t *sets, int nSets,
       char name[EMCGPU_NAME_LEN + 1];
       memcpy(name, mi.name, EMCGPU_NAME_LEN);
       name[EMCGPU_NAME_LEN] = 0;
-      if (mi.sampler <= EMCGPU_SAMPLER_NONE || mi.sampler > EMCGPU_SAMPLER_SCREENED_FROEHLICH)
+      if (mi.sampler <= EMCGPU_SAMPLER_NONE || mi.sampler > EMCGPU_SAMPLER_SINGLE_LAYER_INTERVALLEY)
         return fail(ctx, EMCGPU_E_UNSUPPORTED_MECHANISM,
                     "scatter mechanism '%s' (valley %d, region %d) has no device sampler; it cannot run on "
                     "the GPU path and there is no CPU fallback",
@@ -700,12 +707,16 @@ int emcgpu_set_tables(emcgpu_ctx *ctx, const emcgpu_tableset_t *sets, int nSets,
         if ((d.flags & 1) && (d.bath < 0 || !ctx->bathHasCum))
           return fail(ctx, EMCGPU_E_INVALID, "mechanism '%s' samples |q| from a phonon bath whose prefix sums were not given", name);
       }
-      if (mi.sampler == EMCGPU_SAMPLER_INTERVALLEY) {
+      if (mi.sampler == EMCGPU_SAMPLER_INTERVALLEY || mi.sampler == EMCGPU_SAMPLER_SINGLE_LAYER_INTERVALLEY) {
         if (mi.finalValley < 0 || mi.finalValley >= M.nValleys)
           return fail(ctx, EMCGPU_E_INVALID, "mechanism '%s': final valley %d does not exist", name, mi.finalValley);
-        if (mi.nFinal < 1 || mi.nFinal > EMCGPU_MAX_FINAL)
-          return fail(ctx, EMCGPU_E_CAPACITY, "mechanism '%s': %d final sub-valleys outside [1,%d]", name,
-                      mi.nFinal, EMCGPU_MAX_FINAL);
+        // the single-layer classes have a constructor without a sub-valley map: the sub-valley index is kept
+        const int minFinal = mi.sampler == EMCGPU_SAMPLER_SINGLE_LAYER_INTERVALLEY ? 0 : 1;
+        if (mi.nFinal < minFinal || mi.nFinal > EMCGPU_MAX_FINAL)
+          return fail(ctx, EMCGPU_E_CAPACITY, "mechanism '%s': %d final sub-valleys outside [%d,%d]", name,
+                      mi.nFinal, minFinal, EMCGPU_MAX_FINAL);
+        if (mi.nFinal == 0 && M.valleys[in.valley].deg > M.valleys[mi.finalValley].deg)
+          return fail(ctx, EMCGPU_E_INVALID, "mechanism '%s' keeps the sub-valley index but the final valley has fewer", name);
         const int degF = M.valleys[mi.finalValley].deg;
         for (int s = 0; s < M.valleys[in.valley].deg; s++)
           for (int f = 0; f < mi.nFinal; f++)
