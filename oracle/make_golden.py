@@ -18,7 +18,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from scenarios import DEVICE_CASES, GA2O3_CASES, GOLDEN_CASES, MHP_CASES, MOS2_CASES, ga2o3_args, mhp_args  # noqa: E402
+from scenarios import DEVICE_CASES, DEVICE_LONG_CASES, GA2O3_CASES, GOLDEN_CASES, MHP_CASES, MOS2_CASES, ga2o3_args, mhp_args  # noqa: E402
 
 DT = {"d": np.float64, "q": np.int64, "Q": np.uint64}
 
@@ -115,6 +115,30 @@ def main_device():
         print(name, "->", dst, os.path.getsize(dst) // 1024, "KiB; draws", len(blob["draws"]))
 
 
+def main_device_long():
+    """long chained device runs: snapshots only, the raw draws as count + digest (they are the mt19937_64 stream of the seed)"""
+    import hashlib
+    subprocess.check_call(["make", "-C", HERE, "_ref/ref_device_driver"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    drv = os.path.join(HERE, "_ref", "ref_device_driver")
+    for name, args in DEVICE_LONG_CASES.items():
+        with tempfile.TemporaryDirectory() as tmp:
+            out = os.path.join(tmp, "ref.bin")
+            cmd = [drv, "--out", out]
+            for k, v in args.items():
+                cmd += ["--" + k, str(v)]
+            subprocess.check_call(cmd, cwd=tmp, stdout=subprocess.DEVNULL)
+            blob = read_blob(out)
+        n_draws = len(blob["draws"])
+        blob["draws_count"] = np.array([n_draws], dtype=np.int64)
+        blob["draws_sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(blob["draws"]).tobytes()).digest(), dtype=np.uint8)
+        del blob["draws"]
+        for k in [k for k in blob if k.endswith("_pre_k") or "_pre_" in k]:  # pre = post of the step before, relabelled
+            del blob[k]
+        dst = os.path.join(ROOT, "tests", "golden", name + ".npz")
+        np.savez_compressed(dst, **blob)
+        print(name, "->", dst, os.path.getsize(dst) // 1024, "KiB; draws", n_draws, "final size", int(blob["size_all"][-1]))
+
+
 def main_ga2o3():
     subprocess.check_call(["make", "-C", HERE, "_ref/ref_ga2o3_driver"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     drv = os.path.join(HERE, "_ref", "ref_ga2o3_driver")
@@ -162,6 +186,8 @@ if __name__ == "__main__":
         main()
     if which in ("all", "device"):
         main_device()
+    if which in ("all", "device_long"):
+        main_device_long()
     if which in ("all", "ga2o3"):
         main_ga2o3()
     if which in ("all", "mhp"):

@@ -123,6 +123,8 @@ struct Options {
          dt = 1e-15, acc = 1e-4, omega = 1.8, emax = 4.0, gateVoltage = 0.5, surfYminConst = -1, surfYmaxMom = -1, grainRate = 0,
          grainProb = 0.5;
   int steps = 10, levels = 1000, gate = 0;
+  int snapEvery = 1; // > 1: the grids and ensembles only of every snapEvery-th step and of the last one (long chained runs);
+                     // the per-contact counters and the draw marks of EVERY step are always kept
   unsigned long seed = 5;
   std::string out = "device.blob", scheme = "ngp", electron = "emc";
 };
@@ -287,38 +289,58 @@ template <class PMScheme, class Electron> int run(const Options &o) {
   // ---- performEMCStep, non-FMM branch (emcSimulation.hpp:177-192) -----------------------------
   std::vector<std::uint64_t> drawMarks; // per step: before drift, after drift, after contacts
   bool resetBC = true;
+  std::vector<std::int64_t> removedAll, injectedAll, sizeAll; // every step: per contact, ensemble size after the contacts
   for (int s = 0; s < steps; s++) {
     const std::string p = "s" + std::to_string(s) + "_";
+    const bool snap = o.snapEvery <= 1 || s % o.snapEvery == 0 || s == steps - 1;
     solver.calcNonEquilibriumPotential(results.currPot, device, results.currConc[0], resetBC);
     resetBC = false; // emcSimulation: true only for step 0 (:107, :118-120)
     pmScheme.calcEField(results.eField, results.currPot, device);
-    blob.grid(p + "pot", results.currPot);
-    blob.grid(p + "ex", results.eField[0]);
-    blob.grid(p + "ey", results.eField[1]);
-    if (Dim > 2)
-      blob.grid(p + "ez", results.eField[Dim - 1]);
+    if (snap) {
+      blob.grid(p + "pot", results.currPot);
+      blob.grid(p + "ex", results.eField[0]);
+      blob.grid(p + "ey", results.eField[1]);
+      if (Dim > 2)
+        blob.grid(p + "ez", results.eField[Dim - 1]);
+    }
     // label the particles through the (dynamically inert) grain clock so that removals can be traced -- unless a grain
     // mechanism is set: then the clock is live and is recorded as it is
     if (!(o.grainRate > 0))
       for (size_t i = 0; i < handler.particles[0].size(); i++)
         handler.particles[0][i].grainTau = 1000. + i;
-    dumpEnsemble(blob, p + "pre_", handler);
+    if (snap)
+      dumpEnsemble(blob, p + "pre_", handler);
     drawMarks.push_back(draws.size());
     auto nrRem = handler.driftScatterParticles(dt, results.eField);
     drawMarks.push_back(draws.size());
-    dumpEnsemble(blob, p + "drift_", handler);
+    if (snap)
+      dumpEnsemble(blob, p + "drift_", handler);
     std::vector<std::int64_t> rem(nrRem[0].begin(), nrRem[0].end());
-    blob.i64(p + "removed_per_contact", rem);
+    if (snap)
+      blob.i64(p + "removed_per_contact", rem);
+    removedAll.insert(removedAll.end(), rem.begin(), rem.end());
     auto nrInj = handler.handleOhmicContacts();
     drawMarks.push_back(draws.size());
-    dumpEnsemble(blob, p + "post_", handler);
+    if (snap)
+      dumpEnsemble(blob, p + "post_", handler);
     std::vector<std::int64_t> inj(nrInj[0].begin(), nrInj[0].end());
-    blob.i64(p + "net_injected_per_contact", inj);
+    if (snap)
+      blob.i64(p + "net_injected_per_contact", inj);
+    injectedAll.insert(injectedAll.end(), inj.begin(), inj.end());
+    sizeAll.push_back((std::int64_t)handler.getNrParticles(0));
     results.nrPart[0].fill(0);
     handler.assignParticlesToMesh(0, results.nrPart[0]);
     results.updateCurrentParticleConcentrations(device);
-    blob.grid(p + "count", results.nrPart[0]);
-    blob.grid(p + "conc", results.currConc[0]);
+    if (snap) {
+      blob.grid(p + "count", results.nrPart[0]);
+      blob.grid(p + "conc", results.currConc[0]);
+    }
+  }
+  if (o.snapEvery > 1) {
+    const std::uint64_t nC = removedAll.size() / steps;
+    blob.i64("removed_all", removedAll, {(std::uint64_t)steps, nC});
+    blob.i64("net_injected_all", injectedAll, {(std::uint64_t)steps, nC});
+    blob.i64("size_all", sizeAll, {(std::uint64_t)steps});
   }
   blob.u64("draw_marks", drawMarks);
   blob.u64("draws", draws);
@@ -348,6 +370,7 @@ int main(int argc, char **argv) {
     else if (k == "--acc") o.acc = std::stod(v);
     else if (k == "--omega") o.omega = std::stod(v);
     else if (k == "--steps") o.steps = std::stoi(v);
+    else if (k == "--snap-every") o.snapEvery = std::stoi(v);
     else if (k == "--levels") o.levels = std::stoi(v);
     else if (k == "--emax") o.emax = std::stod(v);
     else if (k == "--gate") o.gate = std::stoi(v); // 1: gate contact on the middle third of YMIN

@@ -28,9 +28,10 @@ def load_golden(case):
             return list(self.keys())
 
     d = _Golden((k, g[k]) for k in g.files)
-    from scenarios import MHP_CASES, MOS2_CASES
+    from scenarios import DEVICE_LONG_CASES, MHP_CASES, MOS2_CASES
     seed = (GOLDEN_CASES[case]["args"]["seed"] if case in GOLDEN_CASES else
-            MOS2_CASES[case]["seed"] if case in MOS2_CASES else MHP_CASES[case]["seed"])
+            MOS2_CASES[case]["seed"] if case in MOS2_CASES else
+            DEVICE_LONG_CASES[case]["seed"] if case in DEVICE_LONG_CASES else MHP_CASES[case]["seed"])
     draws = po.mt_fill(int(seed), int(d["draws_count"][0]))
     assert hashlib.sha256(draws.tobytes()).digest() == d["draws_sha256"].tobytes(), "regenerated draws differ from the recording"
     d["draws"] = draws

@@ -211,9 +211,17 @@ DEVICE_CASES["device_3d_cic"] = {"lx": 1.6e-7, "ly": 8e-8, "lz": 6e-8, "hx": 1e-
 PM_SCHEMES = {"ngp": po.PM_NGP, "cic": po.PM_CIC, "nec": po.PM_NEC, "vwd": po.PM_NEC_VWD}
 
 
+# long CHAINED device run ("a device replay >= 200 steps"): the bar of device_bar, twice as long, 250 time steps;
+# the recorder keeps the grids and ensembles of every 25th step and of the last one, the per-contact counters of every step
+DEVICE_LONG_CASES = {
+    "device_bar_long": {"lx": 4e-7, "ly": 1e-7, "hx": 1e-8, "hy": 2.5e-8, "doping": 1e22, "doping2": 0, "voltage": 0.2,
+                        "dt": 1e-15, "steps": 250, "levels": 1000, "emax": 4.0, "gate": 0, "seed": 77, "snap-every": 25},
+}
+
+
 def build_device(case: str):
     """oracle-side model + device of a DEVICE_CASES entry (mirrors oracle/ref_device_driver.cpp)"""
-    a = DEVICE_CASES[case]
+    a = DEVICE_CASES[case] if case in DEVICE_CASES else DEVICE_LONG_CASES[case]
     regions = (0, 1) if a["doping2"] else (0,)
     if "lz" in a:  # 3-D box
         size, h = [a["lx"], a["ly"], a["lz"]], [a["hx"], a["hy"], a["hz"]]

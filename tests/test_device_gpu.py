@@ -321,3 +321,74 @@ def test_large_grid_poisson_and_empty_ensemble(gpu_ctx_factory):
     assert counters[0, 1, :].sum() == int(np.ceil(expected[expected > 0]).sum()) and counters[:, 0, :].sum() >= 0
     assert ctx2.size == counters[:, 1, :].sum() - counters[:, 0, :].sum()
     assert ctx2.device_get_grid(capi.GRID_COUNT).sum() == ctx2.size
+
+
+@pytest.mark.parametrize("math_mode", [capi.MATH_EXACT, capi.MATH_FAST], ids=["exact", "fast"])
+def test_long_chained_run_replays_the_reference(gpu_ctx_factory, math_mode):
+    """250 CHAINED time steps on the device -- Poisson, field, drift / scatter, contacts, assignment, concentration, every step
+    from the state the device's own previous step left, nothing re-uploaded -- fed the reference's draws (per-particle replay
+    streams for the drift / scatter phase, the contact phase's draws in order).  Every step: removed and injected particles per
+    contact and the ensemble size exact.  Every 25th step and the last: particle state within 1e-12 of the REFERENCE's
+    ensemble (indices exact), potential within 1e-12 of the bias, counts exact."""
+    case = "device_bar_long"
+    from scenarios import DEVICE_LONG_CASES
+    g = load_golden(case)
+    a = DEVICE_LONG_CASES[case]
+    m, dev = build_device(case)
+    marks = g["draw_marks"].reshape(-1, 3)
+    expected = dev.expected_at_contact()
+    ctx = gpu_ctx_factory()
+    upload_model(ctx, m)
+    configure(ctx, dev, expected=g["expected_at_contact"].ravel(), math_mode=math_mode)
+    ctx.device_reserve(2048)
+    ctx.rng_philox(1)  # (not consumed: every draw of the run is replayed)
+    ctx.device_set_grid(capi.GRID_POTENTIAL, g["pot_eq"])
+    ctx.device_set_grid(capi.GRID_CONCENTRATION, g["conc_eq"])
+    upload_ensemble(ctx, ens_from(g, "init_"))
+    # the oracle runs the same chain bit for bit with the reference (tests/test_oracle_device.py): it tells which particle
+    # consumed which draw of the drift / scatter phase
+    mt = po.mt_state(a["seed"])
+    for _ in range(int(g["draws_init_count"][0])):
+        po.lib().orc_mt_next(mt)
+    shadow = po.Ensemble(4096)
+    ens0 = ens_from(g, "init_")
+    for f in po.Ensemble.F64 + po.Ensemble.I32:
+        getattr(shadow, f)[: ens0.n] = getattr(ens0, f)
+    shadow.n = ens0.n
+    pot, conc = g["pot_eq"].ravel().copy(), g["conc_eq"].ravel().copy()
+    n_snaps = 0
+    for s in range(a["steps"]):
+        p = f"s{s}_"
+        snap = (p + "pot") in g
+        # ---- oracle shadow: fields and the attribution of the draws
+        dev.sor(pot, conc, 1e-4, 1.8, s == 0)
+        e = dev.efield(pot)
+        res = dev.step(m, shadow, e, a["dt"], po.rng_mt(mt), step_index=s + 1, record=True)
+        draws = g["draws"][int(marks[s, 0]):int(marks[s, 1])]
+        assert len(res["rec_pid"]) == len(draws)
+        sd, offsets = po.streams_from_record(draws, res["rec_pid"], shadow.n)
+        dev.compact(shadow, res["removed"])
+        dev.contacts(m, shadow, expected, mt)
+        conc = dev.concentration(dev.assign(shadow))
+        # ---- device: its own chain
+        ctx.device_poisson(False, 1e-4, 1.8, s == 0)
+        ctx.device_efield()
+        if snap:
+            assert_grid_close(ctx.device_get_grid(capi.GRID_POTENTIAL), g[p + "pot"], f"step {s}: potential", 1e-12, scale=a["voltage"])
+        ctx.rng_replay(sd, offsets)
+        ctx.set_step_index(s + 1)
+        removed = ctx.device_step(a["dt"])
+        assert np.array_equal(removed, g["removed_all"][s]), f"step {s}: removed per contact"
+        if snap:
+            assert_ensemble_close(download_ensemble(ctx), ens_from(g, p + "drift_"), dev, f"step {s}: after drift")
+        net = ctx.device_contacts(replay_draws=g["draws"][int(marks[s, 1]):int(marks[s, 2])])
+        assert np.array_equal(net, g["net_injected_all"][s]), f"step {s}: contacts"
+        ctx.device_assign()
+        ctx.device_concentration()
+        if snap:
+            got = download_ensemble(ctx)
+            assert got.n == int(g["size_all"][s])
+            assert_ensemble_close(got, ens_from(g, p + "post_"), dev, f"step {s}: after contacts")
+            assert_counts(dev, ctx.device_get_grid(capi.GRID_COUNT), g[p + "count"], f"step {s}: counts")
+            n_snaps += 1
+    assert n_snaps == 11

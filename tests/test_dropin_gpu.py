@@ -358,3 +358,86 @@ def test_grain_scattering_through_the_drop_in_handler_matches_the_cpu_restatemen
     assert abs(v_gpu.mean() - v_cpu.mean()) <= 3 * np.hypot(block_sigma(v_gpu), block_sigma(v_cpu)) + 0.01 * abs(v_cpu.mean())
     assert abs(e_gpu.mean() - e_cpu.mean()) <= 3 * np.hypot(block_sigma(e_gpu), block_sigma(e_cpu)) + 0.005 * e_cpu.mean()
     assert abs(v_gpu.mean()) < 0.8 * abs(v_plain.mean())
+
+
+# ---- single-layer MoS2: the UNMODIFIED examples/singleLayerMoS2/singleLayerMoS2.cpp ----------------------------
+MOS2_FIELDS = (200000, 4000000)            # the two members of the example's field list the reference sample covers
+MOS2_ALL_FIELDS = (100000, 200000, 500000, 1000000, 2000000, 4000000, 6000000, 8000000, 10000000, 15000000, 20000000,
+                   25000000, 30000000, 35000000, 40000000)
+
+
+def _mos2_summary(workdir, field, n=20808):
+    tag = f"E{field}T300N{n}.txt"
+    e = np.loadtxt(os.path.join(workdir, "singleLayerMoS2AvgEnergy" + tag))
+    v = np.loadtxt(os.path.join(workdir, "singleLayerMoS2AvgDriftVelocity" + tag))
+    o = np.loadtxt(os.path.join(workdir, "singleLayerMoS2valleyOccupation" + tag))
+    assert e.shape == v.shape == o.shape == (20001, 3)  # time, K valleys, Q valleys
+    e, v, o = e[-10000:, 1:], v[-10000:, 1:], o[-10000:, 1:]
+    return dict(energy=e.mean(0), drift=v.mean(0), occupation=o.mean(0), energy_all=(e * o).sum(1).mean(), drift_all=(v * o).sum(1).mean())
+
+
+def test_unmodified_single_layer_mos2_main_within_3_sigma_of_the_reference(tmp_path):
+    """electron2D + the Pilotto parameter set (single-layer valley classes, 2 acoustic + 36 zero-order intervalley mechanisms)
+    through the example's own main(): all 15 fields of its sweep; the two fields the reference sample holds are compared --
+    mean over three seeds, two-sample 3 sigma: ensemble averages, per-valley averages and the K -> Q valley transfer."""
+    if not os.path.exists(os.path.join(BIN, "reference_singleLayerMoS2_gpu")):
+        pytest.skip("reference_singleLayerMoS2_gpu is built only where the reference tree is mounted")
+    st = _load("ref_mos2_stats.json")
+    assert st["n_runs"] >= 30
+    runs = []
+    for seed in (1, 2, 3):
+        work = tmp_path / f"seed{seed}"
+        work.mkdir()
+        out = _run("reference_singleLayerMoS2_gpu", [], work, env={"EMCGPU_SEED": str(seed)})
+        assert "idxValley 0 idxRegion 0: tau = 3.38243e-15 s" in out and "idxValley 1 idxRegion 0: tau = 2.4509e-15 s" in out
+        assert out.count("20808 Electrons") == 15 and "Used Parameter from Paper = Pilotto" in out
+        for f in MOS2_ALL_FIELDS:
+            assert os.path.exists(work / f"singleLayerMoS2AvgEnergyE{f}T300N20808.txt"), f
+        runs.append({f: _mos2_summary(str(work), f) for f in MOS2_FIELDS})
+    for f in MOS2_FIELDS:
+        ref = [r[str(f)] for r in st["runs"]]
+        for key in ("energy_all", "drift_all"):
+            assert_scalar([r[f][key] for r in runs], [x[key] for x in ref], f"MoS2 at {f} V/m: {key}")
+        assert_scalar([r[f]["energy"][0] for r in runs], [x["energy"][0] for x in ref], f"MoS2 at {f} V/m: <E> of the K valleys")
+        assert_scalar([r[f]["drift"][0] for r in runs], [x["drift"][0] for x in ref], f"MoS2 at {f} V/m: <v> of the K valleys")
+        assert_scalar([r[f]["occupation"][1] for r in runs], [x["occupation"][1] for x in ref], f"MoS2 at {f} V/m: share of the Q valleys")
+    # physics of the sweep: the drift velocity grows with the field, the Q valleys fill up (valley transfer)
+    assert abs(np.mean([r[4000000]["drift_all"] for r in runs])) > 5 * abs(np.mean([r[200000]["drift_all"] for r in runs]))
+    assert np.mean([r[4000000]["occupation"][1] for r in runs]) > 5 * np.mean([r[200000]["occupation"][1] for r in runs])
+
+
+def test_single_layer_mechanisms_without_a_device_sampler_are_rejected_by_name(tmp_path):
+    """the Kaasbjerg parameter set of the same example uses mechanisms that exist here by name only (first-order intervalley,
+    Froehlich, piezoelectric single-layer classes): adding one stops the program with its name -- nothing runs on the CPU"""
+    src = tmp_path / "kaasbjerg.cpp"
+    src.write_text('''#include <emcDevice.hpp>
+#include <basicBulkParticleHandler.hpp>
+#include <ParticleType/emcElectron.hpp>
+#include <ScatterMechanisms/emcAcousticSingleLayerScatterMechanism.hpp>
+#include <ScatterMechanisms/emcFirstOrderSingleLayerIntervalleyScatterMechanism.hpp>
+#include <ScatterMechanisms/emcFroehlichInteractionSingleLayer.hpp>
+#include <ValleyTypes/emcParabolicIsotropSingleLayerValley.hpp>
+#include <cstring>
+using T = double;
+using Dev = emcDevice<T, 3>;
+int main(int argc, char **argv) {
+  std::unique_ptr<emcParticleType<T, Dev>> type = std::make_unique<emcElectron<T, Dev>>(1000, 0.5, false);
+  type->addValley(std::make_unique<emcParabolicIsotropSingleLayerValley<T>>(0.48, type->getMass(), 1));
+  type->addScatterMechanism({0}, std::make_unique<emcAcousticSingleLayerMechanism<T>>(0, 2.4, 3.1e-6, 6.7e3, 300., "LA"));
+  if (!std::strcmp(argv[1], "first"))
+    type->addScatterMechanism({0}, std::make_unique<emcFirstOrderSingleLayerInterValleyEmissionScatterMechanism<T>>(0, 5.9, 3.1e-6, 300., 0.03, "TA"));
+  else
+    type->addScatterMechanism({0}, std::make_unique<emcFroehlichInteractionAbsorptionSL<T>>(0, 0.048, 0.098, 5.41e-10, 300., "", 0.));
+  return 0;
+}
+''')
+    exe = tmp_path / "kaasbjerg"
+    root = os.path.dirname(os.path.dirname(BIN))
+    inc = os.path.join(root, "viennaemc_b200", "host", "include")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", inc, "-I", os.path.join(root, "include"), "-o", str(exe), str(src), "-L",
+                           os.path.join(root, "viennaemc_b200", "lib"), "-lemcgpu", "-lemcnccl",
+                           "-Wl,-rpath," + os.path.join(root, "viennaemc_b200", "lib")])
+    for which, name in (("first", "FirstInterValleyEmissionSL"), ("froehlich", "froehlichAbsorptionSL")):
+        r = subprocess.run([str(exe), which], capture_output=True, text=True, cwd=tmp_path)
+        assert r.returncode != 0
+        assert f"Scatter mechanism '{name}' has no device final-state sampler" in r.stdout + r.stderr and "no CPU fallback" in r.stdout + r.stderr

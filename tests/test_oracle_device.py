@@ -7,7 +7,7 @@ import pytest
 
 from helpers import load_golden
 from oracle import pyoracle as po
-from scenarios import DEVICE_CASES, build_device
+from scenarios import DEVICE_CASES, DEVICE_LONG_CASES, build_device
 
 CASES = list(DEVICE_CASES)
 
@@ -119,5 +119,56 @@ def test_emc_steps_bit_for_bit(case):
     nxt = po.lib().orc_mt_next(mt)
     ref_mt = po.mt_state(a["seed"])
     for _ in range(len(draws)):
+        po.lib().orc_mt_next(ref_mt)
+    assert nxt == po.lib().orc_mt_next(ref_mt)
+
+
+@pytest.mark.parametrize("case", list(DEVICE_LONG_CASES))
+def test_long_chained_run_bit_for_bit(case):
+    """250 chained time steps (Poisson -> field -> drift / scatter -> contacts -> assignment -> concentration, each step from
+    the state the step before left): the per-contact counters and the ensemble size of EVERY step, and the grids and ensembles
+    of every 25th step and of the last one, consuming the reference's own draw sequence."""
+    g = load_golden(case)
+    a = DEVICE_LONG_CASES[case]
+    m, dev = build_device(case)
+    expected = dev.expected_at_contact()
+    pot = g["pot_eq"].ravel().copy()
+    conc = g["conc_eq"].ravel().copy()
+    mt = po.mt_state(a["seed"])
+    for _ in range(int(g["draws_init_count"][0])):
+        po.lib().orc_mt_next(mt)
+    ens = ens_from(g, "init_")
+    big = po.Ensemble(ens.n + 4000)
+    for f in po.Ensemble.F64 + po.Ensemble.I32:
+        getattr(big, f)[: ens.n] = getattr(ens, f)
+    big.n = ens.n
+    ens = big
+    n_snaps = 0
+    for s in range(a["steps"]):
+        p = f"s{s}_"
+        snap = (p + "pot") in g
+        dev.sor(pot, conc, 1e-4, 1.8, s == 0)
+        e = dev.efield(pot)
+        if snap:
+            assert np.array_equal(pot, g[p + "pot"].ravel()), f"step {s}: potential"
+            assert np.array_equal(e[0], g[p + "ex"].ravel()) and np.array_equal(e[1], g[p + "ey"].ravel())
+        res = dev.step(m, ens, e, a["dt"], po.rng_mt(mt), step_index=s + 1)
+        assert np.array_equal(res["removed_per_contact"], g["removed_all"][s]), f"step {s}: removed"
+        dev.compact(ens, res["removed"])
+        if snap:
+            assert_same_ensemble(ens, ens_from(g, p + "drift_"), f"step {s}: after drift")
+        net = dev.contacts(m, ens, expected, mt)
+        assert np.array_equal(net, g["net_injected_all"][s]), f"step {s}: contacts"
+        assert ens.n == int(g["size_all"][s])
+        count = dev.assign(ens)
+        conc = dev.concentration(count)
+        if snap:
+            assert_same_ensemble(ens, ens_from(g, p + "post_"), f"step {s}: after contacts")
+            assert np.array_equal(count, g[p + "count"].ravel()) and np.array_equal(conc, g[p + "conc"].ravel())
+            n_snaps += 1
+    assert n_snaps == 11 and g["removed_all"].sum() > 10 and np.abs(g["net_injected_all"]).sum() > 10
+    nxt = po.lib().orc_mt_next(mt)
+    ref_mt = po.mt_state(a["seed"])
+    for _ in range(int(g["draws_count"][0])):
         po.lib().orc_mt_next(ref_mt)
     assert nxt == po.lib().orc_mt_next(ref_mt)

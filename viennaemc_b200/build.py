@@ -123,6 +123,16 @@ def build_examples(force: bool = False) -> dict:
                                ref_main, *link])
     if os.path.exists(target):
         out["reference_hotCarrierMHP_gpu"] = target
+    # the UNMODIFIED single-layer MoS2 example (its own electron2D.hpp and parameter*.hpp included; the handler swapped like
+    # above).  Its default parameter set (Pilotto: single-layer valleys, acoustic + zero-order intervalley mechanisms) runs
+    # on the GPU; the Kaasbjerg set names mechanisms without a device sampler and is rejected with their names.
+    ref_main = os.path.join(REFERENCE, "examples", "singleLayerMoS2", "singleLayerMoS2.cpp")
+    target = os.path.join(bindir, "reference_singleLayerMoS2_gpu")
+    if os.path.exists(ref_main) and (force or _newer(target, deps)):
+        subprocess.check_call([*common, "-include", os.path.join(HOST_INC, "basicBulkParticleHandler.hpp"), "-o", target,
+                               ref_main, *link])
+    if os.path.exists(target):
+        out["reference_singleLayerMoS2_gpu"] = target
     # the UNMODIFIED device-run examples of the reference (emcSimulation + emcBasicParticleHandler + emcSORSolver +
     # PM scheme) compiled against OUR headers: every object they create is the GPU-backed drop-in
     for name, rel in (("reference_resistor2D_gpu", ("examples", "resistor2D", "resistor2D.cpp")),):
