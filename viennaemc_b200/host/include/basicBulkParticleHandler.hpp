@@ -26,6 +26,15 @@
 //     rewinds to the state before the launch and repeats exactly the steps served so far: the random numbers are keyed
 //     by particle id and step, so this reproduces them bit for bit.  Types with phonon baths (per-step host feedback)
 //     keep one step per call; the grain clocks of a grain mechanism ride along (the look-ahead copy has its own);
+//   * SEVERAL GPUs: started once per GPU with EMCGPU_SHARD=1 and the launcher variables RANK, WORLD_SIZE,
+//     LOCAL_RANK plus EMCNCCL_ID_FILE (like the device-run handler, ParticleHandler/emcBasicParticleHandler.hpp), every
+//     process creates the same initial ensemble (the seed of rank 0) and keeps a contiguous block of it on its GPU.  The
+//     Philox streams are keyed by the particle's position in the WHOLE ensemble, so every particle moves exactly as in a
+//     one-GPU run of the same seed.  What the driver reads -- the per-valley sums behind getAvg* / occupation, the event
+//     counters of the phonon baths -- is summed over the ranks (ncclAllReduce through libemcnccl: once per look-ahead
+//     window, or once per step with phonon baths), so baths, screening and rebuilt rate tables are identical on all ranks.
+//     getNrParticles() is the size of the whole ensemble; print() / printVelocities() write the block of this rank
+//     ("<...>.rank<r>.txt"); start every rank in a directory of its own if the driver writes files;
 //   * random numbers in the step are counter-based Philox streams keyed by particle
 //     id and step (not one mt19937_64 per OpenMP thread), seeded from the handler seed;
 //   * nothing is moved on the CPU: without a CUDA device, or with a mechanism /
@@ -46,6 +55,7 @@
 #include <detail/emcBulkEnsembleBuilder.hpp>
 #include <emcGpuBinding.hpp>
 #include <emcPhononBath.hpp>
+#include <emcnccl.h>
 #include <emcGrid.hpp>
 #include <emcParticleInitialization.hpp>
 #include <emcUtil.hpp>
@@ -78,6 +88,8 @@ private:
     int recordVel = 0;
     std::vector<double> velAhead;
     SizeType velSteps = 0; // steps of the current window velAhead holds
+    // several GPUs: this process holds the particles [shardFirst, shardFirst + nrLocal) of the ensemble (one GPU: all)
+    SizeType shardFirst = 0, nrLocal = 0;
   };
 
   DeviceType &device;
@@ -90,10 +102,18 @@ private:
   emcRNG hostRng; // particle creation only (the reference's rngs[0])
   unsigned long stepSeed = 0;
   int mathMode = EMCGPU_MATH_FAST;
+  int shardRank = 0, shardWorld = 1;
+  emcnccl_comm *comm = nullptr;
 
-  static int cudaDeviceOrdinal() {
-    const char *e = std::getenv("EMCGPU_DEVICE");
-    return e ? std::atoi(e) : 0;
+  static int envInt(const char *name, int fallback) {
+    const char *e = std::getenv(name);
+    return (e && *e) ? std::atoi(e) : fallback;
+  }
+  int cudaDeviceOrdinal() const { return envInt("EMCGPU_DEVICE", shardWorld > 1 ? envInt("LOCAL_RANK", shardRank) : 0); }
+  // in-place sum over the ranks of a small host array (no-op on one GPU)
+  void sumOverRanks(std::vector<double> &v) const {
+    if (comm && !v.empty() && emcnccl_allreduce_sum_host_f64(comm, v.data(), static_cast<int64_t>(v.size())) != 0)
+      emcMessage::getInstance().addError(std::string("sharded run: all-reduce failed: ") + emcnccl_last_error()).print();
   }
   static SizeType defaultLookahead() {
     const char *e = std::getenv("EMCGPU_LOOKAHEAD");
@@ -107,8 +127,9 @@ private:
   void materialize(SizeType idxType) const {
     auto &st = state.at(idxType);
     if (st.ctx && st.aheadServed < st.aheadN) {
-      emcgpu::require(st.ctx, emcgpu_bulk_rewind(st.ctx), "emcgpu_bulk_rewind");
-      if (st.aheadServed > 0) {
+      if (st.nrLocal > 0)
+        emcgpu::require(st.ctx, emcgpu_bulk_rewind(st.ctx), "emcgpu_bulk_rewind");
+      if (st.aheadServed > 0 && st.nrLocal > 0) {
         emcgpu::require(st.ctx, emcgpu_bulk_record_velocities(st.ctx, 0, nullptr, 0), "emcgpu_bulk_record_velocities");
         std::vector<double> again(st.aheadServed * idxTypeToPartType.at(idxType)->getNrValleys() * 3);
         emcgpu::require(st.ctx,
@@ -141,14 +162,21 @@ private:
     auto &st = state[idxType];
     if (st.uploaded)
       return;
+    // contiguous blocks whose sizes differ by at most one (viennaemc_b200/sharding.py: shard_range); the particle id that
+    // keys the Philox streams is the position in the whole ensemble
+    const SizeType base = st.staging.size() / shardWorld, rem = st.staging.size() % shardWorld;
+    st.shardFirst = shardRank * base + std::min<SizeType>(shardRank, rem);
+    st.nrLocal = base + (static_cast<SizeType>(shardRank) < rem ? 1 : 0);
     const double *ptrs[EMCGPU_N_STREAMS];
     for (int s = 0; s < EMCGPU_N_STREAMS; s++)
-      ptrs[s] = st.staging.stream[s].data();
+      ptrs[s] = st.staging.stream[s].data() + st.shardFirst;
     emcgpu::require(st.ctx,
-                    emcgpu_set_ensemble(st.ctx, static_cast<int64_t>(st.staging.size()), ptrs, st.staging.packed.data(), 0),
+                    emcgpu_set_ensemble(st.ctx, static_cast<int64_t>(st.nrLocal), st.nrLocal ? ptrs : nullptr,
+                                        st.nrLocal ? st.staging.packed.data() + st.shardFirst : nullptr,
+                                        static_cast<int64_t>(st.shardFirst)),
                     "emcgpu_set_ensemble");
-    if (st.grain && st.staging.size())
-      emcgpu::require(st.ctx, emcgpu_set_grain_clock(st.ctx, st.staging.grainTau.data()), "emcgpu_set_grain_clock");
+    if (st.grain && st.nrLocal)
+      emcgpu::require(st.ctx, emcgpu_set_grain_clock(st.ctx, st.staging.grainTau.data() + st.shardFirst), "emcgpu_set_grain_clock");
     emcgpu::require(st.ctx, emcgpu_rng_philox(st.ctx, stepSeed), "emcgpu_rng_philox");
     emcgpu::require(st.ctx, emcgpu_set_step_index(st.ctx, 1), "emcgpu_set_step_index");
     st.uploaded = true;
@@ -158,7 +186,7 @@ private:
   void download(SizeType idxType, HostEnsemble &out) const {
     materialize(idxType);
     const auto &st = state.at(idxType);
-    const SizeType n = st.nrParticles;
+    const SizeType n = st.nrLocal; // the block of this rank
     double *ptrs[EMCGPU_N_STREAMS];
     for (int s = 0; s < EMCGPU_N_STREAMS; s++) {
       out.stream[s].resize(n);
@@ -188,8 +216,9 @@ private:
       materialize(idxType);
       upload(idxType);
       st.lastObs.assign(idxTypeToPartType[idxType]->getNrValleys() * 3, 0.);
-      if (st.nrParticles)
+      if (st.nrLocal)
         emcgpu::require(st.ctx, emcgpu_bulk_observables(st.ctx, st.lastObs.data()), "emcgpu_bulk_observables");
+      sumOverRanks(st.lastObs);
       st.obsValid = true;
     }
     return st.lastObs;
@@ -215,8 +244,31 @@ public:
         : (envSeed && *envSeed)
             ? std::strtoul(envSeed, nullptr, 10)
             : static_cast<unsigned long>(std::chrono::high_resolution_clock::now().time_since_epoch().count());
-    hostRng.seed(seed);
-    stepSeed = seed;
+    unsigned long commonSeed = seed;
+    if (envInt("EMCGPU_SHARD", 0)) {
+      shardWorld = std::max(1, envInt("WORLD_SIZE", 1));
+      shardRank = envInt("RANK", 0);
+    }
+    if (shardWorld > 1) {
+      const char *idFile = std::getenv("EMCNCCL_ID_FILE");
+      if (!idFile || emcnccl_init_from_file(idFile, shardRank, shardWorld, cudaDeviceOrdinal(), 120., &comm) != 0)
+        emcMessage::getInstance()
+            .addError(std::string("sharded run: cannot join the NCCL communicator (EMCNCCL_ID_FILE must name a file all "
+                                  "ranks can reach): ") + emcnccl_last_error())
+            .print();
+      // every rank creates the same ensemble and draws the same step streams: the seed of rank 0, in 16-bit pieces (exact)
+      std::vector<double> pieces(4, 0.);
+      if (shardRank == 0)
+        for (int i = 0; i < 4; i++)
+          pieces[i] = static_cast<double>((static_cast<unsigned long long>(seed) >> (16 * i)) & 0xffffull);
+      sumOverRanks(pieces);
+      unsigned long long joined = 0;
+      for (int i = 0; i < 4; i++)
+        joined |= static_cast<unsigned long long>(pieces[i]) << (16 * i);
+      commonSeed = static_cast<unsigned long>(joined);
+    }
+    hostRng.seed(commonSeed);
+    stepSeed = commonSeed;
     for (const auto &[idxType, type] : idxTypeToPartType) {
       auto &st = state[idxType];
       if (!type->isMoved())
@@ -242,6 +294,8 @@ public:
       if (st.ctx)
         emcgpu_destroy(st.ctx);
     }
+    if (comm)
+      emcnccl_destroy(comm);
   }
 
   // EMCGPU_MATH_EXACT reproduces the reference's rounding operation by operation (replay parity);
@@ -251,6 +305,14 @@ public:
     for (const auto &[idxType, type] : idxTypeToPartType)
       if (type->isMoved())
         configure(idxType);
+  }
+  bool isSharded() const { return shardWorld > 1; }
+  int shardRankOf() const { return shardRank; }
+  int shardWorldSize() const { return shardWorld; }
+  // the particles of a type this rank holds (getNrParticles(): the whole ensemble)
+  SizeType getNrParticlesOfThisRank(SizeType idxType) const {
+    const auto &st = state.at(idxType);
+    return st.uploaded ? st.nrLocal : st.nrParticles;
   }
   // the C-ABI context of a particle type (multi-GPU drivers, tests)
   emcgpu_ctx *getGpuContext(SizeType idxType) {
@@ -324,10 +386,11 @@ public:
       refreshModel(idxType);
       SizeType nAhead = st.phononBaths.empty() ? lookahead : 1;
       st.velSteps = 0;
+      const bool here = st.nrLocal > 0; // (a rank of a sharded run may hold none of a tiny ensemble: it only joins the sums)
       if (st.recordVel) { // the window's velocities come back with it (at most 1 GB of them per window)
-        const SizeType perStep = st.nrParticles * st.recordVel;
+        const SizeType perStep = st.nrLocal * st.recordVel;
         nAhead = std::max<SizeType>(1, std::min<SizeType>(nAhead, (SizeType(1) << 27) / std::max<SizeType>(1, perStep)));
-        st.velAhead.resize(nAhead * perStep);
+        st.velAhead.resize(std::max<SizeType>(1, nAhead * perStep));
         emcgpu::require(st.ctx, emcgpu_bulk_record_velocities(st.ctx, st.recordVel, st.velAhead.data(), static_cast<int64_t>(nAhead)),
                         "emcgpu_bulk_record_velocities");
         st.velSteps = nAhead;
@@ -336,17 +399,22 @@ public:
       }
       if (nAhead > 1) {
         st.ahead.assign(nAhead * nObs, 0.);
-        emcgpu::require(st.ctx,
-                        emcgpu_bulk_step_ahead(st.ctx, tStep, static_cast<int>(nAhead), static_cast<int>(nAhead), st.ahead.data()),
-                        "emcgpu_bulk_step_ahead");
+        if (here)
+          emcgpu::require(st.ctx,
+                          emcgpu_bulk_step_ahead(st.ctx, tStep, static_cast<int>(nAhead), static_cast<int>(nAhead), st.ahead.data()),
+                          "emcgpu_bulk_step_ahead");
+        sumOverRanks(st.ahead); // one all-reduce per look-ahead window
         st.aheadN = nAhead;
         st.aheadServed = 1;
         st.aheadDt = tStep;
         st.lastObs.assign(st.ahead.begin(), st.ahead.begin() + nObs);
       } else {
         st.lastObs.assign(nObs, 0.);
-        emcgpu::require(st.ctx, emcgpu_bulk_step(st.ctx, tStep, 1, 1, st.lastObs.data()), "emcgpu_bulk_step");
-        emcgpu::collectPhononCounts(st.ctx, st.phononBaths); // recordEmission / recordAbsorption of this step
+        if (here)
+          emcgpu::require(st.ctx, emcgpu_bulk_step(st.ctx, tStep, 1, 1, st.lastObs.data()), "emcgpu_bulk_step");
+        sumOverRanks(st.lastObs);
+        // recordEmission / recordAbsorption of this step, of all ranks
+        emcgpu::collectPhononCounts(st.ctx, st.phononBaths, [this](std::vector<double> &v) { sumOverRanks(v); }, here);
       }
       st.obsValid = true;
     }
@@ -362,10 +430,12 @@ public:
     refreshModel(idxType);
     const SizeType nV = idxTypeToPartType[idxType]->getNrValleys();
     series.assign(nSteps * nV * 3, 0.);
-    emcgpu::require(st.ctx,
-                    emcgpu_bulk_step(st.ctx, tStep, static_cast<int>(nSteps), static_cast<int>(stepsPerLaunch), series.data()),
-                    "emcgpu_bulk_step");
-    emcgpu::collectPhononCounts(st.ctx, st.phononBaths);
+    if (st.nrLocal > 0)
+      emcgpu::require(st.ctx,
+                      emcgpu_bulk_step(st.ctx, tStep, static_cast<int>(nSteps), static_cast<int>(stepsPerLaunch), series.data()),
+                      "emcgpu_bulk_step");
+    sumOverRanks(series);
+    emcgpu::collectPhononCounts(st.ctx, st.phononBaths, [this](std::vector<double> &v) { sumOverRanks(v); }, st.nrLocal > 0);
     st.lastObs.assign(series.end() - nV * 3, series.end());
     st.obsValid = true;
   }
@@ -392,15 +462,18 @@ public:
       HostEnsemble h;
       const auto &st = state.at(idxType);
       const HostEnsemble *src = &st.staging;
-      if (st.uploaded) {
+      SizeType n = st.nrParticles, first = 0;
+      if (st.uploaded) { // the block of this rank (one GPU: everything), numbered as in the whole ensemble
         download(idxType, h);
         src = &h;
+        n = st.nrLocal;
+        first = st.shardFirst;
       }
-      std::ofstream os(namePrefix + type->getName() + nameSuffix + ".txt");
+      std::ofstream os(namePrefix + type->getName() + nameSuffix + (comm ? ".rank" + std::to_string(shardRank) : std::string()) +
+                       ".txt");
       os << device.getMaxPos() << "\n";
-      const SizeType n = st.nrParticles;
       for (SizeType i = 0; i < n; i++) {
-        os << i << " " << src->stream[EMCGPU_X][i] << " " << src->stream[EMCGPU_Y][i] << " " << src->stream[EMCGPU_Z][i];
+        os << first + i << " " << src->stream[EMCGPU_X][i] << " " << src->stream[EMCGPU_Y][i] << " " << src->stream[EMCGPU_Z][i];
         if (type->isMoved())
           os << " " << src->stream[EMCGPU_KX][i] << " " << src->stream[EMCGPU_KY][i] << " " << src->stream[EMCGPU_KZ][i]
              << " " << src->stream[EMCGPU_ENERGY][i] << " " << ((src->packed[i] >> 8) & 0xffu) << " "
@@ -469,13 +542,13 @@ private:
       // the step kernels recorded the velocities of the driver's current step: one line from the record
       const SizeType cur = st.aheadN ? st.aheadServed : (st.velSteps ? 1 : 0); // 1-based step of the window
       if (st.recordVel == comps && cur >= 1 && cur <= st.velSteps && st.obsValid) {
-        const double *v = st.velAhead.data() + (cur - 1) * st.nrParticles * comps;
-        for (SizeType i = 0; i < st.nrParticles; i++) {
+        const double *v = st.velAhead.data() + (cur - 1) * st.nrLocal * comps;
+        for (SizeType i = 0; i < st.nrLocal; i++) {
           if (projected)
             os << v[i];
           else
             os << std::array<T, 3>{v[3 * i], v[3 * i + 1], v[3 * i + 2]};
-          if (i + 1 < st.nrParticles)
+          if (i + 1 < st.nrLocal)
             os << " ";
         }
         os << std::endl;
@@ -483,11 +556,13 @@ private:
       }
       st.recordVel = comps; // from the next launch on the kernels record them
       const HostEnsemble *src = &st.staging;
-      if (st.uploaded) {
+      SizeType n = st.nrParticles;
+      if (st.uploaded) { // the block of this rank (one GPU: everything)
         download(idxType, h);
         src = &h;
+        n = st.nrLocal;
       }
-      for (SizeType i = 0; i < st.nrParticles; i++) {
+      for (SizeType i = 0; i < n; i++) {
         const std::array<T, 3> k = {src->stream[EMCGPU_KX][i], src->stream[EMCGPU_KY][i], src->stream[EMCGPU_KZ][i]};
         const auto *valley = type->getValley(src->packed[i] & 0xffu);
         const auto vel = valley->getVelocity(k, src->stream[EMCGPU_ENERGY][i], (src->packed[i] >> 8) & 0xffu);
@@ -495,7 +570,7 @@ private:
           os << innerProduct(vel, appliedFieldDir);
         else
           os << vel;
-        if (i + 1 < st.nrParticles)
+        if (i + 1 < n)
           os << " ";
       }
       os << std::endl;

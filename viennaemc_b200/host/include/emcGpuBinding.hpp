@@ -70,17 +70,32 @@ template <class T> void uploadPhononBaths(emcgpu_ctx *ctx, const std::vector<emc
 }
 
 // recordEmission / recordAbsorption of the step(s) since the last call: device counters -> nEm / nAbs of the baths
-template <class T> void collectPhononCounts(emcgpu_ctx *ctx, const std::vector<emcPhononBath<T> *> &baths) {
+// sumOverRanks: sharded runs (several GPUs) add the counters of all ranks before the baths see them (nEm / nAbs
+// join the per-step all-reduce); counts are integers far below 2^53, so the sum of doubles is exact and identical everywhere.
+// hasParticles = false: this rank holds no particle of the type (it still takes part in the sum).
+template <class T, class Reduce>
+void collectPhononCounts(emcgpu_ctx *ctx, const std::vector<emcPhononBath<T> *> &baths, Reduce &&sumOverRanks,
+                         bool hasParticles = true) {
   if (baths.empty())
     return;
   const SizeType bins = baths[0]->nrBins;
-  std::vector<int64_t> em(baths.size() * bins), ab(baths.size() * bins);
-  require(ctx, emcgpu_get_phonon_counts(ctx, em.data(), ab.data(), 1), "emcgpu_get_phonon_counts");
+  std::vector<int64_t> em(baths.size() * bins, 0), ab(baths.size() * bins, 0);
+  if (hasParticles)
+    require(ctx, emcgpu_get_phonon_counts(ctx, em.data(), ab.data(), 1), "emcgpu_get_phonon_counts");
+  std::vector<double> both(2 * em.size());
+  for (SizeType i = 0; i < em.size(); i++) {
+    both[i] = static_cast<double>(em[i]);
+    both[em.size() + i] = static_cast<double>(ab[i]);
+  }
+  sumOverRanks(both);
   for (SizeType b = 0; b < baths.size(); b++)
     for (SizeType i = 0; i < bins; i++) {
-      baths[b]->nEm[i] += static_cast<T>(em[b * bins + i]);
-      baths[b]->nAbs[i] += static_cast<T>(ab[b * bins + i]);
+      baths[b]->nEm[i] += static_cast<T>(both[b * bins + i]);
+      baths[b]->nAbs[i] += static_cast<T>(both[em.size() + b * bins + i]);
     }
+}
+template <class T> void collectPhononCounts(emcgpu_ctx *ctx, const std::vector<emcPhononBath<T> *> &baths) {
+  collectPhononCounts(ctx, baths, [](std::vector<double> &) {});
 }
 
 // emcgpu_set_valleys + emcgpu_set_phonon_baths + emcgpu_set_tables for one particle type.  To be called after
