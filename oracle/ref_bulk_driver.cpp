@@ -42,6 +42,7 @@
 // single-layer MoS2 (examples/singleLayerMoS2): the example's own particle type and its default parameter set
 #include <electron2D.hpp>       // -I $(REF)/examples/singleLayerMoS2
 #include <parameterPilotto.hpp> //
+#include <parameterKaasbjerg.hpp>
 
 using T = double;
 using DeviceType = emcDevice<T, 3>;
@@ -269,6 +270,21 @@ template <class PT> void buildMoS2Pilotto(PT &type, double temperature) {
   }
 }
 
+// The subset of the example's Kaasbjerg parameter set whose mechanisms have device samplers: ONE parabolic single-layer
+// valley with one sub-valley, two acoustic branches, and the zero-order optical mechanisms through the constructor WITHOUT a
+// sub-valley map (the sub-valley index is kept, no draw for it) -- singleLayerMoS2.cpp:70-74 without the first-order,
+// Froehlich and piezoelectric terms.
+template <class PT> void buildMoS2KaasbjergSubset(PT &type, double temperature) {
+  MoS2Kaasbjerg::addValleys(type);
+  MoS2Kaasbjerg::addAcousticScatterMechanisms(type, {0}, temperature);
+  MoS2Kaasbjerg::addZeroOrderIntervalleyScatterMechanisms(type, {0}, temperature);
+  auto &mechs = type->scatterHandler.scatterMechanisms;
+  for (size_t i = 0; i < mechs.size(); i++) {
+    std::unique_ptr<emcScatterMechanism<T>> inner(mechs[i].release());
+    mechs[i] = std::make_unique<LoggingMechanism>(std::move(inner), (std::int64_t)i);
+  }
+}
+
 // ------------------------------------------------------------------ dumps
 static void dumpEnsemble(Blob &b, const std::string &prefix, Handler &h) {
   auto &parts = h.particles[0];
@@ -328,7 +344,7 @@ int main(int argc, char **argv) {
   RecordingRNG::sink() = &draws;
 
   const T h = a.box / a.cells;
-  const bool mos2 = a.material == "mos2";
+  const bool mos2 = a.material == "mos2" || a.material == "mos2k";
   // mos2: one layer of 0.65 nm (singleLayerMoS2.cpp:44-45), the placeholder material and doping of :133-135
   const T boxZ = mos2 ? 0.65e-9 : a.box, hZ = mos2 ? 0.65e-9 : h;
   DeviceType device{mos2 ? emcMaterial<T>{1, 1, 1, 1, 1} : siMaterial(), {a.box, a.box, boxZ}, {h, h, hZ}, a.temperature};
@@ -339,7 +355,10 @@ int main(int argc, char **argv) {
     types[0] = std::make_unique<electron2D<T, DeviceType>>(); // 5000 levels up to 0.5 eV, 4 particles per grid point
     a.levels = 5000;
     a.emax = 0.5;
-    buildMoS2Pilotto(types[0], a.temperature);
+    if (a.material == "mos2")
+      buildMoS2Pilotto(types[0], a.temperature);
+    else
+      buildMoS2KaasbjergSubset(types[0], a.temperature);
   } else {
     types[0] = std::make_unique<emcElectron<T, DeviceType>>(a.levels, a.emax, false);
     if (a.material == "si")

@@ -131,12 +131,35 @@ def build_mos2_pilotto(temperature=300.0):
     return m
 
 
+def build_mos2_kaasbjerg_subset(temperature=300.0):
+    """the part of parameterKaasbjerg.hpp whose mechanisms have device samplers (oracle/ref_bulk_driver.cpp:
+    buildMoS2KaasbjergSubset): ONE parabolic single-layer valley with one sub-valley, acoustic TA / LA, zero-order LO / homopolar
+    through the constructor without a sub-valley map (emission added before absorption, :143-159)"""
+    dp_cal, rho = 1.60, 3.1e-6
+    m = po.Model(5000, 0.5, temperature, 1.0, 1.0)
+    m.set_electron2d(4)
+    m.add_valley(po.VALLEY_PARABOLIC_ISO_SL, 0.48, 1)
+    m.add_acoustic_sl(0, 0, dp_cal * 1.6, rho, 4.2e3)
+    m.add_acoustic_sl(0, 0, dp_cal * 2.8, rho, 6.7e3)
+    for sigma, ph in ((dp_cal * 2.6e10, 0.041), (dp_cal * 4.1e10, 0.05)):
+        m.add_intervalley_sl(True, 0, 0, 0, sigma, rho, ph, None)
+        m.add_intervalley_sl(False, 0, 0, 0, sigma, rho, ph, None)
+    m.build_tables()
+    return m
+
+
+def build_mos2(case):
+    return build_mos2_kaasbjerg_subset() if MOS2_CASES[case]["material"] == "mos2k" else build_mos2_pilotto()
+
+
 # recorder cases of the single-layer path (oracle/_ref/ref_bulk_driver --material mos2): box = (box, box, 0.65 nm), one cell in z
 MOS2_CASES = {
     # the example's own time step and a high field (valley transfer K -> Q sets in)
     "mos2_pilotto": dict(material="mos2", cells=6, box=6e-8, field=4e6, fdir="1,0,0", dt=1e-16, steps=1500, seed=17),
     # large time step (several events per step), field off the axes
     "mos2_pilotto_bigdt": dict(material="mos2", cells=5, box=5e-8, field=1e7, fdir="0.6,-1,0", dt=2e-15, steps=120, seed=23),
+    # one parabolic single-layer valley, the zero-order mechanisms without a sub-valley map (Kaasbjerg set, supported part)
+    "mos2_kaasbjerg_subset": dict(material="mos2k", cells=5, box=5e-8, field=2e6, fdir="1,0.5,0", dt=1e-15, steps=300, seed=29),
 }
 MOS2_LZ = 0.65e-9
 

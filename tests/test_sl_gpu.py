@@ -11,7 +11,7 @@ import pytest
 
 from helpers import STATE_RTOL, assert_state_close, download_ensemble, field_dir_of, golden_ensemble, load_golden, upload_ensemble, upload_model
 from oracle import pyoracle as po
-from scenarios import MOS2_CASES, MOS2_LZ, build_mos2_pilotto
+from scenarios import MOS2_CASES, MOS2_LZ, build_mos2, build_mos2_pilotto
 from viennaemc_b200 import capi
 
 pytestmark = pytest.mark.gpu
@@ -30,7 +30,7 @@ def box_of(a):
 def test_replay_of_reference_draws(gpu_ctx_factory, case, steps_per_launch, multi_kernel, math_mode):
     g = load_golden(case)
     a = MOS2_CASES[case]
-    m = build_mos2_pilotto()
+    m = build_mos2(case)
     box = box_of(a)
     # which particle consumed which of the reference's draws: from the oracle run that reproduces the reference bit for bit
     # (tests/test_oracle_sl.py)

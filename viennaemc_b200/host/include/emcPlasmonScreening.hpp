@@ -13,24 +13,30 @@
 #include <emcUtil.hpp>
 
 template <class T> class emcPlasmonScreening {
-  T qs2 = T(0);
-  T epsStatic;
-  bool enabled;
-
 public:
-  emcPlasmonScreening() = delete;
-  explicit emcPlasmonScreening(T inEpsStatic, bool inEnabled = true) : epsStatic(inEpsStatic), enabled(inEnabled) {}
-
-  // carrier density [1/m^3] and carrier temperature [K]; a disabled screening keeps qs^2 = 0
-  void update(T density, T carrierTemp) {
-    const bool active = enabled && density > T(0) && carrierTemp > T(0);
-    qs2 = active ? density * constants::q * constants::q / (epsStatic * constants::eps0 * constants::kB * carrierTemp) : T(0);
+  // Debye: qs^2 = n q^2 / (eps_s eps_0 kB T) for a carrier density [1/m^3] at a carrier temperature [K]
+  static T debyeWaveVectorSquared(T density, T carrierTemp, T inEpsStatic) {
+    return density * constants::q * constants::q / (inEpsStatic * constants::eps0 * constants::kB * carrierTemp);
   }
-  void setQs2(T inQs2) { qs2 = enabled ? inQs2 : T(0); }
-  T getQs2() const { return qs2; }
-  T getQs() const { return std::sqrt(qs2); }
-  T getScreeningLength() const { return qs2 > T(0) ? T(1) / std::sqrt(qs2) : std::numeric_limits<T>::infinity(); }
-  bool isEnabled() const { return enabled; }
+
+  emcPlasmonScreening() = delete;
+  explicit emcPlasmonScreening(T inEpsStatic, bool inEnabled = true) : staticPermittivity(inEpsStatic), switchedOn(inEnabled) {}
+
+  bool isEnabled() const { return switchedOn; }
+  // a disabled screening, an empty band or a cold one keep qs^2 = 0
+  void update(T density, T carrierTemp) {
+    value = (switchedOn && density > T(0) && carrierTemp > T(0)) ? debyeWaveVectorSquared(density, carrierTemp, staticPermittivity)
+                                                                 : T(0);
+  }
+  void setQs2(T inQs2) { value = switchedOn ? inQs2 : T(0); }
+  T getQs2() const { return value; }
+  T getQs() const { return std::sqrt(value); }
+  T getScreeningLength() const { return value > T(0) ? T(1) / std::sqrt(value) : std::numeric_limits<T>::infinity(); }
+
+private:
+  T value = T(0); // qs^2 [1/m^2]
+  T staticPermittivity;
+  bool switchedOn;
 };
 
 #endif
