@@ -115,7 +115,8 @@ typedef enum {
   /* emcZeroOrderSingleLayerInterValleyScatterMechanism.hpp:116-147, :293-324: valley <- finalValley; nFinal > 0:
    * subValley <- finalSub[sub][floor(u nFinal)] (nFinal = 0: the one-valley constructor, no draw); E += param[0]
    * (+(hw - dE_valley) absorption, -(dE_valley + hw) emission); then the direction of SINGLE_LAYER_ELASTIC in the final
-   * valley */
+   * valley.  param[1] != 0: the first-order classes (emcFirstOrderSingleLayerIntervalleyScatterMechanism.hpp:104-126, :255-275):
+   * k_x = |k| cos, k_y = |k| sin without the Herring-Vogt weighting, k_z kept */
   EMCGPU_SAMPLER_SINGLE_LAYER_INTERVALLEY = 7
 } emcgpu_sampler_id;
 #define EMCGPU_MAX_BATHS 8

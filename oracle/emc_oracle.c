@@ -285,7 +285,7 @@ void orc_random_direction_wrt_k(const double k[3], double cosTheta, double rnd, 
 }
 
 /* ------------------------------------------------------------------ model */
-enum { MK_ACOUSTIC = 1, MK_ZERO = 2, MK_FIRST = 3, MK_COULOMB = 4, MK_FROEHLICH = 5, MK_ACOUSTIC_SL = 6, MK_ZERO_SL = 7 };
+enum { MK_ACOUSTIC = 1, MK_ZERO = 2, MK_FIRST = 3, MK_COULOMB = 4, MK_FROEHLICH = 5, MK_ACOUSTIC_SL = 6, MK_ZERO_SL = 7, MK_FIRST_SL = 8 };
 
 typedef struct {
   int kind, valley, finalValley, region, emission, nFinal, nInitSub;
@@ -480,13 +480,13 @@ int orc_add_acoustic_sl(orc_model_t *m, int valley, int region, double sigma, do
 
 /* emcZeroOrderSingleLayerInterValleyScatterMechanism.hpp:66-88 (absorption), :243-266 (emission); nFinal = 0: the
  * one-valley constructor (:42-49): nrFinalValleys = 1 and no sub-valley draw */
-int orc_add_intervalley_sl(orc_model_t *m, int emission, int valley, int finalValley, int region, double sigma,
+int orc_add_intervalley_sl(orc_model_t *m, int order, int emission, int valley, int finalValley, int region, double sigma,
                            double density2D, double phE, int nInitSub, int nFinal, const int32_t *finalSub) {
   if (nFinal > ORC_MAX_FINAL || nInitSub > ORC_MAX_SUB)
     return -1;
   mech_t *x = &m->mech[m->nMech];
   memset(x, 0, sizeof *x);
-  x->kind = MK_ZERO_SL;
+  x->kind = order == 0 ? MK_ZERO_SL : MK_FIRST_SL;
   x->valley = valley;
   x->finalValley = finalValley;
   x->region = region;
@@ -500,7 +500,14 @@ int orc_add_intervalley_sl(orc_model_t *m, int emission, int valley, int finalVa
   const double nrFinal = nFinal > 0 ? (double)nFinal : 1.;
   double exponent = phE * C_Q / (C_KB * m->temperature);
   double omega = phE * C_Q / C_HBAR;
-  if (emission)
+  if (order != 0) {
+    /* emcFirstOrderSingleLayerIntervalleyScatterMechanism.hpp:82-88 (absorption), :229-236 (emission); sigma in eV */
+    if (emission)
+      x->scatterConst = nrFinal * pow(sigma * C_Q, 2) * C_Q * exp(exponent) /
+                        (density2D * omega * (exp(exponent) - 1) * pow(C_HBAR, 4));
+    else
+      x->scatterConst = nrFinal * pow(sigma * C_Q, 2) * C_Q / (density2D * omega * (exp(exponent) - 1) * pow(C_HBAR, 4));
+  } else if (emission)
     x->scatterConst = nrFinal * pow(sigma * C_Q / C_HBAR, 2) * exp(exponent) / (2 * density2D * omega * (exp(exponent) - 1));
   else
     x->scatterConst = nrFinal * pow(sigma * C_Q / C_HBAR, 2) / (2 * density2D * omega * (exp(exponent) - 1));
@@ -617,6 +624,19 @@ double orc_raw_rate(const orc_model_t *m, int g, double energy) {
       return md * x->scatterConst * (1 + 2 * alpha * ef);
     }
     return 0;
+  }
+  case MK_FIRST_SL: { /* emcFirstOrderSingleLayer...:96-101, :244-252: mass and non-parabolicity of the INITIAL valley */
+    double md = dos_mass_at_zero(vi);
+    double alpha = vi->alpha;
+    if (x->emission) {
+      if (energy > x->phononEnergy) {
+        double rate = md * md * x->scatterConst * (2 * energy - x->phononEnergy);
+        return rate * (1 + 2 * alpha * energy);
+      }
+      return 0;
+    }
+    double rate = md * md * x->scatterConst * (2 * energy + x->phononEnergy);
+    return rate * (1 + 2 * alpha * energy);
   }
   case MK_FIRST: { /* emcFirstOrder...:102-119, :250-267 */
     double dV = delta_valley(m, x);
@@ -767,10 +787,12 @@ static void fill_mech_desc(const orc_model_t *m, int g, orc_mech_t *d) {
   case MK_ACOUSTIC_SL:
     d->sampler = ORC_SAMPLER_SL_ELASTIC;
     break;
-  case MK_ZERO_SL: { /* abs: E += hw - dV (:127); em: E -= (dV + hw) (:304) */
+  case MK_ZERO_SL:
+  case MK_FIRST_SL: { /* abs: E += hw - dV (:127); em: E -= (dV + hw) (:304); the first-order classes alike */
     d->sampler = ORC_SAMPLER_SL_INTERVALLEY;
     double dV = delta_valley(m, x);
     d->p[0] = x->emission ? -(dV + x->phononEnergy) : (x->phononEnergy - dV);
+    d->p[1] = x->kind == MK_FIRST_SL ? 1. : 0.; /* plain in-plane direction, k_z left as it is */
     break;
   }
   case MK_FROEHLICH:
@@ -885,6 +907,14 @@ static void scatter_with(const orc_model_t *m, const orc_mech_t *d, orc_ensemble
     }
     const orc_valley_t *v = &m->valleys[e->valley[p]];
     double angle = 2 * C_PI * rng_u01(rng);
+    if (d->sampler == ORC_SAMPLER_SL_INTERVALLEY && d->p[1] != 0) {
+      /* emcFirstOrderSingleLayerIntervalleyScatterMechanism.hpp:121-125, :270-274: no Herring-Vogt weighting */
+      double normK = orc_norm_wave_vec(v, e->energy[p]);
+      out[0] = normK * cos(angle);
+      out[1] = normK * sin(angle);
+      out[2] = k[2];
+      break;
+    }
     /* random direction weighted by the Herring-Vogt factors */
     out[0] = cos(angle) / v->vogt[0];
     out[1] = sin(angle) / v->vogt[1];

@@ -42,7 +42,8 @@ enum { ORC_SAMPLER_NONE = 0, ORC_SAMPLER_ISOTROPIC_ELASTIC = 1,
        ORC_SAMPLER_SL_ELASTIC = 6,
        /* emcZeroOrderSingleLayerInterValleyScatterMechanism.hpp:116-147, :293-324: valley <- finalValley; nFinal > 0:
         * sub <- finalSub[sub][floor(u nFinal)] (one draw; none for the one-valley constructor); E += p[0]; then the
-        * direction of SL_ELASTIC in the FINAL valley */
+        * direction of SL_ELASTIC in the FINAL valley.  p[1] != 0 (emcFirstOrderSingleLayerIntervalleyScatterMechanism.hpp
+        * :104-126, :255-275): k_x = |k| cos, k_y = |k| sin without the Herring-Vogt weighting, k_z kept */
        ORC_SAMPLER_SL_INTERVALLEY = 7 };
 
 enum { ORC_RNG_MT_GLOBAL = 0, ORC_RNG_STREAMS = 1, ORC_RNG_PHILOX = 2 };
@@ -90,7 +91,7 @@ void orc_model_set_electron2d(orc_model_t *m, int perGridPoint); /* examples/sin
 void orc_model_set_init_energy(orc_model_t *m, double energyEV); /* emcElectron.hpp:85-88, emcHole.hpp:95-98 */
 /* single-layer mechanisms; density2D [kg/m^2], the model's temperature */
 int orc_add_acoustic_sl(orc_model_t *m, int valley, int region, double sigma, double density2D, double vSound);
-int orc_add_intervalley_sl(orc_model_t *m, int emission, int valley, int finalValley, int region, double sigma,
+int orc_add_intervalley_sl(orc_model_t *m, int order, int emission, int valley, int finalValley, int region, double sigma,
                            double density2D, double phE, int nInitSub, int nFinal, const int32_t *finalSub);
 int orc_add_valley(orc_model_t *m, int kind, const double relMass[3],
                    double particleMass, int deg, double alpha, double eBottom,

@@ -78,7 +78,7 @@ def lib():
                                           C.c_double, C.c_int, C.c_int, _IP]
         L.orc_add_coulomb.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
         L.orc_add_acoustic_sl.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
-        L.orc_add_intervalley_sl.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+        L.orc_add_intervalley_sl.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
                                              C.c_double, C.c_int, C.c_int, _IP]
         L.orc_build_tables.argtypes = [C.c_void_p]
         L.orc_model_set_grain.argtypes = [C.c_void_p, C.c_double, C.c_double]
@@ -256,14 +256,14 @@ class Model:
         """emcAcousticSingleLayerMechanism"""
         return self.L.orc_add_acoustic_sl(self.h, valley, region, sigma, density_2d, v_sound)
 
-    def add_intervalley_sl(self, emission, valley, final_valley, region, sigma, density_2d, phonon_energy, final_sub=None):
-        """emcZeroOrderSingleLayerInterValley{Absorption,Emission}ScatterMechanism; final_sub None: the one-valley form"""
+    def add_intervalley_sl(self, emission, valley, final_valley, region, sigma, density_2d, phonon_energy, final_sub=None, order=0):
+        """emc{Zero,First}OrderSingleLayerInterValley{Absorption,Emission}ScatterMechanism; final_sub None: the one-valley form"""
         if final_sub is None:
-            r = self.L.orc_add_intervalley_sl(self.h, int(emission), valley, final_valley, region, sigma, density_2d,
+            r = self.L.orc_add_intervalley_sl(self.h, order, int(emission), valley, final_valley, region, sigma, density_2d,
                                               phonon_energy, 0, 0, None)
         else:
             fs = np.ascontiguousarray(np.asarray(final_sub, dtype=np.int32))
-            r = self.L.orc_add_intervalley_sl(self.h, int(emission), valley, final_valley, region, sigma, density_2d,
+            r = self.L.orc_add_intervalley_sl(self.h, order, int(emission), valley, final_valley, region, sigma, density_2d,
                                               phonon_energy, fs.shape[0], fs.shape[1], _ip(fs))
         assert r >= 0
         return r

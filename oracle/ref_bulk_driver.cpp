@@ -272,12 +272,13 @@ template <class PT> void buildMoS2Pilotto(PT &type, double temperature) {
 
 // The subset of the example's Kaasbjerg parameter set whose mechanisms have device samplers: ONE parabolic single-layer
 // valley with one sub-valley, two acoustic branches, and the zero-order optical mechanisms through the constructor WITHOUT a
-// sub-valley map (the sub-valley index is kept, no draw for it) -- singleLayerMoS2.cpp:70-74 without the first-order,
-// Froehlich and piezoelectric terms.
+// sub-valley map (the sub-valley index is kept, no draw for it) and the first-order mechanisms likewise --
+// singleLayerMoS2.cpp:70-76 without the Froehlich and piezoelectric terms.
 template <class PT> void buildMoS2KaasbjergSubset(PT &type, double temperature) {
   MoS2Kaasbjerg::addValleys(type);
   MoS2Kaasbjerg::addAcousticScatterMechanisms(type, {0}, temperature);
   MoS2Kaasbjerg::addZeroOrderIntervalleyScatterMechanisms(type, {0}, temperature);
+  MoS2Kaasbjerg::addFirstOrderIntervalleyScatterMechanisms(type, {0}, temperature);
   auto &mechs = type->scatterHandler.scatterMechanisms;
   for (size_t i = 0; i < mechs.size(); i++) {
     std::unique_ptr<emcScatterMechanism<T>> inner(mechs[i].release());

@@ -134,7 +134,8 @@ def build_mos2_pilotto(temperature=300.0):
 def build_mos2_kaasbjerg_subset(temperature=300.0):
     """the part of parameterKaasbjerg.hpp whose mechanisms have device samplers (oracle/ref_bulk_driver.cpp:
     buildMoS2KaasbjergSubset): ONE parabolic single-layer valley with one sub-valley, acoustic TA / LA, zero-order LO / homopolar
-    through the constructor without a sub-valley map (emission added before absorption, :143-159)"""
+    and the four first-order pairs through the constructors without a sub-valley map (emission added before absorption,
+    :143-201)"""
     dp_cal, rho = 1.60, 3.1e-6
     m = po.Model(5000, 0.5, temperature, 1.0, 1.0)
     m.set_electron2d(4)
@@ -144,6 +145,10 @@ def build_mos2_kaasbjerg_subset(temperature=300.0):
     for sigma, ph in ((dp_cal * 2.6e10, 0.041), (dp_cal * 4.1e10, 0.05)):
         m.add_intervalley_sl(True, 0, 0, 0, sigma, rho, ph, None)
         m.add_intervalley_sl(False, 0, 0, 0, sigma, rho, ph, None)
+    # first order (:162-201): TO at K, TO at Gamma, TA, LA -- deformation potentials in eV
+    for sigma, ph in ((dp_cal * 1.9, 0.048), (dp_cal * 4.0, 0.048), (dp_cal * 5.9, 0.023), (dp_cal * 3.9, 0.029)):
+        m.add_intervalley_sl(True, 0, 0, 0, sigma, rho, ph, None, order=1)
+        m.add_intervalley_sl(False, 0, 0, 0, sigma, rho, ph, None, order=1)
     m.build_tables()
     return m
 

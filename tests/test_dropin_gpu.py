@@ -407,14 +407,14 @@ def test_unmodified_single_layer_mos2_main_within_3_sigma_of_the_reference(tmp_p
 
 
 def test_single_layer_mechanisms_without_a_device_sampler_are_rejected_by_name(tmp_path):
-    """the Kaasbjerg parameter set of the same example uses mechanisms that exist here by name only (first-order intervalley,
-    Froehlich, piezoelectric single-layer classes): adding one stops the program with its name -- nothing runs on the CPU"""
+    """the Kaasbjerg parameter set of the same example uses mechanisms that exist here by name only (Froehlich and
+    piezoelectric single-layer classes): adding one stops the program with its name -- nothing runs on the CPU"""
     src = tmp_path / "kaasbjerg.cpp"
     src.write_text('''#include <emcDevice.hpp>
 #include <basicBulkParticleHandler.hpp>
 #include <ParticleType/emcElectron.hpp>
 #include <ScatterMechanisms/emcAcousticSingleLayerScatterMechanism.hpp>
-#include <ScatterMechanisms/emcFirstOrderSingleLayerIntervalleyScatterMechanism.hpp>
+#include <ScatterMechanisms/emcPiezoelectricSingleLayerScatterMechanism.hpp>
 #include <ScatterMechanisms/emcFroehlichInteractionSingleLayer.hpp>
 #include <ValleyTypes/emcParabolicIsotropSingleLayerValley.hpp>
 #include <cstring>
@@ -424,8 +424,8 @@ int main(int argc, char **argv) {
   std::unique_ptr<emcParticleType<T, Dev>> type = std::make_unique<emcElectron<T, Dev>>(1000, 0.5, false);
   type->addValley(std::make_unique<emcParabolicIsotropSingleLayerValley<T>>(0.48, type->getMass(), 1));
   type->addScatterMechanism({0}, std::make_unique<emcAcousticSingleLayerMechanism<T>>(0, 2.4, 3.1e-6, 6.7e3, 300., "LA"));
-  if (!std::strcmp(argv[1], "first"))
-    type->addScatterMechanism({0}, std::make_unique<emcFirstOrderSingleLayerInterValleyEmissionScatterMechanism<T>>(0, 5.9, 3.1e-6, 300., 0.03, "TA"));
+  if (!std::strcmp(argv[1], "piezo"))
+    type->addScatterMechanism({0}, std::make_unique<emcPiezoelectricSingleLayerMechanism<T>>(0, 3.0e-11, 5.41e-10, 3.1e-6, 4.2e3, 300., "TA", 0.));
   else
     type->addScatterMechanism({0}, std::make_unique<emcFroehlichInteractionAbsorptionSL<T>>(0, 0.048, 0.098, 5.41e-10, 300., "", 0.));
   return 0;
@@ -437,7 +437,7 @@ int main(int argc, char **argv) {
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", inc, "-I", os.path.join(root, "include"), "-o", str(exe), str(src), "-L",
                            os.path.join(root, "viennaemc_b200", "lib"), "-lemcgpu", "-lemcnccl",
                            "-Wl,-rpath," + os.path.join(root, "viennaemc_b200", "lib")])
-    for which, name in (("first", "FirstInterValleyEmissionSL"), ("froehlich", "froehlichAbsorptionSL")):
+    for which, name in (("piezo", "PiezoelectricSL"), ("froehlich", "froehlichAbsorptionSL")):
         r = subprocess.run([str(exe), which], capture_output=True, text=True, cwd=tmp_path)
         assert r.returncode != 0
         assert f"Scatter mechanism '{name}' has no device final-state sampler" in r.stdout + r.stderr and "no CPU fallback" in r.stdout + r.stderr

@@ -36,7 +36,7 @@ def test_valley_constants_and_rate_tables_equal_the_reference(case):
         assert np.array_equal(ts["cum"], g["cum" + key])
         assert ts["tau"] == g["tau" + key][0]
         assert [x.globalId for x in ts["mech"]] == list(g["mech" + key])
-    assert [len(ts["mech"]) for ts in sets] == ([15, 23] if case == "mos2_pilotto" else [6])
+    assert [len(ts["mech"]) for ts in sets] == ([15, 23] if case == "mos2_pilotto" else [14])
 
 
 @pytest.mark.parametrize("case", CASES)
@@ -64,7 +64,8 @@ def test_initial_ensemble_and_full_run_bit_for_bit(case):
     if a["material"] == "mos2":
         assert len(set(real[:, 3])) > 15 and (ens.valley == 1).sum() > 0  # many of the 38 mechanisms fired, Q valleys populated
     else:
-        assert len(set(real[:, 3])) == 6 and len(real) > 1000  # all six mechanisms of the one-valley model
+        fired = set(real[:, 3])  # 14 mechanisms in the one-valley model, ids 6-13 of first order
+        assert len(fired) >= 12 and len(fired & set(range(6, 14))) >= 6 and len(real) > 1000
     obs = res["obs"]
     cnt = obs[:, :, 2]
     with np.errstate(invalid="ignore", divide="ignore"):

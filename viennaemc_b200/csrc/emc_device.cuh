@@ -610,6 +610,14 @@ __device__ __forceinline__ void sampleFinalState(const DevModel &model, const De
     const double angle = A::mul(2.0 * kPi, uniform01(rng.raw<RNG_MODE>()));
     double sa, ca;
     sincos(angle, &sa, &ca);
+    if (mech.sampler == EMCGPU_SAMPLER_SINGLE_LAYER_INTERVALLEY && mech.param[1] != 0.0) {
+      // first-order classes (emcFirstOrderSingleLayerIntervalleyScatterMechanism.hpp:121-125, :270-274): |k| (cos, sin) without
+      // the Herring-Vogt weighting, k_z left as it is
+      const double nrm = normWaveVec<EXACT>(v, p.energy);
+      p.k.x = A::mul(nrm, ca);
+      p.k.y = A::mul(nrm, sa);
+      break;
+    }
     double kx = A::div(ca, v.vogt[0]), ky = A::div(sa, v.vogt[1]);
     const double factor = A::div(1.0, A::sqrt(A::add(A::mul(kx, kx), A::mul(ky, ky))));
     const double nrm = normWaveVec<EXACT>(v, p.energy);
