@@ -117,7 +117,16 @@ typedef enum {
    * (+(hw - dE_valley) absorption, -(dE_valley + hw) emission); then the direction of SINGLE_LAYER_ELASTIC in the final
    * valley.  param[1] != 0: the first-order classes (emcFirstOrderSingleLayerIntervalleyScatterMechanism.hpp:104-126, :255-275):
    * k_x = |k| cos, k_y = |k| sin without the Herring-Vogt weighting, k_z kept */
-  EMCGPU_SAMPLER_SINGLE_LAYER_INTERVALLEY = 7
+  EMCGPU_SAMPLER_SINGLE_LAYER_INTERVALLEY = 7,
+  /* emcFroehlichInteractionSingleLayer.hpp (:45-80 sampleSingleLayerFroehlichDeflectionAngle, :149-168 / :273-292 the two
+   * classes): E += param[0] (signed phonon energy); the in-plane direction of k is turned by psi, |k| <- k_norm(E'), k_z = 0.
+   * psi by inversion of the 128-point cumulative sum of erfc(w q/2)^2 / (eps(q)^2 q), q^2 = k^2 + k'^2 - 2 k k' cos(psi),
+   * eps(q) = 1 + q_s/q (emc2DScreening.hpp); one draw for the magnitude, one for the side.  param[1] = form-factor width w
+   * [m], param[2] = 2-D screening wave vector q_s [1/m] (0: unscreened) */
+  EMCGPU_SAMPLER_SINGLE_LAYER_FROEHLICH = 8,
+  /* emcPiezoelectricSingleLayerScatterMechanism.hpp:110-139: elastic; deflection theta by the same inversion with the weight
+   * erfc(w q/2)^2 / eps(q)^2, q = 2 k sin(theta/2); param[1], param[2] as above */
+  EMCGPU_SAMPLER_SINGLE_LAYER_PIEZOELECTRIC = 9
 } emcgpu_sampler_id;
 #define EMCGPU_MAX_BATHS 8
 

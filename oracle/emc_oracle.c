@@ -285,7 +285,7 @@ void orc_random_direction_wrt_k(const double k[3], double cosTheta, double rnd, 
 }
 
 /* ------------------------------------------------------------------ model */
-enum { MK_ACOUSTIC = 1, MK_ZERO = 2, MK_FIRST = 3, MK_COULOMB = 4, MK_FROEHLICH = 5, MK_ACOUSTIC_SL = 6, MK_ZERO_SL = 7, MK_FIRST_SL = 8 };
+enum { MK_ACOUSTIC = 1, MK_ZERO = 2, MK_FIRST = 3, MK_COULOMB = 4, MK_FROEHLICH = 5, MK_ACOUSTIC_SL = 6, MK_ZERO_SL = 7, MK_FIRST_SL = 8, MK_FROEHLICH_SL = 9, MK_PIEZO_SL = 10 };
 
 typedef struct {
   int kind, valley, finalValley, region, emission, nFinal, nInitSub;
@@ -294,6 +294,8 @@ typedef struct {
   /* Froehlich family */
   int variant, bath, qResolved, qResolvedAngle;
   double effMass, nBose;
+  /* long-range single-layer mechanisms: form-factor width [m], 2-D screening wave vector [1/m] */
+  double slWidth, slQs;
 } mech_t;
 
 /* emcPhononBath.hpp */
@@ -514,6 +516,82 @@ int orc_add_intervalley_sl(orc_model_t *m, int order, int emission, int valley, 
   return m->nMech++;
 }
 
+/* ---- long-range single-layer mechanisms (Froehlich, piezoelectric): emc2DScreening.hpp:65-76 and the angular weights */
+static double sl_screening_factor(double q, double qs) {
+  double eps = (q <= 0 || qs <= 0) ? 1. : 1. + qs / q;
+  return 1. / (eps * eps);
+}
+/* emcFroehlichInteractionSingleLayer.hpp:48-56: weight of the deflection angle psi */
+static double sl_froehlich_weight(double psi, double k, double kPrime, double width, double qs) {
+  double q2 = k * k + kPrime * kPrime - 2 * k * kPrime * cos(psi);
+  double q = sqrt(q2 > 0 ? q2 : 0);
+  if (q <= 0)
+    return 0;
+  double ff = erfc(width * q / 2);
+  return ff * ff * sl_screening_factor(q, qs) / q;
+}
+/* emcPiezoelectricSingleLayerScatterMechanism.hpp:62-66 */
+static double sl_piezo_weight(double theta, double k, double width, double qs) {
+  double q = 2 * k * sin(theta / 2);
+  double ff = erfc(width * q / 2);
+  return ff * ff * sl_screening_factor(q, qs);
+}
+/* rate integrands of the Froehlich classes (:190-197 absorption, :303-318 emission) and their midpoint rule (:201-208) */
+static double sl_froehlich_integrand(int emission, double theta, double k, double eFactor, double width, double qs) {
+  double cosTheta = cos(theta);
+  if (!emission) {
+    double root = sqrt(cosTheta * cosTheta + eFactor);
+    double q = k * (-cosTheta + root);
+    return (-cosTheta + root) / root * pow(erfc(width * q / 2.), 2) * sl_screening_factor(q, qs);
+  }
+  double root = sqrt(cosTheta * cosTheta - eFactor);
+  double qPlus = k * (cosTheta + root);
+  double partPlus = (cosTheta + root);
+  partPlus *= pow(erfc(width * qPlus / 2.), 2) * sl_screening_factor(qPlus, qs);
+  double qMinus = k * (cosTheta - root);
+  double partMinus = (cosTheta - root);
+  partMinus *= pow(erfc(width * qMinus / 2.), 2) * sl_screening_factor(qMinus, qs);
+  return (partPlus + partMinus) / root;
+}
+static double sl_froehlich_integral(int emission, double a, double b, int n, double k, double eFactor, double width, double qs) {
+  double dx = (b - a) / (double)n;
+  double result = 0;
+  for (double x = a + dx / 2.; x <= b - dx / 2.; x += dx)
+    result += sl_froehlich_integrand(emission, x, k, eFactor, width, qs);
+  return result * dx;
+}
+/* emcFroehlichInteractionSingleLayer.hpp:120-132 (absorption), :239-251 (emission) */
+int orc_add_froehlich_sl(orc_model_t *m, int emission, int valley, int region, double phE, double couplingConst, double width,
+                         double qs) {
+  mech_t *x = &m->mech[m->nMech];
+  memset(x, 0, sizeof *x);
+  x->kind = MK_FROEHLICH_SL;
+  x->valley = x->finalValley = valley;
+  x->region = region;
+  x->emission = emission;
+  x->phononEnergy = phE;
+  x->slWidth = width;
+  x->slQs = qs;
+  double exponent = C_Q * phE / (C_KB * m->temperature);
+  double nrPhonons = emission ? exp(exponent) / (exp(exponent) - 1.) : 1. / (exp(exponent) - 1.);
+  x->scatterConst = pow(couplingConst * C_Q, 2) * nrPhonons / (2 * C_PI * pow(C_HBAR, 3));
+  return m->nMech++;
+}
+/* emcPiezoelectricSingleLayerScatterMechanism.hpp:71-86 */
+int orc_add_piezo_sl(orc_model_t *m, int valley, int region, double piezoConst, double width, double density2D, double vSound,
+                     double qs) {
+  mech_t *x = &m->mech[m->nMech];
+  memset(x, 0, sizeof *x);
+  x->kind = MK_PIEZO_SL;
+  x->valley = x->finalValley = valley;
+  x->region = region;
+  x->slWidth = width;
+  x->slQs = qs;
+  double couplingEnergy = piezoConst * C_Q / C_EPS0;
+  x->scatterConst = 0.5 * couplingEnergy * couplingEnergy * C_KB * m->temperature / (density2D * vSound * vSound * pow(C_HBAR, 3));
+  return m->nMech++;
+}
+
 /* emcCoulombScatterMechanism.hpp:23-32 */
 int orc_add_coulomb(orc_model_t *m, int valley, int region, double epsR, double regionDoping) {
   mech_t *x = &m->mech[m->nMech];
@@ -624,6 +702,32 @@ double orc_raw_rate(const orc_model_t *m, int g, double energy) {
       return md * x->scatterConst * (1 + 2 * alpha * ef);
     }
     return 0;
+  }
+  case MK_FROEHLICH_SL: { /* emcFroehlichInteractionSingleLayer.hpp:138-145, :257-269 */
+    if (x->emission && !(energy > x->phononEnergy))
+      return 0;
+    double md = dos_mass_at_zero(vi);
+    double k = orc_norm_wave_vec(vi, energy);
+    double eFactor = x->phononEnergy / energy;
+    double integral;
+    if (x->emission) {
+      double thetaMax = acos(sqrt(eFactor));
+      integral = sl_froehlich_integral(1, -thetaMax, thetaMax, 10000, k, eFactor, x->slWidth, x->slQs);
+    } else {
+      integral = sl_froehlich_integral(0, 0., 2 * C_PI, 10000, k, eFactor, x->slWidth, x->slQs);
+    }
+    return integral * x->scatterConst * md;
+  }
+  case MK_PIEZO_SL: { /* emcPiezoelectricSingleLayerScatterMechanism.hpp:92-105 */
+    double md = dos_mass_at_zero(vi);
+    double alpha = vi->alpha;
+    double k = orc_norm_wave_vec(vi, energy);
+    double dtheta = C_PI / 128;
+    double integral = 0;
+    for (int i = 0; i < 128; ++i)
+      integral += sl_piezo_weight((i + 0.5) * dtheta, k, x->slWidth, x->slQs);
+    integral *= dtheta / C_PI;
+    return md * x->scatterConst * (1 + 2 * alpha * energy) * integral;
   }
   case MK_FIRST_SL: { /* emcFirstOrderSingleLayer...:96-101, :244-252: mass and non-parabolicity of the INITIAL valley */
     double md = dos_mass_at_zero(vi);
@@ -795,6 +899,17 @@ static void fill_mech_desc(const orc_model_t *m, int g, orc_mech_t *d) {
     d->p[1] = x->kind == MK_FIRST_SL ? 1. : 0.; /* plain in-plane direction, k_z left as it is */
     break;
   }
+  case MK_FROEHLICH_SL:
+    d->sampler = ORC_SAMPLER_SL_FROEHLICH;
+    d->p[0] = x->emission ? -x->phononEnergy : x->phononEnergy;
+    d->p[1] = x->slWidth;
+    d->p[2] = x->slQs;
+    break;
+  case MK_PIEZO_SL:
+    d->sampler = ORC_SAMPLER_SL_PIEZO;
+    d->p[1] = x->slWidth;
+    d->p[2] = x->slQs;
+    break;
   case MK_FROEHLICH:
     d->sampler = x->variant < 2 ? ORC_SAMPLER_FROEHLICH : ORC_SAMPLER_SCREENED_FROEHLICH;
     d->p[0] = x->emission ? -x->phononEnergy : x->phononEnergy;
@@ -925,6 +1040,66 @@ static void scatter_with(const orc_model_t *m, const orc_mech_t *d, orc_ensemble
     double normK = orc_norm_wave_vec(v, e->energy[p]);
     out[0] *= normK;
     out[1] *= normK;
+    break;
+  }
+  case ORC_SAMPLER_SL_FROEHLICH:
+  case ORC_SAMPLER_SL_PIEZO: {
+    /* emcFroehlichInteractionSingleLayer.hpp:45-80 + :149-168 / :273-292; emcPiezoelectricSingleLayerScatterMechanism.hpp
+     * :110-139: deflection angle by inversion of a 128-point cumulative sum of the angular weight, random sign */
+    const orc_valley_t *v = &m->valleys[e->valley[p]];
+    const int fro = d->sampler == ORC_SAMPLER_SL_FROEHLICH;
+    const double width = d->p[1], qs = d->p[2];
+    double kI, kF;
+    if (fro) {
+      double initEnergy = e->energy[p];
+      e->energy[p] = initEnergy + d->p[0];
+      kI = orc_norm_wave_vec(v, initEnergy);
+      kF = orc_norm_wave_vec(v, e->energy[p]);
+    } else {
+      kI = kF = orc_norm_wave_vec(v, e->energy[p]);
+    }
+    double cdf[129];
+    const double dpsi = C_PI / 128;
+    cdf[0] = 0;
+    for (int i = 1; i <= 128; ++i)
+      cdf[i] = cdf[i - 1] + (fro ? sl_froehlich_weight((i - 0.5) * dpsi, kI, kF, width, qs)
+                                 : sl_piezo_weight((i - 0.5) * dpsi, kI, width, qs));
+    const double total = cdf[128];
+    double angle;
+    if (fro) {
+      double phi = atan2(k[1], k[0]);
+      double psi;
+      if (!(total > 0)) {
+        psi = 2 * C_PI * rng_u01(rng);
+      } else {
+        double target = rng_u01(rng) * total;
+        int lo = 1;
+        while (lo < 128 && cdf[lo] < target)
+          ++lo;
+        double frac = (target - cdf[lo - 1]) / (cdf[lo] - cdf[lo - 1]);
+        double psiMag = ((double)lo - 1 + frac) * dpsi;
+        psi = (rng_u01(rng) < 0.5) ? psiMag : (2 * C_PI - psiMag);
+      }
+      angle = phi + psi;
+    } else {
+      double phi = atan2(k[1], k[0]);
+      double theta;
+      if (!(total > 0)) {
+        theta = C_PI * rng_u01(rng);
+      } else {
+        double target = rng_u01(rng) * total;
+        int lo = 1;
+        while (lo < 128 && cdf[lo] < target)
+          ++lo;
+        theta = ((double)lo - 1 + (target - cdf[lo - 1]) / (cdf[lo] - cdf[lo - 1])) * dpsi;
+      }
+      if (rng_u01(rng) < 0.5)
+        theta = -theta;
+      angle = phi + theta;
+    }
+    out[0] = kF * cos(angle);
+    out[1] = kF * sin(angle);
+    out[2] = 0;
     break;
   }
   case ORC_SAMPLER_COULOMB: {

@@ -44,7 +44,13 @@ enum { ORC_SAMPLER_NONE = 0, ORC_SAMPLER_ISOTROPIC_ELASTIC = 1,
         * sub <- finalSub[sub][floor(u nFinal)] (one draw; none for the one-valley constructor); E += p[0]; then the
         * direction of SL_ELASTIC in the FINAL valley.  p[1] != 0 (emcFirstOrderSingleLayerIntervalleyScatterMechanism.hpp
         * :104-126, :255-275): k_x = |k| cos, k_y = |k| sin without the Herring-Vogt weighting, k_z kept */
-       ORC_SAMPLER_SL_INTERVALLEY = 7 };
+       ORC_SAMPLER_SL_INTERVALLEY = 7,
+       /* emcFroehlichInteractionSingleLayer.hpp (:45-80 the angle, :149-168 / :273-292 the classes): E += p[0] (signed phonon
+        * energy); deflection psi about the in-plane direction of k by inversion of a 128-point cumulative sum of
+        * erfc(w q/2)^2 / (eps(q)^2 q), q^2 = k^2 + k'^2 - 2 k k' cos(psi); p[1] = form-factor width w, p[2] = screening q_s */
+       ORC_SAMPLER_SL_FROEHLICH = 8,
+       /* emcPiezoelectricSingleLayerScatterMechanism.hpp:110-139: elastic; weight erfc(w q/2)^2 / eps(q)^2, q = 2 k sin(theta/2) */
+       ORC_SAMPLER_SL_PIEZO = 9 };
 
 enum { ORC_RNG_MT_GLOBAL = 0, ORC_RNG_STREAMS = 1, ORC_RNG_PHILOX = 2 };
 
@@ -93,6 +99,10 @@ void orc_model_set_init_energy(orc_model_t *m, double energyEV); /* emcElectron.
 int orc_add_acoustic_sl(orc_model_t *m, int valley, int region, double sigma, double density2D, double vSound);
 int orc_add_intervalley_sl(orc_model_t *m, int order, int emission, int valley, int finalValley, int region, double sigma,
                            double density2D, double phE, int nInitSub, int nFinal, const int32_t *finalSub);
+int orc_add_froehlich_sl(orc_model_t *m, int emission, int valley, int region, double phE, double couplingConst, double width,
+                         double qs);
+int orc_add_piezo_sl(orc_model_t *m, int valley, int region, double piezoConst, double width, double density2D, double vSound,
+                     double qs);
 int orc_add_valley(orc_model_t *m, int kind, const double relMass[3],
                    double particleMass, int deg, double alpha, double eBottom,
                    const double *dirs /* [deg][3][3] un-normalised or NULL */);

@@ -80,6 +80,8 @@ def lib():
         L.orc_add_acoustic_sl.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
         L.orc_add_intervalley_sl.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
                                              C.c_double, C.c_int, C.c_int, _IP]
+        L.orc_add_froehlich_sl.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
+        L.orc_add_piezo_sl.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]
         L.orc_build_tables.argtypes = [C.c_void_p]
         L.orc_model_set_grain.argtypes = [C.c_void_p, C.c_double, C.c_double]
         # Froehlich family + phonon bath
@@ -267,6 +269,14 @@ class Model:
                                               phonon_energy, fs.shape[0], fs.shape[1], _ip(fs))
         assert r >= 0
         return r
+
+    def add_froehlich_sl(self, emission, valley, region, phonon_energy, coupling_const, width, qs=0.0):
+        """emcFroehlichInteraction{Absorption,Emission}SL"""
+        return self.L.orc_add_froehlich_sl(self.h, int(emission), valley, region, phonon_energy, coupling_const, width, qs)
+
+    def add_piezo_sl(self, valley, region, piezo_const, width, density_2d, v_sound, qs=0.0):
+        """emcPiezoelectricSingleLayerMechanism"""
+        return self.L.orc_add_piezo_sl(self.h, valley, region, piezo_const, width, density_2d, v_sound, qs)
 
     def add_coulomb(self, valley, region, eps_r, region_doping):
         return self.L.orc_add_coulomb(self.h, valley, region, eps_r, region_doping)

@@ -131,7 +131,7 @@ struct Args {
   std::string out = "ref.bin", material = "si", mechs = "acoustic,zero,first";
   int cells = 2, steps = 100, levels = 1000, snapEvery = 0;
   double box = 1e-7, doping = 1e23, field = 1e6, dt = 1e-16, emax = 1.0,
-         temperature = 300, grainRate = 0, grainProb = 0.5;
+         temperature = 300, grainRate = 0, grainProb = 0.5, sheetDensity = 0;
   double fdir[3] = {-1, 0, 0};
   unsigned long seed = 7;
 };
@@ -274,11 +274,17 @@ template <class PT> void buildMoS2Pilotto(PT &type, double temperature) {
 // valley with one sub-valley, two acoustic branches, and the zero-order optical mechanisms through the constructor WITHOUT a
 // sub-valley map (the sub-valley index is kept, no draw for it) and the first-order mechanisms likewise --
 // singleLayerMoS2.cpp:70-76 without the Froehlich and piezoelectric terms.
-template <class PT> void buildMoS2KaasbjergSubset(PT &type, double temperature) {
+// full = true: the whole set of singleLayerMoS2.cpp:64-77 (setKaasbjergParameter), i.e. with the Froehlich and the piezoelectric
+// mechanisms; sheetDensity > 0 screens those two by the 2-D carrier gas (the optional arguments of the example's helpers).
+template <class PT> void buildMoS2KaasbjergSubset(PT &type, double temperature, bool full = false, double sheetDensity = 0) {
   MoS2Kaasbjerg::addValleys(type);
   MoS2Kaasbjerg::addAcousticScatterMechanisms(type, {0}, temperature);
   MoS2Kaasbjerg::addZeroOrderIntervalleyScatterMechanisms(type, {0}, temperature);
   MoS2Kaasbjerg::addFirstOrderIntervalleyScatterMechanisms(type, {0}, temperature);
+  if (full) {
+    MoS2Kaasbjerg::addFroehlichScatterMechanisms(type, {0}, temperature, sheetDensity);
+    MoS2Kaasbjerg::addPiezoelectricScatterMechanisms(type, {0}, temperature, sheetDensity);
+  }
   auto &mechs = type->scatterHandler.scatterMechanisms;
   for (size_t i = 0; i < mechs.size(); i++) {
     std::unique_ptr<emcScatterMechanism<T>> inner(mechs[i].release());
@@ -333,6 +339,7 @@ int main(int argc, char **argv) {
     else if (key == "--seed") a.seed = std::stoul(val);
     else if (key == "--grain-rate") a.grainRate = std::stod(val); // emcGrainScatterMechanism, [1/s]; 0: none
     else if (key == "--grain-prob") a.grainProb = std::stod(val); // its transmission probability
+    else if (key == "--sheet-density") a.sheetDensity = std::stod(val); // mos2kf: 2-D carrier density [1/m^2] that screens
     else if (key == "--fdir")
       std::sscanf(val.c_str(), "%lf,%lf,%lf", &a.fdir[0], &a.fdir[1], &a.fdir[2]);
     else {
@@ -345,7 +352,7 @@ int main(int argc, char **argv) {
   RecordingRNG::sink() = &draws;
 
   const T h = a.box / a.cells;
-  const bool mos2 = a.material == "mos2" || a.material == "mos2k";
+  const bool mos2 = a.material == "mos2" || a.material == "mos2k" || a.material == "mos2kf";
   // mos2: one layer of 0.65 nm (singleLayerMoS2.cpp:44-45), the placeholder material and doping of :133-135
   const T boxZ = mos2 ? 0.65e-9 : a.box, hZ = mos2 ? 0.65e-9 : h;
   DeviceType device{mos2 ? emcMaterial<T>{1, 1, 1, 1, 1} : siMaterial(), {a.box, a.box, boxZ}, {h, h, hZ}, a.temperature};
@@ -359,7 +366,7 @@ int main(int argc, char **argv) {
     if (a.material == "mos2")
       buildMoS2Pilotto(types[0], a.temperature);
     else
-      buildMoS2KaasbjergSubset(types[0], a.temperature);
+      buildMoS2KaasbjergSubset(types[0], a.temperature, a.material == "mos2kf", a.sheetDensity);
   } else {
     types[0] = std::make_unique<emcElectron<T, DeviceType>>(a.levels, a.emax, false);
     if (a.material == "si")

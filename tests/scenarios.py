@@ -131,7 +131,19 @@ def build_mos2_pilotto(temperature=300.0):
     return m
 
 
-def build_mos2_kaasbjerg_subset(temperature=300.0):
+def twod_screening_wavevector(sheet_density, temperature, env_permittivity, dos_mass, degeneracy=4.0):
+    """emc2DScreening.hpp:49-62 in the reference's operation order"""
+    import math
+    Q, KB, HBAR, EPS0 = 1.60219e-19, 1.38066e-23, 1.05459e-34, 8.85419e-12
+    if sheet_density <= 0 or temperature <= 0 or dos_mass <= 0:
+        return 0.0
+    d0 = degeneracy * dos_mass / (2 * 3.14159265358979323846 * HBAR * HBAR)
+    kbt = KB * temperature
+    dndmu = d0 * (1 - math.exp(-sheet_density / (d0 * kbt)))
+    return Q * Q * dndmu / (2 * EPS0 * env_permittivity)
+
+
+def build_mos2_kaasbjerg_subset(temperature=300.0, full=False, sheet_density=0.0):
     """the part of parameterKaasbjerg.hpp whose mechanisms have device samplers (oracle/ref_bulk_driver.cpp:
     buildMoS2KaasbjergSubset): ONE parabolic single-layer valley with one sub-valley, acoustic TA / LA, zero-order LO / homopolar
     and the four first-order pairs through the constructors without a sub-valley map (emission added before absorption,
@@ -149,12 +161,22 @@ def build_mos2_kaasbjerg_subset(temperature=300.0):
     for sigma, ph in ((dp_cal * 1.9, 0.048), (dp_cal * 4.0, 0.048), (dp_cal * 5.9, 0.023), (dp_cal * 3.9, 0.029)):
         m.add_intervalley_sl(True, 0, 0, 0, sigma, rho, ph, None, order=1)
         m.add_intervalley_sl(False, 0, 0, 0, sigma, rho, ph, None, order=1)
+    if full:  # the whole set (:211-259): Froehlich absorption / emission at the LO phonon, piezoelectric TA / LA
+        qs = twod_screening_wavevector(sheet_density, temperature, 1.0, 0.48 * 9.11e-31, 4.0)
+        cc, width = dp_cal * (0.286 * 1e-10), 5.41e-10
+        m.add_froehlich_sl(False, 0, 0, 0.048, cc, width, qs)
+        m.add_froehlich_sl(True, 0, 0, 0.048, cc, width, qs)
+        m.add_piezo_sl(0, 0, 3.0e-11, width, rho, 4.2e3, qs)
+        m.add_piezo_sl(0, 0, 3.0e-11, width, rho, 6.7e3, qs)
     m.build_tables()
     return m
 
 
 def build_mos2(case):
-    return build_mos2_kaasbjerg_subset() if MOS2_CASES[case]["material"] == "mos2k" else build_mos2_pilotto()
+    a = MOS2_CASES[case]
+    if a["material"] == "mos2":
+        return build_mos2_pilotto()
+    return build_mos2_kaasbjerg_subset(full=a["material"] == "mos2kf", sheet_density=a.get("sheet-density", 0.0))
 
 
 # recorder cases of the single-layer path (oracle/_ref/ref_bulk_driver --material mos2): box = (box, box, 0.65 nm), one cell in z
@@ -165,6 +187,12 @@ MOS2_CASES = {
     "mos2_pilotto_bigdt": dict(material="mos2", cells=5, box=5e-8, field=1e7, fdir="0.6,-1,0", dt=2e-15, steps=120, seed=23),
     # one parabolic single-layer valley, the zero-order mechanisms without a sub-valley map (Kaasbjerg set, supported part)
     "mos2_kaasbjerg_subset": dict(material="mos2k", cells=5, box=5e-8, field=2e6, fdir="1,0.5,0", dt=1e-15, steps=300, seed=29),
+    # the whole Kaasbjerg set (setKaasbjergParameter): + Froehlich and piezoelectric single-layer mechanisms, unscreened as
+    # the example calls them ...
+    "mos2_kaasbjerg": dict(material="mos2kf", cells=5, box=5e-8, field=2e6, fdir="1,0.5,0", dt=1e-15, steps=300, seed=31),
+    # ... and screened by a 2-D carrier gas of 5e16 1/m^2 (the optional argument of the example's helper functions)
+    "mos2_kaasbjerg_screened": {"material": "mos2kf", "cells": 5, "box": 5e-8, "field": 2e6, "fdir": "-0.3,1,0", "dt": 1e-15,
+                                "steps": 300, "seed": 37, "sheet-density": 5e16},
 }
 MOS2_LZ = 0.65e-9
 

@@ -19,7 +19,7 @@ def box_of(a):
     return [a["box"], a["box"], MOS2_LZ]
 
 
-@pytest.mark.parametrize("case", ["mos2_pilotto", "mos2_kaasbjerg_subset"])
+@pytest.mark.parametrize("case", ["mos2_pilotto", "mos2_kaasbjerg", "mos2_kaasbjerg_screened"])
 def test_valley_constants_and_rate_tables_equal_the_reference(case):
     g = load_golden(case)
     m = build_mos2(case)
@@ -36,7 +36,7 @@ def test_valley_constants_and_rate_tables_equal_the_reference(case):
         assert np.array_equal(ts["cum"], g["cum" + key])
         assert ts["tau"] == g["tau" + key][0]
         assert [x.globalId for x in ts["mech"]] == list(g["mech" + key])
-    assert [len(ts["mech"]) for ts in sets] == ([15, 23] if case == "mos2_pilotto" else [14])
+    assert [len(ts["mech"]) for ts in sets] == ([15, 23] if case == "mos2_pilotto" else [18])
 
 
 @pytest.mark.parametrize("case", CASES)
@@ -64,8 +64,10 @@ def test_initial_ensemble_and_full_run_bit_for_bit(case):
     if a["material"] == "mos2":
         assert len(set(real[:, 3])) > 15 and (ens.valley == 1).sum() > 0  # many of the 38 mechanisms fired, Q valleys populated
     else:
-        fired = set(real[:, 3])  # 14 mechanisms in the one-valley model, ids 6-13 of first order
+        fired = set(real[:, 3])  # one-valley model: ids 6-13 first order, 14-15 Froehlich, 16-17 piezoelectric
         assert len(fired) >= 12 and len(fired & set(range(6, 14))) >= 6 and len(real) > 1000
+        if a["material"] == "mos2kf":  # (screening suppresses the long-range piezoelectric terms)
+            assert {14, 15} <= fired and len(fired & {16, 17}) >= (1 if "sheet-density" in a else 2)
     obs = res["obs"]
     cnt = obs[:, :, 2]
     with np.errstate(invalid="ignore", divide="ignore"):

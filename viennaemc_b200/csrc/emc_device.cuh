@@ -566,6 +566,51 @@ __device__ __forceinline__ double bathSampleQ(const BathView &B, int bath, doubl
   return fmax(qMin, fmin(qMax, ((double)a + frac) * B.dq));
 }
 
+// ---- long-range single-layer mechanisms (emcFroehlichInteractionSingleLayer.hpp, emcPiezoelectricSingleLayerScatterMechanism.hpp)
+// 1 / eps(q)^2, eps(q) = 1 + q_s / q  (emc2DScreening.hpp:65-76); plain IEEE operations in the reference's order
+__device__ __forceinline__ double slScreeningFactor(double q, double qs) {
+  const double eps = (q <= 0.0 || qs <= 0.0) ? 1.0 : 1.0 + qs / q;
+  return 1.0 / (eps * eps);
+}
+// weight of a deflection angle: Froehlich erfc(w q/2)^2 / (eps^2 q) with q^2 = k^2 + k'^2 - 2 k k' cos(psi) (:48-56),
+// piezoelectric erfc(w q/2)^2 / eps^2 with q = 2 k sin(theta/2) (:62-66)
+template <bool FROEHLICH>
+__device__ __forceinline__ double slAngularWeight(double angle, double k, double kPrime, double width, double qs) {
+  if constexpr (FROEHLICH) {
+    const double q2 = k * k + kPrime * kPrime - 2.0 * k * kPrime * cos(angle);
+    const double q = sqrt(q2 > 0.0 ? q2 : 0.0);
+    if (q <= 0.0) return 0.0;
+    const double ff = erfc(width * q / 2.0);
+    return ff * ff * slScreeningFactor(q, qs) / q;
+  } else {
+    const double q = 2.0 * k * sin(angle / 2.0);
+    const double ff = erfc(width * q / 2.0);
+    return ff * ff * slScreeningFactor(q, qs);
+  }
+}
+// magnitude of the deflection in [0, pi] by inversion of the 128-point cumulative sum of the weight (midpoint rule).  The
+// reference fills an array; the same running sum is formed twice here (total, then up to the target) -- identical partial sums,
+// no array in local memory.  `total` comes back so that the caller can take the degenerate branch.
+template <bool FROEHLICH>
+__device__ __forceinline__ double slRunningTotal(double k, double kPrime, double width, double qs) {
+  const double dAngle = kPi / 128;
+  double c = 0.0;
+  for (int i = 1; i <= 128; ++i) c = c + slAngularWeight<FROEHLICH>(((double)i - 0.5) * dAngle, k, kPrime, width, qs);
+  return c;
+}
+template <bool FROEHLICH>
+__device__ __forceinline__ double slInvertAngle(double target, double k, double kPrime, double width, double qs) {
+  const double dAngle = kPi / 128;
+  double below = 0.0, at = 0.0;
+  int lo = 0;
+  do { // lo: the first index with cdf[lo] >= target, or 128
+    ++lo;
+    below = at;
+    at = below + slAngularWeight<FROEHLICH>(((double)lo - 0.5) * dAngle, k, kPrime, width, qs);
+  } while (lo < 128 && at < target);
+  return ((double)lo - 1.0 + (target - below) / (at - below)) * dAngle;
+}
+
 template <bool EXACT, int RNG_MODE>
 __device__ __forceinline__ void sampleFinalState(const DevModel &model, const DevMech &mech, Particle &p,
                                                  Rng &rng, const BathView &baths) {
@@ -624,6 +669,48 @@ __device__ __forceinline__ void sampleFinalState(const DevModel &model, const De
     kx = A::mul(A::mul(kx, factor), nrm);
     ky = A::mul(A::mul(ky, factor), nrm);
     p.k = Vec3{kx, ky, 0.0};
+    break;
+  }
+  case EMCGPU_SAMPLER_SINGLE_LAYER_FROEHLICH: {
+    // emcFroehlichInteractionSingleLayer.hpp:149-168 (absorption), :273-292 (emission)
+    const DevValley &v = model.valleys[p.valley];
+    const double width = mech.param[1], qs = mech.param[2];
+    const double kI = normWaveVec<true>(v, p.energy);
+    p.energy = p.energy + mech.param[0];
+    const double kF = normWaveVec<true>(v, p.energy);
+    const double phi = atan2(p.k.y, p.k.x);
+    const double total = slRunningTotal<true>(kI, kF, width, qs);
+    double psi;
+    if (!(total > 0.0)) {
+      psi = 2.0 * kPi * uniform01(rng.raw<RNG_MODE>()); // degenerate: isotropic
+    } else {
+      const double target = uniform01(rng.raw<RNG_MODE>()) * total;
+      const double psiMag = slInvertAngle<true>(target, kI, kF, width, qs);
+      psi = (uniform01(rng.raw<RNG_MODE>()) < 0.5) ? psiMag : (2.0 * kPi - psiMag);
+    }
+    double sa, ca;
+    sincos(phi + psi, &sa, &ca);
+    p.k = Vec3{kF * ca, kF * sa, 0.0};
+    break;
+  }
+  case EMCGPU_SAMPLER_SINGLE_LAYER_PIEZOELECTRIC: {
+    // emcPiezoelectricSingleLayerScatterMechanism.hpp:110-139
+    const DevValley &v = model.valleys[p.valley];
+    const double width = mech.param[1], qs = mech.param[2];
+    const double k = normWaveVec<true>(v, p.energy);
+    const double total = slRunningTotal<false>(k, k, width, qs);
+    const double phi = atan2(p.k.y, p.k.x);
+    double theta;
+    if (!(total > 0.0)) {
+      theta = kPi * uniform01(rng.raw<RNG_MODE>());
+    } else {
+      const double target = uniform01(rng.raw<RNG_MODE>()) * total;
+      theta = slInvertAngle<false>(target, k, k, width, qs);
+    }
+    if (uniform01(rng.raw<RNG_MODE>()) < 0.5) theta = -theta; // left / right
+    double sa, ca;
+    sincos(phi + theta, &sa, &ca);
+    p.k = Vec3{k * ca, k * sa, 0.0};
     break;
   }
   case EMCGPU_SAMPLER_COULOMB: {

@@ -41,7 +41,7 @@ struct DevValley {
 
 struct DevMech {
   int32_t sampler, finalValley, nFinal, mechId;
-  double param[2];
+  double param[3]; // [0]: energy change / Debye energy; [1], [2]: sampler specific (include/emcgpu.h)
   int32_t bath;  // phonon bath of a polar-optical mechanism or -1
   int32_t flags; // bit 0: polar angle through the bath's |q| distribution
   uint8_t finalSub[EMCGPU_MAX_SUBVALLEYS][EMCGPU_MAX_FINAL];

@@ -684,7 +684,7 @@ int emcgpu_set_tables(emcgpu_ctx *ctx, const emcgpu_tableset_t *sets, int nSets,
       char name[EMCGPU_NAME_LEN + 1];
       memcpy(name, mi.name, EMCGPU_NAME_LEN);
       name[EMCGPU_NAME_LEN] = 0;
-      if (mi.sampler <= EMCGPU_SAMPLER_NONE || mi.sampler > EMCGPU_SAMPLER_SINGLE_LAYER_INTERVALLEY)
+      if (mi.sampler <= EMCGPU_SAMPLER_NONE || mi.sampler > EMCGPU_SAMPLER_SINGLE_LAYER_PIEZOELECTRIC)
         return fail(ctx, EMCGPU_E_UNSUPPORTED_MECHANISM,
                     "scatter mechanism '%s' (valley %d, region %d) has no device sampler; it cannot run on "
                     "the GPU path and there is no CPU fallback",
@@ -697,6 +697,7 @@ int emcgpu_set_tables(emcgpu_ctx *ctx, const emcgpu_tableset_t *sets, int nSets,
       d.mechId = mi.mechId;
       d.param[0] = mi.param[0];
       d.param[1] = mi.param[1];
+      d.param[2] = mi.param[2];
       d.bath = -1;
       if (mi.sampler == EMCGPU_SAMPLER_FROEHLICH || mi.sampler == EMCGPU_SAMPLER_SCREENED_FROEHLICH) {
         d.bath = mi.param[2] >= 0 ? (int32_t)mi.param[2] : -1;
