@@ -126,7 +126,22 @@ typedef enum {
   EMCGPU_SAMPLER_SINGLE_LAYER_FROEHLICH = 8,
   /* emcPiezoelectricSingleLayerScatterMechanism.hpp:110-139: elastic; deflection theta by the same inversion with the weight
    * erfc(w q/2)^2 / eps(q)^2, q = 2 k sin(theta/2); param[1], param[2] as above */
-  EMCGPU_SAMPLER_SINGLE_LAYER_PIEZOELECTRIC = 9
+  EMCGPU_SAMPLER_SINGLE_LAYER_PIEZOELECTRIC = 9,
+  /* The four other angle-resolved single-layer mechanisms share one final state: E += dE (elastic: unchanged), the in-plane
+   * direction of k is turned by +-angle, |k| <- k_norm(E'), k_z = 0; the magnitude of the angle by inversion of an N-point
+   * cumulative sum (midpoint rule on [0, pi]) of the mechanism's weight, pi u if the sum vanishes; one more draw for the side.
+   * q = 2 k sin(angle/2) (elastic) or q^2 = k^2 + k'^2 - 2 k k' cos(angle); eps(q) = 1 + q_s/q; param[2] = q_s [1/m] in all.
+   * emc2DChargedImpurityScatterMechanism.hpp:65-72, :107-139: elastic, N = 512, weight (exp(-q d) / (q_s + q + r0 q^2))^2;
+   * param[0] = d [m] (impurity-to-sheet distance), param[1] = r0 [m] (Rytova-Keldysh length) */
+  EMCGPU_SAMPLER_SINGLE_LAYER_CHARGED_IMPURITY = 10,
+  /* emcSurfaceRoughnessScatterMechanism.hpp:59-63, :94-126: elastic, N = 256, weight exp(-q^2 Lambda^2/4) / eps(q)^2;
+   * param[1] = Lambda^2 [m^2] */
+  EMCGPU_SAMPLER_SINGLE_LAYER_SURFACE_ROUGHNESS = 11,
+  /* emcRemoteSurfaceOpticalPhononMechanism.hpp:63-70, :112-149: param[0] = signed phonon energy, N = 128, weight
+   * exp(-2 q d) / (q eps(q)^2); param[1] = d [m] (carrier-to-surface distance) */
+  EMCGPU_SAMPLER_SINGLE_LAYER_REMOTE_SO = 12,
+  /* emcScreenedIntravalleyOpticalMechanism.hpp:58-62, :104-141: param[0] = signed phonon energy, N = 128, weight 1/eps(q)^2 */
+  EMCGPU_SAMPLER_SINGLE_LAYER_SCREENED_OPTICAL = 13
 } emcgpu_sampler_id;
 #define EMCGPU_MAX_BATHS 8
 

@@ -285,7 +285,8 @@ void orc_random_direction_wrt_k(const double k[3], double cosTheta, double rnd, 
 }
 
 /* ------------------------------------------------------------------ model */
-enum { MK_ACOUSTIC = 1, MK_ZERO = 2, MK_FIRST = 3, MK_COULOMB = 4, MK_FROEHLICH = 5, MK_ACOUSTIC_SL = 6, MK_ZERO_SL = 7, MK_FIRST_SL = 8, MK_FROEHLICH_SL = 9, MK_PIEZO_SL = 10 };
+enum { MK_ACOUSTIC = 1, MK_ZERO = 2, MK_FIRST = 3, MK_COULOMB = 4, MK_FROEHLICH = 5, MK_ACOUSTIC_SL = 6, MK_ZERO_SL = 7, MK_FIRST_SL = 8, MK_FROEHLICH_SL = 9, MK_PIEZO_SL = 10,
+       MK_IMPURITY_SL = 11, MK_ROUGHNESS_SL = 12, MK_REMOTE_SO_SL = 13, MK_SCREENED_OPTICAL_SL = 14 };
 
 typedef struct {
   int kind, valley, finalValley, region, emission, nFinal, nInitSub;
@@ -296,6 +297,8 @@ typedef struct {
   double effMass, nBose;
   /* long-range single-layer mechanisms: form-factor width [m], 2-D screening wave vector [1/m] */
   double slWidth, slQs;
+  /* the other angle-resolved single-layer mechanisms: sl[0], sl[1] as documented at ORC_SAMPLER_SL_CHARGED_IMPURITY ... */
+  double sl[2];
 } mech_t;
 
 /* emcPhononBath.hpp */
@@ -592,6 +595,104 @@ int orc_add_piezo_sl(orc_model_t *m, int valley, int region, double piezoConst, 
   return m->nMech++;
 }
 
+/* ---- the other angle-resolved single-layer mechanisms.  Weights: emc2DChargedImpurityScatterMechanism.hpp:65-72,
+ * emcSurfaceRoughnessScatterMechanism.hpp:59-63, emcRemoteSurfaceOpticalPhononMechanism.hpp:63-70,
+ * emcScreenedIntravalleyOpticalMechanism.hpp:58-62.  par = {p0, p1, q_s} as in the sampler description (emc_oracle.h) */
+static int sl_angular_steps(int sampler) {
+  return sampler == ORC_SAMPLER_SL_CHARGED_IMPURITY ? 512 : sampler == ORC_SAMPLER_SL_SURFACE_ROUGHNESS ? 256 : 128;
+}
+static double sl_angular_weight(int sampler, double theta, double k, double kPrime, const double *par) {
+  switch (sampler) {
+  case ORC_SAMPLER_SL_CHARGED_IMPURITY: {
+    double q = 2 * k * sin(theta / 2);
+    double denom = par[2] + q + par[1] * q * q;
+    if (denom <= 0)
+      return 0;
+    double v = exp(-q * par[0]) / denom;
+    return v * v;
+  }
+  case ORC_SAMPLER_SL_SURFACE_ROUGHNESS: {
+    double q = 2 * k * sin(theta / 2);
+    double formFactor = exp(-q * q * par[1] / 4);
+    return formFactor * sl_screening_factor(q, par[2]);
+  }
+  case ORC_SAMPLER_SL_REMOTE_SO: {
+    double q2 = k * k + kPrime * kPrime - 2 * k * kPrime * cos(theta);
+    double q = sqrt(q2 > 0 ? q2 : 0);
+    if (q <= 0)
+      return 0;
+    return exp(-2 * q * par[1]) * sl_screening_factor(q, par[2]) / q;
+  }
+  default: { /* ORC_SAMPLER_SL_SCREENED_OPTICAL */
+    double q2 = k * k + kPrime * kPrime - 2 * k * kPrime * cos(theta);
+    double q = sqrt(q2 > 0 ? q2 : 0);
+    return sl_screening_factor(q, par[2]);
+  }
+  }
+}
+static int sl_angular_sampler_of(int kind) {
+  return kind == MK_IMPURITY_SL ? ORC_SAMPLER_SL_CHARGED_IMPURITY : kind == MK_ROUGHNESS_SL ? ORC_SAMPLER_SL_SURFACE_ROUGHNESS
+         : kind == MK_REMOTE_SO_SL ? ORC_SAMPLER_SL_REMOTE_SO : ORC_SAMPLER_SL_SCREENED_OPTICAL;
+}
+static mech_t *sl_new_mech(orc_model_t *m, int kind, int valley, int region) {
+  mech_t *x = &m->mech[m->nMech];
+  memset(x, 0, sizeof *x);
+  x->kind = kind;
+  x->valley = x->finalValley = valley;
+  x->region = region;
+  return x;
+}
+/* emc2DChargedImpurityScatterMechanism.hpp:77-92 */
+int orc_add_charged_impurity_sl(orc_model_t *m, int valley, int region, double impurityDensity, double epsAvg, double qs,
+                                double rytovaKeldyshLength, double remoteDistance, double chargeNumber) {
+  mech_t *x = sl_new_mech(m, MK_IMPURITY_SL, valley, region);
+  x->sl[0] = remoteDistance;
+  x->sl[1] = rytovaKeldyshLength;
+  x->slQs = qs;
+  double A = chargeNumber * C_Q * C_Q / (2 * C_EPS0 * epsAvg);
+  x->scatterConst = impurityDensity * A * A / (C_PI * pow(C_HBAR, 3));
+  return m->nMech++;
+}
+/* emcSurfaceRoughnessScatterMechanism.hpp:68-79 */
+int orc_add_surface_roughness_sl(orc_model_t *m, int valley, int region, double effectiveField, double roughnessAmplitude,
+                                 double correlationLength, double qs) {
+  mech_t *x = sl_new_mech(m, MK_ROUGHNESS_SL, valley, region);
+  x->sl[1] = correlationLength * correlationLength;
+  x->slQs = qs;
+  double eF = C_Q * effectiveField;
+  x->scatterConst = eF * eF * roughnessAmplitude * roughnessAmplitude * x->sl[1] / pow(C_HBAR, 3);
+  return m->nMech++;
+}
+/* emcRemoteSurfaceOpticalPhononMechanism.hpp:75-91 */
+int orc_add_remote_so_sl(orc_model_t *m, int emission, int valley, int region, double phE, double couplingD,
+                         double remoteDistance, double qs) {
+  mech_t *x = sl_new_mech(m, MK_REMOTE_SO_SL, valley, region);
+  x->emission = emission;
+  x->phononEnergy = phE;
+  x->sl[1] = remoteDistance;
+  x->slQs = qs;
+  double omega = phE * C_Q / C_HBAR;
+  double C = C_Q * C_Q * omega * couplingD / (4 * C_PI * C_EPS0 * C_HBAR * C_HBAR);
+  double xx = phE * C_Q / (C_KB * m->temperature);
+  double nBose = 1. / (exp(xx) - 1.);
+  x->scatterConst = C * (emission ? nBose + 1 : nBose);
+  return m->nMech++;
+}
+/* emcScreenedIntravalleyOpticalMechanism.hpp:67-81 */
+int orc_add_screened_optical_sl(orc_model_t *m, int emission, int valley, int region, double sigma, double density2D, double phE,
+                                double qs) {
+  mech_t *x = sl_new_mech(m, MK_SCREENED_OPTICAL_SL, valley, region);
+  x->emission = emission;
+  x->phononEnergy = phE;
+  x->slQs = qs;
+  double xx = phE * C_Q / (C_KB * m->temperature);
+  double omega = phE * C_Q / C_HBAR;
+  double nBose = 1. / (exp(xx) - 1.);
+  double nFactor = emission ? nBose + 1 : nBose;
+  x->scatterConst = pow(sigma * C_Q / C_HBAR, 2) * nFactor / (2 * density2D * omega);
+  return m->nMech++;
+}
+
 /* emcCoulombScatterMechanism.hpp:23-32 */
 int orc_add_coulomb(orc_model_t *m, int valley, int region, double epsR, double regionDoping) {
   mech_t *x = &m->mech[m->nMech];
@@ -717,6 +818,50 @@ double orc_raw_rate(const orc_model_t *m, int g, double energy) {
       integral = sl_froehlich_integral(0, 0., 2 * C_PI, 10000, k, eFactor, x->slWidth, x->slQs);
     }
     return integral * x->scatterConst * md;
+  }
+  case MK_IMPURITY_SL:   /* emc2DChargedImpurityScatterMechanism.hpp:96-105 */
+  case MK_ROUGHNESS_SL: { /* emcSurfaceRoughnessScatterMechanism.hpp:83-92 */
+    const int sampler = sl_angular_sampler_of(x->kind), n = sl_angular_steps(sampler);
+    const double par[3] = {x->sl[0], x->sl[1], x->slQs};
+    double mc = orc_eff_mass_cond(vi, energy);
+    double k = orc_norm_wave_vec(vi, energy);
+    double dtheta = C_PI / n;
+    double integral = 0;
+    for (int i = 0; i < n; ++i)
+      integral += sl_angular_weight(sampler, (i + 0.5) * dtheta, k, k, par);
+    integral *= dtheta;
+    return x->scatterConst * mc * integral;
+  }
+  case MK_REMOTE_SO_SL: { /* emcRemoteSurfaceOpticalPhononMechanism.hpp:97-110 */
+    if (x->emission && energy <= x->phononEnergy)
+      return 0;
+    const double par[3] = {0, x->sl[1], x->slQs};
+    double finalEnergy = x->emission ? energy - x->phononEnergy : energy + x->phononEnergy;
+    double k = orc_norm_wave_vec(vi, energy);
+    double kPrime = orc_norm_wave_vec(vi, finalEnergy);
+    double mc = orc_eff_mass_cond(vi, finalEnergy);
+    double dtheta = C_PI / 128;
+    double integral = 0;
+    for (int i = 0; i < 128; ++i)
+      integral += sl_angular_weight(ORC_SAMPLER_SL_REMOTE_SO, (i + 0.5) * dtheta, k, kPrime, par);
+    integral *= dtheta;
+    return 2 * x->scatterConst * mc * integral;
+  }
+  case MK_SCREENED_OPTICAL_SL: { /* emcScreenedIntravalleyOpticalMechanism.hpp:88-102 */
+    if (x->emission && energy <= x->phononEnergy)
+      return 0;
+    const double par[3] = {0, 0, x->slQs};
+    double finalEnergy = x->emission ? energy - x->phononEnergy : energy + x->phononEnergy;
+    double md = dos_mass_at_zero(vi);
+    double alpha = vi->alpha;
+    double k = orc_norm_wave_vec(vi, energy);
+    double kPrime = orc_norm_wave_vec(vi, finalEnergy);
+    double dtheta = C_PI / 128;
+    double screenAvg = 0;
+    for (int i = 0; i < 128; ++i)
+      screenAvg += sl_angular_weight(ORC_SAMPLER_SL_SCREENED_OPTICAL, (i + 0.5) * dtheta, k, kPrime, par);
+    screenAvg /= 128;
+    return md * x->scatterConst * (1 + 2 * alpha * finalEnergy) * screenAvg;
   }
   case MK_PIEZO_SL: { /* emcPiezoelectricSingleLayerScatterMechanism.hpp:92-105 */
     double md = dos_mass_at_zero(vi);
@@ -903,6 +1048,16 @@ static void fill_mech_desc(const orc_model_t *m, int g, orc_mech_t *d) {
     d->sampler = ORC_SAMPLER_SL_FROEHLICH;
     d->p[0] = x->emission ? -x->phononEnergy : x->phononEnergy;
     d->p[1] = x->slWidth;
+    d->p[2] = x->slQs;
+    break;
+  case MK_IMPURITY_SL:
+  case MK_ROUGHNESS_SL:
+  case MK_REMOTE_SO_SL:
+  case MK_SCREENED_OPTICAL_SL:
+    d->sampler = sl_angular_sampler_of(x->kind);
+    d->p[0] = (x->kind == MK_REMOTE_SO_SL || x->kind == MK_SCREENED_OPTICAL_SL) ? (x->emission ? -x->phononEnergy : x->phononEnergy)
+                                                                               : x->sl[0];
+    d->p[1] = x->sl[1];
     d->p[2] = x->slQs;
     break;
   case MK_PIEZO_SL:
@@ -1099,6 +1254,44 @@ static void scatter_with(const orc_model_t *m, const orc_mech_t *d, orc_ensemble
     }
     out[0] = kF * cos(angle);
     out[1] = kF * sin(angle);
+    out[2] = 0;
+    break;
+  }
+  case ORC_SAMPLER_SL_CHARGED_IMPURITY:
+  case ORC_SAMPLER_SL_SURFACE_ROUGHNESS:
+  case ORC_SAMPLER_SL_REMOTE_SO:
+  case ORC_SAMPLER_SL_SCREENED_OPTICAL: {
+    /* emc2DChargedImpurityScatterMechanism.hpp:107-139, emcSurfaceRoughnessScatterMechanism.hpp:94-126,
+     * emcRemoteSurfaceOpticalPhononMechanism.hpp:112-149, emcScreenedIntravalleyOpticalMechanism.hpp:104-141 */
+    const orc_valley_t *v = &m->valleys[e->valley[p]];
+    const int inelastic = d->sampler == ORC_SAMPLER_SL_REMOTE_SO || d->sampler == ORC_SAMPLER_SL_SCREENED_OPTICAL;
+    const int n = sl_angular_steps(d->sampler);
+    double kI = orc_norm_wave_vec(v, e->energy[p]), kF = kI;
+    if (inelastic) {
+      e->energy[p] = e->energy[p] + d->p[0];
+      kF = orc_norm_wave_vec(v, e->energy[p]);
+    }
+    double cdf[513];
+    const double dtheta = C_PI / n;
+    cdf[0] = 0;
+    for (int i = 1; i <= n; ++i)
+      cdf[i] = cdf[i - 1] + sl_angular_weight(d->sampler, (i - 0.5) * dtheta, kI, kF, d->p);
+    const double total = cdf[n];
+    double phi = atan2(k[1], k[0]);
+    double theta;
+    if (!(total > 0)) {
+      theta = C_PI * rng_u01(rng);
+    } else {
+      double target = rng_u01(rng) * total;
+      int lo = 1;
+      while (lo < n && cdf[lo] < target)
+        ++lo;
+      theta = ((double)lo - 1 + (target - cdf[lo - 1]) / (cdf[lo] - cdf[lo - 1])) * dtheta;
+    }
+    if (rng_u01(rng) < 0.5)
+      theta = -theta;
+    out[0] = kF * cos(phi + theta);
+    out[1] = kF * sin(phi + theta);
     out[2] = 0;
     break;
   }

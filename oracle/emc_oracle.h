@@ -50,7 +50,17 @@ enum { ORC_SAMPLER_NONE = 0, ORC_SAMPLER_ISOTROPIC_ELASTIC = 1,
         * erfc(w q/2)^2 / (eps(q)^2 q), q^2 = k^2 + k'^2 - 2 k k' cos(psi); p[1] = form-factor width w, p[2] = screening q_s */
        ORC_SAMPLER_SL_FROEHLICH = 8,
        /* emcPiezoelectricSingleLayerScatterMechanism.hpp:110-139: elastic; weight erfc(w q/2)^2 / eps(q)^2, q = 2 k sin(theta/2) */
-       ORC_SAMPLER_SL_PIEZO = 9 };
+       ORC_SAMPLER_SL_PIEZO = 9,
+       /* one final state for four mechanisms: E += dE (elastic: none), in-plane direction turned by +-angle, the magnitude by
+        * inversion of an N-point cumulative sum of the weight (pi u if the sum vanishes), one more draw for the side; p[2] = q_s.
+        * emc2DChargedImpurityScatterMechanism.hpp:107-139: elastic, N = 512, (exp(-q d) / (q_s + q + r0 q^2))^2; p[0] = d, p[1] = r0 */
+       ORC_SAMPLER_SL_CHARGED_IMPURITY = 10,
+       /* emcSurfaceRoughnessScatterMechanism.hpp:94-126: elastic, N = 256, exp(-q^2 Lambda^2/4) / eps(q)^2; p[1] = Lambda^2 */
+       ORC_SAMPLER_SL_SURFACE_ROUGHNESS = 11,
+       /* emcRemoteSurfaceOpticalPhononMechanism.hpp:112-149: p[0] = signed phonon energy, N = 128, exp(-2 q d) / (q eps^2); p[1] = d */
+       ORC_SAMPLER_SL_REMOTE_SO = 12,
+       /* emcScreenedIntravalleyOpticalMechanism.hpp:104-141: p[0] = signed phonon energy, N = 128, 1 / eps(q)^2 */
+       ORC_SAMPLER_SL_SCREENED_OPTICAL = 13 };
 
 enum { ORC_RNG_MT_GLOBAL = 0, ORC_RNG_STREAMS = 1, ORC_RNG_PHILOX = 2 };
 
@@ -103,6 +113,14 @@ int orc_add_froehlich_sl(orc_model_t *m, int emission, int valley, int region, d
                          double qs);
 int orc_add_piezo_sl(orc_model_t *m, int valley, int region, double piezoConst, double width, double density2D, double vSound,
                      double qs);
+int orc_add_charged_impurity_sl(orc_model_t *m, int valley, int region, double impurityDensity, double epsAvg, double qs,
+                                double rytovaKeldyshLength, double remoteDistance, double chargeNumber);
+int orc_add_surface_roughness_sl(orc_model_t *m, int valley, int region, double effectiveField, double roughnessAmplitude,
+                                 double correlationLength, double qs);
+int orc_add_remote_so_sl(orc_model_t *m, int emission, int valley, int region, double phE, double couplingD,
+                         double remoteDistance, double qs);
+int orc_add_screened_optical_sl(orc_model_t *m, int emission, int valley, int region, double sigma, double density2D, double phE,
+                                double qs);
 int orc_add_valley(orc_model_t *m, int kind, const double relMass[3],
                    double particleMass, int deg, double alpha, double eBottom,
                    const double *dirs /* [deg][3][3] un-normalised or NULL */);

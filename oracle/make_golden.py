@@ -68,12 +68,15 @@ def main():
               "draws", n_draws, "events", n_events)
 
 
-def main_mos2():
-    """single-layer MoS2 (examples/singleLayerMoS2, Pilotto parameter set) through the same recorder"""
+def main_mos2(only=None):
+    """single-layer MoS2 (examples/singleLayerMoS2: Pilotto and Kaasbjerg parameter sets, the optional extrinsic mechanisms)
+    through the same recorder; only: comma-separated case names (third command-line argument)"""
     import hashlib
     subprocess.check_call(["make", "-C", HERE, "_ref/ref_bulk_driver"], stdout=subprocess.DEVNULL)
     drv = os.path.join(HERE, "_ref", "ref_bulk_driver")
     for name, args in MOS2_CASES.items():
+        if only and name not in only.split(","):
+            continue
         with tempfile.TemporaryDirectory() as tmp:
             out = os.path.join(tmp, "ref.bin")
             cmd = [drv, "--out", out]
@@ -193,4 +196,4 @@ if __name__ == "__main__":
     if which in ("all", "mhp"):
         main_mhp()
     if which in ("all", "mos2"):
-        main_mos2()
+        main_mos2(sys.argv[2] if len(sys.argv) > 2 else None)

@@ -17,31 +17,53 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 RUNS = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-FIELDS = (200000, 4000000)
+# second argument "kaasbjerg": the example with its Kaasbjerg parameter set and ONE field (its CUSTOM list), see oracle/Makefile
+KAASBJERG = len(sys.argv) > 2 and sys.argv[2] == "kaasbjerg"
+FIELDS = (4000000,) if KAASBJERG else (200000, 4000000)
 
 
 def summary(work, field, n=20808):
     tag = f"E{field}T300N{n}.txt"
-    e = np.loadtxt(os.path.join(work, "singleLayerMoS2AvgEnergy" + tag))[-10000:, 1:]
-    v = np.loadtxt(os.path.join(work, "singleLayerMoS2AvgDriftVelocity" + tag))[-10000:, 1:]
-    o = np.loadtxt(os.path.join(work, "singleLayerMoS2valleyOccupation" + tag))[-10000:, 1:]
+    e = np.loadtxt(os.path.join(work, "singleLayerMoS2AvgEnergy" + tag), ndmin=2)[-10000:, 1:]
+    v = np.loadtxt(os.path.join(work, "singleLayerMoS2AvgDriftVelocity" + tag), ndmin=2)[-10000:, 1:]
+    o = np.loadtxt(os.path.join(work, "singleLayerMoS2valleyOccupation" + tag), ndmin=2)[-10000:, 1:]
     return dict(energy=[float(x) for x in e.mean(0)], drift=[float(x) for x in v.mean(0)], occupation=[float(x) for x in o.mean(0)],
                 energy_all=float((e * o).sum(1).mean()), drift_all=float((v * o).sum(1).mean()))
 
 
+def rate_files(work):
+    """the per-mechanism rate files the scatter handler writes ("<name><valley><region>ScatterMechanism.txt": energy, rate):
+    every 50th of the 5000 levels, as printed (6 significant digits)"""
+    out = {}
+    for name in sorted(os.listdir(work)):
+        if name.endswith("ScatterMechanism.txt"):
+            out[name] = [float(x) for x in np.loadtxt(os.path.join(work, name))[::50, 1]]
+    return out
+
+
 def main():
-    subprocess.check_call(["make", "-C", HERE, "_ref/ref_singleLayerMoS2_two_fields"], stdout=subprocess.DEVNULL)
-    exe = os.path.join(HERE, "_ref", "ref_singleLayerMoS2_two_fields")
-    runs = []
+    name = "ref_singleLayerMoS2_kaasbjerg" if KAASBJERG else "ref_singleLayerMoS2_two_fields"
+    subprocess.check_call(["make", "-C", HERE, "_ref/" + name], stdout=subprocess.DEVNULL)
+    exe = os.path.join(HERE, "_ref", name)
+    runs, rates = [], None
     for r in range(RUNS):
         with tempfile.TemporaryDirectory() as work:
             subprocess.check_call([exe], cwd=work, stdout=subprocess.DEVNULL)
             runs.append({str(f): summary(work, f) for f in FIELDS})
+            rates = rates or rate_files(work)
         print(r, runs[-1], flush=True)
-    out = dict(config="examples/singleLayerMoS2/singleLayerMoS2.cpp with the field list shortened to {2e5, 4e6} V/m (20808 e-, "
-                      "Pilotto parameters, dt 1e-16 s, 20000 steps per field, 4 OpenMP threads, clock seed); means over the last 1 ps",
-               n_runs=RUNS, fields=list(FIELDS), runs=runs)
-    with open(os.path.join(ROOT, "tests", "golden", "ref_mos2_stats.json"), "w") as f:
+    if KAASBJERG:
+        config = ("examples/singleLayerMoS2/singleLayerMoS2.cpp with selectedPaperForParameter = KAASBJERG and appliedFields = CUSTOM "
+                  "(one field, 4e6 V/m): 20808 e-, one parabolic single-layer valley, acoustic + zero- and first-order intervalley + "
+                  "Froehlich + piezoelectric single-layer mechanisms, dt 1e-16 s, 20000 steps, 4 OpenMP threads, clock seed; means "
+                  "over the last 1 ps")
+    else:
+        config = ("examples/singleLayerMoS2/singleLayerMoS2.cpp with the field list shortened to {2e5, 4e6} V/m (20808 e-, "
+                  "Pilotto parameters, dt 1e-16 s, 20000 steps per field, 4 OpenMP threads, clock seed); means over the last 1 ps")
+    out = dict(config=config, n_runs=RUNS, fields=list(FIELDS), runs=runs)
+    if KAASBJERG:
+        out["rate_files_every_50th_level"] = rates
+    with open(os.path.join(ROOT, "tests", "golden", "ref_mos2k_stats.json" if KAASBJERG else "ref_mos2_stats.json"), "w") as f:
         json.dump(out, f, indent=1)
 
 

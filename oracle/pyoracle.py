@@ -82,6 +82,10 @@ def lib():
                                              C.c_double, C.c_int, C.c_int, _IP]
         L.orc_add_froehlich_sl.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
         L.orc_add_piezo_sl.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]
+        L.orc_add_charged_impurity_sl.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_double] * 6
+        L.orc_add_surface_roughness_sl.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_double] * 4
+        L.orc_add_remote_so_sl.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_double] * 4
+        L.orc_add_screened_optical_sl.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_double] * 4
         L.orc_build_tables.argtypes = [C.c_void_p]
         L.orc_model_set_grain.argtypes = [C.c_void_p, C.c_double, C.c_double]
         # Froehlich family + phonon bath
@@ -277,6 +281,24 @@ class Model:
     def add_piezo_sl(self, valley, region, piezo_const, width, density_2d, v_sound, qs=0.0):
         """emcPiezoelectricSingleLayerMechanism"""
         return self.L.orc_add_piezo_sl(self.h, valley, region, piezo_const, width, density_2d, v_sound, qs)
+
+    def add_charged_impurity_sl(self, valley, region, impurity_density, eps_avg, qs, rytova_keldysh_length=0.0, remote_distance=0.0,
+                                charge_number=1.0):
+        """emc2DChargedImpurityScatterMechanism.hpp"""
+        return self.L.orc_add_charged_impurity_sl(self.h, valley, region, impurity_density, eps_avg, qs, rytova_keldysh_length,
+                                                  remote_distance, charge_number)
+
+    def add_surface_roughness_sl(self, valley, region, effective_field, roughness_amplitude, correlation_length, qs):
+        """emcSurfaceRoughnessScatterMechanism.hpp"""
+        return self.L.orc_add_surface_roughness_sl(self.h, valley, region, effective_field, roughness_amplitude, correlation_length, qs)
+
+    def add_remote_so_sl(self, emission, valley, region, phonon_energy, coupling_d, remote_distance, qs=0.0):
+        """emcRemoteSurfaceOpticalPhononMechanism.hpp"""
+        return self.L.orc_add_remote_so_sl(self.h, int(emission), valley, region, phonon_energy, coupling_d, remote_distance, qs)
+
+    def add_screened_optical_sl(self, emission, valley, region, sigma, density_2d, phonon_energy, qs=0.0):
+        """emcScreenedIntravalleyOpticalMechanism.hpp"""
+        return self.L.orc_add_screened_optical_sl(self.h, int(emission), valley, region, sigma, density_2d, phonon_energy, qs)
 
     def add_coulomb(self, valley, region, eps_r, region_doping):
         return self.L.orc_add_coulomb(self.h, valley, region, eps_r, region_doping)

@@ -259,10 +259,12 @@ void buildMixed(PT &type, DeviceType &device, const std::string &mechs) {
 // set (Pilotto: K valleys isotropic, Q valleys anisotropic with in-plane frames, acoustic + zero-order intervalley
 // mechanisms of the single-layer classes).  The mechanisms are added by the example's own helper functions; the logging
 // decorators are put around them afterwards (private vector, -fno-access-control).
-template <class PT> void buildMoS2Pilotto(PT &type, double temperature) {
+// sheetDensity > 0 (material mos2ps): the K -> K Gamma-phonon pair is the free-carrier-screened class
+// (emcScreenedIntravalleyOpticalMechanism, parameterPilotto.hpp:114-131), the optional argument of the example's helper.
+template <class PT> void buildMoS2Pilotto(PT &type, double temperature, double sheetDensity = 0) {
   MoS2Pilotto::addValleys(type);
   MoS2Pilotto::addAcousticScatterMechanisms(type, {0}, temperature);
-  MoS2Pilotto::addZeroOrderIntervalleyScatterMechanisms(type, {0}, temperature);
+  MoS2Pilotto::addZeroOrderIntervalleyScatterMechanisms(type, {0}, temperature, sheetDensity);
   auto &mechs = type->scatterHandler.scatterMechanisms;
   for (size_t i = 0; i < mechs.size(); i++) {
     std::unique_ptr<emcScatterMechanism<T>> inner(mechs[i].release());
@@ -276,7 +278,10 @@ template <class PT> void buildMoS2Pilotto(PT &type, double temperature) {
 // singleLayerMoS2.cpp:70-76 without the Froehlich and piezoelectric terms.
 // full = true: the whole set of singleLayerMoS2.cpp:64-77 (setKaasbjergParameter), i.e. with the Froehlich and the piezoelectric
 // mechanisms; sheetDensity > 0 screens those two by the 2-D carrier gas (the optional arguments of the example's helpers).
-template <class PT> void buildMoS2KaasbjergSubset(PT &type, double temperature, bool full = false, double sheetDensity = 0) {
+// supported = true (material mos2kx): a supported, doped film -- the example's three OPTIONAL extrinsic helpers on top of the whole
+// set (parameterKaasbjerg.hpp:272-351): charged impurities (1e16 1/m^2, eps_avg 4), interface roughness and the two remote
+// surface-optical modes of HfO2 (the helper's own table: eps_inf 5.03, eps_0 23, 12.4 / 48.4 meV), screened by sheetDensity.
+template <class PT> void buildMoS2KaasbjergSubset(PT &type, double temperature, bool full = false, double sheetDensity = 0, bool supported = false) {
   MoS2Kaasbjerg::addValleys(type);
   MoS2Kaasbjerg::addAcousticScatterMechanisms(type, {0}, temperature);
   MoS2Kaasbjerg::addZeroOrderIntervalleyScatterMechanisms(type, {0}, temperature);
@@ -284,6 +289,11 @@ template <class PT> void buildMoS2KaasbjergSubset(PT &type, double temperature, 
   if (full) {
     MoS2Kaasbjerg::addFroehlichScatterMechanisms(type, {0}, temperature, sheetDensity);
     MoS2Kaasbjerg::addPiezoelectricScatterMechanisms(type, {0}, temperature, sheetDensity);
+  }
+  if (supported) {
+    MoS2Kaasbjerg::addChargedImpurityScatterMechanism(type, {0}, temperature, 1e16, sheetDensity, 4.0);
+    MoS2Kaasbjerg::addSurfaceRoughnessScatterMechanism(type, {0}, temperature, sheetDensity, 4.0);
+    MoS2Kaasbjerg::addRemoteSurfaceOpticalPhonon(type, {0}, temperature, sheetDensity, 5.03, 23.0, 0.0124, 0.0484);
   }
   auto &mechs = type->scatterHandler.scatterMechanisms;
   for (size_t i = 0; i < mechs.size(); i++) {
@@ -352,7 +362,7 @@ int main(int argc, char **argv) {
   RecordingRNG::sink() = &draws;
 
   const T h = a.box / a.cells;
-  const bool mos2 = a.material == "mos2" || a.material == "mos2k" || a.material == "mos2kf";
+  const bool mos2 = a.material == "mos2" || a.material == "mos2ps" || a.material == "mos2k" || a.material == "mos2kf" || a.material == "mos2kx";
   // mos2: one layer of 0.65 nm (singleLayerMoS2.cpp:44-45), the placeholder material and doping of :133-135
   const T boxZ = mos2 ? 0.65e-9 : a.box, hZ = mos2 ? 0.65e-9 : h;
   DeviceType device{mos2 ? emcMaterial<T>{1, 1, 1, 1, 1} : siMaterial(), {a.box, a.box, boxZ}, {h, h, hZ}, a.temperature};
@@ -363,10 +373,10 @@ int main(int argc, char **argv) {
     types[0] = std::make_unique<electron2D<T, DeviceType>>(); // 5000 levels up to 0.5 eV, 4 particles per grid point
     a.levels = 5000;
     a.emax = 0.5;
-    if (a.material == "mos2")
-      buildMoS2Pilotto(types[0], a.temperature);
+    if (a.material == "mos2" || a.material == "mos2ps")
+      buildMoS2Pilotto(types[0], a.temperature, a.material == "mos2ps" ? a.sheetDensity : 0);
     else
-      buildMoS2KaasbjergSubset(types[0], a.temperature, a.material == "mos2kf", a.sheetDensity);
+      buildMoS2KaasbjergSubset(types[0], a.temperature, a.material != "mos2k", a.sheetDensity, a.material == "mos2kx");
   } else {
     types[0] = std::make_unique<emcElectron<T, DeviceType>>(a.levels, a.emax, false);
     if (a.material == "si")

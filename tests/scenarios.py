@@ -90,7 +90,7 @@ MOS2_SUB = dict(same=[[0], [1], [2], [3], [4], [5]], next=[[1], [2], [3], [4], [
                 samekind=[[0, 2, 4], [1, 3, 5], [0, 2, 4], [1, 3, 5], [0, 2, 4], [0, 2, 4]])
 
 
-def build_mos2_pilotto(temperature=300.0):
+def build_mos2_pilotto(temperature=300.0, sheet_density=0.0):
     """parameterPilotto.hpp:64-176 on electron2D (5000 energy levels up to 0.5 eV): K valleys (isotropic), Q valleys
     (anisotropic, six in-plane frames 60 degrees apart), acoustic + zero-order intervalley mechanisms, in the order the
     example adds them"""
@@ -109,7 +109,12 @@ def build_mos2_pilotto(temperature=300.0):
         m.add_intervalley_sl(False, vi, vf, 0, sigma, P["rho"], ph, S[sub])
         m.add_intervalley_sl(True, vi, vf, 0, sigma, P["rho"], ph, S[sub])
 
-    pair(0, 0, 5.8e10, P["op_gamma"], "same")
+    if sheet_density > 0:  # parameterPilotto.hpp:119-131: the K -> K Gamma-phonon pair screened by the 2-D carrier gas
+        qs = twod_screening_wavevector(sheet_density, temperature, 1.0, 0.47 * 9.11e-31, 4.0)
+        m.add_screened_optical_sl(False, 0, 0, 5.8e10, P["rho"], P["op_gamma"], qs)
+        m.add_screened_optical_sl(True, 0, 0, 5.8e10, P["rho"], P["op_gamma"], qs)
+    else:
+        pair(0, 0, 5.8e10, P["op_gamma"], "same")
     pair(0, 0, 1.4e10, P["ac_k"], "next")
     pair(0, 0, 2.0e10, P["op_k"], "next")
     pair(0, 1, 0.93e9, P["ac_q"], "samekind")
@@ -143,7 +148,7 @@ def twod_screening_wavevector(sheet_density, temperature, env_permittivity, dos_
     return Q * Q * dndmu / (2 * EPS0 * env_permittivity)
 
 
-def build_mos2_kaasbjerg_subset(temperature=300.0, full=False, sheet_density=0.0):
+def build_mos2_kaasbjerg_subset(temperature=300.0, full=False, sheet_density=0.0, supported=False):
     """the part of parameterKaasbjerg.hpp whose mechanisms have device samplers (oracle/ref_bulk_driver.cpp:
     buildMoS2KaasbjergSubset): ONE parabolic single-layer valley with one sub-valley, acoustic TA / LA, zero-order LO / homopolar
     and the four first-order pairs through the constructors without a sub-valley map (emission added before absorption,
@@ -168,15 +173,26 @@ def build_mos2_kaasbjerg_subset(temperature=300.0, full=False, sheet_density=0.0
         m.add_froehlich_sl(True, 0, 0, 0.048, cc, width, qs)
         m.add_piezo_sl(0, 0, 3.0e-11, width, rho, 4.2e3, qs)
         m.add_piezo_sl(0, 0, 3.0e-11, width, rho, 6.7e3, qs)
+    if supported:  # the three optional extrinsic helpers (:272-351) as oracle/ref_bulk_driver.cpp calls them (material mos2kx)
+        Q, EPS0 = 1.60219e-19, 8.85419e-12
+        qs4 = twod_screening_wavevector(sheet_density, temperature, 4.0, 0.48 * 9.11e-31, 4.0)
+        m.add_charged_impurity_sl(0, 0, 1e16, 4.0, qs4, 4.0e-9, 0.0, 1.0)
+        m.add_surface_roughness_sl(0, 0, Q * sheet_density / (2 * EPS0 * 4.0) + 0.0, 3.0e-10, 1.5e-9, qs4)
+        qs1 = twod_screening_wavevector(sheet_density, temperature, 1.0, 0.48 * 9.11e-31, 4.0)
+        d_per_mode = 0.5 * (1. / (5.03 + 1.0) - 1. / (23.0 + 1.0))
+        for w_so in (0.0124, 0.0484):
+            m.add_remote_so_sl(False, 0, 0, w_so, d_per_mode, 5.0e-10, qs1)
+            m.add_remote_so_sl(True, 0, 0, w_so, d_per_mode, 5.0e-10, qs1)
     m.build_tables()
     return m
 
 
 def build_mos2(case):
     a = MOS2_CASES[case]
-    if a["material"] == "mos2":
-        return build_mos2_pilotto()
-    return build_mos2_kaasbjerg_subset(full=a["material"] == "mos2kf", sheet_density=a.get("sheet-density", 0.0))
+    if a["material"] in ("mos2", "mos2ps"):
+        return build_mos2_pilotto(sheet_density=a.get("sheet-density", 0.0) if a["material"] == "mos2ps" else 0.0)
+    return build_mos2_kaasbjerg_subset(full=a["material"] != "mos2k", sheet_density=a.get("sheet-density", 0.0),
+                                       supported=a["material"] == "mos2kx")
 
 
 # recorder cases of the single-layer path (oracle/_ref/ref_bulk_driver --material mos2): box = (box, box, 0.65 nm), one cell in z
@@ -193,6 +209,13 @@ MOS2_CASES = {
     # ... and screened by a 2-D carrier gas of 5e16 1/m^2 (the optional argument of the example's helper functions)
     "mos2_kaasbjerg_screened": {"material": "mos2kf", "cells": 5, "box": 5e-8, "field": 2e6, "fdir": "-0.3,1,0", "dt": 1e-15,
                                 "steps": 300, "seed": 37, "sheet-density": 5e16},
+    # a supported, doped film: + charged impurities, interface roughness, remote surface-optical phonons of HfO2 (the example's
+    # optional extrinsic helpers), everything screened by 5e16 1/m^2
+    "mos2_kaasbjerg_supported": {"material": "mos2kx", "cells": 5, "box": 5e-8, "field": 2e6, "fdir": "1,-0.4,0", "dt": 1e-15,
+                                 "steps": 300, "seed": 41, "sheet-density": 5e16},
+    # Pilotto set with the K -> K Gamma-phonon pair screened (emcScreenedIntravalleyOpticalMechanism), 1e15 1/m^2
+    "mos2_pilotto_screened": {"material": "mos2ps", "cells": 5, "box": 5e-8, "field": 4e6, "fdir": "1,0.2,0", "dt": 5e-16,
+                              "steps": 400, "seed": 43, "sheet-density": 1e15},
 }
 MOS2_LZ = 0.65e-9
 

@@ -19,7 +19,8 @@ def box_of(a):
     return [a["box"], a["box"], MOS2_LZ]
 
 
-@pytest.mark.parametrize("case", ["mos2_pilotto", "mos2_kaasbjerg", "mos2_kaasbjerg_screened"])
+@pytest.mark.parametrize("case", ["mos2_pilotto", "mos2_kaasbjerg", "mos2_kaasbjerg_screened", "mos2_kaasbjerg_supported",
+                                  "mos2_pilotto_screened"])
 def test_valley_constants_and_rate_tables_equal_the_reference(case):
     g = load_golden(case)
     m = build_mos2(case)
@@ -36,7 +37,7 @@ def test_valley_constants_and_rate_tables_equal_the_reference(case):
         assert np.array_equal(ts["cum"], g["cum" + key])
         assert ts["tau"] == g["tau" + key][0]
         assert [x.globalId for x in ts["mech"]] == list(g["mech" + key])
-    assert [len(ts["mech"]) for ts in sets] == ([15, 23] if case == "mos2_pilotto" else [18])
+    assert [len(ts["mech"]) for ts in sets] == {"mos2": [15, 23], "mos2ps": [15, 23], "mos2kf": [18], "mos2kx": [24]}[MOS2_CASES[case]["material"]]
 
 
 @pytest.mark.parametrize("case", CASES)
@@ -61,11 +62,15 @@ def test_initial_ensemble_and_full_run_bit_for_bit(case):
     ev = res["events"]
     real = ev[ev[:, 2] >= 0]
     assert np.array_equal(real[:, [0, 1, 3]], g["events"])
-    if a["material"] == "mos2":
+    if a["material"] in ("mos2", "mos2ps"):
         assert len(set(real[:, 3])) > 15 and (ens.valley == 1).sum() > 0  # many of the 38 mechanisms fired, Q valleys populated
+        if a["material"] == "mos2ps":  # ids 2, 3: the screened K -> K Gamma-phonon pair
+            assert (real[:, 3] == 2).sum() >= 20 and (real[:, 3] == 3).sum() >= 20
     else:
         fired = set(real[:, 3])  # one-valley model: ids 6-13 first order, 14-15 Froehlich, 16-17 piezoelectric
         assert len(fired) >= 12 and len(fired & set(range(6, 14))) >= 6 and len(real) > 1000
+        if a["material"] == "mos2kx":  # 18 charged impurities, 19 interface roughness, 20-23 remote surface-optical phonons
+            assert (real[:, 3] == 18).sum() >= 100 and (real[:, 3] == 19).sum() >= 20 and {20, 21, 22, 23} <= fired
         if a["material"] == "mos2kf":  # (screening suppresses the long-range piezoelectric terms)
             assert {14, 15} <= fired and len(fired & {16, 17}) >= (1 if "sheet-density" in a else 2)
     obs = res["obs"]

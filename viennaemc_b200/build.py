@@ -133,6 +133,26 @@ def build_examples(force: bool = False) -> dict:
                                ref_main, *link])
     if os.path.exists(target):
         out["reference_singleLayerMoS2_gpu"] = target
+    # the same example with its OTHER parameter set: a generated copy of the main in which two configuration constants are
+    # changed (Kaasbjerg instead of Pilotto parameters, the CUSTOM field list = one field of 40 kV/cm instead of the 15-field
+    # sweep) -- the example has no command line.  One parabolic single-layer valley; acoustic, zero- and first-order
+    # intervalley, Froehlich and piezoelectric single-layer mechanisms.
+    target = os.path.join(bindir, "reference_singleLayerMoS2_kaasbjerg_gpu")
+    if os.path.exists(ref_main) and (force or _newer(target, deps)):
+        text = open(ref_main).read()
+        for old, new in (("PaperType selectedPaperForParameter = PaperType::PILOTTO;", "PaperType selectedPaperForParameter = PaperType::KAASBJERG;"),
+                         ("AppliedFieldsType appliedFields = AppliedFieldsType::HIGH;", "AppliedFieldsType appliedFields = AppliedFieldsType::CUSTOM;")):
+            assert text.count(old) == 1, old
+            text = text.replace(old, new)
+        gen = os.path.join(bindir, "gen")
+        os.makedirs(gen, exist_ok=True)
+        src = os.path.join(gen, "singleLayerMoS2_kaasbjerg.cpp")
+        with open(src, "w") as f:
+            f.write(text)
+        subprocess.check_call([*common, "-I", os.path.dirname(ref_main), "-include", os.path.join(HOST_INC, "basicBulkParticleHandler.hpp"),
+                               "-o", target, src, *link])
+    if os.path.exists(target):
+        out["reference_singleLayerMoS2_kaasbjerg_gpu"] = target
     # the UNMODIFIED device-run examples of the reference (emcSimulation + emcBasicParticleHandler + emcSORSolver +
     # PM scheme) compiled against OUR headers: every object they create is the GPU-backed drop-in
     for name, rel in (("reference_resistor2D_gpu", ("examples", "resistor2D", "resistor2D.cpp")),):

@@ -611,6 +611,93 @@ __device__ __forceinline__ double slInvertAngle(double target, double k, double 
   return ((double)lo - 1.0 + (target - below) / (at - below)) * dAngle;
 }
 
+// ---- the other angle-resolved single-layer mechanisms: 2-D charged impurities, interface roughness, remote surface-optical
+// phonons, screened intravalley optical phonons.  One shape (reference emc2DChargedImpurityScatterMechanism.hpp:107-139,
+// emcSurfaceRoughnessScatterMechanism.hpp:94-126, emcRemoteSurfaceOpticalPhononMechanism.hpp:112-149,
+// emcScreenedIntravalleyOpticalMechanism.hpp:104-141): E += dE (0: elastic), deflection magnitude by inversion of an N-point
+// cumulative sum of the mechanism's weight (isotropic magnitude pi u when the sum vanishes), the side by a second draw,
+// k = |k'| (cos(phi + angle), sin(phi + angle), 0).  KIND = sampler id.
+template <int KIND> struct SlAngular;
+template <> struct SlAngular<EMCGPU_SAMPLER_SINGLE_LAYER_CHARGED_IMPURITY> { // :65-72: (exp(-q d) / (q_s + q + r0 q^2))^2, q = 2 k sin(theta/2)
+  static constexpr int steps = 512;
+  static constexpr bool elastic = true;
+  static __device__ __forceinline__ double weight(double theta, double k, double, const double *par) {
+    const double q = 2.0 * k * sin(theta / 2.0);
+    const double denom = par[2] + q + par[1] * q * q;
+    if (denom <= 0.0) return 0.0;
+    const double v = exp(-q * par[0]) / denom;
+    return v * v;
+  }
+};
+template <> struct SlAngular<EMCGPU_SAMPLER_SINGLE_LAYER_SURFACE_ROUGHNESS> { // :59-63: exp(-q^2 Lambda^2 / 4) / eps(q)^2
+  static constexpr int steps = 256;
+  static constexpr bool elastic = true;
+  static __device__ __forceinline__ double weight(double theta, double k, double, const double *par) {
+    const double q = 2.0 * k * sin(theta / 2.0);
+    const double formFactor = exp(-q * q * par[1] / 4.0);
+    return formFactor * slScreeningFactor(q, par[2]);
+  }
+};
+template <> struct SlAngular<EMCGPU_SAMPLER_SINGLE_LAYER_REMOTE_SO> { // :63-70: exp(-2 q d) / (q eps(q)^2), q^2 = k^2 + k'^2 - 2 k k' cos
+  static constexpr int steps = 128;
+  static constexpr bool elastic = false;
+  static __device__ __forceinline__ double weight(double theta, double k, double kPrime, const double *par) {
+    const double q2 = k * k + kPrime * kPrime - 2.0 * k * kPrime * cos(theta);
+    const double q = sqrt(fmax(0.0, q2));
+    if (q <= 0.0) return 0.0;
+    return exp(-2.0 * q * par[1]) * slScreeningFactor(q, par[2]) / q;
+  }
+};
+template <> struct SlAngular<EMCGPU_SAMPLER_SINGLE_LAYER_SCREENED_OPTICAL> { // :58-62: 1 / eps(q)^2
+  static constexpr int steps = 128;
+  static constexpr bool elastic = false;
+  static __device__ __forceinline__ double weight(double theta, double k, double kPrime, const double *par) {
+    const double q2 = k * k + kPrime * kPrime - 2.0 * k * kPrime * cos(theta);
+    return slScreeningFactor(sqrt(fmax(0.0, q2)), par[2]);
+  }
+};
+// the running sum is formed twice (total, then up to the target) like slRunningTotal / slInvertAngle above: the same partial
+// sums as the reference's array, nothing in local memory.  Out of line and by value (the loops stay out of the step kernels'
+// hot code, no particle state behind a pointer): the signed deflection angle from the two uniform draws.
+template <int KIND>
+__device__ __noinline__ double slSignedAngle(double k, double kPrime, double p0, double p1, double p2, double u1, double u2) {
+  using W = SlAngular<KIND>;
+  const double par[3] = {p0, p1, p2};
+  const double dAngle = kPi / W::steps;
+  double total = 0.0;
+  for (int i = 1; i <= W::steps; ++i) total = total + W::weight(((double)i - 0.5) * dAngle, k, kPrime, par);
+  double angle;
+  if (!(total > 0.0)) {
+    angle = kPi * u1;
+  } else {
+    const double target = u1 * total;
+    double below = 0.0, at = 0.0;
+    int lo = 0;
+    do { // lo: the first index whose cumulative sum reaches the target, or the last one
+      ++lo;
+      below = at;
+      at = below + W::weight(((double)lo - 0.5) * dAngle, k, kPrime, par);
+    } while (lo < W::steps && at < target);
+    angle = ((double)lo - 1.0 + (target - below) / (at - below)) * dAngle;
+  }
+  return u2 < 0.5 ? -angle : angle; // left / right
+}
+template <int KIND, int RNG_MODE>
+__device__ __forceinline__ void slAngularScatter(const DevValley &v, const DevMech &mech, Particle &p, Rng &rng) {
+  const double k = normWaveVec<true>(v, p.energy);
+  double kPrime = k;
+  if constexpr (!SlAngular<KIND>::elastic) {
+    p.energy = p.energy + mech.param[0];
+    kPrime = normWaveVec<true>(v, p.energy);
+  }
+  const double u1 = uniform01(rng.raw<RNG_MODE>());
+  const double u2 = uniform01(rng.raw<RNG_MODE>());
+  const double angle = slSignedAngle<KIND>(k, kPrime, mech.param[0], mech.param[1], mech.param[2], u1, u2);
+  double sa, ca;
+  sincos(atan2(p.k.y, p.k.x) + angle, &sa, &ca);
+  p.k = Vec3{kPrime * ca, kPrime * sa, 0.0};
+}
+
 template <bool EXACT, int RNG_MODE>
 __device__ __forceinline__ void sampleFinalState(const DevModel &model, const DevMech &mech, Particle &p,
                                                  Rng &rng, const BathView &baths) {
@@ -713,6 +800,18 @@ __device__ __forceinline__ void sampleFinalState(const DevModel &model, const De
     p.k = Vec3{k * ca, k * sa, 0.0};
     break;
   }
+  case EMCGPU_SAMPLER_SINGLE_LAYER_CHARGED_IMPURITY:
+    slAngularScatter<EMCGPU_SAMPLER_SINGLE_LAYER_CHARGED_IMPURITY, RNG_MODE>(model.valleys[p.valley], mech, p, rng);
+    break;
+  case EMCGPU_SAMPLER_SINGLE_LAYER_SURFACE_ROUGHNESS:
+    slAngularScatter<EMCGPU_SAMPLER_SINGLE_LAYER_SURFACE_ROUGHNESS, RNG_MODE>(model.valleys[p.valley], mech, p, rng);
+    break;
+  case EMCGPU_SAMPLER_SINGLE_LAYER_REMOTE_SO:
+    slAngularScatter<EMCGPU_SAMPLER_SINGLE_LAYER_REMOTE_SO, RNG_MODE>(model.valleys[p.valley], mech, p, rng);
+    break;
+  case EMCGPU_SAMPLER_SINGLE_LAYER_SCREENED_OPTICAL:
+    slAngularScatter<EMCGPU_SAMPLER_SINGLE_LAYER_SCREENED_OPTICAL, RNG_MODE>(model.valleys[p.valley], mech, p, rng);
+    break;
   case EMCGPU_SAMPLER_COULOMB: {
     // emcCoulombScatterMechanism.hpp:48-59
     const double g = gammaOf<EXACT>(model.valleys[p.valley], p.energy);

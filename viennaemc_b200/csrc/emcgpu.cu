@@ -684,7 +684,7 @@ int emcgpu_set_tables(emcgpu_ctx *ctx, const emcgpu_tableset_t *sets, int nSets,
       char name[EMCGPU_NAME_LEN + 1];
       memcpy(name, mi.name, EMCGPU_NAME_LEN);
       name[EMCGPU_NAME_LEN] = 0;
-      if (mi.sampler <= EMCGPU_SAMPLER_NONE || mi.sampler > EMCGPU_SAMPLER_SINGLE_LAYER_PIEZOELECTRIC)
+      if (mi.sampler <= EMCGPU_SAMPLER_NONE || mi.sampler > EMCGPU_SAMPLER_SINGLE_LAYER_SCREENED_OPTICAL)
         return fail(ctx, EMCGPU_E_UNSUPPORTED_MECHANISM,
                     "scatter mechanism '%s' (valley %d, region %d) has no device sampler; it cannot run on "
                     "the GPU path and there is no CPU fallback",
