@@ -46,10 +46,12 @@ FIELD = 1e6
 DOPING = 1e23
 SEED = 12345
 SPL = 24  # time steps per launch pair of the headline kernels (K1d)
-# FP64 instructions of the flight kernel per particle-step (SASS of bulkFlightKernel<4, AXIS>, hot loop: 13 DFMA + 9 DMUL +
-# 6 DADD; cross-checked against ncu's executed-opcode counts, profiles/r2_*flight*.txt)
-FLIGHT_FP64_PER_PARTICLE_STEP = 28.0
-FLIGHT_FLOP_PER_PARTICLE_STEP = 13 * 2 + 9 + 6
+# FP64 instructions of the flight kernel per particle-step for a field along a coordinate axis (SASS of
+# bulkFlightKernel<4, AXIS = 0>, hot loop: 11 DFMA + 9 DMUL + 4 DADD since the transverse components of k are known not to
+# change -- flightCoreAxis; 28 before, and 28 for a general field direction; cross-checked against ncu's executed-opcode
+# counts, profiles/r2_*flight*.txt)
+FLIGHT_FP64_PER_PARTICLE_STEP = 24.0
+FLIGHT_FLOP_PER_PARTICLE_STEP = 11 * 2 + 9 + 4
 FP64_LANES_PER_SM = 64
 
 
@@ -545,7 +547,7 @@ def main_ours(args):
                                 "bytes of one flight + one event launch (profiles/traffic.json) over their measured "
                                 "durations: the state crosses HBM once per launch pair, so the step is bound by the FP64 "
                                 "pipe, not by HBM; the HBM-bound one-step kernel is in 'one_step_per_launch'"},
-                "note": "per GPU. achieved = 28 FP64 instructions per particle-step (SASS of the flight loop) x particle-steps of "
+                "note": "per GPU. achieved = 24 FP64 instructions per particle-step (SASS of the flight loop) x particle-steps of "
                         "a launch / average flight-launch duration measured with CUDA events in this run; frac = share of the "
                         "FP64 pipe's issue rate (the binding resource, ncu: sm__pipe_fp64_cycles_active)"}
     one_achieved = BYTES_PER_PARTICLE_STEP * n_local * K / (one_ms * 1e-3) / 1e9
@@ -564,6 +566,7 @@ def main_ours(args):
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "one_step_per_launch": one_step,
             "observables": {"mean_energy_eV": mean_e, "mean_drift_velocity_m_s": mean_v}}
+    ctx.close()  # the legs below start processes of their own on this GPU: give the ensemble's memory back first
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:
@@ -583,7 +586,6 @@ def main_ours(args):
                 line["device_runs"] = device_run_numbers()
             except Exception as exc:
                 line["device_runs"] = {"failed": str(exc)}
-    ctx.close()
     if world > 1:
         if not args.no_device_runs:
             # configs 3 / 4 sharded over all GPUs of the run: every rank starts the C++ driver of its rank

@@ -40,7 +40,7 @@ def build_emcgpu(force: bool = False, verbose: bool = False) -> str:
     src = [os.path.join(PKG, "csrc", "emcgpu.cu"), os.path.join(PKG, "csrc", "emcgpu_device.cu")]
     deps = _sources(os.path.join(PKG, "csrc"), os.path.join(ROOT, "include"))
     if force or _newer(target, deps):
-        cmd = ["nvcc", *NVCC_FLAGS, "-o", target, *src]
+        cmd = ["nvcc", "--threads", "2", *NVCC_FLAGS, "-o", target, *src]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.check_call(cmd)

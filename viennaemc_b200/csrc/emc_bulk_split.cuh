@@ -6,7 +6,7 @@
 // flights run in a kernel that contains nothing else:
 //
 //   bulkFlightKernel  every lane keeps PPL particles in registers and advances them by full-dt flights, branch-free,
-//                     ~33 FP64 instructions per particle-step, all launch constants in the constant bank, the three
+//                     28 FP64 instructions per particle-step (24 for a field along a coordinate axis), all launch constants in the constant bank, the three
 //                     Herring-Vogt factors of the particle's sub-valley in registers.  A particle whose flight ends
 //                     inside the coming step (tau < dt) FREEZES IN PLACE: its three factors become 0, after which the
 //                     same instructions leave k and the position exactly unchanged and contribute exact zeros to the
@@ -100,9 +100,10 @@ __device__ __forceinline__ void flightRole(const BulkParams &P, const int cta, c
     const DevValley &v = P.model->valleys[0];
     FastSub fs;
     buildFastSub(v, tid < v.deg ? tid : 0, P.force, P.dir, P.dt, fs);
-    aTab[4 * tid + 0] = fs.a[0];
-    aTab[4 * tid + 1] = fs.a[1];
-    aTab[4 * tid + 2] = fs.a[2];
+    // AXIS >= 0 (flightCoreAxis): the factors of the two transverse axes doubled
+    aTab[4 * tid + 0] = AXIS == 1 || AXIS == 2 ? 2.0 * fs.a[0] : fs.a[0];
+    aTab[4 * tid + 1] = AXIS == 0 || AXIS == 2 ? 2.0 * fs.a[1] : fs.a[1];
+    aTab[4 * tid + 2] = AXIS == 0 || AXIS == 1 ? 2.0 * fs.a[2] : fs.a[2];
     aTab[4 * tid + 3] = 0.0;
   }
   if (tid == 0) {
@@ -191,7 +192,10 @@ __device__ __forceinline__ void flightRole(const BulkParams &P, const int cta, c
           frz = (frz & ~(0xffu << (8 * j))) | ((uint32_t)s << (8 * j));
         }
         FlightAux o;
-        flightCore(a0[j], a1[j], a2[j], f.G[0], f.G[1], f.G[2], f.K2, f.c2a, kx[j], ky[j], kz[j], px[j], py[j], pz[j], o);
+        if constexpr (AXIS < 0)
+          flightCore(a0[j], a1[j], a2[j], f.G[0], f.G[1], f.G[2], f.K2, f.c2a, kx[j], ky[j], kz[j], px[j], py[j], pz[j], o);
+        else
+          flightCoreAxis<AXIS>(a0[j], a1[j], a2[j], f.G[AXIS], f.K2, f.c2a, kx[j], ky[j], kz[j], px[j], py[j], pz[j], o);
         wrap |= (uint32_t)mayNeedWrap(px[j], hiBx) | (uint32_t)mayNeedWrap(py[j], hiBy) | (uint32_t)mayNeedWrap(pz[j], hiBz);
         // live: tau -= dt, sumT += S - 1 (predicated adds); a frozen particle contributes nothing
         const double t = flightSm1(o);
