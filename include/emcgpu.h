@@ -214,7 +214,8 @@ int emcgpu_synchronize(emcgpu_ctx *ctx);
  * per launch pair; FAST arithmetic, one non-parabolic valley with signed-permutation rotations) or else the deferred-event
  * kernel (up to 8 steps per launch), events in place otherwise; 1: always in place; 2: always deferred; 3: always the
  * flight + event pair where the model allows (no effect on results: the trajectories are bit-identical);
- * "split_ppl" = 2 | 4: particles per lane of the flight kernel; "kernel_timing" = 1: see emcgpu_kernel_times; "defer_tables_smem" = 1: the deferred-event kernel
+ * "split_ppl" = 2 | 4: particles per lane of the flight kernel; "event_claim" = particles per claim of a warp of the event kernel
+ * (a multiple of 256; work-distribution grain, no effect on results); "kernel_timing" = 1: see emcgpu_kernel_times; "defer_tables_smem" = 1: the deferred-event kernel
  * stages the rate tables in shared memory instead of reading them through L1/L2 (slower, no effect on results) */
 int emcgpu_set_option(emcgpu_ctx *ctx, const char *name, int64_t value);
 

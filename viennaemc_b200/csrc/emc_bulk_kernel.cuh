@@ -55,6 +55,7 @@ struct BulkParams {
   // claim counter of the event kernel
   uint8_t *frozen;
   unsigned *claim;
+  int32_t eventClaim; // particles per claim of a warp of the event kernel (multiple of 256)
   // flight kernel out of place (emcgpu_bulk_step_ahead: the input ensemble stays as it was): nullptr = in place
   double *streamOut[EMCGPU_N_STREAMS];
   uint32_t *packedOut;

@@ -39,7 +39,7 @@ constexpr int kEventThreadsAlone = 512;  // event kernel
 constexpr int kEventScan = 256;        // bytes of the frozen array a warp scans per refill (8 per lane)
 constexpr int kEventListCap = 32 + kEventScan; // a refill starts with fewer than 32 entries
 constexpr int kEventDense = 12;        // lanes still busy after an event step from which the batch goes on in place
-constexpr int64_t kEventClaim = 8192;  // particles per claim of a warp of the event kernel
+// particles per claim of a warp of the event kernel: option event_claim (default 1024, emcgpu_internal.cuh)
 
 struct SplitFlightSmem {
   // [nSteps][2][threads] doubles, then the Herring-Vogt factors [EMCGPU_MAX_SUBVALLEYS][4], then the control word
@@ -315,14 +315,14 @@ __device__ __forceinline__ void eventRole(const BulkParams &P) {
         unsigned c = 0;
         if (lane == 0) c = atomicAdd(P.claim, 1u);
         c = __shfl_sync(0xffffffffu, c, 0);
-        scanAt = (int64_t)c * kEventClaim;
-        scanEnd = min(scanAt + kEventClaim, P.n);
+        scanAt = (int64_t)c * P.eventClaim;
+        scanEnd = min(scanAt + (int64_t)P.eventClaim, P.n);
         if (scanAt >= P.n) {
           exhausted = true;
           break;
         }
       }
-      // 8 bytes per lane (the claims start on multiples of 8192, the array is padded to a multiple of 256)
+      // 8 bytes per lane (the claims start on multiples of 256, the array is padded to a multiple of 256)
       const int64_t at = scanAt + 8 * lane;
       uint2 fl = make_uint2(0xffffffffu, 0xffffffffu);
       if (at < scanEnd) fl = *reinterpret_cast<const uint2 *>(P.frozen + at);

@@ -244,7 +244,8 @@ cudaError_t launchSplit(emcgpu_ctx *ctx, BulkParams &P, bool outOfPlace) {
   const int64_t nChunks = P.n / (32 * ppl);
   const int warps = kFlightThreadsAlone / 32;
   const int gridFlight = (int)std::max<int64_t>(1, std::min<int64_t>((nChunks + warps - 1) / warps, ctx->smCount));
-  const int64_t claims = (P.n + kEventClaim - 1) / kEventClaim;
+  P.eventClaim = ctx->optEventClaim;
+  const int64_t claims = (P.n + P.eventClaim - 1) / P.eventClaim;
   const int gridEvent = (int)std::max<int64_t>(1, std::min<int64_t>((claims + warps - 1) / warps, ctx->smCount));
   for (int s = 0; s < EMCGPU_N_STREAMS; s++) P.streamOut[s] = outOfPlace ? ctx->dStreamAlt[s] : nullptr;
   P.packedOut = outOfPlace ? ctx->dPackedAlt : nullptr;
@@ -491,6 +492,11 @@ int emcgpu_set_option(emcgpu_ctx *ctx, const char *name, int64_t value) {
   }
   if (!strcmp(name, "kernel_timing")) {
     ctx->optTiming = value != 0;
+    return EMCGPU_OK;
+  }
+  if (!strcmp(name, "event_claim")) {
+    if (value < 256 || value > (1 << 20) || value % 256) return fail(ctx, EMCGPU_E_INVALID, "event_claim must be a multiple of 256 in [256, 2^20] (particles per claim of a warp of the event kernel)");
+    ctx->optEventClaim = (int)value;
     return EMCGPU_OK;
   }
   if (!strcmp(name, "split_ppl")) {

@@ -47,6 +47,7 @@ struct emcgpu_ctx {
   int optStages = 0;       // cap on the TMA ring depth (0 = as many as fit)
   int optDeferTablesSmem = 0; // K1c: 1 = stage the rate tables in shared memory (default: read them through L1/L2)
   int optMultiKernel = 0;  // several steps per launch: 0 = auto (K1d / K1c when the ensemble fills the machine), 1 = in place (K1b), 2 = K1c, 3 = K1d
+  int optEventClaim = 1024;     // K1d event kernel: particles per claim of a warp
   int optSplitPpl = 4;     // K1d flight kernel: particles per lane (2 or 4)
   int optTablesGlobal = 0; // 1 = leave the rate tables in global memory / L2 (more ring stages)
   int optSorKernel = 0;    // 0 = row-per-thread wavefront when it fits, 1 = hyperplane loop
