@@ -246,6 +246,8 @@ def test_sor_variants_agree(gpu_ctx_factory, case):
     m, dev = build_device(case)
     results = {}
     for name, opts in (("rows", {}), ("planes", {"sor_kernel": 1}), ("redblack", {"sor_order": 1}),
+                       ("redblack_fast_8_ctas", {"sor_order": 1, "sor_kernel": 3}),
+                       ("redblack_general_cluster", {"sor_order": 1, "sor_kernel": 2}),
                        ("redblack_one_cta", {"sor_order": 1, "sor_kernel": 1})):
         ctx = gpu_ctx_factory()
         upload_model(ctx, m)
@@ -263,9 +265,12 @@ def test_sor_variants_agree(gpu_ctx_factory, case):
         results[name] = out
     for (s_r, p_r), (s_p, p_p) in zip(results["rows"], results["planes"]):
         assert s_r == s_p and np.array_equal(p_r, p_p)
-    # red-black on a cluster of 8 CTAs (distributed shared memory) and on one CTA: the same iterates
-    for (s_c, p_c), (s_1, p_1) in zip(results["redblack"], results["redblack_one_cta"]):
-        assert s_c == s_1 and np.array_equal(p_c, p_1)
+    # red-black on a cluster (distributed shared memory) -- the fast 2-D form on 16 CTAs of 512 threads where the device
+    # places such a cluster (the default) and on the portable 8 CTAs of 1024, the general cluster kernel -- and on one CTA:
+    # the same iterates
+    for other in ("redblack_fast_8_ctas", "redblack_general_cluster", "redblack_one_cta"):
+        for (s_c, p_c), (s_1, p_1) in zip(results["redblack"], results[other]):
+            assert s_c == s_1 and np.array_equal(p_c, p_1), other
     vt = dev.vt
     for k, tol_volt in ((0, 5e-4), (1, 1e-8), (2, 5e-4)):
         diff = float(np.abs(results["redblack"][k][1] - results["rows"][k][1]).max()) * vt

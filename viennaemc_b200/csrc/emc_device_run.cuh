@@ -1023,6 +1023,184 @@ __global__ void __launch_bounds__(kSorClusterThreads) sorRedBlackClusterKernel(c
   cluster.sync();
 }
 
+// The cluster relaxation for the two-dimensional device-run grids, where every thread owns at most ONE cell per colour
+// (rows per CTA <= THREADS / ceil(ex / 2)).  Same bands, same iterates as sorRedBlackClusterKernel (the operations of a
+// cell update in the same order: bit-identical potentials and sweep counts), but everything an update needs besides
+// the potentials is fixed before the sweeps start: the shared-memory address of the cell, the addresses of the row
+// neighbours (mirrored at the faces; rows of the adjacent bands as shared::cluster addresses of the peer CTA), the Robin
+// term of a gate face (per thread and colour in shared memory).  A sweep is then 7 shared-memory loads, exp, ~20 FP64
+// operations, one division and a store per cell; the stopping test is a __syncthreads_or whose result every CTA stores
+// into every peer's shared memory before the barrier that ends the sweep.
+// Launched as 16 CTAs of 512 threads (non-portable cluster size) where the device places such a cluster, else 8 of 1024.
+constexpr int kSorClusterSizeWide = 16;
+constexpr int kSorClusterThreadsWide = 512;
+__host__ __device__ inline size_t sorClusterFastSmemBytes(int rowsPerCta, int ex, int threads) {
+  const size_t band = ((size_t)rowsPerCta * ex * (3 * sizeof(double) + 1) + 15) & ~size_t(15);
+  return band + (size_t)8 * threads * sizeof(double) + 16; // + [colour][x face: num, den | y face: num, den][thread] gate terms
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) sorRedBlackClusterFastKernel(const __grid_constant__ DevGeometry G, const SorParams S) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ double sBand[]; // [rowsPerCta][ex] potential, electron density, normalised doping, cell kinds; gate terms
+  __shared__ int sOver[kSorClusterSizeWide];
+  const int tid = threadIdx.x;
+  const int cta = (int)cluster.block_rank(), nCta = (int)cluster.num_blocks();
+  if (S.ctl && S.ctl->runSteps % S.ctl->poissonInterval != 0) { // uniform over the cluster
+    if (cta == 0 && tid == 0 && S.sweepsPerStep) S.sweepsPerStep[S.ctl->slot] = 0;
+    return;
+  }
+  const double h0 = __ddiv_rn(G.spacing[0], G.debyeLength), h1 = __ddiv_rn(G.spacing[1], G.debyeLength);
+  const double hF0 = __ddiv_rn(h1, h0), hF1 = __ddiv_rn(h0, h1);
+  const double hProd = __dmul_rn(__dmul_rn(1.0, h0), h1);
+  const double twoHFSum = __dmul_rn(2.0, __dadd_rn(__dadd_rn(0.0, hF0), hF1));
+  const int ex = G.extent[0], ey = G.extent[1];
+  const int rowsPerCta = (ey + nCta - 1) / nCta;
+  const int row0 = cta * rowsPerCta, row1 = min(ey, row0 + rowsPerCta);
+  const int myRows = max(0, row1 - row0);
+  const bool nonEq = S.conc != nullptr;
+  const int cellsPerBand = rowsPerCta * ex;
+  double *sConc = sBand + cellsPerBand, *sDop = sConc + cellsPerBand;
+  unsigned char *sKind = reinterpret_cast<unsigned char *>(sDop + cellsPerBand);
+  double *sGate = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(sBand) + (((size_t)cellsPerBand * 25 + 15) & ~size_t(15)));
+  for (int i = tid; i < myRows * ex; i += THREADS) {
+    sBand[i] = S.pot[row0 * ex + i];
+    sConc[i] = nonEq ? S.conc[row0 * ex + i] : 0.0;
+    sDop[i] = G.dopingNorm[row0 * ex + i];
+    sKind[i] = G.cellKind[row0 * ex + i];
+  }
+  __syncthreads();
+  const int halfX = (ex + 1) / 2;
+  const int tx = tid % halfX, local = tid / halfX; // the thread's row of the band
+  const uint32_t band = (uint32_t)__cvta_generic_to_shared(sBand);
+  const uint32_t concOff = 8u * (uint32_t)cellsPerBand, dopOff = 2u * concOff;
+  const uint32_t gate = (uint32_t)__cvta_generic_to_shared(sGate) + 8u * (uint32_t)tid;
+  auto mapa = [](uint32_t addr, int rank) -> uint32_t {
+    uint32_t r;
+    asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+  };
+  // per colour c, bits 8c...: 0 the cell is relaxed, 1 left neighbour mirrored (x = 0), 2 right neighbour mirrored
+  // (x = ex - 1), 3 the cell has a gate face, 4-7 a gate term follows the neighbour term of face x-, x+, y-, y+ (ex, ey > 1:
+  // at most one gate face per axis)
+  uint32_t flags = 0;
+  uint32_t at0 = 0, at1 = 0, down0 = 0, down1 = 0, up0 = 0, up1 = 0;
+  auto setUp = [&](int colour, uint32_t &at, uint32_t &down, uint32_t &up) {
+    const int y = row0 + local;
+    const int x = 2 * tx + ((y + colour) & 1);
+    if (local >= myRows || x >= ex) return;
+    const int cellLocal = local * ex + x;
+    const unsigned kind = sKind[cellLocal];
+    if (kind & 1u) return;
+    uint32_t f = 1u;
+    if (x == 0) f |= 2u;
+    if (x == ex - 1) f |= 4u;
+    at = band + 8u * (uint32_t)cellLocal;
+    // the row below / above: mirrored at the faces of the device; outside the band it is the last row of the CTA below or
+    // the first row of the CTA above
+    auto rowAddr = [&](int nl) -> uint32_t {
+      if (nl < 0) return mapa(band + 8u * (uint32_t)((rowsPerCta - 1) * ex + x), cta - 1);
+      if (nl >= myRows) return mapa(band + 8u * (uint32_t)x, cta + 1);
+      return mapa(band + 8u * (uint32_t)(nl * ex + x), cta);
+    };
+    down = rowAddr(local + (y == 0 ? 1 : -1));
+    up = rowAddr(local + (y == ey - 1 ? -1 : 1));
+    if (kind & 2u) { // a cell on a contact face: Robin term of a gate (emcSORSolver.hpp:399-412)
+      const int cell = x + ex * y;
+      const bool atFace[4] = {x == 0, x == ex - 1, y == 0, y == ey - 1};
+      for (int face = 0; face < 4; face++) {
+        if (!atFace[face]) continue;
+        const int ct = G.faceContact[cell * 4 + face];
+        if (ct >= 0 && G.contactType[ct] == 2) {
+          const SorGate g = sorGateTerm(G, ct, nonEq, face < 2 ? hF0 : hF1, face < 2 ? h0 : h1);
+          sGate[(4 * colour + (face < 2 ? 0 : 2)) * THREADS + tid] = g.numTerm;
+          sGate[(4 * colour + (face < 2 ? 1 : 3)) * THREADS + tid] = g.denTerm;
+          f |= 8u | (16u << face);
+        }
+      }
+    }
+    flags |= f << (8 * colour);
+  };
+  setUp(0, at0, down0, up0);
+  setUp(1, at1, down1, up1);
+  uint32_t overOfPeer = 0; // thread t < nCta: the address of sOver[cta] in CTA t
+  if (tid < nCta) overOfPeer = mapa((uint32_t)__cvta_generic_to_shared(&sOver[cta]), tid);
+  auto ldShared = [](uint32_t addr) -> double {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+  };
+  auto ldCluster = [](uint32_t addr) -> double {
+    double v;
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+  };
+  const double omega = S.omega, accuracy = S.accuracy;
+  // one cell update; the order of the operations is that of sorRedBlackKernel / sorRedBlackClusterKernel
+  auto relax = [&](uint32_t fl, uint32_t at, uint32_t down, uint32_t up, uint32_t gateAt) -> bool {
+    const double cur = ldShared(at);
+    const double nbL = ldShared((fl & 2u) ? at + 8u : at - 8u);
+    const double nbR = ldShared((fl & 4u) ? at - 8u : at + 8u);
+    const double nbD = ldCluster(down), nbU = ldCluster(up);
+    const double dop = ldShared(at + dopOff);
+    double p, n;
+    if (nonEq) {
+      p = exp(-cur);
+      n = ldShared(at + concOff);
+    } else {
+      n = exp(cur);
+      p = __ddiv_rn(1.0, n);
+    }
+    double num = __dmul_rn(hProd, __dadd_rn(__dadd_rn(__dsub_rn(p, n), dop), __dmul_rn(cur, __dadd_rn(p, n))));
+    double den = __dadd_rn(twoHFSum, __dmul_rn(hProd, __dadd_rn(n, p)));
+    if (!(fl & 8u)) {
+      num = __dadd_rn(num, __dmul_rn(nbL, hF0));
+      num = __dadd_rn(num, __dmul_rn(nbR, hF0));
+      num = __dadd_rn(num, __dmul_rn(nbD, hF1));
+      num = __dadd_rn(num, __dmul_rn(nbU, hF1));
+    } else {
+      const double gxNum = ldShared(gateAt), gxDen = ldShared(gateAt + 8u * THREADS);
+      const double gyNum = ldShared(gateAt + 16u * THREADS), gyDen = ldShared(gateAt + 24u * THREADS);
+      const double nb[4] = {nbL, nbR, nbD, nbU};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        num = __dadd_rn(num, __dmul_rn(nb[k], k < 2 ? hF0 : hF1));
+        if (fl & (16u << k)) {
+          num = __dadd_rn(num, k < 2 ? gxNum : gyNum);
+          den = __dadd_rn(den, k < 2 ? gxDen : gyDen);
+        }
+      }
+    }
+    const double delta = __dmul_rn(omega, __dsub_rn(__ddiv_rn(num, den), cur));
+    const double next = __dadd_rn(cur, delta);
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(at), "d"(next) : "memory");
+    return fabs(delta) > accuracy;
+  };
+  cluster.sync();
+  int sweeps = 0;
+  for (;;) {
+    bool over = false;
+    if (flags & 1u) over = relax(flags & 0xffu, at0, down0, up0, gate);
+    cluster.sync();
+    if (flags & 0x100u) over |= relax((flags >> 8) & 0xffu, at1, down1, up1, gate + 32u * THREADS);
+    const int any = __syncthreads_or(over ? 1 : 0);
+    if (tid < nCta) asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(overOfPeer), "r"(any) : "memory");
+    cluster.sync();
+    int anyOfAll = 0;
+    for (int k = 0; k < nCta; k++) anyOfAll |= sOver[k];
+    sweeps++;
+    if (!anyOfAll || (S.maxSweeps > 0 && sweeps >= S.maxSweeps)) break;
+  }
+  for (int i = tid; i < myRows * ex; i += THREADS) S.pot[row0 * ex + i] = sBand[i];
+  if (cta == 0 && tid == 0) {
+    *S.sweepsOut = sweeps;
+    if (S.ctl && S.sweepsPerStep) S.sweepsPerStep[S.ctl->slot] = sweeps;
+  }
+  // no CTA leaves while a peer may still read its band (the neighbour rows of the last sweep)
+  cluster.sync();
+}
+
 // Dirichlet values at ohmic contacts (emcSORSolver.hpp:57-73, :139-155); faces in the reference's order
 __global__ void sorResetBcKernel(const __grid_constant__ DevGeometry G, double *pot, int nonEquilibrium) {
   const int cell = blockIdx.x * blockDim.x + threadIdx.x;

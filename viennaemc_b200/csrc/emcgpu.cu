@@ -395,6 +395,8 @@ int emcgpu_create(int cudaDevice, emcgpu_ctx **out) {
                 cudaDevice, prop.major, prop.minor);
   }
   ctx->smCount = prop.multiProcessorCount;
+  if (const char *e = std::getenv("EMCGPU_SOR_KERNEL")) // developer switch for unmodified drivers: option sor_kernel
+    ctx->optSorKernel = std::max(0, std::min(3, std::atoi(e)));
   ctx->maxSmemOptin = (int)prop.sharedMemPerBlockOptin;
   ctx->maxSmemPerSm = (int)prop.sharedMemPerMultiprocessor;
   if ((e = ctx->dStatus.ensure(sizeof(int))) != cudaSuccess ||
@@ -462,7 +464,8 @@ int emcgpu_set_option(emcgpu_ctx *ctx, const char *name, int64_t value) {
     return EMCGPU_OK;
   }
   if (!strcmp(name, "sor_kernel")) {
-    if (value != 0 && value != 1) return fail(ctx, EMCGPU_E_INVALID, "sor_kernel must be 0 (rows) or 1 (hyperplanes)");
+    if (value < 0 || value > 3)
+      return fail(ctx, EMCGPU_E_INVALID, "sor_kernel must be 0 (default: rows / fastest cluster form), 1 (hyperplanes / one CTA), 2 (red-black: general cluster kernel) or 3 (red-black: fast form on the portable cluster of 8 CTAs)");
     ctx->optSorKernel = (int)value;
     return EMCGPU_OK;
   }

@@ -242,7 +242,59 @@ int doPoisson(emcgpu_ctx *ctx, bool equilibrium, double accuracyVolt, double ome
     const int nRowsRb = G.extent[1] * (G.dim > 2 ? G.extent[2] : 1);
     const int rowsPerCta = (nRowsRb + kSorClusterSize - 1) / kSorClusterSize;
     const size_t bandBytes = (size_t)rowsPerCta * G.extent[0] * (3 * sizeof(double) + 1) + 16;
-    if (ctx->optSorKernel != 1 && nRowsRb >= kSorClusterSize && bandBytes <= (size_t)ctx->maxSmemOptin - 4096 &&
+    // two dimensions, every thread at most one cell per colour: the fast form of the cluster kernel, on 16 CTAs of 512
+    // threads where the device places such a cluster (decided once per grid), else on 8 CTAs of 1024; option
+    // sor_kernel = 2 keeps the general cluster kernel
+    const int halfX = (G.extent[0] + 1) / 2;
+    auto fastLaunch = [&](int clusterSize, int threads, bool probeOnly) -> cudaError_t {
+      const int rows = (nRowsRb + clusterSize - 1) / clusterSize;
+      const size_t bytes = sorClusterFastSmemBytes(rows, G.extent[0], threads);
+      if (G.dim != 2 || G.extent[0] < 2 || nRowsRb < clusterSize || halfX > threads || rows > threads / halfX ||
+          bytes > (size_t)ctx->maxSmemOptin - 4096)
+        return cudaErrorInvalidConfiguration;
+      const void *kernel = clusterSize == kSorClusterSizeWide ? (const void *)sorRedBlackClusterFastKernel<kSorClusterThreadsWide>
+                                                              : (const void *)sorRedBlackClusterFastKernel<kSorClusterThreads>;
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+      if (e != cudaSuccess) return e;
+      if (clusterSize > 8 && (e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)) != cudaSuccess) return e;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(clusterSize);
+      cfg.blockDim = dim3(threads);
+      cfg.dynamicSmemBytes = bytes;
+      cfg.stream = ctx->stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = clusterSize;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      if (probeOnly) {
+        int nClusters = 0;
+        e = cudaOccupancyMaxActiveClusters(&nClusters, kernel, &cfg);
+        return e != cudaSuccess ? e : nClusters >= 1 ? cudaSuccess : cudaErrorInvalidConfiguration;
+      }
+      SorParams S2 = S;
+      S2.efield = nullptr;
+      void *args[] = {(void *)&G, (void *)&S2};
+      return cudaLaunchKernelExC(&cfg, kernel, args);
+    };
+    const long long fastKey = (long long)G.extent[0] * 1000003LL + nRowsRb * 4LL + G.dim;
+    if (ctx->sorFastKey != fastKey) { // 0: general cluster kernel, 1: fast on 8 x 1024, 2: fast on 16 x 512
+      ctx->sorFastKey = fastKey;
+      ctx->sorFast = fastLaunch(kSorClusterSizeWide, kSorClusterThreadsWide, true) == cudaSuccess ? 2
+                     : fastLaunch(kSorClusterSize, kSorClusterThreads, true) == cudaSuccess    ? 1
+                                                                                               : 0;
+      cudaGetLastError();
+    }
+    if ((ctx->optSorKernel == 0 || ctx->optSorKernel == 3) && ctx->sorFast > 0) {
+      CUDA_TRY(ctx, ctx->sorFast == 2 && ctx->optSorKernel == 0 ? fastLaunch(kSorClusterSizeWide, kSorClusterThreadsWide, false)
+                                      : fastLaunch(kSorClusterSize, kSorClusterThreads, false));
+      if (S.efield) {
+        efieldAfterSolveKernel<<<gridBlocks(G.cells), 256, 0, ctx->stream>>>(G, S.pot, S.efield, S.ctl);
+        ctx->launches++;
+      }
+    } else if (ctx->optSorKernel != 1 && nRowsRb >= kSorClusterSize && bandBytes <= (size_t)ctx->maxSmemOptin - 4096 &&
         (G.extent[0] + 1) / 2 <= kSorClusterThreads) {
       auto kernel = G.dim == 2 ? sorRedBlackClusterKernel<2> : sorRedBlackClusterKernel<3>;
       CUDA_TRY(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bandBytes));

@@ -48,6 +48,10 @@ struct emcgpu_ctx {
   int optDeferTablesSmem = 0; // K1c: 1 = stage the rate tables in shared memory (default: read them through L1/L2)
   int optMultiKernel = 0;  // several steps per launch: 0 = auto (K1d / K1c when the ensemble fills the machine), 1 = in place (K1b), 2 = K1c, 3 = K1d
   int optEventClaim = 1024;     // K1d event kernel: particles per claim of a warp
+  int sorClusterWide = -1; // red-black cluster solver on 16 CTAs of 512 threads: -1 undecided, 0 no, 1 yes
+  long long sorClusterWideKey = -1; // the grid that decision was made for
+  int sorFast = 0;          // red-black cluster solver, fast 2-D form: 0 no, 1 on 8 x 1024 threads, 2 on 16 x 512
+  long long sorFastKey = -1; // the grid that decision was made for
   int optSplitPpl = 4;     // K1d flight kernel: particles per lane (2 or 4)
   int optTablesGlobal = 0; // 1 = leave the rate tables in global memory / L2 (more ring stages)
   int optSorKernel = 0;    // 0 = row-per-thread wavefront when it fits, 1 = hyperplane loop
