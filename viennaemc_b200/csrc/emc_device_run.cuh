@@ -251,7 +251,8 @@ struct AssignParams {
   int32_t useSmem;
 };
 
-__global__ void __launch_bounds__(256) ngpAssignKernel(const __grid_constant__ DevGeometry G, const AssignParams A) {
+constexpr int kAssignThreads = 1024; // the block that finishes last forms the concentration of the whole grid alone
+__global__ void __launch_bounds__(kAssignThreads) ngpAssignKernel(const __grid_constant__ DevGeometry G, const AssignParams A) {
   extern __shared__ double sCount[];
   const int64_t n = A.closeStep ? A.ctl->nKept + A.ctl->toInject : A.ctl->n;
   if (A.useSmem) {
@@ -1625,6 +1626,7 @@ constexpr int kRankThreads = 1024;
 __global__ void __launch_bounds__(kRankThreads) contactRankKernel(const __grid_constant__ DevGeometry G, const ContactParams K,
                                                                    const int countersInSmem) {
   extern __shared__ int sCellCount[];
+  __shared__ int sGroupCell[kRankThreads], sGroupSize[kRankThreads], sGroupBefore[kRankThreads];
   int *cnt = countersInSmem ? sCellCount : K.cellCount;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (countersInSmem)
@@ -1636,18 +1638,26 @@ __global__ void __launch_bounds__(kRankThreads) contactRankKernel(const __grid_c
     const int cell = j < m ? K.listCell[j] : -1;
     const unsigned peers = __match_any_sync(0xffffffffu, cell);
     const int leaderLane = __ffs(peers) - 1;
-    int before = 0; // particles of the cell ahead of this warp
-    for (int w = 0; w < kRankThreads / 32; w++) {
-      if (warp == w && cell >= 0) {
-        if (lane == leaderLane) {
-          before = cnt[cell];
-          cnt[cell] = before + __popc(peers);
+    // the groups (warp, cell) of this chunk take their places in the order of the warps: every group leader posts its cell
+    // and size, warp 0 walks through the 32 warps' groups -- the groups of one warp have different cells, so its lanes
+    // never collide -- and posts the number of particles of the cell ahead of each group
+    sGroupCell[tid] = (cell >= 0 && lane == leaderLane) ? cell : -1;
+    sGroupSize[tid] = __popc(peers);
+    __syncthreads();
+    if (warp == 0) {
+      for (int w = 0; w < kRankThreads / 32; w++) {
+        const int g = 32 * w + lane, c = sGroupCell[g];
+        if (c >= 0) {
+          const int b = cnt[c];
+          cnt[c] = b + sGroupSize[g];
+          sGroupBefore[g] = b;
         }
-        before = __shfl_sync(peers, before, leaderLane);
+        __syncwarp();
       }
-      __syncthreads();
     }
+    __syncthreads();
     if (cell >= 0) {
+      const int before = sGroupBefore[32 * warp + leaderLane]; // particles of the cell ahead of this warp
       int rank = before + __popc(peers & ((1u << lane) - 1u));
       if (K.share) // particles of the lower ranks come first in the global index order
         for (int r = 0; r < K.rank; r++) rank += (int)K.share[(size_t)r * G.cells + cell];

@@ -374,7 +374,7 @@ int doAssign(emcgpu_ctx *ctx, bool withConc, bool closeStep) {
   if (sharded && closeStep) { // the ensemble of this step is the survivors plus the injected particles
     A.closeStep = 2;
   }
-  ngpAssignKernel<<<particleGrid(ctx, 256, 1), 256, A.useSmem ? smem : 0, ctx->stream>>>(G, A);
+  ngpAssignKernel<<<particleGrid(ctx, kAssignThreads, 1), kAssignThreads, A.useSmem ? smem : 0, ctx->stream>>>(G, A);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   if (sharded) {
@@ -511,7 +511,7 @@ int doContacts(emcgpu_ctx *ctx, bool fromStep, const uint64_t *replayDraws, int6
   }
   {
     const size_t counterBytes = (size_t)G.cells * sizeof(int);
-    const int inSmem = counterBytes <= (size_t)ctx->maxSmemOptin - 4096 ? 1 : 0;
+    const int inSmem = counterBytes <= (size_t)ctx->maxSmemOptin - 20480 ? 1 : 0;
     if (inSmem) CUDA_TRY(ctx, cudaFuncSetAttribute(contactRankKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)counterBytes));
     contactRankKernel<<<1, kRankThreads, inSmem ? counterBytes : 0, ctx->stream>>>(G, K, inSmem);
   }
