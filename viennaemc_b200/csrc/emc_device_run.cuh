@@ -132,42 +132,47 @@ __device__ __forceinline__ bool lastBlockDone(unsigned int *ticket) {
   return sLast;
 }
 
-// in-place exclusive scan of a[0..n) by one block (any size that is a multiple of 32, <= 1024); returns the total
+// in-place exclusive scan of a[0..n) by one block (any size that is a multiple of 32, <= 1024); returns the total.
+// Every warp scans a contiguous segment of the array on its own (coalesced rows of 32, a running carry -- no block
+// barrier per row), the warp totals are scanned once, a second pass adds the warp's offset: two block barriers in all.
 __device__ int blockExclusiveScan(int32_t *a, int n) {
-  __shared__ int sCarry;
   __shared__ int sWarp[32];
+  __shared__ int sTotal;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
-  if (threadIdx.x == 0) sCarry = 0;
-  __syncthreads();
-  for (int base = 0; base < n; base += blockDim.x) {
-    const int i = base + threadIdx.x;
-    const int v = i < n ? __ldcg(a + i) : 0;
+  const int rows = (n + 32 * nWarps - 1) / (32 * nWarps); // rows of 32 elements per warp
+  const int begin = min(n, warp * rows * 32), end = min(n, begin + rows * 32);
+  int carry = 0;
+  for (int base = begin; base < end; base += 32) {
+    const int i = base + lane;
+    const int v = i < end ? __ldcg(a + i) : 0;
     int incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += t;
     }
-    if (lane == 31) sWarp[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      int w = lane < nWarps ? sWarp[lane] : 0;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, w, o);
-        if (lane >= o) w += t;
-      }
-      sWarp[lane] = w;
-    }
-    __syncthreads();
-    const int warpOff = warp ? sWarp[warp - 1] : 0;
-    const int carry = sCarry;
-    if (i < n) a[i] = carry + warpOff + incl - v;
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) sCarry = carry + warpOff + incl;
-    __syncthreads();
+    if (i < end) a[i] = carry + incl - v;
+    carry += __shfl_sync(0xffffffffu, incl, 31);
   }
-  return sCarry;
+  if (lane == 0) sWarp[warp] = carry;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = lane < nWarps ? sWarp[lane] : 0;
+    int incl = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    sWarp[lane] = incl - w; // exclusive: elements ahead of the warp's segment
+    if (lane == 31) sTotal = incl;
+  }
+  __syncthreads();
+  const int offset = sWarp[warp];
+  if (offset)
+    for (int i = begin + lane; i < end; i += 32) a[i] += offset;
+  __syncthreads(); // sWarp / sTotal may be reused by the caller's next scan
+  return sTotal;
 }
 
 // ---------------------------------------------------------------------------
