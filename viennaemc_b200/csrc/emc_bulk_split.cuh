@@ -376,18 +376,32 @@ __device__ __forceinline__ void eventRole(const BulkParams &P) {
     for (bool first = true;; first = false) {
       if (active) {
         const FastSub &fs = C.fast[p.valley * EMCGPU_MAX_SUBVALLEYS + p.sub];
+        const FlightConst &f = C.fastV[p.valley].f; // a signed-permutation valley (splitEligible): the a-form of the flight
+        // the full-dt flights between events: fastStep without the accurate energy of every step -- the energy
+        // observable takes (S - 1) / (2 alpha) like the flight kernel, the stored energy is formed once after the last flight
+        FlightAux o;
+        bool flown = false;
         while (s < nSteps && p.tau >= dt) {
           if constexpr (GRAIN) { // a step that ends with a grain event is served below
             const double gNext = __dsub_rn(g, dt);
             if (gNext <= 0.0) break;
             g = gNext;
           }
-          const double vd = fastStep(fs, C.fastV[p.valley], dt, P.box, p.k.x, p.k.y, p.k.z, p.energy, p.tau, p.pos.x,
-                                     p.pos.y, p.pos.z);
-          myObs[(2 * s) * kEventThreads] += p.energy;
-          myObs[(2 * s + 1) * kEventThreads] += vd;
+          flightCore(fs.a[0], fs.a[1], fs.a[2], f.G[0], f.G[1], f.G[2], f.K2, f.c2a, p.k.x, p.k.y, p.k.z, p.pos.x, p.pos.y,
+                     p.pos.z, o);
+          if (mayNeedWrap(p.pos.x, (uint32_t)__double2hiint(P.box.x)) || mayNeedWrap(p.pos.y, (uint32_t)__double2hiint(P.box.y)) ||
+              mayNeedWrap(p.pos.z, (uint32_t)__double2hiint(P.box.z))) {
+            p.pos.x = wrapExact(p.pos.x, P.box.x);
+            p.pos.y = wrapExact(p.pos.y, P.box.y);
+            p.pos.z = wrapExact(p.pos.z, P.box.z);
+          }
+          p.tau -= dt;
+          myObs[(2 * s) * kEventThreads] += flightSm1(o) * f.inv2a;
+          myObs[(2 * s + 1) * kEventThreads] += flightVelocityDt(f.K4[0], f.K4[1], f.K4[2], p.k.x, p.k.y, p.k.z, o);
           s++;
+          flown = true;
         }
+        if (flown) p.energy = flightEnergy(f.fE, o); // as fastStep leaves it (getEnergy of the final k)
         if (s == nSteps) {
           storeParticleState(P, idx, p);
           if constexpr (GRAIN) P.grainTau[idx] = g;
