@@ -234,10 +234,11 @@ def device_run_numbers(budget_s=60.0):
     import re
     import tempfile
     out = {}
-    runs = (("resistor2D", "reference_order", ["--steps", "3000", "--transient", "1000", "--avg", "1000", "--red-black", "0"]),
-            ("resistor2D", "red_black", ["--steps", "3000", "--transient", "1000", "--avg", "1000", "--red-black", "1"]),
+    # run lengths: >= 1 s of Monte Carlo loop each, so that the clock ramp of an idle GPU does not weigh
+    runs = (("resistor2D", "reference_order", ["--steps", "6000", "--transient", "2000", "--avg", "2000", "--red-black", "0"]),
+            ("resistor2D", "red_black", ["--steps", "10000", "--transient", "3000", "--avg", "3000", "--red-black", "1"]),
             ("mosfet2D", "reference_order", ["--steps", "300", "--transient", "100", "--avg", "100", "--red-black", "0"]),
-            ("mosfet2D", "red_black", ["--steps", "600", "--transient", "200", "--avg", "200", "--red-black", "1"]))
+            ("mosfet2D", "red_black", ["--steps", "3000", "--transient", "1000", "--avg", "1000", "--red-black", "1"]))
     t_end = time.time() + budget_s
     for exe, order, extra in runs:
         path = os.path.join(ROOT, "viennaemc_b200", "bin", exe)
@@ -286,8 +287,8 @@ def sharded_device_runs(rank, world, local_rank, id_dir):
     itself asserts that the potential and the averaged concentration are bit-identical on all ranks.  Rank 0 reports."""
     import re
     out = {}
-    runs = (("resistor2D", ["--steps", "3000", "--transient", "1000", "--avg", "1000"]),
-            ("mosfet2D", ["--steps", "600", "--transient", "200", "--avg", "200"]))
+    runs = (("resistor2D", ["--steps", "10000", "--transient", "3000", "--avg", "3000"]),
+            ("mosfet2D", ["--steps", "3000", "--transient", "1000", "--avg", "1000"]))
     for exe, extra in runs:
         path = os.path.join(ROOT, "viennaemc_b200", "bin", exe)
         if not os.path.exists(path):
@@ -566,7 +567,6 @@ def main_ours(args):
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "one_step_per_launch": one_step,
             "observables": {"mean_energy_eV": mean_e, "mean_drift_velocity_m_s": mean_v}}
-    ctx.close()  # the legs below start processes of their own on this GPU: give the ensemble's memory back first
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:
@@ -577,7 +577,7 @@ def main_ours(args):
                                         "sample": f"failed: {exc}"}
         if world == 1 and not args.no_dropin_loop:
             try:
-                line["dropin_loop"] = dropin_loop(n_local, 8 * SPL, SPL, local_rank)
+                line["dropin_loop"] = dropin_loop(n_local, 40 * SPL, SPL, local_rank)  # 960 steps: ~0.4 s, start-up of the process amortised
                 line["dropin_loop"]["frac_of_value"] = line["dropin_loop"].get("value", 0.0) / value
             except Exception as exc:
                 line["dropin_loop"] = {"failed": str(exc)}
@@ -586,6 +586,7 @@ def main_ours(args):
                 line["device_runs"] = device_run_numbers()
             except Exception as exc:
                 line["device_runs"] = {"failed": str(exc)}
+    ctx.close()
     if world > 1:
         if not args.no_device_runs:
             # configs 3 / 4 sharded over all GPUs of the run: every rank starts the C++ driver of its rank
