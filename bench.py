@@ -473,7 +473,7 @@ def main_ours(args):
                 raise RuntimeError("particle count not conserved in emcgpu_bulk_run_host")
             e2e = {"value": n_total * K / (e2e_ms * 1e-3), "unit": UNIT, **e2e_bytes, "ms_total": e2e_ms,
                    "what": f"emcgpu_bulk_run_host on pinned host arrays ({K} time steps, {SPL} per launch, host "
-                           "observables): the ensemble is cut into ~8 slices, each slice is copied in, advanced K steps "
+                           "observables): the ensemble is cut into ~8 slices (~16 for K < 128), each slice is copied in, advanced K steps "
                            "and copied back with the copies of the neighbouring slices overlapping its kernels; all "
                            "inside the timed region (per rank)",
                    "unpipelined": unpipelined}

@@ -320,7 +320,7 @@ int emcgpu_kernel_times(emcgpu_ctx *ctx, double *ms, int64_t *launches, int rese
  * emcgpu_set_ensemble, updated IN PLACE).  The arrays should be PINNED (cudaHostAlloc / cudaHostRegister): only then
  * are the copies asynchronous and overlap the kernels; with pageable arrays the call is still correct, but every
  * cudaMemcpyAsync blocks the host thread and the copies and kernels run one after the other.  The ensemble is cut into
- * slices of sliceParticles (<= 0: about n/8) and slice i runs its nSteps steps while slice i+1 is copied to the
+ * slices of sliceParticles (<= 0: about n/8, n/16 for runs of fewer than 128 steps) and slice i runs its nSteps steps while slice i+1 is copied to the
  * device and slice i-1 back, so the PCIe transfers hide behind the step kernels and n is not limited by the HBM
  * size. Results equal emcgpu_set_ensemble + emcgpu_bulk_step + emcgpu_get_ensemble (particle states bit for bit,
  * the Philox stream of a particle is keyed by particleIdBase + index; obs = the same sums in another order).

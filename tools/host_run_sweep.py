@@ -5,7 +5,7 @@ import numpy as np
 import torch
 from viennaemc_b200 import capi, hostapi
 
-N, K, SPL, DT, DOPING = 100_000_000, 1000, 8, 1e-16, 1e23
+N, K, SPL, DT, DOPING = 100_000_000, int(os.environ.get("SWEEP_K", "1000")), 24, 1e-16, 1e23
 box = [(N / DOPING) ** (1.0 / 3.0)] * 3
 ctx = capi.Context(0)
 ctx.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -20,7 +20,7 @@ packed = hp.numpy().view(np.uint32)
 ctx.get_ensemble_into(streams, packed)
 out = {}
 quantum = 148 * 16 * 64
-for slices in (16, 12, 8, 6, 4, 3, 24):
+for slices in (32, 24, 16, 12, 8, 6, 4):
     sl = ((N // slices + quantum - 1) // quantum) * quantum
     ctx.bulk_run_host(streams, packed, DT, SPL, SPL, sl, want_obs=False)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -29,4 +29,4 @@ for slices in (16, 12, 8, 6, 4, 3, 24):
     e1.record(); torch.cuda.synchronize()
     out[slices] = e0.elapsed_time(e1)
     print(slices, sl, out[slices], flush=True)
-json.dump(out, open("gpurun_out/host_run_sweep.json", "w"))
+json.dump(out, open("gpurun_out/host_run_sweep_k%d.json" % K, "w"))

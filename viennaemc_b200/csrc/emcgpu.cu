@@ -1156,10 +1156,13 @@ int emcgpu_bulk_run_host(emcgpu_ctx *ctx, int64_t n, double *const *soa, uint32_
   CUDA_TRY(ctx, ctx->dObs.ensure(obsBytes));
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->dObs.ptr, 0, obsBytes, ctx->stream));
   if (n > 0) {
-    // slice: a multiple of what one pass of the deferred-event kernel takes (all SMs x warps x chunk), about n/8
-    // (measured at n = 1e8, 1000 steps: 3 slices 988 ms, 4: 973, 6: 965, 8: 960, 12: 970, 16: 985, 24: 1050)
+    // slice: a multiple of what one pass of the deferred-event kernel takes (all SMs x warps x chunk), about n/8 -- n/16 for
+    // short runs, which are bound by the copies and gain from a shorter fill and drain of the pipeline
+    // (measured at n = 1e8 with the flight / event pair, profiles/bench/r2_y_host_run_sweep.json: 1000 steps -- 4 slices 452 ms,
+    // 6: 436, 8: 440, 12: 447, 16: 448, 24: 463, 32: 527; 20 steps -- 4: 172, 6: 166, 8: 158, 12: 155, 16: 153, 24: 154, 32: 154)
     const int64_t quantum = (int64_t)ctx->smCount * kDeferWarps * kDeferChunk;
-    int64_t slice = sliceParticles > 0 ? sliceParticles : std::max<int64_t>((n / 8 + quantum - 1) / quantum * quantum, 16 * quantum);
+    const int64_t parts = nSteps < 128 ? 16 : 8;
+    int64_t slice = sliceParticles > 0 ? sliceParticles : std::max<int64_t>((n / parts + quantum - 1) / quantum * quantum, 16 * quantum);
     slice = std::min(slice, n);
     if (slice >= (int64_t)1 << 32) return fail(ctx, EMCGPU_E_CAPACITY, "at most 2^32-1 particles per slice");
     const int nBuf = 3;
