@@ -496,9 +496,48 @@ def main_ours(args):
         if K < 200 and not args.no_e2e_long:
             # the same call on a run long enough to amortise the two copies (K = 1000 time steps)
             KL = 1000
+            long_sampler = ClockSampler(local_rank)
+            if rank == 0:
+                long_sampler.start()
             long_ms = timed(lambda: ctx.bulk_run_host(streams, packed, DT, KL, SPL, 0, particle_id_base=base_id, want_obs=False))
             e2e["long_run"] = {"steps": KL, "value": n_total * KL / (long_ms * 1e-3), "unit": UNIT, "ms_total": long_ms,
                                "h2d_bytes_per_step": 68.0 * n_local / KL, "d2h_bytes_per_step": 68.0 * n_local / KL}
+            if rank == 0:  # a run this long is where a power or thermal cap would show
+                e2e["long_run"]["clocks"] = long_sampler.stop()
+        # both directions AT ONCE (what a pipelined run actually gets from the link): one half of every array goes in while the
+        # other half comes back, on two streams; twice that time = 68 B per particle each way in full duplex
+        try:
+            dev = [torch.empty(n_local, dtype=torch.float64, device="cuda") for _ in range(capi.N_STREAMS)]
+            dev_packed = torch.empty(n_local, dtype=torch.int32, device="cuda")
+            s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+            half = n_local // 2
+
+            def duplex():
+                cur = torch.cuda.current_stream()
+                s_in.wait_stream(cur)
+                s_out.wait_stream(cur)
+                with torch.cuda.stream(s_in):
+                    for a, d in zip(host, dev):
+                        d[:half].copy_(a[:half], non_blocking=True)
+                    dev_packed[:half].copy_(host_packed[:half], non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    for a, d in zip(host, dev):
+                        a[half:].copy_(d[half:], non_blocking=True)
+                    host_packed[half:].copy_(dev_packed[half:], non_blocking=True)
+                cur.wait_stream(s_in)
+                cur.wait_stream(s_out)
+
+            duplex()
+            t_duplex = 2.0 * timed(duplex)
+            cc = e2e["copy_ceiling"]
+            cc["duplex_ms"] = t_duplex
+            cc["duplex_value"] = n_total * K / (t_duplex * 1e-3)
+            cc["frac_of_duplex"] = e2e["value"] / cc["duplex_value"]
+            cc["what"] += ("; duplex_ms = the same bytes with both directions busy at the same time (two streams, half of every "
+                           "array each way, time doubled): the bound of a PIPELINED run, frac_of_duplex = e2e / that")
+            del dev, dev_packed
+        except Exception as exc:  # reported, never required
+            e2e["copy_ceiling"]["duplex_failed"] = str(exc)
         del host, host_packed
 
     # ---- roofline of the step kernel -------------------------------------------------------------
