@@ -195,7 +195,13 @@ __global__ void concentrationKernel(const __grid_constant__ DevGeometry G, const
 //   NEC:      calcEFieldAtEdgeMidPts (:35-53): Vt (phi[here] - phi[next]) / h in the interior;
 //   both with setEFieldBoundaryValues (:58-82): on a face 0 (artificial boundary) or the inner neighbour's value (contact);
 //   NEC-VWD:  examples/mosfet2D/NECSchemeVWD.hpp:82-99: forward difference everywhere, 0 on the max face.
-__device__ __forceinline__ void cellEField(const DevGeometry &G, int cell, const double *pot, double *e) {
+// CG: the potential was just written by other SMs of the same launch (cluster solver): read it past L1
+template <bool CG = false>
+__device__ __forceinline__ void cellEField(const DevGeometry &G, int cell, const double *potIn, double *e) {
+  struct Pot {
+    const double *p;
+    __device__ __forceinline__ double operator[](int i) const { return CG ? __ldcg(p + i) : p[i]; }
+  } pot{potIn};
   int c[3];
   cellCoord(G, cell, c);
   const int stride[3] = {1, G.extent[0], G.extent[0] * G.extent[1]};
@@ -1203,8 +1209,14 @@ __global__ void __launch_bounds__(THREADS) sorRedBlackClusterFastKernel(const __
     *S.sweepsOut = sweeps;
     if (S.ctl && S.sweepsPerStep) S.sweepsPerStep[S.ctl->slot] = sweeps;
   }
-  // no CTA leaves while a peer may still read its band (the neighbour rows of the last sweep)
+  // no CTA leaves while a peer may still read its band (the neighbour rows of the last sweep); with the field asked for,
+  // the barrier also publishes the potential every CTA has just written (device-scope fence before it)
+  if (S.efield) __threadfence();
   cluster.sync();
+  // the field of this CTA's rows follows the potential inside the same launch (difference quotients reach up to two rows
+  // into the neighbouring bands: read from global memory, past L1)
+  if (S.efield)
+    for (int i = tid; i < myRows * ex; i += THREADS) cellEField<true>(G, row0 * ex + i, S.pot, S.efield);
 }
 
 // Dirichlet values at ohmic contacts (emcSORSolver.hpp:57-73, :139-155); faces in the reference's order

@@ -274,9 +274,7 @@ int doPoisson(emcgpu_ctx *ctx, bool equilibrium, double accuracyVolt, double ome
         e = cudaOccupancyMaxActiveClusters(&nClusters, kernel, &cfg);
         return e != cudaSuccess ? e : nClusters >= 1 ? cudaSuccess : cudaErrorInvalidConfiguration;
       }
-      SorParams S2 = S;
-      S2.efield = nullptr;
-      void *args[] = {(void *)&G, (void *)&S2};
+      void *args[] = {(void *)&G, (void *)&S}; // the field follows the potential inside the launch
       return cudaLaunchKernelExC(&cfg, kernel, args);
     };
     const long long fastKey = (long long)G.extent[0] * 1000003LL + nRowsRb * 4LL + G.dim;
@@ -290,10 +288,6 @@ int doPoisson(emcgpu_ctx *ctx, bool equilibrium, double accuracyVolt, double ome
     if ((ctx->optSorKernel == 0 || ctx->optSorKernel == 3) && ctx->sorFast > 0) {
       CUDA_TRY(ctx, ctx->sorFast == 2 && ctx->optSorKernel == 0 ? fastLaunch(kSorClusterSizeWide, kSorClusterThreadsWide, false)
                                       : fastLaunch(kSorClusterSize, kSorClusterThreads, false));
-      if (S.efield) {
-        efieldAfterSolveKernel<<<gridBlocks(G.cells), 256, 0, ctx->stream>>>(G, S.pot, S.efield, S.ctl);
-        ctx->launches++;
-      }
     } else if (ctx->optSorKernel != 1 && nRowsRb >= kSorClusterSize && bandBytes <= (size_t)ctx->maxSmemOptin - 4096 &&
         (G.extent[0] + 1) / 2 <= kSorClusterThreads) {
       auto kernel = G.dim == 2 ? sorRedBlackClusterKernel<2> : sorRedBlackClusterKernel<3>;
