@@ -1569,13 +1569,14 @@ struct EnsemblePtrs {
   double *grain;    // grain clocks travel with their particle (may be null)
 };
 
-__global__ void __launch_bounds__(kChunk)
-    compactScatterKernel(const int32_t *flag, const RunCtl *ctl, const int32_t *chunkOffset, EnsemblePtrs src, EnsemblePtrs dst) {
+// (block `blk` of `nBlk` blocks of kChunk threads: the kernel below, or the compaction blocks of compactInjectKernel)
+__device__ __forceinline__ void compactScatterRole(const int32_t *flag, const RunCtl *ctl, const int32_t *chunkOffset,
+                                                   const EnsemblePtrs &src, const EnsemblePtrs &dst, int blk, int nBlk) {
   __shared__ int sWarp[kChunk / 32];
   const int64_t n = ctl->n;
   const int nChunks = (int)((n + kChunk - 1) / kChunk);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int chunk = blockIdx.x; chunk < nChunks; chunk += gridDim.x) {
+  for (int chunk = blk; chunk < nChunks; chunk += nBlk) {
     const int64_t i = (int64_t)chunk * kChunk + threadIdx.x;
     const bool keep = i < n && flag[i] != kGone;
     const unsigned b = __ballot_sync(0xffffffffu, keep);
@@ -1593,6 +1594,10 @@ __global__ void __launch_bounds__(kChunk)
     }
     __syncthreads();
   }
+}
+__global__ void __launch_bounds__(kChunk)
+    compactScatterKernel(const int32_t *flag, const RunCtl *ctl, const int32_t *chunkOffset, EnsemblePtrs src, EnsemblePtrs dst) {
+  compactScatterRole(flag, ctl, chunkOffset, src, dst, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // ---------------------------------------------------------------------------
@@ -1729,19 +1734,19 @@ struct InjectParams {
 };
 
 template <int DIM>
-__global__ void __launch_bounds__(128) contactInjectKernel(const __grid_constant__ DevGeometry G, const InjectParams J) {
+__device__ __forceinline__ void contactInjectRole(const DevGeometry &G, const InjectParams &J, int blk, int nBlk) {
   const DevModel &model = *J.model;
   const int total = J.injectCount[G.cells];
   const int64_t first = J.ctl->nKept;
   const long long step = J.ctl->step;
   if (first + total > J.ctl->capacity) { // the host reserves head room between chunks; running out of it is an error
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (blk == 0 && threadIdx.x == 0) {
       atomicExch(J.status, (int)EMCGPU_E_CAPACITY);
       J.ctl->toInject = 0; // keeps the later kernels of the chunk inside the allocation
     }
     return;
   }
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x) {
+  for (int j = blk * blockDim.x + threadIdx.x; j < total; j += nBlk * blockDim.x) {
     // cell of injected particle j: the last cell whose offset is <= j (empty cells share the offset of their successor)
     int lo = 0, hi = G.cells - 1;
     while (lo < hi) {
@@ -1815,6 +1820,22 @@ __global__ void __launch_bounds__(128) contactInjectKernel(const __grid_constant
     if (J.ens.cursor) J.ens.cursor[at] = 0;
     if (J.ens.grain) J.ens.grain[at] = __dmul_rn(-log(uniformLog(raw[d++])), J.grainTau0);
   }
+}
+template <int DIM>
+__global__ void __launch_bounds__(128) contactInjectKernel(const __grid_constant__ DevGeometry G, const InjectParams J) {
+  contactInjectRole<DIM>(G, J, (int)blockIdx.x, (int)gridDim.x);
+}
+// The order-preserving compaction and the injection behind the survivors in ONE launch: the two write disjoint parts of the
+// new ensemble ([0, nKept) and [nKept, nKept + toInject)) and both only need the counts of the kernels before them.  The
+// first compactBlocks blocks compact, the others inject (J.ens = the ensemble the compaction writes).
+template <int DIM>
+__global__ void __launch_bounds__(kChunk)
+    compactInjectKernel(const __grid_constant__ DevGeometry G, const __grid_constant__ InjectParams J, const int32_t *flag,
+                        const int32_t *chunkOffset, const __grid_constant__ EnsemblePtrs src, int compactBlocks) {
+  if ((int)blockIdx.x < compactBlocks)
+    compactScatterRole(flag, J.ctl, chunkOffset, src, J.ens, (int)blockIdx.x, compactBlocks);
+  else
+    contactInjectRole<DIM>(G, J, (int)blockIdx.x - compactBlocks, (int)gridDim.x - compactBlocks);
 }
 
 } // namespace emc

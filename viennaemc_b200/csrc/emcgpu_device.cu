@@ -440,7 +440,8 @@ int doStep(emcgpu_ctx *ctx, double dt) {
 }
 
 // drop the particles flagged kGone, keeping the order of the others (into the twin buffer, which becomes the ensemble)
-int doCompaction(emcgpu_ctx *ctx) {
+// inject != nullptr: the injection behind the survivors rides in the same launch (inject->ens is set here)
+int doCompaction(emcgpu_ctx *ctx, InjectParams *inject = nullptr) {
   DeviceRunState *r = ctx->run;
   RunCtl *ctl = r->dCtl.as<RunCtl>();
   const int32_t *flag = r->dFlag.as<const int32_t>();
@@ -454,7 +455,16 @@ int doCompaction(emcgpu_ctx *ctx) {
                             grain ? ctx->dGrain.as<double>() : nullptr);
   EnsemblePtrs dst = ptrsOf(r->altEnsemble.ptr, ctx->capacity, replay ? r->altCursor.as<uint32_t>() : nullptr,
                             grain ? r->altGrain.as<double>() : nullptr);
-  compactScatterKernel<<<grid, kChunk, 0, ctx->stream>>>(flag, ctl, chunkCount, src, dst);
+  if (inject) {
+    const int injectGrid = 4; // a few hundred particles per step at most; grid-stride
+    inject->ens = dst;
+    if (r->dim == 2)
+      compactInjectKernel<2><<<grid + injectGrid, kChunk, 0, ctx->stream>>>(r->geo, *inject, flag, chunkCount, src, grid);
+    else
+      compactInjectKernel<3><<<grid + injectGrid, kChunk, 0, ctx->stream>>>(r->geo, *inject, flag, chunkCount, src, grid);
+  } else {
+    compactScatterKernel<<<grid, kChunk, 0, ctx->stream>>>(flag, ctl, chunkCount, src, dst);
+  }
   ctx->launches += 2;
   CUDA_TRY(ctx, cudaGetLastError());
   std::swap(ctx->dEnsemble, r->altEnsemble);
@@ -511,10 +521,7 @@ int doContacts(emcgpu_ctx *ctx, bool fromStep, const uint64_t *replayDraws, int6
   }
   ctx->launches += 3;
   CUDA_TRY(ctx, cudaGetLastError());
-  if (int rc = doCompaction(ctx)) return rc;
   InjectParams J;
-  J.ens = ptrsOf(ctx->dEnsemble.ptr, ctx->capacity, ctx->rngMode == RNG_REPLAY ? ctx->dCursor.as<uint32_t>() : nullptr,
-                 ctx->grainOn ? ctx->dGrain.as<double>() : nullptr);
   J.grainTau0 = ctx->grainTau0;
   J.injectCount = K.injectCount;
   J.model = ctx->dModel.as<const DevModel>();
@@ -530,14 +537,7 @@ int doContacts(emcgpu_ctx *ctx, bool fromStep, const uint64_t *replayDraws, int6
     J.replay = r->dReplay.as<const uint64_t>();
     J.replayCount = nReplay;
   }
-  const int injectGrid = 8; // a few hundred particles per step at most; grid-stride
-  if (r->dim == 2)
-    contactInjectKernel<2><<<injectGrid, 128, 0, ctx->stream>>>(G, J);
-  else
-    contactInjectKernel<3><<<injectGrid, 128, 0, ctx->stream>>>(G, J);
-  ctx->launches++;
-  CUDA_TRY(ctx, cudaGetLastError());
-  return EMCGPU_OK;
+  return doCompaction(ctx, &J); // compaction and injection in one launch
 }
 
 } // namespace
