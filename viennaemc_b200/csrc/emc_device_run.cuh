@@ -1244,6 +1244,9 @@ struct DeviceStepParams {
   double charge;
   int32_t *flag;     // [capacity] out
   RunCtl *ctl;       // n, step index, removedPerContact
+  // not nullptr: the kernel also does the work of selectCountKernel<SELECT_RESERVOIR> -- reservoir particles per chunk of
+  // kChunk consecutive particles, turned into offsets by the block that finishes last (ctl->nReservoir)
+  int32_t *chunkCount;
 };
 
 // emcSurfaceScatterMechanism (SurfaceScatterMechanisms/emcSurfaceScatterMechanism.hpp): with probability pDiff the
@@ -1415,8 +1418,12 @@ __global__ void __launch_bounds__(kBulkThreads, 2)
   using A = Arith<EXACT>;
   const int64_t n = D.ctl->n;
   const long long step = D.ctl->step;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  // a block takes whole chunks of kBulkThreads (= kChunk of the ordered selections below) consecutive particles
+  const int nChunks = (int)((n + kBulkThreads - 1) / kBulkThreads);
+  for (int chunk = blockIdx.x; chunk < nChunks; chunk += gridDim.x) {
+    const int64_t i = (int64_t)chunk * kBulkThreads + threadIdx.x;
+    bool inReservoir = false;
+    if (i < n) {
     Particle p;
     Rng rng;
     loadParticle(P, i, p, rng);
@@ -1481,8 +1488,19 @@ __global__ void __launch_bounds__(kBulkThreads, 2)
       D.flag[i] = kGone;
       atomicAdd(&D.ctl->removedPerContact[cellContact(G, cell)], 1);
     } else {
-      D.flag[i] = (G.cellKind[cell] & 1u) ? cell : kFree;
+      inReservoir = (G.cellKind[cell] & 1u) != 0;
+      D.flag[i] = inReservoir ? cell : kFree;
     }
+    }
+    if (D.chunkCount) { // block-uniform
+      const int count = __syncthreads_count(inReservoir);
+      if (threadIdx.x == 0) D.chunkCount[chunk] = count;
+    }
+  }
+  if (D.chunkCount) {
+    if (!lastBlockDone(&D.ctl->ticket[0])) return; // the ticket of selectCountKernel<SELECT_RESERVOIR>
+    const int total = blockExclusiveScan(D.chunkCount, nChunks);
+    if (threadIdx.x == 0) D.ctl->nReservoir = total;
   }
 }
 

@@ -411,7 +411,9 @@ template <bool EXACT, int MODE> cudaError_t launchStepDim(emcgpu_ctx *ctx, const
 }
 
 // particle step: ensemble in place, flags for the contact handling / compaction, removedPerContact in the control block
-int doStep(emcgpu_ctx *ctx, double dt) {
+// countReservoir: the step kernel also counts the reservoir particles per chunk (the contact handling that follows in the
+// same step then starts at its list kernel)
+int doStep(emcgpu_ctx *ctx, double dt, bool countReservoir = false) {
   DeviceRunState *r = ctx->run;
   DeviceStepParams D;
   fillParams(ctx, D.P);
@@ -421,6 +423,7 @@ int doStep(emcgpu_ctx *ctx, double dt) {
   D.charge = r->charge;
   D.flag = r->dFlag.as<int32_t>();
   D.ctl = r->dCtl.as<RunCtl>();
+  D.chunkCount = countReservoir ? r->dChunkCount.as<int32_t>() : nullptr;
   bool inSmem = true;
   size_t smem = BulkSmem(0, ctx->hModel.nValleys, (int)ctx->hMechs.size(), ctx->hModel.tableDoubles, true, 0).total;
   if (smem > (size_t)ctx->maxSmemOptin / 2) { // two CTAs per SM
@@ -477,7 +480,8 @@ int doCompaction(emcgpu_ctx *ctx, InjectParams *inject = nullptr) {
 
 // ohmic contacts on the flags of the step (fromStep) or of the resting ensemble: excess particles -> kGone,
 // compaction, injection behind the survivors
-int doContacts(emcgpu_ctx *ctx, bool fromStep, const uint64_t *replayDraws, int64_t nReplay) {
+// countedByStep: the step kernel has counted the reservoir particles already (doStep(..., true))
+int doContacts(emcgpu_ctx *ctx, bool fromStep, const uint64_t *replayDraws, int64_t nReplay, bool countedByStep = false) {
   DeviceRunState *r = ctx->run;
   const DevGeometry &G = r->geo;
   RunCtl *ctl = r->dCtl.as<RunCtl>();
@@ -489,7 +493,7 @@ int doContacts(emcgpu_ctx *ctx, bool fromStep, const uint64_t *replayDraws, int6
                                                                             ctx->dStream[EMCGPU_Z], ctl, flag);
     ctx->launches++;
   }
-  selectCountKernel<SELECT_RESERVOIR><<<grid, kChunk, 0, ctx->stream>>>(flag, ctl, chunkCount);
+  if (!countedByStep) selectCountKernel<SELECT_RESERVOIR><<<grid, kChunk, 0, ctx->stream>>>(flag, ctl, chunkCount);
   reservoirListKernel<<<grid, kChunk, 0, ctx->stream>>>(flag, ctl, chunkCount, r->dListParticle.as<int32_t>(),
                                                         r->dListCell.as<int32_t>());
   ContactParams K;
@@ -863,8 +867,8 @@ int emcgpu_device_run_averaging(emcgpu_ctx *ctx, double dt, int nSteps, int nAve
     for (int s = 0; s < chunk; s++) {
       // performEMCStep (emcSimulation.hpp:177-192)
       if (int rc = doPoisson(ctx, false, accuracyVolt, omega, resetBCFirst && done + s == 0, true, true)) return rc;
-      if (int rc = doStep(ctx, dt)) return rc;
-      if (int rc = doContacts(ctx, true, nullptr, 0)) return rc;
+      if (int rc = doStep(ctx, dt, true)) return rc;
+      if (int rc = doContacts(ctx, true, nullptr, 0, true)) return rc;
       if (int rc = doAssign(ctx, true, true)) return rc;
     }
     if (counters)
