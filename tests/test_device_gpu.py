@@ -19,13 +19,13 @@ pytestmark = pytest.mark.gpu
 CASES = list(DEVICE_CASES)
 
 
-def configure(ctx, dev: po.Device, expected=None, math_mode=capi.MATH_EXACT):
+def configure(ctx, dev: po.Device, expected=None, math_mode=capi.MATH_EXACT, nr_carriers=1.0):
     if expected is None and dev.electron_kind == po.ELECTRON_VWD:
         expected = dev.expected_at_contact()  # the library's default is emcElectron's rule (no rounding)
     ctx.device_configure(dev.dim, dev.extent, dev.spacing, dev.max_pos, dev.vt, dev.debye, dev.ni, dev.cell_volume,
                          dev.eps_r, dev.contact_type, dev.contact_voltage, dev.gate_eps, dev.gate_thick,
                          dev.gate_barrier, dev.region, dev.face_contact, dev.doping, expected=expected,
-                         math_mode=math_mode, pm_scheme=dev.pm_scheme)
+                         math_mode=math_mode, pm_scheme=dev.pm_scheme, nr_carriers=nr_carriers)
     for face in range(2 * dev.dim):
         if dev.surface_kind[face]:
             ctx.device_set_surface(face, dev.surface_kind[face], dev.surface_param[face])
@@ -192,6 +192,42 @@ def test_contacts_replay_the_reference(gpu_ctx_factory, case):
         assert_grid_close(ctx.device_get_grid(capi.GRID_CONCENTRATION), g[p + "conc"], "concentration",
                           1e-12 if dev.pm_scheme == po.PM_CIC else 1e-15)
     assert injected_total > 0
+
+
+@pytest.mark.parametrize("case", ["device_nec", "device_vwd"])
+@pytest.mark.parametrize("nr_carriers", [1.0, 3.0, 2.5])
+def test_nec_deposit_by_integer_hits(gpu_ctx_factory, case, nr_carriers):
+    """NEC / NEC-VWD charge assignment (2-D schemes): the default kernel counts particles per mesh cell with integer atomics
+    and lets every node collect its four cells (integer-valued carriers per particle only; 2.5 takes the fp64 atomics); option
+    assign_fp64 forces one fp64 atomic per corner.  Both equal the oracle's deposit bit for bit, also with particles on the
+    lower and just inside the upper faces of the device."""
+    g = load_golden(case)
+    m, dev = build_device(case)
+    ens = ens_from(g, "init_")
+    rng = np.random.default_rng(7)
+    if ens.n < 1000:  # some fixtures hold few particles: crowd the box instead
+        ens = po.Ensemble(5000)
+        ens.n = 5000
+        ens.x[:], ens.y[:] = rng.uniform(0, dev.max_pos[0], ens.n), rng.uniform(0, dev.max_pos[1], ens.n)
+        if dev.dim > 2:
+            ens.z[:] = rng.uniform(0, dev.max_pos[2], ens.n)
+    k = min(64, ens.n)  # some particles on the lower faces and just inside the upper faces and corners of the box
+    ens.x[:k] = rng.choice([0.0, np.nextafter(dev.max_pos[0], 0.0)], k)
+    ens.y[k // 2:k] = rng.choice([0.0, np.nextafter(dev.max_pos[1], 0.0)], k - k // 2)
+    if dev.dim > 2:
+        ens.z[k // 4:k // 2] = np.nextafter(dev.max_pos[2], 0.0)
+    want = dev.assign(ens, nr_carriers)
+    got = {}
+    for fp64 in (0, 1):
+        ctx = gpu_ctx_factory()
+        upload_model(ctx, m)
+        configure(ctx, dev, nr_carriers=nr_carriers)
+        ctx.set_option("assign_fp64", fp64)
+        upload_ensemble(ctx, ens)
+        ctx.device_assign()
+        got[fp64] = ctx.device_get_grid(capi.GRID_COUNT)
+        assert got[fp64].sum() == nr_carriers * ens.n
+        assert np.array_equal(got[fp64], np.asarray(want).ravel()), f"assign_fp64={fp64}"
 
 
 def test_self_consistent_run_conserves_bookkeeping_and_stays_physical(gpu_ctx_factory):

@@ -259,14 +259,15 @@ struct AssignParams {
   RunCtl *ctl;
   int32_t *counters; // [slots][2][nContacts] or nullptr
   int32_t closeStep; // 1: the ensemble is ctl->nKept + ctl->toInject particles and the step ends here; 2: only the former
-  int32_t useSmem;
+  int32_t useSmem;   // 1: fp64 copy of the grid in shared memory, 2: integer hits per mesh cell (NEC / NEC-VWD)
+  int32_t *hits;     // [cells], zeroed by the caller (useSmem == 2)
 };
 
 constexpr int kAssignThreads = 1024; // the block that finishes last forms the concentration of the whole grid alone
 __global__ void __launch_bounds__(kAssignThreads) ngpAssignKernel(const __grid_constant__ DevGeometry G, const AssignParams A) {
   extern __shared__ double sCount[];
   const int64_t n = A.closeStep ? A.ctl->nKept + A.ctl->toInject : A.ctl->n;
-  if (A.useSmem) {
+  if (A.useSmem == 1) {
     for (int i = threadIdx.x; i < G.cells; i += blockDim.x) sCount[i] = 0.0;
     __syncthreads();
   }
@@ -274,7 +275,24 @@ __global__ void __launch_bounds__(kAssignThreads) ngpAssignKernel(const __grid_c
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t nRounded = (n + 31) & ~int64_t(31);
   double *target = A.useSmem ? sCount : A.count;
-  if (G.pmScheme == PM_NGP) {
+  if (A.useSmem == 2) {
+    // NEC / NEC-VWD with an integer-valued nrCarriers (the host checks it): every deposit is the same share, so a node's
+    // sum is share x (particles in the up to 2^dim mesh cells it is a corner of), exact whatever the order.  Particles are
+    // counted per mesh cell (one warp-aggregated integer atomic per particle instead of 2^dim fp64 atomics); the block that
+    // finishes last lets every node collect its cells.
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nRounded; i += stride) {
+      const bool live = i < n;
+      int base = -1;
+      if (live) {
+        const double pos[3] = {A.x[i], A.y[i], G.dim > 2 ? A.z[i] : 0.0};
+        double w[3];
+        int c[3];
+        base = posToLowerCell(G, pos, w, c);
+      }
+      const unsigned peers = __match_any_sync(0xffffffffu, base);
+      if (live && lane == __ffs(peers) - 1) atomicAdd(&A.hits[base], __popc(peers));
+    }
+  } else if (G.pmScheme == PM_NGP) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nRounded; i += stride) {
       const bool live = i < n;
       const int cell = live ? posToCell(G, A.x[i], A.y[i], G.dim > 2 ? A.z[i] : 0.0) : -1;
@@ -317,23 +335,60 @@ __global__ void __launch_bounds__(kAssignThreads) ngpAssignKernel(const __grid_c
       }
     }
   }
-  if (A.useSmem) {
+  if (A.useSmem == 1) {
     __syncthreads();
     for (int i = threadIdx.x; i < G.cells; i += blockDim.x)
       if (sCount[i] != 0.0) atomicAdd(&A.count[i], sCount[i]);
   }
-  if (!A.conc && A.closeStep != 1) return;
+  const bool fromHits = A.useSmem == 2;
+  if (!fromHits && !A.conc && A.closeStep != 1) return;
   if (!lastBlockDone(&A.ctl->ticket[3])) return;
   const bool average = A.closeStep == 1 && A.ctl->slot >= A.ctl->avgFromSlot;
-  if (A.conc)
-    for (int cell = threadIdx.x; cell < G.cells; cell += blockDim.x) {
-      const double v = cellConcentration(G, cell, __ldcg(A.count + cell));
-      A.conc[cell] = v;
-      if (average) {
-        A.sumPot[cell] = __dadd_rn(A.sumPot[cell], A.pot[cell]);
-        A.sumConc[cell] = __dadd_rn(A.sumConc[cell], v);
+  if (A.conc || fromHits) {
+    // one block, the whole grid: kBatch cells per thread at a time, all their loads in flight before the first division
+    constexpr int kBatch = 4;
+    const int sy = G.extent[0], sz = G.extent[0] * G.extent[1];
+    const double share = __dmul_rn(G.dim == 2 ? 0.25 : 0.125, A.nrCarriers);
+    for (int cell0 = threadIdx.x; cell0 < G.cells; cell0 += kBatch * blockDim.x) {
+      double count[kBatch], pot[kBatch], sumPot[kBatch], sumConc[kBatch];
+#pragma unroll
+      for (int k = 0; k < kBatch; k++) {
+        const int cell = cell0 + k * blockDim.x;
+        if (cell >= G.cells) break;
+        if (fromHits) {
+          // a mesh cell never starts in the last column / row / plane, so the cells reached across a row or plane end hold 0
+          int h = 0;
+          for (int dz = 0; dz < (G.dim > 2 ? 2 : 1); dz++)
+            for (int dy = 0; dy < 2; dy++)
+              for (int dx = 0; dx < 2; dx++) {
+                const int b = cell - dx - dy * sy - dz * sz;
+                if (b >= 0) h += __ldcg(A.hits + b);
+              }
+          count[k] = __dmul_rn(share, (double)h);
+        } else {
+          count[k] = __ldcg(A.count + cell);
+        }
+        if (average) {
+          pot[k] = A.pot[cell];
+          sumPot[k] = A.sumPot[cell];
+          sumConc[k] = A.sumConc[cell];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kBatch; k++) {
+        const int cell = cell0 + k * blockDim.x;
+        if (cell >= G.cells) break;
+        if (fromHits) A.count[cell] = count[k];
+        if (!A.conc) continue;
+        const double v = cellConcentration(G, cell, count[k]);
+        A.conc[cell] = v;
+        if (average) {
+          A.sumPot[cell] = __dadd_rn(sumPot[k], pot[k]);
+          A.sumConc[cell] = __dadd_rn(sumConc[k], v);
+        }
       }
     }
+  }
   if (A.closeStep == 1 && threadIdx.x == 0) {
     RunCtl &c = *A.ctl;
     if (A.counters)

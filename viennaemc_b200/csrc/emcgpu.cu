@@ -469,6 +469,10 @@ int emcgpu_set_option(emcgpu_ctx *ctx, const char *name, int64_t value) {
     ctx->optSorKernel = (int)value;
     return EMCGPU_OK;
   }
+  if (!strcmp(name, "assign_fp64")) {
+    ctx->optAssignFp64 = value != 0;
+    return EMCGPU_OK;
+  }
   if (!strcmp(name, "sor_order")) {
     if (value != 0 && value != 1) return fail(ctx, EMCGPU_E_INVALID, "sor_order must be 0 (lexicographic) or 1 (red-black)");
     ctx->optSorOrder = (int)value;

@@ -18,7 +18,7 @@ struct DeviceRunState {
   double charge = 0, nrCarriers = 1;
   DeviceBuffer dRegion, dFace, dDoping, dDopingNorm, dCellKind, dSorHistory;
   DeviceBuffer grid[EMCGPU_N_GRIDS];
-  DeviceBuffer dCtl, dFlag, dChunkCount, dListParticle, dListCell, dCellCount, dInjectCount, dSweeps, dReplay;
+  DeviceBuffer dCtl, dFlag, dChunkCount, dListParticle, dListCell, dCellCount, dInjectCount, dSweeps, dReplay, dHits;
   DeviceBuffer dCounters, dSweepsPerStep; // per-step outputs of a chunk of the step loop
   DeviceBuffer altEnsemble, altCursor, altGrain; // second ensemble buffer for the order-preserving compaction
   int64_t reserve = 0;
@@ -33,7 +33,7 @@ struct DeviceRunState {
 void releaseDeviceRun(emcgpu_ctx *ctx) {
   if (!ctx->run) return;
   DeviceRunState *r = ctx->run;
-  for (DeviceBuffer *b : {&r->dRegion, &r->dFace, &r->dDoping, &r->dDopingNorm, &r->dCellKind, &r->dSorHistory, &r->dCtl, &r->dFlag, &r->dChunkCount, &r->dListParticle,
+  for (DeviceBuffer *b : {&r->dRegion, &r->dFace, &r->dDoping, &r->dDopingNorm, &r->dCellKind, &r->dSorHistory, &r->dCtl, &r->dFlag, &r->dHits, &r->dChunkCount, &r->dListParticle,
                           &r->dListCell, &r->dCellCount, &r->dInjectCount, &r->dSweeps, &r->dReplay, &r->dCounters,
                           &r->dSweepsPerStep, &r->altEnsemble, &r->altCursor, &r->altGrain, &r->dShare})
     b->release();
@@ -343,7 +343,6 @@ int doAssign(emcgpu_ctx *ctx, bool withConc, bool closeStep) {
   DeviceRunState *r = ctx->run;
   const DevGeometry &G = r->geo;
   double *count = r->grid[EMCGPU_GRID_COUNT].as<double>();
-  CUDA_TRY(ctx, cudaMemsetAsync(count, 0, (size_t)G.cells * sizeof(double), ctx->stream));
   AssignParams A;
   A.x = ctx->dStream[EMCGPU_X];
   A.y = ctx->dStream[EMCGPU_Y];
@@ -362,13 +361,27 @@ int doAssign(emcgpu_ctx *ctx, bool withConc, bool closeStep) {
     A.conc = nullptr;
     A.closeStep = 0;
   }
-  const size_t smem = (size_t)G.cells * sizeof(double);
+  size_t smem = (size_t)G.cells * sizeof(double);
   A.useSmem = smem <= 96 * 1024 ? 1 : 0;
-  if (A.useSmem) CUDA_TRY(ctx, cudaFuncSetAttribute(ngpAssignKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // NEC / NEC-VWD deposits of an integer-valued nrCarriers: integer hits per mesh cell (share x hits is exact)
+  const bool necHits = (G.pmScheme == PM_NEC || G.pmScheme == PM_NEC_VWD) && r->nrCarriers == std::floor(r->nrCarriers) &&
+                       r->nrCarriers > 0 && r->nrCarriers < 16777216.0 && ctx->capacity < (int64_t(1) << 26) &&
+                       !ctx->optAssignFp64;
+  A.hits = nullptr;
+  if (necHits) {
+    A.useSmem = 2;
+    smem = 0;
+    CUDA_TRY(ctx, r->dHits.ensure((size_t)G.cells * sizeof(int32_t)));
+    A.hits = r->dHits.as<int32_t>();
+    CUDA_TRY(ctx, cudaMemsetAsync(A.hits, 0, (size_t)G.cells * sizeof(int32_t), ctx->stream));
+  } else {
+    CUDA_TRY(ctx, cudaMemsetAsync(count, 0, (size_t)G.cells * sizeof(double), ctx->stream));
+  }
+  if (A.useSmem == 1) CUDA_TRY(ctx, cudaFuncSetAttribute(ngpAssignKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (sharded && closeStep) { // the ensemble of this step is the survivors plus the injected particles
     A.closeStep = 2;
   }
-  ngpAssignKernel<<<particleGrid(ctx, kAssignThreads, 1), kAssignThreads, A.useSmem ? smem : 0, ctx->stream>>>(G, A);
+  ngpAssignKernel<<<particleGrid(ctx, kAssignThreads, 1), kAssignThreads, A.useSmem == 1 ? smem : 0, ctx->stream>>>(G, A);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   if (sharded) {
