@@ -102,8 +102,7 @@ __device__ __forceinline__ int posToLowerCell(const DevGeometry &g, const double
 // ---------------------------------------------------------------------------
 // Control block of the step loop, resident in device memory.  Everything the kernels of one EMC step hand to
 // each other (ensemble size, list sizes, step index, counters) lives here, so that the host never has to
-// wait for a kernel between the steps of a chunk and the per-step launch sequence is the same for every step
-// (it is captured once as a CUDA graph).
+// wait for a kernel between the steps of a chunk and the per-step launch sequence is the same for every step.
 struct RunCtl {
   int32_t n;          // live particles
   int32_t nKept;      // survivors of this step's compaction
