@@ -1113,6 +1113,9 @@ __global__ void __launch_bounds__(THREADS) sorRedBlackClusterFastKernel(const __
   __shared__ int sOver[kSorClusterSizeWide];
   const int tid = threadIdx.x;
   const int cta = (int)cluster.block_rank(), nCta = (int)cluster.num_blocks();
+  // the solver keeps 16 (8) SMs busy: a kernel behind it that was launched as a programmatic dependent (the particle step of
+  // emcgpu_device_run*) may take the other SMs now and do what does not depend on this solve; it waits for the end of this grid
+  asm volatile("griddepcontrol.launch_dependents;");
   if (S.ctl && S.ctl->runSteps % S.ctl->poissonInterval != 0) { // uniform over the cluster
     if (cta == 0 && tid == 0 && S.sweepsPerStep) S.sweepsPerStep[S.ctl->slot] = 0;
     return;
@@ -1468,6 +1471,9 @@ __global__ void __launch_bounds__(kBulkThreads, 2)
   __shared__ uint64_t tableBar;
   const BulkParams &P = D.P;
   const CtaState C = stageCta(P, smemRaw, &tableBar, 0, 0);
+  // launched as a programmatic dependent of the kernel ahead in the stream (emcgpu_device_run*): model and tables are staged,
+  // everything below reads what the earlier kernels of the step wrote -- wait for them (returns at once in a plain launch)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const DevModel &model = *C.model;
   using A = Arith<EXACT>;
   const int64_t n = D.ctl->n;

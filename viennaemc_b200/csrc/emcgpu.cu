@@ -397,6 +397,8 @@ int emcgpu_create(int cudaDevice, emcgpu_ctx **out) {
   ctx->smCount = prop.multiProcessorCount;
   if (const char *e = std::getenv("EMCGPU_SOR_KERNEL")) // developer switch for unmodified drivers: option sor_kernel
     ctx->optSorKernel = std::max(0, std::min(3, std::atoi(e)));
+  if (const char *e = std::getenv("EMCGPU_EARLY_STEP")) // developer switch: option early_step
+    ctx->optEarlyStep = std::atoi(e) != 0;
   ctx->maxSmemOptin = (int)prop.sharedMemPerBlockOptin;
   ctx->maxSmemPerSm = (int)prop.sharedMemPerMultiprocessor;
   if ((e = ctx->dStatus.ensure(sizeof(int))) != cudaSuccess ||
@@ -467,6 +469,10 @@ int emcgpu_set_option(emcgpu_ctx *ctx, const char *name, int64_t value) {
     if (value < 0 || value > 3)
       return fail(ctx, EMCGPU_E_INVALID, "sor_kernel must be 0 (default: rows / fastest cluster form), 1 (hyperplanes / one CTA), 2 (red-black: general cluster kernel) or 3 (red-black: fast form on the portable cluster of 8 CTAs)");
     ctx->optSorKernel = (int)value;
+    return EMCGPU_OK;
+  }
+  if (!strcmp(name, "early_step")) {
+    ctx->optEarlyStep = value != 0;
     return EMCGPU_OK;
   }
   if (!strcmp(name, "assign_fp64")) {

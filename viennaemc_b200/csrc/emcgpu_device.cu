@@ -411,12 +411,31 @@ int doConcentration(emcgpu_ctx *ctx) {
   return EMCGPU_OK;
 }
 
-template <bool EXACT, int MODE> cudaError_t launchStepDim(emcgpu_ctx *ctx, const DeviceStepParams &D, size_t smem, int grid) {
+// early: programmatic dependent launch -- the CTAs may become resident and stage model and tables while the kernel ahead in the
+// stream (the cluster solver, which releases its dependents at its start) still runs; the kernel waits for that kernel's end
+// (griddepcontrol.wait) before it touches anything a step produces
+template <bool EXACT, int MODE>
+cudaError_t launchStepDim(emcgpu_ctx *ctx, const DeviceStepParams &D, size_t smem, int grid, bool early) {
   const DevGeometry &G = ctx->run->geo;
   auto go = [&](auto kernel) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kernel<<<grid, kBulkThreads, smem, ctx->stream>>>(G, D);
+    if (early) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(kBulkThreads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = ctx->stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      e = cudaLaunchKernelEx(&cfg, kernel, G, D);
+      if (e != cudaSuccess) return e;
+    } else {
+      kernel<<<grid, kBulkThreads, smem, ctx->stream>>>(G, D);
+    }
     ctx->launches++;
     return cudaGetLastError();
   };
@@ -426,7 +445,7 @@ template <bool EXACT, int MODE> cudaError_t launchStepDim(emcgpu_ctx *ctx, const
 // particle step: ensemble in place, flags for the contact handling / compaction, removedPerContact in the control block
 // countReservoir: the step kernel also counts the reservoir particles per chunk (the contact handling that follows in the
 // same step then starts at its list kernel)
-int doStep(emcgpu_ctx *ctx, double dt, bool countReservoir = false) {
+int doStep(emcgpu_ctx *ctx, double dt, bool countReservoir = false, bool early = false) {
   DeviceRunState *r = ctx->run;
   DeviceStepParams D;
   fillParams(ctx, D.P);
@@ -448,9 +467,9 @@ int doStep(emcgpu_ctx *ctx, double dt, bool countReservoir = false) {
   const bool exact = ctx->mathMode == EMCGPU_MATH_EXACT;
   cudaError_t e;
   if (ctx->rngMode == RNG_PHILOX)
-    e = exact ? launchStepDim<true, RNG_PHILOX>(ctx, D, smem, grid) : launchStepDim<false, RNG_PHILOX>(ctx, D, smem, grid);
+    e = exact ? launchStepDim<true, RNG_PHILOX>(ctx, D, smem, grid, early) : launchStepDim<false, RNG_PHILOX>(ctx, D, smem, grid, early);
   else
-    e = exact ? launchStepDim<true, RNG_REPLAY>(ctx, D, smem, grid) : launchStepDim<false, RNG_REPLAY>(ctx, D, smem, grid);
+    e = exact ? launchStepDim<true, RNG_REPLAY>(ctx, D, smem, grid, early) : launchStepDim<false, RNG_REPLAY>(ctx, D, smem, grid, early);
   if (e != cudaSuccess) return fail(ctx, EMCGPU_E_CUDA, "device step launch failed: %s", cudaGetErrorString(e));
   return EMCGPU_OK;
 }
@@ -880,7 +899,7 @@ int emcgpu_device_run_averaging(emcgpu_ctx *ctx, double dt, int nSteps, int nAve
     for (int s = 0; s < chunk; s++) {
       // performEMCStep (emcSimulation.hpp:177-192)
       if (int rc = doPoisson(ctx, false, accuracyVolt, omega, resetBCFirst && done + s == 0, true, true)) return rc;
-      if (int rc = doStep(ctx, dt, true)) return rc;
+      if (int rc = doStep(ctx, dt, true, ctx->optEarlyStep != 0)) return rc;
       if (int rc = doContacts(ctx, true, nullptr, 0, true)) return rc;
       if (int rc = doAssign(ctx, true, true)) return rc;
     }

@@ -55,6 +55,7 @@ struct emcgpu_ctx {
   int optSplitPpl = 4;     // K1d flight kernel: particles per lane (2 or 4)
   int optTablesGlobal = 0; // 1 = leave the rate tables in global memory / L2 (more ring stages)
   int optSorKernel = 0;    // 0 = row-per-thread wavefront when it fits, 1 = hyperplane loop
+  int optEarlyStep = 1;    // device runs: the step kernel stages its tables while the Poisson solver ahead of it still runs
   int optAssignFp64 = 0;   // 1 = NEC / NEC-VWD deposits as fp64 atomics per corner instead of integer hits per mesh cell
   int optSorOrder = 0;     // 0 = the reference's lexicographic order (bit-identical iterates), 1 = red-black
   int optPoissonInterval = 1; // device run: solve Poisson every n-th step (emcSimulation::setPoissonInterval)
