@@ -264,6 +264,7 @@ struct AssignParams {
 
 constexpr int kAssignThreads = 1024; // the block that finishes last forms the concentration of the whole grid alone
 __global__ void __launch_bounds__(kAssignThreads) ngpAssignKernel(const __grid_constant__ DevGeometry G, const AssignParams A) {
+  asm volatile("griddepcontrol.launch_dependents;"); // the solver of the next step (chainedLaunch, emcgpu_device.cu)
   extern __shared__ double sCount[];
   const int64_t n = A.closeStep ? A.ctl->nKept + A.ctl->toInject : A.ctl->n;
   if (A.useSmem == 1) {
@@ -1116,6 +1117,7 @@ __global__ void __launch_bounds__(THREADS) sorRedBlackClusterFastKernel(const __
   // the solver keeps 16 (8) SMs busy: a kernel behind it that was launched as a programmatic dependent (the particle step of
   // emcgpu_device_run*) may take the other SMs now and do what does not depend on this solve; it waits for the end of this grid
   asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory"); // itself a programmatic dependent of the charge assignment of the last step
   if (S.ctl && S.ctl->runSteps % S.ctl->poissonInterval != 0) { // uniform over the cluster
     if (cta == 0 && tid == 0 && S.sweepsPerStep) S.sweepsPerStep[S.ctl->slot] = 0;
     return;
@@ -1467,6 +1469,7 @@ __device__ __forceinline__ Vec3 pmForce(const DevGeometry &G, const double *e, c
 template <bool EXACT, int RNG_MODE, int DIM>
 __global__ void __launch_bounds__(kBulkThreads, 2)
     deviceStepKernel(const __grid_constant__ DevGeometry G, const __grid_constant__ DeviceStepParams D) {
+  asm volatile("griddepcontrol.launch_dependents;"); // the reservoir list kernel behind it (chainedLaunch, emcgpu_device.cu)
   extern __shared__ __align__(16) unsigned char smemRaw[];
   __shared__ uint64_t tableBar;
   const BulkParams &P = D.P;
@@ -1590,6 +1593,8 @@ template <int WHAT> __device__ __forceinline__ bool selected(int32_t flag) {
 
 template <int WHAT>
 __global__ void __launch_bounds__(kChunk) selectCountKernel(const int32_t *flag, RunCtl *ctl, int32_t *chunkCount) {
+  asm volatile("griddepcontrol.launch_dependents;"); // see chainedLaunch (emcgpu_device.cu): no-ops in a plain launch
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   __shared__ int sWarp[kChunk / 32];
   const int64_t n = ctl->n;
   const int nChunks = (int)((n + kChunk - 1) / kChunk);
@@ -1619,6 +1624,8 @@ __global__ void __launch_bounds__(kChunk) selectCountKernel(const int32_t *flag,
 __global__ void __launch_bounds__(kChunk)
     reservoirListKernel(const int32_t *flag, const RunCtl *ctl, const int32_t *chunkOffset, int32_t *listParticle,
                         int32_t *listCell) {
+  asm volatile("griddepcontrol.launch_dependents;"); // see chainedLaunch (emcgpu_device.cu): no-ops in a plain launch
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   __shared__ int sWarp[kChunk / 32];
   const int64_t n = ctl->n;
   const int nChunks = (int)((n + kChunk - 1) / kChunk);
@@ -1725,6 +1732,8 @@ constexpr int kRankThreads = 1024;
 
 __global__ void __launch_bounds__(kRankThreads) contactRankKernel(const __grid_constant__ DevGeometry G, const ContactParams K,
                                                                    const int countersInSmem) {
+  asm volatile("griddepcontrol.launch_dependents;"); // see chainedLaunch (emcgpu_device.cu): no-ops in a plain launch
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   extern __shared__ int sCellCount[];
   __shared__ int sGroupCell[kRankThreads], sGroupSize[kRankThreads], sGroupBefore[kRankThreads];
   int *cnt = countersInSmem ? sCellCount : K.cellCount;
@@ -1910,6 +1919,8 @@ template <int DIM>
 __global__ void __launch_bounds__(kChunk)
     compactInjectKernel(const __grid_constant__ DevGeometry G, const __grid_constant__ InjectParams J, const int32_t *flag,
                         const int32_t *chunkOffset, const __grid_constant__ EnsemblePtrs src, int compactBlocks) {
+  asm volatile("griddepcontrol.launch_dependents;"); // see chainedLaunch (emcgpu_device.cu): no-ops in a plain launch
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if ((int)blockIdx.x < compactBlocks)
     compactScatterRole(flag, J.ctl, chunkOffset, src, J.ens, (int)blockIdx.x, compactBlocks);
   else

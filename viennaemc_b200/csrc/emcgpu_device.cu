@@ -19,6 +19,7 @@ struct DeviceRunState {
   DeviceBuffer dRegion, dFace, dDoping, dDopingNorm, dCellKind, dSorHistory;
   DeviceBuffer grid[EMCGPU_N_GRIDS];
   DeviceBuffer dCtl, dFlag, dChunkCount, dListParticle, dListCell, dCellCount, dInjectCount, dSweeps, dReplay, dHits;
+  bool chained = false; // inside emcgpu_device_run* on one GPU: kernels of a step are launched as programmatic dependents (chainedLaunch)
   DeviceBuffer dCounters, dSweepsPerStep; // per-step outputs of a chunk of the step loop
   DeviceBuffer altEnsemble, altCursor, altGrain; // second ensemble buffer for the order-preserving compaction
   int64_t reserve = 0;
@@ -194,6 +195,26 @@ int pullCtl(emcgpu_ctx *ctx, RunCtl *out = nullptr) {
   return EMCGPU_OK;
 }
 
+// Launch on the context's stream; inside the step loop of a run (DeviceRunState::chained) as a PROGRAMMATIC DEPENDENT of the kernel
+// ahead of it in the stream: every kernel of the chain releases its dependents first thing (griddepcontrol.launch_dependents) and
+// waits for the end of its predecessor before it touches global memory (griddepcontrol.wait), so the CTAs of the next kernel are
+// resident -- the step kernel even with its tables staged -- when the predecessor ends, instead of paying a launch after it.
+template <typename... P, typename... A>
+cudaError_t chainedLaunch(emcgpu_ctx *ctx, void (*kernel)(P...), int grid, int block, size_t smem, A &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  const bool chained = ctx->run && ctx->run->chained;
+  cfg.attrs = chained ? attr : nullptr;
+  cfg.numAttrs = chained ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<A>(args)...);
+}
+
 int particleGrid(emcgpu_ctx *ctx, int threads, int perSm) {
   return (int)std::max<int64_t>(1, std::min<int64_t>((ctx->capacity + threads - 1) / threads, (int64_t)perSm * ctx->smCount));
 }
@@ -262,13 +283,15 @@ int doPoisson(emcgpu_ctx *ctx, bool equilibrium, double accuracyVolt, double ome
       cfg.blockDim = dim3(threads);
       cfg.dynamicSmemBytes = bytes;
       cfg.stream = ctx->stream;
-      cudaLaunchAttribute attr[1];
+      cudaLaunchAttribute attr[2];
       attr[0].id = cudaLaunchAttributeClusterDimension;
       attr[0].val.clusterDim.x = clusterSize;
       attr[0].val.clusterDim.y = 1;
       attr[0].val.clusterDim.z = 1;
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; // behind the charge assignment of the last step
+      attr[1].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = attr;
-      cfg.numAttrs = 1;
+      cfg.numAttrs = !probeOnly && inLoop && r->chained ? 2 : 1;
       if (probeOnly) {
         int nClusters = 0;
         e = cudaOccupancyMaxActiveClusters(&nClusters, kernel, &cfg);
@@ -482,7 +505,7 @@ int doCompaction(emcgpu_ctx *ctx, InjectParams *inject = nullptr) {
   const int32_t *flag = r->dFlag.as<const int32_t>();
   int32_t *chunkCount = r->dChunkCount.as<int32_t>();
   const int grid = particleGrid(ctx, kChunk, 8);
-  selectCountKernel<SELECT_KEPT><<<grid, kChunk, 0, ctx->stream>>>(flag, ctl, chunkCount);
+  CUDA_TRY(ctx, chainedLaunch(ctx, selectCountKernel<SELECT_KEPT>, grid, kChunk, 0, flag, ctl, chunkCount));
   const bool replay = ctx->rngMode == RNG_REPLAY;
   if (replay) CUDA_TRY(ctx, r->altCursor.ensure((size_t)ctx->capacity * sizeof(uint32_t)));
   const bool grain = ctx->grainOn;
@@ -494,9 +517,9 @@ int doCompaction(emcgpu_ctx *ctx, InjectParams *inject = nullptr) {
     const int injectGrid = 4; // a few hundred particles per step at most; grid-stride
     inject->ens = dst;
     if (r->dim == 2)
-      compactInjectKernel<2><<<grid + injectGrid, kChunk, 0, ctx->stream>>>(r->geo, *inject, flag, chunkCount, src, grid);
+      CUDA_TRY(ctx, chainedLaunch(ctx, compactInjectKernel<2>, grid + injectGrid, kChunk, 0, r->geo, *inject, flag, (const int32_t *)chunkCount, src, grid));
     else
-      compactInjectKernel<3><<<grid + injectGrid, kChunk, 0, ctx->stream>>>(r->geo, *inject, flag, chunkCount, src, grid);
+      CUDA_TRY(ctx, chainedLaunch(ctx, compactInjectKernel<3>, grid + injectGrid, kChunk, 0, r->geo, *inject, flag, (const int32_t *)chunkCount, src, grid));
   } else {
     compactScatterKernel<<<grid, kChunk, 0, ctx->stream>>>(flag, ctl, chunkCount, src, dst);
   }
@@ -526,8 +549,8 @@ int doContacts(emcgpu_ctx *ctx, bool fromStep, const uint64_t *replayDraws, int6
     ctx->launches++;
   }
   if (!countedByStep) selectCountKernel<SELECT_RESERVOIR><<<grid, kChunk, 0, ctx->stream>>>(flag, ctl, chunkCount);
-  reservoirListKernel<<<grid, kChunk, 0, ctx->stream>>>(flag, ctl, chunkCount, r->dListParticle.as<int32_t>(),
-                                                        r->dListCell.as<int32_t>());
+  CUDA_TRY(ctx, chainedLaunch(ctx, reservoirListKernel, grid, kChunk, 0, (const int32_t *)flag, (const RunCtl *)ctl, (const int32_t *)chunkCount,
+                              r->dListParticle.as<int32_t>(), r->dListCell.as<int32_t>()));
   ContactParams K;
   K.nrCarriers = r->nrCarriers;
   K.expected = r->grid[EMCGPU_GRID_EXPECTED].as<const double>();
@@ -553,7 +576,7 @@ int doContacts(emcgpu_ctx *ctx, bool fromStep, const uint64_t *replayDraws, int6
     const size_t counterBytes = (size_t)G.cells * sizeof(int);
     const int inSmem = counterBytes <= (size_t)ctx->maxSmemOptin - 20480 ? 1 : 0;
     if (inSmem) CUDA_TRY(ctx, cudaFuncSetAttribute(contactRankKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)counterBytes));
-    contactRankKernel<<<1, kRankThreads, inSmem ? counterBytes : 0, ctx->stream>>>(G, K, inSmem);
+    CUDA_TRY(ctx, chainedLaunch(ctx, contactRankKernel, 1, kRankThreads, inSmem ? counterBytes : 0, G, K, inSmem));
   }
   ctx->launches += 3;
   CUDA_TRY(ctx, cudaGetLastError());
@@ -896,13 +919,15 @@ int emcgpu_device_run_averaging(emcgpu_ctx *ctx, double dt, int nSteps, int nAve
       if (int rc = growEnsemble(ctx, std::max<int64_t>(want + want / 8, r->reserve))) return rc;
     const int chunk = (int)std::min<int64_t>(std::min(kRunChunk, nSteps - done), std::max<int64_t>(1, (ctx->capacity - ctx->n) / perStep));
     if (int rc = pushCtl(ctx, std::max(0, (nSteps - nAverage) - done))) return rc;
+    r->chained = ctx->optEarlyStep != 0 && r->world == 1;
     for (int s = 0; s < chunk; s++) {
       // performEMCStep (emcSimulation.hpp:177-192)
       if (int rc = doPoisson(ctx, false, accuracyVolt, omega, resetBCFirst && done + s == 0, true, true)) return rc;
-      if (int rc = doStep(ctx, dt, true, ctx->optEarlyStep != 0)) return rc;
+      if (int rc = doStep(ctx, dt, true, r->chained)) return rc;
       if (int rc = doContacts(ctx, true, nullptr, 0, true)) return rc;
       if (int rc = doAssign(ctx, true, true)) return rc;
     }
+    r->chained = false;
     if (counters)
       CUDA_TRY(ctx, cudaMemcpyAsync(hCounters.data(), r->dCounters.ptr, (size_t)chunk * 2 * nC * sizeof(int32_t),
                                     cudaMemcpyDeviceToHost, ctx->stream));
