@@ -211,9 +211,9 @@ int emcgpu_synchronize(emcgpu_ctx *ctx);
  * the same potential within the solver's accuracy); "sor_kernel" = 1 forces the general hyperplane
  * form of the lexicographic solver / the one-CTA form of the red-black solver, 2 the general cluster kernel of the
  * red-black solver, 3 its fast 2-D form on the portable cluster of 8 CTAs (default 0: the fastest form the grid and the
- * device allow -- red-black: 16 CTAs of 512 threads; no effect on results); "early_step" = 0: the particle step of
- * emcgpu_device_run* as a plain launch (default 1: programmatic dependent launch behind the Poisson solver -- model and tables
- * are staged while the solver still runs; same results); "assign_fp64" = 1: NEC / NEC-VWD charge
+ * device allow -- red-black: 16 CTAs of 512 threads; no effect on results); "early_step" = 0: the kernels of a step of
+ * emcgpu_device_run* as plain launches (default 1: a chain of programmatic dependent launches -- the next kernel's CTAs are
+ * resident, the particle step's tables staged, while the predecessor still runs; same results); "assign_fp64" = 1: NEC / NEC-VWD charge
  * assignment with one fp64 atomic per corner instead of integer hits per mesh cell (same sums, slower); "multi_kernel": kernel of emcgpu_bulk_step*
  * with stepsPerLaunch > 1 -- 0 (default): for ensembles that fill the GPU the flight + event kernel pair (up to 24 steps
  * per launch pair; FAST arithmetic, one non-parabolic valley with signed-permutation rotations) or else the deferred-event
